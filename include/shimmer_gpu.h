@@ -1,0 +1,286 @@
+/*
+ * shimmer_gpu.h -- C ABI of the B200 wavefront path-tracing backend for shimmer.
+ *
+ * The reference (jalberse/shimmer) has NO FFI today: no `extern`, no build.rs,
+ * no -sys crate (Cargo.toml:14-39).  This header therefore *defines* the
+ * boundary that a `render::render_gpu` sibling of `render_cpu`
+ * (src/render.rs:8-55) binds.  Every entry point below names the reference
+ * interface it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative SgStatus otherwise; they
+ *     never unwind, abort or call exit() (the reference panics instead:
+ *     integrator.rs:36, aggregate.rs:27 -- the Rust side turns !=0 into panic!)
+ *   - sg_last_error() returns a thread-local, NUL-terminated description
+ *   - the host owns every input array; the library only borrows it for the
+ *     duration of sg_scene_create (it is copied to HBM once)
+ *   - all floats are IEEE f32 (`Float = f32`, src/float.rs:1-4); the film is f64
+ *     (`RgbFilmPixel`, src/film.rs:470-479)
+ *   - one process drives one GPU (sg_init selects it); multi-GPU runs one
+ *     process per GPU and reduces the film with NCCL (see DESIGN.md section e)
+ */
+#ifndef SHIMMER_GPU_H
+#define SHIMMER_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+typedef enum SgStatus {
+    SG_OK = 0,
+    SG_ERR_INVALID_ARGUMENT = -1,
+    SG_ERR_CUDA = -2,
+    SG_ERR_OUT_OF_MEMORY = -3,
+    SG_ERR_UNSUPPORTED = -4,
+    SG_ERR_NOT_INITIALIZED = -5
+} SgStatus;
+
+/* ---- acceleration structure ------------------------------------------------
+ * Flattened `LinearBvhNode` (src/aggregate.rs:471-481): depth-first order, the
+ * first child of an interior node is `index+1`, the second is `offset`.
+ * `usize` fields are narrowed to u32 (range-checked by the host shim), which
+ * packs the reference's 64-byte node into 32 bytes. */
+typedef struct SgBvhNode {
+    float    bmin[3];
+    float    bmax[3];
+    uint32_t offset;   /* leaf: primitive_offset; interior: second_child_offset */
+    uint16_t n_prims;  /* >0 => leaf */
+    uint8_t  axis;     /* interior: split axis 0/1/2 */
+    uint8_t  pad;
+} SgBvhNode;
+
+/* One entry per `Primitive::{Simple,Geometric}` in BVH leaf order
+ * (`ordered_primitives`, src/aggregate.rs:236-266; src/primitive.rs:30-35). */
+typedef struct SgPrimitive {
+    uint32_t mesh;      /* index into SgSceneDesc.meshes                        */
+    uint32_t tri;       /* Triangle::tri_index within that mesh (triangle.rs:49) */
+    uint32_t material;  /* index into materials                                  */
+    int32_t  light;     /* area light index into lights, or -1 (SimplePrimitive) */
+} SgPrimitive;
+
+/* `TriangleMesh` (src/shape/mesh.rs:9-20); vertices already in render space
+ * (mesh.rs:43-46).  Attribute arrays are scene-global; a mesh addresses
+ * [first_vertex, first_vertex+n_vertices) and indices
+ * [first_index, first_index+3*n_triangles) hold MESH-LOCAL vertex numbers. */
+enum {
+    SG_MESH_HAS_N = 1, SG_MESH_HAS_UV = 2, SG_MESH_HAS_S = 4,
+    SG_MESH_REVERSE_ORIENTATION = 8, SG_MESH_SWAPS_HANDEDNESS = 16
+};
+typedef struct SgMesh {
+    uint32_t first_index;
+    uint32_t first_vertex;
+    uint32_t n_triangles;
+    uint32_t n_vertices;
+    uint32_t flags;
+    uint32_t pad[3];
+} SgMesh;
+
+/* ---- spectra ---------------------------------------------------------------
+ * `Spectrum` enum (src/spectra/spectrum.rs:39-48).  Data lives in one float
+ * pool. */
+typedef enum SgSpectrumKind {
+    SG_SPECTRUM_CONSTANT = 0,        /* ConstantSpectrum, spectrum.rs:146-168: c        */
+    SG_SPECTRUM_DENSE = 1,           /* DenselySampledSpectrum, :171-292: pool[off_a..+n], lambda_min */
+    SG_SPECTRUM_PIECEWISE_LINEAR = 2,/* PiecewiseLinearSpectrum, :295-440: lambdas at off_a, values at off_b, n */
+    SG_SPECTRUM_BLACKBODY = 3        /* BlackbodySpectrum, :443-495: c = T, scale = normalization_factor */
+} SgSpectrumKind;
+typedef struct SgSpectrum {
+    int32_t  kind;
+    int32_t  n;
+    int32_t  lambda_min;
+    float    c;
+    float    scale;
+    uint32_t off_a;
+    uint32_t off_b;
+    uint32_t pad;
+} SgSpectrum;
+
+/* ---- materials (src/material.rs) -------------------------------------------
+ * Textures on this path are the reference's `*ConstantTexture`s
+ * (texture.rs), i.e. a spectrum id or a float. */
+typedef enum SgMaterialKind {
+    SG_MATERIAL_DIFFUSE = 0,    /* DiffuseMaterial    material.rs:298-338  spec_a = reflectance          */
+    SG_MATERIAL_CONDUCTOR = 1,  /* ConductorMaterial  material.rs:453-526  spec_a = eta, spec_b = k      */
+    SG_MATERIAL_DIELECTRIC = 2  /* DielectricMaterial material.rs:600-662  spec_a = eta (`Spectrum`)     */
+} SgMaterialKind;
+enum {
+    SG_MAT_REMAP_ROUGHNESS = 1,  /* `remaproughness`, default true                      */
+    SG_MAT_HAS_DISPLACEMENT = 2  /* material stores Some(displacement) -> bump_map runs
+                                    (always true for Diffuse: material.rs:280)           */
+};
+typedef struct SgMaterial {
+    int32_t kind;
+    int32_t spec_a;
+    int32_t spec_b;
+    int32_t flags;
+    float   u_roughness;
+    float   v_roughness;
+    float   displacement;  /* constant displacement texture value (0 by default) */
+    float   pad;
+} SgMaterial;
+
+/* ---- lights (src/light.rs) ------------------------------------------------- */
+typedef enum SgLightKind {
+    SG_LIGHT_DIFFUSE_AREA = 0,     /* DiffuseAreaLight light.rs:524-694 over one Triangle */
+    SG_LIGHT_POINT = 1,            /* PointLight light.rs:403-519                         */
+    SG_LIGHT_UNIFORM_INFINITE = 2  /* UniformInfiniteLight light.rs:697-803               */
+} SgLightKind;
+typedef struct SgLight {
+    int32_t kind;
+    int32_t spectrum;     /* dense 360..830 table: l_emit / i                              */
+    float   scale;        /* already divided by spectrum_to_photometric (light.rs:583)     */
+    int32_t two_sided;
+    uint32_t mesh, tri;   /* area: the Triangle the light samples (scene.rs:609-622)       */
+    float   area;         /* Shape::area() cached at construction (light.rs:546)           */
+    float   pos[3];       /* point: render_from_light(0,0,0)                               */
+    float   scene_center[3];
+    float   scene_radius; /* infinite: preprocess() result (light.rs:797-802)              */
+    float   pad[2];
+} SgLight;
+
+/* ---- camera (src/camera.rs:830-1114 PerspectiveCamera) --------------------- */
+typedef struct SgCamera {
+    float camera_from_raster[16];     /* row-major 4x4, ProjectiveCameraBase camera.rs:632 */
+    float render_from_camera[16];     /* CameraTransform camera.rs:518                     */
+    float camera_from_render[16];     /* its inverse (Transform::m_inv)                     */
+    float dx_camera[3];
+    float dy_camera[3];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+    float min_pos_differential_x[3], min_pos_differential_y[3];
+    float min_dir_differential_x[3], min_dir_differential_y[3];
+} SgCamera;
+
+/* ---- film (src/film.rs RgbFilm + PixelSensor) ------------------------------ */
+typedef struct SgFilm {
+    int32_t full_resolution[2];
+    int32_t pixel_bounds[4];      /* min.x, min.y, max.x, max.y (max exclusive)            */
+    float   filter_radius[2];     /* BoxFilter radius, filter.rs:64-106                    */
+    int32_t r_bar, g_bar, b_bar;  /* dense spectra ids, PixelSensor film.rs:754-765         */
+    float   imaging_ratio;
+    float   max_component_value;  /* RgbFilm::max_component_value (film.rs:462), +inf default */
+    float   output_rgb_from_sensor_rgb[9]; /* used only by sg_film_develop                  */
+} SgFilm;
+
+typedef struct SgSceneDesc {
+    uint32_t abi_version;         /* SG_ABI_VERSION */
+    uint32_t n_nodes;      const SgBvhNode*   nodes;
+    uint32_t n_primitives; const SgPrimitive* primitives;
+    uint32_t n_meshes;     const SgMesh*      meshes;
+    uint32_t n_indices;    const uint32_t*    indices;     /* 3 per triangle               */
+    uint32_t n_vertices;   const float*       p;           /* xyz per vertex               */
+                           const float*       n;           /* xyz per vertex or NULL       */
+                           const float*       uv;          /* uv per vertex or NULL        */
+                           const float*       s;           /* xyz per vertex or NULL       */
+    uint32_t n_spectra;    const SgSpectrum*  spectra;
+    uint32_t n_pool;       const float*       spectrum_pool;
+    uint32_t n_materials;  const SgMaterial*  materials;
+    uint32_t n_lights;     const SgLight*     lights;      /* order = light sampler order  */
+    SgCamera camera;
+    SgFilm   film;
+} SgSceneDesc;
+
+/* ---- render parameters: Options (options.rs:15-36), sampler (sampler.rs:95-99),
+ *      integrator parameters (integrator.rs:188-192) ----------------------------- */
+enum {
+    SG_OPT_DISABLE_PIXEL_JITTER = 1,
+    SG_OPT_DISABLE_WAVELENGTH_JITTER = 2,
+    SG_OPT_DISABLE_TEXTURE_FILTERING = 4,
+    SG_OPT_FORCE_DIFFUSE = 8
+};
+typedef struct SgRenderParams {
+    uint64_t seed;              /* IndependentSampler seed                                  */
+    int32_t  samples_per_pixel; /* `pixelsamples`: used for ray-differential scale          */
+    int32_t  sample_begin;      /* this call renders sample indices [begin, end) of every   */
+    int32_t  sample_end;        /*   pixel: the multi-GPU split (DESIGN.md section e)       */
+    int32_t  max_depth;         /* `maxdepth`, default 5                                    */
+    int32_t  regularize;        /* `regularize`, default false                              */
+    uint32_t option_flags;      /* SG_OPT_*                                                 */
+    int32_t  max_paths_in_flight; /* wavefront width; 0 = library default                   */
+    int32_t  reserved;
+} SgRenderParams;
+
+/* `RgbFilmPixel` without the (unused on this path) splat: film.rs:470-479. */
+typedef struct SgFilmPixel {
+    double rgb_sum[3];
+    double weight_sum;
+} SgFilmPixel;
+
+typedef struct SgStats {
+    uint64_t camera_paths;
+    uint64_t closest_hit_rays;
+    uint64_t shadow_rays;
+    uint64_t nodes_visited;     /* bounds tests, counted in reference traversal order      */
+    uint64_t tris_tested;       /* intersect_triangle entries                              */
+    uint64_t kernel_launches;
+    double   render_ms;         /* device time of the wavefront loop                       */
+    double   trace_ms;          /* device time inside closest-hit + any-hit kernels        */
+} SgStats;
+
+/* `ShapeIntersection` reduced to what parity needs (shape.rs:221-225 +
+ * TriangleIntersection triangle.rs:748-755 + geometric normal triangle.rs:407-412). */
+typedef struct SgHit {
+    int32_t prim;     /* index into SgSceneDesc.primitives, -1 = miss */
+    float   t;
+    float   b0, b1, b2;
+    float   ng[3];
+} SgHit;
+
+typedef struct SgScene SgScene;
+
+/* Selects the CUDA device of this process and creates the library's stream. */
+int sg_init(int device);
+int sg_shutdown(void);
+const char* sg_last_error(void);
+int sg_abi_version(void);
+
+/* Replaces the object graph `render_cpu` builds before `integrator.render`
+ * (render.rs:33-52): flattens nothing itself, uploads the host-flattened scene. */
+int sg_scene_create(const SgSceneDesc* desc, SgScene** out);
+int sg_scene_destroy(SgScene* scene);
+
+/* Replaces `ImageTileIntegrator::render` (integrator.rs:227-321) for the `path`
+ * integrator: evaluates samples [sample_begin,sample_end) of every pixel and
+ * ADDS them into `film` (row-major (y-y0)*W+(x-x0), vec2d.rs:24-28).
+ * sg_render: `film` is host memory (copied back inside the call).
+ * sg_render_device: `film` is device memory of this process's GPU, zeroed by
+ * the caller; `stream` is a cudaStream_t (NULL = library stream). */
+int sg_render(SgScene* scene, const SgRenderParams* params, SgFilmPixel* film, SgStats* stats);
+int sg_render_device(SgScene* scene, const SgRenderParams* params, void* d_film, SgStats* stats, void* stream);
+
+/* Replaces `BvhAggregate::intersect` / `intersect_predicate`
+ * (aggregate.rs:71-203) for a batch of rays: the ray-cast parity entry.
+ * o,d: xyz per ray; any_hit!=0 -> predicate (out[i].prim is 0 on hit, -1 on miss). */
+int sg_trace(SgScene* scene, int64_t n, const float* o, const float* d, const float* t_max,
+             int any_hit, SgHit* out, SgStats* stats);
+/* Same with every buffer in device memory (bench: inputs resident in HBM). */
+int sg_trace_device(SgScene* scene, int64_t n, const void* d_o, const void* d_d, const void* d_t_max,
+                    int any_hit, void* d_out, SgStats* stats, void* stream);
+
+/* Replaces `IndependentSampler::get_1d` (sampler.rs:123-125) over the stream
+ * assigned to (pixel_index, sample_index): RNG known-answer entry.
+ * raw!=0 -> seed the generator with `seed` directly (SmallRng::seed_from_u64). */
+int sg_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sample_index,
+                    int64_t n, float* out);
+
+/* Replaces `evaluate_pixel_sample`'s camera stage (integrator.rs:339-362):
+ * wavelengths + camera ray for n (pixel,sample) pairs; out_rays: o.xyz d.xyz per
+ * sample, out_lambda: 4 lambdas + 4 pdfs per sample. */
+int sg_camera_rays(SgScene* scene, const SgRenderParams* params, int64_t n,
+                   const int32_t* pixel_xy, const int32_t* sample_index,
+                   float* out_rays, float* out_lambda);
+
+/* Replaces `RgbFilm::get_pixel_rgb` (film.rs:720-738): rgb_sum/weight_sum then
+ * output_rgb_from_sensor_rgb; out: 3 floats per pixel. */
+int sg_film_develop(SgScene* scene, const SgFilmPixel* film, int64_t n_pixels, float* out_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHIMMER_GPU_H */

@@ -1,0 +1,319 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.h header).  parity status: see orc_math.h.
+// Geometry layer of the CPU restatement: bounds, watertight triangle test, BVH build +
+// traversal, surface interaction construction.  Consumes the same flattened
+// SgSceneDesc the C ABI takes (include/shimmer_gpu.h).
+#pragma once
+#include "orc_math.h"
+#include "../include/shimmer_gpu.h"
+#include <vector>
+
+namespace orc {
+
+struct Ray { V3 o, d; };
+
+struct Counters { uint64_t nodes = 0, tris = 0, closest = 0, shadow = 0; };
+
+// bounding_box.rs:520-564
+inline bool bounds_intersect_p_cached(const SgBvhNode& b, V3 o, Float ray_t_max, V3 inv_dir, const int dir_is_neg[3]) {
+    const Float* lohi[2] = {b.bmin, b.bmax};
+    const Float k = 1.0f + 2.0f * gamma_n(3);
+    Float t_min = (lohi[dir_is_neg[0]][0] - o.x) * inv_dir.x;
+    Float t_max = (lohi[1 - dir_is_neg[0]][0] - o.x) * inv_dir.x;
+    Float ty_min = (lohi[dir_is_neg[1]][1] - o.y) * inv_dir.y;
+    Float ty_max = (lohi[1 - dir_is_neg[1]][1] - o.y) * inv_dir.y;
+    t_max *= k;
+    ty_max *= k;
+    if (t_min > ty_max || ty_min > t_max) return false;
+    if (ty_min > t_min) t_min = ty_min;
+    if (ty_max < t_max) t_max = ty_max;
+    Float tz_min = (lohi[dir_is_neg[2]][2] - o.z) * inv_dir.z;
+    Float tz_max = (lohi[1 - dir_is_neg[2]][2] - o.z) * inv_dir.z;
+    tz_max *= k;
+    if (t_min > tz_max || tz_min > t_max) return false;
+    if (tz_min > t_min) t_min = tz_min;
+    if (tz_max < t_max) t_max = tz_max;
+    return t_min < ray_t_max && t_max > 0.0f;
+}
+
+struct TriHit { Float b0, b1, b2, t; };
+
+// triangle.rs:173-302
+inline bool intersect_triangle(const Ray& ray, Float t_max, V3 p0, V3 p1, V3 p2, TriHit* out) {
+    if (length_squared(cross(p2 - p0, p1 - p0)) == 0.0f) return false;
+    V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
+    int kz = max_component_index(vabs(ray.d));
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    V3 d = permute(ray.d, kx, ky, kz);
+    p0t = permute(p0t, kx, ky, kz);
+    p1t = permute(p1t, kx, ky, kz);
+    p2t = permute(p2t, kx, ky, kz);
+    Float sx = -d.x / d.z, sy = -d.y / d.z, sz = 1.0f / d.z;
+    p0t.x += sx * p0t.z; p0t.y += sy * p0t.z;
+    p1t.x += sx * p1t.z; p1t.y += sy * p1t.z;
+    p2t.x += sx * p2t.z; p2t.y += sy * p2t.z;
+    Float e0 = difference_of_products(p1t.x, p2t.y, p1t.y, p2t.x);
+    Float e1 = difference_of_products(p2t.x, p0t.y, p2t.y, p0t.x);
+    Float e2 = difference_of_products(p0t.x, p1t.y, p0t.y, p1t.x);
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {             // :232-242 double fallback
+        double p2txp1ty = (double)p2t.x * (double)p1t.y;
+        double p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (Float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y;
+        double p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (Float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y;
+        double p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (Float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+    Float det = e0 + e1 + e2;
+    if (det == 0.0f) return false;
+    p0t.z *= sz; p1t.z *= sz; p2t.z *= sz;
+    Float t_scaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0.0f && (t_scaled >= 0.0f || t_scaled < t_max * det)) return false;
+    else if (det > 0.0f && (t_scaled <= 0.0f || t_scaled > t_max * det)) return false;
+    Float inv_det = 1.0f / det;
+    Float b0 = e0 * inv_det, b1 = e1 * inv_det, b2 = e2 * inv_det;
+    Float t = t_scaled * inv_det;
+    Float max_zt = max_component_value(vabs(v3(p0t.z, p1t.z, p2t.z)));
+    Float delta_z = gamma_n(3) * max_zt;
+    Float max_xt = max_component_value(vabs(v3(p0t.x, p1t.x, p2t.x)));
+    Float max_yt = max_component_value(vabs(v3(p0t.y, p1t.y, p2t.y)));
+    Float delta_x = gamma_n(5) * (max_xt + max_zt);
+    Float delta_y = gamma_n(5) * (max_yt + max_zt);
+    Float delta_e = 2.0f * (gamma_n(2) * max_xt * max_yt + delta_y * max_xt + delta_x * max_yt);
+    Float max_e = max_component_value(vabs(v3(e0, e1, e2)));
+    Float delta_t = 3.0f * (gamma_n(3) * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * std::fabs(inv_det);
+    if (t <= delta_t) return false;
+    out->b0 = b0; out->b1 = b1; out->b2 = b2; out->t = t;
+    return true;
+}
+
+// Read-only view over the flattened scene.
+struct Scene {
+    const SgSceneDesc* d;
+    explicit Scene(const SgSceneDesc* desc) : d(desc) {}
+    inline V3 vertex(const SgMesh& m, uint32_t local) const {
+        const float* q = d->p + 3 * (size_t)(m.first_vertex + local);
+        return v3(q[0], q[1], q[2]);
+    }
+    inline V3 normal(const SgMesh& m, uint32_t local) const {
+        const float* q = d->n + 3 * (size_t)(m.first_vertex + local);
+        return v3(q[0], q[1], q[2]);
+    }
+    inline V2 uv(const SgMesh& m, uint32_t local) const {
+        const float* q = d->uv + 2 * (size_t)(m.first_vertex + local);
+        V2 r = {q[0], q[1]}; return r;
+    }
+    inline void tri_indices(uint32_t mesh, uint32_t tri, uint32_t v[3]) const {
+        const SgMesh& m = d->meshes[mesh];
+        const uint32_t* ix = d->indices + m.first_index + 3 * (size_t)tri;
+        v[0] = ix[0]; v[1] = ix[1]; v[2] = ix[2];
+    }
+    inline void tri_points(uint32_t mesh, uint32_t tri, V3* p0, V3* p1, V3* p2) const {   // triangle.rs:148-159
+        uint32_t v[3]; tri_indices(mesh, tri, v);
+        const SgMesh& m = d->meshes[mesh];
+        *p0 = vertex(m, v[0]); *p1 = vertex(m, v[1]); *p2 = vertex(m, v[2]);
+    }
+};
+
+struct Hit { int32_t prim; TriHit th; };
+
+// aggregate.rs:71-139 (any_hit = false) and :141-203 (any_hit = true).
+// The reference builds the full SurfaceInteraction for every accepted candidate
+// (triangle.rs:529-535); only the last one survives, so it is built once by the caller.
+inline bool bvh_intersect(const Scene& sc, const Ray& ray, Float t_max, bool any_hit, Hit* hit, Counters* ctr) {
+    const SgSceneDesc* D = sc.d;
+    hit->prim = -1;
+    if (D->n_nodes == 0) return false;
+    V3 inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+    int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
+    uint32_t to_visit = 0, cur = 0;
+    uint32_t stack[64];
+    bool found = false;
+    for (;;) {
+        const SgBvhNode& node = D->nodes[cur];
+        if (ctr) ctr->nodes++;
+        if (bounds_intersect_p_cached(node, ray.o, t_max, inv_dir, dir_is_neg)) {
+            if (node.n_prims > 0) {
+                for (uint32_t i = 0; i < node.n_prims; ++i) {
+                    uint32_t pi = node.offset + i;
+                    const SgPrimitive& pr = D->primitives[pi];
+                    V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);
+                    TriHit th;
+                    if (ctr) ctr->tris++;
+                    if (intersect_triangle(ray, t_max, p0, p1, p2, &th)) {
+                        if (any_hit) { hit->prim = (int32_t)pi; hit->th = th; return true; }
+                        t_max = th.t; hit->prim = (int32_t)pi; hit->th = th; found = true;
+                    }
+                }
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            } else {
+                if (dir_is_neg[node.axis]) { stack[to_visit++] = cur + 1; cur = node.offset; }
+                else { stack[to_visit++] = node.offset; cur = cur + 1; }
+            }
+        } else {
+            if (to_visit == 0) break;
+            cur = stack[--to_visit];
+        }
+    }
+    return found;
+}
+
+// ---- BVH build: aggregate.rs:207-468 ----------------------------------------
+struct BuildPrim { uint32_t index; float bmin[3], bmax[3]; };
+inline Float centroid_axis(const BuildPrim& p, int a) { return 0.5f * p.bmin[a] + p.bmax[a] * 0.5f; }  // aggregate.rs:490-492
+
+struct BvhBuilder {
+    std::vector<SgBvhNode> nodes;
+    std::vector<uint32_t> order;
+    // Iterative restatement of build_recursive + flatten_bvh: depth-first emission gives
+    // the same linear order as flatten_bvh (:425-467) because the tree is emitted
+    // node, left subtree, right subtree.
+    uint32_t build(BuildPrim* prims, size_t n) {
+        uint32_t my = (uint32_t)nodes.size();
+        nodes.push_back(SgBvhNode());
+        float bmin[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+        float bmax[3] = {std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest()};
+        for (size_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {       // :320-324 Bounds3::union via f32::min/max
+            bmin[a] = fmin_(bmin[a], prims[i].bmin[a]);
+            bmax[a] = fmax_(bmax[a], prims[i].bmax[a]);
+        }
+        Float dx = bmax[0] - bmin[0], dy = bmax[1] - bmin[1], dz = bmax[2] - bmin[2];
+        Float sa = 2.0f * (dx * dy + dx * dz + dy * dz);                    // bounding_box.rs:394-397
+        auto make_leaf = [&]() {
+            SgBvhNode nd; std::memset(&nd, 0, sizeof nd);
+            for (int a = 0; a < 3; ++a) { nd.bmin[a] = bmin[a]; nd.bmax[a] = bmax[a]; }
+            nd.offset = (uint32_t)order.size(); nd.n_prims = (uint16_t)n; nd.axis = 0;
+            for (size_t i = 0; i < n; ++i) order.push_back(prims[i].index);
+            nodes[my] = nd;
+        };
+        if (sa == 0.0f || n == 1) { make_leaf(); return my; }              // :326-337
+        float cmin[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+        float cmax[3] = {std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest()};
+        for (size_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {
+            Float c = centroid_axis(prims[i], a);
+            cmin[a] = fmin_(cmin[a], c); cmax[a] = fmax_(cmax[a], c);
+        }
+        Float ex = cmax[0] - cmin[0], ey = cmax[1] - cmin[1], ez = cmax[2] - cmin[2];
+        int dim = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);            // bounding_box.rs:404-415
+        if (cmax[dim] == cmin[dim]) { make_leaf(); return my; }            // :345-355
+        Float pmid = (cmin[dim] + cmax[dim]) / 2.0f;                       // :360
+        // itertools::partition (two-pointer swap partition), :361-364
+        size_t split = 0;
+        {
+            size_t front = 0, back = n;
+            for (;;) {
+                if (front == back) break;
+                if (!(centroid_axis(prims[front], dim) < pmid)) {
+                    bool swapped = false;
+                    while (back > front + 1) {
+                        --back;
+                        if (centroid_axis(prims[back], dim) < pmid) { std::swap(prims[front], prims[back]); swapped = true; break; }
+                    }
+                    if (!swapped) break;
+                }
+                ++front; ++split;
+            }
+        }
+        if (split == 0 || split == n) {                                     // :366-374 pdqselect fallback
+            split = n / 2;
+            std::nth_element(prims, prims + split, prims + n, [dim](const BuildPrim& a, const BuildPrim& b) {
+                return centroid_axis(a, dim) < centroid_axis(b, dim);
+            });
+        }
+        build(prims, split);
+        uint32_t second = build(prims + split, n - split);
+        SgBvhNode nd; std::memset(&nd, 0, sizeof nd);
+        const SgBvhNode& l = nodes[my + 1]; const SgBvhNode& r = nodes[second];   // init_interior :540-545
+        for (int a = 0; a < 3; ++a) { nd.bmin[a] = fmin_(l.bmin[a], r.bmin[a]); nd.bmax[a] = fmax_(l.bmax[a], r.bmax[a]); }
+        nd.offset = second; nd.n_prims = 0; nd.axis = (uint8_t)dim;
+        nodes[my] = nd;
+        return my;
+    }
+};
+
+// ---- surface interaction -----------------------------------------------------
+struct SurfaceInteraction {
+    P3fi pi; V3 wo; V3 n; V2 uv;
+    V3 dpdu, dpdv;
+    V3 sn, sdpdu, sdpdv;     // shading.n / shading.dpdu / shading.dpdv
+    int32_t material, light;
+    inline V3 p() const { return p3fi_mid(pi); }
+};
+
+// triangle.rs:305-504.  dndu/dndv and the screen-space differentials are not restated:
+// with the constant textures of this path they are only ever multiplied by a zero
+// displacement (material.rs:1500-1507) or feed auxiliary rays that nothing reads
+// (SURVEY.md 8a row a12).
+inline SurfaceInteraction interaction_from_intersection(const Scene& sc, uint32_t mesh_id, uint32_t tri, const TriHit& ti, V3 wo) {
+    const SgMesh& m = sc.d->meshes[mesh_id];
+    uint32_t v[3]; sc.tri_indices(mesh_id, tri, v);
+    V3 p0 = sc.vertex(m, v[0]), p1 = sc.vertex(m, v[1]), p2 = sc.vertex(m, v[2]);
+    V2 uv[3];
+    if (!(m.flags & SG_MESH_HAS_UV)) { uv[0] = {0.0f, 0.0f}; uv[1] = {1.0f, 0.0f}; uv[2] = {1.0f, 1.0f}; }
+    else { uv[0] = sc.uv(m, v[0]); uv[1] = sc.uv(m, v[1]); uv[2] = sc.uv(m, v[2]); }
+    V2 duv02 = {uv[0].x - uv[2].x, uv[0].y - uv[2].y}, duv12 = {uv[1].x - uv[2].x, uv[1].y - uv[2].y};
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    Float determinant = difference_of_products(duv02.x, duv12.y, duv02.y, duv12.x);
+    bool degenerate_uv = std::fabs(determinant) < 1e-9f;
+    V3 dpdu = v3(0, 0, 0), dpdv = v3(0, 0, 0);
+    if (!degenerate_uv) {
+        Float inv_det = 1.0f / determinant;
+        // difference_of_products_float_vec, math.rs:214-219 (unfused)
+        auto dopv = [](Float a, V3 b, Float c, V3 d) { V3 cd = c * d; V3 diff = a * b - cd; V3 err = (-c) * d + cd; return diff + err; };
+        dpdu = dopv(duv12.y, dp02, duv02.y, dp12) * inv_det;
+        dpdv = dopv(duv02.x, dp12, duv12.x, dp02) * inv_det;
+    }
+    if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f) {
+        V3 ng = cross(p2 - p0, p1 - p0);
+        if (length_squared(ng) == 0.0f) {
+            V3 v1 = p2 - p0, v2 = p1 - p0;
+            ng = v3((Float)difference_of_products_d(v1.y, v2.z, v1.z, v2.y),
+                    (Float)difference_of_products_d(v1.z, v2.x, v1.x, v2.z),
+                    (Float)difference_of_products_d(v1.x, v2.y, v1.y, v2.x));
+        }
+        coordinate_system(normalize(ng), &dpdu, &dpdv);
+    }
+    V3 p_hit = ti.b0 * p0 + ti.b1 * p1 + ti.b2 * p2;
+    V2 uv_hit = {ti.b0 * uv[0].x + ti.b1 * uv[1].x + ti.b2 * uv[2].x, ti.b0 * uv[0].y + ti.b1 * uv[1].y + ti.b2 * uv[2].y};
+    bool flip = ((m.flags & SG_MESH_REVERSE_ORIENTATION) != 0) ^ ((m.flags & SG_MESH_SWAPS_HANDEDNESS) != 0);
+    V3 p_abs_sum = vabs(ti.b0 * p0) + vabs(ti.b1 * p1) + vabs(ti.b2 * p2);
+    V3 p_error = gamma_n(7) * p_abs_sum;
+    SurfaceInteraction si;
+    si.pi = p3fi_from_value_and_error(p_hit, p_error);
+    si.uv = uv_hit; si.wo = wo; si.dpdu = dpdu; si.dpdv = dpdv;
+    si.sdpdu = dpdu; si.sdpdv = dpdv;
+    si.n = normalize(cross(dp02, dp12));                                  // :407-412
+    if (flip) si.n = -si.n;
+    si.sn = si.n;
+    si.material = -1; si.light = -1;
+    if (m.flags & (SG_MESH_HAS_N | SG_MESH_HAS_S)) {                      // :414-501
+        V3 ns;
+        if (!(m.flags & SG_MESH_HAS_N)) ns = si.n;
+        else {
+            V3 nn = ti.b0 * sc.normal(m, v[0]) + ti.b1 * sc.normal(m, v[1]) + ti.b2 * sc.normal(m, v[2]);
+            ns = length_squared(nn) > 0.0f ? normalize(nn) : si.n;
+        }
+        V3 ss = si.dpdu;
+        if (m.flags & SG_MESH_HAS_S) {
+            const float* S = sc.d->s;
+            auto sv = [&](uint32_t l) { const float* q = S + 3 * (size_t)(m.first_vertex + l); return v3(q[0], q[1], q[2]); };
+            V3 s = ti.b0 * sv(v[0]) + ti.b1 * sv(v[1]) + ti.b2 * sv(v[2]);
+            if (length_squared(s) != 0.0f) ss = s;
+        }
+        V3 ts = cross(ns, ss);
+        if (length_squared(ts) > 0.0f) ss = cross(ts, ns);
+        else coordinate_system(ns, &ss, &ts);
+        // set_shading_geometry(ns, ss, ts, .., orientation_is_authoritative = true) interaction.rs:379-405
+        si.sn = ns;
+        si.n = face_forward(si.n, si.sn);
+        si.sdpdu = ss; si.sdpdv = ts;
+        while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
+    }
+    return si;
+}
+
+}  // namespace orc

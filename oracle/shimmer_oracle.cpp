@@ -1,0 +1,415 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// CPU restatement of jalberse/shimmer's `path` integrator hot path
+// (ImageTileIntegrator::render -> evaluate_pixel_sample -> PathIntegrator::li -> sample_ld
+//  -> RgbFilm::add_sample; integrator.rs:227-396,748-963, film.rs:548-574).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
+// legs may load liborc; the product library never does.
+//
+// PARITY STATUS: "pinned against the reference's own unit-test vectors" for the arithmetic
+// that has any (tests/test_oracle_kat.py lists them with file:line); the reference binary
+// itself cannot be built in this image, and rand::SmallRng / num-complex are
+// restated from their published algorithms => those two are "parity unpinned".
+#include "orc_shading.h"
+#include <atomic>
+#include <thread>
+#include <chrono>
+#include <vector>
+#include <cstdio>
+
+using namespace orc;
+
+namespace {
+
+struct PathCounters { Counters c; };
+
+// Ray::spawn_ray_to_both_offset ray.rs:83-99 via Interaction::spawn_ray_to_interaction interaction.rs:81-85
+inline Ray spawn_ray_to_both_offset(const P3fi& p_from, V3 n_from, const P3fi& p_to, V3 n_to) {
+    V3 pf = offset_ray_origin(p_from, n_from, p3fi_mid(p_to) - p3fi_mid(p_from));
+    V3 pt = offset_ray_origin(p_to, n_to, pf - p3fi_mid(p_to));
+    Ray r; r.o = pf; r.d = pt - pf; return r;
+}
+
+struct PathCtx {
+    const Scene* sc;
+    const SgRenderParams* rp;
+    Counters* ctr;
+};
+
+// PathIntegrator::sample_ld integrator.rs:897-963
+static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, const BSDF& bsdf, const Wavelengths& lambda, Rng& rng) {
+    const SgSceneDesc* D = pc.sc->d;
+    LightSampleContext ctx; ctx.pi = intr.pi; ctx.n = intr.n; ctx.ns = intr.sn;
+    int flags = bsdf.flags();
+    bool refl = flags & BX_REFLECTION, trans = flags & BX_TRANSMISSION;
+    if (refl && !trans) ctx.pi = p3fi_exact(offset_ray_origin(intr.pi, intr.n, intr.wo));
+    else if (trans && !refl) ctx.pi = p3fi_exact(offset_ray_origin(intr.pi, intr.n, -intr.wo));
+    Float u = rng.get_1d();
+    V2 u_light; u_light.x = rng.get_1d(); u_light.y = rng.get_1d();
+    if (D->n_lights == 0) return spec_const(0.0f);
+    // UniformLightSampler::sample_light light_sampler.rs:91-103 (`as usize` saturates)
+    Float fl = u * (Float)D->n_lights;
+    uint32_t li = fl != fl ? 0u : (fl <= 0.0f ? 0u : (fl >= 4294967296.0f ? 0xffffffffu : (uint32_t)fl));
+    if (li > D->n_lights - 1) li = D->n_lights - 1;
+    Float p_choose = 1.0f / (Float)D->n_lights;
+    const SgLight& lt = D->lights[li];
+    LightLiSample ls;
+    if (!light_sample_li(*pc.sc, lt, ctx, u_light, lambda, &ls)) return spec_const(0.0f);
+    if (spec_is_zero(ls.l) || ls.pdf == 0.0f) return spec_const(0.0f);
+    V3 wo = intr.wo, wi = ls.wi;
+    Spec f = bsdf.f(wo, wi) * abs_dot(wi, intr.sn);
+    if (spec_is_zero(f)) return spec_const(0.0f);
+    Ray sray = spawn_ray_to_both_offset(intr.pi, intr.n, ls.p_light, ls.n_light);   // IntegratorBase::unoccluded :114-116
+    Hit h;
+    if (pc.ctr) pc.ctr->shadow++;
+    if (bvh_intersect(*pc.sc, sray, 1.0f - 0.0001f, true, &h, pc.ctr)) return spec_const(0.0f);
+    Float p_l = p_choose * ls.pdf;
+    if (lt.kind == SG_LIGHT_POINT) return ls.l * f / p_l;
+    Float p_b = bsdf.pdf(wo, wi);
+    Float w_l = power_heuristic(p_l, p_b);
+    return w_l * ls.l * f / p_l;
+}
+
+// PathIntegrator::li integrator.rs:748-895
+static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
+    const SgSceneDesc* D = pc.sc->d;
+    Spec L = spec_const(0.0f), beta = spec_const(1.0f);
+    int depth = 0;
+    Float p_b = 1.0f, eta_scale = 1.0f;
+    bool specular_bounce = false, any_non_specular_bounces = false;
+    LightSampleContext prev_ctx; prev_ctx.pi = p3fi_exact(v3(0, 0, 0)); prev_ctx.n = v3(0, 0, 0); prev_ctx.ns = v3(0, 0, 0);
+    for (;;) {
+        Hit hit;
+        if (pc.ctr) pc.ctr->closest++;
+        bool found = bvh_intersect(*pc.sc, ray, F_INF, false, &hit, pc.ctr);
+        if (!found) {
+            for (uint32_t i = 0; i < D->n_lights; ++i) {                          // :779-792
+                const SgLight& lt = D->lights[i];
+                if (lt.kind != SG_LIGHT_UNIFORM_INFINITE) continue;
+                Spec le = lt.scale * spectrum_sample(D, lt.spectrum, lambda);     // light.rs:792-794
+                if (depth == 0 || specular_bounce) L = L + beta * le;
+                else {
+                    Float p_l = (1.0f / (Float)D->n_lights) * light_pdf_li(*pc.sc, lt, prev_ctx, ray.d);
+                    Float w_b = power_heuristic(p_b, p_l);
+                    L = L + beta * w_b * le;
+                }
+            }
+            break;
+        }
+        const SgPrimitive& prim = D->primitives[hit.prim];
+        SurfaceInteraction si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -ray.d);
+        si.material = (int32_t)prim.material; si.light = prim.light;
+        if (si.light >= 0) {                                                       // :798-813
+            const SgLight& lt = D->lights[si.light];
+            Spec le = light_l(D, lt, si.n, -ray.d, lambda);
+            if (!spec_is_zero(le)) {
+                if (depth == 0 || specular_bounce) L = L + beta * le;
+                else {
+                    Float p_l = (1.0f / (Float)D->n_lights) * light_pdf_li(*pc.sc, lt, prev_ctx, ray.d);
+                    Float w_l = power_heuristic(p_b, p_l);
+                    L = L + beta * w_l * le;
+                }
+            }
+        }
+        BSDF bsdf = get_bsdf(D, si, lambda);                                      // :816
+        if (pc.rp->regularize && any_non_specular_bounces) bsdf.mf.regularize();  // :825-828
+        if (depth == pc.rp->max_depth) break;
+        depth += 1;
+        if (bsdf.flags() & (BX_DIFFUSE | BX_GLOSSY)) {                            // :837-841
+            Spec ld = sample_ld(pc, si, bsdf, lambda, rng);
+            L = L + beta * ld;
+        }
+        V3 wo = -ray.d;
+        Float u = rng.get_1d();
+        V2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+        BSDFSample bs;
+        if (!bsdf.sample_f(wo, u, u2, &bs)) break;
+        beta = beta * (bs.f * abs_dot(bs.wi, si.sn) / bs.pdf);                    // :859
+        p_b = bs.pdf;
+        specular_bounce = (bs.flags & BX_SPECULAR) != 0;
+        any_non_specular_bounces |= !specular_bounce;
+        if (bs.flags & BX_TRANSMISSION) eta_scale *= sqr(bs.eta);
+        prev_ctx.pi = si.pi; prev_ctx.n = si.n; prev_ctx.ns = si.sn;
+        ray.o = offset_ray_origin(si.pi, si.n, bs.wi); ray.d = bs.wi;             // spawn_ray interaction.rs:72-79
+        if (std::isfinite(eta_scale)) {                                           // :878-891
+            Spec rr_beta = beta * eta_scale;
+            if (spec_max(rr_beta) < 1.0f && depth > 1) {
+                Float q = fmax_(0.0f, 1.0f - spec_max(rr_beta));
+                if (rng.get_1d() < q) break;
+                beta = beta / (1.0f - q);
+            }
+        }
+    }
+    return L;
+}
+
+// evaluate_pixel_sample integrator.rs:326-396 + get_camera_sample sampling.rs:347-371 + BoxFilter::sample filter.rs:99-105
+static void camera_stage(const SgSceneDesc* D, const SgRenderParams* rp, int px, int py, Rng& rng, Wavelengths* lambda, Ray* ray, Float* weight) {
+    Float lu = (rp->option_flags & SG_OPT_DISABLE_WAVELENGTH_JITTER) ? 0.5f : rng.get_1d();
+    *lambda = sample_visible(lu);
+    V2 pu; pu.x = rng.get_1d(); pu.y = rng.get_1d();                  // get_pixel_2d, always consumed
+    CameraSample cs;
+    if (rp->option_flags & SG_OPT_DISABLE_PIXEL_JITTER) {
+        cs.p_film.x = (Float)px + 0.5f; cs.p_film.y = (Float)py + 0.5f;
+        cs.p_lens.x = 0.5f; cs.p_lens.y = 0.5f; cs.time = 0.5f; cs.filter_weight = 1.0f;
+    } else {
+        Float rx = D->film.filter_radius[0], ry = D->film.filter_radius[1];
+        V2 fp = {lerp(pu.x, -rx, rx), lerp(pu.y, -ry, ry)};          // BoxFilter::sample
+        cs.p_film.x = (Float)px + fp.x + 0.5f; cs.p_film.y = (Float)py + fp.y + 0.5f;
+        cs.p_lens.x = rng.get_1d(); cs.p_lens.y = rng.get_1d();
+        cs.time = rng.get_1d();
+        cs.filter_weight = 1.0f;
+    }
+    *ray = camera_generate_ray(D->camera, cs);
+    *weight = cs.filter_weight;
+}
+
+static void eval_sample(const PathCtx& pc, int px, int py, Rng& rng, SgFilmPixel* film) {
+    const SgSceneDesc* D = pc.sc->d;
+    Wavelengths lambda; Ray ray; Float weight;
+    camera_stage(D, pc.rp, px, py, rng, &lambda, &ray, &weight);
+    Spec L = path_li(pc, ray, lambda, rng);          // camera_ray.weight == 1 (camera.rs:997-1000)
+    int W = D->film.pixel_bounds[2] - D->film.pixel_bounds[0];
+    SgFilmPixel* pxl = film + (size_t)(py - D->film.pixel_bounds[1]) * W + (px - D->film.pixel_bounds[0]);
+    film_add_sample(D, pxl, L, lambda, weight);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_header(void) {
+    return "shimmer oracle: CPU restatement, TEST INFRASTRUCTURE ONLY; pinned against the reference's unit-test "
+           "vectors; rand::SmallRng and num-complex restated from published algorithms (parity unpinned)";
+}
+
+void orc_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sample_index, int64_t n, float* out) {
+    Rng r; r.seed_from_u64(raw ? seed : stream_key(seed, pixel_index, sample_index));
+    for (int64_t i = 0; i < n; ++i) out[i] = r.get_1d();
+}
+void orc_rng_u64(uint64_t seed, int from_state, const uint64_t* state, int64_t n, uint64_t* out, uint64_t* state_out) {
+    Rng r;
+    if (from_state) for (int i = 0; i < 4; ++i) r.s[i] = state[i]; else r.seed_from_u64(seed);
+    if (state_out) for (int i = 0; i < 4; ++i) state_out[i] = r.s[i];
+    for (int64_t i = 0; i < n; ++i) out[i] = r.next_u64();
+}
+
+// aggregate.rs:207-468.  prim_bounds: 6 floats (min xyz, max xyz) per primitive in input order.
+// out_nodes must hold 2*n-1 nodes, out_order n entries.  Returns node count.
+int64_t orc_bvh_build(int64_t n, const float* prim_bounds, SgBvhNode* out_nodes, uint32_t* out_order) {
+    std::vector<BuildPrim> prims((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        prims[i].index = (uint32_t)i;
+        for (int a = 0; a < 3; ++a) { prims[i].bmin[a] = prim_bounds[6 * i + a]; prims[i].bmax[a] = prim_bounds[6 * i + 3 + a]; }
+    }
+    BvhBuilder b; b.nodes.reserve((size_t)(2 * n)); b.order.reserve((size_t)n);
+    if (n > 0) b.build(prims.data(), (size_t)n);
+    std::memcpy(out_nodes, b.nodes.data(), b.nodes.size() * sizeof(SgBvhNode));
+    std::memcpy(out_order, b.order.data(), b.order.size() * sizeof(uint32_t));
+    return (int64_t)b.nodes.size();
+}
+
+void orc_trace(const SgSceneDesc* desc, int64_t n, const float* o, const float* d, const float* t_max, int any_hit,
+               SgHit* out, SgStats* stats, int n_threads) {
+    Scene sc(desc);
+    if (n_threads < 1) n_threads = 1;
+    std::vector<Counters> ctrs((size_t)n_threads);
+    auto work = [&](int tid) {
+        Counters& c = ctrs[tid];
+        for (int64_t i = tid; i < n; i += n_threads) {
+            Ray r; r.o = v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+            Hit h;
+            bool found = bvh_intersect(sc, r, t_max[i], any_hit != 0, &h, &c);
+            SgHit& oh = out[i];
+            std::memset(&oh, 0, sizeof oh);
+            if (!found) { oh.prim = -1; continue; }
+            if (any_hit) { oh.prim = 0; continue; }
+            oh.prim = h.prim; oh.t = h.th.t; oh.b0 = h.th.b0; oh.b1 = h.th.b1; oh.b2 = h.th.b2;
+            const SgPrimitive& pr = desc->primitives[h.prim];
+            SurfaceInteraction si = interaction_from_intersection(sc, pr.mesh, pr.tri, h.th, -r.d);
+            // geometric normal as produced by triangle.rs:407-412 (before any shading-normal face-forwarding)
+            V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);
+            V3 ng = normalize(cross(p0 - p2, p1 - p2));
+            const SgMesh& m = desc->meshes[pr.mesh];
+            if (((m.flags & SG_MESH_REVERSE_ORIENTATION) != 0) ^ ((m.flags & SG_MESH_SWAPS_HANDEDNESS) != 0)) ng = -ng;
+            (void)si;
+            oh.ng[0] = ng.x; oh.ng[1] = ng.y; oh.ng[2] = ng.z;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (auto& c : ctrs) { stats->nodes_visited += c.nodes; stats->tris_tested += c.tris; }
+        if (any_hit) stats->shadow_rays = (uint64_t)n; else stats->closest_hit_rays = (uint64_t)n;
+    }
+}
+
+void orc_camera_rays(const SgSceneDesc* desc, const SgRenderParams* rp, int64_t n, const int32_t* pixel_xy,
+                     const int32_t* sample_index, float* out_rays, float* out_lambda) {
+    for (int64_t i = 0; i < n; ++i) {
+        int px = pixel_xy[2 * i], py = pixel_xy[2 * i + 1];
+        Rng rng; rng.seed_from_u64(stream_key(rp->seed, (uint32_t)(py * desc->film.full_resolution[0] + px), (uint32_t)sample_index[i]));
+        Wavelengths lam; Ray ray; Float w;
+        camera_stage(desc, rp, px, py, rng, &lam, &ray, &w);
+        float* r = out_rays + 6 * i;
+        r[0] = ray.o.x; r[1] = ray.o.y; r[2] = ray.o.z; r[3] = ray.d.x; r[4] = ray.d.y; r[5] = ray.d.z;
+        for (int k = 0; k < 4; ++k) { out_lambda[8 * i + k] = lam.lambda[k]; out_lambda[8 * i + 4 + k] = lam.pdf[k]; }
+    }
+}
+
+// ImageTileIntegrator::render integrator.rs:227-321.
+// stream_mode 0: deterministic (pixel,sample) streams (shared with the CUDA path).
+// stream_mode 1: the reference's behaviour -- one generator per worker thread, cloned from the
+//                same seed, consumed in tile-scheduling order (integrator.rs:252-263).
+// film is ADDED to (caller zeroes it).  Returns seconds spent in the tile loop.
+double orc_render(const SgSceneDesc* desc, const SgRenderParams* rp, SgFilmPixel* film, SgStats* stats,
+                  int n_threads, int stream_mode) {
+    Scene sc(desc);
+    if (n_threads < 1) n_threads = 1;
+    const int x0 = desc->film.pixel_bounds[0], y0 = desc->film.pixel_bounds[1];
+    const int x1 = desc->film.pixel_bounds[2], y1 = desc->film.pixel_bounds[3];
+    // Tile::tile(bounds, 8, 8) tile.rs:21-104: row-major tiles, remainders kept
+    struct TileB { int x0, y0, x1, y1; };
+    std::vector<TileB> tiles;
+    for (int ty = y0; ty < y1; ty += 8) for (int tx = x0; tx < x1; tx += 8)
+        tiles.push_back({tx, ty, std::min(tx + 8, x1), std::min(ty + 8, y1)});
+    std::vector<Counters> ctrs((size_t)n_threads);
+    std::vector<Rng> thread_rng((size_t)n_threads);
+    for (auto& r : thread_rng) r.seed_from_u64(rp->seed);
+    auto t_begin = std::chrono::steady_clock::now();
+    // waves 1,1,2,4,...,64 (:231-233,306-308), restricted to [sample_begin, sample_end)
+    int wave_start = 0, wave_end = 1, next_wave = 1;
+    const int spp_hi = rp->sample_end;
+    while (wave_start < spp_hi) {
+        int ws = std::max(wave_start, rp->sample_begin), we = std::min(wave_end, spp_hi);
+        if (ws < we) {
+            std::atomic<size_t> next_tile(0);
+            auto work = [&](int tid) {
+                PathCtx pc; pc.sc = &sc; pc.rp = rp; pc.ctr = &ctrs[tid];
+                for (;;) {
+                    size_t ti = next_tile.fetch_add(1);
+                    if (ti >= tiles.size()) break;
+                    const TileB& t = tiles[ti];
+                    for (int x = t.x0; x < t.x1; ++x) for (int y = t.y0; y < t.y1; ++y)       // x outer, y inner :257-258
+                        for (int s = ws; s < we; ++s) {
+                            if (stream_mode == 0) {
+                                Rng rng; rng.seed_from_u64(stream_key(rp->seed, (uint32_t)(y * desc->film.full_resolution[0] + x), (uint32_t)s));
+                                eval_sample(pc, x, y, rng, film);
+                            } else {
+                                eval_sample(pc, x, y, thread_rng[tid], film);
+                            }
+                        }
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto& t : th) t.join();
+        }
+        wave_start = wave_end;
+        wave_end = std::min(spp_hi, wave_end + next_wave);
+        next_wave = std::min(2 * next_wave, 64);
+    }
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (auto& c : ctrs) { stats->nodes_visited += c.nodes; stats->tris_tested += c.tris; stats->closest_hit_rays += c.closest; stats->shadow_rays += c.shadow; }
+        stats->camera_paths = (uint64_t)(x1 - x0) * (uint64_t)(y1 - y0) * (uint64_t)std::max(0, rp->sample_end - rp->sample_begin);
+        stats->render_ms = secs * 1e3;
+    }
+    return secs;
+}
+
+// RgbFilm::get_pixel_rgb film.rs:720-738 (splat term is zero on this path)
+void orc_film_develop(const SgSceneDesc* desc, const SgFilmPixel* film, int64_t n, float* out_rgb) {
+    const float* M = desc->film.output_rgb_from_sensor_rgb;
+    for (int64_t i = 0; i < n; ++i) {
+        Float rgb[3] = {(Float)film[i].rgb_sum[0], (Float)film[i].rgb_sum[1], (Float)film[i].rgb_sum[2]};
+        if (film[i].weight_sum != 0.0) for (int c = 0; c < 3; ++c) rgb[c] /= (Float)film[i].weight_sum;
+        for (int r = 0; r < 3; ++r) out_rgb[3 * i + r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+    }
+}
+
+// ---- known-answer entry points (tests/test_oracle_kat.py) --------------------------
+float orc_difference_of_products(float a, float b, float c, float d) { return difference_of_products(a, b, c, d); }
+float orc_lerp(float t, float a, float b) { return lerp(t, a, b); }
+float orc_next_float_up(float v) { return next_float_up(v); }
+float orc_next_float_down(float v) { return next_float_down(v); }
+float orc_gamma(int n) { return gamma_n(n); }
+float orc_visible_wavelengths_pdf(float l) { return visible_wavelengths_pdf(l); }
+float orc_sample_visible_wavelengths(float u) { return sample_visible_wavelengths(u); }
+float orc_tr_d(float ax, float ay, const float* wm) { return TR::make(ax, ay).d(v3(wm[0], wm[1], wm[2])); }
+float orc_tr_g(float ax, float ay, const float* wo, const float* wi) { return TR::make(ax, ay).g(v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2])); }
+float orc_fresnel_dielectric(float c, float eta) { return fresnel_dielectric(c, eta); }
+float orc_fresnel_complex(float c, float eta, float k) { return fresnel_complex(c, cx(eta, k)); }
+float orc_blackbody(float lambda, float t) { return blackbody(lambda, t); }
+float orc_spectrum_get(const SgSceneDesc* d, int id, float lambda) { return spectrum_get(d, id, lambda); }
+void orc_spectrum_sample(const SgSceneDesc* d, int id, const float* lambda4, float* out4) {
+    Wavelengths w; for (int i = 0; i < 4; ++i) { w.lambda[i] = lambda4[i]; w.pdf[i] = 1.0f; }
+    Spec s = spectrum_sample(d, id, w); for (int i = 0; i < 4; ++i) out4[i] = s.v[i];
+}
+// dielectric BxDF::sample_f in local space: out = f[4], wi[3], pdf, flags, eta ; returns 0 if None
+int orc_dielectric_sample_f(float eta, float ax, float ay, const float* wo, float uc, const float* u2, float* out) {
+    BSDF b; b.kind = SG_MATERIAL_DIELECTRIC; b.eta = eta; b.mf = TR::make(ax, ay); b.r = spec_const(0); b.k = spec_const(0);
+    BSDFSample bs; V2 u = {u2[0], u2[1]};
+    if (!b.sample_local(v3(wo[0], wo[1], wo[2]), uc, u, &bs)) return 0;
+    for (int i = 0; i < 4; ++i) out[i] = bs.f.v[i];
+    out[4] = bs.wi.x; out[5] = bs.wi.y; out[6] = bs.wi.z; out[7] = bs.pdf; out[8] = (float)bs.flags; out[9] = bs.eta;
+    return 1;
+}
+// generic local-space BxDF evaluation: kind, params(r[4],k[4],eta,ax,ay) ; out f[4], pdf
+void orc_bxdf_eval(int kind, const float* prm, const float* wo, const float* wi, float* out) {
+    BSDF b; b.kind = kind;
+    for (int i = 0; i < 4; ++i) { b.r.v[i] = prm[i]; b.k.v[i] = prm[4 + i]; }
+    b.eta = prm[8]; b.mf = TR::make(prm[9], prm[10]);
+    Spec f = b.f_local(v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]));
+    for (int i = 0; i < 4; ++i) out[i] = f.v[i];
+    out[4] = b.pdf_local(v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]));
+}
+int orc_bxdf_sample(int kind, const float* prm, const float* wo, float uc, const float* u2, float* out) {
+    BSDF b; b.kind = kind;
+    for (int i = 0; i < 4; ++i) { b.r.v[i] = prm[i]; b.k.v[i] = prm[4 + i]; }
+    b.eta = prm[8]; b.mf = TR::make(prm[9], prm[10]);
+    BSDFSample bs; V2 u = {u2[0], u2[1]};
+    if (!b.sample_local(v3(wo[0], wo[1], wo[2]), uc, u, &bs)) return 0;
+    for (int i = 0; i < 4; ++i) out[i] = bs.f.v[i];
+    out[4] = bs.wi.x; out[5] = bs.wi.y; out[6] = bs.wi.z; out[7] = bs.pdf; out[8] = (float)bs.flags; out[9] = bs.eta;
+    return 1;
+}
+// Triangle::sample / sample_with_context on a free-standing triangle (triangle.rs:773-848 tests)
+int orc_tri_intersect(const float* o, const float* d, float t_max, const float* p, float* out4) {
+    Ray r; r.o = v3(o[0], o[1], o[2]); r.d = v3(d[0], d[1], d[2]);
+    TriHit th;
+    if (!intersect_triangle(r, t_max, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(p[6], p[7], p[8]), &th)) return 0;
+    out4[0] = th.b0; out4[1] = th.b1; out4[2] = th.b2; out4[3] = th.t; return 1;
+}
+int orc_bounds_intersect(const float* bmin, const float* bmax, const float* o, const float* d, float t_max) {
+    SgBvhNode n; std::memset(&n, 0, sizeof n);
+    for (int a = 0; a < 3; ++a) { n.bmin[a] = bmin[a]; n.bmax[a] = bmax[a]; }
+    V3 inv = v3(1.0f / d[0], 1.0f / d[1], 1.0f / d[2]);
+    int neg[3] = {inv.x < 0.0f, inv.y < 0.0f, inv.z < 0.0f};
+    return bounds_intersect_p_cached(n, v3(o[0], o[1], o[2]), t_max, inv, neg) ? 1 : 0;
+}
+// sample a light from a context: out = l[4], wi[3], pdf, p_light mid[3], n[3]
+int orc_light_sample(const SgSceneDesc* desc, int light, const float* ctx_p, const float* ctx_n, const float* ctx_ns,
+                     const float* u2, const float* lambda4, float* out) {
+    Scene sc(desc);
+    LightSampleContext ctx; ctx.pi = p3fi_exact(v3(ctx_p[0], ctx_p[1], ctx_p[2])); ctx.n = v3(ctx_n[0], ctx_n[1], ctx_n[2]); ctx.ns = v3(ctx_ns[0], ctx_ns[1], ctx_ns[2]);
+    Wavelengths w; for (int i = 0; i < 4; ++i) { w.lambda[i] = lambda4[i]; w.pdf[i] = 1.0f; }
+    LightLiSample ls; V2 u = {u2[0], u2[1]};
+    if (!light_sample_li(sc, desc->lights[light], ctx, u, w, &ls)) return 0;
+    for (int i = 0; i < 4; ++i) out[i] = ls.l.v[i];
+    out[4] = ls.wi.x; out[5] = ls.wi.y; out[6] = ls.wi.z; out[7] = ls.pdf;
+    V3 pm = p3fi_mid(ls.p_light); out[8] = pm.x; out[9] = pm.y; out[10] = pm.z;
+    out[11] = ls.n_light.x; out[12] = ls.n_light.y; out[13] = ls.n_light.z;
+    return 1;
+}
+float orc_light_pdf(const SgSceneDesc* desc, int light, const float* ctx_p, const float* ctx_n, const float* ctx_ns, const float* wi) {
+    Scene sc(desc);
+    LightSampleContext ctx; ctx.pi = p3fi_exact(v3(ctx_p[0], ctx_p[1], ctx_p[2])); ctx.n = v3(ctx_n[0], ctx_n[1], ctx_n[2]); ctx.ns = v3(ctx_ns[0], ctx_ns[1], ctx_ns[2]);
+    return light_pdf_li(sc, desc->lights[light], ctx, v3(wi[0], wi[1], wi[2]));
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""In-tree build of the native libraries (no JIT cache: the built .so files travel with the repo
+snapshot to the GPU box).
+
+  libshimmer_gpu.so  : CUDA kernels + C ABI, sm_100a only, -fmad=false (arithmetic contract)
+  libshimmer_host.so : host-side BVH build (stands in for shimmer's Rust BvhAggregate::new)
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_gpu(force=False, verbose=False):
+    out = os.path.join(HERE, "libshimmer_gpu.so")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(HERE, "..", "include", "shimmer_gpu.h"))
+    if not force and not _stale(out, srcs):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "shimmer_gpu.cu")]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def build_host(force=False):
+    out = os.path.join(HERE, "libshimmer_host.so")
+    srcs = [os.path.join(CSRC, "host_bvh.cpp"), os.path.join(HERE, "..", "include", "shimmer_gpu.h")]
+    if not force and not _stale(out, srcs):
+        return out
+    cxx = shutil.which("g++") or "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, srcs[0]], check=True)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return build_host(force), build_gpu(force, verbose)
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,441 @@
+// Wavefront state + kernels of the B200 path tracer.
+//
+// One wavefront = up to `capacity` camera paths resident in HBM as structure-of-arrays
+// (float4-packed so every access is one LDG.128/STG.128).  Per bounce the stream runs
+//   trace_closest -> shade_miss / shade<Diffuse|Conductor|Dielectric> -> trace_shadow
+// with device-side queues: kernels read their work count from device counters, so a whole
+// batch (max_depth+1 bounces) is enqueued without a single host synchronisation.
+// Queue appends are warp-aggregated (__ballot_sync + one atomicAdd per warp and queue).
+#pragma once
+#include "sg_shading.cuh"
+
+namespace sg {
+
+struct PathState {
+    float4* ray_o;      // o.xyz
+    float4* ray_d;      // d.xyz
+    float4* hit_b;      // b0 b1 b2 t
+    int*    hit_prim;
+    float4* L;
+    float4* beta;
+    float4* lambda;
+    float4* lpdf;
+    ulonglong2* rng_a;  // xoshiro256++ s0 s1
+    ulonglong2* rng_b;  //               s2 s3
+    uint32_t* pixel;    // linear index inside the film window
+    uint32_t* flags;    // [0:8) depth, bit 8 specular_bounce, bit 9 any_non_specular_bounces
+    float2* pb_eta;     // p_b, eta_scale
+    float4* ctx0;       // prev LightSampleContext: pi.lo.xyz, pi.hi.x
+    float4* ctx1;       //   pi.hi.yz, n.xy
+    float4* ctx2;       //   n.z, ns.xyz
+    float4* sh_o;       // shadow ray origin
+    float4* sh_d;       // shadow ray direction (unnormalised p_to - p_from)
+    float4* sh_L;       // beta * Ld, added to L if the shadow ray is unoccluded
+};
+static constexpr int kPathBytes = 16 * 16 + 4 + 4 + 4 + 8;   // per-path HBM footprint (276 B)
+
+enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_NKINDS = 4 };
+// per-depth counter block (uint32 x 16)
+enum { C_NRAY = 0, C_NSHADE = 1 /*..4*/, C_NSHADOW = 5, C_CUR_CLOSEST = 6, C_CUR_SHADOW = 7, C_STRIDE = 16 };
+
+struct Queues {
+    uint32_t* ray[2];
+    uint32_t* shade[Q_NKINDS];
+    uint32_t* shadow;
+    uint32_t* counters;     // (max_depth + 2) * C_STRIDE
+};
+
+struct RenderConst {
+    uint64_t seed;
+    int32_t  sample_begin;
+    int32_t  spp;
+    int32_t  max_depth;
+    int32_t  regularize;
+    uint32_t option_flags;
+    int32_t  win_x0, win_y0, win_w, win_h;
+    int32_t  full_res_x;
+};
+
+struct DevStats { unsigned long long closest, shadow, nodes, tris; };
+
+#define SG_SHADOW_TMAX 0.9999f        /* 1.0 - SHADOW_EPISLON, integrator.rs:66,115 */
+static constexpr int kTraceThreads = 128;
+
+// ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
+                                                  unsigned long long first_item, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) q.counters[C_NRAY] = count;
+    if (i >= count) return;
+    const unsigned long long g = first_item + i;
+    const unsigned long long npix = (unsigned long long)rc.win_w * (unsigned long long)rc.win_h;
+    const int s = rc.sample_begin + (int)(g / npix);
+    const uint32_t pix = (uint32_t)(g % npix);
+    const int px = rc.win_x0 + (int)(pix % (uint32_t)rc.win_w), py = rc.win_y0 + (int)(pix / (uint32_t)rc.win_w);
+    Rng rng; rng.seed_from_u64(stream_key(rc.seed, (uint32_t)(py * rc.full_res_x + px), (uint32_t)s));
+    Wavelengths lam; float3 o, d; float w;
+    camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
+    st.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
+    st.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    st.L[i] = spec1(0.0f);
+    st.beta[i] = spec1(1.0f);
+    st.lambda[i] = lam.lambda; st.lpdf[i] = lam.pdf;
+    st.rng_a[i] = make_ulonglong2(rng.s0, rng.s1); st.rng_b[i] = make_ulonglong2(rng.s2, rng.s3);
+    st.pixel[i] = pix;
+    st.flags[i] = 0u;
+    st.pb_eta[i] = make_float2(1.0f, 1.0f);
+    st.ctx0[i] = make_float4(0, 0, 0, 0); st.ctx1[i] = make_float4(0, 0, 0, 0); st.ctx2[i] = make_float4(0, 0, 0, 0);
+    q.ray[0][i] = i;
+}
+
+// ---- closest-hit / any-hit traversal over a ray queue ----
+// Persistent CTAs (grid = SMs x resident CTAs): each warp claims 32 queue entries with one
+// atomicAdd, traverses with a per-thread 64-entry stack in shared memory (bank-conflict-free:
+// level-major, one word per thread per level), then compacts results into the material queues.
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ DScene sc, PathState st, Queues q,
+                                                         int depth, DevStats* stats) {
+    __shared__ uint32_t s_stack[64 * kTraceThreads];
+    uint32_t* C = q.counters + depth * C_STRIDE;
+    const uint32_t n = C[ANY ? C_NSHADOW : C_NRAY];
+    const uint32_t* queue = ANY ? q.shadow : q.ray[depth & 1];
+    uint32_t* cursor = C + (ANY ? C_CUR_SHADOW : C_CUR_CLOSEST);
+    const int lane = threadIdx.x & 31;
+    uint32_t cnt_nodes = 0, cnt_tris = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + lane;
+        const bool active = idx < n;
+        int kind = -1;
+        uint32_t path = 0;
+        if (active) {
+            path = queue[idx];
+            HitRec hit;
+            if (ANY) {
+                const float4 o = st.sh_o[path], d = st.sh_d[path];
+                bool occluded = traverse<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), SG_SHADOW_TMAX, hit,
+                                                      s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
+                if (!occluded) st.L[path] = st.L[path] + st.sh_L[path];
+            } else {
+                const float4 o = st.ray_o[path], d = st.ray_d[path];
+                bool found = traverse<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), INFINITY, hit,
+                                                    s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
+                st.hit_prim[path] = hit.prim;
+                if (found) {
+                    st.hit_b[path] = make_float4(hit.b0, hit.b1, hit.b2, hit.t);
+                    kind = 1 + (int)(__float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)hit.prim).w) >> 28);
+                } else kind = Q_MISS;
+            }
+        }
+        if (!ANY) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < Q_NKINDS; ++k) {
+                const uint32_t mask = __ballot_sync(0xffffffffu, kind == k);
+                if (mask) {
+                    uint32_t qbase = 0;
+                    const int leader = __ffs(mask) - 1;
+                    if (lane == leader) qbase = atomicAdd(C + C_NSHADE + k, (uint32_t)__popc(mask));
+                    qbase = __shfl_sync(0xffffffffu, qbase, leader);
+                    if (kind == k) q.shade[k][qbase + __popc(mask & ((1u << lane) - 1u))] = path;
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
+        atomicAdd(&stats->tris, (unsigned long long)cnt_tris);
+    }
+}
+
+// ---- escaped rays: infinite lights, integrator.rs:776-794 ----
+__global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DScene sc, PathState st, Queues q, int depth) {
+    const uint32_t* C = q.counters + depth * C_STRIDE;
+    const uint32_t n = C[C_NSHADE + Q_MISS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t path = q.shade[Q_MISS][i];
+        const uint32_t fl = st.flags[path];
+        const int pdepth = fl & 0xff; const bool specular_bounce = (fl >> 8) & 1u;
+        Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
+        Spec L = st.L[path]; const Spec beta = st.beta[path];
+        const float p_b = st.pb_eta[path].x;
+        for (int k = 0; k < sc.n_infinite; ++k) {
+            const SgLight lt = sc.lights[sc.infinite_ids[k]];
+            Spec le = lt.scale * spectrum_sample(sc, lt.spectrum, lam);          // UniformInfiniteLight::le light.rs:792-794
+            if (pdepth == 0 || specular_bounce) L = L + beta * le;
+            else {
+                float p_l = (1.0f / (float)sc.n_lights) * 0.0f;                  // pdf_li(.., allow_incomplete_pdf = true) = 0, light.rs:770-781
+                float w_b = power_heuristic(p_b, p_l);
+                L = L + beta * w_b * le;
+            }
+        }
+        st.L[path] = L;
+    }
+}
+
+// ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
+//      + sample_ld :897-963 ----
+template <int KIND>
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+    uint32_t* C = q.counters + depth * C_STRIDE;
+    uint32_t* Cn = C + C_STRIDE;
+    const int qk = 1 + KIND;
+    const uint32_t n = C[C_NSHADE + qk];
+    const uint32_t* queue = q.shade[qk];
+    uint32_t* q_next = q.ray[(depth + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
+        const uint32_t i = base + lane;
+        bool want_shadow = false, want_next = false;
+        uint32_t path = 0;
+        if (i < n) {
+            path = queue[i];
+            const float4 rd4 = st.ray_d[path];
+            const float3 rd = f3(rd4.x, rd4.y, rd4.z);
+            const float3 wo = -rd;
+            const int prim_id = st.hit_prim[path];
+            const float4 hb = st.hit_b[path];
+            const SgPrimitive prim = sc.prims[prim_id];
+            uint32_t fl = st.flags[path];
+            int pdepth = fl & 0xff; bool specular_bounce = (fl >> 8) & 1u; bool any_non_specular = (fl >> 9) & 1u;
+            Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
+            Spec L = st.L[path]; Spec beta = st.beta[path];
+            float2 pbe = st.pb_eta[path];
+            float p_b = pbe.x, eta_scale = pbe.y;
+
+            Surf s = make_surface(sc, prim.mesh, prim.tri, hb.x, hb.y, hb.z);
+
+            // emission + MIS against light sampling, :798-813
+            if (prim.light >= 0) {
+                const SgLight lt = sc.lights[prim.light];
+                Spec le = light_l(sc, lt, s.n, wo, lam);
+                if (!spec_zero(le)) {
+                    if (pdepth == 0 || specular_bounce) L = L + beta * le;
+                    else {
+                        LightCtx pc;
+                        const float4 c0 = st.ctx0[path], c1 = st.ctx1[path], c2 = st.ctx2[path];
+                        pc.pi.lo = f3(c0.x, c0.y, c0.z); pc.pi.hi = f3(c0.w, c1.x, c1.y);
+                        pc.n = f3(c1.z, c1.w, c2.x); pc.ns = f3(c2.y, c2.z, c2.w);
+                        float p_l = (1.0f / (float)sc.n_lights) * light_pdf_li(sc, lt, pc, rd);
+                        float w_l = power_heuristic(p_b, p_l);
+                        L = L + beta * w_l * le;
+                    }
+                }
+            }
+
+            // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
+            const SgMaterial mat = sc.materials[prim.material];
+            if (mat.flags & SG_MAT_HAS_DISPLACEMENT) apply_constant_bump(s);
+            BSDF<KIND> bsdf;
+            bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
+            if (KIND == SG_MATERIAL_DIFFUSE) {
+                bsdf.r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);          // material.rs:307-310
+            } else {
+                float ur = mat.u_roughness, vr = mat.v_roughness;
+                if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }     // roughness_to_alpha
+                if (KIND == SG_MATERIAL_CONDUCTOR) {
+                    bsdf.r = spectrum_sample(sc, mat.spec_a, lam); bsdf.k = spectrum_sample(sc, mat.spec_b, lam);
+                } else {
+                    float se = spectrum_get(sc, mat.spec_a, lam.lambda.x);                      // material.rs:609-624
+                    if (sc.spectra[mat.spec_a].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
+                    if (se == 0.0f) se = 1.0f;
+                    bsdf.eta = se;
+                }
+                bsdf.mf = TR::make(ur, vr);
+            }
+            bsdf.fx = normalize3(s.sdpdu); bsdf.fz = s.sn; bsdf.fy = cross3(bsdf.fz, bsdf.fx);
+            if (rc.regularize && any_non_specular) bsdf.mf.regularize();                        // :825-828
+
+            bool alive = pdepth != rc.max_depth;                                               // :830-833
+            if (alive) {
+                pdepth += 1;
+                Rng rng; { ulonglong2 a = st.rng_a[path], b = st.rng_b[path]; rng.s0 = a.x; rng.s1 = a.y; rng.s2 = b.x; rng.s3 = b.y; }
+                const int bflags = bsdf.flags();
+                // ---- sample_ld :897-963 ----
+                if (bflags & (BX_DIFFUSE | BX_GLOSSY)) {
+                    LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;
+                    const bool refl = bflags & BX_REFLECTION, trans = bflags & BX_TRANSMISSION;
+                    if (refl && !trans) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, wo));
+                    else if (trans && !refl) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, -wo));
+                    const float ul = rng.get_1d();
+                    float2 u_light; u_light.x = rng.get_1d(); u_light.y = rng.get_1d();
+                    if (sc.n_lights > 0) {
+                        // UniformLightSampler::sample_light light_sampler.rs:91-103 (`as usize` saturates, NaN -> 0)
+                        uint32_t li = __float2uint_rz(ul * (float)sc.n_lights);
+                        if (li > sc.n_lights - 1) li = sc.n_lights - 1;
+                        const float p_choose = 1.0f / (float)sc.n_lights;
+                        const SgLight lt = sc.lights[li];
+                        LightSample ls;
+                        if (light_sample_li(sc, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
+                            Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);
+                            if (!spec_zero(f)) {
+                                const float p_l = p_choose * ls.pdf;
+                                Spec ld;
+                                if (lt.kind == SG_LIGHT_POINT) ld = ls.l * f / p_l;
+                                else {
+                                    float p_bsdf = bsdf.pdf(wo, ls.wi);
+                                    float w_l = power_heuristic(p_l, p_bsdf);
+                                    ld = w_l * ls.l * f / p_l;
+                                }
+                                // Ray::spawn_ray_to_both_offset ray.rs:83-99
+                                float3 pf = offset_ray_origin(s.pi, s.n, p3fi_mid(ls.p_light) - p3fi_mid(s.pi));
+                                float3 pt = offset_ray_origin(ls.p_light, ls.n_light, pf - p3fi_mid(ls.p_light));
+                                float3 sd = pt - pf;
+                                st.sh_o[path] = make_float4(pf.x, pf.y, pf.z, 0.0f);
+                                st.sh_d[path] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                                st.sh_L[path] = beta * ld;
+                                want_shadow = true;
+                            }
+                        }
+                    }
+                }
+                // ---- BSDF sampling :843-875 ----
+                const float u = rng.get_1d();
+                float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+                BSDFSample bs;
+                alive = bsdf.sample_f(wo, u, u2, bs);
+                if (alive) {
+                    beta = beta * (bs.f * absdot3(bs.wi, s.sn) / bs.pdf);
+                    p_b = bs.pdf;
+                    specular_bounce = (bs.flags & BX_SPECULAR) != 0;
+                    any_non_specular = any_non_specular || !specular_bounce;
+                    if (bs.flags & BX_TRANSMISSION) eta_scale *= sqr(bs.eta);
+                    st.ctx0[path] = make_float4(s.pi.lo.x, s.pi.lo.y, s.pi.lo.z, s.pi.hi.x);
+                    st.ctx1[path] = make_float4(s.pi.hi.y, s.pi.hi.z, s.n.x, s.n.y);
+                    st.ctx2[path] = make_float4(s.n.z, s.sn.x, s.sn.y, s.sn.z);
+                    const float3 no = offset_ray_origin(s.pi, s.n, bs.wi);                     // Interaction::spawn_ray
+                    st.ray_o[path] = make_float4(no.x, no.y, no.z, 0.0f);
+                    st.ray_d[path] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.0f);
+                    // Russian roulette :878-891
+                    if (isfinite(eta_scale)) {
+                        const float m = spec_max(beta * eta_scale);
+                        if (m < 1.0f && pdepth > 1) {
+                            const float qq = fmaxf(0.0f, 1.0f - m);
+                            if (rng.get_1d() < qq) alive = false;
+                            else beta = beta / (1.0f - qq);
+                        }
+                    }
+                }
+                st.rng_a[path] = make_ulonglong2(rng.s0, rng.s1); st.rng_b[path] = make_ulonglong2(rng.s2, rng.s3);
+            }
+            st.L[path] = L;
+            if (alive) {
+                st.beta[path] = beta;
+                st.pb_eta[path] = make_float2(p_b, eta_scale);
+                st.flags[path] = (uint32_t)pdepth | (specular_bounce ? 256u : 0u) | (any_non_specular ? 512u : 0u);
+            }
+            if (KIND == SG_MATERIAL_DIELECTRIC) st.lpdf[path] = lam.pdf;                        // terminate_secondary
+            want_next = alive;
+        }
+        __syncwarp();
+        {   // warp-aggregated queue appends
+            uint32_t mask = __ballot_sync(0xffffffffu, want_shadow);
+            if (mask) {
+                uint32_t qb = 0; const int leader = __ffs(mask) - 1;
+                if (lane == leader) qb = atomicAdd(C + C_NSHADOW, (uint32_t)__popc(mask));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (want_shadow) q.shadow[qb + __popc(mask & ((1u << lane) - 1u))] = path;
+            }
+            mask = __ballot_sync(0xffffffffu, want_next);
+            if (mask) {
+                uint32_t qb = 0; const int leader = __ffs(mask) - 1;
+                if (lane == leader) qb = atomicAdd(Cn + C_NRAY, (uint32_t)__popc(mask));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (want_next) q_next[qb + __popc(mask & ((1u << lane) - 1u))] = path;
+            }
+        }
+    }
+}
+
+// ---- RgbFilm::add_sample for every path of the batch ----
+__global__ void __launch_bounds__(256) k_film(const __grid_constant__ DScene sc, PathState st, uint32_t count, double* film) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Wavelengths lam; lam.lambda = st.lambda[i]; lam.pdf = st.lpdf[i];
+    film_add_sample(sc, film + 4 * (size_t)st.pixel[i], st.L[i], lam, 1.0f);
+}
+
+__global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
+    unsigned long long c = 0, s = 0;
+    for (int d = 0; d < n_depths; ++d) { c += counters[d * C_STRIDE + C_NRAY]; s += counters[d * C_STRIDE + C_NSHADOW]; }
+    stats->closest += c; stats->shadow += s;
+}
+
+// ---- free-standing ray batches: the ray-cast parity / roofline entry (sg_trace) ----
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_rays(const __grid_constant__ DScene sc, long long n, const float* __restrict__ o,
+                                                              const float* __restrict__ d, const float* __restrict__ tmax,
+                                                              SgHit* __restrict__ out, unsigned long long* cursor, DevStats* stats) {
+    __shared__ uint32_t s_stack[64 * kTraceThreads];
+    const int lane = threadIdx.x & 31;
+    uint32_t cnt_nodes = 0, cnt_tris = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)n) break;
+        const unsigned long long i = base + lane;
+        if (i < (unsigned long long)n) {
+            const float3 ro = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rdir = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+            HitRec hit;
+            bool found = traverse<ANY, COUNT>(sc, ro, rdir, tmax[i], hit, s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
+            SgHit h; h.prim = -1; h.t = 0.0f; h.b0 = h.b1 = h.b2 = 0.0f; h.ng[0] = h.ng[1] = h.ng[2] = 0.0f;
+            if (found) {
+                if (ANY) h.prim = 0;
+                else {
+                    h.prim = hit.prim; h.t = hit.t; h.b0 = hit.b0; h.b1 = hit.b1; h.b2 = hit.b2;
+                    const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 1),
+                                 v2 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 2);
+                    const float3 p0 = f3(v0.x, v0.y, v0.z), p1 = f3(v1.x, v1.y, v1.z), p2 = f3(v2.x, v2.y, v2.z);
+                    float3 ng = normalize3(cross3(p0 - p2, p1 - p2));                    // triangle.rs:407-412
+                    const uint32_t mflags = sc.meshes[__float_as_uint(v2.w)].flags;
+                    if (((mflags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((mflags & SG_MESH_SWAPS_HANDEDNESS) != 0)) ng = -ng;
+                    h.ng[0] = ng.x; h.ng[1] = ng.y; h.ng[2] = ng.z;
+                }
+            }
+            out[i] = h;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
+        atomicAdd(&stats->tris, (unsigned long long)cnt_tris);
+    }
+}
+
+// ---- KAT kernels ----
+__global__ void k_sampler_fill(uint64_t seed, int raw, uint32_t pixel, uint32_t sample, long long n, float* out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Rng r; r.seed_from_u64(raw ? seed : stream_key(seed, pixel, sample));
+    for (long long i = 0; i < n; ++i) out[i] = r.get_1d();
+}
+__global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc, long long n, const int* pixel_xy, const int* sample_index,
+                              float* out_rays, float* out_lambda) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int px = pixel_xy[2 * i], py = pixel_xy[2 * i + 1];
+    Rng rng; rng.seed_from_u64(stream_key(rc.seed, (uint32_t)(py * rc.full_res_x + px), (uint32_t)sample_index[i]));
+    Wavelengths lam; float3 o, d; float w;
+    camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
+    float* r = out_rays + 6 * i;
+    r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    float* l = out_lambda + 8 * i;
+    l[0] = lam.lambda.x; l[1] = lam.lambda.y; l[2] = lam.lambda.z; l[3] = lam.lambda.w;
+    l[4] = lam.pdf.x; l[5] = lam.pdf.y; l[6] = lam.pdf.z; l[7] = lam.pdf.w;
+}
+// RgbFilm::get_pixel_rgb film.rs:720-738
+__global__ void k_film_develop(const __grid_constant__ DScene sc, const double* film, long long n, float* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float rgb[3] = {(float)film[4 * i], (float)film[4 * i + 1], (float)film[4 * i + 2]};
+    const double ws = film[4 * i + 3];
+    if (ws != 0.0) { rgb[0] /= (float)ws; rgb[1] /= (float)ws; rgb[2] /= (float)ws; }
+    const float* M = sc.film.output_rgb_from_sensor_rgb;
+    for (int r = 0; r < 3; ++r) out[3 * i + r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+}
+
+}  // namespace sg

@@ -1,0 +1,423 @@
+// libshimmer_gpu.so -- C ABI implementation (include/shimmer_gpu.h).
+// Host side: scene upload (one-time staging into HBM), wavefront scheduling on one CUDA
+// stream with device-side queue counters (no host sync inside a batch), film readback.
+// There is NO CPU fallback: every entry point either runs the sm_100a kernels or fails.
+#include "sg_wavefront.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+using namespace sg;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+int g_num_sms = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    return fail(e__ == cudaErrorMemoryAllocation ? SG_ERR_OUT_OF_MEMORY : SG_ERR_CUDA, \
+                std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+
+template <class T> int upload(const T* src, size_t n, T** dst, std::vector<void*>& owned) {
+    *dst = nullptr;
+    if (n == 0 || src == nullptr) return SG_OK;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, n * sizeof(T)));
+    owned.push_back(p);
+    CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (T*)p;
+    return SG_OK;
+}
+
+struct Workspace {
+    uint32_t capacity = 0;
+    int max_depth = -1;
+    PathState st{};
+    Queues q{};
+    std::vector<void*> owned;
+    void release() { for (void* p : owned) cudaFree(p); owned.clear(); capacity = 0; max_depth = -1; }
+};
+
+}  // namespace
+
+struct SgScene {
+    DScene d{};
+    std::vector<void*> owned;
+    Workspace ws;
+    DevStats* d_stats = nullptr;
+    unsigned long long* d_cursor = nullptr;
+    bool kinds_present[3] = {false, false, false};
+    double* d_film = nullptr; size_t film_pixels = 0;
+    uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
+};
+
+namespace {
+
+template <class T> int ws_alloc(Workspace& w, T** p, size_t n) {
+    void* q = nullptr;
+    CU(cudaMalloc(&q, n * sizeof(T)));
+    w.owned.push_back(q);
+    *p = (T*)q;
+    return SG_OK;
+}
+int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
+    Workspace& w = s->ws;
+    if (w.capacity >= capacity && w.max_depth >= max_depth) return SG_OK;
+    w.release();
+    int rc;
+    const size_t n = capacity;
+#define WS(field) if ((rc = ws_alloc(w, &w.st.field, n)) != SG_OK) return rc
+    WS(ray_o); WS(ray_d); WS(hit_b); WS(hit_prim); WS(L); WS(beta); WS(lambda); WS(lpdf); WS(rng_a); WS(rng_b);
+    WS(pixel); WS(flags); WS(pb_eta); WS(ctx0); WS(ctx1); WS(ctx2); WS(sh_o); WS(sh_d); WS(sh_L);
+#undef WS
+    if ((rc = ws_alloc(w, &w.q.ray[0], n)) != SG_OK) return rc;
+    if ((rc = ws_alloc(w, &w.q.ray[1], n)) != SG_OK) return rc;
+    for (int k = 0; k < Q_NKINDS; ++k) if ((rc = ws_alloc(w, &w.q.shade[k], n)) != SG_OK) return rc;
+    if ((rc = ws_alloc(w, &w.q.shadow, n)) != SG_OK) return rc;
+    if ((rc = ws_alloc(w, &w.q.counters, (size_t)(max_depth + 3) * C_STRIDE)) != SG_OK) return rc;
+    w.capacity = capacity; w.max_depth = max_depth;
+    return SG_OK;
+}
+
+int persistent_grid(const void* kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return g_num_sms * per_sm;      // grid = SM count x resident CTAs: one full wave, persistent
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+const char* sg_last_error(void) { return g_err.c_str(); }
+
+int sg_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(SG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(SG_ERR_INVALID_ARGUMENT, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SG_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; found ") + prop.name);
+    g_num_sms = prop.multiProcessorCount;
+    if (!g_stream) CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    return SG_OK;
+}
+
+int sg_shutdown(void) {
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    g_device = -1;
+    return SG_OK;
+}
+
+int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!desc || !out) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (desc->abi_version != SG_ABI_VERSION) return fail(SG_ERR_INVALID_ARGUMENT, "SgSceneDesc.abi_version mismatch");
+    if (desc->n_primitives > 0 && (!desc->nodes || !desc->primitives || !desc->meshes || !desc->indices || !desc->p))
+        return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
+    if (desc->n_primitives >= (1u << 31)) return fail(SG_ERR_UNSUPPORTED, "too many primitives");
+    // validate references so device code never reads out of bounds
+    for (uint32_t i = 0; i < desc->n_primitives; ++i) {
+        const SgPrimitive& p = desc->primitives[i];
+        if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
+            p.light >= (int32_t)desc->n_lights)
+            return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references out-of-range mesh/triangle/material/light");
+    }
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const SgMaterial& m = desc->materials[i];
+        if (m.kind < 0 || m.kind > SG_MATERIAL_DIELECTRIC) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.spec_a < 0 || m.spec_a >= (int32_t)desc->n_spectra || (m.kind == SG_MATERIAL_CONDUCTOR && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra)))
+            return fail(SG_ERR_INVALID_ARGUMENT, "material spectrum id out of range");
+    }
+    for (uint32_t i = 0; i < desc->n_nodes; ++i) {
+        const SgBvhNode& nd = desc->nodes[i];
+        if (nd.n_prims > 0 ? (nd.offset + nd.n_prims > desc->n_primitives) : (nd.offset >= desc->n_nodes || i + 1 >= desc->n_nodes))
+            return fail(SG_ERR_INVALID_ARGUMENT, "BVH node " + std::to_string(i) + " is malformed");
+    }
+    SgScene* s = new (std::nothrow) SgScene();
+    if (!s) return fail(SG_ERR_OUT_OF_MEMORY, "host allocation failed");
+    int rc = SG_OK;
+    auto bail = [&](int code) { sg_scene_destroy(s); return code; };
+    DScene& d = s->d;
+    // pre-gathered triangle vertices in BVH-leaf order (DESIGN.md "Data layout")
+    std::vector<float4> tv((size_t)desc->n_primitives * 3);
+    for (uint32_t i = 0; i < desc->n_primitives; ++i) {
+        const SgPrimitive& p = desc->primitives[i];
+        const SgMesh& m = desc->meshes[p.mesh];
+        const uint32_t* ix = desc->indices + m.first_index + 3 * (size_t)p.tri;
+        const uint32_t w[3] = {p.material | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, p.mesh};
+        for (int k = 0; k < 3; ++k) {
+            if (ix[k] >= m.n_vertices) { g_err = "vertex index out of range"; return bail(SG_ERR_INVALID_ARGUMENT); }
+            const float* q = desc->p + 3 * (size_t)(m.first_vertex + ix[k]);
+            float wf; std::memcpy(&wf, &w[k], 4);
+            tv[3 * (size_t)i + k] = make_float4(q[0], q[1], q[2], wf);
+        }
+        s->kinds_present[desc->materials[p.material].kind] = true;
+    }
+    float4* d_nodes = nullptr; float4* d_tv = nullptr;
+    if ((rc = upload((const float4*)desc->nodes, (size_t)desc->n_nodes * 2, &d_nodes, s->owned)) != SG_OK) return bail(rc);
+    if ((rc = upload(tv.data(), tv.size(), &d_tv, s->owned)) != SG_OK) return bail(rc);
+    d.nodes = d_nodes; d.tri_verts = d_tv;
+#define UP(field, src, n, T) { T* p__ = nullptr; if ((rc = upload((const T*)(src), (size_t)(n), &p__, s->owned)) != SG_OK) return bail(rc); d.field = p__; }
+    UP(prims, desc->primitives, desc->n_primitives, SgPrimitive);
+    UP(meshes, desc->meshes, desc->n_meshes, SgMesh);
+    UP(indices, desc->indices, desc->n_indices, uint32_t);
+    UP(p, desc->p, (size_t)desc->n_vertices * 3, float);
+    UP(n, desc->n, desc->n ? (size_t)desc->n_vertices * 3 : 0, float);
+    UP(uv, desc->uv, desc->uv ? (size_t)desc->n_vertices * 2 : 0, float);
+    UP(s, desc->s, desc->s ? (size_t)desc->n_vertices * 3 : 0, float);
+    UP(spectra, desc->spectra, desc->n_spectra, SgSpectrum);
+    UP(pool, desc->spectrum_pool, desc->n_pool, float);
+    UP(materials, desc->materials, desc->n_materials, SgMaterial);
+    UP(lights, desc->lights, desc->n_lights, SgLight);
+#undef UP
+    d.n_nodes = desc->n_nodes; d.n_prims = desc->n_primitives; d.n_lights = desc->n_lights; d.n_materials = desc->n_materials;
+    d.n_infinite = 0;
+    for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_UNIFORM_INFINITE) {
+        if (d.n_infinite >= 4) { g_err = "more than 4 infinite lights"; return bail(SG_ERR_UNSUPPORTED); }
+        d.infinite_ids[d.n_infinite++] = (int32_t)i;
+    }
+    d.camera = desc->camera; d.film = desc->film;
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(DevStats)) != cudaSuccess) { g_err = "cudaMalloc stats"; return bail(SG_ERR_OUT_OF_MEMORY); }
+    s->owned.push_back(p); s->d_stats = (DevStats*)p;
+    if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) { g_err = "cudaMalloc cursor"; return bail(SG_ERR_OUT_OF_MEMORY); }
+    s->owned.push_back(p); s->d_cursor = (unsigned long long*)p;
+    *out = s;
+    return SG_OK;
+}
+
+int sg_scene_destroy(SgScene* s) {
+    if (!s) return SG_OK;
+    cudaDeviceSynchronize();
+    s->ws.release();
+    for (void* p : s->owned) cudaFree(p);
+    if (s->d_film) cudaFree(s->d_film);
+    delete s;
+    return SG_OK;
+}
+
+int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats* stats, void* stream_v) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || !rp || !d_film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (rp->sample_end < rp->sample_begin || rp->sample_begin < 0) return fail(SG_ERR_INVALID_ARGUMENT, "bad sample range");
+    if (rp->max_depth < 0 || rp->max_depth > 254) return fail(SG_ERR_INVALID_ARGUMENT, "max_depth out of range");
+    if (rp->option_flags & SG_OPT_FORCE_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "force_diffuse is not on the GPU path");
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
+    const uint64_t npix = s->n_pixels();
+    const uint64_t total = npix * (uint64_t)(rp->sample_end - rp->sample_begin);
+    uint64_t cap64 = rp->max_paths_in_flight > 0 ? (uint64_t)rp->max_paths_in_flight : (1ull << 22);
+    if (cap64 > total) cap64 = total;
+    if (cap64 == 0) cap64 = 1;
+    const uint32_t capacity = (uint32_t)cap64;
+    int rc = ensure_workspace(s, capacity, rp->max_depth);
+    if (rc != SG_OK) return rc;
+    Workspace& w = s->ws;
+    RenderConst k;
+    k.seed = rp->seed; k.sample_begin = rp->sample_begin; k.spp = rp->samples_per_pixel; k.max_depth = rp->max_depth;
+    k.regularize = rp->regularize; k.option_flags = rp->option_flags;
+    k.win_x0 = s->d.film.pixel_bounds[0]; k.win_y0 = s->d.film.pixel_bounds[1];
+    k.win_w = s->d.film.pixel_bounds[2] - k.win_x0; k.win_h = s->d.film.pixel_bounds[3] - k.win_y0;
+    k.full_res_x = s->d.film.full_resolution[0];
+    const bool count = (rp->reserved & 1) != 0;       // bit 0: count nodes/tris (slower, for roofline accounting)
+    const bool time_trace = (rp->reserved & 2) != 0;  // bit 1: time the traversal kernels separately
+    const int n_depths = rp->max_depth + 1;
+    static int grid_closest[2] = {0, 0}, grid_shadow[2] = {0, 0};
+    if (!grid_closest[0]) {
+        grid_closest[0] = persistent_grid((const void*)k_trace<false, false>, kTraceThreads);
+        grid_closest[1] = persistent_grid((const void*)k_trace<false, true>, kTraceThreads);
+        grid_shadow[0] = persistent_grid((const void*)k_trace<true, false>, kTraceThreads);
+        grid_shadow[1] = persistent_grid((const void*)k_trace<true, true>, kTraceThreads);
+    }
+    const int shade_grid = g_num_sms * 8;
+    CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    std::vector<cudaEvent_t> tev;
+    uint64_t launches = 0;
+    CU(cudaEventRecord(ev0, stream));
+    for (uint64_t first = 0; first < total; first += capacity) {
+        const uint32_t cnt = (uint32_t)((total - first) < capacity ? (total - first) : capacity);
+        CU(cudaMemsetAsync(w.q.counters, 0, (size_t)(rp->max_depth + 3) * C_STRIDE * sizeof(uint32_t), stream));
+        k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
+        for (int depth = 0; depth < n_depths; ++depth) {
+            if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+            if (count) k_trace<false, true><<<grid_closest[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+            else k_trace<false, false><<<grid_closest[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+            ++launches;
+            if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+            if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
+            if (s->kinds_present[SG_MATERIAL_DIFFUSE]) { k_shade<SG_MATERIAL_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            if (s->kinds_present[SG_MATERIAL_CONDUCTOR]) { k_shade<SG_MATERIAL_CONDUCTOR><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            if (s->kinds_present[SG_MATERIAL_DIELECTRIC]) { k_shade<SG_MATERIAL_DIELECTRIC><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            if (depth < rp->max_depth && s->d.n_lights > 0) {
+                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+                if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+                else k_trace<true, false><<<grid_shadow[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+                ++launches;
+                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+            }
+        }
+        k_film<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, cnt, (double*)d_film); ++launches;
+        k_accum_stats<<<1, 1, 0, stream>>>(w.q.counters, n_depths, s->d_stats); ++launches;
+    }
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    CU(cudaGetLastError());
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    double trace_ms = 0.0;
+    for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); trace_ms += t; }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) {
+        DevStats h;
+        CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats->camera_paths = total; stats->closest_hit_rays = h.closest; stats->shadow_rays = h.shadow;
+        stats->nodes_visited = h.nodes; stats->tris_tested = h.tris; stats->kernel_launches = launches;
+        stats->render_ms = ms; stats->trace_ms = trace_ms;
+    }
+    return SG_OK;
+}
+
+int sg_render(SgScene* s, const SgRenderParams* rp, SgFilmPixel* film, SgStats* stats) {
+    if (!s || !rp || !film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    const size_t npix = (size_t)s->n_pixels();
+    if (s->film_pixels < npix) {
+        if (s->d_film) cudaFree(s->d_film);
+        s->d_film = nullptr; s->film_pixels = 0;
+        CU(cudaMalloc((void**)&s->d_film, npix * sizeof(SgFilmPixel)));
+        s->film_pixels = npix;
+    }
+    CU(cudaMemsetAsync(s->d_film, 0, npix * sizeof(SgFilmPixel), g_stream));
+    int rc = sg_render_device(s, rp, s->d_film, stats, g_stream);
+    if (rc != SG_OK) return rc;
+    std::vector<SgFilmPixel> tmp(npix);
+    CU(cudaMemcpy(tmp.data(), s->d_film, npix * sizeof(SgFilmPixel), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npix; ++i) {
+        for (int c = 0; c < 3; ++c) film[i].rgb_sum[c] += tmp[i].rgb_sum[c];
+        film[i].weight_sum += tmp[i].weight_sum;
+    }
+    return SG_OK;
+}
+
+int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, const void* d_t_max, int any_hit, void* d_out,
+                    SgStats* stats, void* stream_v) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || n < 0 || (n > 0 && (!d_o || !d_d || !d_t_max || !d_out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
+    const bool count = stats != nullptr;
+    CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
+    CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), stream));
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, stream));
+    if (n > 0) {
+#define LAUNCH(A, C) { int g = persistent_grid((const void*)k_trace_rays<A, C>, kTraceThreads); \
+        k_trace_rays<A, C><<<g, kTraceThreads, 0, stream>>>(s->d, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats); }
+        if (any_hit) { if (count) LAUNCH(true, true) else LAUNCH(true, false) }
+        else { if (count) LAUNCH(false, true) else LAUNCH(false, false) }
+#undef LAUNCH
+    }
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    CU(cudaGetLastError());
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) {
+        DevStats h;
+        CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        if (any_hit) stats->shadow_rays = (uint64_t)n; else stats->closest_hit_rays = (uint64_t)n;
+        stats->nodes_visited = h.nodes; stats->tris_tested = h.tris; stats->kernel_launches = n > 0 ? 1 : 0;
+        stats->render_ms = ms; stats->trace_ms = ms;
+    }
+    return SG_OK;
+}
+
+int sg_trace(SgScene* s, int64_t n, const float* o, const float* d, const float* t_max, int any_hit, SgHit* out, SgStats* stats) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || n < 0 || (n > 0 && (!o || !d || !t_max || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) { if (stats) std::memset(stats, 0, sizeof *stats); return SG_OK; }
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; SgHit* d_out = nullptr;
+    int rc = SG_OK;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_out); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CUX(cudaMalloc((void**)&d_o, (size_t)n * 12)); CUX(cudaMalloc((void**)&d_d, (size_t)n * 12));
+    CUX(cudaMalloc((void**)&d_t, (size_t)n * 4)); CUX(cudaMalloc((void**)&d_out, (size_t)n * sizeof(SgHit)));
+    CUX(cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, g_stream));
+    CUX(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, g_stream));
+    CUX(cudaMemcpyAsync(d_t, t_max, (size_t)n * 4, cudaMemcpyHostToDevice, g_stream));
+    rc = sg_trace_device(s, n, d_o, d_d, d_t, any_hit, d_out, stats, g_stream);
+    if (rc == SG_OK) CUX(cudaMemcpy(out, d_out, (size_t)n * sizeof(SgHit), cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return rc;
+}
+
+int sg_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sample_index, int64_t n, float* out) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (n < 0 || (n > 0 && !out)) return fail(SG_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (n == 0) return SG_OK;
+    float* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)n * 4));
+    k_sampler_fill<<<1, 1, 0, g_stream>>>(seed, raw, pixel_index, sample_index, (long long)n, d);
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(e));
+    return SG_OK;
+}
+
+int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_t* pixel_xy, const int32_t* sample_index,
+                   float* out_rays, float* out_lambda) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || !rp || n < 0 || (n > 0 && (!pixel_xy || !sample_index || !out_rays || !out_lambda))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return SG_OK;
+    int *d_xy = nullptr, *d_si = nullptr; float *d_r = nullptr, *d_l = nullptr;
+    auto cleanup = [&]() { cudaFree(d_xy); cudaFree(d_si); cudaFree(d_r); cudaFree(d_l); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CUX(cudaMalloc((void**)&d_xy, (size_t)n * 8)); CUX(cudaMalloc((void**)&d_si, (size_t)n * 4));
+    CUX(cudaMalloc((void**)&d_r, (size_t)n * 24)); CUX(cudaMalloc((void**)&d_l, (size_t)n * 32));
+    CUX(cudaMemcpy(d_xy, pixel_xy, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_si, sample_index, (size_t)n * 4, cudaMemcpyHostToDevice));
+    RenderConst k{}; k.seed = rp->seed; k.option_flags = rp->option_flags; k.full_res_x = s->d.film.full_resolution[0];
+    k_camera_rays<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, k, (long long)n, d_xy, d_si, d_r, d_l);
+    CUX(cudaStreamSynchronize(g_stream));
+    CUX(cudaMemcpy(out_rays, d_r, (size_t)n * 24, cudaMemcpyDeviceToHost));
+    CUX(cudaMemcpy(out_lambda, d_l, (size_t)n * 32, cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return SG_OK;
+}
+
+int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_rgb) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || n < 0 || (n > 0 && (!film || !out_rgb))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return SG_OK;
+    double* d_f = nullptr; float* d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_f); cudaFree(d_o); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CUX(cudaMalloc((void**)&d_f, (size_t)n * 32)); CUX(cudaMalloc((void**)&d_o, (size_t)n * 12));
+    CUX(cudaMemcpy(d_f, film, (size_t)n * 32, cudaMemcpyHostToDevice));
+    k_film_develop<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(s->d, d_f, (long long)n, d_o);
+    CUX(cudaStreamSynchronize(g_stream));
+    CUX(cudaMemcpy(out_rgb, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return SG_OK;
+}
+
+}  // extern "C"

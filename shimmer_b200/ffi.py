@@ -1,0 +1,176 @@
+"""ctypes binding of the C ABI in include/shimmer_gpu.h.
+
+This is the Python twin of the Rust `extern "C"` block shown in INTEGRATION.md: plain
+pointers and sizes, no torch types.  The product path fails loudly when the CUDA library is
+missing -- there is no CPU fallback (the CPU oracle under oracle/ is test infrastructure
+and is never imported from this package).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshimmer_gpu.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
+
+SG_ABI_VERSION = 1
+
+# enums (mirror include/shimmer_gpu.h)
+SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
+SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
+SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
+SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC = 0, 1, 2
+SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
+SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE = 0, 1, 2
+SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
+SG_OPT_DISABLE_TEXTURE_FILTERING, SG_OPT_FORCE_DIFFUSE = 4, 8
+
+
+class SgBvhNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("offset", C.c_uint32),
+                ("n_prims", C.c_uint16), ("axis", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class SgPrimitive(C.Structure):
+    _fields_ = [("mesh", C.c_uint32), ("tri", C.c_uint32), ("material", C.c_uint32), ("light", C.c_int32)]
+
+
+class SgMesh(C.Structure):
+    _fields_ = [("first_index", C.c_uint32), ("first_vertex", C.c_uint32), ("n_triangles", C.c_uint32),
+                ("n_vertices", C.c_uint32), ("flags", C.c_uint32), ("pad", C.c_uint32 * 3)]
+
+
+class SgSpectrum(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("lambda_min", C.c_int32), ("c", C.c_float),
+                ("scale", C.c_float), ("off_a", C.c_uint32), ("off_b", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class SgMaterial(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("spec_a", C.c_int32), ("spec_b", C.c_int32), ("flags", C.c_int32),
+                ("u_roughness", C.c_float), ("v_roughness", C.c_float), ("displacement", C.c_float), ("pad", C.c_float)]
+
+
+class SgLight(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("spectrum", C.c_int32), ("scale", C.c_float), ("two_sided", C.c_int32),
+                ("mesh", C.c_uint32), ("tri", C.c_uint32), ("area", C.c_float), ("pos", C.c_float * 3),
+                ("scene_center", C.c_float * 3), ("scene_radius", C.c_float), ("pad", C.c_float * 2)]
+
+
+class SgCamera(C.Structure):
+    _fields_ = [("camera_from_raster", C.c_float * 16), ("render_from_camera", C.c_float * 16),
+                ("camera_from_render", C.c_float * 16), ("dx_camera", C.c_float * 3), ("dy_camera", C.c_float * 3),
+                ("lens_radius", C.c_float), ("focal_distance", C.c_float), ("shutter_open", C.c_float),
+                ("shutter_close", C.c_float),
+                ("min_pos_differential_x", C.c_float * 3), ("min_pos_differential_y", C.c_float * 3),
+                ("min_dir_differential_x", C.c_float * 3), ("min_dir_differential_y", C.c_float * 3)]
+
+
+class SgFilm(C.Structure):
+    _fields_ = [("full_resolution", C.c_int32 * 2), ("pixel_bounds", C.c_int32 * 4), ("filter_radius", C.c_float * 2),
+                ("r_bar", C.c_int32), ("g_bar", C.c_int32), ("b_bar", C.c_int32), ("imaging_ratio", C.c_float),
+                ("max_component_value", C.c_float), ("output_rgb_from_sensor_rgb", C.c_float * 9)]
+
+
+class SgSceneDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32),
+                ("n_nodes", C.c_uint32), ("nodes", C.POINTER(SgBvhNode)),
+                ("n_primitives", C.c_uint32), ("primitives", C.POINTER(SgPrimitive)),
+                ("n_meshes", C.c_uint32), ("meshes", C.POINTER(SgMesh)),
+                ("n_indices", C.c_uint32), ("indices", C.POINTER(C.c_uint32)),
+                ("n_vertices", C.c_uint32), ("p", C.POINTER(C.c_float)),
+                ("n", C.POINTER(C.c_float)), ("uv", C.POINTER(C.c_float)), ("s", C.POINTER(C.c_float)),
+                ("n_spectra", C.c_uint32), ("spectra", C.POINTER(SgSpectrum)),
+                ("n_pool", C.c_uint32), ("spectrum_pool", C.POINTER(C.c_float)),
+                ("n_materials", C.c_uint32), ("materials", C.POINTER(SgMaterial)),
+                ("n_lights", C.c_uint32), ("lights", C.POINTER(SgLight)),
+                ("camera", SgCamera), ("film", SgFilm)]
+
+
+class SgRenderParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("samples_per_pixel", C.c_int32), ("sample_begin", C.c_int32),
+                ("sample_end", C.c_int32), ("max_depth", C.c_int32), ("regularize", C.c_int32),
+                ("option_flags", C.c_uint32), ("max_paths_in_flight", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SgFilmPixel(C.Structure):
+    _fields_ = [("rgb_sum", C.c_double * 3), ("weight_sum", C.c_double)]
+
+
+class SgStats(C.Structure):
+    _fields_ = [("camera_paths", C.c_uint64), ("closest_hit_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SgHit(C.Structure):
+    _fields_ = [("prim", C.c_int32), ("t", C.c_float), ("b0", C.c_float), ("b1", C.c_float), ("b2", C.c_float),
+                ("ng", C.c_float * 3)]
+
+
+# every symbol include/shimmer_gpu.h declares; tests/test_abi.py checks the library exports all
+ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
+               "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
+               "sg_film_develop"]
+
+
+class ShimmerGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+_host = None
+
+
+def load_library():
+    """dlopen libshimmer_gpu.so and declare the prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShimmerGpuError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "The GPU path has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    fp = C.POINTER(C.c_float)
+    lib.sg_init.argtypes = [C.c_int]; lib.sg_init.restype = C.c_int
+    lib.sg_shutdown.argtypes = []; lib.sg_shutdown.restype = C.c_int
+    lib.sg_last_error.argtypes = []; lib.sg_last_error.restype = C.c_char_p
+    lib.sg_abi_version.argtypes = []; lib.sg_abi_version.restype = C.c_int
+    lib.sg_scene_create.argtypes = [C.POINTER(SgSceneDesc), C.POINTER(vp)]; lib.sg_scene_create.restype = C.c_int
+    lib.sg_scene_destroy.argtypes = [vp]; lib.sg_scene_destroy.restype = C.c_int
+    lib.sg_render.argtypes = [vp, C.POINTER(SgRenderParams), vp, C.POINTER(SgStats)]; lib.sg_render.restype = C.c_int
+    lib.sg_render_device.argtypes = [vp, C.POINTER(SgRenderParams), vp, C.POINTER(SgStats), vp]
+    lib.sg_render_device.restype = C.c_int
+    lib.sg_trace.argtypes = [vp, i64, vp, vp, vp, C.c_int, vp, C.POINTER(SgStats)]; lib.sg_trace.restype = C.c_int
+    lib.sg_trace_device.argtypes = [vp, i64, vp, vp, vp, C.c_int, vp, C.POINTER(SgStats), vp]
+    lib.sg_trace_device.restype = C.c_int
+    lib.sg_sampler_fill.argtypes = [u64, C.c_int, u32, u32, i64, vp]; lib.sg_sampler_fill.restype = C.c_int
+    lib.sg_camera_rays.argtypes = [vp, C.POINTER(SgRenderParams), i64, vp, vp, vp, vp]
+    lib.sg_camera_rays.restype = C.c_int
+    lib.sg_film_develop.argtypes = [vp, vp, i64, vp]; lib.sg_film_develop.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def load_host_library():
+    """Host-side helpers (BVH build standing in for shimmer's Rust BvhAggregate::new)."""
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_LIB_PATH):
+        raise ShimmerGpuError(f"{HOST_LIB_PATH} not found: run __graft_entry__.build()")
+    h = C.CDLL(HOST_LIB_PATH)
+    h.sh_bvh_build.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]; h.sh_bvh_build.restype = C.c_int64
+    h.sh_triangle_bounds.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]; h.sh_triangle_bounds.restype = None
+    _host = h
+    return h
+
+
+def check(rc, what="shimmer_gpu call"):
+    """Turn a non-zero status into an exception -- the reference panics (integrator.rs:36)."""
+    if rc != 0:
+        msg = load_library().sg_last_error()
+        raise ShimmerGpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,477 @@
+"""Host-side scene assembly: the Python stand-in for what shimmer's Rust host does between
+`parse_files` and `integrator.render` (src/render.rs:8-55, src/loading/scene.rs:381-907).
+
+In the real integration these objects already exist in Rust (camera, film, sensor, spectra,
+lights, materials, BvhAggregate) and the `render_gpu` shim only FLATTENS them into
+`SgSceneDesc`.  This module builds the same flattened arrays for the
+synthetic benchmark scenes so tests and bench.py can drive the C ABI without a Rust
+toolchain.  Everything here is host preparation; nothing on the render hot path.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import ffi
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "spectra.npz")
+LAMBDA_MIN, LAMBDA_MAX = 360, 830           # spectra/spectrum.rs:24-26
+CIE_Y_INTEGRAL = np.float32(106.856895)     # spectra/cie.rs:11
+f32 = np.float32
+
+
+# ----------------------------------------------------------------------------------------------
+# 4x4 transforms (src/transform.rs).  Matrices are built in f64 and rounded once to f32: they are
+# INPUTS to both the CUDA path and the oracle, so only their values matter, not how they are made.
+# ----------------------------------------------------------------------------------------------
+class Transform:
+    def __init__(self, m, m_inv=None):
+        self.m = np.asarray(m, dtype=np.float64).reshape(4, 4)
+        self.m_inv = np.linalg.inv(self.m) if m_inv is None else np.asarray(m_inv, dtype=np.float64).reshape(4, 4)
+
+    def __mul__(self, o):            # transform.rs:356-361
+        return Transform(self.m @ o.m, o.m_inv @ self.m_inv)
+
+    def inverse(self):
+        return Transform(self.m_inv, self.m)
+
+    @staticmethod
+    def identity():
+        return Transform(np.eye(4), np.eye(4))
+
+    @staticmethod
+    def translate(d):                # transform.rs:94-108
+        m = np.eye(4); m[:3, 3] = d
+        mi = np.eye(4); mi[:3, 3] = -np.asarray(d, dtype=np.float64)
+        return Transform(m, mi)
+
+    @staticmethod
+    def scale(x, y, z):              # transform.rs:110-124
+        return Transform(np.diag([x, y, z, 1.0]), np.diag([1.0 / x, 1.0 / y, 1.0 / z, 1.0]))
+
+    @staticmethod
+    def rotate(theta_deg, axis):     # transform.rs:198-226
+        a = np.asarray(axis, dtype=np.float64); a = a / np.linalg.norm(a)
+        s, c = math.sin(math.radians(theta_deg)), math.cos(math.radians(theta_deg))
+        m = np.eye(4)
+        m[0, :3] = [a[0] * a[0] + (1 - a[0] * a[0]) * c, a[0] * a[1] * (1 - c) - a[2] * s, a[0] * a[2] * (1 - c) + a[1] * s]
+        m[1, :3] = [a[0] * a[1] * (1 - c) + a[2] * s, a[1] * a[1] + (1 - a[1] * a[1]) * c, a[1] * a[2] * (1 - c) - a[0] * s]
+        m[2, :3] = [a[0] * a[2] * (1 - c) - a[1] * s, a[1] * a[2] * (1 - c) + a[0] * s, a[2] * a[2] + (1 - a[2] * a[2]) * c]
+        return Transform(m, m.T)
+
+    @staticmethod
+    def look_at(pos, look, up):      # transform.rs:272-307 -> camera_from_world
+        pos, look, up = (np.asarray(v, dtype=np.float64) for v in (pos, look, up))
+        d = look - pos; d /= np.linalg.norm(d)
+        right = np.cross(up / np.linalg.norm(up), d); right /= np.linalg.norm(right)
+        new_up = np.cross(d, right)
+        wfc = np.eye(4)
+        wfc[:3, 0], wfc[:3, 1], wfc[:3, 2], wfc[:3, 3] = right, new_up, d, pos
+        return Transform(np.linalg.inv(wfc), wfc)
+
+    @staticmethod
+    def perspective(fov_deg, n, f):  # transform.rs:309-321
+        persp = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, f / (f - n), -f * n / (f - n)], [0, 0, 1, 0]], dtype=np.float64)
+        inv_tan = 1.0 / math.tan(math.radians(fov_deg) / 2.0)
+        return Transform.scale(inv_tan, inv_tan, 1.0) * Transform(persp)
+
+    def swaps_handedness(self):      # transform.rs:331-340
+        return np.linalg.det(self.m[:3, :3]) < 0.0
+
+    def m32(self):
+        return self.m.astype(np.float32)
+
+    def apply_points_f32(self, p):
+        """apply_point_helper (transform.rs:753-767) evaluated in f32, left to right, unfused."""
+        m = self.m32(); p = np.asarray(p, dtype=np.float32)
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        out = np.empty_like(p)
+        for r in range(3):
+            out[:, r] = ((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3]
+        wp = ((m[3, 0] * x + m[3, 1] * y) + m[3, 2] * z) + m[3, 3]
+        if not np.all(wp == 1.0):
+            out = out / wp[:, None]
+        return out
+
+    def apply_normals_f32(self, n):
+        """apply_normal_helper (transform.rs:779-786): transpose of m_inv."""
+        mi = self.m_inv.astype(np.float32); n = np.asarray(n, dtype=np.float32)
+        x, y, z = n[:, 0], n[:, 1], n[:, 2]
+        out = np.empty_like(n)
+        for r in range(3):
+            out[:, r] = (mi[0, r] * x + mi[1, r] * y) + mi[2, r] * z
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Spectra (src/spectra/*.rs).  All sums are carried in f32 in the reference's order.
+# ----------------------------------------------------------------------------------------------
+_tables = None
+
+
+def tables():
+    global _tables
+    if _tables is None:
+        _tables = dict(np.load(_DATA))
+    return _tables
+
+
+def _pl_get(lams, vals, lam):
+    """PiecewiseLinearSpectrum::get (spectrum.rs:408-423) for an array of wavelengths, f32."""
+    lams = np.asarray(lams, dtype=np.float32); vals = np.asarray(vals, dtype=np.float32)
+    lam = np.asarray(lam, dtype=np.float32)
+    o = np.clip(np.searchsorted(lams, lam, side="right") - 1, 0, len(lams) - 2)
+    t = (lam - lams[o]) / (lams[o + 1] - lams[o])
+    out = vals[o] * (f32(1.0) - t) + vals[o + 1] * t
+    out[(lam < lams[0]) | (lam > lams[-1])] = 0.0
+    return out.astype(np.float32)
+
+
+def _interleaved(samples, normalize):
+    """PiecewiseLinearSpectrum::from_interleaved (spectrum.rs:324-370)."""
+    s = np.asarray(samples, dtype=np.float32)
+    lam, v = list(s[0::2]), list(s[1::2])
+    if lam[0] > LAMBDA_MIN:
+        lam.insert(0, f32(LAMBDA_MIN - 1)); v.insert(0, v[0])
+    if lam[-1] < LAMBDA_MAX:
+        lam.append(f32(LAMBDA_MAX + 1)); v.append(v[-1])
+    lam, v = np.asarray(lam, dtype=np.float32), np.asarray(v, dtype=np.float32)
+    if normalize:
+        ip = f32(0.0)
+        y = cie("Y")
+        g = _pl_get(lam, v, np.arange(LAMBDA_MIN, LAMBDA_MAX + 1, dtype=np.float32))
+        for i in range(LAMBDA_MAX - LAMBDA_MIN + 1):
+            ip = f32(ip + f32(g[i] * y[i]))
+        v = (v * f32(CIE_Y_INTEGRAL / ip)).astype(np.float32)
+    return lam, v
+
+
+def cie(which):
+    """Dense 360..830 CIE matching function (spectra/cie.rs:19-32: PiecewiseLinear over CIE_LAMBDA, densely sampled)."""
+    t = tables()
+    return _pl_get(t["CIE_LAMBDA"], t["CIE_" + which], np.arange(LAMBDA_MIN, LAMBDA_MAX + 1, dtype=np.float32))
+
+
+def named_spectrum(name):
+    """Spectrum::get_named_spectrum (spectrum.rs:111-133) -> ('pl', lambdas, values)."""
+    t = tables()
+    key, norm = {
+        "stdillum-D65": ("CIE_ILLUM_D6500", True), "illum-acesD60": ("ACES_ILLUM_D60", True),
+        "glass-BK7": ("GLASS_BK7_ETA_SAMPLES", False), "glass-BAF10": ("GLASS_BAF10_ETA_SAMPLES", False),
+        "glass-F11": ("GLASS_F11_ETA_SAMPLES", False),
+        "metal-Cu-eta": ("CU_ETA_SAMPLES", False), "metal-Cu-k": ("CU_K_SAMPLES", False),
+        "metal-Au-eta": ("AU_ETA_SAMPLES", False), "metal-Au-k": ("AU_K_SAMPLES", False),
+        "metal-Ag-eta": ("AG_ETA_SAMPLES", False), "metal-Ag-k": ("AG_K_SAMPLES", False),
+        "metal-Al-eta": ("AL_ETA_SAMPLES", False), "metal-Al-k": ("AL_K_SAMPLES", False),
+    }[name]
+    lam, v = _interleaved(t[key], norm)
+    return ("pl", lam, v)
+
+
+def spectrum_dense(spec):
+    """DenselySampledSpectrum::new (spectrum.rs:179-197): spectrum.get(lambda) for lambda in 360..=830."""
+    lam = np.arange(LAMBDA_MIN, LAMBDA_MAX + 1, dtype=np.float32)
+    kind = spec[0]
+    if kind == "const":
+        return np.full(lam.shape, f32(spec[1]), dtype=np.float32)
+    if kind == "pl":
+        return _pl_get(spec[1], spec[2], lam)
+    if kind == "dense":
+        return np.asarray(spec[1], dtype=np.float32)
+    raise ValueError(kind)
+
+
+def spectrum_to_photometric(spec):
+    """spectrum.rs:617-631, f32 running sum."""
+    d, y = spectrum_dense(spec), cie("Y")
+    acc = f32(0.0)
+    for i in range(len(d)):
+        acc = f32(acc + f32(y[i] * d[i]))
+    return acc
+
+
+def srgb_output_matrix():
+    """RgbColorSpace::new for sRGB (colorspace.rs:26-62,133-141) -> rgb_from_xyz; the cie1931 sensor
+    without white balance has xyz_from_sensor_rgb = identity (film.rs:825-844), so this is
+    output_rgb_from_sensor_rgb."""
+    ill = spectrum_dense(named_spectrum("stdillum-D65")).astype(np.float64)
+    X, Y, Z = (cie(c).astype(np.float64) for c in "XYZ")
+    w = np.array([np.sum(X * ill), np.sum(Y * ill), np.sum(Z * ill)]) / float(CIE_Y_INTEGRAL)
+
+    def xyY(xy):
+        return np.array([xy[0] / xy[1], 1.0, (1.0 - xy[0] - xy[1]) / xy[1]])
+    rgb = np.stack([xyY((0.64, 0.33)), xyY((0.3, 0.6)), xyY((0.15, 0.06))], axis=1)
+    c = np.linalg.inv(rgb) @ w
+    xyz_from_rgb = rgb @ np.diag(c)
+    return np.linalg.inv(xyz_from_rgb).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Scene builder
+# ----------------------------------------------------------------------------------------------
+class SceneDesc:
+    """Owns the numpy arrays behind an SgSceneDesc (keeps them alive for the C call)."""
+
+    def __init__(self):
+        self.arrays = {}
+        self.desc = ffi.SgSceneDesc()
+        self.meta = {}
+
+    def ptr(self):
+        return C.byref(self.desc)
+
+
+def _as_ptr(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class SceneBuilder:
+    def __init__(self, rendering_space="camera-world"):
+        self.rendering_space = rendering_space     # main.rs:66-67 default
+        self.spectra = []        # list of tuples
+        self._spec_cache = {}
+        self.materials = []
+        self.meshes = []         # dicts
+        self.extra_lights = []   # non-area lights in add order (scene.rs add_light)
+        self.camera = None
+        self.film = None
+        self.world_from_camera = None
+
+    # -- spectra / materials ---------------------------------------------------------------
+    def spectrum(self, spec, key=None):
+        if key is not None and key in self._spec_cache:
+            return self._spec_cache[key]
+        self.spectra.append(spec)
+        if key is not None:
+            self._spec_cache[key] = len(self.spectra) - 1
+        return len(self.spectra) - 1
+
+    def diffuse(self, reflectance):
+        """DiffuseMaterial::create (material.rs:259-283): displacement is ALWAYS Some(0.0)."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_DIFFUSE, spec_a=self.spectrum(reflectance), spec_b=-1,
+                                   flags=ffi.SG_MAT_HAS_DISPLACEMENT | ffi.SG_MAT_REMAP_ROUGHNESS, ur=0.0, vr=0.0))
+        return len(self.materials) - 1
+
+    def conductor(self, eta, k, roughness=0.0, remap=True):
+        """ConductorMaterial::create (material.rs:362-431), eta/k form."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_CONDUCTOR, spec_a=self.spectrum(eta), spec_b=self.spectrum(k),
+                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
+        return len(self.materials) - 1
+
+    def dielectric(self, eta, roughness=0.0, remap=True):
+        """DielectricMaterial::create (material.rs:538-581)."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_DIELECTRIC, spec_a=self.spectrum(eta), spec_b=-1,
+                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
+        return len(self.materials) - 1
+
+    # -- camera / film -----------------------------------------------------------------------
+    def set_camera(self, pos, look, up, fov, resolution, lens_radius=0.0, focal_distance=1e6, crop=None):
+        """PerspectiveCamera::create/new (camera.rs:839-963) + CameraTransform::new (:506-523) +
+        ProjectiveCameraBase::new (:595-642)."""
+        W, H = resolution
+        camera_from_world = Transform.look_at(pos, look, up)
+        world_from_camera = camera_from_world.inverse()
+        if self.rendering_space == "camera-world":
+            p_cam = world_from_camera.m[:3, 3]
+            world_from_render = Transform.translate(p_cam)
+        elif self.rendering_space == "world":
+            world_from_render = Transform.identity()
+        else:
+            world_from_render = world_from_camera
+        self.render_from_world = world_from_render.inverse()
+        render_from_camera = self.render_from_world * world_from_camera
+        frame = W / H
+        screen = (-frame, frame, -1.0, 1.0) if frame > 1.0 else (-1.0, 1.0, -1.0 / frame, 1.0 / frame)
+        screen_from_camera = Transform.perspective(fov, 1e-2, 1000.0)
+        ndc_from_screen = Transform.scale(1.0 / (screen[1] - screen[0]), 1.0 / (screen[3] - screen[2]), 1.0) * \
+            Transform.translate((-screen[0], -screen[3], 0.0))
+        raster_from_ndc = Transform.scale(W, -H, 1.0)
+        raster_from_screen = raster_from_ndc * ndc_from_screen
+        camera_from_raster = screen_from_camera.inverse() * raster_from_screen.inverse()
+        cfr = camera_from_raster
+
+        def app(p):
+            v = cfr.m @ np.array([p[0], p[1], p[2], 1.0]); return v[:3] / v[3]
+        dx_camera = app((1, 0, 0)) - app((0, 0, 0))
+        dy_camera = app((0, 1, 0)) - app((0, 0, 0))
+        cam = ffi.SgCamera()
+        cam.camera_from_raster[:] = camera_from_raster.m32().ravel().tolist()
+        cam.render_from_camera[:] = render_from_camera.m32().ravel().tolist()
+        cam.camera_from_render[:] = render_from_camera.m_inv.astype(np.float32).ravel().tolist()
+        cam.dx_camera[:] = dx_camera.astype(np.float32).tolist()
+        cam.dy_camera[:] = dy_camera.astype(np.float32).tolist()
+        cam.lens_radius = lens_radius; cam.focal_distance = focal_distance
+        cam.shutter_open = 0.0; cam.shutter_close = 1.0
+        self.camera = cam
+        film = ffi.SgFilm()
+        film.full_resolution[:] = [W, H]
+        film.pixel_bounds[:] = list(crop) if crop else [0, 0, W, H]
+        film.filter_radius[:] = [0.5, 0.5]                  # BoxFilter default radius (filter.rs:64-97)
+        film.imaging_ratio = 1.0                            # exposure_time * iso / 100 (film.rs:787)
+        film.max_component_value = float("inf")             # `maxcomponentvalue` default (film.rs RgbFilm::create)
+        film.output_rgb_from_sensor_rgb[:] = srgb_output_matrix().ravel().tolist()
+        self.film = film
+
+    # -- geometry ------------------------------------------------------------------------------
+    def add_mesh(self, p, indices, material, n=None, uv=None, area_light=None, reverse_orientation=False,
+                 object_from_world=None):
+        """Shape "trianglemesh" (triangle.rs:56-127 + mesh.rs:22-94).  `area_light` =
+        dict(L=spectrum tuple, scale=float, two_sided=bool) -> one DiffuseAreaLight per triangle
+        (scene.rs:609-622)."""
+        ctm = object_from_world if object_from_world is not None else Transform.identity()
+        rfo = self.render_from_world * ctm
+        p = rfo.apply_points_f32(np.asarray(p, dtype=np.float32).reshape(-1, 3))
+        if n is not None:
+            n = rfo.apply_normals_f32(np.asarray(n, dtype=np.float32).reshape(-1, 3))
+            if reverse_orientation:
+                n = -n
+        flags = 0
+        if n is not None: flags |= ffi.SG_MESH_HAS_N
+        if uv is not None: flags |= ffi.SG_MESH_HAS_UV
+        if reverse_orientation: flags |= ffi.SG_MESH_REVERSE_ORIENTATION
+        if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
+        self.meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 3), n=n,
+                                uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2),
+                                flags=flags, material=material, area_light=area_light))
+        return len(self.meshes) - 1
+
+    def add_point_light(self, pos, I, scale=1.0):
+        """PointLight::create (light.rs:421-453)."""
+        sc = f32(scale) / spectrum_to_photometric(I)
+        pr = self.render_from_world.apply_points_f32(np.asarray([pos], dtype=np.float32))[0]
+        self.extra_lights.append(dict(kind=ffi.SG_LIGHT_POINT, spectrum=self.spectrum(("dense", spectrum_dense(I))),
+                                      scale=float(sc), pos=pr))
+
+    def add_uniform_infinite_light(self, L, scale=1.0):
+        """Light::create "infinite" with a constant L (light.rs:697-728)."""
+        sc = f32(scale) / spectrum_to_photometric(L)
+        self.extra_lights.append(dict(kind=ffi.SG_LIGHT_UNIFORM_INFINITE, spectrum=self.spectrum(("dense", spectrum_dense(L))),
+                                      scale=float(sc), pos=np.zeros(3, np.float32)))
+
+    # -- flatten ---------------------------------------------------------------------------------
+    def build(self):
+        out = SceneDesc()
+        A = out.arrays
+        host = ffi.load_host_library()
+        # spectra pool
+        pool, spec_rows = [], np.zeros(len(self.spectra), dtype=np.dtype(ffi.SgSpectrum))
+        off = 0
+        recs = []
+        for sp in self.spectra:
+            r = ffi.SgSpectrum()
+            if sp[0] == "const":
+                r.kind, r.c = ffi.SG_SPECTRUM_CONSTANT, float(sp[1])
+            elif sp[0] == "dense":
+                v = np.asarray(sp[1], dtype=np.float32)
+                r.kind, r.n, r.lambda_min, r.off_a = ffi.SG_SPECTRUM_DENSE, len(v), LAMBDA_MIN, off
+                pool.append(v); off += len(v)
+            elif sp[0] == "pl":
+                lam, v = np.asarray(sp[1], dtype=np.float32), np.asarray(sp[2], dtype=np.float32)
+                r.kind, r.n, r.off_a, r.off_b = ffi.SG_SPECTRUM_PIECEWISE_LINEAR, len(lam), off, off + len(lam)
+                pool.extend([lam, v]); off += 2 * len(lam)
+            else:
+                raise ValueError(sp[0])
+            recs.append(r)
+        # film sensor spectra appended last
+        film_ids = []
+        for cname in "XYZ":
+            v = cie(cname)
+            r = ffi.SgSpectrum(); r.kind, r.n, r.lambda_min, r.off_a = ffi.SG_SPECTRUM_DENSE, len(v), LAMBDA_MIN, off
+            pool.append(v); off += len(v); recs.append(r); film_ids.append(len(recs) - 1)
+        # lights: non-area first, then one per emissive triangle in shape order (scene.rs:532-632)
+        lights = []
+        for el in self.extra_lights:
+            L = ffi.SgLight(); L.kind = el["kind"]; L.spectrum = el["spectrum"]; L.scale = el["scale"]
+            L.pos[:] = [float(x) for x in el["pos"]]
+            lights.append(L)
+        mesh_light_base = {}
+        for mi, m in enumerate(self.meshes):
+            al = m["area_light"]
+            if al is None:
+                continue
+            sc = f32(al.get("scale", 1.0)) / spectrum_to_photometric(al["L"])
+            dense = spectrum_dense(al["L"])
+            r = ffi.SgSpectrum(); r.kind, r.n, r.lambda_min, r.off_a = ffi.SG_SPECTRUM_DENSE, len(dense), LAMBDA_MIN, off
+            pool.append(dense); off += len(dense); recs.append(r); sid = len(recs) - 1
+            mesh_light_base[mi] = len(lights)
+            P, I = m["p"], m["idx"]
+            e1 = P[I[:, 1]] - P[I[:, 0]]; e2 = P[I[:, 2]] - P[I[:, 0]]
+            area = 0.5 * np.linalg.norm(np.cross(e1.astype(np.float64), e2.astype(np.float64)), axis=1)
+            for t in range(len(I)):
+                L = ffi.SgLight(); L.kind = ffi.SG_LIGHT_DIFFUSE_AREA; L.spectrum = sid; L.scale = float(sc)
+                L.two_sided = 1 if al.get("two_sided", False) else 0
+                L.mesh, L.tri, L.area = mi, t, float(area[t])
+                lights.append(L)
+        # geometry arrays
+        any_n = any(m["n"] is not None for m in self.meshes)
+        any_uv = any(m["uv"] is not None for m in self.meshes)
+        nv = sum(len(m["p"]) for m in self.meshes); nt = sum(len(m["idx"]) for m in self.meshes)
+        A["p"] = np.empty((nv, 3), np.float32); A["idx"] = np.empty((nt, 3), np.uint32)
+        A["n"] = np.zeros((nv, 3), np.float32) if any_n else None
+        A["uv"] = np.zeros((nv, 2), np.float32) if any_uv else None
+        mesh_rows = (ffi.SgMesh * len(self.meshes))()
+        prim_in = np.empty((nt, 4), np.int64)       # mesh, tri, material, light (input order)
+        gidx = np.empty((nt, 3), np.uint32)
+        v0 = t0 = 0
+        for mi, m in enumerate(self.meshes):
+            k, t = len(m["p"]), len(m["idx"])
+            A["p"][v0:v0 + k] = m["p"]; A["idx"][t0:t0 + t] = m["idx"]; gidx[t0:t0 + t] = m["idx"] + v0
+            if m["n"] is not None: A["n"][v0:v0 + k] = m["n"]
+            if m["uv"] is not None: A["uv"][v0:v0 + k] = m["uv"]
+            mr = mesh_rows[mi]
+            mr.first_index, mr.first_vertex, mr.n_triangles, mr.n_vertices, mr.flags = 3 * t0, v0, t, k, m["flags"]
+            prim_in[t0:t0 + t, 0] = mi; prim_in[t0:t0 + t, 1] = np.arange(t); prim_in[t0:t0 + t, 2] = m["material"]
+            prim_in[t0:t0 + t, 3] = (mesh_light_base[mi] + np.arange(t)) if mi in mesh_light_base else -1
+            v0 += k; t0 += t
+        # BVH over Triangle::bounds in input order (aggregate.rs:207-290)
+        bounds = np.empty((nt, 6), np.float32)
+        host.sh_triangle_bounds(nt, gidx.ctypes.data, A["p"].ctypes.data, bounds.ctypes.data)
+        nodes = np.zeros(max(2 * nt - 1, 1), dtype=np.dtype(ffi.SgBvhNode))
+        order = np.empty(nt, np.uint32)
+        n_nodes = host.sh_bvh_build(nt, bounds.ctypes.data, nodes.ctypes.data, order.ctypes.data)
+        if n_nodes <= 0:
+            raise ffi.ShimmerGpuError("sh_bvh_build failed")
+        A["nodes"] = nodes[:n_nodes].copy(); A["order"] = order; A["prim_bounds"] = bounds
+        po = prim_in[order]
+        prims = np.zeros(nt, dtype=np.dtype(ffi.SgPrimitive))
+        prims["mesh"], prims["tri"], prims["material"], prims["light"] = po[:, 0], po[:, 1], po[:, 2], po[:, 3]
+        A["prims"] = prims
+        # scene bounds -> infinite-light preprocess (light.rs:797-802, bounding_box.rs:460-468)
+        root = A["nodes"][0]
+        bmin, bmax = np.array(root["bmin"], np.float32), np.array(root["bmax"], np.float32)
+        center = (bmin + bmax) / f32(2.0)
+        inside = bool(np.all(center >= bmin) and np.all(center <= bmax))
+        radius = float(np.sqrt(np.sum((center - bmax).astype(np.float32) ** 2, dtype=np.float32))) if inside else 0.0
+        for L in lights:
+            if L.kind == ffi.SG_LIGHT_UNIFORM_INFINITE:
+                L.scene_center[:] = center.tolist(); L.scene_radius = radius
+        A["pool"] = np.concatenate(pool).astype(np.float32) if pool else np.zeros(1, np.float32)
+        A["spectra"] = (ffi.SgSpectrum * len(recs))(*recs)
+        mats = (ffi.SgMaterial * max(len(self.materials), 1))()
+        for i, m in enumerate(self.materials):
+            mats[i].kind, mats[i].spec_a, mats[i].spec_b, mats[i].flags = m["kind"], m["spec_a"], m["spec_b"], m["flags"]
+            mats[i].u_roughness, mats[i].v_roughness, mats[i].displacement = m["ur"], m["vr"], 0.0
+        A["materials"] = mats
+        A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
+        A["meshes"] = mesh_rows
+        d = out.desc
+        d.abi_version = ffi.SG_ABI_VERSION
+        d.n_nodes = n_nodes; d.nodes = _as_ptr(A["nodes"], ffi.SgBvhNode)
+        d.n_primitives = nt; d.primitives = _as_ptr(A["prims"], ffi.SgPrimitive)
+        d.n_meshes = len(self.meshes); d.meshes = A["meshes"]
+        d.n_indices = 3 * nt; d.indices = _as_ptr(A["idx"], C.c_uint32)
+        d.n_vertices = nv; d.p = _as_ptr(A["p"], C.c_float)
+        d.n = _as_ptr(A["n"], C.c_float) if any_n else None
+        d.uv = _as_ptr(A["uv"], C.c_float) if any_uv else None
+        d.s = None
+        d.n_spectra = len(recs); d.spectra = A["spectra"]
+        d.n_pool = len(A["pool"]); d.spectrum_pool = _as_ptr(A["pool"], C.c_float)
+        d.n_materials = len(self.materials); d.materials = A["materials"]
+        d.n_lights = len(lights); d.lights = A["lights"]
+        d.camera = self.camera
+        self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
+        d.film = self.film
+        out.meta = dict(n_triangles=nt, n_nodes=int(n_nodes), n_lights=len(lights),
+                        resolution=tuple(self.film.full_resolution), window=tuple(self.film.pixel_bounds))
+        return out

@@ -1,0 +1,213 @@
+"""Deterministic generators for the benchmark configurations of BASELINE.json (C1..C5) and a few
+tiny parity scenes.  Every generator is closed-form (no files, no RNG state outside a fixed seed)
+so the oracle, the CUDA path and -- on a machine with a Rust toolchain -- real shimmer render
+the same geometry.  Materials use `"spectrum"`-typed parameters only (never "rgb"), so the
+hot path never needs the rgb2spec tables that are missing from the reference checkout
+(SURVEY.md 8c).
+"""
+import math
+
+import numpy as np
+
+from . import host
+from .host import SceneBuilder, Transform, named_spectrum
+
+f32 = np.float32
+
+
+def _quad(a, b, c, d):
+    """Two triangles (a,b,c), (a,c,d)."""
+    return np.array([a, b, c, d], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+def _pl(pairs):
+    lam = np.array([p[0] for p in pairs], np.float32); v = np.array([p[1] for p in pairs], np.float32)
+    return ("pl", lam, v)
+
+
+# Smooth synthetic stand-ins for the measured Cornell-box spectra (tabulated every 20 nm so they
+# become PiecewiseLinearSpectrum in shimmer: "spectrum reflectance" [ l0 v0 l1 v1 ... ]).
+def _white():
+    return _pl([(l, 0.72 + 0.04 * math.sin((l - 400) / 300.0 * math.pi)) for l in range(360, 831, 20)])
+
+
+def _red():
+    return _pl([(l, 0.045 + 0.58 / (1.0 + math.exp(-(l - 598.0) / 9.0))) for l in range(360, 831, 10)])
+
+
+def _green():
+    return _pl([(l, 0.06 + 0.42 * math.exp(-((l - 535.0) / 42.0) ** 2)) for l in range(360, 831, 10)])
+
+
+def _light_spectrum():
+    # the classic Cornell light samples, extended flat to the visible range ends
+    return _pl([(360, 0.0), (400, 0.0), (500, 8.0), (600, 15.6), (700, 18.4), (830, 18.4)])
+
+
+def cornell_geometry():
+    """Classic 555-unit Cornell layout: 5 walls, short + tall block, ceiling light quad."""
+    quads = {}
+    quads["floor"] = _quad((552.8, 0, 0), (0, 0, 0), (0, 0, 559.2), (549.6, 0, 559.2))
+    quads["ceiling"] = _quad((556, 548.8, 0), (556, 548.8, 559.2), (0, 548.8, 559.2), (0, 548.8, 0))
+    quads["back"] = _quad((549.6, 0, 559.2), (0, 0, 559.2), (0, 548.8, 559.2), (556, 548.8, 559.2))
+    quads["right"] = _quad((0, 0, 559.2), (0, 0, 0), (0, 548.8, 0), (0, 548.8, 559.2))
+    quads["left"] = _quad((552.8, 0, 0), (549.6, 0, 559.2), (556, 548.8, 559.2), (556, 548.8, 0))
+    # light sits 0.5 below the ceiling so no primary ray sees a t-tie between the two planes
+    quads["light"] = _quad((343, 548.3, 227), (343, 548.3, 332), (213, 548.3, 332), (213, 548.3, 227))
+    short = [((130, 165, 65), (82, 165, 225), (240, 165, 272), (290, 165, 114)),
+             ((290, 0, 114), (290, 165, 114), (240, 165, 272), (240, 0, 272)),
+             ((130, 0, 65), (130, 165, 65), (290, 165, 114), (290, 0, 114)),
+             ((82, 0, 225), (82, 165, 225), (130, 165, 65), (130, 0, 65)),
+             ((240, 0, 272), (240, 165, 272), (82, 165, 225), (82, 0, 225))]
+    tall = [((423, 330, 247), (265, 330, 296), (314, 330, 456), (472, 330, 406)),
+            ((423, 0, 247), (423, 330, 247), (472, 330, 406), (472, 0, 406)),
+            ((472, 0, 406), (472, 330, 406), (314, 330, 456), (314, 0, 456)),
+            ((314, 0, 456), (314, 330, 456), (265, 330, 296), (265, 0, 296)),
+            ((265, 0, 296), (265, 330, 296), (423, 330, 247), (423, 0, 247))]
+
+    def box(faces):
+        P, I = [], []
+        for f in faces:
+            p, i = _quad(*f); I.append(i + len(P) * 4); P.append(p)
+        return np.concatenate(P), np.concatenate(I)
+    quads["short"] = box(short)
+    quads["tall"] = box(tall)
+    return quads
+
+
+def cornell_box(resolution=(512, 512), crop=None, light_scale=20.0, add_to=None):
+    """C1: synthetic Cornell box, diffuse + one two-triangle area light, fov 39.3 (BASELINE.json configs[0])."""
+    b = add_to or SceneBuilder()
+    if add_to is None:
+        b.set_camera(pos=(278, 273, -800), look=(278, 273, 0), up=(0, 1, 0),
+                     fov=2.0 * math.degrees(math.atan(0.0125 / 0.035)), resolution=resolution, crop=crop)
+    white, red, green = b.diffuse(_white()), b.diffuse(_red()), b.diffuse(_green())
+    g = cornell_geometry()
+    for name, mat in (("floor", white), ("ceiling", white), ("back", white), ("right", green), ("left", red),
+                      ("short", white), ("tall", white)):
+        b.add_mesh(g[name][0], g[name][1], mat)
+    b.add_mesh(g["light"][0], g["light"][1], white,
+               area_light=dict(L=_light_spectrum(), scale=light_scale, two_sided=False))
+    return b
+
+
+def displaced_sphere(n_theta, n_phi, center, radius, amp=0.06, freq=7.0):
+    """Lat-long tessellated sphere with a smooth radial displacement, vertices from closed-form
+    trig in f64 (written as f32).  2*n_phi*(n_theta-1) triangles.  Poles are single vertices."""
+    th = np.linspace(0.0, math.pi, n_theta + 1)[1:-1]            # interior rings
+    ph = np.linspace(0.0, 2.0 * math.pi, n_phi, endpoint=False)
+    T, Pp = np.meshgrid(th, ph, indexing="ij")
+    r = radius * (1.0 + amp * np.sin(freq * T + 0.3) * np.cos(freq * Pp * 0.5 + 1.1) + 0.5 * amp * np.sin(3.0 * freq * Pp + T))
+    x = r * np.sin(T) * np.cos(Pp); y = r * np.cos(T); z = r * np.sin(T) * np.sin(Pp)
+    ring = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    top = np.array([[0.0, radius, 0.0]]); bot = np.array([[0.0, -radius, 0.0]])
+    P = np.concatenate([top, ring, bot]) + np.asarray(center, dtype=np.float64)
+    nr = n_theta - 1
+    idx = []
+    j = np.arange(n_phi); jn = (j + 1) % n_phi
+    idx.append(np.stack([np.zeros_like(j), 1 + jn, 1 + j], axis=1))                     # top cap
+    for i in range(nr - 1):
+        a = 1 + i * n_phi + j; bq = 1 + i * n_phi + jn; c = 1 + (i + 1) * n_phi + j; d = 1 + (i + 1) * n_phi + jn
+        idx.append(np.stack([a, bq, d], axis=1)); idx.append(np.stack([a, d, c], axis=1))
+    last = 1 + (nr - 1) * n_phi
+    idx.append(np.stack([np.full_like(j, len(P) - 1), last + j, last + jn], axis=1))   # bottom cap
+    I = np.concatenate(idx).astype(np.uint32)
+    return P.astype(np.float32), I
+
+
+def mesh_scene(n_theta=708, n_phi=708, resolution=(1024, 1024), crop=None, roughness=0.1):
+    """C2: ~1 M-triangle displaced sphere split half diffuse / half conductor (Cu eta/k, roughness
+    0.1) over a ground quad, one area-light quad (BASELINE.json configs[1])."""
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 1.6, -4.2), look=(0.0, 0.9, 0.0), up=(0, 1, 0), fov=38.0, resolution=resolution, crop=crop)
+    white = b.diffuse(_white()); clay = b.diffuse(_red())
+    copper = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=roughness)
+    P, I = displaced_sphere(n_theta, n_phi, center=(0.0, 1.0, 0.0), radius=1.0)
+    # split by triangle centroid x: left half diffuse, right half conductor (two meshes share vertices by copy)
+    cx = P[I].mean(axis=1)[:, 0]
+    for mask, mat in ((cx < 0.0, clay), (cx >= 0.0, copper)):
+        sub = I[mask]
+        used, inv = np.unique(sub.ravel(), return_inverse=True)
+        b.add_mesh(P[used], inv.reshape(-1, 3).astype(np.uint32), mat)
+    gp, gi = _quad((-6, -0.06, -6), (-6, -0.06, 6), (6, -0.06, 6), (6, -0.06, -6))
+    b.add_mesh(gp, gi, white)
+    lp, li = _quad((-1.5, 4.0, -1.5), (1.5, 4.0, -1.5), (1.5, 4.0, 1.5), (-1.5, 4.0, 1.5))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=12.0, two_sided=False))
+    return b
+
+
+def glass_scene(n_theta=128, n_phi=256, resolution=(1024, 1024), crop=None):
+    """C3: glass prism + tessellated glass sphere with a NON-constant tabulated BK7 eta (-> wavelength
+    termination, material.rs:609-620), small bright area light (BASELINE.json configs[2])."""
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 1.4, -4.5), look=(0.0, 0.7, 0.0), up=(0, 1, 0), fov=36.0, resolution=resolution, crop=crop)
+    white = b.diffuse(_white())
+    glass = b.dielectric(named_spectrum("glass-BK7"))
+    P, I = displaced_sphere(n_theta, n_phi, center=(0.9, 0.75, 0.2), radius=0.75, amp=0.0)
+    b.add_mesh(P, I, glass)
+    # triangular prism along z
+    a, bb, c = (-1.6, 0.0, -0.6), (-0.4, 0.0, -0.6), (-1.0, 1.04, -0.6)
+    a2, b2, c2 = (-1.6, 0.0, 0.6), (-0.4, 0.0, 0.6), (-1.0, 1.04, 0.6)
+    PP = np.array([a, bb, c, a2, b2, c2], np.float32)
+    II = np.array([[0, 2, 1], [3, 4, 5], [0, 1, 4], [0, 4, 3], [1, 2, 5], [1, 5, 4], [2, 0, 3], [2, 3, 5]], np.uint32)
+    b.add_mesh(PP, II, glass, object_from_world=Transform.translate((0.0, 0.002, 0.0)))
+    gp, gi = _quad((-6, 0.0, -6), (-6, 0.0, 6), (6, 0.0, 6), (6, 0.0, -6))
+    b.add_mesh(gp, gi, white)
+    wp, wi = _quad((-6, 0.0, 3), (-6, 6, 3), (6, 6, 3), (6, 0.0, 3))
+    b.add_mesh(wp, wi, white)
+    lp, li = _quad((-2.6, 3.0, -1.0), (-2.2, 3.0, -1.0), (-2.2, 3.0, -0.6), (-2.6, 3.0, -0.6))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=900.0, two_sided=False))
+    return b
+
+
+def composite_scene(n_theta=708, n_phi=708, resolution=(3840, 2160), crop=None):
+    """C5: the Cornell room enclosing the C2 mesh (BASELINE.json configs[4])."""
+    b = SceneBuilder()
+    b.set_camera(pos=(278, 273, -800), look=(278, 273, 0), up=(0, 1, 0),
+                 fov=2.0 * math.degrees(math.atan(0.0125 / 0.035)) * 1.35, resolution=resolution, crop=crop)
+    cornell_box(add_to=b)
+    copper = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.1)
+    P, I = displaced_sphere(n_theta, n_phi, center=(0.0, 0.0, 0.0), radius=1.0)
+    xf = Transform.translate((300.0, 420.0, 150.0)) * Transform.scale(70.0, 70.0, 70.0)
+    b.add_mesh(P, I, copper, object_from_world=xf)
+    return b
+
+
+def tiny_scene(kind="diffuse", resolution=(32, 32)):
+    """A few dozen triangles exercising one material each; used by the fast parity tests."""
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
+    white = b.diffuse(_white())
+    if kind == "diffuse":
+        mat = b.diffuse(_green())
+    elif kind == "conductor":
+        mat = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.1)
+    elif kind == "mirror":
+        mat = b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0)
+    elif kind == "glass":
+        mat = b.dielectric(named_spectrum("glass-BK7"))
+    elif kind == "roughglass":
+        mat = b.dielectric(("const", 1.5), roughness=0.2)
+    else:
+        raise ValueError(kind)
+    P, I = displaced_sphere(12, 16, center=(0.0, 0.6, 0.0), radius=0.6, amp=0.0)
+    b.add_mesh(P, I, mat)
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, white)
+    lp, li = _quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    if kind == "mirror":
+        b.add_uniform_infinite_light(("const", 1.0), scale=0.3)
+    return b
+
+
+CONFIGS = {
+    "cornell": dict(builder=cornell_box, resolution=(512, 512), spp=16, max_depth=5,
+                    desc="C1 synthetic Cornell box, 32 triangles, diffuse + area light, 512x512, 16 spp"),
+    "mesh1m": dict(builder=mesh_scene, resolution=(1024, 1024), spp=64, max_depth=5,
+                   desc="C2 procedural ~1M-triangle displaced sphere, diffuse + Cu conductor, 1024x1024, 64 spp"),
+    "glass": dict(builder=glass_scene, resolution=(1024, 1024), spp=256, max_depth=5,
+                  desc="C3 glass dispersion (tabulated BK7 eta), 1024x1024, 256 spp"),
+    "composite": dict(builder=composite_scene, resolution=(3840, 2160), spp=1024, max_depth=5,
+                      desc="C5 Cornell + 1M-triangle mesh composite, 3840x2160, 1024 spp"),
+}

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the native libraries in-tree (nvcc cross-compiles without a GPU)."""
+    from shimmer_b200 import build
+    build.build_all()
+    import orc
+    orc.lib()
+
+
+@pytest.fixture(scope="session")
+def cornell64():
+    from shimmer_b200 import scenes
+    return scenes.cornell_box(resolution=(64, 64)).build()

@@ -1,0 +1,107 @@
+"""ctypes loader for the CPU oracle (oracle/_build/liborc.so).  TEST INFRASTRUCTURE: importable only
+from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+ORC_LIB = os.path.join(ORC_DIR, "_build", "liborc.so")
+
+import sys
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from shimmer_b200 import ffi  # noqa: E402  (struct definitions only)
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORC_DIR], check=True)
+    return ORC_LIB
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".cpp", ".h"))]
+    if not os.path.exists(ORC_LIB) or any(os.path.getmtime(s) > os.path.getmtime(ORC_LIB) for s in srcs):
+        build()
+    L = C.CDLL(ORC_LIB)
+    vp = C.c_void_p
+    L.orc_header.restype = C.c_char_p
+    L.orc_sampler_fill.argtypes = [C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_int64, vp]
+    L.orc_rng_u64.argtypes = [C.c_uint64, C.c_int, vp, C.c_int64, vp, vp]
+    L.orc_bvh_build.argtypes = [C.c_int64, vp, vp, vp]; L.orc_bvh_build.restype = C.c_int64
+    L.orc_trace.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, vp, vp, C.c_int]
+    L.orc_camera_rays.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.orc_render.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int]; L.orc_render.restype = C.c_double
+    L.orc_film_develop.argtypes = [vp, vp, C.c_int64, vp]
+    for name, nargs in (("orc_difference_of_products", 4), ("orc_lerp", 3), ("orc_next_float_up", 1), ("orc_next_float_down", 1),
+                        ("orc_visible_wavelengths_pdf", 1), ("orc_sample_visible_wavelengths", 1), ("orc_fresnel_dielectric", 2),
+                        ("orc_fresnel_complex", 3), ("orc_blackbody", 2)):
+        f = getattr(L, name); f.argtypes = [C.c_float] * nargs; f.restype = C.c_float
+    L.orc_gamma.argtypes = [C.c_int]; L.orc_gamma.restype = C.c_float
+    L.orc_tr_d.argtypes = [C.c_float, C.c_float, vp]; L.orc_tr_d.restype = C.c_float
+    L.orc_tr_g.argtypes = [C.c_float, C.c_float, vp, vp]; L.orc_tr_g.restype = C.c_float
+    L.orc_spectrum_get.argtypes = [vp, C.c_int, C.c_float]; L.orc_spectrum_get.restype = C.c_float
+    L.orc_spectrum_sample.argtypes = [vp, C.c_int, vp, vp]
+    L.orc_dielectric_sample_f.argtypes = [C.c_float, C.c_float, C.c_float, vp, C.c_float, vp, vp]; L.orc_dielectric_sample_f.restype = C.c_int
+    L.orc_bxdf_eval.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.orc_bxdf_sample.argtypes = [C.c_int, vp, vp, C.c_float, vp, vp]; L.orc_bxdf_sample.restype = C.c_int
+    L.orc_tri_intersect.argtypes = [vp, vp, C.c_float, vp, vp]; L.orc_tri_intersect.restype = C.c_int
+    L.orc_bounds_intersect.argtypes = [vp, vp, vp, vp, C.c_float]; L.orc_bounds_intersect.restype = C.c_int
+    L.orc_light_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]; L.orc_light_sample.restype = C.c_int
+    L.orc_light_pdf.argtypes = [vp, C.c_int, vp, vp, vp, vp]; L.orc_light_pdf.restype = C.c_float
+    _lib = L
+    return L
+
+
+def fa(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def make_params(seed=0, spp=4, sample_range=None, max_depth=5, regularize=False, flags=0):
+    p = ffi.SgRenderParams()
+    p.seed = seed; p.samples_per_pixel = spp
+    p.sample_begin, p.sample_end = sample_range if sample_range else (0, spp)
+    p.max_depth = max_depth; p.regularize = int(regularize); p.option_flags = flags
+    return p
+
+
+def render(scene, params, n_threads=None, stream_mode=0):
+    """Returns (film (H*W,4) f64, stats, seconds)."""
+    x0, y0, x1, y1 = scene.desc.film.pixel_bounds
+    film = np.zeros(((y1 - y0) * (x1 - x0), 4), np.float64)
+    st = ffi.SgStats()
+    nt = n_threads or os.cpu_count() or 1
+    secs = lib().orc_render(scene.ptr(), C.byref(params), film.ctypes.data, C.byref(st), nt, stream_mode)
+    return film, st, secs
+
+
+def trace(scene, o, d, t_max, any_hit=False, n_threads=None):
+    o, d, t_max = fa(o), fa(d), fa(t_max)
+    n = len(t_max)
+    out = np.zeros(n, dtype=np.dtype(ffi.SgHit))
+    st = ffi.SgStats()
+    lib().orc_trace(scene.ptr(), n, o.ctypes.data, d.ctypes.data, t_max.ctypes.data, int(any_hit), out.ctypes.data,
+                    C.byref(st), n_threads or os.cpu_count() or 1)
+    return out, st
+
+
+def camera_rays(scene, params, pixel_xy, sample_index):
+    pixel_xy = np.ascontiguousarray(pixel_xy, np.int32); sample_index = np.ascontiguousarray(sample_index, np.int32)
+    n = len(sample_index)
+    rays = np.zeros((n, 6), np.float32); lam = np.zeros((n, 8), np.float32)
+    lib().orc_camera_rays(scene.ptr(), C.byref(params), n, pixel_xy.ctypes.data, sample_index.ctypes.data,
+                          rays.ctypes.data, lam.ctypes.data)
+    return rays, lam
+
+
+def develop(scene, film):
+    out = np.zeros((len(film), 3), np.float32)
+    lib().orc_film_develop(scene.ptr(), np.ascontiguousarray(film).ctypes.data, len(film), out.ctypes.data)
+    return out

@@ -1,0 +1,220 @@
+"""GPU parity tests proper: every call goes through the C ABI (libshimmer_gpu.so) and is compared with the
+CPU oracle on the same seeded inputs.  Bars (BASELINE.json north_star):
+  * bit-exact: RNG streams; first-hit primitive index and hit/miss on the ray-cast sets
+  * hit t, barycentrics, geometric normal: <= 1e-5 relative (observed: bit-exact)
+  * films: per-sample deterministic streams are shared, so films agree to float round-off except for the
+    rare path whose control flow flips on a libm last-bit difference (atanh/cosh/sin/cos/atan2/asin)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from shimmer_b200 import Options, create_integrator, ffi, scenes
+from shimmer_b200.integrator import sampler_fill
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def cornell_gpu(cornell64):
+    integ = create_integrator("wavefront", {"maxdepth": 5}, cornell64, {"pixelsamples": 16})
+    yield integ
+    integ.close()
+
+
+def test_native_library_is_the_one_running():
+    import ctypes
+    lib = ffi.load_library()
+    assert isinstance(lib, ctypes.CDLL) and os.path.samefile(lib._name, ffi.LIB_PATH)
+
+
+# ---- bit-exact: sampler / RNG ---------------------------------------------------------------------
+def test_rng_stream_bit_exact():
+    ref = np.zeros(4096, np.float32)
+    orc.lib().orc_sampler_fill(0, 1, 0, 0, len(ref), ref.ctypes.data)
+    got = sampler_fill(0, len(ref), raw=True)
+    assert got.tobytes() == ref.tobytes()
+    assert got[:4].tolist() == [0.3245752453804016, 0.38223928213119507, 0.3596171736717224, 0.0114554762840271]
+    for seed, pix, smp in ((0, 0, 0), (7, 123456, 3), (2 ** 63 + 5, 4095 * 4096, 1023)):
+        orc.lib().orc_sampler_fill(seed, 0, pix, smp, 256, ref.ctypes.data)
+        assert sampler_fill(seed, 256, pix, smp).tobytes() == ref[:256].tobytes()
+
+
+def test_camera_rays_and_wavelengths(cornell_gpu, cornell64):
+    rng = np.random.default_rng(0)
+    n = 2000
+    xy = rng.integers(0, 64, size=(n, 2)).astype(np.int32); si = rng.integers(0, 64, size=n).astype(np.int32)
+    opts = Options(seed=9)
+    rays, lam = cornell_gpu.camera_rays(opts, xy, si)
+    p = orc.make_params(seed=9, spp=16)
+    r_ref, l_ref = orc.camera_rays(cornell64, p, xy, si)
+    assert np.array_equal(rays, r_ref)                      # pure IEEE arithmetic: bit-exact
+    assert np.allclose(lam, l_ref, rtol=2e-6, atol=0)       # atanh / cosh come from different libms
+    opts2 = Options(seed=9, disable_pixel_jitter=True, disable_wavelength_jitter=True)
+    rays2, lam2 = cornell_gpu.camera_rays(opts2, xy, si)
+    p2 = orc.make_params(seed=9, spp=16, flags=ffi.SG_OPT_DISABLE_PIXEL_JITTER | ffi.SG_OPT_DISABLE_WAVELENGTH_JITTER)
+    r2, l2 = orc.camera_rays(cornell64, p2, xy, si)
+    assert np.array_equal(rays2, r2) and np.allclose(lam2, l2, rtol=2e-6)
+
+
+# ---- bit-exact: first hit ------------------------------------------------------------------------------
+def _ray_set(sc, n, seed):
+    """camera-like rays + uniformly random origin/direction pairs inside the scene bounds + adversarial rays
+    (axis-parallel directions with zero components -> +-inf inv_dir, rays through shared edges/vertices)."""
+    rng = np.random.default_rng(seed)
+    root = sc.arrays["nodes"][0]
+    lo, hi = np.array(root["bmin"]), np.array(root["bmax"])
+    o = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 8
+    axes = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], (k, 1)).astype(np.float32)
+    d[:k] = axes
+    # aim a batch of rays exactly at mesh vertices and edge midpoints
+    P = sc.arrays["p"]; I = sc.arrays["idx"]
+    tri = I[rng.integers(0, len(I), k)]
+    base = np.array([m.first_vertex for m in sc.arrays["meshes"]])
+    mesh_of_tri = np.searchsorted(np.cumsum([m.n_triangles for m in sc.arrays["meshes"]]), rng.integers(0, len(I), k), side="right")
+    tri_ids = rng.integers(0, len(I), k)
+    first_tri = np.concatenate([[0], np.cumsum([m.n_triangles for m in sc.arrays["meshes"]])])
+    mesh_of_tri = np.searchsorted(first_tri, tri_ids, side="right") - 1
+    v = I[tri_ids] + base[mesh_of_tri][:, None]
+    target = np.where(rng.random((k, 1)) < 0.5, P[v[:, 0]], (P[v[:, 0]] + P[v[:, 1]]) * np.float32(0.5)).astype(np.float32)
+    d[k:2 * k] = target - o[k:2 * k]
+    return o, d.astype(np.float32)
+
+
+def _assert_hits_equal(got, ref):
+    assert np.array_equal(got["prim"], ref["prim"])                       # bit-exact hit/miss + primitive index
+    hit = ref["prim"] >= 0
+    for f in ("t", "b0", "b1", "b2"):
+        assert np.allclose(got[f][hit], ref[f][hit], rtol=1e-5, atol=0)
+    assert np.allclose(got["ng"][hit], ref["ng"][hit], rtol=1e-5, atol=1e-7)
+    exact = sum(np.array_equal(got[f], ref[f]) for f in ("t", "b0", "b1", "b2"))
+    return exact
+
+
+def test_raycast_golden_fixture(cornell_gpu):
+    g = np.load(os.path.join(GOLDEN, "cornell_raycast.npz"))
+    got, st = cornell_gpu.trace(g["o"], g["d"], np.full(len(g["o"]), np.inf, np.float32), want_stats=True)
+    assert np.array_equal(got["prim"], g["prim"])
+    hit = g["prim"] >= 0
+    assert np.array_equal(got["t"][hit], g["t"][hit])
+    assert np.array_equal(np.stack([got["b0"], got["b1"], got["b2"]], 1)[hit], g["b"][hit])
+    assert np.array_equal(got["ng"][hit], g["ng"][hit])
+    # traversal order is the reference's: identical visit counts
+    assert st.nodes_visited == int(g["nodes"]) and st.tris_tested == int(g["tris"])
+
+
+@pytest.mark.parametrize("name", ["cornell", "tiny", "mesh"])
+def test_raycast_parity_closest_and_any(name, cornell64):
+    sc = {"cornell": lambda: cornell64, "tiny": lambda: scenes.tiny_scene("glass").build(),
+          "mesh": lambda: scenes.mesh_scene(n_theta=120, n_phi=120, resolution=(32, 32)).build()}[name]()
+    integ = create_integrator("wavefront", {}, sc)
+    n = 1 << 17
+    o, d = _ray_set(sc, n, seed=1)
+    tmax = np.full(n, np.inf, np.float32)
+    got, gst = integ.trace(o, d, tmax, want_stats=True)
+    ref, rst = orc.trace(sc, o, d, tmax)
+    assert _assert_hits_equal(got, ref) == 4                                # observed: all four fields bit-exact
+    assert gst.nodes_visited == rst.nodes_visited and gst.tris_tested == rst.tris_tested
+    assert (ref["prim"] >= 0).mean() > 0.3
+    # any-hit with the shadow-ray convention: unnormalised direction, t_max = 1 - 1e-4
+    d2 = (d * np.float32(3.0)).astype(np.float32)
+    t2 = np.full(n, np.float32(0.9999), np.float32)
+    got2 = integ.trace(o, d2, t2, any_hit=True)
+    ref2, _ = orc.trace(sc, o, d2, t2, any_hit=True)
+    assert np.array_equal(got2["prim"], ref2["prim"])
+    integ.close()
+
+
+def test_trace_edge_cases(cornell_gpu):
+    e = np.zeros((0, 3), np.float32)
+    assert len(cornell_gpu.trace(e, e, np.zeros(0, np.float32))) == 0      # empty batch
+    o = np.array([[0, 0, 1080]] * 3, np.float32)
+    d = np.array([[0, 0, 1], [0, 0, 1], [np.nan, 0, 1]], np.float32)
+    t = np.array([np.inf, 1e-3, np.inf], np.float32)
+    got = cornell_gpu.trace(o, d, t)
+    assert got["prim"][0] >= 0 and got["prim"][1] == -1                     # t_max clips the hit
+
+
+# ---- films ---------------------------------------------------------------------------------------------
+def _film_close(got, ref, frac=0.999, rtol=2e-3):
+    assert np.array_equal(got[:, 3], ref[:, 3])                             # weight sums are exact
+    lum_g, lum_r = got[:, :3].sum(axis=1), ref[:, :3].sum(axis=1)
+    scale = max(lum_r.mean(), 1e-12)
+    ok = np.abs(lum_g - lum_r) <= rtol * np.maximum(lum_r, 0.05 * scale)
+    assert ok.mean() >= frac, f"only {ok.mean():.5f} of pixels within {rtol}"
+    assert abs(lum_g.sum() - lum_r.sum()) / lum_r.sum() < 2e-3
+    return ok.mean()
+
+
+def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
+    film = cornell_gpu.render(Options(seed=0)).copy()
+    ref, rst, _ = orc.render(cornell64, orc.make_params(seed=0, spp=16))
+    _film_close(film, ref)
+    gst = cornell_gpu.stats
+    assert gst.camera_paths == rst.camera_paths == 64 * 64 * 16
+    assert abs(int(gst.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-4 * rst.closest_hit_rays
+    assert abs(int(gst.shadow_rays) - int(rst.shadow_rays)) <= 1e-4 * rst.shadow_rays
+    assert gst.kernel_launches > 0
+    # developed image: RMSE and mean relative luminance error <= 1 % (north-star image bar)
+    img_g = cornell_gpu.develop(film).reshape(-1, 3); img_r = orc.develop(cornell64, ref)
+    rmse = np.sqrt(np.mean((img_g - img_r) ** 2)) / np.mean(img_r)
+    assert rmse < 0.01
+
+
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass"])
+def test_tiny_scene_films(kind):
+    sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 4, "seed": 5})
+    film = integ.render(Options()).copy()
+    ref, rst, _ = orc.render(sc, orc.make_params(seed=5, spp=4))
+    _film_close(film, ref, frac=0.99)
+    gold = json.load(open(os.path.join(GOLDEN, "tiny_films.json")))[kind]
+    assert abs(int(integ.stats.closest_hit_rays) - gold["closest_hit_rays"]) <= 2
+    assert np.allclose(film.sum(axis=0), gold["film_sum"], rtol=5e-3)
+    integ.close()
+
+
+def test_sample_range_split_and_batching(cornell_gpu, cornell64):
+    """(a) sample ranges add up (the multi-GPU decomposition); (b) the result does not depend on the
+    wavefront width (ragged last batch, tiny batches)."""
+    opts = Options(seed=2, pixel_samples=6)
+    full = cornell_gpu.render(opts).copy()
+    cornell_gpu.film[:] = 0
+    a = cornell_gpu.render(opts, sample_range=(0, 2)).copy(); cornell_gpu.film[:] = 0
+    b = cornell_gpu.render(opts, sample_range=(2, 6)).copy(); cornell_gpu.film[:] = 0
+    assert np.allclose(a + b, full, rtol=1e-9)
+    small = create_integrator("wavefront", {}, cornell64, {"pixelsamples": 6}, max_paths_in_flight=1000)
+    c = small.render(opts).copy()
+    assert np.allclose(c, full, rtol=1e-9)
+    small.close()
+
+
+def test_options_and_depth_limits(cornell_gpu, cornell64):
+    integ = create_integrator("wavefront", {"maxdepth": 0}, cornell64, {"pixelsamples": 2})
+    f = integ.render(Options()).copy()
+    assert integ.stats.shadow_rays == 0 and integ.stats.closest_hit_rays == 64 * 64 * 2
+    ref, _, _ = orc.render(cornell64, orc.make_params(seed=0, spp=2, max_depth=0))
+    assert np.allclose(f, ref, rtol=1e-5, atol=1e-12)
+    integ.close()
+    with pytest.raises(ffi.ShimmerGpuError):
+        cornell_gpu.render(Options(force_diffuse=True))                     # not on the GPU path: error, not fallback
+
+
+def test_scene_validation_errors(cornell64):
+    import copy
+    import ctypes as C
+    lib = ffi.load_library()
+    bad = ffi.SgSceneDesc.from_buffer_copy(cornell64.desc)
+    bad.abi_version = 99
+    h = C.c_void_p()
+    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) == -1 and b"abi_version" in lib.sg_last_error()
+    bad = ffi.SgSceneDesc.from_buffer_copy(cornell64.desc)
+    prims = cornell64.arrays["prims"].copy(); prims["material"][0] = 1000
+    bad.primitives = prims.ctypes.data_as(C.POINTER(ffi.SgPrimitive))
+    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) == -1
