@@ -221,6 +221,12 @@ typedef struct SgStats {
     uint64_t kernel_launches;
     double   render_ms;         /* device time of the wavefront loop                       */
     double   trace_ms;          /* device time inside closest-hit + any-hit kernels        */
+    uint64_t closest_nodes;     /* nodes_visited / tris_tested of the closest-hit rays only */
+    uint64_t closest_tris;
+    uint64_t closest_launches;  /* closest-hit / any-hit traversal kernel launches          */
+    uint64_t shadow_launches;
+    double   closest_ms;        /* device time of the closest-hit kernels (reserved bit 1)  */
+    double   shadow_ms;         /* device time of the any-hit kernels     (reserved bit 1)  */
 } SgStats;
 
 /* `ShapeIntersection` reduced to what parity needs (shape.rs:221-225 +

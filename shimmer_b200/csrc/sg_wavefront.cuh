@@ -56,7 +56,7 @@ struct RenderConst {
     int32_t  full_res_x;
 };
 
-struct DevStats { unsigned long long closest, shadow, nodes, tris; };
+struct DevStats { unsigned long long closest, shadow, nodes, tris, nodes_closest, tris_closest; };
 
 #define SG_SHADOW_TMAX 0.9999f        /* 1.0 - SHADOW_EPISLON, integrator.rs:66,115 */
 static constexpr int kTraceThreads = 128;
@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
         atomicAdd(&stats->tris, (unsigned long long)cnt_tris);
+        if (!ANY) {
+            atomicAdd(&stats->nodes_closest, (unsigned long long)cnt_nodes);
+            atomicAdd(&stats->tris_closest, (unsigned long long)cnt_tris);
+        }
     }
 }
 

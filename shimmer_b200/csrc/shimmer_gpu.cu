@@ -243,8 +243,8 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     cudaEvent_t ev0, ev1;
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
-    std::vector<cudaEvent_t> tev;
-    uint64_t launches = 0;
+    std::vector<cudaEvent_t> tev, sev;      // event pairs around closest-hit / any-hit launches
+    uint64_t launches = 0, closest_launches = 0, shadow_launches = 0;
     CU(cudaEventRecord(ev0, stream));
     for (uint64_t first = 0; first < total; first += capacity) {
         const uint32_t cnt = (uint32_t)((total - first) < capacity ? (total - first) : capacity);
@@ -254,18 +254,18 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (count) k_trace<false, true><<<grid_closest[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
             else k_trace<false, false><<<grid_closest[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
-            ++launches;
+            ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
             if (s->kinds_present[SG_MATERIAL_DIFFUSE]) { k_shade<SG_MATERIAL_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->kinds_present[SG_MATERIAL_CONDUCTOR]) { k_shade<SG_MATERIAL_CONDUCTOR><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->kinds_present[SG_MATERIAL_DIELECTRIC]) { k_shade<SG_MATERIAL_DIELECTRIC><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
-                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
                 if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
                 else k_trace<true, false><<<grid_shadow[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
-                ++launches;
-                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+                ++launches; ++shadow_launches;
+                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
             }
         }
         k_film<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, cnt, (double*)d_film); ++launches;
@@ -276,9 +276,11 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     CU(cudaGetLastError());
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    double trace_ms = 0.0;
-    for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); trace_ms += t; }
+    double closest_ms = 0.0, shadow_ms = 0.0;
+    for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); closest_ms += t; }
+    for (size_t i = 0; i + 1 < sev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, sev[i], sev[i + 1]); shadow_ms += t; }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    for (cudaEvent_t e : sev) cudaEventDestroy(e);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         DevStats h;
@@ -286,7 +288,10 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         std::memset(stats, 0, sizeof *stats);
         stats->camera_paths = total; stats->closest_hit_rays = h.closest; stats->shadow_rays = h.shadow;
         stats->nodes_visited = h.nodes; stats->tris_tested = h.tris; stats->kernel_launches = launches;
-        stats->render_ms = ms; stats->trace_ms = trace_ms;
+        stats->render_ms = ms; stats->trace_ms = closest_ms + shadow_ms;
+        stats->closest_nodes = h.nodes_closest; stats->closest_tris = h.tris_closest;
+        stats->closest_launches = closest_launches; stats->shadow_launches = shadow_launches;
+        stats->closest_ms = closest_ms; stats->shadow_ms = shadow_ms;
     }
     return SG_OK;
 }
@@ -343,6 +348,8 @@ int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, con
         if (any_hit) stats->shadow_rays = (uint64_t)n; else stats->closest_hit_rays = (uint64_t)n;
         stats->nodes_visited = h.nodes; stats->tris_tested = h.tris; stats->kernel_launches = n > 0 ? 1 : 0;
         stats->render_ms = ms; stats->trace_ms = ms;
+        if (any_hit) { stats->shadow_ms = ms; stats->shadow_launches = n > 0 ? 1 : 0; }
+        else { stats->closest_ms = ms; stats->closest_launches = n > 0 ? 1 : 0; stats->closest_nodes = h.nodes; stats->closest_tris = h.tris; }
     }
     return SG_OK;
 }

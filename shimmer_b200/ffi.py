@@ -98,7 +98,9 @@ class SgFilmPixel(C.Structure):
 class SgStats(C.Structure):
     _fields_ = [("camera_paths", C.c_uint64), ("closest_hit_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+                ("render_ms", C.c_double), ("trace_ms", C.c_double),
+                ("closest_nodes", C.c_uint64), ("closest_tris", C.c_uint64), ("closest_launches", C.c_uint64),
+                ("shadow_launches", C.c_uint64), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

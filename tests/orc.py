@@ -27,9 +27,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".cpp", ".h"))]
-    if not os.path.exists(ORC_LIB) or any(os.path.getmtime(s) > os.path.getmtime(ORC_LIB) for s in srcs):
-        build()
+    build()      # `make` is a no-op when liborc.so is newer than its sources and the ABI header
     L = C.CDLL(ORC_LIB)
     vp = C.c_void_p
     L.orc_header.restype = C.c_char_p

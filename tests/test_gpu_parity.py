@@ -153,6 +153,7 @@ def _film_close(got, ref, frac=0.999, rtol=2e-3):
 
 
 def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
+    cornell_gpu.film[:] = 0
     film = cornell_gpu.render(Options(seed=0)).copy()
     ref, rst, _ = orc.render(cornell64, orc.make_params(seed=0, spp=16))
     _film_close(film, ref)
@@ -184,6 +185,7 @@ def test_sample_range_split_and_batching(cornell_gpu, cornell64):
     """(a) sample ranges add up (the multi-GPU decomposition); (b) the result does not depend on the
     wavefront width (ragged last batch, tiny batches)."""
     opts = Options(seed=2, pixel_samples=6)
+    cornell_gpu.film[:] = 0                      # sg_render ADDS into the caller's film
     full = cornell_gpu.render(opts).copy()
     cornell_gpu.film[:] = 0
     a = cornell_gpu.render(opts, sample_range=(0, 2)).copy(); cornell_gpu.film[:] = 0
