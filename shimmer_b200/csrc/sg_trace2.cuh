@@ -1,0 +1,160 @@
+// Traversal kernel core, generation 2: the hot loop of the path tracer.
+//
+// Same visiting order, same box/triangle arithmetic and therefore the same hits, ties and visit
+// counts as BvhAggregate::intersect / intersect_predicate (aggregate.rs:71-203) -- but laid out
+// for a GPU:
+//   * Node64: an interior node stores BOTH children's bounds (64 B = 4 x LDG.128), so one fetch
+//     feeds two slab tests and the dependent-load chain per level is halved.  The reference
+//     tests a node's bounds when it is visited/popped; here the near child is tested at once and
+//     the far child's entry distance is pushed with it, re-checked against the (possibly
+//     shrunken) t_max on pop -- exactly the `t_min < ray_t_max` term of intersect_p_cached
+//     (bounding_box.rs:563), the only term that depends on t_max.
+//   * while-while scheduling: every lane first walks interior nodes until it holds a leaf, then
+//     the warp runs triangle tests together (no box-test lanes idling behind a 130-instruction
+//     triangle test).
+//   * persistent warps with per-lane replacement: a lane whose ray terminated claims a new ray
+//     with a warp-aggregated atomicAdd as soon as warp utilisation drops below a threshold.
+//   * per-thread traversal stack in shared memory, level-major (bank-conflict-free), sized from
+//     the tree depth computed at upload.
+#pragma once
+#include "sg_scene.cuh"
+
+namespace sg {
+
+static constexpr uint32_t kLeafBit = 0x80000000u;
+static constexpr uint32_t kFailBit = 0x40000000u;     // COUNT builds only: far child failed its box test
+static constexpr uint32_t kEmptyRef = 0x7fffffffu;
+static constexpr uint32_t kLastInLeaf = 0x80000000u;  // flag in tri_verts[3*i+2].w (mesh id word)
+
+// slab test of bounding_box.rs:520-564 split into its t_max-independent part (return value) and
+// the entry distance the `t_min < ray_t_max` term needs.
+SGD bool slab_entry(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                    float3 o, float3 inv_dir, int nx, int ny, int nz, float& t_entry) {
+    const float k = 1.0f + 2.0f * gamma_n(3);
+    float t_min = ((nx ? bmaxx : bminx) - o.x) * inv_dir.x;
+    float t_max = ((nx ? bminx : bmaxx) - o.x) * inv_dir.x;
+    float ty_min = ((ny ? bmaxy : bminy) - o.y) * inv_dir.y;
+    float ty_max = ((ny ? bminy : bmaxy) - o.y) * inv_dir.y;
+    t_max *= k; ty_max *= k;
+    bool ok = !(t_min > ty_max || ty_min > t_max);
+    if (ty_min > t_min) t_min = ty_min;
+    if (ty_max < t_max) t_max = ty_max;
+    float tz_min = ((nz ? bmaxz : bminz) - o.z) * inv_dir.z;
+    float tz_max = ((nz ? bminz : bmaxz) - o.z) * inv_dir.z;
+    tz_max *= k;
+    ok = ok && !(t_min > tz_max || tz_min > t_max);
+    if (tz_min > t_min) t_min = tz_min;
+    if (tz_max < t_max) t_max = tz_max;
+    t_entry = t_min;
+    return ok && t_max > 0.0f;
+}
+
+struct TraceScene {
+    const float4* node64;       // 4 float4 per interior node
+    const float4* tri_verts;    // 3 float4 per primitive (see sg_scene.cuh)
+    float root_bmin[3], root_bmax[3];
+    uint32_t root_ref;          // kEmptyRef for an empty scene
+    int stack_depth;            // entries per thread
+};
+
+// One lane's traversal state.
+struct Lane {
+    float3 o, inv_dir;
+    RayPre rp;
+    float t_max;
+    uint32_t cur;
+    int sp;
+    int nx, ny, nz;
+    HitRec hit;
+};
+
+template <bool ANY>
+SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_max, uint32_t& n_nodes, bool count) {
+    L.o = o;
+    L.inv_dir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                 // aggregate.rs:76
+    L.nx = L.inv_dir.x < 0.0f; L.ny = L.inv_dir.y < 0.0f; L.nz = L.inv_dir.z < 0.0f;
+    L.rp = ray_precompute(d);
+    L.t_max = t_max; L.sp = 0; L.hit.prim = -1;
+    L.cur = kEmptyRef;
+    if (ts.root_ref != kEmptyRef) {
+        float te;
+        if (count) n_nodes++;
+        bool ok = slab_entry(ts.root_bmin[0], ts.root_bmin[1], ts.root_bmin[2], ts.root_bmax[0], ts.root_bmax[1], ts.root_bmax[2],
+                             o, L.inv_dir, L.nx, L.ny, L.nz, te);
+        if (ok && te < t_max) L.cur = ts.root_ref;
+    }
+}
+
+// Pops the next node whose entry distance is still in range; kEmptyRef when the stack runs dry.
+template <bool ANY, bool COUNT>
+SGD uint32_t lane_pop(Lane& L, const uint32_t* s_ref, const float* s_t, int stride, uint32_t& n_nodes) {
+    while (L.sp > 0) {
+        --L.sp;
+        const uint32_t ref = s_ref[L.sp * stride];
+        if (COUNT) n_nodes++;                                   // the reference tests the bounds at pop time
+        if (COUNT && (ref & kFailBit)) continue;
+        if (ANY) return ref;                                    // t_max never shrinks for the predicate
+        if (s_t[L.sp * stride] < L.t_max) return ref;
+    }
+    return kEmptyRef;
+}
+
+// Runs the lane until its ray terminates or `budget` leaf/interior phases elapsed.
+// Returns true when the ray is finished.
+template <bool ANY, bool COUNT>
+SGD bool lane_advance(const TraceScene& ts, Lane& L, uint32_t* s_ref, float* s_t, int stride,
+                      uint32_t& n_nodes, uint32_t& n_tris, unsigned min_active) {
+    while (L.cur != kEmptyRef) {
+        // ---- phase 1: interior nodes ----
+        while (!(L.cur & kLeafBit)) {
+            const float4* nd = ts.node64 + 4 * (size_t)L.cur;
+            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+            float t0, t1;
+            const bool ok0 = slab_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L.o, L.inv_dir, L.nx, L.ny, L.nz, t0);
+            const bool ok1 = slab_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L.o, L.inv_dir, L.nx, L.ny, L.nz, t1);
+            const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
+            const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);       // near child by dir_is_neg[axis], aggregate.rs:119-127
+            const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
+            const bool near_ok = neg ? ok1 : ok0, far_ok = neg ? ok0 : ok1;
+            const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
+            // The reference tests the far child against t_max when it is POPPED, and t_max is not
+            // monotone: intersect_triangle compares t_scaled with t_max*det, so an accepted hit can
+            // round to a t up to (1+2^-24)^3 above the previous t_max (vertex/edge ties).  Pruning at
+            // push time must therefore leave slack; 2^-10 covers > 5000 successive tie increases and
+            // costs almost no extra pushes.  The decisive `entry < t_max` test is made on pop.
+            const bool far_take = far_ok && (ANY ? far_t < L.t_max : far_t <= L.t_max * 1.0009765625f);
+            if (far_take || COUNT) {
+                s_ref[L.sp * stride] = far_take ? far_ref : (far_ref | kFailBit);
+                if (!ANY) s_t[L.sp * stride] = far_t;
+                L.sp++;
+            }
+            if (COUNT) n_nodes++;                                               // near child's bounds test
+            if (near_ok && near_t < L.t_max) L.cur = near_ref;
+            else {
+                L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
+                if (L.cur == kEmptyRef) return true;
+            }
+        }
+        // ---- phase 2: the leaf's primitives (aggregate.rs:99-110) ----
+        uint32_t pi = L.cur & ~kLeafBit;
+        for (;;) {
+            const float4* tv = ts.tri_verts + 3 * (size_t)pi;
+            const float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+            if (COUNT) n_tris++;
+            float b0, b1, b2, t;
+            if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
+                L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
+                if (ANY) { L.cur = kEmptyRef; return true; }
+                L.t_max = t;
+            }
+            if (__float_as_uint(v2.w) & kLastInLeaf) break;
+            ++pi;
+        }
+        L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
+        // dynamic fetch: leave so that finished lanes can claim new rays once utilisation drops
+        if (__popc(__activemask()) < min_active) break;
+    }
+    return L.cur == kEmptyRef;
+}
+
+}  // namespace sg

@@ -8,6 +8,7 @@
 // Queue appends are warp-aggregated (__ballot_sync + one atomicAdd per warp and queue).
 #pragma once
 #include "sg_shading.cuh"
+#include "sg_trace2.cuh"
 
 namespace sg {
 
@@ -89,61 +90,106 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 }
 
 // ---- closest-hit / any-hit traversal over a ray queue ----
-// Persistent CTAs (grid = SMs x resident CTAs): each warp claims 32 queue entries with one
-// atomicAdd, traverses with a per-thread 64-entry stack in shared memory (bank-conflict-free:
-// level-major, one word per thread per level), then compacts results into the material queues.
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ DScene sc, PathState st, Queues q,
-                                                         int depth, DevStats* stats) {
-    __shared__ uint32_t s_stack[64 * kTraceThreads];
-    uint32_t* C = q.counters + depth * C_STRIDE;
-    const uint32_t n = C[ANY ? C_NSHADOW : C_NRAY];
-    const uint32_t* queue = ANY ? q.shadow : q.ray[depth & 1];
-    uint32_t* cursor = C + (ANY ? C_CUR_SHADOW : C_CUR_CLOSEST);
+// Persistent warps (grid = SMs x resident CTAs).  See sg_trace2.cuh for the traversal core.
+// `IO` supplies rays and consumes results; retire() is called warp-convergently so it may use
+// warp collectives (ballot-compacted appends into the material queues).
+static constexpr unsigned kDynamicFetchThreshold = 24;
+
+template <bool ANY, bool COUNT, class IO, class CursorT>
+SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* cursor, uint32_t* s_mem,
+                          uint32_t& cnt_nodes, uint32_t& cnt_tris) {
     const int lane = threadIdx.x & 31;
-    uint32_t cnt_nodes = 0, cnt_tris = 0;
+    const int stride = blockDim.x;
+    uint32_t* s_ref = s_mem + threadIdx.x;
+    float* s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.stack_depth * blockDim.x) + threadIdx.x;
+    Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1;
+    bool has_ray = false, dead = false, finished = false;
+    CursorT idx = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t idx = base + lane;
-        const bool active = idx < n;
+        if (__ballot_sync(0xffffffffu, finished)) io.retire(finished, idx, L.hit, lane);
+        finished = false;
+        const bool need = !has_ray && !dead;
+        const uint32_t mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            CursorT base = 0;
+            const int leader = __ffs(mask) - 1;
+            if (lane == leader) base = atomicAdd(cursor, (CursorT)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                idx = base + (CursorT)__popc(mask & ((1u << lane) - 1u));
+                if (idx < n) {
+                    float3 o, d; float tmax;
+                    io.load(idx, o, d, tmax);
+                    lane_begin<ANY>(ts, L, o, d, tmax, cnt_nodes, COUNT);
+                    has_ray = true;
+                } else dead = true;
+            }
+        }
+        const uint32_t live = __ballot_sync(0xffffffffu, has_ray);
+        if (!live) break;
+        if (has_ray) {
+            const unsigned thr = min(kDynamicFetchThreshold, (unsigned)__popc(live));
+            if (lane_advance<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes, cnt_tris, thr)) { finished = true; has_ray = false; }
+        }
+        __syncwarp();
+    }
+}
+
+struct ClosestIO {
+    const DScene& sc; PathState st; Queues q; uint32_t* C; const uint32_t* queue;
+    uint32_t path;
+    SGD void load(uint32_t i, float3& o, float3& d, float& tmax) {
+        path = queue[i];
+        const float4 o4 = st.ray_o[path], d4 = st.ray_d[path];
+        o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = INFINITY;
+    }
+    SGD void retire(bool fin, uint32_t, const HitRec& hit, int lane) {
         int kind = -1;
-        uint32_t path = 0;
-        if (active) {
-            path = queue[idx];
-            HitRec hit;
-            if (ANY) {
-                const float4 o = st.sh_o[path], d = st.sh_d[path];
-                bool occluded = traverse<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), SG_SHADOW_TMAX, hit,
-                                                      s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
-                if (!occluded) st.L[path] = st.L[path] + st.sh_L[path];
-            } else {
-                const float4 o = st.ray_o[path], d = st.ray_d[path];
-                bool found = traverse<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), INFINITY, hit,
-                                                    s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
-                st.hit_prim[path] = hit.prim;
-                if (found) {
-                    st.hit_b[path] = make_float4(hit.b0, hit.b1, hit.b2, hit.t);
-                    kind = 1 + (int)(__float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)hit.prim).w) >> 28);
-                } else kind = Q_MISS;
-            }
+        if (fin) {
+            st.hit_prim[path] = hit.prim;
+            if (hit.prim >= 0) {
+                st.hit_b[path] = make_float4(hit.b0, hit.b1, hit.b2, hit.t);
+                kind = 1 + (int)((__float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)hit.prim).w) >> 28) & 7u);
+            } else kind = Q_MISS;
         }
-        if (!ANY) {
-            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < Q_NKINDS; ++k) {
-                const uint32_t mask = __ballot_sync(0xffffffffu, kind == k);
-                if (mask) {
-                    uint32_t qbase = 0;
-                    const int leader = __ffs(mask) - 1;
-                    if (lane == leader) qbase = atomicAdd(C + C_NSHADE + k, (uint32_t)__popc(mask));
-                    qbase = __shfl_sync(0xffffffffu, qbase, leader);
-                    if (kind == k) q.shade[k][qbase + __popc(mask & ((1u << lane) - 1u))] = path;
-                }
+        for (int k = 0; k < Q_NKINDS; ++k) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, kind == k);
+            if (mask) {
+                uint32_t qbase = 0;
+                const int leader = __ffs(mask) - 1;
+                if (lane == leader) qbase = atomicAdd(C + C_NSHADE + k, (uint32_t)__popc(mask));
+                qbase = __shfl_sync(0xffffffffu, qbase, leader);
+                if (kind == k) q.shade[k][qbase + __popc(mask & ((1u << lane) - 1u))] = path;
             }
         }
+    }
+};
+struct ShadowIO {
+    PathState st; const uint32_t* queue;
+    uint32_t path;
+    SGD void load(uint32_t i, float3& o, float3& d, float& tmax) {
+        path = queue[i];
+        const float4 o4 = st.sh_o[path], d4 = st.sh_d[path];
+        o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = SG_SHADOW_TMAX;
+    }
+    SGD void retire(bool fin, uint32_t, const HitRec& hit, int) {
+        if (fin && hit.prim < 0) st.L[path] = st.L[path] + st.sh_L[path];      // unoccluded: L += beta * Ld
+    }
+};
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+                                                         PathState st, Queues q, int depth, DevStats* stats) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t* C = q.counters + depth * C_STRIDE;
+    uint32_t cnt_nodes = 0, cnt_tris = 0;
+    if (ANY) {
+        ShadowIO io{st, q.shadow, 0};
+        trace_persistent<true, COUNT>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, cnt_nodes, cnt_tris);
+    } else {
+        ClosestIO io{sc, st, q, C, q.ray[depth & 1], 0};
+        trace_persistent<false, COUNT>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
     }
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
@@ -371,40 +417,40 @@ __global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* 
 }
 
 // ---- free-standing ray batches: the ray-cast parity / roofline entry (sg_trace) ----
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace_rays(const __grid_constant__ DScene sc, long long n, const float* __restrict__ o,
-                                                              const float* __restrict__ d, const float* __restrict__ tmax,
-                                                              SgHit* __restrict__ out, unsigned long long* cursor, DevStats* stats) {
-    __shared__ uint32_t s_stack[64 * kTraceThreads];
-    const int lane = threadIdx.x & 31;
-    uint32_t cnt_nodes = 0, cnt_tris = 0;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned long long)n) break;
-        const unsigned long long i = base + lane;
-        if (i < (unsigned long long)n) {
-            const float3 ro = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rdir = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-            HitRec hit;
-            bool found = traverse<ANY, COUNT>(sc, ro, rdir, tmax[i], hit, s_stack + threadIdx.x, kTraceThreads, cnt_nodes, cnt_tris);
-            SgHit h; h.prim = -1; h.t = 0.0f; h.b0 = h.b1 = h.b2 = 0.0f; h.ng[0] = h.ng[1] = h.ng[2] = 0.0f;
-            if (found) {
-                if (ANY) h.prim = 0;
-                else {
-                    h.prim = hit.prim; h.t = hit.t; h.b0 = hit.b0; h.b1 = hit.b1; h.b2 = hit.b2;
-                    const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 1),
-                                 v2 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 2);
-                    const float3 p0 = f3(v0.x, v0.y, v0.z), p1 = f3(v1.x, v1.y, v1.z), p2 = f3(v2.x, v2.y, v2.z);
-                    float3 ng = normalize3(cross3(p0 - p2, p1 - p2));                    // triangle.rs:407-412
-                    const uint32_t mflags = sc.meshes[__float_as_uint(v2.w)].flags;
-                    if (((mflags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((mflags & SG_MESH_SWAPS_HANDEDNESS) != 0)) ng = -ng;
-                    h.ng[0] = ng.x; h.ng[1] = ng.y; h.ng[2] = ng.z;
-                }
-            }
-            out[i] = h;
-        }
+template <bool ANY>
+struct RaysIO {
+    const DScene& sc; const float* o; const float* d; const float* tmax; SgHit* out;
+    SGD void load(unsigned long long i, float3& ro, float3& rd, float& t) {
+        ro = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); rd = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); t = tmax[i];
     }
+    SGD void retire(bool fin, unsigned long long i, const HitRec& hit, int) {
+        if (!fin) return;
+        SgHit h; h.prim = -1; h.t = 0.0f; h.b0 = h.b1 = h.b2 = 0.0f; h.ng[0] = h.ng[1] = h.ng[2] = 0.0f;
+        if (hit.prim >= 0) {
+            if (ANY) h.prim = 0;
+            else {
+                h.prim = hit.prim; h.t = hit.t; h.b0 = hit.b0; h.b1 = hit.b1; h.b2 = hit.b2;
+                const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 1),
+                             v2 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 2);
+                const float3 p0 = f3(v0.x, v0.y, v0.z), p1 = f3(v1.x, v1.y, v1.z), p2 = f3(v2.x, v2.y, v2.z);
+                float3 ng = normalize3(cross3(p0 - p2, p1 - p2));                    // triangle.rs:407-412
+                const uint32_t mflags = sc.meshes[__float_as_uint(v2.w) & ~kLastInLeaf].flags;
+                if (((mflags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((mflags & SG_MESH_SWAPS_HANDEDNESS) != 0)) ng = -ng;
+                h.ng[0] = ng.x; h.ng[1] = ng.y; h.ng[2] = ng.z;
+            }
+        }
+        out[i] = h;
+    }
+};
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_rays(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+                                                              long long n, const float* __restrict__ o, const float* __restrict__ d,
+                                                              const float* __restrict__ tmax, SgHit* __restrict__ out,
+                                                              unsigned long long* cursor, DevStats* stats) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t cnt_nodes = 0, cnt_tris = 0;
+    RaysIO<ANY> io{sc, o, d, tmax, out};
+    trace_persistent<ANY, COUNT>(ts, io, (unsigned long long)n, cursor, s_mem, cnt_nodes, cnt_tris);
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
         atomicAdd(&stats->tris, (unsigned long long)cnt_tris);

@@ -48,6 +48,8 @@ struct Workspace {
 
 struct SgScene {
     DScene d{};
+    TraceScene ts{};
+    size_t smem_closest = 0, smem_shadow = 0;
     std::vector<void*> owned;
     Workspace ws;
     DevStats* d_stats = nullptr;
@@ -85,9 +87,10 @@ int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
     return SG_OK;
 }
 
-int persistent_grid(const void* kernel, int threads) {
+int persistent_grid(const void* kernel, int threads, size_t smem) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     return g_num_sms * per_sm;      // grid = SM count x resident CTAs: one full wave, persistent
 }
 
@@ -164,10 +167,53 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         }
         s->kinds_present[desc->materials[p.material].kind] = true;
     }
-    float4* d_nodes = nullptr; float4* d_tv = nullptr;
+    // Node64 (sg_trace2.cuh): interior nodes with both children's bounds; leaves are folded into child refs.
+    std::vector<float4> n64;
+    {
+        const uint32_t N = desc->n_nodes;
+        std::vector<uint32_t> idx64(N, 0), depth(N, 0);
+        uint32_t n_interior = 0, max_depth = N ? 1 : 0;
+        for (uint32_t i = 0; i < N; ++i) if (desc->nodes[i].n_prims == 0) idx64[i] = n_interior++;
+        if (N) depth[0] = 1;
+        n64.resize((size_t)n_interior * 4);
+        for (uint32_t i = 0; i < N; ++i) {
+            const SgBvhNode& nd = desc->nodes[i];
+            if (depth[i] > max_depth) max_depth = depth[i];
+            if (nd.n_prims > 0) {
+                uint32_t last = nd.offset + nd.n_prims - 1, wbits;
+                std::memcpy(&wbits, &tv[3 * (size_t)last + 2].w, 4); wbits |= kLastInLeaf; std::memcpy(&tv[3 * (size_t)last + 2].w, &wbits, 4);
+                continue;
+            }
+            const uint32_t c[2] = {i + 1, nd.offset};
+            uint32_t ref[2];
+            for (int k = 0; k < 2; ++k) {
+                const SgBvhNode& ch = desc->nodes[c[k]];
+                depth[c[k]] = depth[i] + 1;
+                ref[k] = ch.n_prims > 0 ? (kLeafBit | ch.offset) : idx64[c[k]];
+            }
+            const SgBvhNode& a = desc->nodes[c[0]]; const SgBvhNode& b = desc->nodes[c[1]];
+            float4* o = &n64[(size_t)idx64[i] * 4];
+            float r0, r1, mt; uint32_t meta = nd.axis;
+            std::memcpy(&r0, &ref[0], 4); std::memcpy(&r1, &ref[1], 4); std::memcpy(&mt, &meta, 4);
+            o[0] = make_float4(a.bmin[0], a.bmin[1], a.bmin[2], a.bmax[0]);
+            o[1] = make_float4(a.bmax[1], a.bmax[2], b.bmin[0], b.bmin[1]);
+            o[2] = make_float4(b.bmin[2], b.bmax[0], b.bmax[1], b.bmax[2]);
+            o[3] = make_float4(r0, r1, mt, 0.0f);
+        }
+        if (max_depth > 64) { g_err = "BVH deeper than 64 levels: the reference's fixed traversal stack (aggregate.rs:90) would overflow"; return bail(SG_ERR_UNSUPPORTED); }
+        if (desc->n_primitives >= (1u << 30)) { g_err = "too many primitives"; return bail(SG_ERR_UNSUPPORTED); }
+        s->ts.stack_depth = max_depth < 1 ? 1 : (int)max_depth;
+        s->ts.root_ref = N == 0 ? kEmptyRef : (desc->nodes[0].n_prims > 0 ? (kLeafBit | desc->nodes[0].offset) : 0u);
+        for (int k = 0; k < 3 && N; ++k) { s->ts.root_bmin[k] = desc->nodes[0].bmin[k]; s->ts.root_bmax[k] = desc->nodes[0].bmax[k]; }
+        s->smem_closest = (size_t)s->ts.stack_depth * kTraceThreads * 8;
+        s->smem_shadow = (size_t)s->ts.stack_depth * kTraceThreads * 4;
+    }
+    float4* d_nodes = nullptr; float4* d_tv = nullptr; float4* d_n64 = nullptr;
+    if ((rc = upload(n64.data(), n64.size(), &d_n64, s->owned)) != SG_OK) return bail(rc);
+    s->ts.node64 = d_n64;
     if ((rc = upload((const float4*)desc->nodes, (size_t)desc->n_nodes * 2, &d_nodes, s->owned)) != SG_OK) return bail(rc);
     if ((rc = upload(tv.data(), tv.size(), &d_tv, s->owned)) != SG_OK) return bail(rc);
-    d.nodes = d_nodes; d.tri_verts = d_tv;
+    d.nodes = d_nodes; d.tri_verts = d_tv; s->ts.tri_verts = d_tv;
 #define UP(field, src, n, T) { T* p__ = nullptr; if ((rc = upload((const T*)(src), (size_t)(n), &p__, s->owned)) != SG_OK) return bail(rc); d.field = p__; }
     UP(prims, desc->primitives, desc->n_primitives, SgPrimitive);
     UP(meshes, desc->meshes, desc->n_meshes, SgMesh);
@@ -232,13 +278,11 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     const bool count = (rp->reserved & 1) != 0;       // bit 0: count nodes/tris (slower, for roofline accounting)
     const bool time_trace = (rp->reserved & 2) != 0;  // bit 1: time the traversal kernels separately
     const int n_depths = rp->max_depth + 1;
-    static int grid_closest[2] = {0, 0}, grid_shadow[2] = {0, 0};
-    if (!grid_closest[0]) {
-        grid_closest[0] = persistent_grid((const void*)k_trace<false, false>, kTraceThreads);
-        grid_closest[1] = persistent_grid((const void*)k_trace<false, true>, kTraceThreads);
-        grid_shadow[0] = persistent_grid((const void*)k_trace<true, false>, kTraceThreads);
-        grid_shadow[1] = persistent_grid((const void*)k_trace<true, true>, kTraceThreads);
-    }
+    const size_t smc = s->smem_closest, sms = s->smem_shadow;
+    const int grid_closest[2] = {persistent_grid((const void*)k_trace<false, false>, kTraceThreads, smc),
+                                 persistent_grid((const void*)k_trace<false, true>, kTraceThreads, smc)};
+    const int grid_shadow[2] = {persistent_grid((const void*)k_trace<true, false>, kTraceThreads, sms),
+                                persistent_grid((const void*)k_trace<true, true>, kTraceThreads, sms)};
     const int shade_grid = g_num_sms * 8;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     cudaEvent_t ev0, ev1;
@@ -252,8 +296,8 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
         for (int depth = 0; depth < n_depths; ++depth) {
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
-            if (count) k_trace<false, true><<<grid_closest[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
-            else k_trace<false, false><<<grid_closest[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+            if (count) k_trace<false, true><<<grid_closest[1], kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
+            else k_trace<false, false><<<grid_closest[0], kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
@@ -262,8 +306,8 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             if (s->kinds_present[SG_MATERIAL_DIELECTRIC]) { k_shade<SG_MATERIAL_DIELECTRIC><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
-                if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
-                else k_trace<true, false><<<grid_shadow[0], kTraceThreads, 0, stream>>>(s->d, w.st, w.q, depth, s->d_stats);
+                if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
+                else k_trace<true, false><<<grid_shadow[0], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
                 ++launches; ++shadow_launches;
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
             }
@@ -329,8 +373,9 @@ int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, con
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, stream));
     if (n > 0) {
-#define LAUNCH(A, C) { int g = persistent_grid((const void*)k_trace_rays<A, C>, kTraceThreads); \
-        k_trace_rays<A, C><<<g, kTraceThreads, 0, stream>>>(s->d, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats); }
+#define LAUNCH(A, C) { const size_t sm = (A) ? s->smem_shadow : s->smem_closest; \
+        int g = persistent_grid((const void*)k_trace_rays<A, C>, kTraceThreads, sm); \
+        k_trace_rays<A, C><<<g, kTraceThreads, sm, stream>>>(s->d, s->ts, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats); }
         if (any_hit) { if (count) LAUNCH(true, true) else LAUNCH(true, false) }
         else { if (count) LAUNCH(false, true) else LAUNCH(false, false) }
 #undef LAUNCH
