@@ -6,14 +6,15 @@
 //   * Node64: an interior node stores BOTH children's bounds (64 B = 4 x LDG.128), so one fetch
 //     feeds two slab tests and the dependent-load chain per level is halved.  The reference
 //     tests a node's bounds when it is visited/popped; here the near child is tested at once and
-//     the far child's entry distance is pushed with it, re-checked against the (possibly
-//     shrunken) t_max on pop -- exactly the `t_min < ray_t_max` term of intersect_p_cached
+//     the far child's entry distance is pushed with it, re-checked against the current t_max on pop -- exactly the `t_min < ray_t_max` term of intersect_p_cached
 //     (bounding_box.rs:563), the only term that depends on t_max.
-//   * while-while scheduling: every lane first walks interior nodes until it holds a leaf, then
-//     the warp runs triangle tests together (no box-test lanes idling behind a 130-instruction
-//     triangle test).
-//   * persistent warps with per-lane replacement: a lane whose ray terminated claims a new ray
-//     with a warp-aggregated atomicAdd as soon as warp utilisation drops below a threshold.
+//   * warp-voted phase scheduling (sg_wavefront.cuh trace_persistent): every iteration the warp
+//     ballots its lanes' states (interior / holding a leaf / finished) and runs ONE phase for
+//     all lanes that want it -- interior steps by default, triangle tests once enough lanes hold
+//     a leaf, retire+refill once enough lanes finished -- so box-test lanes never idle behind a
+//     130-instruction triangle test and finished lanes never wait for the slowest ray.
+//   * persistent warps with per-lane replacement: finished lanes claim new rays with one
+//     warp-aggregated atomicAdd.
 //   * per-thread traversal stack in shared memory, level-major (bank-conflict-free), sized from
 //     the tree depth computed at upload.
 #pragma once
@@ -55,6 +56,10 @@ struct TraceScene {
     float root_bmin[3], root_bmax[3];
     uint32_t root_ref;          // kEmptyRef for an empty scene
     int stack_depth;            // entries per thread
+    int leaf_threshold;         // warp-vote scheduling knobs (see trace_persistent)
+    int refill_threshold;
+    int interior_burst;
+    int prefetch;
 };
 
 // One lane's traversal state.
@@ -99,62 +104,60 @@ SGD uint32_t lane_pop(Lane& L, const uint32_t* s_ref, const float* s_t, int stri
     return kEmptyRef;
 }
 
-// Runs the lane until its ray terminates or `budget` leaf/interior phases elapsed.
-// Returns true when the ray is finished.
+// One interior step: fetch a Node64, test both children, push the far one, move to the near one
+// (or pop).  Leaves `L.cur` at an interior ref, a leaf ref, or kEmptyRef (ray finished).
 template <bool ANY, bool COUNT>
-SGD bool lane_advance(const TraceScene& ts, Lane& L, uint32_t* s_ref, float* s_t, int stride,
-                      uint32_t& n_nodes, uint32_t& n_tris, unsigned min_active) {
-    while (L.cur != kEmptyRef) {
-        // ---- phase 1: interior nodes ----
-        while (!(L.cur & kLeafBit)) {
-            const float4* nd = ts.node64 + 4 * (size_t)L.cur;
-            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-            float t0, t1;
-            const bool ok0 = slab_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L.o, L.inv_dir, L.nx, L.ny, L.nz, t0);
-            const bool ok1 = slab_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L.o, L.inv_dir, L.nx, L.ny, L.nz, t1);
-            const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
-            const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);       // near child by dir_is_neg[axis], aggregate.rs:119-127
-            const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
-            const bool near_ok = neg ? ok1 : ok0, far_ok = neg ? ok0 : ok1;
-            const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
-            // The reference tests the far child against t_max when it is POPPED, and t_max is not
-            // monotone: intersect_triangle compares t_scaled with t_max*det, so an accepted hit can
-            // round to a t up to (1+2^-24)^3 above the previous t_max (vertex/edge ties).  Pruning at
-            // push time must therefore leave slack; 2^-10 covers > 5000 successive tie increases and
-            // costs almost no extra pushes.  The decisive `entry < t_max` test is made on pop.
-            const bool far_take = far_ok && (ANY ? far_t < L.t_max : far_t <= L.t_max * 1.0009765625f);
-            if (far_take || COUNT) {
-                s_ref[L.sp * stride] = far_take ? far_ref : (far_ref | kFailBit);
-                if (!ANY) s_t[L.sp * stride] = far_t;
-                L.sp++;
-            }
-            if (COUNT) n_nodes++;                                               // near child's bounds test
-            if (near_ok && near_t < L.t_max) L.cur = near_ref;
-            else {
-                L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
-                if (L.cur == kEmptyRef) return true;
-            }
-        }
-        // ---- phase 2: the leaf's primitives (aggregate.rs:99-110) ----
-        uint32_t pi = L.cur & ~kLeafBit;
-        for (;;) {
-            const float4* tv = ts.tri_verts + 3 * (size_t)pi;
-            const float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
-            if (COUNT) n_tris++;
-            float b0, b1, b2, t;
-            if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
-                L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
-                if (ANY) { L.cur = kEmptyRef; return true; }
-                L.t_max = t;
-            }
-            if (__float_as_uint(v2.w) & kLastInLeaf) break;
-            ++pi;
-        }
-        L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
-        // dynamic fetch: leave so that finished lanes can claim new rays once utilisation drops
-        if (__popc(__activemask()) < min_active) break;
+SGD void lane_step_interior(const TraceScene& ts, Lane& L, uint32_t* s_ref, float* s_t, int stride, uint32_t& n_nodes) {
+    const float4* nd = ts.node64 + 4 * (size_t)L.cur;
+    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+    const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
+    const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);       // near child by dir_is_neg[axis], aggregate.rs:119-127
+    const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
+    if (ts.prefetch) {
+        // start pulling the near child's node (or triangle) towards L1 while the two slab tests run
+        const float4* nxt = (near_ref & kLeafBit) ? ts.tri_verts + 3 * (size_t)(near_ref & ~kLeafBit) : ts.node64 + 4 * (size_t)near_ref;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
     }
-    return L.cur == kEmptyRef;
+    float t0, t1;
+    const bool ok0 = slab_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L.o, L.inv_dir, L.nx, L.ny, L.nz, t0);
+    const bool ok1 = slab_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L.o, L.inv_dir, L.nx, L.ny, L.nz, t1);
+    const bool near_ok = neg ? ok1 : ok0, far_ok = neg ? ok0 : ok1;
+    const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
+    // The reference tests the far child against t_max when it is POPPED, and t_max is not
+    // monotone: intersect_triangle compares t_scaled with t_max*det, so an accepted hit can
+    // round to a t up to (1+2^-24)^3 above the previous t_max (vertex/edge ties).  Pruning at
+    // push time must therefore leave slack; 2^-10 covers > 5000 successive tie increases and
+    // costs almost no extra pushes.  The decisive `entry < t_max` test is made on pop.
+    const bool far_take = far_ok && (ANY ? far_t < L.t_max : far_t <= L.t_max * 1.0009765625f);
+    if (far_take || COUNT) {
+        s_ref[L.sp * stride] = far_take ? far_ref : (far_ref | kFailBit);
+        if (!ANY) s_t[L.sp * stride] = far_t;
+        L.sp++;
+    }
+    if (COUNT) n_nodes++;                                               // near child's bounds test
+    if (near_ok && near_t < L.t_max) L.cur = near_ref;
+    else L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
+}
+
+// The leaf's primitives (aggregate.rs:99-110), then pop.  Returns true when an any-hit ray is done.
+template <bool ANY, bool COUNT>
+SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const uint32_t* s_ref, const float* s_t, int stride,
+                        uint32_t& n_nodes, uint32_t& n_tris) {
+    uint32_t pi = L.cur & ~kLeafBit;
+    for (;;) {
+        const float4* tv = ts.tri_verts + 3 * (size_t)pi;
+        const float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+        if (COUNT) n_tris++;
+        float b0, b1, b2, t;
+        if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
+            L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
+            if (ANY) { L.cur = kEmptyRef; return; }
+            L.t_max = t;
+        }
+        if (__float_as_uint(v2.w) & kLastInLeaf) break;
+        ++pi;
+    }
+    L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
 }
 
 }  // namespace sg

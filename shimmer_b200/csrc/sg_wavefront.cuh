@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // Persistent warps (grid = SMs x resident CTAs).  See sg_trace2.cuh for the traversal core.
 // `IO` supplies rays and consumes results; retire() is called warp-convergently so it may use
 // warp collectives (ballot-compacted appends into the material queues).
-static constexpr unsigned kDynamicFetchThreshold = 24;
-
+// Scheduling thresholds (lanes): run the triangle phase once this many lanes hold a leaf, and
+// the retire/refill phase once this many lanes wait for a ray; kInteriorBurst interior steps
+// are run back to back between votes.
 template <bool ANY, bool COUNT, class IO, class CursorT>
 SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* cursor, uint32_t* s_mem,
                           uint32_t& cnt_nodes, uint32_t& cnt_tris) {
@@ -106,32 +107,52 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     bool has_ray = false, dead = false, finished = false;
     CursorT idx = 0;
     for (;;) {
-        if (__ballot_sync(0xffffffffu, finished)) io.retire(finished, idx, L.hit, lane);
-        finished = false;
-        const bool need = !has_ray && !dead;
-        const uint32_t mask = __ballot_sync(0xffffffffu, need);
-        if (mask) {
-            CursorT base = 0;
-            const int leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(cursor, (CursorT)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-                idx = base + (CursorT)__popc(mask & ((1u << lane) - 1u));
-                if (idx < n) {
-                    float3 o, d; float tmax;
-                    io.load(idx, o, d, tmax);
-                    lane_begin<ANY>(ts, L, o, d, tmax, cnt_nodes, COUNT);
-                    has_ray = true;
-                } else dead = true;
+        const bool is_leaf = has_ray && (L.cur & kLeafBit) != 0;
+        const bool is_int = has_ray && !is_leaf;
+        const uint32_t m_int = __ballot_sync(0xffffffffu, is_int);
+        const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
+        const uint32_t m_wait = __ballot_sync(0xffffffffu, finished || (!has_ray && !dead));
+        if ((m_int | m_leaf) == 0u || __popc(m_wait) >= ts.refill_threshold) {
+            // ---- retire finished rays, claim new ones (warp-aggregated) ----
+            if (__ballot_sync(0xffffffffu, finished)) io.retire(finished, idx, L.hit, lane);
+            finished = false;
+            const bool need = !has_ray && !dead;
+            const uint32_t mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {
+                CursorT base = 0;
+                const int leader = __ffs(mask) - 1;
+                if (lane == leader) base = atomicAdd(cursor, (CursorT)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) {
+                    idx = base + (CursorT)__popc(mask & ((1u << lane) - 1u));
+                    if (idx < n) {
+                        float3 o, d; float tmax;
+                        io.load(idx, o, d, tmax);
+                        lane_begin<ANY>(ts, L, o, d, tmax, cnt_nodes, COUNT);
+                        if (L.cur == kEmptyRef) finished = true; else has_ray = true;
+                    } else dead = true;
+                }
+            }
+            if (!__ballot_sync(0xffffffffu, has_ray || finished)) break;
+            continue;
+        }
+        if (__popc(m_leaf) >= ts.leaf_threshold || m_int == 0u) {
+            // ---- triangle phase ----
+            if (is_leaf) {
+                lane_step_leaf<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes, cnt_tris);
+                if (L.cur == kEmptyRef) { finished = true; has_ray = false; }
+            }
+            continue;
+        }
+        // ---- interior phase ----
+        if (is_int) {
+#pragma unroll 1
+            for (int k = 0; k < ts.interior_burst; ++k) {
+                lane_step_interior<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes);
+                if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
+                if (L.cur & kLeafBit) break;
             }
         }
-        const uint32_t live = __ballot_sync(0xffffffffu, has_ray);
-        if (!live) break;
-        if (has_ray) {
-            const unsigned thr = min(kDynamicFetchThreshold, (unsigned)__popc(live));
-            if (lane_advance<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes, cnt_tris, thr)) { finished = true; has_ray = false; }
-        }
-        __syncwarp();
     }
 }
 

@@ -205,6 +205,11 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         s->ts.stack_depth = max_depth < 1 ? 1 : (int)max_depth;
         s->ts.root_ref = N == 0 ? kEmptyRef : (desc->nodes[0].n_prims > 0 ? (kLeafBit | desc->nodes[0].offset) : 0u);
         for (int k = 0; k < 3 && N; ++k) { s->ts.root_bmin[k] = desc->nodes[0].bmin[k]; s->ts.root_bmax[k] = desc->nodes[0].bmax[k]; }
+        auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+        s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 8);
+        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 6);
+        s->ts.interior_burst = env_int("SG_INTERIOR_BURST", 4);
+        s->ts.prefetch = env_int("SG_PREFETCH", 0);
         s->smem_closest = (size_t)s->ts.stack_depth * kTraceThreads * 8;
         s->smem_shadow = (size_t)s->ts.stack_depth * kTraceThreads * 4;
     }
