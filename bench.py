@@ -117,8 +117,8 @@ def run_reference(args):
         return
     sc, cfg, res, spp, build_s = build_scene(args)
     threads = os.cpu_count() or 1
-    # bounded sample of the same workload: all pixels, 1 sample index per step
-    sample_spp = 1
+    # bounded sample of the same workload: all pixels, a quarter of the sample indices per step (~4 s on 16 cores)
+    sample_spp = max(1, spp // 4)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_run(sc, sample_spp, cfg["max_depth"], threads)
     t_paths = t_rays = 0; t_secs = 0.0
@@ -163,13 +163,13 @@ def main():
     npix = W * H
     film = torch.zeros((npix, 4), dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    my_range = (rank * spp, (rank + 1) * spp)         # weak scaling: every rank renders spp NEW sample indices
+    from shimmer_b200.distributed import reduce_film, sample_range_for_rank
+    my_range = sample_range_for_rank(spp, rank, world, "weak")   # weak scaling: every rank renders spp NEW sample indices
 
     def step(reserved=0):
         film.zero_()
         integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, reserved=reserved)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(film, dst=0)                      # one NCCL reduce of the f64 film per step (no-op at N=1)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -241,7 +241,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample_spp = 2 if args.workload != "cornell" else 16
+            sample_spp = max(1, spp // 2)            # ~10 s of CPU work on the 16-core box for C2
             r = cpu_reference_run(sc, sample_spp, cfg["max_depth"], threads)
             cpu = {"value": r["paths"] / r["secs"] / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
                    "mrays_per_s": r["rays"] / r["secs"] / 1e6, "seconds": r["secs"],
