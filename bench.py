@@ -166,9 +166,9 @@ def main():
     from shimmer_b200.distributed import reduce_film, sample_range_for_rank
     my_range = sample_range_for_rank(spp, rank, world, "weak")   # weak scaling: every rank renders spp NEW sample indices
 
-    def step(reserved=0):
+    def step(flags=0):
         film.zero_()
-        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, reserved=reserved)
+        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, flags=flags)
         reduce_film(film, dst=0)                      # one NCCL reduce of the f64 film per step (no-op at N=1)
 
     for _ in range(max(args.warmup, 3)):
@@ -206,8 +206,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        host_film[:] = 0
-        integ.render(opts, sample_range=my_range)
+        integ.render(opts, sample_range=my_range, flags=4)      # SG_RENDER_OVERWRITE_FILM: film of this step only
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -217,10 +216,10 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (closest-hit traversal), measured live with CUDA events
         film.zero_()
-        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, reserved=2)   # per-kernel events
+        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, flags=2)   # per-kernel events
         st_t = integ.stats.as_dict()
         film.zero_()
-        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, reserved=1)   # visit counters
+        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream, flags=1)   # visit counters
         st_c = integ.stats.as_dict()
         n_closest = st_c["closest_hit_rays"]
         nodes_per_ray = st_c["closest_nodes"] / max(n_closest, 1); tris_per_ray = st_c["closest_tris"] / max(n_closest, 1)
@@ -253,7 +252,7 @@ def main():
                            "triangles": sc.meta["n_triangles"], "bvh_nodes": sc.meta["n_nodes"],
                            "integrator": "path maxdepth=%d, independent sampler, uniform light sampler" % cfg["max_depth"],
                            "parallelism": f"replicated scene, sample-range split x{world}, 1 NCCL film reduce/step" if world > 1 else "single GPU",
-                           "l2": "working set (path state %.2f GB + scene) exceeds the 126 MB L2; no explicit flush" % (min(npix * spp, integ.max_paths_in_flight or (1 << 22)) * 276 / 1e9),
+                           "l2": "working set (path state %.2f GB + scene) exceeds the 126 MB L2; no explicit flush" % (min(npix * spp, integ.max_paths_in_flight or (1 << 26)) * 276 / 1e9),
                            "scene_build_s": build_s, "scene_upload_s": upload_s},
                 "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(__import__("shimmer_b200").ffi.SgRenderParams),
                         "d2h_bytes_per_step": npix * 32, "note": "sg_render: host film buffer, scene resident (uploaded once)"},

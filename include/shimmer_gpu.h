@@ -202,9 +202,14 @@ typedef struct SgRenderParams {
     int32_t  max_depth;         /* `maxdepth`, default 5                                    */
     int32_t  regularize;        /* `regularize`, default false                              */
     uint32_t option_flags;      /* SG_OPT_*                                                 */
-    int32_t  max_paths_in_flight; /* wavefront width; 0 = library default                   */
-    int32_t  reserved;
+    int32_t  max_paths_in_flight; /* wavefront width; 0 = library default (64 Mi paths, 18.5 GB) */
+    int32_t  flags;             /* SG_RENDER_*                                              */
 } SgRenderParams;
+enum {
+    SG_RENDER_COUNT_VISITS = 1,   /* count BVH nodes / triangles tested (slower; roofline accounting) */
+    SG_RENDER_TIME_KERNELS = 2,   /* CUDA events around every traversal launch -> closest_ms/shadow_ms */
+    SG_RENDER_OVERWRITE_FILM = 4  /* sg_render: store the film instead of adding to the caller's sums  */
+};
 
 /* `RgbFilmPixel` without the (unused on this path) splat: film.rs:470-479. */
 typedef struct SgFilmPixel {

@@ -7,7 +7,8 @@
 //               render-space vertices pre-gathered through vertex_indices so a triangle
 //               test costs 3 x LDG.128 instead of the reference's 5 dependent loads
 //               (Arc<Primitive> -> Arc<Shape> -> Arc<TriangleMesh> -> indices -> p).
-//               .w lanes: [0] material | kind<<28, [1] area-light id, [2] mesh id.
+//               .w lanes: [0] material | mesh flags<<23 | kind<<28, [1] area-light id,
+//               [2] mesh id | last-in-leaf<<31.
 //   everything else is the host arrays copied verbatim.
 #pragma once
 #include "sg_math.cuh"
@@ -18,6 +19,7 @@ namespace sg {
 struct DScene {
     const float4* nodes;        // 2 float4 per node
     const float4* tri_verts;    // 3 float4 per primitive
+    const float4* light_verts;  // 3 float4 per light (area lights: the emitter triangle; .w[0] = mesh flags)
     const SgPrimitive* prims;
     const SgMesh* meshes;
     const uint32_t* indices;

@@ -482,16 +482,43 @@ struct Surf {
 };
 SGD float3 ldv3(const float* a, size_t i) { return f3(__ldg(a + 3 * i), __ldg(a + 3 * i + 1), __ldg(a + 3 * i + 2)); }
 
+// Triangle geometry handle.  Vertices come from the pre-gathered tri_verts / light_verts records
+// (one cache line, already touched by the traversal kernel); the index/attribute arrays are only
+// read for meshes that carry normals, uvs or tangents.
+struct TriGeo { float3 p0, p1, p2; uint32_t flags; uint32_t mesh; uint32_t tri; uint32_t prim; };
+static constexpr uint32_t kTriUnknown = 0xffffffffu;
+SGD TriGeo geo_from_prim(const DScene& sc, uint32_t prim_id, uint32_t& material, int& light) {
+    const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim_id), v1 = __ldg(sc.tri_verts + 3 * (size_t)prim_id + 1),
+                 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim_id + 2);
+    const uint32_t w0 = __float_as_uint(v0.w);
+    TriGeo g; g.p0 = f3(v0.x, v0.y, v0.z); g.p1 = f3(v1.x, v1.y, v1.z); g.p2 = f3(v2.x, v2.y, v2.z);
+    g.flags = (w0 >> 23) & 31u; g.mesh = __float_as_uint(v2.w) & 0x7fffffffu; g.tri = kTriUnknown; g.prim = prim_id;
+    material = w0 & 0x7fffffu; light = (int)__float_as_uint(v1.w);
+    return g;
+}
+SGD TriGeo geo_from_light(const DScene& sc, uint32_t light_id, const SgLight& lt) {
+    const float4 v0 = __ldg(sc.light_verts + 3 * (size_t)light_id), v1 = __ldg(sc.light_verts + 3 * (size_t)light_id + 1),
+                 v2 = __ldg(sc.light_verts + 3 * (size_t)light_id + 2);
+    TriGeo g; g.p0 = f3(v0.x, v0.y, v0.z); g.p1 = f3(v1.x, v1.y, v1.z); g.p2 = f3(v2.x, v2.y, v2.z);
+    g.flags = __float_as_uint(v0.w); g.mesh = lt.mesh; g.tri = lt.tri; g.prim = 0;
+    return g;
+}
+SGD void geo_indices(const DScene& sc, const TriGeo& g, uint32_t& i0, uint32_t& i1, uint32_t& i2, size_t& fv) {
+    const uint32_t tri = g.tri != kTriUnknown ? g.tri : sc.prims[g.prim].tri;
+    const SgMesh m = sc.meshes[g.mesh];
+    const uint32_t* ix = sc.indices + m.first_index + 3 * (size_t)tri;
+    i0 = __ldg(ix); i1 = __ldg(ix + 1); i2 = __ldg(ix + 2); fv = m.first_vertex;
+}
+
 // Builds geometric + shading frame for the FINAL hit only (the reference does it for every
 // accepted candidate along the ray, triangle.rs:529-535; only the last survives).
 // The uv-derived dpdu/dpdv follow :314-372; dndu/dndv and ray differentials are dropped --
 // on this path they are multiplied by a zero displacement or never read.
-SGD Surf make_surface(const DScene& sc, uint32_t mesh_id, uint32_t tri, float b0, float b1, float b2) {
-    const SgMesh m = sc.meshes[mesh_id];
-    const uint32_t* ix = sc.indices + m.first_index + 3 * (size_t)tri;
-    const uint32_t i0 = __ldg(ix), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
-    const size_t fv = m.first_vertex;
-    float3 p0 = ldv3(sc.p, fv + i0), p1 = ldv3(sc.p, fv + i1), p2 = ldv3(sc.p, fv + i2);
+SGD Surf make_surface(const DScene& sc, const TriGeo& g, float b0, float b1, float b2) {
+    struct { uint32_t flags; } m; m.flags = g.flags;
+    const float3 p0 = g.p0, p1 = g.p1, p2 = g.p2;
+    uint32_t i0 = 0, i1 = 0, i2 = 0; size_t fv = 0;
+    if (m.flags & (SG_MESH_HAS_UV | SG_MESH_HAS_N | SG_MESH_HAS_S)) geo_indices(sc, g, i0, i1, i2, fv);
     float2 uv0 = make_float2(0.0f, 0.0f), uv1 = make_float2(1.0f, 0.0f), uv2 = make_float2(1.0f, 1.0f);
     if (m.flags & SG_MESH_HAS_UV) {
         uv0 = make_float2(__ldg(sc.uv + 2 * (fv + i0)), __ldg(sc.uv + 2 * (fv + i0) + 1));
@@ -564,14 +591,6 @@ SGD Spec light_l(const DScene& sc, const SgLight& lt, float3 n, float3 w, const 
     if (!lt.two_sided && dot3(n, w) < 0.0f) return spec1(0.0f);
     return lt.scale * spectrum_sample(sc, lt.spectrum, lam);
 }
-struct TriGeo { float3 p0, p1, p2; uint32_t i0, i1, i2; size_t fv; uint32_t flags; };
-SGD TriGeo load_tri(const DScene& sc, uint32_t mesh_id, uint32_t tri) {
-    const SgMesh m = sc.meshes[mesh_id];
-    const uint32_t* ix = sc.indices + m.first_index + 3 * (size_t)tri;
-    TriGeo g; g.i0 = __ldg(ix); g.i1 = __ldg(ix + 1); g.i2 = __ldg(ix + 2); g.fv = m.first_vertex; g.flags = m.flags;
-    g.p0 = ldv3(sc.p, g.fv + g.i0); g.p1 = ldv3(sc.p, g.fv + g.i1); g.p2 = ldv3(sc.p, g.fv + g.i2);
-    return g;
-}
 SGD float tri_area(const TriGeo& g) { return 0.5f * len3(cross3(g.p1 - g.p0, g.p2 - g.p0)); }           // triangle.rs:543-546
 SGD float tri_solid_angle(const TriGeo& g, float3 p) {                                                    // :162-169
     return spherical_tri_area(normalize3(g.p0 - p), normalize3(g.p1 - p), normalize3(g.p2 - p));
@@ -587,7 +606,8 @@ SGD bool tri_sample_with_context(const DScene& sc, const TriGeo& g, const LightC
         float3 p = bb0 * g.p0 + bb1 * g.p1 + bb2 * g.p2;
         float3 n = normalize3(cross3(g.p1 - g.p0, g.p2 - g.p0));
         if (!(g.flags & SG_MESH_HAS_N)) n = n * -1.0f;                 // :558-560 always negated (reference quirk)
-        else { float3 ns = bb0 * ldv3(sc.n, g.fv + g.i0) + bb1 * ldv3(sc.n, g.fv + g.i1) + bb2 * ldv3(sc.n, g.fv + g.i2); n = faceforward3(n, ns); }
+        else { uint32_t i0, i1, i2; size_t fv; geo_indices(sc, g, i0, i1, i2, fv);
+               float3 ns = bb0 * ldv3(sc.n, fv + i0) + bb1 * ldv3(sc.n, fv + i1) + bb2 * ldv3(sc.n, fv + i2); n = faceforward3(n, ns); }
         float3 p_abs_sum = abs3(bb0 * g.p0) + abs3(bb1 * g.p1) + abs3(bb2 * g.p2);
         out_pi = p3fi_make(p, gamma_n(6) * p_abs_sum);
         out_n = n;
@@ -616,14 +636,14 @@ SGD bool tri_sample_with_context(const DScene& sc, const TriGeo& g, const LightC
     float3 p_abs_sum = abs3(b0 * g.p0) + abs3(b1 * g.p1) + abs3((1.0f - b0 - b1) * g.p2);
     float3 p = b0 * g.p0 + b1 * g.p1 + b2 * g.p2;
     float3 n = normalize3(cross3(g.p1 - g.p0, g.p2 - g.p0));
-    if (g.flags & SG_MESH_HAS_N) { float3 ns = b0 * ldv3(sc.n, g.fv + g.i0) + b1 * ldv3(sc.n, g.fv + g.i1) + b2 * ldv3(sc.n, g.fv + g.i2); n = faceforward3(n, ns); }
+    if (g.flags & SG_MESH_HAS_N) { uint32_t i0, i1, i2; size_t fv; geo_indices(sc, g, i0, i1, i2, fv);
+                                   float3 ns = b0 * ldv3(sc.n, fv + i0) + b1 * ldv3(sc.n, fv + i1) + b2 * ldv3(sc.n, fv + i2); n = faceforward3(n, ns); }
     else if (((g.flags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((g.flags & SG_MESH_SWAPS_HANDEDNESS) != 0)) n = n * -1.0f;
     out_pi = p3fi_make(p, gamma_n(6) * p_abs_sum); out_n = n; out_pdf = pdf;
     return true;
 }
 // Triangle::pdf_with_context :696-745 (mesh_id/tri needed for the rare area-sampling branch)
-SGD float tri_pdf_with_context(const DScene& sc, uint32_t mesh_id, uint32_t tri, const LightCtx& ctx, float3 wi) {
-    const TriGeo g = load_tri(sc, mesh_id, tri);
+SGD float tri_pdf_with_context(const DScene& sc, const TriGeo& g, const LightCtx& ctx, float3 wi) {
     const float3 cp = p3fi_mid(ctx.pi);
     const float sa = tri_solid_angle(g, cp);
     if (sa < 3e-4f || sa > 6.22f) {
@@ -631,7 +651,7 @@ SGD float tri_pdf_with_context(const DScene& sc, uint32_t mesh_id, uint32_t tri,
         RayPre rp = ray_precompute(wi);
         float b0, b1, b2, t;
         if (!intersect_triangle(o, rp, INFINITY, g.p0, g.p1, g.p2, b0, b1, b2, t)) return 0.0f;
-        Surf s = make_surface(sc, mesh_id, tri, b0, b1, b2);
+        Surf s = make_surface(sc, g, b0, b1, b2);
         float pdf = (1.0f / tri_area(g)) / (absdot3(s.n, -wi) / dist2(cp, p3fi_mid(s.pi)));
         if (isinf(pdf)) return 0.0f;
         return pdf;
@@ -647,9 +667,9 @@ SGD float tri_pdf_with_context(const DScene& sc, uint32_t mesh_id, uint32_t tri,
     return pdf;
 }
 // Light::sample_li with allow_incomplete_pdf = true (integrator.rs:933)
-SGD bool light_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls) {
+SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) {                                  // light.rs:632-661
-        const TriGeo g = load_tri(sc, lt.mesh, lt.tri);
+        const TriGeo g = geo_from_light(sc, light_id, lt);
         P3fi pi; float3 n; float pdf;
         if (!tri_sample_with_context(sc, g, ctx, u, pi, n, pdf)) return false;
         float3 sp = p3fi_mid(pi), cp = p3fi_mid(ctx.pi);
@@ -668,8 +688,8 @@ SGD bool light_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ct
     }
     return false;                                                            // UniformInfiniteLight: None, light.rs:748-750
 }
-SGD float light_pdf_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float3 wi) {
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, lt.mesh, lt.tri, ctx, wi);     // light.rs:663-666
+SGD float light_pdf_li(const DScene& sc, const SgLight& lt, const TriGeo& g, const LightCtx& ctx, float3 wi) {
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, g, ctx, wi);                   // light.rs:663-666
     return 0.0f;                                                             // :486-494, :770-781 (allow_incomplete_pdf)
 }
 

@@ -60,7 +60,10 @@ struct RenderConst {
 struct DevStats { unsigned long long closest, shadow, nodes, tris, nodes_closest, tris_closest; };
 
 #define SG_SHADOW_TMAX 0.9999f        /* 1.0 - SHADOW_EPISLON, integrator.rs:66,115 */
-static constexpr int kTraceThreads = 128;
+#ifndef SG_TRACE_THREADS
+#define SG_TRACE_THREADS 128
+#endif
+static constexpr int kTraceThreads = SG_TRACE_THREADS;
 
 // ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
@@ -249,8 +252,11 @@ __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DSce
 
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
+#ifndef SG_SHADE_MIN_BLOCKS
+#define SG_SHADE_MIN_BLOCKS 4
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+__global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
     const int qk = 1 + KIND;
@@ -271,7 +277,8 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
             const float3 wo = -rd;
             const int prim_id = st.hit_prim[path];
             const float4 hb = st.hit_b[path];
-            const SgPrimitive prim = sc.prims[prim_id];
+            uint32_t material_id; int light_id;
+            const TriGeo geo = geo_from_prim(sc, (uint32_t)prim_id, material_id, light_id);
             uint32_t fl = st.flags[path];
             int pdepth = fl & 0xff; bool specular_bounce = (fl >> 8) & 1u; bool any_non_specular = (fl >> 9) & 1u;
             Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
@@ -279,11 +286,11 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
             float2 pbe = st.pb_eta[path];
             float p_b = pbe.x, eta_scale = pbe.y;
 
-            Surf s = make_surface(sc, prim.mesh, prim.tri, hb.x, hb.y, hb.z);
+            Surf s = make_surface(sc, geo, hb.x, hb.y, hb.z);
 
             // emission + MIS against light sampling, :798-813
-            if (prim.light >= 0) {
-                const SgLight lt = sc.lights[prim.light];
+            if (light_id >= 0) {
+                const SgLight lt = sc.lights[light_id];
                 Spec le = light_l(sc, lt, s.n, wo, lam);
                 if (!spec_zero(le)) {
                     if (pdepth == 0 || specular_bounce) L = L + beta * le;
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
                         const float4 c0 = st.ctx0[path], c1 = st.ctx1[path], c2 = st.ctx2[path];
                         pc.pi.lo = f3(c0.x, c0.y, c0.z); pc.pi.hi = f3(c0.w, c1.x, c1.y);
                         pc.n = f3(c1.z, c1.w, c2.x); pc.ns = f3(c2.y, c2.z, c2.w);
-                        float p_l = (1.0f / (float)sc.n_lights) * light_pdf_li(sc, lt, pc, rd);
+                        float p_l = (1.0f / (float)sc.n_lights) * light_pdf_li(sc, lt, geo, pc, rd);
                         float w_l = power_heuristic(p_b, p_l);
                         L = L + beta * w_l * le;
                     }
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
             }
 
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
-            const SgMaterial mat = sc.materials[prim.material];
+            const SgMaterial mat = sc.materials[material_id];
             if (mat.flags & SG_MAT_HAS_DISPLACEMENT) apply_constant_bump(s);
             BSDF<KIND> bsdf;
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
                         const float p_choose = 1.0f / (float)sc.n_lights;
                         const SgLight lt = sc.lights[li];
                         LightSample ls;
-                        if (light_sample_li(sc, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
+                        if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
                             Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);
                             if (!spec_zero(f)) {
                                 const float p_l = p_choose * ls.pdf;

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <thread>
+#include <algorithm>
 
 using namespace sg;
 
@@ -56,6 +58,7 @@ struct SgScene {
     unsigned long long* d_cursor = nullptr;
     bool kinds_present[3] = {false, false, false};
     double* d_film = nullptr; size_t film_pixels = 0;
+    SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
     uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
 };
 
@@ -158,7 +161,8 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         const SgPrimitive& p = desc->primitives[i];
         const SgMesh& m = desc->meshes[p.mesh];
         const uint32_t* ix = desc->indices + m.first_index + 3 * (size_t)p.tri;
-        const uint32_t w[3] = {p.material | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, p.mesh};
+        if (p.material >= (1u << 23)) { g_err = "more than 2^23 materials"; return bail(SG_ERR_UNSUPPORTED); }
+        const uint32_t w[3] = {p.material | ((m.flags & 31u) << 23) | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, p.mesh};
         for (int k = 0; k < 3; ++k) {
             if (ix[k] >= m.n_vertices) { g_err = "vertex index out of range"; return bail(SG_ERR_INVALID_ARGUMENT); }
             const float* q = desc->p + 3 * (size_t)(m.first_vertex + ix[k]);
@@ -238,6 +242,24 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (d.n_infinite >= 4) { g_err = "more than 4 infinite lights"; return bail(SG_ERR_UNSUPPORTED); }
         d.infinite_ids[d.n_infinite++] = (int32_t)i;
     }
+    {   // emitter triangles pre-gathered per light (light.rs:524-535: each area light owns its Shape)
+        std::vector<float4> lv((size_t)desc->n_lights * 3, make_float4(0, 0, 0, 0));
+        for (uint32_t i = 0; i < desc->n_lights; ++i) {
+            const SgLight& L = desc->lights[i];
+            if (L.kind != SG_LIGHT_DIFFUSE_AREA) continue;
+            if (L.mesh >= desc->n_meshes || L.tri >= desc->meshes[L.mesh].n_triangles) { g_err = "light references out-of-range triangle"; return bail(SG_ERR_INVALID_ARGUMENT); }
+            const SgMesh& m = desc->meshes[L.mesh];
+            const uint32_t* ix = desc->indices + m.first_index + 3 * (size_t)L.tri;
+            for (int k = 0; k < 3; ++k) {
+                const float* q = desc->p + 3 * (size_t)(m.first_vertex + ix[k]);
+                float wf = 0.0f; if (k == 0) { uint32_t fl = m.flags; std::memcpy(&wf, &fl, 4); }
+                lv[3 * (size_t)i + k] = make_float4(q[0], q[1], q[2], wf);
+            }
+        }
+        float4* d_lv = nullptr;
+        if ((rc = upload(lv.data(), lv.size(), &d_lv, s->owned)) != SG_OK) return bail(rc);
+        d.light_verts = d_lv;
+    }
     d.camera = desc->camera; d.film = desc->film;
     void* p = nullptr;
     if (cudaMalloc(&p, sizeof(DevStats)) != cudaSuccess) { g_err = "cudaMalloc stats"; return bail(SG_ERR_OUT_OF_MEMORY); }
@@ -254,6 +276,7 @@ int sg_scene_destroy(SgScene* s) {
     s->ws.release();
     for (void* p : s->owned) cudaFree(p);
     if (s->d_film) cudaFree(s->d_film);
+    if (s->h_film) cudaFreeHost(s->h_film);
     delete s;
     return SG_OK;
 }
@@ -267,7 +290,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
     const uint64_t npix = s->n_pixels();
     const uint64_t total = npix * (uint64_t)(rp->sample_end - rp->sample_begin);
-    uint64_t cap64 = rp->max_paths_in_flight > 0 ? (uint64_t)rp->max_paths_in_flight : (1ull << 22);
+    uint64_t cap64 = rp->max_paths_in_flight > 0 ? (uint64_t)rp->max_paths_in_flight : (1ull << 26);   // 64 Mi paths = 18.5 GB of 180 GB
     if (cap64 > total) cap64 = total;
     if (cap64 == 0) cap64 = 1;
     const uint32_t capacity = (uint32_t)cap64;
@@ -280,8 +303,8 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.win_x0 = s->d.film.pixel_bounds[0]; k.win_y0 = s->d.film.pixel_bounds[1];
     k.win_w = s->d.film.pixel_bounds[2] - k.win_x0; k.win_h = s->d.film.pixel_bounds[3] - k.win_y0;
     k.full_res_x = s->d.film.full_resolution[0];
-    const bool count = (rp->reserved & 1) != 0;       // bit 0: count nodes/tris (slower, for roofline accounting)
-    const bool time_trace = (rp->reserved & 2) != 0;  // bit 1: time the traversal kernels separately
+    const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
+    const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
     const int n_depths = rp->max_depth + 1;
     const size_t smc = s->smem_closest, sms = s->smem_shadow;
     const int grid_closest[2] = {persistent_grid((const void*)k_trace<false, false>, kTraceThreads, smc),
@@ -357,12 +380,29 @@ int sg_render(SgScene* s, const SgRenderParams* rp, SgFilmPixel* film, SgStats* 
     CU(cudaMemsetAsync(s->d_film, 0, npix * sizeof(SgFilmPixel), g_stream));
     int rc = sg_render_device(s, rp, s->d_film, stats, g_stream);
     if (rc != SG_OK) return rc;
-    std::vector<SgFilmPixel> tmp(npix);
-    CU(cudaMemcpy(tmp.data(), s->d_film, npix * sizeof(SgFilmPixel), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < npix; ++i) {
-        for (int c = 0; c < 3; ++c) film[i].rgb_sum[c] += tmp[i].rgb_sum[c];
-        film[i].weight_sum += tmp[i].weight_sum;
+    // D2H through a pinned staging buffer (allocated once per scene), then accumulate into the caller's film
+    if (s->h_film_pixels < npix) {
+        if (s->h_film) cudaFreeHost(s->h_film);
+        s->h_film = nullptr; s->h_film_pixels = 0;
+        CU(cudaHostAlloc((void**)&s->h_film, npix * sizeof(SgFilmPixel), cudaHostAllocDefault));
+        s->h_film_pixels = npix;
     }
+    CU(cudaMemcpyAsync(s->h_film, s->d_film, npix * sizeof(SgFilmPixel), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    const double* src = reinterpret_cast<const double*>(s->h_film);
+    double* dst = reinterpret_cast<double*>(film);
+    const bool overwrite = (rp->flags & SG_RENDER_OVERWRITE_FILM) != 0;
+    const size_t n = 4 * npix;
+    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned t) {
+        const size_t b = n * t / nt, e = n * (t + 1) / nt;
+        if (overwrite) std::memcpy(dst + b, src + b, (e - b) * sizeof(double));
+        else for (size_t i = b; i < e; ++i) dst[i] += src[i];
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
     return SG_OK;
 }
 

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshimmer_gpu.so")
+LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
 SG_ABI_VERSION = 1
@@ -23,6 +23,7 @@ SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
 SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE = 0, 1, 2
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
 SG_OPT_DISABLE_TEXTURE_FILTERING, SG_OPT_FORCE_DIFFUSE = 4, 8
+SG_RENDER_COUNT_VISITS, SG_RENDER_TIME_KERNELS, SG_RENDER_OVERWRITE_FILM = 1, 2, 4
 
 
 class SgBvhNode(C.Structure):
@@ -88,7 +89,7 @@ class SgSceneDesc(C.Structure):
 class SgRenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("samples_per_pixel", C.c_int32), ("sample_begin", C.c_int32),
                 ("sample_end", C.c_int32), ("max_depth", C.c_int32), ("regularize", C.c_int32),
-                ("option_flags", C.c_uint32), ("max_paths_in_flight", C.c_int32), ("reserved", C.c_int32)]
+                ("option_flags", C.c_uint32), ("max_paths_in_flight", C.c_int32), ("flags", C.c_int32)]
 
 
 class SgFilmPixel(C.Structure):

@@ -90,7 +90,7 @@ class WavefrontPathIntegrator(Integrator):
         self.stats = ffi.SgStats()
 
     # -- helpers -----------------------------------------------------------------------------
-    def _params(self, options, sample_range=None, reserved=0):
+    def _params(self, options, sample_range=None, flags=0):
         spp = options.pixel_samples if options.pixel_samples is not None else self.samples_per_pixel
         seed = self.sampler_seed if self.sampler_seed is not None else options.seed
         p = ffi.SgRenderParams()
@@ -98,19 +98,19 @@ class WavefrontPathIntegrator(Integrator):
         p.samples_per_pixel = spp
         p.sample_begin, p.sample_end = sample_range if sample_range else (0, spp)
         p.max_depth = self.max_depth; p.regularize = int(self.regularize)
-        p.option_flags = options.flags(); p.max_paths_in_flight = self.max_paths_in_flight; p.reserved = reserved
+        p.option_flags = options.flags(); p.max_paths_in_flight = self.max_paths_in_flight; p.flags = flags
         return p
 
     # -- Integrator::render ------------------------------------------------------------------
-    def render(self, options: Options, sample_range=None, reserved=0):
+    def render(self, options: Options, sample_range=None, flags=0):
         """Renders into self.film (host, f64 rgb_sum[3] + weight_sum per pixel, row-major)."""
-        p = self._params(options, sample_range, reserved)
+        p = self._params(options, sample_range, flags)
         ffi.check(self._lib.sg_render(self._handle, C.byref(p), self.film.ctypes.data, C.byref(self.stats)), "sg_render")
         return self.film
 
-    def render_device(self, options: Options, d_film_ptr, sample_range=None, stream=None, reserved=0):
+    def render_device(self, options: Options, d_film_ptr, sample_range=None, stream=None, flags=0):
         """Accumulates into a device film buffer (e.g. a torch.float64 CUDA tensor's data_ptr())."""
-        p = self._params(options, sample_range, reserved)
+        p = self._params(options, sample_range, flags)
         ffi.check(self._lib.sg_render_device(self._handle, C.byref(p), C.c_void_p(d_film_ptr), C.byref(self.stats),
                                              C.c_void_p(stream) if stream else None), "sg_render_device")
 
