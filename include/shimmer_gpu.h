@@ -105,7 +105,9 @@ typedef struct SgSpectrum {
 typedef enum SgMaterialKind {
     SG_MATERIAL_DIFFUSE = 0,    /* DiffuseMaterial    material.rs:298-338  spec_a = reflectance          */
     SG_MATERIAL_CONDUCTOR = 1,  /* ConductorMaterial  material.rs:453-526  spec_a = eta, spec_b = k      */
-    SG_MATERIAL_DIELECTRIC = 2  /* DielectricMaterial material.rs:600-662  spec_a = eta (`Spectrum`)     */
+    SG_MATERIAL_DIELECTRIC = 2, /* DielectricMaterial material.rs:600-662  spec_a = eta (`Spectrum`)     */
+    SG_MATERIAL_COATED_DIFFUSE = 3 /* CoatedDiffuseMaterial material.rs:913-992: spec_a = reflectance, spec_b = albedo,
+                                      spec_c = eta, thickness, g, max_depth, n_samples (LayeredBxDF bxdf.rs:883-1620) */
 } SgMaterialKind;
 enum {
     SG_MAT_REMAP_ROUGHNESS = 1,  /* `remaproughness`, default true                      */
@@ -120,7 +122,11 @@ typedef struct SgMaterial {
     float   u_roughness;
     float   v_roughness;
     float   displacement;  /* constant displacement texture value (0 by default) */
-    float   pad;
+    int32_t spec_c;        /* coated diffuse: eta spectrum                        */
+    float   thickness;     /* coated diffuse: `thickness` (0.01)                  */
+    float   g;             /* coated diffuse: HG asymmetry (0)                    */
+    int32_t max_depth;     /* coated diffuse: `maxdepth` (10)                     */
+    int32_t n_samples;     /* coated diffuse: `nsamples` (1)                      */
 } SgMaterial;
 
 /* ---- lights (src/light.rs) ------------------------------------------------- */

@@ -317,7 +317,11 @@ struct TR {
 
 // ---- BxDFs (bxdf.rs) + BSDF frame wrapper (bsdf.rs) ---------------------------
 enum { BX_UNSET = 0, BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 };   // bxdf.rs:1773-1789
-struct BSDFSample { Spec f; V3 wi; Float pdf; int flags; Float eta; };
+struct BSDFSample { Spec f; V3 wi; Float pdf; int flags; Float eta; bool proportional = false; };
+
+}  // namespace orc
+#include "orc_layered.h"     // CoatedDiffuse = LayeredBxDF<Dielectric, Diffuse> (needs TR / BSDFSample above)
+namespace orc {
 
 struct BSDF {
     int kind;            // SgMaterialKind
@@ -325,7 +329,10 @@ struct BSDF {
     Spec k;              // conductor k
     Float eta;           // dielectric
     TR mf;
+    Layered lay;         // CoatedDiffuse
+    uint64_t layer_seed = 0;   // seeds the LayeredBxDF's private generator for the NEXT f/sample_f/pdf call
     V3 fx, fy, fz;       // Frame::from_xz(normalize(dpdus), ns)  bsdf.rs:22-28, frame.rs:14-17
+    Rng layer_rng() const { Rng r; r.seed_from_u64(layer_seed); return r; }
 
     V3 to_local(V3 v) const { return v3(dot(v, fx), dot(v, fy), dot(v, fz)); }          // frame.rs:39-41
     V3 from_local(V3 v) const { return v.x * fx + v.y * fy + v.z * fz; }               // frame.rs:51-53
@@ -334,6 +341,7 @@ struct BSDF {
         switch (kind) {
         case SG_MATERIAL_DIFFUSE: return spec_is_zero(r) ? BX_UNSET : (BX_DIFFUSE | BX_REFLECTION);                 // bxdf.rs:256-262
         case SG_MATERIAL_CONDUCTOR: return mf.effectively_smooth() ? (BX_SPECULAR | BX_REFLECTION) : (BX_GLOSSY | BX_REFLECTION);   // :447-453
+        case SG_MATERIAL_COATED_DIFFUSE: return lay.flags();
         default: {                                                                                                 // :778-790
             int f = (eta == 1.0f) ? BX_TRANSMISSION : (BX_REFLECTION | BX_TRANSMISSION);
             return f | (mf.effectively_smooth() ? BX_SPECULAR : BX_GLOSSY);
@@ -342,6 +350,7 @@ struct BSDF {
     }
     // local-space f
     Spec f_local(V3 wo, V3 wi) const {
+        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.f(wo, wi, r); }
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // bxdf.rs:196-202
             if (!same_hemisphere(wo, wi)) return spec_const(0.0f);
@@ -378,6 +387,7 @@ struct BSDF {
         }
     }
     Float pdf_local(V3 wo, V3 wi) const {
+        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.pdf(wo, wi, r); }
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // :240-254
             if (!same_hemisphere(wo, wi)) return 0.0f;
@@ -410,7 +420,8 @@ struct BSDF {
         }
     }
     bool sample_local(V3 wo, Float uc, V2 u, BSDFSample* bs) const {
-        bs->eta = 1.0f;
+        bs->eta = 1.0f; bs->proportional = false;
+        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.sample_f(wo, uc, u, r, bs, &bs->proportional); }
         switch (kind) {
         case SG_MATERIAL_DIFFUSE: {                                             // :204-238
             V3 wi = sample_cosine_hemisphere(u);
@@ -526,6 +537,20 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         b.r = spectrum_sample(D, m.spec_a, lambda);
         b.k = spectrum_sample(D, m.spec_b, lambda);
         b.mf = TR::make(ur, vr);
+    } else if (m.kind == SG_MATERIAL_COATED_DIFFUSE) {                       // material.rs:917-963
+        b.lay.r = spec_clamp(spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
+        Float ur = m.u_roughness, vr = m.v_roughness;
+        if (m.flags & SG_MAT_REMAP_ROUGHNESS) { ur = std::sqrt(ur); vr = std::sqrt(vr); }
+        b.lay.mf = TR::make(ur, vr);
+        b.lay.thickness = m.thickness;
+        Float sampled_eta = spectrum_get(D, m.spec_c, lambda.lambda[0]);
+        if (D->spectra[m.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lambda);
+        if (sampled_eta == 0.0f) sampled_eta = 1.0f;
+        b.lay.eta = sampled_eta;
+        b.lay.albedo = spec_clamp(spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
+        b.lay.g = clampf(m.g, -1.0f, 1.0f);
+        b.lay.max_depth = m.max_depth; b.lay.n_samples = m.n_samples;
+        b.mf = b.lay.mf;
     } else {
         Float sampled_eta = spectrum_get(D, m.spec_a, lambda.lambda[0]);
         if (D->spectra[m.spec_a].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lambda);

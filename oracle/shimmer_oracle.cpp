@@ -36,7 +36,12 @@ struct PathCtx {
 };
 
 // PathIntegrator::sample_ld integrator.rs:897-963
-static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, const BSDF& bsdf, const Wavelengths& lambda, Rng& rng) {
+// Seed for the LayeredBxDF's private generator (the reference uses from_entropy, bxdf.rs:1011): derived from the
+// path stream's current state and the call site (1 = f in sample_ld, 2 = pdf in sample_ld, 3 = sample_f, 4 = pdf after
+// sample_f) WITHOUT advancing the path stream.  Same definition in sg_wavefront.cuh.
+static inline uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s[0] ^ (site * 0x9e3779b97f4a7c15ULL)); }
+
+static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, BSDF& bsdf, const Wavelengths& lambda, Rng& rng) {
     const SgSceneDesc* D = pc.sc->d;
     LightSampleContext ctx; ctx.pi = intr.pi; ctx.n = intr.n; ctx.ns = intr.sn;
     int flags = bsdf.flags();
@@ -56,6 +61,7 @@ static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, const B
     if (!light_sample_li(*pc.sc, lt, ctx, u_light, lambda, &ls)) return spec_const(0.0f);
     if (spec_is_zero(ls.l) || ls.pdf == 0.0f) return spec_const(0.0f);
     V3 wo = intr.wo, wi = ls.wi;
+    bsdf.layer_seed = layer_seed(rng, 1);
     Spec f = bsdf.f(wo, wi) * abs_dot(wi, intr.sn);
     if (spec_is_zero(f)) return spec_const(0.0f);
     Ray sray = spawn_ray_to_both_offset(intr.pi, intr.n, ls.p_light, ls.n_light);   // IntegratorBase::unoccluded :114-116
@@ -64,6 +70,7 @@ static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, const B
     if (bvh_intersect(*pc.sc, sray, 1.0f - 0.0001f, true, &h, pc.ctr)) return spec_const(0.0f);
     Float p_l = p_choose * ls.pdf;
     if (lt.kind == SG_LIGHT_POINT) return ls.l * f / p_l;
+    bsdf.layer_seed = layer_seed(rng, 2);
     Float p_b = bsdf.pdf(wo, wi);
     Float w_l = power_heuristic(p_l, p_b);
     return w_l * ls.l * f / p_l;
@@ -111,7 +118,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
             }
         }
         BSDF bsdf = get_bsdf(D, si, lambda);                                      // :816
-        if (pc.rp->regularize && any_non_specular_bounces) bsdf.mf.regularize();  // :825-828
+        if (pc.rp->regularize && any_non_specular_bounces) { bsdf.mf.regularize(); bsdf.lay.mf.regularize(); }  // :825-828
         if (depth == pc.rp->max_depth) break;
         depth += 1;
         if (bsdf.flags() & (BX_DIFFUSE | BX_GLOSSY)) {                            // :837-841
@@ -122,9 +129,11 @@ static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
         Float u = rng.get_1d();
         V2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
         BSDFSample bs;
+        bsdf.layer_seed = layer_seed(rng, 3);
         if (!bsdf.sample_f(wo, u, u2, &bs)) break;
         beta = beta * (bs.f * abs_dot(bs.wi, si.sn) / bs.pdf);                    // :859
-        p_b = bs.pdf;
+        if (bs.proportional) { bsdf.layer_seed = layer_seed(rng, 4); p_b = bsdf.pdf(wo, bs.wi); }   // :860-865
+        else p_b = bs.pdf;
         specular_bounce = (bs.flags & BX_SPECULAR) != 0;
         any_non_specular_bounces |= !specular_bounce;
         if (bs.flags & BX_TRANSMISSION) eta_scale *= sqr(bs.eta);

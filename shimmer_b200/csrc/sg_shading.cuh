@@ -315,21 +315,31 @@ struct TR {
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 };   // bxdf.rs:1773-1789
 struct BSDFSample { Spec f; float3 wi; float pdf; int flags; float eta; };
 
+}  // namespace sg
+#include "sg_layered.cuh"     // CoatedDiffuse (needs TR, BSDFSample and the dielectric helpers above)
+namespace sg {
+
 template <int KIND> struct BSDF {
     Spec r, k;            // diffuse: r ; conductor: eta (in r), k
     float eta;            // dielectric
     TR mf;
+    Layered lay;          // CoatedDiffuse only
+    uint64_t layer_seed;  // seeds the LayeredBxDF's private generator for the next f / sample_f / pdf call
+    bool proportional;    // BSDFSample::pdf_is_proportional of the last sample_f
     float3 fx, fy, fz;    // Frame::from_xz(normalize(dpdus), ns), bsdf.rs:22-28
+    SGD Rng layer_rng() const { Rng r; r.seed_from_u64(layer_seed); return r; }
 
     SGD float3 to_local(float3 v) const { return f3(dot3(v, fx), dot3(v, fy), dot3(v, fz)); }      // frame.rs:39-41
     SGD float3 from_local(float3 v) const { return v.x * fx + v.y * fy + v.z * fz; }               // frame.rs:51-53
     SGD int flags() const {
+        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.flags();
         if (KIND == SG_MATERIAL_DIFFUSE) return spec_zero(r) ? 0 : (BX_DIFFUSE | BX_REFLECTION);     // bxdf.rs:256-262
         if (KIND == SG_MATERIAL_CONDUCTOR) return (mf.smooth() ? BX_SPECULAR : BX_GLOSSY) | BX_REFLECTION;   // :447-453
         int f = (eta == 1.0f) ? BX_TRANSMISSION : (BX_REFLECTION | BX_TRANSMISSION);               // :778-790
         return f | (mf.smooth() ? BX_SPECULAR : BX_GLOSSY);
     }
     SGD Spec f_local(float3 wo, float3 wi) const {
+        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.f(wo, wi, layer_rng());
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :196-202
             if (!same_hemisphere(wo, wi)) return spec1(0.0f);
             return r * kInvPi;
@@ -362,6 +372,7 @@ template <int KIND> struct BSDF {
         }
     }
     SGD float pdf_local(float3 wo, float3 wi) const {
+        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.pdf(wo, wi, layer_rng());
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :240-254
             if (!same_hemisphere(wo, wi)) return 0.0f;
             return fabsf(wi.z) * kInvPi;
@@ -390,8 +401,9 @@ template <int KIND> struct BSDF {
             return mf.pdf(wo, wm) * dwm_dwi * pt / (pr + pt);
         }
     }
-    SGD bool sample_local(float3 wo, float uc, float2 u, BSDFSample& bs) const {
-        bs.eta = 1.0f;
+    SGD bool sample_local(float3 wo, float uc, float2 u, BSDFSample& bs, bool& prop) const {
+        bs.eta = 1.0f; prop = false;
+        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.sample_f(wo, uc, u, layer_rng(), bs, prop);
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :204-238
             float3 wi = sample_cosine_hemisphere(u);
             if (wo.z < 0.0f) wi.z *= -1.0f;
@@ -461,10 +473,10 @@ template <int KIND> struct BSDF {
         if (wo.z == 0.0f) return spec1(0.0f);
         return f_local(wo, wi);
     }
-    SGD bool sample_f(float3 wo_r, float uc, float2 u, BSDFSample& bs) const {     // bsdf.rs:60-82
+    SGD bool sample_f(float3 wo_r, float uc, float2 u, BSDFSample& bs, bool& prop) const {     // bsdf.rs:60-82
         float3 wo = to_local(wo_r);
         if (wo.z == 0.0f || !(flags() & (BX_REFLECTION | BX_TRANSMISSION))) return false;
-        if (!sample_local(wo, uc, u, bs)) return false;
+        if (!sample_local(wo, uc, u, bs, prop)) return false;
         if (spec_zero(bs.f) || bs.pdf == 0.0f || bs.wi.z == 0.0f) return false;
         bs.wi = from_local(bs.wi);
         return true;

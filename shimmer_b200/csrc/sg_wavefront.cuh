@@ -35,9 +35,9 @@ struct PathState {
 };
 static constexpr int kPathBytes = 16 * 16 + 4 + 4 + 4 + 8;   // per-path HBM footprint (276 B)
 
-enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_NKINDS = 4 };
+enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_NKINDS = 5 };
 // per-depth counter block (uint32 x 16)
-enum { C_NRAY = 0, C_NSHADE = 1 /*..4*/, C_NSHADOW = 5, C_CUR_CLOSEST = 6, C_CUR_SHADOW = 7, C_STRIDE = 16 };
+enum { C_NRAY = 0, C_NSHADE = 1 /*..5*/, C_NSHADOW = 6, C_CUR_CLOSEST = 7, C_CUR_SHADOW = 8, C_STRIDE = 16 };
 
 struct Queues {
     uint32_t* ray[2];
@@ -250,6 +250,10 @@ __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DSce
     }
 }
 
+// Seed of the LayeredBxDF's private generator: path-stream state x call site (1 = f in sample_ld, 2 = pdf in
+// sample_ld, 3 = sample_f, 4 = pdf after sample_f); does not advance the path stream.  Same as the oracle.
+SGD uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s0 ^ (site * 0x9e3779b97f4a7c15ULL)); }
+
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
 #ifndef SG_SHADE_MIN_BLOCKS
@@ -313,6 +317,19 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
                 bsdf.r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);          // material.rs:307-310
+            } else if (KIND == SG_MATERIAL_COATED_DIFFUSE) {                                    // material.rs:917-963
+                bsdf.lay.r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);
+                float ur = mat.u_roughness, vr = mat.v_roughness;
+                if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }
+                bsdf.lay.mf = TR::make(ur, vr);
+                bsdf.lay.thickness = mat.thickness;
+                float se = spectrum_get(sc, mat.spec_c, lam.lambda.x);
+                if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
+                if (se == 0.0f) se = 1.0f;
+                bsdf.lay.eta = se;
+                bsdf.lay.albedo = spec_clamp(spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                bsdf.lay.g = clampf(mat.g, -1.0f, 1.0f);
+                bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
             } else {
                 float ur = mat.u_roughness, vr = mat.v_roughness;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }     // roughness_to_alpha
@@ -327,7 +344,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 bsdf.mf = TR::make(ur, vr);
             }
             bsdf.fx = normalize3(s.sdpdu); bsdf.fz = s.sn; bsdf.fy = cross3(bsdf.fz, bsdf.fx);
-            if (rc.regularize && any_non_specular) bsdf.mf.regularize();                        // :825-828
+            if (rc.regularize && any_non_specular) { bsdf.mf.regularize(); if (KIND == SG_MATERIAL_COATED_DIFFUSE) bsdf.lay.mf.regularize(); }   // :825-828
 
             bool alive = pdepth != rc.max_depth;                                               // :830-833
             if (alive) {
@@ -350,12 +367,14 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                         const SgLight lt = sc.lights[li];
                         LightSample ls;
                         if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
+                            bsdf.layer_seed = layer_seed(rng, 1);
                             Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);
                             if (!spec_zero(f)) {
                                 const float p_l = p_choose * ls.pdf;
                                 Spec ld;
                                 if (lt.kind == SG_LIGHT_POINT) ld = ls.l * f / p_l;
                                 else {
+                                    bsdf.layer_seed = layer_seed(rng, 2);
                                     float p_bsdf = bsdf.pdf(wo, ls.wi);
                                     float w_l = power_heuristic(p_l, p_bsdf);
                                     ld = w_l * ls.l * f / p_l;
@@ -375,11 +394,13 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 // ---- BSDF sampling :843-875 ----
                 const float u = rng.get_1d();
                 float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
-                BSDFSample bs;
-                alive = bsdf.sample_f(wo, u, u2, bs);
+                BSDFSample bs; bool prop = false;
+                bsdf.layer_seed = layer_seed(rng, 3);
+                alive = bsdf.sample_f(wo, u, u2, bs, prop);
                 if (alive) {
                     beta = beta * (bs.f * absdot3(bs.wi, s.sn) / bs.pdf);
-                    p_b = bs.pdf;
+                    if (prop) { bsdf.layer_seed = layer_seed(rng, 4); p_b = bsdf.pdf(wo, bs.wi); }      // pdf_is_proportional :860-865
+                    else p_b = bs.pdf;
                     specular_bounce = (bs.flags & BX_SPECULAR) != 0;
                     any_non_specular = any_non_specular || !specular_bounce;
                     if (bs.flags & BX_TRANSMISSION) eta_scale *= sqr(bs.eta);
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 st.pb_eta[path] = make_float2(p_b, eta_scale);
                 st.flags[path] = (uint32_t)pdepth | (specular_bounce ? 256u : 0u) | (any_non_specular ? 512u : 0u);
             }
-            if (KIND == SG_MATERIAL_DIELECTRIC) st.lpdf[path] = lam.pdf;                        // terminate_secondary
+            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE) st.lpdf[path] = lam.pdf;   // terminate_secondary
             want_next = alive;
         }
         __syncwarp();

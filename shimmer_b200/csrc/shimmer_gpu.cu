@@ -56,7 +56,7 @@ struct SgScene {
     Workspace ws;
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
-    bool kinds_present[3] = {false, false, false};
+    bool kinds_present[4] = {false, false, false, false};
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
     uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
@@ -141,7 +141,10 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     }
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
-        if (m.kind < 0 || m.kind > SG_MATERIAL_DIELECTRIC) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.kind < 0 || m.kind > SG_MATERIAL_COATED_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.kind == SG_MATERIAL_COATED_DIFFUSE && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra || m.spec_c < 0 || m.spec_c >= (int32_t)desc->n_spectra ||
+                                                     m.max_depth < 0 || m.n_samples < 1))
+            return fail(SG_ERR_INVALID_ARGUMENT, "coated diffuse material parameters out of range");
         if (m.spec_a < 0 || m.spec_a >= (int32_t)desc->n_spectra || (m.kind == SG_MATERIAL_CONDUCTOR && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra)))
             return fail(SG_ERR_INVALID_ARGUMENT, "material spectrum id out of range");
     }
@@ -332,6 +335,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             if (s->kinds_present[SG_MATERIAL_DIFFUSE]) { k_shade<SG_MATERIAL_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->kinds_present[SG_MATERIAL_CONDUCTOR]) { k_shade<SG_MATERIAL_CONDUCTOR><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->kinds_present[SG_MATERIAL_DIELECTRIC]) { k_shade<SG_MATERIAL_DIELECTRIC><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            if (s->kinds_present[SG_MATERIAL_COATED_DIFFUSE]) { k_shade<SG_MATERIAL_COATED_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
                 if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);

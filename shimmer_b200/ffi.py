@@ -18,7 +18,7 @@ SG_ABI_VERSION = 1
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
 SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
 SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
-SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC = 0, 1, 2
+SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE = 0, 1, 2, 3
 SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
 SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE = 0, 1, 2
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
@@ -47,7 +47,8 @@ class SgSpectrum(C.Structure):
 
 class SgMaterial(C.Structure):
     _fields_ = [("kind", C.c_int32), ("spec_a", C.c_int32), ("spec_b", C.c_int32), ("flags", C.c_int32),
-                ("u_roughness", C.c_float), ("v_roughness", C.c_float), ("displacement", C.c_float), ("pad", C.c_float)]
+                ("u_roughness", C.c_float), ("v_roughness", C.c_float), ("displacement", C.c_float), ("spec_c", C.c_int32),
+                ("thickness", C.c_float), ("g", C.c_float), ("max_depth", C.c_int32), ("n_samples", C.c_int32)]
 
 
 class SgLight(C.Structure):

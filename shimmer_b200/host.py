@@ -265,6 +265,14 @@ class SceneBuilder:
                                    flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
         return len(self.materials) - 1
 
+    def coated_diffuse(self, reflectance, eta=("const", 1.5), roughness=0.0, thickness=0.01, albedo=("const", 0.0), g=0.0,
+                       max_depth=10, n_samples=1, remap=True):
+        """CoatedDiffuseMaterial::create (material.rs:820-903); displacement defaults to None."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_COATED_DIFFUSE, spec_a=self.spectrum(reflectance), spec_b=self.spectrum(albedo),
+                                   spec_c=self.spectrum(eta), flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness,
+                                   thickness=thickness, g=g, max_depth=max_depth, n_samples=n_samples))
+        return len(self.materials) - 1
+
     # -- camera / film -----------------------------------------------------------------------
     def set_camera(self, pos, look, up, fov, resolution, lens_radius=0.0, focal_distance=1e6, crop=None):
         """PerspectiveCamera::create/new (camera.rs:839-963) + CameraTransform::new (:506-523) +
@@ -452,6 +460,8 @@ class SceneBuilder:
         for i, m in enumerate(self.materials):
             mats[i].kind, mats[i].spec_a, mats[i].spec_b, mats[i].flags = m["kind"], m["spec_a"], m["spec_b"], m["flags"]
             mats[i].u_roughness, mats[i].v_roughness, mats[i].displacement = m["ur"], m["vr"], 0.0
+            mats[i].spec_c = m.get("spec_c", -1); mats[i].thickness = m.get("thickness", 0.0); mats[i].g = m.get("g", 0.0)
+            mats[i].max_depth = m.get("max_depth", 0); mats[i].n_samples = m.get("n_samples", 0)
         A["materials"] = mats
         A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
         A["meshes"] = mesh_rows

@@ -188,6 +188,10 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         mat = b.dielectric(named_spectrum("glass-BK7"))
     elif kind == "roughglass":
         mat = b.dielectric(("const", 1.5), roughness=0.2)
+    elif kind == "coated":
+        mat = b.coated_diffuse(_red())
+    elif kind == "coatedrough":
+        mat = b.coated_diffuse(_green(), roughness=0.15, albedo=("const", 0.4), g=0.3, thickness=0.05)
     else:
         raise ValueError(kind)
     P, I = displaced_sphere(12, 16, center=(0.0, 0.6, 0.0), radius=0.6, amp=0.0)

@@ -168,7 +168,7 @@ def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
     assert rmse < 0.01
 
 
-@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass"])
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"])
 def test_tiny_scene_films(kind):
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
     integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 4, "seed": 5})
