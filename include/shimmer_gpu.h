@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -127,7 +127,35 @@ typedef struct SgMaterial {
     float   g;             /* coated diffuse: HG asymmetry (0)                    */
     int32_t max_depth;     /* coated diffuse: `maxdepth` (10)                     */
     int32_t n_samples;     /* coated diffuse: `nsamples` (1)                      */
+    int32_t tex_reflectance;  /* SpectrumImageTexture for `reflectance` (diffuse / coated diffuse) or -1 -> spec_a */
+    int32_t tex_displacement; /* FloatImageTexture for `displacement` (bump_map, material.rs:1477-1509) or -1     */
+    int32_t pad2[2];
 } SgMaterial;
+
+/* ---- image textures (src/texture.rs:700-808, src/mipmap.rs, src/image.rs:134-177,619-646) ------
+ * The host owns image decoding and pyramid generation (image.rs:699-846); it passes every MIP
+ * level as linear f32 texels (what `Image::get_channel` returns after colour-encoding).  Level 0 is
+ * the full-resolution image, the last level is 1x1.  One-channel images evaluate to a constant
+ * spectrum (texture.rs:803-807); RGB images need the third-party rgb2spec tables, which are missing
+ * from the reference checkout (.MISSING_LARGE_BLOBS) -> not accepted yet (SG_ERR_UNSUPPORTED). */
+typedef enum SgWrapMode { SG_WRAP_REPEAT = 0, SG_WRAP_BLACK = 1, SG_WRAP_CLAMP = 2 } SgWrapMode;       /* image.rs WrapMode */
+typedef enum SgFilterFunction { SG_FILTER_POINT = 0, SG_FILTER_BILINEAR = 1, SG_FILTER_TRILINEAR = 2, SG_FILTER_EWA = 3 } SgFilterFunction; /* mipmap.rs:337-345 */
+typedef struct SgImageLevel {
+    uint32_t offset;           /* into SgSceneDesc.texels                */
+    int32_t  res[2];           /* resolution x, y                        */
+    uint32_t pad;
+} SgImageLevel;
+typedef struct SgTexture {
+    int32_t  n_channels;       /* 1 (3 = RGB: unsupported, see above)    */
+    int32_t  n_levels;
+    uint32_t first_level;      /* into SgSceneDesc.image_levels          */
+    int32_t  wrap;             /* SgWrapMode, `wrap` default repeat      */
+    int32_t  filter;           /* SgFilterFunction, default bilinear (texture.rs:741) */
+    float    max_anisotropy;   /* default 8                              */
+    float    scale;            /* default 1                              */
+    int32_t  invert;
+    float    su, sv, du, dv;   /* UVMapping (texture.rs:896-936)         */
+} SgTexture;
 
 /* ---- lights (src/light.rs) ------------------------------------------------- */
 typedef enum SgLightKind {
@@ -188,6 +216,10 @@ typedef struct SgSceneDesc {
     uint32_t n_pool;       const float*       spectrum_pool;
     uint32_t n_materials;  const SgMaterial*  materials;
     uint32_t n_lights;     const SgLight*     lights;      /* order = light sampler order  */
+    uint32_t n_textures;   const SgTexture*   textures;
+    uint32_t n_image_levels; const SgImageLevel* image_levels;
+    uint64_t n_texels;     const float*       texels;
+    const float* mip_filter_lut;                            /* MIP_FILTER_LUT[128], mipmap.rs:388-518 (EWA) or NULL */
     SgCamera camera;
     SgFilm   film;
 } SgSceneDesc;

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 1
+SG_ABI_VERSION = 2
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -48,7 +48,22 @@ class SgSpectrum(C.Structure):
 class SgMaterial(C.Structure):
     _fields_ = [("kind", C.c_int32), ("spec_a", C.c_int32), ("spec_b", C.c_int32), ("flags", C.c_int32),
                 ("u_roughness", C.c_float), ("v_roughness", C.c_float), ("displacement", C.c_float), ("spec_c", C.c_int32),
-                ("thickness", C.c_float), ("g", C.c_float), ("max_depth", C.c_int32), ("n_samples", C.c_int32)]
+                ("thickness", C.c_float), ("g", C.c_float), ("max_depth", C.c_int32), ("n_samples", C.c_int32),
+                ("tex_reflectance", C.c_int32), ("tex_displacement", C.c_int32), ("pad2", C.c_int32 * 2)]
+
+
+class SgImageLevel(C.Structure):
+    _fields_ = [("offset", C.c_uint32), ("res", C.c_int32 * 2), ("pad", C.c_uint32)]
+
+
+class SgTexture(C.Structure):
+    _fields_ = [("n_channels", C.c_int32), ("n_levels", C.c_int32), ("first_level", C.c_uint32), ("wrap", C.c_int32),
+                ("filter", C.c_int32), ("max_anisotropy", C.c_float), ("scale", C.c_float), ("invert", C.c_int32),
+                ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float)]
+
+
+SG_WRAP_REPEAT, SG_WRAP_BLACK, SG_WRAP_CLAMP = 0, 1, 2
+SG_FILTER_POINT, SG_FILTER_BILINEAR, SG_FILTER_TRILINEAR, SG_FILTER_EWA = 0, 1, 2, 3
 
 
 class SgLight(C.Structure):
@@ -84,6 +99,10 @@ class SgSceneDesc(C.Structure):
                 ("n_pool", C.c_uint32), ("spectrum_pool", C.POINTER(C.c_float)),
                 ("n_materials", C.c_uint32), ("materials", C.POINTER(SgMaterial)),
                 ("n_lights", C.c_uint32), ("lights", C.POINTER(SgLight)),
+                ("n_textures", C.c_uint32), ("textures", C.POINTER(SgTexture)),
+                ("n_image_levels", C.c_uint32), ("image_levels", C.POINTER(SgImageLevel)),
+                ("n_texels", C.c_uint64), ("texels", C.POINTER(C.c_float)),
+                ("mip_filter_lut", C.POINTER(C.c_float)),
                 ("camera", SgCamera), ("film", SgFilm)]
 
 

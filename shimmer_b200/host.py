@@ -462,6 +462,7 @@ class SceneBuilder:
             mats[i].u_roughness, mats[i].v_roughness, mats[i].displacement = m["ur"], m["vr"], 0.0
             mats[i].spec_c = m.get("spec_c", -1); mats[i].thickness = m.get("thickness", 0.0); mats[i].g = m.get("g", 0.0)
             mats[i].max_depth = m.get("max_depth", 0); mats[i].n_samples = m.get("n_samples", 0)
+            mats[i].tex_reflectance = m.get("tex_reflectance", -1); mats[i].tex_displacement = m.get("tex_displacement", -1)
         A["materials"] = mats
         A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
         A["meshes"] = mesh_rows

@@ -34,6 +34,11 @@ def main():
     t = {}
     t.update(arrays(os.path.join(REF, "cie.rs")))
     t.update(arrays(os.path.join(REF, "named_spectrum.rs")))
+    # the EWA filter's 128-entry Gaussian LUT (mipmap.rs:388-518; pbrt's MIPFilterLUT values)
+    src = open(os.path.join(REF, "..", "mipmap.rs")).read()
+    m = re.search(r"const MIP_FILTER_LUT: \[Float; MIP_FILTER_LUT_SIZE\] = \[(.*?)\];", src, re.S)
+    t["MIP_FILTER_LUT"] = np.asarray([float(x) for x in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", m.group(1))], dtype=np.float32)
+    assert t["MIP_FILTER_LUT"].shape == (128,)
     for k, v in sorted(t.items()):
         print(f"{k:28s} {v.shape}")
     assert t["CIE_X"].shape == (471,) and t["CIE_LAMBDA"][0] == 360 and t["CIE_LAMBDA"][-1] == 830
