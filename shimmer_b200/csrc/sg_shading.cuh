@@ -769,10 +769,11 @@ SGD void camera_stage(const DScene& sc, uint32_t option_flags, int px, int py, R
 }
 
 // ---------------- film: PixelSensor::to_sensor_rgb (film.rs:907-914) + RgbFilm::add_sample (:548-574) --------
-SGD void film_add_sample(const DScene& sc, double* film_px, Spec L, const Wavelengths& lam, float weight) {
+// PixelSensor::to_sensor_rgb film.rs:907-914 + the clamp of RgbFilm::add_sample film.rs:548-567: the sensor RGB one
+// sample contributes (before the filter weight).
+SGD void film_sample_rgb(const DScene& sc, Spec L, const Wavelengths& lam, float rgb[3]) {
     Spec l = make_float4(lam.pdf.x != 0.0f ? L.x / lam.pdf.x : 0.0f, lam.pdf.y != 0.0f ? L.y / lam.pdf.y : 0.0f,
                          lam.pdf.z != 0.0f ? L.z / lam.pdf.z : 0.0f, lam.pdf.w != 0.0f ? L.w / lam.pdf.w : 0.0f);   // safe_div
-    float rgb[3];
     const int ids[3] = {sc.film.r_bar, sc.film.g_bar, sc.film.b_bar};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -782,11 +783,6 @@ SGD void film_add_sample(const DScene& sc, double* film_px, Spec L, const Wavele
     }
     float m = fmaxf(fmaxf(rgb[0], rgb[1]), rgb[2]);
     if (m > sc.film.max_component_value) { for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] * sc.film.max_component_value / m; }
-    // samples of one pixel live in different wavefront slots -> f64 atomics (RED.ADD.F64)
-    atomicAdd(film_px + 0, (double)(weight * rgb[0]));
-    atomicAdd(film_px + 1, (double)(weight * rgb[1]));
-    atomicAdd(film_px + 2, (double)(weight * rgb[2]));
-    atomicAdd(film_px + 3, (double)weight);
 }
 
 }  // namespace sg

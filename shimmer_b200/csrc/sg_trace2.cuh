@@ -55,11 +55,29 @@ struct TraceScene {
     const float4* tri_verts;    // 3 float4 per primitive (see sg_scene.cuh)
     float root_bmin[3], root_bmax[3];
     uint32_t root_ref;          // kEmptyRef for an empty scene
-    int stack_depth;            // entries per thread
+    int stack_depth;            // entries per thread (tree depth)
+    int smem_levels;            // entries per thread held in shared memory; deeper entries spill to local memory
     int leaf_threshold;         // warp-vote scheduling knobs (see trace_persistent)
     int refill_threshold;
     int interior_burst;
     int prefetch;
+};
+
+// Per-thread traversal stack: the first `levels` entries live in shared memory (level-major, so a warp's
+// accesses to one level hit 32 consecutive banks), deeper ones in a small local-memory array.  Capping the
+// shared part is what lets 8 CTAs (32 warps) share an SM on deep trees; the spill path is rarely taken.
+static constexpr int kSpillLevels = 48;
+struct Stack {
+    uint32_t* s_ref; float* s_t; int stride; int levels;
+    uint2* spill;
+    template <bool ANY> SGD void put(int sp, uint32_t ref, float t) const {
+        if (sp < levels) { s_ref[sp * stride] = ref; if (!ANY) s_t[sp * stride] = t; }
+        else spill[sp - levels] = make_uint2(ref, __float_as_uint(t));
+    }
+    template <bool ANY> SGD void get(int sp, uint32_t& ref, float& t) const {
+        if (sp < levels) { ref = s_ref[sp * stride]; if (!ANY) t = s_t[sp * stride]; }
+        else { const uint2 e = spill[sp - levels]; ref = e.x; t = __uint_as_float(e.y); }
+    }
 };
 
 // One lane's traversal state.
@@ -92,14 +110,15 @@ SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_m
 
 // Pops the next node whose entry distance is still in range; kEmptyRef when the stack runs dry.
 template <bool ANY, bool COUNT>
-SGD uint32_t lane_pop(Lane& L, const uint32_t* s_ref, const float* s_t, int stride, uint32_t& n_nodes) {
+SGD uint32_t lane_pop(Lane& L, const Stack& S, uint32_t& n_nodes) {
     while (L.sp > 0) {
         --L.sp;
-        const uint32_t ref = s_ref[L.sp * stride];
+        uint32_t ref; float t = 0.0f;
+        S.get<ANY>(L.sp, ref, t);
         if (COUNT) n_nodes++;                                   // the reference tests the bounds at pop time
         if (COUNT && (ref & kFailBit)) continue;
         if (ANY) return ref;                                    // t_max never shrinks for the predicate
-        if (s_t[L.sp * stride] < L.t_max) return ref;
+        if (t < L.t_max) return ref;
     }
     return kEmptyRef;
 }
@@ -107,7 +126,7 @@ SGD uint32_t lane_pop(Lane& L, const uint32_t* s_ref, const float* s_t, int stri
 // One interior step: fetch a Node64, test both children, push the far one, move to the near one
 // (or pop).  Leaves `L.cur` at an interior ref, a leaf ref, or kEmptyRef (ray finished).
 template <bool ANY, bool COUNT>
-SGD void lane_step_interior(const TraceScene& ts, Lane& L, uint32_t* s_ref, float* s_t, int stride, uint32_t& n_nodes) {
+SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes) {
     const float4* nd = ts.node64 + 4 * (size_t)L.cur;
     const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
     const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
@@ -130,19 +149,17 @@ SGD void lane_step_interior(const TraceScene& ts, Lane& L, uint32_t* s_ref, floa
     // costs almost no extra pushes.  The decisive `entry < t_max` test is made on pop.
     const bool far_take = far_ok && (ANY ? far_t < L.t_max : far_t <= L.t_max * 1.0009765625f);
     if (far_take || COUNT) {
-        s_ref[L.sp * stride] = far_take ? far_ref : (far_ref | kFailBit);
-        if (!ANY) s_t[L.sp * stride] = far_t;
+        S.put<ANY>(L.sp, far_take ? far_ref : (far_ref | kFailBit), far_t);
         L.sp++;
     }
     if (COUNT) n_nodes++;                                               // near child's bounds test
     if (near_ok && near_t < L.t_max) L.cur = near_ref;
-    else L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
+    else L.cur = lane_pop<ANY, COUNT>(L, S, n_nodes);
 }
 
 // The leaf's primitives (aggregate.rs:99-110), then pop.  Returns true when an any-hit ray is done.
 template <bool ANY, bool COUNT>
-SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const uint32_t* s_ref, const float* s_t, int stride,
-                        uint32_t& n_nodes, uint32_t& n_tris) {
+SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes, uint32_t& n_tris) {
     uint32_t pi = L.cur & ~kLeafBit;
     for (;;) {
         const float4* tv = ts.tri_verts + 3 * (size_t)pi;
@@ -157,7 +174,7 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const uint32_t* s_ref, co
         if (__float_as_uint(v2.w) & kLastInLeaf) break;
         ++pi;
     }
-    L.cur = lane_pop<ANY, COUNT>(L, s_ref, s_t, stride, n_nodes);
+    L.cur = lane_pop<ANY, COUNT>(L, S, n_nodes);
 }
 
 }  // namespace sg

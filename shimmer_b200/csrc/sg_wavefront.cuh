@@ -55,7 +55,28 @@ struct RenderConst {
     uint32_t option_flags;
     int32_t  win_x0, win_y0, win_w, win_h;
     int32_t  full_res_x;
+    int32_t  n_samples;          // sample_end - sample_begin of this call
+    int32_t  path_order;         // 0 = sample-major row-major (debug), 1 = pixel-major tiled
 };
+
+// Path order of a wavefront.  Wavefront slot g -> (pixel, sample): pixel-major, so the samples of one pixel
+// sit in adjacent lanes (identical origin, near-identical direction at depth 0, neighbouring hit points at
+// every later depth), and pixels follow 8x4 tiles inside 32x32 blocks so that the ~100k paths resident on
+// the GPU at any moment cover a compact screen region.  Edge tiles are clipped; the map is a bijection for
+// any window size.  The reference's order is rayon's tile schedule (integrator.rs:235-263), i.e. arbitrary.
+SGD void pixel_from_order(uint32_t ord, int w, int h, int& x, int& y) {
+    const uint32_t W = (uint32_t)w, H = (uint32_t)h;
+    const uint32_t by = ord / (W * 32u); uint32_t r = ord - by * W * 32u;
+    const uint32_t bh = min(32u, H - by * 32u);
+    const uint32_t bx = r / (32u * bh); r -= bx * 32u * bh;
+    const uint32_t bw = min(32u, W - bx * 32u);
+    const uint32_t ty = r / (bw * 4u); r -= ty * bw * 4u;
+    const uint32_t th = min(4u, bh - ty * 4u);
+    const uint32_t tx = r / (8u * th); r -= tx * 8u * th;
+    const uint32_t tw = min(8u, bw - tx * 8u);
+    const uint32_t yi = r / tw, xi = r - yi * tw;
+    x = (int)(bx * 32u + tx * 8u + xi); y = (int)(by * 32u + ty * 4u + yi);
+}
 
 struct DevStats { unsigned long long closest, shadow, nodes, tris, nodes_closest, tris_closest; };
 
@@ -64,6 +85,9 @@ struct DevStats { unsigned long long closest, shadow, nodes, tris, nodes_closest
 #define SG_TRACE_THREADS 128
 #endif
 static constexpr int kTraceThreads = SG_TRACE_THREADS;
+#ifndef SG_TRACE_MIN_BLOCKS
+#define SG_TRACE_MIN_BLOCKS 1
+#endif
 
 // ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
@@ -72,10 +96,18 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     if (i == 0) q.counters[C_NRAY] = count;
     if (i >= count) return;
     const unsigned long long g = first_item + i;
-    const unsigned long long npix = (unsigned long long)rc.win_w * (unsigned long long)rc.win_h;
-    const int s = rc.sample_begin + (int)(g / npix);
-    const uint32_t pix = (uint32_t)(g % npix);
-    const int px = rc.win_x0 + (int)(pix % (uint32_t)rc.win_w), py = rc.win_y0 + (int)(pix / (uint32_t)rc.win_w);
+    int s, wx, wy;
+    if (rc.path_order == 0) {
+        const unsigned long long npix = (unsigned long long)rc.win_w * (unsigned long long)rc.win_h;
+        s = rc.sample_begin + (int)(g / npix);
+        const uint32_t lin = (uint32_t)(g % npix);
+        wx = (int)(lin % (uint32_t)rc.win_w); wy = (int)(lin / (uint32_t)rc.win_w);
+    } else {
+        s = rc.sample_begin + (int)(g % (unsigned long long)rc.n_samples);
+        pixel_from_order((uint32_t)(g / (unsigned long long)rc.n_samples), rc.win_w, rc.win_h, wx, wy);
+    }
+    const uint32_t pix = (uint32_t)wy * (uint32_t)rc.win_w + (uint32_t)wx;
+    const int px = rc.win_x0 + wx, py = rc.win_y0 + wy;
     Rng rng; rng.seed_from_u64(stream_key(rc.seed, (uint32_t)(py * rc.full_res_x + px), (uint32_t)s));
     Wavelengths lam; float3 o, d; float w;
     camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
@@ -103,9 +135,11 @@ template <bool ANY, bool COUNT, class IO, class CursorT>
 SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* cursor, uint32_t* s_mem,
                           uint32_t& cnt_nodes, uint32_t& cnt_tris) {
     const int lane = threadIdx.x & 31;
-    const int stride = blockDim.x;
-    uint32_t* s_ref = s_mem + threadIdx.x;
-    float* s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.stack_depth * blockDim.x) + threadIdx.x;
+    uint2 spill[kSpillLevels];
+    Stack S;
+    S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
+    S.s_ref = s_mem + threadIdx.x;
+    S.s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1;
     bool has_ray = false, dead = false, finished = false;
     CursorT idx = 0;
@@ -142,7 +176,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         if (__popc(m_leaf) >= ts.leaf_threshold || m_int == 0u) {
             // ---- triangle phase ----
             if (is_leaf) {
-                lane_step_leaf<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes, cnt_tris);
+                lane_step_leaf<ANY, COUNT>(ts, L, S, cnt_nodes, cnt_tris);
                 if (L.cur == kEmptyRef) { finished = true; has_ray = false; }
             }
             continue;
@@ -151,7 +185,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         if (is_int) {
 #pragma unroll 1
             for (int k = 0; k < ts.interior_burst; ++k) {
-                lane_step_interior<ANY, COUNT>(ts, L, s_ref, s_t, stride, cnt_nodes);
+                lane_step_interior<ANY, COUNT>(ts, L, S, cnt_nodes);
                 if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
                 if (L.cur & kLeafBit) break;
             }
@@ -203,7 +237,7 @@ struct ShadowIO {
 };
 
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+__global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                          PathState st, Queues q, int depth, DevStats* stats) {
     extern __shared__ uint32_t s_mem[];
     uint32_t* C = q.counters + depth * C_STRIDE;
@@ -451,12 +485,34 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
     }
 }
 
-// ---- RgbFilm::add_sample for every path of the batch ----
+// ---- RgbFilm::add_sample for every path of the batch (film.rs:548-574) ----
+// `rgb_sum[c] += (w * rgb[c]) as f64; weight_sum += w` with f64 atomics (RED.ADD.F64): samples of one pixel live
+// in different wavefront slots.  Paths are pixel-major, so a warp usually holds 32 samples of ONE pixel: those
+// are summed in f64 across the warp first (one atomic per channel per warp instead of 32 same-address ones).
 __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DScene sc, PathState st, uint32_t count, double* film) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Wavelengths lam; lam.lambda = st.lambda[i]; lam.pdf = st.lpdf[i];
-    film_add_sample(sc, film + 4 * (size_t)st.pixel[i], st.L[i], lam, 1.0f);
+    const bool live = i < count;
+    float rgb[3] = {0.0f, 0.0f, 0.0f};
+    uint32_t pixel = 0xffffffffu;
+    if (live) {
+        Wavelengths lam; lam.lambda = st.lambda[i]; lam.pdf = st.lpdf[i];
+        film_sample_rgb(sc, st.L[i], lam, rgb);
+        pixel = st.pixel[i];
+    }
+    const float weight = 1.0f;                                                      // BoxFilter::sample weight, filter.rs:99-105
+    double v[4] = {(double)(weight * rgb[0]), (double)(weight * rgb[1]), (double)(weight * rgb[2]), (double)weight};
+    const uint32_t first = __shfl_sync(0xffffffffu, pixel, 0);
+    if (__all_sync(0xffffffffu, pixel == first)) {
+        if (!live) return;                                                          // whole warp past the end
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+        if ((threadIdx.x & 31) == 0) { double* px = film + 4 * (size_t)pixel; for (int c = 0; c < 4; ++c) atomicAdd(px + c, v[c]); }
+    } else if (live) {
+        double* px = film + 4 * (size_t)pixel;
+        for (int c = 0; c < 4; ++c) atomicAdd(px + c, v[c]);
+    }
 }
 
 __global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
@@ -492,7 +548,7 @@ struct RaysIO {
     }
 };
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace_rays(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+__global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS) k_trace_rays(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                               long long n, const float* __restrict__ o, const float* __restrict__ d,
                                                               const float* __restrict__ tmax, SgHit* __restrict__ out,
                                                               unsigned long long* cursor, DevStats* stats) {

@@ -217,8 +217,12 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 6);
         s->ts.interior_burst = env_int("SG_INTERIOR_BURST", 4);
         s->ts.prefetch = env_int("SG_PREFETCH", 0);
-        s->smem_closest = (size_t)s->ts.stack_depth * kTraceThreads * 8;
-        s->smem_shadow = (size_t)s->ts.stack_depth * kTraceThreads * 4;
+        // shared-memory part of the per-thread stack: 20 levels x 8 B x 128 threads = 20.5 KB -> 9 CTAs (36 warps, the register limit at 56 regs) per SM;
+        // deeper levels (if the tree has them) spill to local memory (sg_trace2.cuh Stack)
+        s->ts.smem_levels = std::min(s->ts.stack_depth, std::max(1, env_int("SG_SMEM_LEVELS", 20)));
+        if (s->ts.stack_depth - s->ts.smem_levels > kSpillLevels) s->ts.smem_levels = s->ts.stack_depth - kSpillLevels;
+        s->smem_closest = (size_t)s->ts.smem_levels * kTraceThreads * 8;
+        s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
     }
     float4* d_nodes = nullptr; float4* d_tv = nullptr; float4* d_n64 = nullptr;
     if ((rc = upload(n64.data(), n64.size(), &d_n64, s->owned)) != SG_OK) return bail(rc);
@@ -306,6 +310,9 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.win_x0 = s->d.film.pixel_bounds[0]; k.win_y0 = s->d.film.pixel_bounds[1];
     k.win_w = s->d.film.pixel_bounds[2] - k.win_x0; k.win_h = s->d.film.pixel_bounds[3] - k.win_y0;
     k.full_res_x = s->d.film.full_resolution[0];
+    k.n_samples = rp->sample_end - rp->sample_begin;
+    { const char* v = std::getenv("SG_PATH_ORDER"); k.path_order = v ? std::atoi(v) : 1; }
+    if (k.n_samples == 0) k.n_samples = 1;
     const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
     const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
     const int n_depths = rp->max_depth + 1;
@@ -355,6 +362,13 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     double closest_ms = 0.0, shadow_ms = 0.0;
     for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); closest_ms += t; }
     for (size_t i = 0; i + 1 < sev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, sev[i], sev[i + 1]); shadow_ms += t; }
+    if (time_trace && std::getenv("SG_DEBUG_TIMING")) {      // per-launch device times, one line per render call
+        std::fprintf(stderr, "[sg] closest ms:");
+        for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); std::fprintf(stderr, " %.3f", t); }
+        std::fprintf(stderr, " | shadow ms:");
+        for (size_t i = 0; i + 1 < sev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, sev[i], sev[i + 1]); std::fprintf(stderr, " %.3f", t); }
+        std::fprintf(stderr, " | total %.3f\n", ms);
+    }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
     for (cudaEvent_t e : sev) cudaEventDestroy(e);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
