@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2
+#define SG_ABI_VERSION 3
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -132,21 +132,24 @@ typedef struct SgMaterial {
     int32_t pad2[2];
 } SgMaterial;
 
-/* ---- image textures (src/texture.rs:700-808, src/mipmap.rs, src/image.rs:134-177,619-646) ------
+/* ---- image textures (src/texture.rs:393-404,700-808,896-936, src/mipmap.rs:121-331, src/image.rs:134-177,619-646) ------
  * The host owns image decoding and pyramid generation (image.rs:699-846); it passes every MIP
- * level as linear f32 texels (what `Image::get_channel` returns after colour-encoding).  Level 0 is
- * the full-resolution image, the last level is 1x1.  One-channel images evaluate to a constant
- * spectrum (texture.rs:803-807); RGB images need the third-party rgb2spec tables, which are missing
- * from the reference checkout (.MISSING_LARGE_BLOBS) -> not accepted yet (SG_ERR_UNSUPPORTED). */
+ * level as linear f32 texels (what `Image::get_channel` returns after colour-decoding), channels
+ * interleaved.  Level 0 is the full-resolution image, the last level is 1x1.  One-channel images
+ * evaluate to a constant spectrum (texture.rs:803-807); three-channel images go through
+ * RgbAlbedoSpectrum / RgbUnboundedSpectrum (spectrum.rs:498-588), i.e. the rgb2spec coefficient
+ * table of the texture's colour space (SgSceneDesc.rgb2spec_*) and RgbSigmoidPolynomial::get
+ * (color.rs:352-383).  Texture mapping is UVMapping (texture.rs:896-936). */
 typedef enum SgWrapMode { SG_WRAP_REPEAT = 0, SG_WRAP_BLACK = 1, SG_WRAP_CLAMP = 2 } SgWrapMode;       /* image.rs WrapMode */
 typedef enum SgFilterFunction { SG_FILTER_POINT = 0, SG_FILTER_BILINEAR = 1, SG_FILTER_TRILINEAR = 2, SG_FILTER_EWA = 3 } SgFilterFunction; /* mipmap.rs:337-345 */
+typedef enum SgSpectrumType { SG_SPECTRUM_TYPE_ALBEDO = 0, SG_SPECTRUM_TYPE_UNBOUNDED = 1 } SgSpectrumType; /* texture.rs SpectrumType; Illuminant is not on this path */
 typedef struct SgImageLevel {
-    uint32_t offset;           /* into SgSceneDesc.texels                */
+    uint32_t offset;           /* into SgSceneDesc.texels (in floats)    */
     int32_t  res[2];           /* resolution x, y                        */
     uint32_t pad;
 } SgImageLevel;
 typedef struct SgTexture {
-    int32_t  n_channels;       /* 1 (3 = RGB: unsupported, see above)    */
+    int32_t  n_channels;       /* 1 or 3                                 */
     int32_t  n_levels;
     uint32_t first_level;      /* into SgSceneDesc.image_levels          */
     int32_t  wrap;             /* SgWrapMode, `wrap` default repeat      */
@@ -155,6 +158,8 @@ typedef struct SgTexture {
     float    scale;            /* default 1                              */
     int32_t  invert;
     float    su, sv, du, dv;   /* UVMapping (texture.rs:896-936)         */
+    int32_t  spectrum_type;    /* SgSpectrumType (three-channel spectrum textures) */
+    int32_t  pad[3];
 } SgTexture;
 
 /* ---- lights (src/light.rs) ------------------------------------------------- */
@@ -220,6 +225,9 @@ typedef struct SgSceneDesc {
     uint32_t n_image_levels; const SgImageLevel* image_levels;
     uint64_t n_texels;     const float*       texels;
     const float* mip_filter_lut;                            /* MIP_FILTER_LUT[128], mipmap.rs:388-518 (EWA) or NULL */
+    /* rgb2spec coefficient table of the scene colour space (rgb_to_spectra.rs:16-45; third-party `rgb2spec` 0.1.1,
+     * RGB2Spec{res, scale[res], data[3*res^3*3]}); required iff a three-channel texture exists */
+    uint32_t rgb2spec_res; const float* rgb2spec_scale; const float* rgb2spec_data;
     SgCamera camera;
     SgFilm   film;
 } SgSceneDesc;
@@ -324,6 +332,11 @@ int sg_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sampl
 int sg_camera_rays(SgScene* scene, const SgRenderParams* params, int64_t n,
                    const int32_t* pixel_xy, const int32_t* sample_index,
                    float* out_rays, float* out_lambda);
+
+/* Replaces `SpectrumImageTexture::evaluate` (texture.rs:777-808; as_float!=0: `FloatImageTexture::evaluate`
+ * :393-404, value replicated) for n lookups of texture `tex`: the texture-filtering parity entry.
+ * q: u v dudx dudy dvdx dvdy per lookup (TextureEvalContext); lambda: 4 wavelengths per lookup; out: 4 floats. */
+int sg_texture_eval(SgScene* scene, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out);
 
 /* Replaces `RgbFilm::get_pixel_rgb` (film.rs:720-738): rgb_sum/weight_sum then
  * output_rgb_from_sensor_rgb; out: 3 floats per pixel. */

@@ -240,14 +240,14 @@ struct SurfaceInteraction {
     P3fi pi; V3 wo; V3 n; V2 uv;
     V3 dpdu, dpdv;
     V3 sn, sdpdu, sdpdv;     // shading.n / shading.dpdu / shading.dpdv
+    V3 sdndu = {0, 0, 0}, sdndv = {0, 0, 0};                    // shading.dndu / shading.dndv
+    Float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0;               // compute_differentials interaction.rs:280-366
+    V3 dpdx = {0, 0, 0}, dpdy = {0, 0, 0};
     int32_t material, light;
     inline V3 p() const { return p3fi_mid(pi); }
 };
 
-// triangle.rs:305-504.  dndu/dndv and the screen-space differentials are not restated:
-// with the constant textures of this path they are only ever multiplied by a zero
-// displacement (material.rs:1500-1507) or feed auxiliary rays that nothing reads
-// (SURVEY.md 8a row a12).
+// triangle.rs:305-504 (dndu/dndv :451-498 feed bump mapping and specular ray differentials).
 inline SurfaceInteraction interaction_from_intersection(const Scene& sc, uint32_t mesh_id, uint32_t tri, const TriHit& ti, V3 wo) {
     const SgMesh& m = sc.d->meshes[mesh_id];
     uint32_t v[3]; sc.tri_indices(mesh_id, tri, v);
@@ -311,6 +311,19 @@ inline SurfaceInteraction interaction_from_intersection(const Scene& sc, uint32_
         si.sn = ns;
         si.n = face_forward(si.n, si.sn);
         si.sdpdu = ss; si.sdpdv = ts;
+        if (m.flags & SG_MESH_HAS_N) {                                     // dndu, dndv :451-498
+            V3 n0 = sc.normal(m, v[0]), n1 = sc.normal(m, v[1]), n2 = sc.normal(m, v[2]);
+            if (degenerate_uv) {
+                V3 dn = cross(n2 - n0, n1 - n0);
+                if (length_squared(dn) != 0.0f) coordinate_system(dn, &si.sdndu, &si.sdndv);
+            } else {
+                Float inv_det = 1.0f / determinant;
+                V3 dn1 = n0 - n2, dn2 = n1 - n2;
+                auto dopv = [](Float a, V3 b, Float c, V3 d) { V3 cd = c * d; V3 diff = a * b - cd; V3 err = (-c) * d + cd; return diff + err; };
+                si.sdndu = dopv(duv12.y, dn1, duv02.y, dn2) * inv_det;
+                si.sdndv = dopv(duv02.x, dn2, duv12.x, dn1) * inv_det;
+            }
+        }
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
     return si;

@@ -513,24 +513,32 @@ struct BSDF {
     }
 };
 
+}  // namespace orc
+#include "orc_texture.h"
+namespace orc {
+
 // SurfaceInteraction::get_bsdf (interaction.rs:187-278) + Material::get_bsdf
-// (material.rs:301-322, 456-511, 603-648) for constant textures.
-inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& lambda) {
+// (material.rs:301-322, 456-511, 603-648, 917-963).
+inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& lambda, const AuxRays& aux, const SgRenderParams* rp) {
     const SgMaterial& m = D->materials[si.material];
+    // compute_differentials feeds image-texture filtering, the bump-map step and specular ray differentials; scenes
+    // without image textures never read its results (constant textures ignore the footprint)
+    if (D->n_textures > 0) compute_differentials(D, si, aux, rp->samples_per_pixel, rp->option_flags);
     if (m.flags & SG_MAT_HAS_DISPLACEMENT) {
-        // bump_map with a constant displacement texture (material.rs:1477-1509): the three
-        // evaluations are equal, so dpdu' = shading.dpdu + 0/du*n + displace*dndu; dndu is
-        // only ever multiplied by `displace` (0 for every scene on this path).
-        V3 dpdu = si.sdpdu, dpdv = si.sdpdv;
+        // bump_map (material.rs:1477-1509) then set_shading_geometry(ns, dpdu, dpdv, dndu, dndv, false) interaction.rs:229-250
+        V3 dpdu, dpdv;
+        if (m.tex_displacement >= 0 || m.displacement != 0.0f) bump_map(D, m.tex_displacement, m.displacement, si, &dpdu, &dpdv);
+        else { dpdu = si.sdpdu; dpdv = si.sdpdv; }    // constant 0: dpdu + 0/du*n + 0*dndu
         V3 ns = normalize(cross(dpdu, dpdv));                                   // interaction.rs:246
-        si.sn = face_forward(ns, si.n);                                          // set_shading_geometry(.., false) :379-405
+        si.sn = face_forward(ns, si.n);                                          // :379-405
         si.sdpdu = dpdu; si.sdpdv = dpdv;
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
+    TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy};
     BSDF b;
     b.kind = m.kind; b.r = spec_const(0.0f); b.k = spec_const(0.0f); b.eta = 1.0f; b.mf = TR::make(0.0f, 0.0f);
     if (m.kind == SG_MATERIAL_DIFFUSE) {
-        b.r = spec_clamp(spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
+        b.r = spec_clamp(m.tex_reflectance >= 0 ? eval_spectrum_texture(D, m.tex_reflectance, tc, lambda) : spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
     } else if (m.kind == SG_MATERIAL_CONDUCTOR) {
         Float ur = m.u_roughness, vr = m.v_roughness;
         if (m.flags & SG_MAT_REMAP_ROUGHNESS) { ur = std::sqrt(ur); vr = std::sqrt(vr); }   // roughness_to_alpha scattering.rs:197-199
@@ -538,7 +546,7 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         b.k = spectrum_sample(D, m.spec_b, lambda);
         b.mf = TR::make(ur, vr);
     } else if (m.kind == SG_MATERIAL_COATED_DIFFUSE) {                       // material.rs:917-963
-        b.lay.r = spec_clamp(spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
+        b.lay.r = spec_clamp(m.tex_reflectance >= 0 ? eval_spectrum_texture(D, m.tex_reflectance, tc, lambda) : spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
         Float ur = m.u_roughness, vr = m.v_roughness;
         if (m.flags & SG_MAT_REMAP_ROUGHNESS) { ur = std::sqrt(ur); vr = std::sqrt(vr); }
         b.lay.mf = TR::make(ur, vr);
@@ -720,9 +728,9 @@ inline Ray xform_ray(const float m[16], Ray r) {
     Ray out; out.o = p3fi_mid(o); out.d = d; return out;
 }
 struct CameraSample { V2 p_film, p_lens; Float time; Float filter_weight; };
-// PerspectiveCamera::generate_ray_differential camera.rs:1003-1079 (main ray; the auxiliary rays are not
-// restated, see interaction_from_intersection)
-inline Ray camera_generate_ray(const SgCamera& cam, const CameraSample& cs) {
+// PerspectiveCamera::generate_ray_differential camera.rs:1003-1079; `aux` (may be null) receives the auxiliary rays in
+// render space (Transform::apply_ray(RayDifferential) transform.rs:534-556: plain point / vector transforms)
+inline Ray camera_generate_ray(const SgCamera& cam, const CameraSample& cs, AuxRays* aux = nullptr) {
     V3 p_film = v3(cs.p_film.x, cs.p_film.y, 0.0f);
     V3 p_camera = xform_point(cam.camera_from_raster, p_film);
     Ray r; r.o = v3(0, 0, 0); r.d = normalize(p_camera);
@@ -733,6 +741,28 @@ inline Ray camera_generate_ray(const SgCamera& cam, const CameraSample& cs) {
         V3 p_focus = r.o + r.d * ft;
         r.o = v3(pl.x, pl.y, 0.0f);
         r.d = normalize(p_focus - r.o);
+    }
+    if (aux) {
+        V3 dxc = v3(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2]), dyc = v3(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2]);
+        V3 rxo, rxd, ryo, ryd;
+        if (cam.lens_radius > 0.0f) {
+            V2 pl = sample_uniform_disk_concentric(cs.p_lens);
+            pl.x = cam.lens_radius * pl.x; pl.y = cam.lens_radius * pl.y;
+            V3 dx = normalize(p_camera + dxc);
+            Float ft = cam.focal_distance / dx.z;
+            V3 pf = v3(0, 0, 0) + ft * dx;
+            rxo = v3(pl.x, pl.y, 0.0f); rxd = normalize(pf - rxo);
+            V3 dy = normalize(p_camera + dyc);
+            ft = cam.focal_distance / dy.z;
+            pf = v3(0, 0, 0) + ft * dy;
+            ryo = v3(pl.x, pl.y, 0.0f); ryd = normalize(pf - ryo);
+        } else {
+            rxo = r.o; ryo = r.o;
+            rxd = normalize(p_camera + dxc); ryd = normalize(p_camera + dyc);
+        }
+        aux->has = true;
+        aux->rxo = xform_point(cam.render_from_camera, rxo); aux->rxd = xform_vector(cam.render_from_camera, rxd);
+        aux->ryo = xform_point(cam.render_from_camera, ryo); aux->ryd = xform_vector(cam.render_from_camera, ryd);
     }
     return xform_ray(cam.render_from_camera, r);
 }

@@ -77,7 +77,7 @@ static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, BSDF& b
 }
 
 // PathIntegrator::li integrator.rs:748-895
-static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
+static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda, Rng& rng) {
     const SgSceneDesc* D = pc.sc->d;
     Spec L = spec_const(0.0f), beta = spec_const(1.0f);
     int depth = 0;
@@ -117,7 +117,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
                 }
             }
         }
-        BSDF bsdf = get_bsdf(D, si, lambda);                                      // :816
+        BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp);                          // :816
         if (pc.rp->regularize && any_non_specular_bounces) { bsdf.mf.regularize(); bsdf.lay.mf.regularize(); }  // :825-828
         if (depth == pc.rp->max_depth) break;
         depth += 1;
@@ -138,6 +138,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
         any_non_specular_bounces |= !specular_bounce;
         if (bs.flags & BX_TRANSMISSION) eta_scale *= sqr(bs.eta);
         prev_ctx.pi = si.pi; prev_ctx.n = si.n; prev_ctx.ns = si.sn;
+        if (D->n_textures > 0) aux = spawn_differentials(si, aux, bs.wi, bs.flags, bs.eta);   // spawn_ray_with_differentials :434-502
         ray.o = offset_ray_origin(si.pi, si.n, bs.wi); ray.d = bs.wi;             // spawn_ray interaction.rs:72-79
         if (std::isfinite(eta_scale)) {                                           // :878-891
             Spec rr_beta = beta * eta_scale;
@@ -152,7 +153,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, Wavelengths& lambda, Rng& rng) {
 }
 
 // evaluate_pixel_sample integrator.rs:326-396 + get_camera_sample sampling.rs:347-371 + BoxFilter::sample filter.rs:99-105
-static void camera_stage(const SgSceneDesc* D, const SgRenderParams* rp, int px, int py, Rng& rng, Wavelengths* lambda, Ray* ray, Float* weight) {
+static void camera_stage(const SgSceneDesc* D, const SgRenderParams* rp, int px, int py, Rng& rng, Wavelengths* lambda, Ray* ray, Float* weight, AuxRays* aux = nullptr) {
     Float lu = (rp->option_flags & SG_OPT_DISABLE_WAVELENGTH_JITTER) ? 0.5f : rng.get_1d();
     *lambda = sample_visible(lu);
     V2 pu; pu.x = rng.get_1d(); pu.y = rng.get_1d();                  // get_pixel_2d, always consumed
@@ -168,15 +169,20 @@ static void camera_stage(const SgSceneDesc* D, const SgRenderParams* rp, int px,
         cs.time = rng.get_1d();
         cs.filter_weight = 1.0f;
     }
-    *ray = camera_generate_ray(D->camera, cs);
+    *ray = camera_generate_ray(D->camera, cs, aux);
+    if (aux && aux->has && !(rp->option_flags & SG_OPT_DISABLE_PIXEL_JITTER)) {       // integrator.rs:355-361 + Ray::scale_differentials ray.rs:137-145
+        Float s = fmax_(0.125f, 1.0f / std::sqrt((Float)rp->samples_per_pixel));
+        aux->rxo = ray->o + (aux->rxo - ray->o) * s; aux->ryo = ray->o + (aux->ryo - ray->o) * s;
+        aux->rxd = ray->d + (aux->rxd - ray->d) * s; aux->ryd = ray->d + (aux->ryd - ray->d) * s;
+    }
     *weight = cs.filter_weight;
 }
 
 static void eval_sample(const PathCtx& pc, int px, int py, Rng& rng, SgFilmPixel* film) {
     const SgSceneDesc* D = pc.sc->d;
-    Wavelengths lambda; Ray ray; Float weight;
-    camera_stage(D, pc.rp, px, py, rng, &lambda, &ray, &weight);
-    Spec L = path_li(pc, ray, lambda, rng);          // camera_ray.weight == 1 (camera.rs:997-1000)
+    Wavelengths lambda; Ray ray; Float weight; AuxRays aux;
+    camera_stage(D, pc.rp, px, py, rng, &lambda, &ray, &weight, D->n_textures > 0 ? &aux : nullptr);
+    Spec L = path_li(pc, ray, aux, lambda, rng);          // camera_ray.weight == 1 (camera.rs:997-1000)
     int W = D->film.pixel_bounds[2] - D->film.pixel_bounds[0];
     SgFilmPixel* pxl = film + (size_t)(py - D->film.pixel_bounds[1]) * W + (px - D->film.pixel_bounds[0]);
     film_add_sample(D, pxl, L, lambda, weight);
@@ -355,6 +361,30 @@ float orc_fresnel_dielectric(float c, float eta) { return fresnel_dielectric(c, 
 float orc_fresnel_complex(float c, float eta, float k) { return fresnel_complex(c, cx(eta, k)); }
 float orc_blackbody(float lambda, float t) { return blackbody(lambda, t); }
 float orc_spectrum_get(const SgSceneDesc* d, int id, float lambda) { return spectrum_get(d, id, lambda); }
+// ---- texture / differential KAT entry points ----
+void orc_rotate_from_to(const float* from, const float* to, float* out9) {
+    rotate_from_to(v3(from[0], from[1], from[2]), v3(to[0], to[1], to[2]), out9);
+}
+float orc_sigmoid_poly_get(const float* c3, float lambda) { return sigmoid_poly_get(c3, lambda); }
+void orc_rgb2spec_fetch(const SgSceneDesc* d, const float* rgb, float* out3) { rgb2spec_fetch(d, rgb, out3); }
+// n lookups; q = u v dudx dudy dvdx dvdy per lookup; lambda4 per lookup; out4 per lookup (float textures: value replicated)
+void orc_texture_eval(const SgSceneDesc* d, int tex, int as_float, int64_t n, const float* q, const float* lambda4, float* out4) {
+    for (int64_t i = 0; i < n; ++i) {
+        TexCoordCtx c; c.uv.x = q[6 * i]; c.uv.y = q[6 * i + 1]; c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
+        if (as_float) { Float v = eval_float_texture(d, tex, c); for (int k = 0; k < 4; ++k) out4[4 * i + k] = v; }
+        else {
+            Wavelengths w; for (int k = 0; k < 4; ++k) { w.lambda[k] = lambda4[4 * i + k]; w.pdf[k] = 1.0f; }
+            Spec s = eval_spectrum_texture(d, tex, c, w);
+            for (int k = 0; k < 4; ++k) out4[4 * i + k] = s.v[k];
+        }
+    }
+}
+void orc_approximate_dp_dxy(const SgSceneDesc* d, const float* p, const float* n, int spp, uint32_t option_flags, float* out6) {
+    V3 dpdx, dpdy;
+    approximate_dp_dxy(d->camera, v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2]), spp, option_flags, &dpdx, &dpdy);
+    out6[0] = dpdx.x; out6[1] = dpdx.y; out6[2] = dpdx.z; out6[3] = dpdy.x; out6[4] = dpdy.y; out6[5] = dpdy.z;
+}
+
 void orc_spectrum_sample(const SgSceneDesc* d, int id, const float* lambda4, float* out4) {
     Wavelengths w; for (int i = 0; i < 4; ++i) { w.lambda[i] = lambda4[i]; w.pdf[i] = 1.0f; }
     Spec s = spectrum_sample(d, id, w); for (int i = 0; i < 4; ++i) out4[i] = s.v[i];

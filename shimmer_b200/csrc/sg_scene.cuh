@@ -31,6 +31,13 @@ struct DScene {
     const float* pool;
     const SgMaterial* materials;
     const SgLight* lights;
+    const SgTexture* textures;          // image textures (sg_texture.cuh)
+    const SgImageLevel* image_levels;
+    const float* texels;
+    const float* mip_lut;               // MIP_FILTER_LUT[128]
+    const float* rgb2spec_scale;        // rgb2spec table of the scene colour space
+    const float* rgb2spec_data;
+    uint32_t rgb2spec_res, n_textures;
     uint32_t n_nodes, n_prims, n_lights, n_materials;
     int32_t n_infinite;          // number of SG_LIGHT_UNIFORM_INFINITE lights
     int32_t infinite_ids[4];

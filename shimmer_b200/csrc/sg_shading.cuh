@@ -524,9 +524,12 @@ SGD void geo_indices(const DScene& sc, const TriGeo& g, uint32_t& i0, uint32_t& 
 
 // Builds geometric + shading frame for the FINAL hit only (the reference does it for every
 // accepted candidate along the ray, triangle.rs:529-535; only the last survives).
-// The uv-derived dpdu/dpdv follow :314-372; dndu/dndv and ray differentials are dropped --
-// on this path they are multiplied by a zero displacement or never read.
-SGD Surf make_surface(const DScene& sc, const TriGeo& g, float b0, float b1, float b2) {
+// The uv-derived dpdu/dpdv follow :314-372.  Scenes with image textures (or a non-zero displacement) also need the
+// hit uv, the geometric dpdu/dpdv and dndu/dndv (:451-498): `x` (sg_texture.cuh SurfTex) receives them when TEX.
+struct SurfTex;
+template <bool TEX> SGD void surf_tex_store(SurfTex* x, float2 uv, float3 dpdu, float3 dpdv, float3 dndu, float3 dndv);
+template <bool TEX = false>
+SGD Surf make_surface(const DScene& sc, const TriGeo& g, float b0, float b1, float b2, SurfTex* x = nullptr) {
     struct { uint32_t flags; } m; m.flags = g.flags;
     const float3 p0 = g.p0, p1 = g.p1, p2 = g.p2;
     uint32_t i0 = 0, i1 = 0, i2 = 0; size_t fv = 0;
@@ -567,11 +570,26 @@ SGD Surf make_surface(const DScene& sc, const TriGeo& g, float b0, float b1, flo
     const bool flip = ((m.flags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((m.flags & SG_MESH_SWAPS_HANDEDNESS) != 0);
     if (flip) s.n = -s.n;
     s.sn = s.n; s.sdpdu = dpdu; s.sdpdv = dpdv;
+    float3 dndu = f3(0.0f, 0.0f, 0.0f), dndv = f3(0.0f, 0.0f, 0.0f);
     if (m.flags & (SG_MESH_HAS_N | SG_MESH_HAS_S)) {                        // :414-501
         float3 ns = s.n;
         if (m.flags & SG_MESH_HAS_N) {
-            float3 nn = b0 * ldv3(sc.n, fv + i0) + b1 * ldv3(sc.n, fv + i1) + b2 * ldv3(sc.n, fv + i2);
+            const float3 n0 = ldv3(sc.n, fv + i0), n1 = ldv3(sc.n, fv + i1), n2 = ldv3(sc.n, fv + i2);
+            float3 nn = b0 * n0 + b1 * n1 + b2 * n2;
             if (len2(nn) > 0.0f) ns = normalize3(nn);
+            if (TEX) {                                                      // dndu, dndv :451-498
+                if (degenerate_uv) {
+                    const float3 dn = cross3(n2 - n0, n1 - n0);
+                    if (len2(dn) != 0.0f) coord_system(dn, dndu, dndv);
+                } else {
+                    const float inv_det = 1.0f / determinant;
+                    const float3 dn1 = n0 - n2, dn2 = n1 - n2;
+                    float3 cd = duv02.y * dn2; float3 df = duv12.y * dn1 - cd; float3 er = (-duv02.y) * dn2 + cd;
+                    dndu = (df + er) * inv_det;
+                    cd = duv12.x * dn1; df = duv02.x * dn2 - cd; er = (-duv12.x) * dn1 + cd;
+                    dndv = (df + er) * inv_det;
+                }
+            }
         }
         float3 ss = dpdu;
         if (m.flags & SG_MESH_HAS_S) {
@@ -585,6 +603,7 @@ SGD Surf make_surface(const DScene& sc, const TriGeo& g, float b0, float b1, flo
         s.sdpdu = ss; s.sdpdv = ts;
         while (len2(s.sdpdu) > 1e16f || len2(s.sdpdv) > 1e16f) { s.sdpdu = s.sdpdu / 1e8f; s.sdpdv = s.sdpdv / 1e8f; }
     }
+    if (TEX) surf_tex_store<TEX>(x, make_float2(b0 * uv0.x + b1 * uv1.x + b2 * uv2.x, b0 * uv0.y + b1 * uv1.y + b2 * uv2.y), dpdu, dpdv, dndu, dndv);
     return s;
 }
 // bump_map with the constant displacement texture of this path (material.rs:1477-1509) followed by
@@ -739,7 +758,10 @@ SGD void xform_ray(const float* m, float3& o, float3& d) {
 }
 // evaluate_pixel_sample's camera stage (integrator.rs:339-362) + get_camera_sample (sampling.rs:347-371)
 // + BoxFilter::sample (filter.rs:99-105) + PerspectiveCamera::generate_ray_differential (main ray)
-SGD void camera_stage(const DScene& sc, uint32_t option_flags, int px, int py, Rng& rng, Wavelengths& lam, float3& o, float3& d, float& weight) {
+struct AuxRays;
+SGD void camera_aux(const DScene& sc, float3 p_camera, float2 p_lens, float3 o_cam, AuxRays* aux);      // sg_texture.cuh
+SGD void camera_stage(const DScene& sc, uint32_t option_flags, int px, int py, Rng& rng, Wavelengths& lam, float3& o, float3& d, float& weight,
+                      AuxRays* aux = nullptr) {
     float lu = (option_flags & SG_OPT_DISABLE_WAVELENGTH_JITTER) ? 0.5f : rng.get_1d();
     lam = sample_visible(lu);
     float2 pu; pu.x = rng.get_1d(); pu.y = rng.get_1d();
@@ -765,6 +787,7 @@ SGD void camera_stage(const DScene& sc, uint32_t option_flags, int px, int py, R
         o = f3(pl.x, pl.y, 0.0f);
         d = normalize3(p_focus - o);
     }
+    if (aux) camera_aux(sc, p_camera, p_lens, o, aux);
     xform_ray(sc.camera.render_from_camera, o, d);
 }
 

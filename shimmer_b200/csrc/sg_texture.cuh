@@ -1,0 +1,366 @@
+// Image textures, MIP filtering, screen-space differentials and bump mapping on the device.
+//
+// Reference: SpectrumImageTexture / FloatImageTexture::evaluate (texture.rs:393-404,777-808), UVMapping::map
+// (:918-936), MIPMap::filter / ewa (mipmap.rs:121-293), Image::get_channel_wrapped / bilerp_channel_wrapped /
+// remap_pixel_coords (image.rs:134-177,452-475,619-646), RgbAlbedoSpectrum / RgbUnboundedSpectrum
+// (spectrum.rs:498-588), RgbSigmoidPolynomial::get (color.rs:352-383), compute_differentials
+// (interaction.rs:280-366), Camera::approximate_dp_dxy (camera.rs:308-354), Transform::rotate_from_to
+// (transform.rs:227-253), bump_map (material.rs:1477-1509), spawn_ray_with_differentials (interaction.rs:434-502).
+//
+// Layout: every MIP level is a dense row-major array of f32 texels with interleaved channels in one pool
+// (`texels`); a bilinear tap is four scalar __ldg's per channel (two 8-byte-adjacent pairs), served from L1/L2.
+// The third-party pieces (rgb2spec fetch, fast_polynomial's Estrin `poly`) follow the published algorithms.
+#pragma once
+#include "sg_shading.cuh"
+
+namespace sg {
+
+struct AuxRays { bool has; float3 rxo, rxd, ryo, ryd; };
+
+// auxiliary rays of PerspectiveCamera::generate_ray_differential (camera.rs:1036-1079) in render space
+// (Transform::apply_ray(RayDifferential) transform.rs:534-556: plain point / vector transforms)
+SGD void camera_aux(const DScene& sc, float3 p_camera, float2 p_lens, float3 o_cam, AuxRays* aux) {
+    const SgCamera& cam = sc.camera;
+    const float3 dxc = f3(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2]), dyc = f3(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2]);
+    float3 rxo, rxd, ryo, ryd;
+    if (cam.lens_radius > 0.0f) {
+        float2 pl = sample_disk_concentric(p_lens);
+        pl.x = cam.lens_radius * pl.x; pl.y = cam.lens_radius * pl.y;
+        const float3 dx = normalize3(p_camera + dxc);
+        float ft = cam.focal_distance / dx.z;
+        float3 pf = f3(0.0f, 0.0f, 0.0f) + ft * dx;
+        rxo = f3(pl.x, pl.y, 0.0f); rxd = normalize3(pf - rxo);
+        const float3 dy = normalize3(p_camera + dyc);
+        ft = cam.focal_distance / dy.z;
+        pf = f3(0.0f, 0.0f, 0.0f) + ft * dy;
+        ryo = f3(pl.x, pl.y, 0.0f); ryd = normalize3(pf - ryo);
+    } else {
+        rxo = o_cam; ryo = o_cam;
+        rxd = normalize3(p_camera + dxc); ryd = normalize3(p_camera + dyc);
+    }
+    aux->has = true;
+    aux->rxo = xform_point(cam.render_from_camera, rxo); aux->rxd = xform_vector(cam.render_from_camera, rxd);
+    aux->ryo = xform_point(cam.render_from_camera, ryo); aux->ryd = xform_vector(cam.render_from_camera, ryd);
+}
+
+SGD int modulo_i(int a, int b) { int r = a - (a / b) * b; return r < 0 ? r + b : r; }            // math.rs:439-451
+SGD uint32_t f2u_sat(float f) { return __float2uint_rz(f); }                                       // Rust `as usize`: saturating, NaN -> 0
+
+struct TexView {
+    const DScene& sc; const SgTexture& t;
+    SGD SgImageLevel level(int l) const { return sc.image_levels[t.first_level + l]; }
+    // Image::get_channel_wrapped image.rs:452-475 + remap_pixel_coords :134-177
+    SGD float channel(const SgImageLevel& L, int x, int y, int c) const {
+        if (x < 0 || x >= L.res[0]) {
+            if (t.wrap == SG_WRAP_BLACK) return 0.0f;
+            x = t.wrap == SG_WRAP_CLAMP ? min(max(x, 0), L.res[0] - 1) : modulo_i(x, L.res[0]);
+        }
+        if (y < 0 || y >= L.res[1]) {
+            if (t.wrap == SG_WRAP_BLACK) return 0.0f;
+            y = t.wrap == SG_WRAP_CLAMP ? min(max(y, 0), L.res[1] - 1) : modulo_i(y, L.res[1]);
+        }
+        return __ldg(sc.texels + (size_t)L.offset + ((size_t)y * L.res[0] + x) * t.n_channels + c);
+    }
+    // Image::bilerp_channel_wrapped image.rs:619-646
+    SGD float bilerp_channel(const SgImageLevel& L, float2 st, int c) const {
+        const float x = st.x * (float)L.res[0] - 0.5f, y = st.y * (float)L.res[1] - 0.5f;
+        const int xi = f2i_sat(floorf(x)), yi = f2i_sat(floorf(y));
+        const float dx = x - (float)xi, dy = y - (float)yi;
+        const float v0 = channel(L, xi, yi, c), v1 = channel(L, xi + 1, yi, c), v2 = channel(L, xi, yi + 1, c), v3 = channel(L, xi + 1, yi + 1, c);
+        return (1.0f - dx) * (1.0f - dy) * v0 + dx * (1.0f - dy) * v1 + (1.0f - dx) * dy * v2 + dx * dy * v3;
+    }
+};
+
+// texel value: RGB (texel_rgb mipmap.rs:203-219) or Float replicated (texel_float :221-225)
+SGD float3 tex_lerp(float t, float3 a, float3 b) { return a * (1.0f - t) + b * t; }
+
+template <bool RGB> SGD float3 tex_texel(const TexView& tv, int l, int x, int y) {
+    const SgImageLevel L = tv.level(l);
+    if (RGB && tv.t.n_channels == 3) return f3(tv.channel(L, x, y, 0), tv.channel(L, x, y, 1), tv.channel(L, x, y, 2));
+    const float v = tv.channel(L, x, y, 0); return f3(v, v, v);
+}
+template <bool RGB> SGD float3 tex_bilerp(const TexView& tv, int l, float2 st) {                 // mipmap.rs:298-331
+    const SgImageLevel L = tv.level(l);
+    if (RGB && tv.t.n_channels == 3) return f3(tv.bilerp_channel(L, st, 0), tv.bilerp_channel(L, st, 1), tv.bilerp_channel(L, st, 2));
+    const float v = tv.bilerp_channel(L, st, 0); return f3(v, v, v);
+}
+// TexelType::ewa mipmap.rs:233-293
+template <bool RGB> __device__ __noinline__ float3 tex_ewa(const TexView& tv, int l, float2 st, float2 d0, float2 d1) {
+    if (l >= tv.t.n_levels) return tex_texel<RGB>(tv, tv.t.n_levels - 1, 0, 0);
+    const SgImageLevel L = tv.level(l);
+    st.x = st.x * (float)L.res[0] - 0.5f; st.y = st.y * (float)L.res[1] - 0.5f;
+    d0.x *= (float)L.res[0]; d0.y *= (float)L.res[1]; d1.x *= (float)L.res[0]; d1.y *= (float)L.res[1];
+    float a = sqr(d0.y) + sqr(d1.y) + 1.0f;
+    float b = -2.0f * (d0.x * d0.y + d1.x * d1.y);
+    float c = sqr(d0.x) + sqr(d1.x) + 1.0f;
+    const float inv_f = 1.0f / (a * c - sqr(b) * 0.25f);
+    a *= inv_f; b *= inv_f; c *= inv_f;
+    const float det = -sqr(b) + 4.0f * a * c;
+    const float inv_det = 1.0f / det;
+    const float u_sqrt = safe_sqrt(det * c), v_sqrt = safe_sqrt(a * det);
+    const int s0 = f2i_sat(ceilf(st.x - 2.0f * inv_det * u_sqrt)), s1 = f2i_sat(floorf(st.x + 2.0f * inv_det * u_sqrt));
+    const int t0 = f2i_sat(ceilf(st.y - 2.0f * inv_det * v_sqrt)), t1 = f2i_sat(floorf(st.y + 2.0f * inv_det * v_sqrt));
+    float3 sum = f3(0.0f, 0.0f, 0.0f); float sum_wts = 0.0f;
+    for (int it = t0; it <= t1; ++it) {
+        const float tt = (float)it - st.y;
+        for (int is = s0; is <= s1; ++is) {
+            const float ss = (float)is - st.x;
+            const float r2 = a * sqr(ss) + b * ss * tt + c * sqr(tt);
+            if (r2 < 1.0f) {
+                const uint32_t index = min(f2u_sat(r2 * 128.0f), 127u);
+                const float w = __ldg(tv.sc.mip_lut + index);
+                float3 tx;
+                if (RGB && tv.t.n_channels == 3) tx = f3(tv.channel(L, is, it, 0), tv.channel(L, is, it, 1), tv.channel(L, is, it, 2));
+                else { const float v = tv.channel(L, is, it, 0); tx = f3(v, v, v); }
+                sum = sum + tx * w;
+                sum_wts += w;
+            }
+        }
+    }
+    return sum / sum_wts;
+}
+// MIPMap::filter mipmap.rs:121-201
+template <bool RGB> SGD float3 tex_filter(const TexView& tv, float2 st, float2 dst0, float2 dst1) {
+    const int n_levels = tv.t.n_levels;
+    if (tv.t.filter == SG_FILTER_EWA) {
+        if (dst0.x * dst0.x + dst0.y * dst0.y < dst1.x * dst1.x + dst1.y * dst1.y) { const float2 tmp = dst0; dst0 = dst1; dst1 = tmp; }
+        const float longer = sqrtf(dst0.x * dst0.x + dst0.y * dst0.y);
+        float shorter = sqrtf(dst1.x * dst1.x + dst1.y * dst1.y);
+        if (shorter * tv.t.max_anisotropy < longer && shorter > 0.0f) {
+            const float scale = longer / (shorter * tv.t.max_anisotropy);
+            dst1.x *= scale; dst1.y *= scale; shorter *= scale;
+        }
+        if (shorter == 0.0f) return tex_bilerp<RGB>(tv, 0, st);
+        const float lod = fmaxf(0.0f, (float)n_levels - 1.0f + log2f(shorter));
+        const int ilod = (int)(f2u_sat(floorf(lod)) & 0x7fffffffu);
+        return tex_lerp(lod - (float)ilod, tex_ewa<RGB>(tv, ilod, st, dst0, dst1), tex_ewa<RGB>(tv, ilod + 1, st, dst0, dst1));
+    }
+    const float width = 2.0f * fmaxf(fmaxf(fmaxf(fabsf(dst0.x), fabsf(dst0.y)), fabsf(dst1.x)), fabsf(dst1.y));
+    const float level = (float)n_levels - 1.0f + log2f(fmaxf(width, 1e-8f));
+    if (level >= (float)n_levels - 1.0f) return tex_texel<RGB>(tv, n_levels - 1, 0, 0);
+    const int il = max(0, f2i_sat(floorf(level)));
+    if (tv.t.filter == SG_FILTER_POINT) {
+        const SgImageLevel L = tv.level(il);
+        return tex_texel<RGB>(tv, il, f2i_sat(roundf(st.x * (float)L.res[0] - 0.5f)), f2i_sat(roundf(st.y * (float)L.res[1] - 0.5f)));
+    }
+    if (tv.t.filter == SG_FILTER_BILINEAR) return tex_bilerp<RGB>(tv, il, st);
+    if (il == 0) return tex_bilerp<RGB>(tv, 0, st);                                              // trilinear
+    return tex_lerp(level - (float)il, tex_bilerp<RGB>(tv, il, st), tex_bilerp<RGB>(tv, il + 1, st));
+}
+
+// rgb2spec 0.1.1 RGB2Spec::fetch (third party; published rgb2spec.c `rgb2spec_fetch`)
+SGD void rgb2spec_fetch(const DScene& sc, const float rgb_in[3], float out[3]) {
+    const int res = (int)sc.rgb2spec_res;
+    float rgb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rgb[i] = fmaxf(fminf(rgb_in[i], 1.0f), 0.0f);
+    int i = 0;
+    if (rgb[1] >= rgb[i]) i = 1;
+    if (rgb[2] >= (i == 0 ? rgb[0] : rgb[1])) i = 2;
+    const float z = i == 0 ? rgb[0] : (i == 1 ? rgb[1] : rgb[2]);
+    const float cx = i == 0 ? rgb[1] : (i == 1 ? rgb[2] : rgb[0]);
+    const float cy = i == 0 ? rgb[2] : (i == 1 ? rgb[0] : rgb[1]);
+    const float scale = (float)(res - 1) / z, x = cx * scale, y = cy * scale;
+    const uint32_t xi = min(f2u_sat(x), (uint32_t)(res - 2)), yi = min(f2u_sat(y), (uint32_t)(res - 2));
+    uint32_t left = 0, last = (uint32_t)res - 2, size = last;
+    while (size > 0) {
+        const uint32_t half = size >> 1, middle = left + half + 1;
+        if (__ldg(sc.rgb2spec_scale + middle) <= z) { left = middle; size -= half + 1; } else size = half;
+    }
+    const uint32_t zi = min(left, last);
+    size_t offset = ((((size_t)i * res + zi) * res + yi) * res + xi) * 3;
+    const size_t dx = 3, dy = 3 * (size_t)res, dz = 3 * (size_t)res * res;
+    const float x1 = x - (float)xi, x0 = 1.0f - x1, y1 = y - (float)yi, y0 = 1.0f - y1;
+    const float sz0 = __ldg(sc.rgb2spec_scale + zi), sz1 = __ldg(sc.rgb2spec_scale + zi + 1);
+    const float z1 = (z - sz0) / (sz1 - sz0), z0 = 1.0f - z1;
+    const float* T = sc.rgb2spec_data;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        out[j] = ((__ldg(T + offset) * x0 + __ldg(T + offset + dx) * x1) * y0 + (__ldg(T + offset + dy) * x0 + __ldg(T + offset + dy + dx) * x1) * y1) * z0 +
+                 ((__ldg(T + offset + dz) * x0 + __ldg(T + offset + dz + dx) * x1) * y0 + (__ldg(T + offset + dz + dy) * x0 + __ldg(T + offset + dz + dy + dx) * x1) * y1) * z1;
+        offset++;
+    }
+}
+// RgbSigmoidPolynomial::get color.rs:352-383; poly(lambda, [c2, c1, c0]) = c2 + c1 x + c0 x^2 (Estrin: fused)
+SGD float sigmoid_poly_get(const float c[3], float lambda) {
+    const float x = fmaf(lambda * lambda, c[0], fmaf(lambda, c[1], c[2]));
+    if (isinf(x)) return x > 0.0f ? 1.0f : 0.0f;
+    return 0.5f + x / (2.0f * sqrtf(1.0f + x * x));
+}
+
+struct TexCoordCtx { float2 uv; float dudx, dudy, dvdx, dvdy; };
+
+SGD void uv_map(const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {   // texture.rs:918-936
+    const float dsdx = t.su * c.dudx, dsdy = t.su * c.dudy, dtdx = t.sv * c.dvdx, dtdy = t.sv * c.dvdy;
+    st.x = t.su * c.uv.x + t.du; st.y = t.sv * c.uv.y + t.dv;
+    st.y = 1.0f - st.y;
+    dst0 = make_float2(dsdx, dtdx); dst1 = make_float2(dsdy, dtdy);
+}
+// FloatImageTexture::evaluate texture.rs:393-404
+__device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
+    const SgTexture t = sc.textures[tex];
+    const TexView tv{sc, t};
+    float2 st, d0, d1; uv_map(t, c, st, d0, d1);
+    const float v = tex_filter<false>(tv, st, d0, d1).x * t.scale;
+    return t.invert ? fmaxf(0.0f, 1.0f - v) : v;
+}
+// SpectrumImageTexture::evaluate texture.rs:777-808
+__device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
+    const SgTexture t = sc.textures[tex];
+    const TexView tv{sc, t};
+    float2 st, d0, d1; uv_map(t, c, st, d0, d1);
+    float3 rgb = tex_filter<true>(tv, st, d0, d1) * t.scale;
+    if (t.invert) rgb = f3(1.0f - rgb.x, 1.0f - rgb.y, 1.0f - rgb.z);
+    rgb = f3(fmaxf(0.0f, rgb.x), fmaxf(0.0f, rgb.y), fmaxf(0.0f, rgb.z));                        // clamp_zero
+    if (t.n_channels != 3) return spec1(rgb.x);
+    float in[3] = {rgb.x, rgb.y, rgb.z}, coef[3], scale = 1.0f;
+    if (t.spectrum_type == SG_SPECTRUM_TYPE_UNBOUNDED) {                                         // spectrum.rs:534-546
+        const float m = fmaxf(fmaxf(rgb.x, rgb.y), rgb.z);
+        scale = 2.0f * m;
+        if (scale != 0.0f) { in[0] = rgb.x / scale; in[1] = rgb.y / scale; in[2] = rgb.z / scale; } else { in[0] = in[1] = in[2] = 0.0f; }
+    }
+    rgb2spec_fetch(sc, in, coef);
+    Spec s = make_float4(sigmoid_poly_get(coef, lam.lambda.x), sigmoid_poly_get(coef, lam.lambda.y), sigmoid_poly_get(coef, lam.lambda.z),
+                         sigmoid_poly_get(coef, lam.lambda.w));
+    if (t.spectrum_type == SG_SPECTRUM_TYPE_UNBOUNDED) s = scale * s;
+    return s;
+}
+
+// ---- screen-space differentials ----
+SGD float3 xform_normal_t(const float* m, float3 n) {             // apply_normal_helper transform.rs:779-786
+    return f3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
+}
+SGD float3 mul3(const float* r, float3 v) { return f3(r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z); }
+SGD float3 mul3t(const float* r, float3 v) { return f3(r[0] * v.x + r[3] * v.y + r[6] * v.z, r[1] * v.x + r[4] * v.y + r[7] * v.z, r[2] * v.x + r[5] * v.y + r[8] * v.z); }
+SGD float3 ld3(const float* a) { return f3(a[0], a[1], a[2]); }
+
+// Camera::approximate_dp_dxy camera.rs:308-354 (Transform::rotate_from_to transform.rs:227-253 inlined)
+__device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, float3 n, int spp, uint32_t option_flags, float3& dpdx, float3& dpdy) {
+    const SgCamera& cam = sc.camera;
+    const float3 p_camera = xform_point(cam.camera_from_render, p);
+    const float3 from = normalize3(p_camera), to = f3(0.0f, 0.0f, 1.0f);
+    float3 ref1;
+    if (fabsf(from.x) < 0.72f && fabsf(to.x) < 0.72f) ref1 = f3(1.0f, 0.0f, 0.0f);
+    else if (fabsf(from.y) < 0.72f && fabsf(to.y) < 0.72f) ref1 = f3(0.0f, 1.0f, 0.0f);
+    else ref1 = f3(0.0f, 0.0f, 1.0f);
+    const float3 u = ref1 - from, v = ref1 - to;
+    float r[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float kron = i == j ? 1.0f : 0.0f;
+            r[3 * i + j] = kron - 2.0f / dot3(u, u) * comp3(u, i) * comp3(u, j) - 2.0f / dot3(v, v) * comp3(v, i) * comp3(v, j)
+                           + 4.0f * dot3(u, v) / (dot3(u, u) * dot3(v, v)) * comp3(v, i) * comp3(u, j);
+        }
+    const float3 p_down_z = f3(r[0] * p_camera.x + r[1] * p_camera.y + r[2] * p_camera.z + 0.0f, r[3] * p_camera.x + r[4] * p_camera.y + r[5] * p_camera.z + 0.0f,
+                               r[6] * p_camera.x + r[7] * p_camera.y + r[8] * p_camera.z + 0.0f);
+    const float3 n_down_z = mul3(r, xform_normal_t(cam.render_from_camera, n));
+    const float d = n_down_z.z * p_down_z.z;
+    const float3 xo = f3(0.0f, 0.0f, 0.0f) + ld3(cam.min_pos_differential_x), xd = f3(0.0f, 0.0f, 1.0f) + ld3(cam.min_dir_differential_x);
+    const float tx = -(dot3(n_down_z, xo) - d) / dot3(n_down_z, xd);
+    const float3 yo = f3(0.0f, 0.0f, 0.0f) + ld3(cam.min_pos_differential_y), yd = f3(0.0f, 0.0f, 1.0f) + ld3(cam.min_dir_differential_y);
+    const float ty = -(dot3(n_down_z, yo) - d) / dot3(n_down_z, yd);
+    const float3 px = xo + xd * tx, py = yo + yd * ty;
+    const float spp_scale = (option_flags & SG_OPT_DISABLE_PIXEL_JITTER) ? 1.0f : fmaxf(0.125f, 1.0f / sqrtf((float)spp));
+    dpdx = spp_scale * xform_vector(cam.render_from_camera, mul3t(r, px - p_down_z));
+    dpdy = spp_scale * xform_vector(cam.render_from_camera, mul3t(r, py - p_down_z));
+}
+
+// Extra per-hit geometry the textured path needs (Surf keeps what every path needs).
+struct SurfTex {
+    float2 uv; float3 dpdu, dpdv;        // geometric parameterisation (interaction.rs:111-148)
+    float3 dndu, dndv;                   // shading.dndu / dndv (triangle.rs:451-498)
+    float dudx, dudy, dvdx, dvdy; float3 dpdx, dpdy;
+};
+
+template <> SGD void surf_tex_store<false>(SurfTex*, float2, float3, float3, float3, float3) {}
+template <> SGD void surf_tex_store<true>(SurfTex* x, float2 uv, float3 dpdu, float3 dpdv, float3 dndu, float3 dndv) {
+    x->uv = uv; x->dpdu = dpdu; x->dpdv = dpdv; x->dndu = dndu; x->dndv = dndv;
+    x->dudx = x->dudy = x->dvdx = x->dvdy = 0.0f; x->dpdx = f3(0.0f, 0.0f, 0.0f); x->dpdy = f3(0.0f, 0.0f, 0.0f);
+}
+
+// SurfaceInteraction::compute_differentials interaction.rs:280-366
+SGD void compute_differentials(const DScene& sc, const Surf& s, SurfTex& x, const AuxRays& aux, int spp, uint32_t option_flags) {
+    if (option_flags & SG_OPT_DISABLE_TEXTURE_FILTERING) {
+        x.dudx = x.dudy = x.dvdx = x.dvdy = 0.0f; x.dpdx = f3(0.0f, 0.0f, 0.0f); x.dpdy = f3(0.0f, 0.0f, 0.0f);
+        return;
+    }
+    const float3 p = p3fi_mid(s.pi);
+    if (aux.has && dot3(s.n, aux.rxd) != 0.0f && dot3(s.n, aux.ryd) != 0.0f) {
+        const float d = -dot3(s.n, p);
+        const float tx = (-dot3(s.n, aux.rxo) - d) / dot3(s.n, aux.rxd);
+        const float3 px = aux.rxo + tx * aux.rxd;
+        const float ty = (-dot3(s.n, aux.ryo) - d) / dot3(s.n, aux.ryd);
+        const float3 py = aux.ryo + ty * aux.ryd;
+        x.dpdx = px - p; x.dpdy = py - p;
+    } else {
+        approximate_dp_dxy(sc, p, s.n, spp, option_flags, x.dpdx, x.dpdy);
+    }
+    const float ata00 = dot3(x.dpdu, x.dpdu), ata01 = dot3(x.dpdu, x.dpdv), ata11 = dot3(x.dpdv, x.dpdv);
+    float inv_det = 1.0f / dop(ata00, ata11, ata01, ata01);
+    if (!isfinite(inv_det)) inv_det = 0.0f;
+    const float atb0x = dot3(x.dpdu, x.dpdx), atb1x = dot3(x.dpdv, x.dpdx), atb0y = dot3(x.dpdu, x.dpdy), atb1y = dot3(x.dpdv, x.dpdy);
+    x.dudx = dop(ata11, atb0x, ata01, atb1x) * inv_det;
+    x.dvdx = dop(ata00, atb1x, ata01, atb0x) * inv_det;
+    x.dudy = dop(ata11, atb0y, ata01, atb1y) * inv_det;
+    x.dvdy = dop(ata00, atb1y, ata01, atb0y) * inv_det;
+    x.dudx = isfinite(x.dudx) ? clampf(x.dudx, -1e8f, 1e8f) : 0.0f;
+    x.dvdx = isfinite(x.dvdx) ? clampf(x.dvdx, -1e8f, 1e8f) : 0.0f;
+    x.dudy = isfinite(x.dudy) ? clampf(x.dudy, -1e8f, 1e8f) : 0.0f;
+    x.dvdy = isfinite(x.dvdy) ? clampf(x.dvdy, -1e8f, 1e8f) : 0.0f;
+}
+
+// bump_map material.rs:1477-1509 for a FloatImageTexture (tex >= 0) or the constant displacement `cdisp`; writes the
+// displaced shading.dpdu / dpdv (the caller then rebuilds the shading normal, interaction.rs:229-250)
+SGD void bump_map(const DScene& sc, int tex, float cdisp, Surf& s, const SurfTex& x) {
+    const TexCoordCtx c{x.uv, x.dudx, x.dudy, x.dvdx, x.dvdy};
+    float du = 0.5f * (fabsf(x.dudx) + fabsf(x.dudy));
+    if (du == 0.0f) du = 0.0005f;
+    float dv = 0.5f * (fabsf(x.dvdx) + fabsf(x.dvdy));
+    if (dv == 0.0f) dv = 0.0005f;
+    float u_displace, v_displace, displace;
+    if (tex >= 0) {
+        TexCoordCtx cu = c; cu.uv = make_float2(x.uv.x + du, x.uv.y + 0.0f);
+        TexCoordCtx cv = c; cv.uv = make_float2(x.uv.x + 0.0f, x.uv.y + dv);
+        u_displace = eval_float_texture(sc, tex, cu); v_displace = eval_float_texture(sc, tex, cv); displace = eval_float_texture(sc, tex, c);
+    } else u_displace = v_displace = displace = cdisp;
+    const float3 dpdu = s.sdpdu + (u_displace - displace) / du * s.sn + displace * x.dndu;
+    const float3 dpdv = s.sdpdv + (v_displace - displace) / dv * s.sn + displace * x.dndv;
+    s.sdpdu = dpdu; s.sdpdv = dpdv;
+}
+
+// SurfaceInteraction::spawn_ray_with_differentials interaction.rs:434-502 (auxiliary rays only)
+SGD AuxRays spawn_differentials(const Surf& s, const SurfTex& x, const AuxRays& in, float3 wo, float3 wi, int bx_flags, float eta) {
+    AuxRays out; out.has = false;
+    out.rxo = out.rxd = out.ryo = out.ryd = f3(0.0f, 0.0f, 0.0f);
+    if (!in.has) return out;
+    float3 n = s.sn;
+    float3 dndx = x.dndu * x.dudx + x.dndv * x.dvdx;
+    float3 dndy = x.dndu * x.dudy + x.dndv * x.dvdy;
+    const float3 dwodx = -in.rxd - wo, dwody = -in.ryd - wo;
+    const float3 p = p3fi_mid(s.pi);
+    if (bx_flags == (BX_SPECULAR | BX_REFLECTION)) {
+        out.has = true;
+        out.rxo = p + x.dpdx; out.ryo = p + x.dpdy;
+        const float dwo_dotn_dx = dot3(dwodx, n) + dot3(wo, dndx);
+        const float dwo_dotn_dy = dot3(dwody, n) + dot3(wo, dndy);
+        out.rxd = wi - dwodx + 2.0f * (dot3(wo, n) * dndx + dwo_dotn_dx * n);
+        out.ryd = wi - dwody + 2.0f * (dot3(wo, n) * dndy + dwo_dotn_dy * n);
+    } else if (bx_flags == (BX_SPECULAR | BX_TRANSMISSION)) {
+        out.has = true;
+        out.rxo = p + x.dpdx; out.ryo = p + x.dpdy;
+        if (dot3(wo, n) < 0.0f) { n = -n; dndx = -dndx; dndy = -dndy; }
+        const float dwo_dotn_dx = dot3(dwodx, n) + dot3(wo, dndx);
+        const float dwo_dotn_dy = dot3(dwody, n) + dot3(wo, dndy);
+        const float mu = dot3(wo, n) / eta - absdot3(wi, n);
+        const float dmudx = dwo_dotn_dx * (1.0f / eta + 1.0f / sqr(eta) * dot3(wo, n) / dot3(wi, n));
+        const float dmudy = dwo_dotn_dy * (1.0f / eta + 1.0f / sqr(eta) * dot3(wo, n) / dot3(wi, n));
+        out.rxd = wi - eta * dwodx + (mu * dndx + dmudx * n);
+        out.ryd = wi - eta * dwody + (mu * dndy + dmudy * n);
+    }
+    if (out.has && (len2(out.rxd) > 1e16f || len2(out.ryd) > 1e16f || len2(out.rxo) > 1e16f || len2(out.ryo) > 1e16f)) out.has = false;
+    return out;
+}
+
+}  // namespace sg

@@ -8,6 +8,7 @@
 // Queue appends are warp-aggregated (__ballot_sync + one atomicAdd per warp and queue).
 #pragma once
 #include "sg_shading.cuh"
+#include "sg_texture.cuh"
 #include "sg_trace2.cuh"
 
 namespace sg {
@@ -32,8 +33,24 @@ struct PathState {
     float4* sh_o;       // shadow ray origin
     float4* sh_d;       // shadow ray direction (unnormalised p_to - p_from)
     float4* sh_L;       // beta * Ld, added to L if the shadow ray is unoccluded
+    // auxiliary (differential) rays, allocated only for scenes with image textures: flags bit 10 = present
+    float4* aux0;       // rx_origin.xyz, rx_direction.x
+    float4* aux1;       // rx_direction.yz, ry_origin.xy
+    float4* aux2;       // ry_origin.z, ry_direction.xyz
 };
-static constexpr int kPathBytes = 16 * 16 + 4 + 4 + 4 + 8;   // per-path HBM footprint (276 B)
+static constexpr int kPathBytes = 16 * 16 + 4 + 4 + 4 + 8;   // per-path HBM footprint (276 B; +48 B with image textures)
+static constexpr uint32_t kFlagSpecular = 256u, kFlagNonSpecular = 512u, kFlagAux = 1024u;
+SGD AuxRays aux_load(const PathState& st, uint32_t path) {
+    const float4 a = st.aux0[path], b = st.aux1[path], c = st.aux2[path];
+    AuxRays r; r.has = true;
+    r.rxo = f3(a.x, a.y, a.z); r.rxd = f3(a.w, b.x, b.y); r.ryo = f3(b.z, b.w, c.x); r.ryd = f3(c.y, c.z, c.w);
+    return r;
+}
+SGD void aux_store(const PathState& st, uint32_t path, const AuxRays& r) {
+    st.aux0[path] = make_float4(r.rxo.x, r.rxo.y, r.rxo.z, r.rxd.x);
+    st.aux1[path] = make_float4(r.rxd.y, r.rxd.z, r.ryo.x, r.ryo.y);
+    st.aux2[path] = make_float4(r.ryo.z, r.ryd.x, r.ryd.y, r.ryd.z);
+}
 
 enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_NKINDS = 5 };
 // per-depth counter block (uint32 x 16)
@@ -110,7 +127,18 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     const int px = rc.win_x0 + wx, py = rc.win_y0 + wy;
     Rng rng; rng.seed_from_u64(stream_key(rc.seed, (uint32_t)(py * rc.full_res_x + px), (uint32_t)s));
     Wavelengths lam; float3 o, d; float w;
-    camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
+    uint32_t flags0 = 0u;
+    if (st.aux0 != nullptr) {                        // scene has image textures: camera ray differentials (camera.rs:1036-1079)
+        AuxRays aux;
+        camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w, &aux);
+        if (!(rc.option_flags & SG_OPT_DISABLE_PIXEL_JITTER)) {                    // integrator.rs:355-361, ray.rs:137-145
+            const float sc_ = fmaxf(0.125f, 1.0f / sqrtf((float)rc.spp));
+            aux.rxo = o + (aux.rxo - o) * sc_; aux.ryo = o + (aux.ryo - o) * sc_;
+            aux.rxd = d + (aux.rxd - d) * sc_; aux.ryd = d + (aux.ryd - d) * sc_;
+        }
+        aux_store(st, i, aux);
+        flags0 = kFlagAux;
+    } else camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
     st.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
     st.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
     st.L[i] = spec1(0.0f);
@@ -118,7 +146,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     st.lambda[i] = lam.lambda; st.lpdf[i] = lam.pdf;
     st.rng_a[i] = make_ulonglong2(rng.s0, rng.s1); st.rng_b[i] = make_ulonglong2(rng.s2, rng.s3);
     st.pixel[i] = pix;
-    st.flags[i] = 0u;
+    st.flags[i] = flags0;
     st.pb_eta[i] = make_float2(1.0f, 1.0f);
     st.ctx0[i] = make_float4(0, 0, 0, 0); st.ctx1[i] = make_float4(0, 0, 0, 0); st.ctx2[i] = make_float4(0, 0, 0, 0);
     q.ray[0][i] = i;
@@ -293,7 +321,9 @@ SGD uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s0 ^ (
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS 4
 #endif
-template <int KIND>
+// TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture
+// lookups, bump mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.
+template <int KIND, bool TEX>
 __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
@@ -324,7 +354,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             float2 pbe = st.pb_eta[path];
             float p_b = pbe.x, eta_scale = pbe.y;
 
-            Surf s = make_surface(sc, geo, hb.x, hb.y, hb.z);
+            SurfTex sx;
+            Surf s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
 
             // emission + MIS against light sampling, :798-813
             if (light_id >= 0) {
@@ -346,13 +377,25 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
 
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
             const SgMaterial mat = sc.materials[material_id];
+            AuxRays aux; aux.has = false;
+            if (TEX) {
+                if (sc.n_textures > 0) {
+                    if (fl & kFlagAux) aux = aux_load(st, path);
+                    compute_differentials(sc, s, sx, aux, rc.spp, rc.option_flags);                 // interaction.rs:201
+                }
+                if ((mat.flags & SG_MAT_HAS_DISPLACEMENT) && (mat.tex_displacement >= 0 || mat.displacement != 0.0f))
+                    bump_map(sc, mat.tex_displacement, mat.displacement, s, sx);
+            }
             if (mat.flags & SG_MAT_HAS_DISPLACEMENT) apply_constant_bump(s);
+            TexCoordCtx tc; if (TEX) tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
             BSDF<KIND> bsdf;
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
-                bsdf.r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);          // material.rs:307-310
+                bsdf.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
+                                                                    : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);          // material.rs:307-310
             } else if (KIND == SG_MATERIAL_COATED_DIFFUSE) {                                    // material.rs:917-963
-                bsdf.lay.r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);
+                bsdf.lay.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
+                                                                        : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);
                 float ur = mat.u_roughness, vr = mat.v_roughness;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }
                 bsdf.lay.mf = TR::make(ur, vr);
@@ -441,6 +484,10 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                     st.ctx0[path] = make_float4(s.pi.lo.x, s.pi.lo.y, s.pi.lo.z, s.pi.hi.x);
                     st.ctx1[path] = make_float4(s.pi.hi.y, s.pi.hi.z, s.n.x, s.n.y);
                     st.ctx2[path] = make_float4(s.n.z, s.sn.x, s.sn.y, s.sn.z);
+                    if (TEX && sc.n_textures > 0) {                                            // spawn_ray_with_differentials :434-502
+                        aux = spawn_differentials(s, sx, aux, wo, bs.wi, bs.flags, bs.eta);
+                        if (aux.has) aux_store(st, path, aux);
+                    }
                     const float3 no = offset_ray_origin(s.pi, s.n, bs.wi);                     // Interaction::spawn_ray
                     st.ray_o[path] = make_float4(no.x, no.y, no.z, 0.0f);
                     st.ray_d[path] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.0f);
@@ -460,7 +507,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             if (alive) {
                 st.beta[path] = beta;
                 st.pb_eta[path] = make_float2(p_b, eta_scale);
-                st.flags[path] = (uint32_t)pdepth | (specular_bounce ? 256u : 0u) | (any_non_specular ? 512u : 0u);
+                st.flags[path] = (uint32_t)pdepth | (specular_bounce ? kFlagSpecular : 0u) | (any_non_specular ? kFlagNonSpecular : 0u) |
+                                 (TEX && aux.has ? kFlagAux : 0u);
             }
             if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE) st.lpdf[path] = lam.pdf;   // terminate_secondary
             want_next = alive;
@@ -581,6 +629,18 @@ __global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc,
     float* l = out_lambda + 8 * i;
     l[0] = lam.lambda.x; l[1] = lam.lambda.y; l[2] = lam.lambda.z; l[3] = lam.lambda.w;
     l[4] = lam.pdf.x; l[5] = lam.pdf.y; l[6] = lam.pdf.z; l[7] = lam.pdf.w;
+}
+__global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* lambda, float* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TexCoordCtx c; c.uv = make_float2(q[6 * i], q[6 * i + 1]); c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
+    Spec s;
+    if (as_float) s = spec1(eval_float_texture(sc, tex, c));
+    else {
+        Wavelengths w; w.lambda = make_float4(lambda[4 * i], lambda[4 * i + 1], lambda[4 * i + 2], lambda[4 * i + 3]); w.pdf = spec1(1.0f);
+        s = eval_spectrum_texture(sc, tex, c, w);
+    }
+    out[4 * i] = s.x; out[4 * i + 1] = s.y; out[4 * i + 2] = s.z; out[4 * i + 3] = s.w;
 }
 // RgbFilm::get_pixel_rgb film.rs:720-738
 __global__ void k_film_develop(const __grid_constant__ DScene sc, const double* film, long long n, float* out) {

@@ -57,6 +57,7 @@ struct SgScene {
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
     bool kinds_present[4] = {false, false, false, false};
+    bool tex_path = false;          // image textures or a non-zero constant displacement: k_shade<KIND, true>
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
     uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
@@ -75,11 +76,13 @@ int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
     Workspace& w = s->ws;
     if (w.capacity >= capacity && w.max_depth >= max_depth) return SG_OK;
     w.release();
+    w.st = PathState{};
     int rc;
     const size_t n = capacity;
 #define WS(field) if ((rc = ws_alloc(w, &w.st.field, n)) != SG_OK) return rc
     WS(ray_o); WS(ray_d); WS(hit_b); WS(hit_prim); WS(L); WS(beta); WS(lambda); WS(lpdf); WS(rng_a); WS(rng_b);
     WS(pixel); WS(flags); WS(pb_eta); WS(ctx0); WS(ctx1); WS(ctx2); WS(sh_o); WS(sh_d); WS(sh_L);
+    if (s->d.n_textures > 0) { WS(aux0); WS(aux1); WS(aux2); }      // ray differentials only feed image-texture filtering
 #undef WS
     if ((rc = ws_alloc(w, &w.q.ray[0], n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.ray[1], n)) != SG_OK) return rc;
@@ -148,6 +151,36 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (m.spec_a < 0 || m.spec_a >= (int32_t)desc->n_spectra || (m.kind == SG_MATERIAL_CONDUCTOR && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra)))
             return fail(SG_ERR_INVALID_ARGUMENT, "material spectrum id out of range");
     }
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const SgMaterial& m = desc->materials[i];
+        for (int32_t t : {m.tex_reflectance, m.tex_displacement})
+            if (t >= (int32_t)desc->n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + " references an out-of-range texture");
+        if (m.tex_reflectance >= 0 && m.kind != SG_MATERIAL_DIFFUSE && m.kind != SG_MATERIAL_COATED_DIFFUSE)
+            return fail(SG_ERR_UNSUPPORTED, "reflectance textures are on the GPU path for diffuse and coated-diffuse materials only");
+        if (m.tex_displacement >= 0 && desc->textures[m.tex_displacement].n_channels != 1)
+            return fail(SG_ERR_UNSUPPORTED, "displacement textures must be one-channel images");
+    }
+    bool need_rgb2spec = false;
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const SgTexture& t = desc->textures[i];
+        if (!desc->textures || !desc->image_levels || !desc->texels) return fail(SG_ERR_INVALID_ARGUMENT, "texture arrays missing");
+        if ((t.n_channels != 1 && t.n_channels != 3) || t.n_levels < 1 || (uint64_t)t.first_level + (uint64_t)t.n_levels > desc->n_image_levels)
+            return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": bad channel count or level range");
+        if (t.wrap < SG_WRAP_REPEAT || t.wrap > SG_WRAP_CLAMP || t.filter < SG_FILTER_POINT || t.filter > SG_FILTER_EWA ||
+            t.spectrum_type < SG_SPECTRUM_TYPE_ALBEDO || t.spectrum_type > SG_SPECTRUM_TYPE_UNBOUNDED)
+            return fail(SG_ERR_UNSUPPORTED, "texture " + std::to_string(i) + ": wrap / filter / spectrum type not on the GPU path");
+        if (t.filter == SG_FILTER_EWA && !desc->mip_filter_lut) return fail(SG_ERR_INVALID_ARGUMENT, "EWA filtering needs mip_filter_lut");
+        for (int32_t l = 0; l < t.n_levels; ++l) {
+            const SgImageLevel& L = desc->image_levels[t.first_level + l];
+            if (L.res[0] < 1 || L.res[1] < 1 || (uint64_t)L.offset + (uint64_t)L.res[0] * (uint64_t)L.res[1] * (uint64_t)t.n_channels > desc->n_texels)
+                return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": MIP level outside the texel pool");
+        }
+        const SgImageLevel& last = desc->image_levels[t.first_level + t.n_levels - 1];
+        if (last.res[0] != 1 || last.res[1] != 1) return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": the last MIP level must be 1x1 (image.rs:783)");
+        need_rgb2spec |= t.n_channels == 3;
+    }
+    if (need_rgb2spec && (desc->rgb2spec_res < 2 || !desc->rgb2spec_scale || !desc->rgb2spec_data))
+        return fail(SG_ERR_INVALID_ARGUMENT, "three-channel textures need the rgb2spec table of the scene colour space");
     for (uint32_t i = 0; i < desc->n_nodes; ++i) {
         const SgBvhNode& nd = desc->nodes[i];
         if (nd.n_prims > 0 ? (nd.offset + nd.n_prims > desc->n_primitives) : (nd.offset >= desc->n_nodes || i + 1 >= desc->n_nodes))
@@ -242,7 +275,17 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     UP(pool, desc->spectrum_pool, desc->n_pool, float);
     UP(materials, desc->materials, desc->n_materials, SgMaterial);
     UP(lights, desc->lights, desc->n_lights, SgLight);
+    UP(textures, desc->textures, desc->n_textures, SgTexture);
+    UP(image_levels, desc->image_levels, desc->n_textures ? desc->n_image_levels : 0, SgImageLevel);
+    UP(texels, desc->texels, desc->n_textures ? desc->n_texels : 0, float);
+    UP(mip_lut, desc->mip_filter_lut, desc->mip_filter_lut ? 128 : 0, float);
+    UP(rgb2spec_scale, desc->rgb2spec_scale, need_rgb2spec ? desc->rgb2spec_res : 0, float);
+    UP(rgb2spec_data, desc->rgb2spec_data, need_rgb2spec ? (size_t)9 * desc->rgb2spec_res * desc->rgb2spec_res * desc->rgb2spec_res : 0, float);
 #undef UP
+    d.n_textures = desc->n_textures; d.rgb2spec_res = need_rgb2spec ? desc->rgb2spec_res : 0;
+    s->tex_path = desc->n_textures > 0;
+    for (uint32_t i = 0; i < desc->n_materials; ++i)
+        if ((desc->materials[i].flags & SG_MAT_HAS_DISPLACEMENT) && desc->materials[i].displacement != 0.0f) s->tex_path = true;
     d.n_nodes = desc->n_nodes; d.n_prims = desc->n_primitives; d.n_lights = desc->n_lights; d.n_materials = desc->n_materials;
     d.n_infinite = 0;
     for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_UNIFORM_INFINITE) {
@@ -339,10 +382,12 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
-            if (s->kinds_present[SG_MATERIAL_DIFFUSE]) { k_shade<SG_MATERIAL_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
-            if (s->kinds_present[SG_MATERIAL_CONDUCTOR]) { k_shade<SG_MATERIAL_CONDUCTOR><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
-            if (s->kinds_present[SG_MATERIAL_DIELECTRIC]) { k_shade<SG_MATERIAL_DIELECTRIC><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
-            if (s->kinds_present[SG_MATERIAL_COATED_DIFFUSE]) { k_shade<SG_MATERIAL_COATED_DIFFUSE><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+#define SHADE(KIND) if (s->kinds_present[KIND]) { \
+                if (s->tex_path) k_shade<KIND, true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
+                else k_shade<KIND, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
+                ++launches; }
+            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE)
+#undef SHADE
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
                 if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
@@ -513,6 +558,25 @@ int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_
     CUX(cudaStreamSynchronize(g_stream));
     CUX(cudaMemcpy(out_rays, d_r, (size_t)n * 24, cudaMemcpyDeviceToHost));
     CUX(cudaMemcpy(out_lambda, d_l, (size_t)n * 32, cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return SG_OK;
+}
+
+int sg_texture_eval(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || n < 0 || (n > 0 && (!q || !lambda || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (tex < 0 || (uint32_t)tex >= s->d.n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture id out of range");
+    if (n == 0) return SG_OK;
+    float *d_q = nullptr, *d_l = nullptr, *d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_l); cudaFree(d_o); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CUX(cudaMalloc((void**)&d_q, (size_t)n * 24)); CUX(cudaMalloc((void**)&d_l, (size_t)n * 16)); CUX(cudaMalloc((void**)&d_o, (size_t)n * 16));
+    CUX(cudaMemcpy(d_q, q, (size_t)n * 24, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_l, lambda, (size_t)n * 16, cudaMemcpyHostToDevice));
+    k_texture_eval<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, tex, as_float, (long long)n, d_q, d_l, d_o);
+    CUX(cudaStreamSynchronize(g_stream));
+    CUX(cudaMemcpy(out, d_o, (size_t)n * 16, cudaMemcpyDeviceToHost));
 #undef CUX
     cleanup();
     return SG_OK;

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 2
+SG_ABI_VERSION = 3
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -59,11 +59,13 @@ class SgImageLevel(C.Structure):
 class SgTexture(C.Structure):
     _fields_ = [("n_channels", C.c_int32), ("n_levels", C.c_int32), ("first_level", C.c_uint32), ("wrap", C.c_int32),
                 ("filter", C.c_int32), ("max_anisotropy", C.c_float), ("scale", C.c_float), ("invert", C.c_int32),
-                ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float)]
+                ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float),
+                ("spectrum_type", C.c_int32), ("pad", C.c_int32 * 3)]
 
 
 SG_WRAP_REPEAT, SG_WRAP_BLACK, SG_WRAP_CLAMP = 0, 1, 2
 SG_FILTER_POINT, SG_FILTER_BILINEAR, SG_FILTER_TRILINEAR, SG_FILTER_EWA = 0, 1, 2, 3
+SG_SPECTRUM_TYPE_ALBEDO, SG_SPECTRUM_TYPE_UNBOUNDED = 0, 1
 
 
 class SgLight(C.Structure):
@@ -103,6 +105,7 @@ class SgSceneDesc(C.Structure):
                 ("n_image_levels", C.c_uint32), ("image_levels", C.POINTER(SgImageLevel)),
                 ("n_texels", C.c_uint64), ("texels", C.POINTER(C.c_float)),
                 ("mip_filter_lut", C.POINTER(C.c_float)),
+                ("rgb2spec_res", C.c_uint32), ("rgb2spec_scale", C.POINTER(C.c_float)), ("rgb2spec_data", C.POINTER(C.c_float)),
                 ("camera", SgCamera), ("film", SgFilm)]
 
 
@@ -135,7 +138,7 @@ class SgHit(C.Structure):
 # every symbol include/shimmer_gpu.h declares; tests/test_abi.py checks the library exports all
 ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
                "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
-               "sg_film_develop"]
+               "sg_film_develop", "sg_texture_eval"]
 
 
 class ShimmerGpuError(RuntimeError):
@@ -174,6 +177,7 @@ def load_library():
     lib.sg_camera_rays.argtypes = [vp, C.POINTER(SgRenderParams), i64, vp, vp, vp, vp]
     lib.sg_camera_rays.restype = C.c_int
     lib.sg_film_develop.argtypes = [vp, vp, i64, vp]; lib.sg_film_develop.restype = C.c_int
+    lib.sg_texture_eval.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp]; lib.sg_texture_eval.restype = C.c_int
     _lib = lib
     return lib
 

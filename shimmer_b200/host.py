@@ -234,6 +234,7 @@ class SceneBuilder:
         self.materials = []
         self.meshes = []         # dicts
         self.extra_lights = []   # non-area lights in add order (scene.rs add_light)
+        self.textures = []       # dicts: levels (list of HxWxC f32 arrays) + SgTexture parameters
         self.camera = None
         self.film = None
         self.world_from_camera = None
@@ -247,10 +248,40 @@ class SceneBuilder:
             self._spec_cache[key] = len(self.spectra) - 1
         return len(self.spectra) - 1
 
-    def diffuse(self, reflectance):
-        """DiffuseMaterial::create (material.rs:259-283): displacement is ALWAYS Some(0.0)."""
+    def image_texture(self, image, filter="bilinear", wrap="repeat", max_anisotropy=8.0, scale=1.0, invert=False,
+                      su=1.0, sv=1.0, du=0.0, dv=0.0, spectrum_type="albedo"):
+        """ImageTextureBase::new (texture.rs:283-330) + MIPMap::new -> Image::generate_pyramid (image.rs:699-787).
+        `image`: H x W (one channel) or H x W x 3 array of LINEAR values, row 0 = top of the image (what
+        Image::get_channel returns after colour decoding).  Power-of-two sizes only: the reference first
+        resamples other sizes with a Lanczos filter (image.rs float_resize_up), which this host stand-in omits."""
+        img = np.asarray(image, dtype=np.float32)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        H, W, Cn = img.shape
+        if Cn not in (1, 3) or (W & (W - 1)) or (H & (H - 1)):
+            raise ValueError("image textures must be one- or three-channel with power-of-two resolution")
+        levels = [img]
+        while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:           # 2x2 box filter, image.rs:733-768
+            a = levels[-1]
+            h, w = a.shape[:2]
+            y1 = np.arange(0, h, 2) + (1 if h > 1 else 0); x1 = np.arange(0, w, 2) + (1 if w > 1 else 0)
+            y0 = np.arange(0, h, 2); x0 = np.arange(0, w, 2)
+            nxt = f32(0.25) * (((a[y0][:, x0] + a[y0][:, x1]) + a[y1][:, x0]) + a[y1][:, x1])
+            levels.append(nxt.astype(np.float32))
+        self.textures.append(dict(levels=levels, n_channels=Cn,
+                                  filter={"point": 0, "bilinear": 1, "trilinear": 2, "ewa": 3, "EWA": 3}[filter],
+                                  wrap={"repeat": 0, "black": 1, "clamp": 2}[wrap], max_anisotropy=max_anisotropy, scale=scale,
+                                  invert=1 if invert else 0, su=su, sv=sv, du=du, dv=dv,
+                                  spectrum_type={"albedo": 0, "unbounded": 1}[spectrum_type]))
+        return len(self.textures) - 1
+
+    def diffuse(self, reflectance, reflectance_tex=None, displacement_tex=None):
+        """DiffuseMaterial::create (material.rs:259-283): displacement is ALWAYS Some(0.0) unless a texture is given.
+        `reflectance_tex` / `displacement_tex`: ids from image_texture()."""
         self.materials.append(dict(kind=ffi.SG_MATERIAL_DIFFUSE, spec_a=self.spectrum(reflectance), spec_b=-1,
-                                   flags=ffi.SG_MAT_HAS_DISPLACEMENT | ffi.SG_MAT_REMAP_ROUGHNESS, ur=0.0, vr=0.0))
+                                   flags=ffi.SG_MAT_HAS_DISPLACEMENT | ffi.SG_MAT_REMAP_ROUGHNESS, ur=0.0, vr=0.0,
+                                   tex_reflectance=-1 if reflectance_tex is None else reflectance_tex,
+                                   tex_displacement=-1 if displacement_tex is None else displacement_tex))
         return len(self.materials) - 1
 
     def conductor(self, eta, k, roughness=0.0, remap=True):
@@ -266,11 +297,15 @@ class SceneBuilder:
         return len(self.materials) - 1
 
     def coated_diffuse(self, reflectance, eta=("const", 1.5), roughness=0.0, thickness=0.01, albedo=("const", 0.0), g=0.0,
-                       max_depth=10, n_samples=1, remap=True):
+                       max_depth=10, n_samples=1, remap=True, reflectance_tex=None, displacement_tex=None):
         """CoatedDiffuseMaterial::create (material.rs:820-903); displacement defaults to None."""
         self.materials.append(dict(kind=ffi.SG_MATERIAL_COATED_DIFFUSE, spec_a=self.spectrum(reflectance), spec_b=self.spectrum(albedo),
                                    spec_c=self.spectrum(eta), flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness,
-                                   thickness=thickness, g=g, max_depth=max_depth, n_samples=n_samples))
+                                   thickness=thickness, g=g, max_depth=max_depth, n_samples=n_samples,
+                                   tex_reflectance=-1 if reflectance_tex is None else reflectance_tex,
+                                   tex_displacement=-1 if displacement_tex is None else displacement_tex))
+        if displacement_tex is not None:
+            self.materials[-1]["flags"] |= ffi.SG_MAT_HAS_DISPLACEMENT
         return len(self.materials) - 1
 
     # -- camera / film -----------------------------------------------------------------------
@@ -311,6 +346,7 @@ class SceneBuilder:
         cam.dy_camera[:] = dy_camera.astype(np.float32).tolist()
         cam.lens_radius = lens_radius; cam.focal_distance = focal_distance
         cam.shutter_open = 0.0; cam.shutter_close = 1.0
+        self._find_minimum_differentials(cam, W, H)
         self.camera = cam
         film = ffi.SgFilm()
         film.full_resolution[:] = [W, H]
@@ -320,6 +356,43 @@ class SceneBuilder:
         film.max_component_value = float("inf")             # `maxcomponentvalue` default (film.rs RgbFilm::create)
         film.output_rgb_from_sensor_rgb[:] = srgb_output_matrix().ravel().tolist()
         self.film = film
+
+    @staticmethod
+    def _find_minimum_differentials(cam, W, H):
+        """CameraBase::find_minimum_differentials (camera.rs:356-430): 512 film samples along the diagonal with
+        p_lens = (0.5, 0.5) (centre of the lens -> the thin-lens and pinhole branches of generate_ray_differential
+        coincide).  Host-side camera construction; f32 arithmetic like the reference."""
+        cfr = np.array(cam.camera_from_raster[:], np.float32).reshape(4, 4)
+        rfc = np.array(cam.render_from_camera[:], np.float32).reshape(4, 4)
+        cfrn = np.array(cam.camera_from_render[:], np.float32).reshape(4, 4)
+        dxc, dyc = np.array(cam.dx_camera[:], np.float32), np.array(cam.dy_camera[:], np.float32)
+
+        def nrm(v):
+            return (v / np.sqrt(np.sum(v * v, dtype=np.float32), dtype=np.float32)).astype(np.float32)
+
+        def length(v):
+            return float(np.sqrt(np.sum(v * v, dtype=np.float32)))
+        best = [np.full(3, np.inf, np.float32) for _ in range(4)]
+        n = 512
+        for i in range(n):
+            pf = np.array([f32(i) / f32(n - 1) * f32(W), f32(i) / f32(n - 1) * f32(H), 0.0, 1.0], np.float32)
+            pc = cfr @ pf
+            pc = (pc[:3] / pc[3]).astype(np.float32) if pc[3] != 1.0 else pc[:3]
+            d = rfc[:3, :3] @ nrm(pc)
+            rxd = rfc[:3, :3] @ nrm(pc + dxc); ryd = rfc[:3, :3] @ nrm(pc + dyc)
+            dox = cfrn[:3, :3] @ np.zeros(3, np.float32); doy = dox          # rx_origin == ry_origin == o for a perspective camera
+            if length(dox) < length(best[0]): best[0] = dox
+            if length(doy) < length(best[1]): best[1] = doy
+            d, rxd, ryd = nrm(d), nrm(rxd), nrm(ryd)
+            sign = f32(math.copysign(1.0, d[2])); a = f32(-1.0) / (sign + d[2]); b = d[0] * d[1] * a      # Frame::from_z -> coordinate_system
+            fx = np.array([f32(1.0) + sign * d[0] * d[0] * a, sign * b, -sign * d[0]], np.float32)
+            fy = np.array([b, sign + d[1] * d[1] * a, -d[1]], np.float32)
+            F = np.stack([fx, fy, d]).astype(np.float32)
+            df = F @ d; dxf = nrm(F @ rxd); dyf = nrm(F @ ryd)
+            if length(dxf - df) < length(best[2]): best[2] = (dxf - df).astype(np.float32)
+            if length(dyf - df) < length(best[3]): best[3] = (dyf - df).astype(np.float32)
+        cam.min_pos_differential_x[:] = best[0].tolist(); cam.min_pos_differential_y[:] = best[1].tolist()
+        cam.min_dir_differential_x[:] = best[2].tolist(); cam.min_dir_differential_y[:] = best[3].tolist()
 
     # -- geometry ------------------------------------------------------------------------------
     def add_mesh(self, p, indices, material, n=None, uv=None, area_light=None, reverse_orientation=False,
@@ -466,6 +539,26 @@ class SceneBuilder:
         A["materials"] = mats
         A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
         A["meshes"] = mesh_rows
+        # image textures: every MIP level, linear f32 texels, channels interleaved
+        tex_rows = (ffi.SgTexture * max(len(self.textures), 1))()
+        level_rows, texel_chunks, toff = [], [], 0
+        for ti, t in enumerate(self.textures):
+            r = tex_rows[ti]
+            r.n_channels, r.n_levels, r.first_level = t["n_channels"], len(t["levels"]), len(level_rows)
+            r.wrap, r.filter, r.max_anisotropy, r.scale, r.invert = t["wrap"], t["filter"], t["max_anisotropy"], t["scale"], t["invert"]
+            r.su, r.sv, r.du, r.dv, r.spectrum_type = t["su"], t["sv"], t["du"], t["dv"], t["spectrum_type"]
+            for lv in t["levels"]:
+                L = ffi.SgImageLevel(); L.offset = toff; L.res[:] = [lv.shape[1], lv.shape[0]]
+                level_rows.append(L); texel_chunks.append(np.ascontiguousarray(lv, np.float32).ravel()); toff += lv.size
+        A["textures"] = tex_rows
+        A["image_levels"] = (ffi.SgImageLevel * max(len(level_rows), 1))(*level_rows)
+        A["texels"] = np.concatenate(texel_chunks) if texel_chunks else np.zeros(1, np.float32)
+        A["mip_lut"] = np.ascontiguousarray(tables()["MIP_FILTER_LUT"], np.float32)
+        need_rgb = any(t["n_channels"] == 3 for t in self.textures)
+        if need_rgb:
+            from . import rgb2spec
+            sc_, dt_ = rgb2spec.build_table(16)
+            A["rgb2spec_scale"] = np.ascontiguousarray(sc_, np.float32); A["rgb2spec_data"] = np.ascontiguousarray(dt_, np.float32).ravel()
         d = out.desc
         d.abi_version = ffi.SG_ABI_VERSION
         d.n_nodes = n_nodes; d.nodes = _as_ptr(A["nodes"], ffi.SgBvhNode)
@@ -480,6 +573,13 @@ class SceneBuilder:
         d.n_pool = len(A["pool"]); d.spectrum_pool = _as_ptr(A["pool"], C.c_float)
         d.n_materials = len(self.materials); d.materials = A["materials"]
         d.n_lights = len(lights); d.lights = A["lights"]
+        d.n_textures = len(self.textures); d.textures = A["textures"]
+        d.n_image_levels = len(level_rows); d.image_levels = A["image_levels"]
+        d.n_texels = len(A["texels"]) if texel_chunks else 0; d.texels = _as_ptr(A["texels"], C.c_float)
+        d.mip_filter_lut = _as_ptr(A["mip_lut"], C.c_float)
+        if need_rgb:
+            d.rgb2spec_res = len(A["rgb2spec_scale"]); d.rgb2spec_scale = _as_ptr(A["rgb2spec_scale"], C.c_float)
+            d.rgb2spec_data = _as_ptr(A["rgb2spec_data"], C.c_float)
         d.camera = self.camera
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
         d.film = self.film

@@ -134,6 +134,16 @@ class WavefrontPathIntegrator(Integrator):
                                            rays.ctypes.data, lam.ctypes.data), "sg_camera_rays")
         return rays, lam
 
+    def texture_eval(self, tex, q, lambda4=None, as_float=False):
+        """SpectrumImageTexture / FloatImageTexture::evaluate (texture.rs:393-404,777-808) for n lookups; q = n x 6
+        (u v dudx dudy dvdx dvdy) -> n x 4."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 6); n = len(q)
+        lam = np.ascontiguousarray(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4, np.float32).reshape(-1, 4)
+        out = np.zeros((n, 4), np.float32)
+        ffi.check(self._lib.sg_texture_eval(self._handle, int(tex), 1 if as_float else 0, n, q.ctypes.data, lam.ctypes.data,
+                                            out.ctypes.data), "sg_texture_eval")
+        return out
+
     def develop(self, film=None):
         """RgbFilm::get_pixel_rgb (film.rs:720-738) -> (H, W, 3) f32 output RGB."""
         film = self.film if film is None else film

@@ -173,8 +173,41 @@ def composite_scene(n_theta=708, n_phi=708, resolution=(3840, 2160), crop=None):
     return b
 
 
+def procedural_image(n=64, channels=3):
+    """Deterministic linear-valued test image (row 0 = top): checker x gradients, closed form."""
+    y, x = np.mgrid[0:n, 0:n].astype(np.float64) / n
+    checker = (np.floor(x * 8.0) + np.floor(y * 8.0)) % 2.0
+    r = 0.12 + 0.76 * checker
+    g = 0.18 + 0.64 * x
+    bl = 0.22 + 0.56 * y * (1.0 - 0.5 * checker)
+    if channels == 1:
+        return (0.2 + 0.6 * (0.5 + 0.5 * np.sin(9.0 * x + 2.0) * np.cos(7.0 * y))).astype(np.float32)
+    return np.stack([r, g, bl], axis=-1).astype(np.float32)
+
+
+def uv_sphere(n_theta, n_phi, center, radius):
+    """Sphere with vertex normals and lat-long uv (duplicated seam column so uv stays continuous)."""
+    th = np.linspace(0.0, math.pi, n_theta + 1)
+    ph = np.linspace(0.0, 2.0 * math.pi, n_phi + 1)
+    T, Pp = np.meshgrid(th, ph, indexing="ij")
+    N = np.stack([np.sin(T) * np.cos(Pp), np.cos(T), np.sin(T) * np.sin(Pp)], axis=-1).reshape(-1, 3)
+    P = N * radius + np.asarray(center, dtype=np.float64)
+    UV = np.stack([Pp / (2.0 * math.pi), 1.0 - T / math.pi], axis=-1).reshape(-1, 2)
+    idx = []
+    for i in range(n_theta):
+        for j in range(n_phi):
+            a = i * (n_phi + 1) + j; b = a + 1; c = a + n_phi + 1; d = c + 1
+            if i > 0: idx.append((a, b, d))
+            if i < n_theta - 1: idx.append((a, d, c))
+    return P.astype(np.float32), np.asarray(idx, np.uint32), N.astype(np.float32), UV.astype(np.float32)
+
+
+TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
+
+
 def tiny_scene(kind="diffuse", resolution=(32, 32)):
-    """A few dozen triangles exercising one material each; used by the fast parity tests."""
+    """A few dozen triangles exercising one material each; used by the fast parity tests.  The `tex*` kinds add image
+    textures (RGB + one-channel, every filter / wrap mode), bump mapping and specular ray-differential propagation."""
     b = SceneBuilder()
     b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
     white = b.diffuse(_white())
@@ -192,12 +225,35 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         mat = b.coated_diffuse(_red())
     elif kind == "coatedrough":
         mat = b.coated_diffuse(_green(), roughness=0.15, albedo=("const", 0.4), g=0.3, thickness=0.05)
+    elif kind in TEXTURED_KINDS:
+        rgb_img, mono_img = procedural_image(64, 3), procedural_image(32, 1)
+        guv = np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32)
+        if kind == "tex":        # bilinear RGB ground (tiled), trilinear one-channel sphere with interpolated normals
+            ground = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="bilinear", su=3.0, sv=3.0, du=0.25))
+            mat = b.diffuse(_white(), reflectance_tex=b.image_texture(mono_img, filter="trilinear", su=2.0, sv=1.0))
+        elif kind == "texewa":   # EWA RGB ground seen directly and through a smooth mirror (specular reflection differentials)
+            ground = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="ewa", su=5.0, sv=5.0, max_anisotropy=8.0))
+            mat = b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0)
+        elif kind == "texbump":  # point-filtered, clamped, unbounded-spectrum ground with an image displacement; glass sphere (transmission differentials)
+            ground = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="point", wrap="clamp", su=1.5, sv=1.5, scale=0.9,
+                                                                         spectrum_type="unbounded"),
+                               displacement_tex=b.image_texture(mono_img, filter="bilinear", su=6.0, sv=6.0, scale=0.05))
+            mat = b.dielectric(("const", 1.5))
+        else:                    # coated diffuse with an inverted, black-wrapped texture + bump on the sphere
+            ground = b.coated_diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="trilinear", wrap="black", su=1.3, sv=1.3, du=-0.15,
+                                                                                 invert=True))
+            mat = b.diffuse(_green(), displacement_tex=b.image_texture(mono_img, filter="ewa", su=4.0, sv=2.0, scale=0.02))
+        P, I, Nn, UV = uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)
+        b.add_mesh(P, I, mat, n=Nn, uv=UV)
+        gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+        b.add_mesh(gp, gi, ground, uv=guv)
     else:
         raise ValueError(kind)
-    P, I = displaced_sphere(12, 16, center=(0.0, 0.6, 0.0), radius=0.6, amp=0.0)
-    b.add_mesh(P, I, mat)
-    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
-    b.add_mesh(gp, gi, white)
+    if kind not in TEXTURED_KINDS:
+        P, I = displaced_sphere(12, 16, center=(0.0, 0.6, 0.0), radius=0.6, amp=0.0)
+        b.add_mesh(P, I, mat)
+        gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+        b.add_mesh(gp, gi, white)
     lp, li = _quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
     b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
     if kind == "mirror":

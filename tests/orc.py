@@ -54,6 +54,11 @@ def lib():
     L.orc_bounds_intersect.argtypes = [vp, vp, vp, vp, C.c_float]; L.orc_bounds_intersect.restype = C.c_int
     L.orc_light_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]; L.orc_light_sample.restype = C.c_int
     L.orc_light_pdf.argtypes = [vp, C.c_int, vp, vp, vp, vp]; L.orc_light_pdf.restype = C.c_float
+    L.orc_rotate_from_to.argtypes = [vp, vp, vp]
+    L.orc_sigmoid_poly_get.argtypes = [vp, C.c_float]; L.orc_sigmoid_poly_get.restype = C.c_float
+    L.orc_rgb2spec_fetch.argtypes = [vp, vp, vp]
+    L.orc_texture_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
+    L.orc_approximate_dp_dxy.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp]
     _lib = L
     return L
 
@@ -102,4 +107,13 @@ def camera_rays(scene, params, pixel_xy, sample_index):
 def develop(scene, film):
     out = np.zeros((len(film), 3), np.float32)
     lib().orc_film_develop(scene.ptr(), np.ascontiguousarray(film).ctypes.data, len(film), out.ctypes.data)
+    return out
+
+
+def texture_eval(scene, tex, q, lambda4=None, as_float=False):
+    """q: n x 6 (u v dudx dudy dvdx dvdy); returns n x 4."""
+    q = fa(q).reshape(-1, 6); n = len(q)
+    lam = fa(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4).reshape(-1, 4)
+    out = np.zeros((n, 4), np.float32)
+    lib().orc_texture_eval(scene.ptr(), tex, 1 if as_float else 0, n, q.ctypes.data, lam.ctypes.data, out.ctypes.data)
     return out

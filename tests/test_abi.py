@@ -35,7 +35,7 @@ def test_struct_sizes_match_the_header_layout():
     assert C.sizeof(ffi.SgMesh) == 32
     assert C.sizeof(ffi.SgSpectrum) == 32
     assert C.sizeof(ffi.SgMaterial) == 64
-    assert C.sizeof(ffi.SgTexture) == 48 and C.sizeof(ffi.SgImageLevel) == 16
+    assert C.sizeof(ffi.SgTexture) == 64 and C.sizeof(ffi.SgImageLevel) == 16
     assert C.sizeof(ffi.SgLight) == 64
     assert C.sizeof(ffi.SgFilmPixel) == 32
     assert C.sizeof(ffi.SgHit) == 32

@@ -168,7 +168,7 @@ def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
     assert rmse < 0.01
 
 
-@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"])
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"] + list(scenes.TEXTURED_KINDS))
 def test_tiny_scene_films(kind):
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
     integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 4, "seed": 5})
@@ -178,6 +178,39 @@ def test_tiny_scene_films(kind):
     gold = json.load(open(os.path.join(GOLDEN, "tiny_films.json")))[kind]
     assert abs(int(integ.stats.closest_hit_rays) - gold["closest_hit_rays"]) <= 2
     assert np.allclose(film.sum(axis=0), gold["film_sum"], rtol=5e-3)
+    integ.close()
+
+
+def test_texture_lookup_parity():
+    """sg_texture_eval vs the oracle for every filter / wrap mode, RGB and one-channel, random footprints (incl. zero
+    and strongly anisotropic ones).  Filtering is pure f32 arithmetic; only log2f (level selection) may differ in the
+    last bit, so a handful of lookups that sit exactly on a level boundary are allowed to disagree."""
+    rgb_img, mono = scenes.procedural_image(64, 3), scenes.procedural_image(32, 1)
+    b = scenes.SceneBuilder(); b.set_camera((0, 0, -3), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+    ids = []
+    for filt in ("point", "bilinear", "trilinear", "ewa"):
+        for wrap in ("repeat", "clamp", "black"):
+            ids.append((b.image_texture(rgb_img, filter=filt, wrap=wrap, su=1.7, sv=0.8, du=0.1, dv=-0.2, scale=0.9,
+                                        spectrum_type="unbounded" if wrap == "clamp" else "albedo", invert=(wrap == "black")), False))
+            ids.append((b.image_texture(mono, filter=filt, wrap=wrap, max_anisotropy=4.0), True))
+    m = b.diffuse(("const", 0.5), reflectance_tex=ids[0][0])
+    b.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32), m)
+    sc = b.build()
+    integ = create_integrator("wavefront", {}, sc, {"pixelsamples": 1})
+    rng = np.random.default_rng(4)
+    n = 4096
+    q = np.zeros((n, 6), np.float32)
+    q[:, :2] = rng.random((n, 2)) * 4.0 - 1.5
+    q[:, 2:] = (rng.random((n, 4)) - 0.5) * (10.0 ** rng.uniform(-4, -0.3, (n, 1)))
+    q[: n // 8, 2:] = 0.0                                                   # zero footprint
+    q[n // 8: n // 4, 4:] *= 0.02                                           # anisotropic
+    lam = rng.uniform(360.0, 830.0, (n, 4)).astype(np.float32)
+    for tex, as_float in ids:
+        got = integ.texture_eval(tex, q, lam, as_float=as_float)
+        exp = orc.texture_eval(sc, tex, q, lam, as_float=as_float)
+        close = np.isclose(got, exp, rtol=2e-5, atol=2e-6).all(axis=1)
+        assert close.mean() > 0.998, (tex, as_float, close.mean())
+        assert np.isfinite(got[close]).all()
     integ.close()
 
 
