@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3
+#define SG_ABI_VERSION 4
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -55,12 +55,33 @@ typedef struct SgBvhNode {
 
 /* One entry per `Primitive::{Simple,Geometric}` in BVH leaf order
  * (`ordered_primitives`, src/aggregate.rs:236-266; src/primitive.rs:30-35). */
+#define SG_PRIM_INSTANCE 0xffffffffu   /* SgPrimitive.mesh of a `Primitive::Transformed`: tri = index into instances */
 typedef struct SgPrimitive {
-    uint32_t mesh;      /* index into SgSceneDesc.meshes                        */
-    uint32_t tri;       /* Triangle::tri_index within that mesh (triangle.rs:49) */
+    uint32_t mesh;      /* index into SgSceneDesc.meshes, or SG_PRIM_INSTANCE   */
+    uint32_t tri;       /* Triangle::tri_index within that mesh (triangle.rs:49), or the instance index */
     uint32_t material;  /* index into materials                                  */
     int32_t  light;     /* area light index into lights, or -1 (SimplePrimitive) */
 } SgPrimitive;
+
+/* ---- object instancing (src/primitive.rs:136-176 TransformedPrimitive, src/loading/scene.rs:814-866) ----
+ * An object definition is a group of primitives with its own BvhAggregate (scene.rs:821-830).  Its nodes live in
+ * SgSceneDesc.nodes at [first_node, first_node + n_nodes) with second-child offsets RELATIVE to first_node and leaf
+ * primitive offsets RELATIVE to first_prim; its primitives are SgSceneDesc.primitives[first_prim, first_prim + n_prims)
+ * in that BVH's leaf order.  n_nodes == 0: the definition is one bare primitive (no aggregate).  The top-level
+ * BvhAggregate is nodes[0, n_top_nodes) over primitives[0, n_top_primitives); only it may hold instance primitives. */
+typedef struct SgObject {
+    uint32_t first_node, n_nodes, first_prim, n_prims;
+} SgObject;
+typedef struct SgInstance {
+    float    render_from_primitive[16];   /* Transform::m, row-major     */
+    float    primitive_from_render[16];   /* Transform::m_inv            */
+    uint32_t object;                      /* index into objects          */
+    uint32_t pad[3];
+} SgInstance;
+/* The reference transforms shadow rays with the FORWARD instance transform (primitive.rs:172-175; closest-hit uses
+ * the inverse, :159-163) and maps interaction vectors/normals through the INVERSE transform (transform.rs:573-609).
+ * Default: reproduce exactly that.  SG_SCENE_FIX_INSTANCING selects the pbrt semantics instead. */
+enum { SG_SCENE_FIX_INSTANCING = 1 };
 
 /* `TriangleMesh` (src/shape/mesh.rs:9-20); vertices already in render space
  * (mesh.rs:43-46).  Attribute arrays are scene-global; a mesh addresses
@@ -211,6 +232,11 @@ typedef struct SgSceneDesc {
     uint32_t abi_version;         /* SG_ABI_VERSION */
     uint32_t n_nodes;      const SgBvhNode*   nodes;
     uint32_t n_primitives; const SgPrimitive* primitives;
+    uint32_t n_top_nodes;                                   /* top-level BVH = nodes[0, n_top_nodes); 0 = n_nodes           */
+    uint32_t n_top_primitives;                              /* top-level primitives;                  0 = n_primitives      */
+    uint32_t n_objects;    const SgObject*    objects;
+    uint32_t n_instances;  const SgInstance*  instances;
+    uint32_t scene_flags;                                   /* SG_SCENE_*                                                   */
     uint32_t n_meshes;     const SgMesh*      meshes;
     uint32_t n_indices;    const uint32_t*    indices;     /* 3 per triangle               */
     uint32_t n_vertices;   const float*       p;           /* xyz per vertex               */
@@ -283,7 +309,7 @@ typedef struct SgStats {
 /* `ShapeIntersection` reduced to what parity needs (shape.rs:221-225 +
  * TriangleIntersection triangle.rs:748-755 + geometric normal triangle.rs:407-412). */
 typedef struct SgHit {
-    int32_t prim;     /* index into SgSceneDesc.primitives, -1 = miss */
+    int32_t prim;     /* index into SgSceneDesc.primitives (for an instanced hit: the primitive inside the object), -1 = miss */
     float   t;
     float   b0, b1, b2;
     float   ng[3];

@@ -118,34 +118,97 @@ struct Scene {
     }
 };
 
-struct Hit { int32_t prim; TriHit th; };
+struct Hit { int32_t prim; int32_t inst; TriHit th; };
 
-// aggregate.rs:71-139 (any_hit = false) and :141-203 (any_hit = true).
+// Transform::apply_ray_inverse transform.rs:701-723 (inverse = true) / Transform::apply_ray :515-532 (inverse = false)
+// with Some(t_max): origin through the Point3fi transform of an EXACT point (:631-700 / :385-457 -- note the inverse
+// variant's error term omits the translation column), shifted to the edge of its error bounds; t_max reduced by dt.
+inline Ray instance_ray(const SgInstance& I, const Ray& r, bool inverse, Float* t_max) {
+    const float* m = inverse ? I.primitive_from_render : I.render_from_primitive;
+    Float x = r.o.x, y = r.o.y, z = r.o.z;
+    Float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
+    Float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
+    Float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
+    Float wp = (m[12] * x + m[13] * y) + (m[14] * z + m[15]);
+    V3 err;
+    if (inverse) err = v3(gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z)),
+                          gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z)),
+                          gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z)));
+    else err = v3(gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3])),
+                  gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7])),
+                  gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])));
+    P3fi o = p3fi_from_value_and_error(v3(xp, yp, zp), err);
+    (void)wp;                    // instance transforms are affine (last row 0 0 0 1): the `/ wp` branch (:453-457) is never taken
+    V3 d = v3(m[0] * r.d.x + m[1] * r.d.y + m[2] * r.d.z, m[4] * r.d.x + m[5] * r.d.y + m[6] * r.d.z, m[8] * r.d.x + m[9] * r.d.y + m[10] * r.d.z);
+    Float ls = length_squared(d);
+    if (ls > 0.0f) {
+        Float dt = dot(vabs(d), p3fi_error(o)) / ls;
+        *t_max = *t_max - dt;
+        V3 off = d * dt;
+        o.lo = v3(next_float_down(o.lo.x + off.x), next_float_down(o.lo.y + off.y), next_float_down(o.lo.z + off.z));   // interval.rs:353-356
+        o.hi = v3(next_float_up(o.hi.x + off.x), next_float_up(o.hi.y + off.y), next_float_up(o.hi.z + off.z));
+    }
+    Ray out; out.o = p3fi_mid(o); out.d = d; return out;
+}
+
+inline bool bvh_intersect_range(const Scene& sc, uint32_t node_base, uint32_t n_nodes, uint32_t prim_base, uint32_t n_prims,
+                                const Ray& ray, Float t_max, bool any_hit, Hit* hit, Counters* ctr);
+
+// One primitive: a Triangle behind Geometric/SimplePrimitive (primitive.rs:65-131) or a TransformedPrimitive (:136-176).
+inline bool primitive_intersect(const Scene& sc, uint32_t pi, const Ray& ray, Float t_max, bool any_hit, Hit* h, Counters* ctr) {
+    const SgSceneDesc* D = sc.d;
+    const SgPrimitive& pr = D->primitives[pi];
+    if (pr.mesh == SG_PRIM_INSTANCE) {
+        const SgInstance& I = D->instances[pr.tri];
+        const SgObject& O = D->objects[I.object];
+        // closest hit: inverse transform (:159-163); predicate: FORWARD transform in the reference (:172-175)
+        bool inverse = !any_hit || (D->scene_flags & SG_SCENE_FIX_INSTANCING);
+        Float tm = t_max;
+        Ray r2 = instance_ray(I, ray, inverse, &tm);
+        Hit h2;
+        if (!bvh_intersect_range(sc, O.first_node, O.n_nodes, O.first_prim, O.n_prims, r2, tm, any_hit, &h2, ctr)) return false;
+        h->prim = h2.prim; h->inst = (int32_t)pr.tri; h->th = h2.th;
+        return true;
+    }
+    V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);
+    if (ctr) ctr->tris++;
+    if (!intersect_triangle(ray, t_max, p0, p1, p2, &h->th)) return false;
+    h->prim = (int32_t)pi; h->inst = -1;
+    return true;
+}
+
+// aggregate.rs:71-139 (any_hit = false) and :141-203 (any_hit = true) over one BvhAggregate.
 // The reference builds the full SurfaceInteraction for every accepted candidate
 // (triangle.rs:529-535); only the last one survives, so it is built once by the caller.
-inline bool bvh_intersect(const Scene& sc, const Ray& ray, Float t_max, bool any_hit, Hit* hit, Counters* ctr) {
+inline bool bvh_intersect_range(const Scene& sc, uint32_t node_base, uint32_t n_nodes, uint32_t prim_base, uint32_t n_prims,
+                                const Ray& ray, Float t_max, bool any_hit, Hit* hit, Counters* ctr) {
     const SgSceneDesc* D = sc.d;
-    hit->prim = -1;
-    if (D->n_nodes == 0) return false;
+    hit->prim = -1; hit->inst = -1;
+    bool found = false;
+    if (n_nodes == 0) {                                       // bare primitive(s) without an aggregate
+        for (uint32_t i = 0; i < n_prims; ++i) {
+            Hit h;
+            if (primitive_intersect(sc, prim_base + i, ray, t_max, any_hit, &h, ctr)) {
+                *hit = h; if (any_hit) return true;
+                t_max = h.th.t; found = true;
+            }
+        }
+        return found;
+    }
     V3 inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
     uint32_t to_visit = 0, cur = 0;
     uint32_t stack[64];
-    bool found = false;
     for (;;) {
-        const SgBvhNode& node = D->nodes[cur];
+        const SgBvhNode& node = D->nodes[node_base + cur];
         if (ctr) ctr->nodes++;
         if (bounds_intersect_p_cached(node, ray.o, t_max, inv_dir, dir_is_neg)) {
             if (node.n_prims > 0) {
                 for (uint32_t i = 0; i < node.n_prims; ++i) {
-                    uint32_t pi = node.offset + i;
-                    const SgPrimitive& pr = D->primitives[pi];
-                    V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);
-                    TriHit th;
-                    if (ctr) ctr->tris++;
-                    if (intersect_triangle(ray, t_max, p0, p1, p2, &th)) {
-                        if (any_hit) { hit->prim = (int32_t)pi; hit->th = th; return true; }
-                        t_max = th.t; hit->prim = (int32_t)pi; hit->th = th; found = true;
+                    Hit h;
+                    if (primitive_intersect(sc, prim_base + node.offset + i, ray, t_max, any_hit, &h, ctr)) {
+                        *hit = h; if (any_hit) return true;
+                        t_max = h.th.t; found = true;
                     }
                 }
                 if (to_visit == 0) break;
@@ -160,6 +223,13 @@ inline bool bvh_intersect(const Scene& sc, const Ray& ray, Float t_max, bool any
         }
     }
     return found;
+}
+inline bool bvh_intersect(const Scene& sc, const Ray& ray, Float t_max, bool any_hit, Hit* hit, Counters* ctr) {
+    const SgSceneDesc* D = sc.d;
+    hit->prim = -1; hit->inst = -1;
+    if (D->n_nodes == 0) return false;
+    uint32_t tn = D->n_top_nodes ? D->n_top_nodes : D->n_nodes, tp = D->n_top_primitives ? D->n_top_primitives : D->n_primitives;
+    return bvh_intersect_range(sc, 0, tn, 0, tp, ray, t_max, any_hit, hit, ctr);
 }
 
 // ---- BVH build: aggregate.rs:207-468 ----------------------------------------
@@ -327,6 +397,39 @@ inline SurfaceInteraction interaction_from_intersection(const Scene& sc, uint32_
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
     return si;
+}
+
+
+// Transform::apply(SurfaceInteraction) transform.rs:573-609 for an instanced hit.  The reference maps every vector and
+// normal through `t = self.inverse()`: vectors by M^-1, normals by apply_normal_helper(t.m_inv = M) = M^T.  With
+// SG_SCENE_FIX_INSTANCING vectors go through M and normals through (M^-1)^T (pbrt).  pi: forward Point3fi transform of an
+// inexact point (:385-457).
+inline void transform_interaction(const SgSceneDesc* D, const SgInstance& I, SurfaceInteraction& si) {
+    const float* M = I.render_from_primitive; const float* Mi = I.primitive_from_render;
+    bool fix = (D->scene_flags & SG_SCENE_FIX_INSTANCING) != 0;
+    auto vec = [&](V3 v) { const float* m = fix ? M : Mi; return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
+    auto nrm = [&](V3 n) { const float* m = fix ? Mi : M; return v3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z); };
+    V3 p = p3fi_mid(si.pi), e = p3fi_error(si.pi);
+    Float x = p.x, y = p.y, z = p.z;
+    Float xp = (M[0] * x + M[1] * y) + (M[2] * z + M[3]);
+    Float yp = (M[4] * x + M[5] * y) + (M[6] * z + M[7]);
+    Float zp = (M[8] * x + M[9] * y) + (M[10] * z + M[11]);
+    V3 err;
+    bool exact = si.pi.lo.x == si.pi.hi.x && si.pi.lo.y == si.pi.hi.y && si.pi.lo.z == si.pi.hi.z;
+    auto row_err = [&](int r) {
+        Float a = gamma_n(3) * (std::fabs(M[4 * r] * x) + std::fabs(M[4 * r + 1] * y) + std::fabs(M[4 * r + 2] * z) + std::fabs(M[4 * r + 3]));
+        if (exact) return a;
+        return (gamma_n(3) + 1.0f) * (std::fabs(M[4 * r]) * e.x + std::fabs(M[4 * r + 1]) * e.y + std::fabs(M[4 * r + 2]) * e.z) + a;
+    };
+    err = v3(row_err(0), row_err(1), row_err(2));
+    si.pi = p3fi_from_value_and_error(v3(xp, yp, zp), err);
+    V3 n = normalize(nrm(si.n));
+    si.n = n;
+    si.wo = normalize(vec(si.wo));
+    si.dpdu = vec(si.dpdu); si.dpdv = vec(si.dpdv);
+    si.sn = face_forward(normalize(nrm(si.sn)), n);
+    si.sdpdu = vec(si.sdpdu); si.sdpdv = vec(si.sdpdv);
+    si.sdndu = nrm(si.sdndu); si.sdndv = nrm(si.sdndv);
 }
 
 }  // namespace orc

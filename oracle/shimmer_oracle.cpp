@@ -103,7 +103,15 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
             break;
         }
         const SgPrimitive& prim = D->primitives[hit.prim];
-        SurfaceInteraction si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -ray.d);
+        SurfaceInteraction si;
+        if (hit.inst >= 0) {                                                       // TransformedPrimitive::intersect primitive.rs:155-169
+            const SgInstance& I = D->instances[hit.inst];
+            const float* mi = I.primitive_from_render;
+            V3 d2 = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
+                       mi[8] * ray.d.x + mi[9] * ray.d.y + mi[10] * ray.d.z);
+            si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -d2);
+            transform_interaction(D, I, si);
+        } else si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -ray.d);
         si.material = (int32_t)prim.material; si.light = prim.light;
         if (si.light >= 0) {                                                       // :798-813
             const SgLight& lt = D->lights[si.light];

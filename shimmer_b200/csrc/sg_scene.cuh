@@ -16,6 +16,18 @@
 
 namespace sg {
 
+// One `TransformedPrimitive` (primitive.rs:136-176) as the kernels want it: both 3x4 matrices, the root of the object's
+// BvhAggregate (Node64 ref, or a leaf ref for a bare primitive) and that root's bounds.
+struct DInstance {
+    float m[12];            // render_from_primitive, rows 0..2
+    float mi[12];           // primitive_from_render, rows 0..2
+    float bmin[3], bmax[3]; // bounds of the object's root node (tested on entry like aggregate.rs:92-98)
+    uint32_t root_ref;
+    uint32_t root_has_bounds;   // 0: bare primitive without an aggregate (scene.rs:831-833)
+    uint32_t pad[2];
+};
+static constexpr uint32_t kKindInstance = 7u;     // tri_verts[3*i].w kind field of an instance primitive
+
 struct DScene {
     const float4* nodes;        // 2 float4 per node
     const float4* tri_verts;    // 3 float4 per primitive
@@ -38,6 +50,8 @@ struct DScene {
     const float* rgb2spec_scale;        // rgb2spec table of the scene colour space
     const float* rgb2spec_data;
     uint32_t rgb2spec_res, n_textures;
+    const DInstance* instances;         // object instancing
+    uint32_t n_instances, scene_flags;
     uint32_t n_nodes, n_prims, n_lights, n_materials;
     int32_t n_infinite;          // number of SG_LIGHT_UNIFORM_INFINITE lights
     int32_t infinite_ids[4];
@@ -129,7 +143,7 @@ SGD bool slab_test(float3 bmin, float3 bmax, float3 o, float3 inv_dir, int nx, i
     return t_min < ray_t_max && t_max > 0.0f;
 }
 
-struct HitRec { int prim; float t, b0, b1, b2; };
+struct HitRec { int prim; float t, b0, b1, b2; int inst; };
 
 // BvhAggregate::intersect (ANY=false, aggregate.rs:71-139) / intersect_predicate (ANY=true,
 // :141-203): same visiting order (near child by dir_is_neg[axis], far child pushed), same

@@ -280,6 +280,36 @@ template <> SGD void surf_tex_store<true>(SurfTex* x, float2 uv, float3 dpdu, fl
     x->dudx = x->dudy = x->dvdx = x->dvdy = 0.0f; x->dpdx = f3(0.0f, 0.0f, 0.0f); x->dpdy = f3(0.0f, 0.0f, 0.0f);
 }
 
+// Transform::apply(SurfaceInteraction) (transform.rs:573-609) for a hit inside an object instance.  `s` / `x` were built
+// in the instance's space with wo = -(M^-1 d).  The reference maps vectors through M^-1 and normals through M^T
+// (`t = self.inverse()`); with SG_SCENE_FIX_INSTANCING vectors go through M and normals through (M^-1)^T.  pi: forward
+// Point3fi transform of an inexact point (:385-457).  Returns interaction.wo in `wo_si`.
+template <bool TEX>
+__device__ __noinline__ void transform_interaction(const DScene& sc, const DInstance& I, float3 rd, Surf& s, SurfTex* x, float3& wo_si) {
+    const bool fix = (sc.scene_flags & SG_SCENE_FIX_INSTANCING) != 0;
+    const float* M = I.m; const float* Mi = I.mi;
+    const float* mv = fix ? M : Mi; const float* mn = fix ? Mi : M;
+    auto vec = [&](float3 v) { return f3(mv[0] * v.x + mv[1] * v.y + mv[2] * v.z, mv[4] * v.x + mv[5] * v.y + mv[6] * v.z, mv[8] * v.x + mv[9] * v.y + mv[10] * v.z); };
+    auto nrm = [&](float3 n) { return f3(mn[0] * n.x + mn[4] * n.y + mn[8] * n.z, mn[1] * n.x + mn[5] * n.y + mn[9] * n.z, mn[2] * n.x + mn[6] * n.y + mn[10] * n.z); };
+    const float3 d2 = f3(Mi[0] * rd.x + Mi[1] * rd.y + Mi[2] * rd.z, Mi[4] * rd.x + Mi[5] * rd.y + Mi[6] * rd.z, Mi[8] * rd.x + Mi[9] * rd.y + Mi[10] * rd.z);
+    wo_si = normalize3(vec(-d2));
+    const float3 p = p3fi_mid(s.pi), e = p3fi_err(s.pi);
+    const bool exact = s.pi.lo.x == s.pi.hi.x && s.pi.lo.y == s.pi.hi.y && s.pi.lo.z == s.pi.hi.z;
+    float pp[3], ee[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        pp[r] = (M[4 * r] * p.x + M[4 * r + 1] * p.y) + (M[4 * r + 2] * p.z + M[4 * r + 3]);
+        const float a = gamma_n(3) * (fabsf(M[4 * r] * p.x) + fabsf(M[4 * r + 1] * p.y) + fabsf(M[4 * r + 2] * p.z) + fabsf(M[4 * r + 3]));
+        ee[r] = exact ? a : (gamma_n(3) + 1.0f) * (fabsf(M[4 * r]) * e.x + fabsf(M[4 * r + 1]) * e.y + fabsf(M[4 * r + 2]) * e.z) + a;
+    }
+    s.pi = p3fi_make(f3(pp[0], pp[1], pp[2]), f3(ee[0], ee[1], ee[2]));
+    const float3 n = normalize3(nrm(s.n));
+    s.n = n;
+    s.sn = faceforward3(normalize3(nrm(s.sn)), n);
+    s.sdpdu = vec(s.sdpdu); s.sdpdv = vec(s.sdpdv);
+    if (TEX) { x->dpdu = vec(x->dpdu); x->dpdv = vec(x->dpdv); x->dndu = nrm(x->dndu); x->dndv = nrm(x->dndv); }
+}
+
 // SurfaceInteraction::compute_differentials interaction.rs:280-366
 SGD void compute_differentials(const DScene& sc, const Surf& s, SurfTex& x, const AuxRays& aux, int spp, uint32_t option_flags) {
     if (option_flags & SG_OPT_DISABLE_TEXTURE_FILTERING) {

@@ -61,6 +61,8 @@ struct TraceScene {
     int refill_threshold;
     int interior_burst;
     int prefetch;
+    const DInstance* instances; // object instancing (INST kernels only)
+    uint32_t scene_flags;
 };
 
 // Per-thread traversal stack: the first `levels` entries live in shared memory (level-major, so a warp's
@@ -89,14 +91,21 @@ struct Lane {
     int sp;
     int nx, ny, nz;
     HitRec hit;
+    // object instancing (INST kernels only): the instance being traversed (-1: top level), the stack level its
+    // traversal started at, the top-level t_max to restore on the way out, and whether it produced a hit
+    int inst; int sp_base; float t_saved; bool inst_hit;
 };
 
-template <bool ANY>
-SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_max, uint32_t& n_nodes, bool count) {
+SGD void lane_set_ray(Lane& L, float3 o, float3 d) {
     L.o = o;
     L.inv_dir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                 // aggregate.rs:76
     L.nx = L.inv_dir.x < 0.0f; L.ny = L.inv_dir.y < 0.0f; L.nz = L.inv_dir.z < 0.0f;
     L.rp = ray_precompute(d);
+}
+
+template <bool ANY>
+SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_max, uint32_t& n_nodes, bool count) {
+    lane_set_ray(L, o, d);
     L.t_max = t_max; L.sp = 0; L.hit.prim = -1;
     L.cur = kEmptyRef;
     if (ts.root_ref != kEmptyRef) {
@@ -109,24 +118,92 @@ SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_m
 }
 
 // Pops the next node whose entry distance is still in range; kEmptyRef when the stack runs dry.
-template <bool ANY, bool COUNT>
-SGD uint32_t lane_pop(Lane& L, const Stack& S, uint32_t& n_nodes) {
-    while (L.sp > 0) {
-        --L.sp;
-        uint32_t ref; float t = 0.0f;
-        S.get<ANY>(L.sp, ref, t);
-        if (COUNT) n_nodes++;                                   // the reference tests the bounds at pop time
-        if (COUNT && (ref & kFailBit)) continue;
-        if (ANY) return ref;                                    // t_max never shrinks for the predicate
-        if (t < L.t_max) return ref;
+// Transform::apply_ray_inverse (transform.rs:701-723, inverse = true) / apply_ray (:515-532) with Some(t_max): the
+// origin goes through the Point3fi transform of an exact point (the inverse variant's error term omits the translation
+// column, :650-662), is shifted to the edge of its error box, and t_max shrinks by dt.
+SGD void instance_ray(const DInstance& I, bool inverse, float3& o, float3& d, float& t_max) {
+    const float* m = inverse ? I.mi : I.m;
+    const float x = o.x, y = o.y, z = o.z;
+    const float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
+    const float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
+    const float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
+    float3 err = f3(fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z), fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z),
+                    fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z));
+    if (!inverse) err = f3(err.x + fabsf(m[3]), err.y + fabsf(m[7]), err.z + fabsf(m[11]));
+    err = f3(gamma_n(3) * err.x, gamma_n(3) * err.y, gamma_n(3) * err.z);
+    P3fi oi = p3fi_make(f3(xp, yp, zp), err);
+    const float3 dd = f3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z);
+    const float ls = len2(dd);
+    if (ls > 0.0f) {
+        const float dt = dot3(abs3(dd), p3fi_err(oi)) / ls;
+        t_max = t_max - dt;
+        const float3 off = dd * dt;
+        oi.lo = f3(next_down(oi.lo.x + off.x), next_down(oi.lo.y + off.y), next_down(oi.lo.z + off.z));   // interval.rs:353-356
+        oi.hi = f3(next_up(oi.hi.x + off.x), next_up(oi.hi.y + off.y), next_up(oi.hi.z + off.z));
     }
-    return kEmptyRef;
+    o = p3fi_mid(oi); d = dd;
+}
+
+// TransformedPrimitive::intersect / intersect_predicate (primitive.rs:155-175): move the lane into the instance's space
+// and start on the object's BvhAggregate.  The closest-hit path uses the inverse transform; the predicate uses the FORWARD
+// one in the reference (unless SG_SCENE_FIX_INSTANCING).
+template <bool ANY, bool COUNT>
+SGD void lane_enter_instance(const TraceScene& ts, Lane& L, uint32_t inst_id, float3 o, float3 d, uint32_t& n_nodes) {
+    const DInstance& I = ts.instances[inst_id];
+    float tm = L.t_max;
+    instance_ray(I, !ANY || (ts.scene_flags & SG_SCENE_FIX_INSTANCING) != 0, o, d, tm);
+    L.t_saved = L.t_max; L.t_max = tm; L.inst = (int)inst_id; L.sp_base = L.sp; L.inst_hit = false;
+    lane_set_ray(L, o, d);
+    L.cur = I.root_ref;
+    if (I.root_has_bounds) {
+        float te;
+        if (COUNT) n_nodes++;
+        const bool ok = slab_entry(I.bmin[0], I.bmin[1], I.bmin[2], I.bmax[0], I.bmax[1], I.bmax[2], o, L.inv_dir, L.nx, L.ny, L.nz, te);
+        if (!(ok && te < tm)) L.cur = kEmptyRef;
+    }
+}
+
+// Pops the next node whose entry distance is still in range; kEmptyRef when the stack runs dry.  When an instance's
+// part of the stack is exhausted the lane returns to render space (the original ray is re-read through `io`) and goes
+// on with the top-level entries below.
+template <bool ANY, bool COUNT, bool INST, class IO, class IdxT>
+SGD uint32_t lane_pop(Lane& L, const Stack& S, uint32_t& n_nodes, IO& io, IdxT idx) {
+    if constexpr (!INST) {
+        while (L.sp > 0) {
+            --L.sp;
+            uint32_t ref; float t = 0.0f;
+            S.get<ANY>(L.sp, ref, t);
+            if (COUNT) n_nodes++;                                   // the reference tests the bounds at pop time
+            if (COUNT && (ref & kFailBit)) continue;
+            if (ANY) return ref;                                    // t_max never shrinks for the predicate
+            if (t < L.t_max) return ref;
+        }
+        return kEmptyRef;
+    } else {
+        for (;;) {
+            while (L.sp > L.sp_base) {
+                --L.sp;
+                uint32_t ref; float t = 0.0f;
+                S.get<ANY>(L.sp, ref, t);
+                if (COUNT) n_nodes++;
+                if (COUNT && (ref & kFailBit)) continue;
+                if (ANY) return ref;
+                if (t < L.t_max) return ref;
+            }
+            if (L.inst < 0) return kEmptyRef;
+            float3 o, d; float tm;
+            io.load(idx, o, d, tm);                                 // back to the render-space ray
+            lane_set_ray(L, o, d);
+            if (!L.inst_hit) L.t_max = L.t_saved;                   // else t_max = si.t_hit of the instanced hit (primitive.rs:162)
+            L.inst = -1; L.sp_base = 0;
+        }
+    }
 }
 
 // One interior step: fetch a Node64, test both children, push the far one, move to the near one
 // (or pop).  Leaves `L.cur` at an interior ref, a leaf ref, or kEmptyRef (ray finished).
-template <bool ANY, bool COUNT>
-SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes) {
+template <bool ANY, bool COUNT, bool INST, class IO, class IdxT>
+SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes, IO& io, IdxT idx) {
     const float4* nd = ts.node64 + 4 * (size_t)L.cur;
     const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
     const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
@@ -154,27 +231,40 @@ SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint3
     }
     if (COUNT) n_nodes++;                                               // near child's bounds test
     if (near_ok && near_t < L.t_max) L.cur = near_ref;
-    else L.cur = lane_pop<ANY, COUNT>(L, S, n_nodes);
+    else L.cur = lane_pop<ANY, COUNT, INST>(L, S, n_nodes, io, idx);
 }
 
 // The leaf's primitives (aggregate.rs:99-110), then pop.  Returns true when an any-hit ray is done.
-template <bool ANY, bool COUNT>
-SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes, uint32_t& n_tris) {
+template <bool ANY, bool COUNT, bool INST, class IO, class IdxT>
+SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& n_nodes, uint32_t& n_tris, IO& io, IdxT idx) {
     uint32_t pi = L.cur & ~kLeafBit;
     for (;;) {
         const float4* tv = ts.tri_verts + 3 * (size_t)pi;
         const float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+        if constexpr (INST) if (((__float_as_uint(v0.w) >> 28) & 7u) == kKindInstance) {
+            // a TransformedPrimitive: the rest of this leaf (if any) resumes from the stack after the instance
+            if (!(__float_as_uint(v2.w) & kLastInLeaf)) {
+                S.put<ANY>(L.sp, kLeafBit | (pi + 1), -INFINITY); L.sp++;
+                if (COUNT) n_nodes--;                               // the resume entry is not a node visit
+            }
+            float3 o, d; float tm;
+            io.load(idx, o, d, tm);
+            lane_enter_instance<ANY, COUNT>(ts, L, __float_as_uint(v1.w), o, d, n_nodes);
+            if (L.cur == kEmptyRef) L.cur = lane_pop<ANY, COUNT, INST>(L, S, n_nodes, io, idx);
+            return;
+        }
         if (COUNT) n_tris++;
         float b0, b1, b2, t;
         if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
             L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
+            if constexpr (INST) { L.hit.inst = L.inst; L.inst_hit = true; }
             if (ANY) { L.cur = kEmptyRef; return; }
             L.t_max = t;
         }
         if (__float_as_uint(v2.w) & kLastInLeaf) break;
         ++pi;
     }
-    L.cur = lane_pop<ANY, COUNT>(L, S, n_nodes);
+    L.cur = lane_pop<ANY, COUNT, INST>(L, S, n_nodes, io, idx);
 }
 
 }  // namespace sg

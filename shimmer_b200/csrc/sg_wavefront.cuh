@@ -18,6 +18,7 @@ struct PathState {
     float4* ray_d;      // d.xyz
     float4* hit_b;      // b0 b1 b2 t
     int*    hit_prim;
+    int*    hit_inst;   // instance index of the hit or -1; allocated only for scenes with object instances
     float4* L;
     float4* beta;
     float4* lambda;
@@ -102,8 +103,14 @@ struct DevStats { unsigned long long closest, shadow, nodes, tris, nodes_closest
 #define SG_TRACE_THREADS 128
 #endif
 static constexpr int kTraceThreads = SG_TRACE_THREADS;
+// Resident CTAs per SM the traversal kernels are compiled for: 9 x 128 threads caps ptxas at 56 registers, which is
+// what the closest-hit kernel needs without spilling and what the shared-memory stack (20 levels) leaves room for;
+// the instanced variants carry more lane state and are given 8 (64 registers).
 #ifndef SG_TRACE_MIN_BLOCKS
-#define SG_TRACE_MIN_BLOCKS 1
+#define SG_TRACE_MIN_BLOCKS 9
+#endif
+#ifndef SG_TRACE_MIN_BLOCKS_INST
+#define SG_TRACE_MIN_BLOCKS_INST 8
 #endif
 
 // ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // Scheduling thresholds (lanes): run the triangle phase once this many lanes hold a leaf, and
 // the retire/refill phase once this many lanes wait for a ray; kInteriorBurst interior steps
 // are run back to back between votes.
-template <bool ANY, bool COUNT, class IO, class CursorT>
+template <bool ANY, bool COUNT, bool INST, class IO, class CursorT>
 SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* cursor, uint32_t* s_mem,
                           uint32_t& cnt_nodes, uint32_t& cnt_tris) {
     const int lane = threadIdx.x & 31;
@@ -168,7 +175,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
     S.s_ref = s_mem + threadIdx.x;
     S.s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x;
-    Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1;
+    Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     bool has_ray = false, dead = false, finished = false;
     CursorT idx = 0;
     for (;;) {
@@ -179,6 +186,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         const uint32_t m_wait = __ballot_sync(0xffffffffu, finished || (!has_ray && !dead));
         if ((m_int | m_leaf) == 0u || __popc(m_wait) >= ts.refill_threshold) {
             // ---- retire finished rays, claim new ones (warp-aggregated) ----
+            if constexpr (!INST) L.hit.inst = -1;
             if (__ballot_sync(0xffffffffu, finished)) io.retire(finished, idx, L.hit, lane);
             finished = false;
             const bool need = !has_ray && !dead;
@@ -194,6 +202,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
                         float3 o, d; float tmax;
                         io.load(idx, o, d, tmax);
                         lane_begin<ANY>(ts, L, o, d, tmax, cnt_nodes, COUNT);
+                        if constexpr (INST) { L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.inst_hit = false; }
                         if (L.cur == kEmptyRef) finished = true; else has_ray = true;
                     } else dead = true;
                 }
@@ -204,7 +213,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         if (__popc(m_leaf) >= ts.leaf_threshold || m_int == 0u) {
             // ---- triangle phase ----
             if (is_leaf) {
-                lane_step_leaf<ANY, COUNT>(ts, L, S, cnt_nodes, cnt_tris);
+                lane_step_leaf<ANY, COUNT, INST>(ts, L, S, cnt_nodes, cnt_tris, io, idx);
                 if (L.cur == kEmptyRef) { finished = true; has_ray = false; }
             }
             continue;
@@ -213,7 +222,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         if (is_int) {
 #pragma unroll 1
             for (int k = 0; k < ts.interior_burst; ++k) {
-                lane_step_interior<ANY, COUNT>(ts, L, S, cnt_nodes);
+                lane_step_interior<ANY, COUNT, INST>(ts, L, S, cnt_nodes, io, idx);
                 if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
                 if (L.cur & kLeafBit) break;
             }
@@ -233,6 +242,7 @@ struct ClosestIO {
         int kind = -1;
         if (fin) {
             st.hit_prim[path] = hit.prim;
+            if (st.hit_inst) st.hit_inst[path] = hit.inst;
             if (hit.prim >= 0) {
                 st.hit_b[path] = make_float4(hit.b0, hit.b1, hit.b2, hit.t);
                 kind = 1 + (int)((__float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)hit.prim).w) >> 28) & 7u);
@@ -264,18 +274,18 @@ struct ShadowIO {
     }
 };
 
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+template <bool ANY, bool COUNT, bool INST>
+__global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST : SG_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                          PathState st, Queues q, int depth, DevStats* stats) {
     extern __shared__ uint32_t s_mem[];
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t cnt_nodes = 0, cnt_tris = 0;
     if (ANY) {
         ShadowIO io{st, q.shadow, 0};
-        trace_persistent<true, COUNT>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, cnt_nodes, cnt_tris);
+        trace_persistent<true, COUNT, INST>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, cnt_nodes, cnt_tris);
     } else {
         ClosestIO io{sc, st, q, C, q.ray[depth & 1], 0};
-        trace_persistent<false, COUNT>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
+        trace_persistent<false, COUNT, INST>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
     }
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
@@ -356,6 +366,11 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
 
             SurfTex sx;
             Surf s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
+            float3 wo_si = wo;                                   // SurfaceInteraction::wo (what sample_ld reads, integrator.rs:905-917)
+            if (st.hit_inst != nullptr) {                        // TransformedPrimitive::intersect primitive.rs:155-169
+                const int inst = st.hit_inst[path];
+                if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst], rd, s, &sx, wo_si);
+            }
 
             // emission + MIS against light sampling, :798-813
             if (light_id >= 0) {
@@ -432,8 +447,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 if (bflags & (BX_DIFFUSE | BX_GLOSSY)) {
                     LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;
                     const bool refl = bflags & BX_REFLECTION, trans = bflags & BX_TRANSMISSION;
-                    if (refl && !trans) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, wo));
-                    else if (trans && !refl) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, -wo));
+                    if (refl && !trans) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, wo_si));
+                    else if (trans && !refl) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, -wo_si));
                     const float ul = rng.get_1d();
                     float2 u_light; u_light.x = rng.get_1d(); u_light.y = rng.get_1d();
                     if (sc.n_lights > 0) {
@@ -445,14 +460,14 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                         LightSample ls;
                         if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
                             bsdf.layer_seed = layer_seed(rng, 1);
-                            Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);
+                            Spec f = bsdf.f(wo_si, ls.wi) * absdot3(ls.wi, s.sn);
                             if (!spec_zero(f)) {
                                 const float p_l = p_choose * ls.pdf;
                                 Spec ld;
                                 if (lt.kind == SG_LIGHT_POINT) ld = ls.l * f / p_l;
                                 else {
                                     bsdf.layer_seed = layer_seed(rng, 2);
-                                    float p_bsdf = bsdf.pdf(wo, ls.wi);
+                                    float p_bsdf = bsdf.pdf(wo_si, ls.wi);
                                     float w_l = power_heuristic(p_l, p_bsdf);
                                     ld = w_l * ls.l * f / p_l;
                                 }
@@ -595,15 +610,15 @@ struct RaysIO {
         out[i] = h;
     }
 };
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS) k_trace_rays(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+template <bool ANY, bool COUNT, bool INST>
+__global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST : SG_TRACE_MIN_BLOCKS) k_trace_rays(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                               long long n, const float* __restrict__ o, const float* __restrict__ d,
                                                               const float* __restrict__ tmax, SgHit* __restrict__ out,
                                                               unsigned long long* cursor, DevStats* stats) {
     extern __shared__ uint32_t s_mem[];
     uint32_t cnt_nodes = 0, cnt_tris = 0;
     RaysIO<ANY> io{sc, o, d, tmax, out};
-    trace_persistent<ANY, COUNT>(ts, io, (unsigned long long)n, cursor, s_mem, cnt_nodes, cnt_tris);
+    trace_persistent<ANY, COUNT, INST>(ts, io, (unsigned long long)n, cursor, s_mem, cnt_nodes, cnt_tris);
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);
         atomicAdd(&stats->tris, (unsigned long long)cnt_tris);

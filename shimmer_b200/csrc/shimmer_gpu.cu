@@ -57,6 +57,7 @@ struct SgScene {
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
     bool kinds_present[4] = {false, false, false, false};
+    bool instanced = false;         // object instances: k_trace<.., INST = true> and the hit_inst path-state array
     bool tex_path = false;          // image textures or a non-zero constant displacement: k_shade<KIND, true>
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
@@ -82,7 +83,8 @@ int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
 #define WS(field) if ((rc = ws_alloc(w, &w.st.field, n)) != SG_OK) return rc
     WS(ray_o); WS(ray_d); WS(hit_b); WS(hit_prim); WS(L); WS(beta); WS(lambda); WS(lpdf); WS(rng_a); WS(rng_b);
     WS(pixel); WS(flags); WS(pb_eta); WS(ctx0); WS(ctx1); WS(ctx2); WS(sh_o); WS(sh_d); WS(sh_L);
-    if (s->d.n_textures > 0) { WS(aux0); WS(aux1); WS(aux2); }      // ray differentials only feed image-texture filtering
+    if (s->d.n_textures > 0) { WS(aux0); WS(aux1); WS(aux2); }
+    if (s->instanced) { WS(hit_inst); }      // ray differentials only feed image-texture filtering
 #undef WS
     if ((rc = ws_alloc(w, &w.q.ray[0], n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.ray[1], n)) != SG_OK) return rc;
@@ -91,6 +93,17 @@ int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
     if ((rc = ws_alloc(w, &w.q.counters, (size_t)(max_depth + 3) * C_STRIDE)) != SG_OK) return rc;
     w.capacity = capacity; w.max_depth = max_depth;
     return SG_OK;
+}
+
+typedef void (*TraceKernel)(const DScene, const TraceScene, PathState, Queues, int, DevStats*);
+TraceKernel trace_kernel(bool any, bool count, bool inst) {
+    if (any) return count ? (inst ? k_trace<true, true, true> : k_trace<true, true, false>) : (inst ? k_trace<true, false, true> : k_trace<true, false, false>);
+    return count ? (inst ? k_trace<false, true, true> : k_trace<false, true, false>) : (inst ? k_trace<false, false, true> : k_trace<false, false, false>);
+}
+typedef void (*TraceRaysKernel)(const DScene, const TraceScene, long long, const float*, const float*, const float*, SgHit*, unsigned long long*, DevStats*);
+TraceRaysKernel trace_rays_kernel(bool any, bool count, bool inst) {
+    if (any) return count ? (inst ? k_trace_rays<true, true, true> : k_trace_rays<true, true, false>) : (inst ? k_trace_rays<true, false, true> : k_trace_rays<true, false, false>);
+    return count ? (inst ? k_trace_rays<false, true, true> : k_trace_rays<false, true, false>) : (inst ? k_trace_rays<false, false, true> : k_trace_rays<false, false, false>);
 }
 
 int persistent_grid(const void* kernel, int threads, size_t smem) {
@@ -136,12 +149,29 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
     if (desc->n_primitives >= (1u << 31)) return fail(SG_ERR_UNSUPPORTED, "too many primitives");
     // validate references so device code never reads out of bounds
+    const uint32_t n_top_nodes = desc->n_top_nodes ? desc->n_top_nodes : desc->n_nodes;
+    const uint32_t n_top_prims = desc->n_top_primitives ? desc->n_top_primitives : desc->n_primitives;
+    if (n_top_nodes > desc->n_nodes || n_top_prims > desc->n_primitives) return fail(SG_ERR_INVALID_ARGUMENT, "top-level ranges exceed the node / primitive arrays");
+    if ((desc->n_objects && !desc->objects) || (desc->n_instances && !desc->instances)) return fail(SG_ERR_INVALID_ARGUMENT, "object / instance arrays missing");
     for (uint32_t i = 0; i < desc->n_primitives; ++i) {
         const SgPrimitive& p = desc->primitives[i];
+        if (p.mesh == SG_PRIM_INSTANCE) {
+            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "nested object instances are not supported (pbrt-v4 scene format)");
+            if (p.tri >= desc->n_instances) return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references an out-of-range instance");
+            continue;
+        }
         if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
             p.light >= (int32_t)desc->n_lights)
             return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references out-of-range mesh/triangle/material/light");
     }
+    for (uint32_t i = 0; i < desc->n_objects; ++i) {
+        const SgObject& o = desc->objects[i];
+        if ((uint64_t)o.first_node + o.n_nodes > desc->n_nodes || (uint64_t)o.first_prim + o.n_prims > desc->n_primitives || o.n_prims == 0 ||
+            o.first_prim < n_top_prims || (o.n_nodes && o.first_node < n_top_nodes))
+            return fail(SG_ERR_INVALID_ARGUMENT, "object " + std::to_string(i) + ": node / primitive range is malformed");
+    }
+    for (uint32_t i = 0; i < desc->n_instances; ++i)
+        if (desc->instances[i].object >= desc->n_objects) return fail(SG_ERR_INVALID_ARGUMENT, "instance " + std::to_string(i) + " references an out-of-range object");
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
         if (m.kind < 0 || m.kind > SG_MATERIAL_COATED_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
@@ -181,11 +211,17 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     }
     if (need_rgb2spec && (desc->rgb2spec_res < 2 || !desc->rgb2spec_scale || !desc->rgb2spec_data))
         return fail(SG_ERR_INVALID_ARGUMENT, "three-channel textures need the rgb2spec table of the scene colour space");
-    for (uint32_t i = 0; i < desc->n_nodes; ++i) {
-        const SgBvhNode& nd = desc->nodes[i];
-        if (nd.n_prims > 0 ? (nd.offset + nd.n_prims > desc->n_primitives) : (nd.offset >= desc->n_nodes || i + 1 >= desc->n_nodes))
-            return fail(SG_ERR_INVALID_ARGUMENT, "BVH node " + std::to_string(i) + " is malformed");
-    }
+    auto check_bvh = [&](uint32_t node_base, uint32_t nn, uint32_t np) -> bool {          // offsets are relative to the BVH's own ranges
+        for (uint32_t i = 0; i < nn; ++i) {
+            const SgBvhNode& nd = desc->nodes[node_base + i];
+            if (nd.n_prims > 0 ? ((uint64_t)nd.offset + nd.n_prims > np) : (nd.offset >= nn || nd.offset <= i || i + 1 >= nn)) return false;
+        }
+        return true;
+    };
+    if (!check_bvh(0, n_top_nodes, n_top_prims)) return fail(SG_ERR_INVALID_ARGUMENT, "top-level BVH is malformed");
+    for (uint32_t i = 0; i < desc->n_objects; ++i)
+        if (!check_bvh(desc->objects[i].first_node, desc->objects[i].n_nodes, desc->objects[i].n_prims))
+            return fail(SG_ERR_INVALID_ARGUMENT, "BVH of object " + std::to_string(i) + " is malformed");
     SgScene* s = new (std::nothrow) SgScene();
     if (!s) return fail(SG_ERR_OUT_OF_MEMORY, "host allocation failed");
     int rc = SG_OK;
@@ -195,6 +231,11 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     std::vector<float4> tv((size_t)desc->n_primitives * 3);
     for (uint32_t i = 0; i < desc->n_primitives; ++i) {
         const SgPrimitive& p = desc->primitives[i];
+        if (p.mesh == SG_PRIM_INSTANCE) {                   // TransformedPrimitive: no vertices; kind 7, instance id in word 1
+            const uint32_t w[3] = {kKindInstance << 28, p.tri, 0u};
+            for (int k = 0; k < 3; ++k) { float wf; std::memcpy(&wf, &w[k], 4); tv[3 * (size_t)i + k] = make_float4(0.0f, 0.0f, 0.0f, wf); }
+            continue;
+        }
         const SgMesh& m = desc->meshes[p.mesh];
         const uint32_t* ix = desc->indices + m.first_index + 3 * (size_t)p.tri;
         if (p.material >= (1u << 23)) { g_err = "more than 2^23 materials"; return bail(SG_ERR_UNSUPPORTED); }
@@ -207,44 +248,80 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         }
         s->kinds_present[desc->materials[p.material].kind] = true;
     }
-    // Node64 (sg_trace2.cuh): interior nodes with both children's bounds; leaves are folded into child refs.
+    // Node64 (sg_trace2.cuh): interior nodes with both children's bounds; leaves are folded into child refs.  One
+    // conversion per BvhAggregate (the top level and every object definition); refs index the shared node64 / tri_verts arrays.
     std::vector<float4> n64;
+    std::vector<DInstance> dinst(desc->n_instances);
     {
-        const uint32_t N = desc->n_nodes;
-        std::vector<uint32_t> idx64(N, 0), depth(N, 0);
-        uint32_t n_interior = 0, max_depth = N ? 1 : 0;
-        for (uint32_t i = 0; i < N; ++i) if (desc->nodes[i].n_prims == 0) idx64[i] = n_interior++;
-        if (N) depth[0] = 1;
-        n64.resize((size_t)n_interior * 4);
-        for (uint32_t i = 0; i < N; ++i) {
-            const SgBvhNode& nd = desc->nodes[i];
-            if (depth[i] > max_depth) max_depth = depth[i];
-            if (nd.n_prims > 0) {
-                uint32_t last = nd.offset + nd.n_prims - 1, wbits;
+        struct Root { uint32_t ref; uint32_t depth; };
+        bool too_deep = false;
+        auto convert = [&](uint32_t node_base, uint32_t N, uint32_t prim_base, uint32_t n_direct_prims) -> Root {
+            if (N == 0) {                                    // bare primitives without an aggregate: one leaf
+                if (n_direct_prims == 0) return Root{kEmptyRef, 0};
+                uint32_t last = prim_base + n_direct_prims - 1, wbits;
                 std::memcpy(&wbits, &tv[3 * (size_t)last + 2].w, 4); wbits |= kLastInLeaf; std::memcpy(&tv[3 * (size_t)last + 2].w, &wbits, 4);
-                continue;
+                return Root{kLeafBit | prim_base, 1};
             }
-            const uint32_t c[2] = {i + 1, nd.offset};
-            uint32_t ref[2];
-            for (int k = 0; k < 2; ++k) {
-                const SgBvhNode& ch = desc->nodes[c[k]];
-                depth[c[k]] = depth[i] + 1;
-                ref[k] = ch.n_prims > 0 ? (kLeafBit | ch.offset) : idx64[c[k]];
+            const SgBvhNode* nodes = desc->nodes + node_base;
+            std::vector<uint32_t> idx64(N, 0), depth(N, 0);
+            const uint32_t first64 = (uint32_t)(n64.size() / 4);
+            uint32_t n_interior = 0, max_depth = 1;
+            for (uint32_t i = 0; i < N; ++i) if (nodes[i].n_prims == 0) idx64[i] = first64 + n_interior++;
+            depth[0] = 1;
+            n64.resize(n64.size() + (size_t)n_interior * 4);
+            for (uint32_t i = 0; i < N; ++i) {
+                const SgBvhNode& nd = nodes[i];
+                if (depth[i] > max_depth) max_depth = depth[i];
+                if (nd.n_prims > 0) {
+                    uint32_t last = prim_base + nd.offset + nd.n_prims - 1, wbits;
+                    std::memcpy(&wbits, &tv[3 * (size_t)last + 2].w, 4); wbits |= kLastInLeaf; std::memcpy(&tv[3 * (size_t)last + 2].w, &wbits, 4);
+                    continue;
+                }
+                const uint32_t c[2] = {i + 1, nd.offset};
+                uint32_t ref[2];
+                for (int k = 0; k < 2; ++k) {
+                    const SgBvhNode& ch = nodes[c[k]];
+                    depth[c[k]] = depth[i] + 1;
+                    ref[k] = ch.n_prims > 0 ? (kLeafBit | (prim_base + ch.offset)) : idx64[c[k]];
+                }
+                const SgBvhNode& a = nodes[c[0]]; const SgBvhNode& b = nodes[c[1]];
+                float4* o = &n64[(size_t)idx64[i] * 4];
+                float r0, r1, mt; uint32_t meta = nd.axis;
+                std::memcpy(&r0, &ref[0], 4); std::memcpy(&r1, &ref[1], 4); std::memcpy(&mt, &meta, 4);
+                o[0] = make_float4(a.bmin[0], a.bmin[1], a.bmin[2], a.bmax[0]);
+                o[1] = make_float4(a.bmax[1], a.bmax[2], b.bmin[0], b.bmin[1]);
+                o[2] = make_float4(b.bmin[2], b.bmax[0], b.bmax[1], b.bmax[2]);
+                o[3] = make_float4(r0, r1, mt, 0.0f);
             }
-            const SgBvhNode& a = desc->nodes[c[0]]; const SgBvhNode& b = desc->nodes[c[1]];
-            float4* o = &n64[(size_t)idx64[i] * 4];
-            float r0, r1, mt; uint32_t meta = nd.axis;
-            std::memcpy(&r0, &ref[0], 4); std::memcpy(&r1, &ref[1], 4); std::memcpy(&mt, &meta, 4);
-            o[0] = make_float4(a.bmin[0], a.bmin[1], a.bmin[2], a.bmax[0]);
-            o[1] = make_float4(a.bmax[1], a.bmax[2], b.bmin[0], b.bmin[1]);
-            o[2] = make_float4(b.bmin[2], b.bmax[0], b.bmax[1], b.bmax[2]);
-            o[3] = make_float4(r0, r1, mt, 0.0f);
+            if (max_depth > 64) too_deep = true;
+            return Root{nodes[0].n_prims > 0 ? (kLeafBit | (prim_base + nodes[0].offset)) : idx64[0], max_depth};
+        };
+        if (desc->n_primitives >= (1u << 28)) { g_err = "too many primitives"; return bail(SG_ERR_UNSUPPORTED); }
+        const Root top = convert(0, n_top_nodes, 0, 0);
+        uint32_t obj_depth = 0;
+        std::vector<Root> oroot(desc->n_objects);
+        for (uint32_t i = 0; i < desc->n_objects; ++i) {
+            const SgObject& o = desc->objects[i];
+            oroot[i] = convert(o.first_node, o.n_nodes, o.first_prim, o.n_prims);
+            obj_depth = std::max(obj_depth, oroot[i].depth);
         }
-        if (max_depth > 64) { g_err = "BVH deeper than 64 levels: the reference's fixed traversal stack (aggregate.rs:90) would overflow"; return bail(SG_ERR_UNSUPPORTED); }
-        if (desc->n_primitives >= (1u << 30)) { g_err = "too many primitives"; return bail(SG_ERR_UNSUPPORTED); }
+        if (too_deep) { g_err = "BVH deeper than 64 levels: the reference's fixed traversal stack (aggregate.rs:90) would overflow"; return bail(SG_ERR_UNSUPPORTED); }
+        for (uint32_t i = 0; i < desc->n_instances; ++i) {
+            const SgInstance& I = desc->instances[i]; const SgObject& o = desc->objects[I.object];
+            DInstance& D = dinst[i];
+            std::memcpy(D.m, I.render_from_primitive, 12 * sizeof(float)); std::memcpy(D.mi, I.primitive_from_render, 12 * sizeof(float));
+            const float* r3 = I.render_from_primitive + 12;
+            if (r3[0] != 0.0f || r3[1] != 0.0f || r3[2] != 0.0f || r3[3] != 1.0f) { g_err = "instance transforms must be affine"; return bail(SG_ERR_UNSUPPORTED); }
+            D.root_ref = oroot[I.object].ref; D.root_has_bounds = o.n_nodes > 0 ? 1u : 0u;
+            for (int k = 0; k < 3; ++k) { D.bmin[k] = o.n_nodes ? desc->nodes[o.first_node].bmin[k] : 0.0f; D.bmax[k] = o.n_nodes ? desc->nodes[o.first_node].bmax[k] : 0.0f; }
+        }
+        const uint32_t N = n_top_nodes;
+        // stack levels: the top-level tree, the deepest object tree, and one resume entry per instance entered from a multi-primitive leaf
+        const uint32_t max_depth = top.depth + (desc->n_instances ? obj_depth + 1 : 0);
         s->ts.stack_depth = max_depth < 1 ? 1 : (int)max_depth;
-        s->ts.root_ref = N == 0 ? kEmptyRef : (desc->nodes[0].n_prims > 0 ? (kLeafBit | desc->nodes[0].offset) : 0u);
+        s->ts.root_ref = N == 0 ? kEmptyRef : top.ref;
         for (int k = 0; k < 3 && N; ++k) { s->ts.root_bmin[k] = desc->nodes[0].bmin[k]; s->ts.root_bmax[k] = desc->nodes[0].bmax[k]; }
+        s->ts.scene_flags = desc->scene_flags;
         auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
         s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 8);
         s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 6);
@@ -256,6 +333,12 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (s->ts.stack_depth - s->ts.smem_levels > kSpillLevels) s->ts.smem_levels = s->ts.stack_depth - kSpillLevels;
         s->smem_closest = (size_t)s->ts.smem_levels * kTraceThreads * 8;
         s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
+    }
+    s->instanced = desc->n_instances > 0;
+    {
+        DInstance* d_inst = nullptr;
+        if ((rc = upload(dinst.data(), dinst.size(), &d_inst, s->owned)) != SG_OK) return bail(rc);
+        s->ts.instances = d_inst; d.instances = d_inst; d.n_instances = desc->n_instances; d.scene_flags = desc->scene_flags;
     }
     float4* d_nodes = nullptr; float4* d_tv = nullptr; float4* d_n64 = nullptr;
     if ((rc = upload(n64.data(), n64.size(), &d_n64, s->owned)) != SG_OK) return bail(rc);
@@ -338,6 +421,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     if (rp->max_depth < 0 || rp->max_depth > 254) return fail(SG_ERR_INVALID_ARGUMENT, "max_depth out of range");
     if (rp->option_flags & SG_OPT_FORCE_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "force_diffuse is not on the GPU path");
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
+    const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
     const uint64_t npix = s->n_pixels();
     const uint64_t total = npix * (uint64_t)(rp->sample_end - rp->sample_begin);
     uint64_t cap64 = rp->max_paths_in_flight > 0 ? (uint64_t)rp->max_paths_in_flight : (1ull << 26);   // 64 Mi paths = 18.5 GB of 180 GB
@@ -356,14 +440,12 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.n_samples = rp->sample_end - rp->sample_begin;
     { const char* v = std::getenv("SG_PATH_ORDER"); k.path_order = v ? std::atoi(v) : 1; }
     if (k.n_samples == 0) k.n_samples = 1;
-    const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
     const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
     const int n_depths = rp->max_depth + 1;
     const size_t smc = s->smem_closest, sms = s->smem_shadow;
-    const int grid_closest[2] = {persistent_grid((const void*)k_trace<false, false>, kTraceThreads, smc),
-                                 persistent_grid((const void*)k_trace<false, true>, kTraceThreads, smc)};
-    const int grid_shadow[2] = {persistent_grid((const void*)k_trace<true, false>, kTraceThreads, sms),
-                                persistent_grid((const void*)k_trace<true, true>, kTraceThreads, sms)};
+    const TraceKernel kern_closest = trace_kernel(false, count, s->instanced), kern_shadow = trace_kernel(true, count, s->instanced);
+    const int grid_closest = persistent_grid((const void*)kern_closest, kTraceThreads, smc);
+    const int grid_shadow = persistent_grid((const void*)kern_shadow, kTraceThreads, sms);
     const int shade_grid = g_num_sms * 8;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     cudaEvent_t ev0, ev1;
@@ -377,8 +459,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
         for (int depth = 0; depth < n_depths; ++depth) {
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
-            if (count) k_trace<false, true><<<grid_closest[1], kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
-            else k_trace<false, false><<<grid_closest[0], kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
+            kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
@@ -390,8 +471,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
 #undef SHADE
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
-                if (count) k_trace<true, true><<<grid_shadow[1], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
-                else k_trace<true, false><<<grid_shadow[0], kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
+                kern_shadow<<<grid_shadow, kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
                 ++launches; ++shadow_launches;
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
             }
@@ -481,12 +561,10 @@ int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, con
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, stream));
     if (n > 0) {
-#define LAUNCH(A, C) { const size_t sm = (A) ? s->smem_shadow : s->smem_closest; \
-        int g = persistent_grid((const void*)k_trace_rays<A, C>, kTraceThreads, sm); \
-        k_trace_rays<A, C><<<g, kTraceThreads, sm, stream>>>(s->d, s->ts, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats); }
-        if (any_hit) { if (count) LAUNCH(true, true) else LAUNCH(true, false) }
-        else { if (count) LAUNCH(false, true) else LAUNCH(false, false) }
-#undef LAUNCH
+        const size_t sm = any_hit ? s->smem_shadow : s->smem_closest;
+        const TraceRaysKernel kern = trace_rays_kernel(any_hit != 0, count, s->instanced);
+        const int g = persistent_grid((const void*)kern, kTraceThreads, sm);
+        kern<<<g, kTraceThreads, sm, stream>>>(s->d, s->ts, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats);
     }
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));

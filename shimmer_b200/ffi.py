@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 3
+SG_ABI_VERSION = 4
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -33,6 +33,19 @@ class SgBvhNode(C.Structure):
 
 class SgPrimitive(C.Structure):
     _fields_ = [("mesh", C.c_uint32), ("tri", C.c_uint32), ("material", C.c_uint32), ("light", C.c_int32)]
+
+
+SG_PRIM_INSTANCE = 0xffffffff
+SG_SCENE_FIX_INSTANCING = 1
+
+
+class SgObject(C.Structure):
+    _fields_ = [("first_node", C.c_uint32), ("n_nodes", C.c_uint32), ("first_prim", C.c_uint32), ("n_prims", C.c_uint32)]
+
+
+class SgInstance(C.Structure):
+    _fields_ = [("render_from_primitive", C.c_float * 16), ("primitive_from_render", C.c_float * 16), ("object", C.c_uint32),
+                ("pad", C.c_uint32 * 3)]
 
 
 class SgMesh(C.Structure):
@@ -93,6 +106,10 @@ class SgSceneDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32),
                 ("n_nodes", C.c_uint32), ("nodes", C.POINTER(SgBvhNode)),
                 ("n_primitives", C.c_uint32), ("primitives", C.POINTER(SgPrimitive)),
+                ("n_top_nodes", C.c_uint32), ("n_top_primitives", C.c_uint32),
+                ("n_objects", C.c_uint32), ("objects", C.POINTER(SgObject)),
+                ("n_instances", C.c_uint32), ("instances", C.POINTER(SgInstance)),
+                ("scene_flags", C.c_uint32),
                 ("n_meshes", C.c_uint32), ("meshes", C.POINTER(SgMesh)),
                 ("n_indices", C.c_uint32), ("indices", C.POINTER(C.c_uint32)),
                 ("n_vertices", C.c_uint32), ("p", C.POINTER(C.c_float)),

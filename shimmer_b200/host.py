@@ -235,6 +235,9 @@ class SceneBuilder:
         self.meshes = []         # dicts
         self.extra_lights = []   # non-area lights in add order (scene.rs add_light)
         self.textures = []       # dicts: levels (list of HxWxC f32 arrays) + SgTexture parameters
+        self.n_objects = 0       # object definitions (ObjectBegin/End); meshes carry an `object` id or None
+        self.instances = []      # (object id, render_from_instance Transform)
+        self.fix_instancing = False
         self.camera = None
         self.film = None
         self.world_from_camera = None
@@ -395,8 +398,18 @@ class SceneBuilder:
         cam.min_dir_differential_x[:] = best[2].tolist(); cam.min_dir_differential_y[:] = best[3].tolist()
 
     # -- geometry ------------------------------------------------------------------------------
+    def begin_object(self):
+        """ObjectBegin: returns an object-definition id for add_mesh(object=...) / add_instance."""
+        self.n_objects += 1
+        return self.n_objects - 1
+
+    def add_instance(self, obj, world_from_instance=None):
+        """ObjectInstance: render_from_instance = render_from_object * world_from_render (scene.rs:2002)."""
+        ctm = world_from_instance if world_from_instance is not None else Transform.identity()
+        self.instances.append((obj, self.render_from_world * ctm * self.render_from_world.inverse()))
+
     def add_mesh(self, p, indices, material, n=None, uv=None, area_light=None, reverse_orientation=False,
-                 object_from_world=None):
+                 object_from_world=None, object=None):
         """Shape "trianglemesh" (triangle.rs:56-127 + mesh.rs:22-94).  `area_light` =
         dict(L=spectrum tuple, scale=float, two_sided=bool) -> one DiffuseAreaLight per triangle
         (scene.rs:609-622)."""
@@ -414,7 +427,9 @@ class SceneBuilder:
         if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
         self.meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 3), n=n,
                                 uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2),
-                                flags=flags, material=material, area_light=area_light))
+                                flags=flags, material=material, area_light=area_light, object=object))
+        if object is not None and area_light is not None:
+            raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
     def add_point_light(self, pos, I, scale=1.0):
@@ -505,19 +520,73 @@ class SceneBuilder:
             prim_in[t0:t0 + t, 0] = mi; prim_in[t0:t0 + t, 1] = np.arange(t); prim_in[t0:t0 + t, 2] = m["material"]
             prim_in[t0:t0 + t, 3] = (mesh_light_base[mi] + np.arange(t)) if mi in mesh_light_base else -1
             v0 += k; t0 += t
-        # BVH over Triangle::bounds in input order (aggregate.rs:207-290)
+        # Triangle::bounds per triangle (input order)
         bounds = np.empty((nt, 6), np.float32)
         host.sh_triangle_bounds(nt, gidx.ctypes.data, A["p"].ctypes.data, bounds.ctypes.data)
-        nodes = np.zeros(max(2 * nt - 1, 1), dtype=np.dtype(ffi.SgBvhNode))
-        order = np.empty(nt, np.uint32)
-        n_nodes = host.sh_bvh_build(nt, bounds.ctypes.data, nodes.ctypes.data, order.ctypes.data)
-        if n_nodes <= 0:
-            raise ffi.ShimmerGpuError("sh_bvh_build failed")
-        A["nodes"] = nodes[:n_nodes].copy(); A["order"] = order; A["prim_bounds"] = bounds
-        po = prim_in[order]
-        prims = np.zeros(nt, dtype=np.dtype(ffi.SgPrimitive))
+        tri_obj = np.full(nt, -1, np.int64)
+        t0 = 0
+        for m in self.meshes:
+            t = len(m["idx"])
+            if m["object"] is not None: tri_obj[t0:t0 + t] = m["object"]
+            t0 += t
+
+        def build_bvh(b):            # BvhAggregate::new (aggregate.rs:207-290) -> (nodes, leaf order)
+            k = len(b)
+            nd = np.zeros(max(2 * k - 1, 1), dtype=np.dtype(ffi.SgBvhNode)); od = np.empty(k, np.uint32)
+            bc = np.ascontiguousarray(b, np.float32)
+            nn = host.sh_bvh_build(k, bc.ctypes.data, nd.ctypes.data, od.ctypes.data)
+            if nn <= 0:
+                raise ffi.ShimmerGpuError("sh_bvh_build failed")
+            return nd[:nn].copy(), od
+        # object definitions: one BvhAggregate each when they hold more than one primitive (scene.rs:818-830)
+        obj_rows = (ffi.SgObject * max(self.n_objects, 1))()
+        obj_nodes, obj_prims, obj_root_bounds = [], [], []
+        for o in range(self.n_objects):
+            sel = np.nonzero(tri_obj == o)[0]
+            if len(sel) == 0:
+                raise ValueError("empty object definition")
+            if len(sel) > 1:
+                nd, od = build_bvh(bounds[sel])
+                obj_nodes.append(nd); obj_prims.append(prim_in[sel][od])
+                obj_root_bounds.append(np.concatenate([nd[0]["bmin"], nd[0]["bmax"]]))
+            else:
+                obj_nodes.append(np.zeros(0, dtype=np.dtype(ffi.SgBvhNode))); obj_prims.append(prim_in[sel])
+                obj_root_bounds.append(bounds[sel[0]])
+        # top level: shapes first, then one TransformedPrimitive per instance (scene.rs:806,849-866)
+        top_sel = np.nonzero(tri_obj < 0)[0]
+        inst_rows = (ffi.SgInstance * max(len(self.instances), 1))()
+        inst_bounds = np.empty((len(self.instances), 6), np.float32)
+        for ii, (o, xf) in enumerate(self.instances):
+            r = inst_rows[ii]
+            r.render_from_primitive[:] = xf.m32().ravel().tolist(); r.primitive_from_render[:] = xf.m_inv.astype(np.float32).ravel().tolist()
+            r.object = o
+            lo, hi = obj_root_bounds[o][:3], obj_root_bounds[o][3:]
+            corners = np.array([[(hi if (c >> a) & 1 else lo)[a] for a in range(3)] for c in range(8)], np.float32)   # Transform::apply(Bounds3f) transform.rs:557-570
+            pc = xf.apply_points_f32(corners)
+            inst_bounds[ii, :3] = pc.min(axis=0); inst_bounds[ii, 3:] = pc.max(axis=0)
+        top_bounds = np.concatenate([bounds[top_sel], inst_bounds]) if len(self.instances) else bounds[top_sel]
+        top_prim_in = prim_in[top_sel]
+        if len(self.instances):
+            ip = np.zeros((len(self.instances), 4), np.int64)
+            ip[:, 0] = ffi.SG_PRIM_INSTANCE; ip[:, 1] = np.arange(len(self.instances)); ip[:, 3] = -1
+            top_prim_in = np.concatenate([top_prim_in, ip])
+        nodes, order = build_bvh(top_bounds)
+        n_top_nodes, n_top_prims = len(nodes), len(top_prim_in)
+        all_nodes, all_prims = [nodes], [top_prim_in[order]]
+        node_off, prim_off = n_top_nodes, n_top_prims
+        for o in range(self.n_objects):
+            obj_rows[o].first_node, obj_rows[o].n_nodes = node_off, len(obj_nodes[o])
+            obj_rows[o].first_prim, obj_rows[o].n_prims = prim_off, len(obj_prims[o])
+            all_nodes.append(obj_nodes[o]); all_prims.append(obj_prims[o])
+            node_off += len(obj_nodes[o]); prim_off += len(obj_prims[o])
+        A["nodes"] = np.concatenate(all_nodes); A["order"] = order; A["prim_bounds"] = top_bounds
+        n_nodes = len(A["nodes"])
+        po = np.concatenate(all_prims)
+        nprim = len(po)
+        prims = np.zeros(nprim, dtype=np.dtype(ffi.SgPrimitive))
         prims["mesh"], prims["tri"], prims["material"], prims["light"] = po[:, 0], po[:, 1], po[:, 2], po[:, 3]
         A["prims"] = prims
+        A["objects"] = obj_rows; A["instances"] = inst_rows
         # scene bounds -> infinite-light preprocess (light.rs:797-802, bounding_box.rs:460-468)
         root = A["nodes"][0]
         bmin, bmax = np.array(root["bmin"], np.float32), np.array(root["bmax"], np.float32)
@@ -562,7 +631,11 @@ class SceneBuilder:
         d = out.desc
         d.abi_version = ffi.SG_ABI_VERSION
         d.n_nodes = n_nodes; d.nodes = _as_ptr(A["nodes"], ffi.SgBvhNode)
-        d.n_primitives = nt; d.primitives = _as_ptr(A["prims"], ffi.SgPrimitive)
+        d.n_primitives = nprim; d.primitives = _as_ptr(A["prims"], ffi.SgPrimitive)
+        d.n_top_nodes, d.n_top_primitives = n_top_nodes, n_top_prims
+        d.n_objects = self.n_objects; d.objects = A["objects"]
+        d.n_instances = len(self.instances); d.instances = A["instances"]
+        d.scene_flags = ffi.SG_SCENE_FIX_INSTANCING if self.fix_instancing else 0
         d.n_meshes = len(self.meshes); d.meshes = A["meshes"]
         d.n_indices = 3 * nt; d.indices = _as_ptr(A["idx"], C.c_uint32)
         d.n_vertices = nv; d.p = _as_ptr(A["p"], C.c_float)
@@ -583,6 +656,7 @@ class SceneBuilder:
         d.camera = self.camera
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
         d.film = self.film
-        out.meta = dict(n_triangles=nt, n_nodes=int(n_nodes), n_lights=len(lights),
+        inst_tris = sum(int(obj_rows[o].n_prims) for o, _ in self.instances)
+        out.meta = dict(n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights),
                         resolution=tuple(self.film.full_resolution), window=tuple(self.film.pixel_bounds))
         return out

@@ -203,11 +203,63 @@ def uv_sphere(n_theta, n_phi, center, radius):
 
 
 TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
+INSTANCED_KINDS = ("inst", "instrot", "instfix", "insttex")
+
+
+def instanced_tiny_scene(kind="inst", resolution=(32, 32), flatten=False):
+    """Object instancing (primitive.rs:136-176): one object definition (a small sphere + a single-triangle object) placed
+    several times.  `inst`: translations only (where the reference's closest-hit path is right and only its shadow-ray
+    quirk shows); `instrot`: rotation + non-uniform scale (every quirk of transform.rs:573-609 shows); `instfix`: the
+    same with SG_SCENE_FIX_INSTANCING; `insttex`: textured, normal-interpolated instances.  flatten=True bakes the
+    instances into ordinary meshes (what `instfix` must reproduce)."""
+    b = SceneBuilder()
+    b.fix_instancing = kind == "instfix"
+    b.set_camera(pos=(0.0, 1.4, -4.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
+    white = b.diffuse(_white())
+    if kind == "insttex":
+        mat = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="trilinear", su=2.0, sv=2.0))
+        copper = b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0)
+    else:
+        mat = b.diffuse(_green())
+        copper = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.15)
+    P, I, Nn, UV = uv_sphere(8, 12, center=(0.0, 0.0, 0.0), radius=0.4)
+    TP = np.array([[-0.3, -0.2, 0.0], [0.3, -0.2, 0.0], [0.0, 0.45, 0.1]], np.float32); TI = np.array([[0, 1, 2]], np.uint32)
+    if kind in ("instrot", "instfix"):
+        xfs = [Transform.translate((-1.2, 0.5, 0.3)) * Transform.rotate(35.0, (0, 1, 0.3)) * Transform.scale(1.0, 1.4, 0.8),
+               Transform.translate((0.0, 0.6, 0.0)) * Transform.scale(1.3, 1.3, 1.3),
+               Transform.translate((1.2, 0.45, -0.2)) * Transform.rotate(-50.0, (1, 0.2, 0))]
+        txf = [Transform.translate((0.6, 1.3, 0.4)) * Transform.rotate(20.0, (0, 0, 1))]
+    else:
+        xfs = [Transform.translate((-1.2, 0.5, 0.3)), Transform.translate((0.0, 0.6, 0.0)), Transform.translate((1.2, 0.45, -0.2)),
+               Transform.translate((0.5, 1.5, 0.8))]
+        txf = [Transform.translate((-0.6, 1.3, 0.4)), Transform.translate((0.7, 1.2, -0.5))]
+    use_n = kind == "insttex"
+    if flatten:
+        for xf in xfs:
+            b.add_mesh(P, I, mat, n=Nn if use_n else None, uv=UV, object_from_world=xf)
+        for xf in txf:
+            b.add_mesh(TP, TI, copper, object_from_world=xf)
+    else:
+        sphere_obj = b.begin_object()
+        b.add_mesh(P, I, mat, n=Nn if use_n else None, uv=UV, object=sphere_obj)
+        tri_obj = b.begin_object()                                    # a one-primitive definition: no aggregate (scene.rs:821-832)
+        b.add_mesh(TP, TI, copper, object=tri_obj)
+        for xf in xfs:
+            b.add_instance(sphere_obj, xf)
+        for xf in txf:
+            b.add_instance(tri_obj, xf)
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, white, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    lp, li = _quad((-0.6, 2.8, -0.6), (0.6, 2.8, -0.6), (0.6, 2.8, 0.6), (-0.6, 2.8, 0.6))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b
 
 
 def tiny_scene(kind="diffuse", resolution=(32, 32)):
     """A few dozen triangles exercising one material each; used by the fast parity tests.  The `tex*` kinds add image
     textures (RGB + one-channel, every filter / wrap mode), bump mapping and specular ray-differential propagation."""
+    if kind in INSTANCED_KINDS:
+        return instanced_tiny_scene(kind, resolution)
     b = SceneBuilder()
     b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
     white = b.diffuse(_white())

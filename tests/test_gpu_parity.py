@@ -109,10 +109,12 @@ def test_raycast_golden_fixture(cornell_gpu):
     assert st.nodes_visited == int(g["nodes"]) and st.tris_tested == int(g["tris"])
 
 
-@pytest.mark.parametrize("name", ["cornell", "tiny", "mesh"])
+@pytest.mark.parametrize("name", ["cornell", "tiny", "mesh", "inst", "instrot", "instfix"])
 def test_raycast_parity_closest_and_any(name, cornell64):
     sc = {"cornell": lambda: cornell64, "tiny": lambda: scenes.tiny_scene("glass").build(),
-          "mesh": lambda: scenes.mesh_scene(n_theta=120, n_phi=120, resolution=(32, 32)).build()}[name]()
+          "mesh": lambda: scenes.mesh_scene(n_theta=120, n_phi=120, resolution=(32, 32)).build(),
+          "inst": lambda: scenes.tiny_scene("inst").build(), "instrot": lambda: scenes.tiny_scene("instrot").build(),
+          "instfix": lambda: scenes.tiny_scene("instfix").build()}[name]()
     integ = create_integrator("wavefront", {}, sc)
     n = 1 << 17
     o, d = _ray_set(sc, n, seed=1)
@@ -168,7 +170,8 @@ def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
     assert rmse < 0.01
 
 
-@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"] + list(scenes.TEXTURED_KINDS))
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"] + list(scenes.TEXTURED_KINDS)
+                         + list(scenes.INSTANCED_KINDS))
 def test_tiny_scene_films(kind):
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
     integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 4, "seed": 5})
