@@ -202,6 +202,69 @@ def uv_sphere(n_theta, n_phi, center, radius):
     return P.astype(np.float32), np.asarray(idx, np.uint32), N.astype(np.float32), UV.astype(np.float32)
 
 
+def uv_sphere_fast(n_theta, n_phi, center, radius, amp=0.0, freq=6.0):
+    """uv_sphere() with vectorised index generation and an optional closed-form radial displacement (large meshes)."""
+    th = np.linspace(0.0, math.pi, n_theta + 1)
+    ph = np.linspace(0.0, 2.0 * math.pi, n_phi + 1)
+    T, Pp = np.meshgrid(th, ph, indexing="ij")
+    N = np.stack([np.sin(T) * np.cos(Pp), np.cos(T), np.sin(T) * np.sin(Pp)], axis=-1).reshape(-1, 3)
+    r = radius * (1.0 + amp * np.sin(freq * T) * np.cos(freq * Pp)).reshape(-1, 1)
+    P = N * r + np.asarray(center, dtype=np.float64)
+    UV = np.stack([Pp / (2.0 * math.pi), 1.0 - T / math.pi], axis=-1).reshape(-1, 2)
+    i, j = np.meshgrid(np.arange(n_theta), np.arange(n_phi), indexing="ij")
+    a = (i * (n_phi + 1) + j).ravel(); b = a + 1; c = a + n_phi + 1; d = c + 1
+    up = np.stack([a, b, d], axis=1)[(i > 0).ravel()]
+    lo = np.stack([a, d, c], axis=1)[(i < n_theta - 1).ravel()]
+    return P.astype(np.float32), np.concatenate([up, lo]).astype(np.uint32), N.astype(np.float32), UV.astype(np.float32)
+
+
+def instanced_scene(n_theta=224, n_phi=224, grid=10, resolution=(1920, 1080), crop=None, lights=(16, 32), fix_instancing=True,
+                    tex_size=512):
+    """C4: one ~100 k-triangle uv-mapped object definition placed grid x grid (= 100) times with rotations and
+    non-uniform scales (10 M instanced triangles), image textures (EWA on the instances, bilinear on the ground, a
+    one-channel bump map on every other row) and 2 x lights[0] x lights[1] (= 1024) emissive triangles sampled through
+    the uniform light sampler + MIS (BASELINE.json configs[3]).  Instance semantics: SG_SCENE_FIX_INSTANCING by
+    default -- the reference's literal TransformedPrimitive (forward transform on shadow rays, inverse on normals,
+    primitive.rs:172-175, transform.rs:573-597) is available with fix_instancing=False and is parity-tested on the
+    tiny instanced scenes."""
+    b = SceneBuilder()
+    b.fix_instancing = fix_instancing
+    half = 2.0 * grid
+    b.set_camera(pos=(0.0, 0.55 * half, -1.25 * half), look=(0.0, 0.0, -0.1 * half), up=(0, 1, 0), fov=42.0, resolution=resolution, crop=crop)
+    rgb_img, mono_img = procedural_image(tex_size, 3), procedural_image(tex_size // 2, 1)
+    ground = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(2 * tex_size, 3), filter="bilinear", su=8.0, sv=8.0))
+    skin = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="ewa", su=4.0, sv=2.0, max_anisotropy=8.0))
+    bumpy = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="trilinear", su=2.0, sv=2.0),
+                      displacement_tex=b.image_texture(mono_img, filter="bilinear", su=12.0, sv=6.0, scale=0.02))
+    white = b.diffuse(_white())
+    P, I, Nn, UV = uv_sphere_fast(n_theta, n_phi, center=(0.0, 0.0, 0.0), radius=1.0, amp=0.05)
+    objs = []
+    for mat in (skin, bumpy):
+        o = b.begin_object()
+        b.add_mesh(P, I, mat, n=Nn, uv=UV, object=o)
+        objs.append(o)
+    for gy in range(grid):
+        for gx in range(grid):
+            k = gy * grid + gx
+            x = (gx - 0.5 * (grid - 1)) * 4.0; z = (gy - 0.5 * (grid - 1)) * 4.0
+            sx_, sy_, sz_ = 1.0 + 0.25 * math.sin(1.7 * k), 1.1 + 0.3 * math.cos(0.9 * k), 1.0 + 0.2 * math.sin(2.3 * k + 1.0)
+            xf = (Transform.translate((x, 1.25 * sy_, z)) * Transform.rotate(37.0 * k, (0.3 * math.sin(k), 1.0, 0.2 * math.cos(k))) *
+                  Transform.scale(sx_, sy_, sz_))
+            b.add_instance(objs[gy & 1], xf)
+    gp, gi = _quad((-half - 4, 0.0, -half - 4), (-half - 4, 0.0, half + 4), (half + 4, 0.0, half + 4), (half + 4, 0.0, -half - 4))
+    b.add_mesh(gp, gi, ground, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    # many emitters: a ceiling of small downward-facing quads, one DiffuseAreaLight per triangle (scene.rs:609-622)
+    ny, nx = lights
+    LP, LI = [], []
+    for iy in range(ny):
+        for ix in range(nx):
+            cx = (ix + 0.5) / nx * 2.0 * half - half; cz = (iy + 0.5) / ny * 2.0 * half - half; h = 0.22; y = 9.0
+            p, idx = _quad((cx - h, y, cz - h), (cx + h, y, cz - h), (cx + h, y, cz + h), (cx - h, y, cz + h))
+            LI.append(idx + 4 * len(LP)); LP.append(p)
+    b.add_mesh(np.concatenate(LP), np.concatenate(LI), white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=160.0, two_sided=False))
+    return b
+
+
 TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
 INSTANCED_KINDS = ("inst", "instrot", "instfix", "insttex")
 
@@ -320,6 +383,9 @@ CONFIGS = {
                    desc="C2 procedural ~1M-triangle displaced sphere, diffuse + Cu conductor, 1024x1024, 64 spp"),
     "glass": dict(builder=glass_scene, resolution=(1024, 1024), spp=256, max_depth=5,
                   desc="C3 glass dispersion (tabulated BK7 eta), 1024x1024, 256 spp"),
+    "instanced": dict(builder=instanced_scene, resolution=(1920, 1080), spp=128, max_depth=5,
+                      desc="C4 100 instances x ~100k-triangle uv-mapped mesh (10M instanced triangles), EWA/bilinear/bump image textures, "
+                           "1024 emissive triangles, 1920x1080, 128 spp"),
     "composite": dict(builder=composite_scene, resolution=(3840, 2160), spp=1024, max_depth=5,
                       desc="C5 Cornell + 1M-triangle mesh composite, 3840x2160, 1024 spp"),
 }
