@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mesh1m", choices=["mesh1m", "cornell", "glass"])
+    ap.add_argument("--workload", default="mesh1m", choices=["mesh1m", "cornell", "glass", "instanced", "composite"])
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (default: the config's)")
     ap.add_argument("--res", type=int, default=0, help="override square resolution (debug only)")
     ap.add_argument("--paths-in-flight", type=int, default=0)

@@ -368,6 +368,16 @@ int sg_texture_eval(SgScene* scene, int tex, int as_float, int64_t n, const floa
  * output_rgb_from_sensor_rgb; out: 3 floats per pixel. */
 int sg_film_develop(SgScene* scene, const SgFilmPixel* film, int64_t n_pixels, float* out_rgb);
 
+/* Replaces `RgbFilm::get_image` (film.rs:647-707): get_pixel_rgb per pixel, the fp16 clamp exactly as written there
+ * (when any channel exceeds 65504: r and b are clamped, a too-large g clamps r AGAIN and stays -- film.rs:683-685),
+ * then the pixel store of `Image::set_channel` (image.rs:648-661: NaN -> 0; PixelFormat::Half rounds through
+ * `half::f16::from_f32`, IEEE round-to-nearest-even) and the read-back `Image::write_pfm` does (image.rs:1352-1358:
+ * f16 -> f32).  SG_IMAGE_FP16 = `savefp16` (film.rs:491, default true); SG_IMAGE_BOTTOM_UP emits rows in PFM raster
+ * order (bottom row first, image.rs:1350) so the buffer can be written straight after the "PF\nW H\n-1\n" header.
+ * film / out_rgb: width*height pixels, row-major; out: 3 floats per pixel. */
+enum SgImageFlags { SG_IMAGE_FP16 = 1, SG_IMAGE_BOTTOM_UP = 2 };
+int sg_film_get_image(SgScene* scene, const SgFilmPixel* film, int32_t width, int32_t height, uint32_t flags, float* out_rgb);
+
 #ifdef __cplusplus
 }
 #endif

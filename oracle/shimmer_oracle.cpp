@@ -9,6 +9,7 @@
 // that has any (tests/test_oracle_kat.py lists them with file:line); the reference binary
 // itself cannot be built in this image, and rand::SmallRng / num-complex are
 // restated from their published algorithms => those two are "parity unpinned".
+#include <cstring>
 #include "orc_shading.h"
 #include <atomic>
 #include <thread>
@@ -352,6 +353,71 @@ void orc_film_develop(const SgSceneDesc* desc, const SgFilmPixel* film, int64_t 
         Float rgb[3] = {(Float)film[i].rgb_sum[0], (Float)film[i].rgb_sum[1], (Float)film[i].rgb_sum[2]};
         if (film[i].weight_sum != 0.0) for (int c = 0; c < 3; ++c) rgb[c] /= (Float)film[i].weight_sum;
         for (int r = 0; r < 3; ++r) out_rgb[3 * i + r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+    }
+}
+
+// half 2.2.1 `f16::from_f32` (software path; Cargo.lock pins half 2.2.1): IEEE 754 binary32 -> binary16, round to nearest
+// even, overflow -> inf, NaN keeps a quiet payload; restated from the published algorithm (third-party crate, not in
+// /root/reference) and pinned against numpy's float16 conversion in tests/test_oracle_kat.py.
+static uint16_t f16_bits_from_f32(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u, man = x & 0x007fffffu;
+    const int32_t exp = (int32_t)((x >> 23) & 0xffu);
+    if (exp == 255) return (uint16_t)(sign | 0x7c00u | (man ? (0x0200u | (man >> 13)) : 0u));
+    const int32_t he = exp - 127 + 15;
+    if (he >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (he <= 0) {
+        if (14 - he > 24) return (uint16_t)sign;                              // too small: +-0
+        const uint32_t m = man | 0x00800000u;
+        const int shift = 14 - he;                                            // 14..24
+        uint32_t hm = m >> shift;
+        const uint32_t round_bit = 1u << (shift - 1);
+        if ((m & round_bit) && (m & (3u * round_bit - 1u))) hm++;             // RNE: round bit and (sticky or odd)
+        return (uint16_t)(sign | hm);
+    }
+    uint32_t h = sign | ((uint32_t)he << 10) | (man >> 13);
+    if ((man & 0x1000u) && (man & 0x2fffu)) h++;                              // may carry into the exponent (-> inf): correct
+    return (uint16_t)h;
+}
+static float f32_from_f16_bits(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16; const uint32_t e = (h >> 10) & 31u, m = h & 0x3ffu;
+    uint32_t x;
+    if (e == 0) {
+        if (m == 0) x = sign;
+        else { int k = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++k; } x = sign | ((uint32_t)(127 - 15 - k + 1) << 23) | ((mm & 0x3ffu) << 13); }
+    } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+    else x = sign | ((e - 15 + 127) << 23) | (m << 13);
+    float f; std::memcpy(&f, &x, 4); return f;
+}
+void orc_f16_round(int64_t n, const float* in, float* out, uint16_t* bits) {
+    for (int64_t i = 0; i < n; ++i) { const uint16_t b = f16_bits_from_f32(in[i]); if (bits) bits[i] = b; out[i] = f32_from_f16_bits(b); }
+}
+// RgbFilm::get_image film.rs:647-707 + Image::set_channel image.rs:648-661 + the row order of write_pfm image.rs:1350
+void orc_film_get_image(const SgSceneDesc* desc, const SgFilmPixel* film, int32_t w, int32_t h, uint32_t flags, float* out_rgb) {
+    const float* M = desc->film.output_rgb_from_sensor_rgb;
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        const int64_t i = (int64_t)y * w + x;
+        Float rgb[3] = {(Float)film[i].rgb_sum[0], (Float)film[i].rgb_sum[1], (Float)film[i].rgb_sum[2]};
+        if (film[i].weight_sum != 0.0) for (int c = 0; c < 3; ++c) rgb[c] /= (Float)film[i].weight_sum;
+        Float o[3];
+        for (int r = 0; r < 3; ++r) o[r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+        if (flags & SG_IMAGE_FP16) {
+            const Float max_f16 = 65504.0f;
+            Float mx = -INFINITY;
+            for (int c = 0; c < 3; ++c) mx = std::fmax(mx, o[c]);            // Float::max ignores NaN
+            if (mx > max_f16) {
+                if (o[0] > max_f16) o[0] = max_f16;
+                if (o[1] > max_f16) o[0] = max_f16;                           // sic, film.rs:683-685
+                if (o[2] > max_f16) o[2] = max_f16;
+            }
+        }
+        const int64_t dst = (flags & SG_IMAGE_BOTTOM_UP) ? (int64_t)(h - 1 - y) * w + x : i;
+        for (int c = 0; c < 3; ++c) {
+            Float v = o[c];
+            if (std::isnan(v)) v = 0.0f;
+            if (flags & SG_IMAGE_FP16) v = f32_from_f16_bits(f16_bits_from_f32(v));
+            out_rgb[3 * dst + c] = v;
+        }
     }
 }
 

@@ -7,6 +7,7 @@
 // batch (max_depth+1 bounces) is enqueued without a single host synchronisation.
 // Queue appends are warp-aggregated (__ballot_sync + one atomicAdd per warp and queue).
 #pragma once
+#include <cuda_fp16.h>
 #include "sg_shading.cuh"
 #include "sg_texture.cuh"
 #include "sg_trace2.cuh"
@@ -666,6 +667,34 @@ __global__ void k_film_develop(const __grid_constant__ DScene sc, const double* 
     if (ws != 0.0) { rgb[0] /= (float)ws; rgb[1] /= (float)ws; rgb[2] /= (float)ws; }
     const float* M = sc.film.output_rgb_from_sensor_rgb;
     for (int r = 0; r < 3; ++r) out[3 * i + r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+}
+// RgbFilm::get_image film.rs:647-707 + Image::set_channel image.rs:648-661 (see sg_film_get_image in shimmer_gpu.h)
+__global__ void k_film_image(const __grid_constant__ DScene sc, const double* film, int w, int h, uint32_t flags, float* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)w * h) return;
+    float rgb[3] = {(float)film[4 * i], (float)film[4 * i + 1], (float)film[4 * i + 2]};
+    const double ws = film[4 * i + 3];
+    if (ws != 0.0) { rgb[0] /= (float)ws; rgb[1] /= (float)ws; rgb[2] /= (float)ws; }
+    const float* M = sc.film.output_rgb_from_sensor_rgb;
+    float o[3];
+    for (int r = 0; r < 3; ++r) o[r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
+    if (flags & SG_IMAGE_FP16) {
+        const float max_f16 = 65504.0f;
+        // the fold uses Float::max, which ignores NaN operands
+        if (fmaxf(fmaxf(fmaxf(-INFINITY, o[0]), o[1]), o[2]) > max_f16) {
+            if (o[0] > max_f16) o[0] = max_f16;
+            if (o[1] > max_f16) o[0] = max_f16;                         // sic: film.rs:683-685 assigns r
+            if (o[2] > max_f16) o[2] = max_f16;
+        }
+    }
+    const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+    const long long dst = (flags & SG_IMAGE_BOTTOM_UP) ? (long long)(h - 1 - y) * w + x : i;
+    for (int c = 0; c < 3; ++c) {
+        float v = o[c];
+        if (isnan(v)) v = 0.0f;
+        if (flags & SG_IMAGE_FP16) v = __half2float(__float2half_rn(v));
+        out[3 * dst + c] = v;
+    }
 }
 
 }  // namespace sg

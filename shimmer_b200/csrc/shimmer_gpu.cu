@@ -677,4 +677,23 @@ int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_r
     return SG_OK;
 }
 
+int sg_film_get_image(SgScene* s, const SgFilmPixel* film, int32_t w, int32_t h, uint32_t flags, float* out_rgb) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || w < 0 || h < 0 || (flags & ~3u)) return fail(SG_ERR_INVALID_ARGUMENT, "sg_film_get_image: bad size or flags");
+    const size_t n = (size_t)w * (size_t)h;
+    if (n == 0) return SG_OK;
+    if (!film || !out_rgb) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    double* d_f = nullptr; float* d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_f); cudaFree(d_o); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CUX(cudaMalloc((void**)&d_f, n * 32)); CUX(cudaMalloc((void**)&d_o, n * 12));
+    CUX(cudaMemcpy(d_f, film, n * 32, cudaMemcpyHostToDevice));
+    k_film_image<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(s->d, d_f, w, h, flags, d_o);
+    CUX(cudaStreamSynchronize(g_stream));
+    CUX(cudaMemcpy(out_rgb, d_o, n * 12, cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return SG_OK;
+}
+
 }  // extern "C"

@@ -152,6 +152,24 @@ class WavefrontPathIntegrator(Integrator):
                   "sg_film_develop")
         return out.reshape(self.height, self.width, 3)
 
+    def get_image(self, film=None, write_fp16=True, bottom_up=False):
+        """RgbFilm::get_image (film.rs:647-707): developed RGB after the fp16 clamp + f16 quantisation of the default
+        `savefp16` film (film.rs:491) -> (H, W, 3) f32; bottom_up=True gives PFM raster order (image.rs:1350)."""
+        film = self.film if film is None else film
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        ffi.check(self._lib.sg_film_get_image(self._handle, np.ascontiguousarray(film).ctypes.data, self.width, self.height,
+                                              (1 if write_fp16 else 0) | (2 if bottom_up else 0), out.ctypes.data), "sg_film_get_image")
+        return out
+
+    def write_image(self, path, film=None, write_fp16=True):
+        """RgbFilm::write_image (film.rs:709-713) for the one output format the reference can write (PFM, image.rs:1314-1327)."""
+        if not str(path).lower().endswith(".pfm"):
+            raise ffi.ShimmerGpuError("Invalid file extension!")                   # image.rs:1322-1326
+        raster = self.get_image(film, write_fp16=write_fp16, bottom_up=True)
+        with open(path, "wb") as f:
+            f.write(b"PF\n%d %d\n-1\n" % (self.width, self.height))            # Rust `{}` of -1.0f64 prints "-1"
+            f.write(np.ascontiguousarray(raster, dtype="<f4").tobytes())
+
     def close(self):
         if getattr(self, "_handle", None):
             self._lib.sg_scene_destroy(self._handle)
@@ -193,5 +211,5 @@ def write_pfm(path, rgb):
     """Image::write_pfm (image.rs:1333-1377): 'PF', w h, scale -1 (little endian), rows bottom-to-top, f32."""
     h, w, _ = rgb.shape
     with open(path, "wb") as f:
-        f.write(b"PF\n%d %d\n-1.000000\n" % (w, h))
+        f.write(b"PF\n%d %d\n-1\n" % (w, h))
         f.write(np.ascontiguousarray(rgb[::-1], dtype="<f4").tobytes())

@@ -38,6 +38,8 @@ def lib():
     L.orc_camera_rays.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
     L.orc_render.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int]; L.orc_render.restype = C.c_double
     L.orc_film_develop.argtypes = [vp, vp, C.c_int64, vp]
+    L.orc_film_get_image.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, vp]
+    L.orc_f16_round.argtypes = [C.c_int64, vp, vp, vp]
     for name, nargs in (("orc_difference_of_products", 4), ("orc_lerp", 3), ("orc_next_float_up", 1), ("orc_next_float_down", 1),
                         ("orc_visible_wavelengths_pdf", 1), ("orc_sample_visible_wavelengths", 1), ("orc_fresnel_dielectric", 2),
                         ("orc_fresnel_complex", 3), ("orc_blackbody", 2)):
@@ -108,6 +110,19 @@ def develop(scene, film):
     out = np.zeros((len(film), 3), np.float32)
     lib().orc_film_develop(scene.ptr(), np.ascontiguousarray(film).ctypes.data, len(film), out.ctypes.data)
     return out
+
+
+def film_get_image(scene, film, width, height, fp16=True, bottom_up=False):
+    out = np.zeros((height, width, 3), np.float32)
+    lib().orc_film_get_image(scene.ptr(), np.ascontiguousarray(film).ctypes.data, width, height, (1 if fp16 else 0) | (2 if bottom_up else 0),
+                             out.ctypes.data)
+    return out
+
+
+def f16_round(x):
+    x = fa(x).ravel(); out = np.zeros_like(x); bits = np.zeros(len(x), np.uint16)
+    lib().orc_f16_round(len(x), x.ctypes.data, out.ctypes.data, bits.ctypes.data)
+    return out, bits
 
 
 def texture_eval(scene, tex, q, lambda4=None, as_float=False):

@@ -190,3 +190,45 @@ def test_slab_test_axis_parallel_and_nan():
     assert f([0.5, 0.5, 2], [0, 0, 1]) == 0             # t_max > 0
     assert f([0.5, 0.5, 0.5], [1, 0, 0]) == 1           # origin inside
     assert f([0.0, 0.5, -1], [0, 0, 1]) in (0, 1)       # on the slab plane: 0*inf = NaN, must not crash
+
+
+# ---- film output stage: f16 quantisation + get_image ---------------------------------
+def test_f16_round_matches_ieee_rne():
+    """`half::f16::from_f32` (third-party, pinned 2.2.1) is IEEE round-to-nearest-even; numpy's float16 cast is an
+    independent implementation of the same rounding: all 2^16 half values, their neighbours/midpoints, and 2^20 random
+    bit patterns must agree bit for bit."""
+    rng = np.random.default_rng(11)
+    halves = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    fin = halves[np.isfinite(halves)]
+    mids = (fin[:-1].astype(np.float64) + np.sort(fin)[1:].astype(np.float64)) / 2          # not all are midpoints; fine
+    x = np.concatenate([halves, np.nextafter(fin, np.float32(np.inf)), np.nextafter(fin, np.float32(-np.inf)),
+                        mids.astype(np.float32), rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64).astype(np.uint32).view(np.float32),
+                        np.array([65504.0, 65519.99, 65520.0, 65536.0, 1e-8, 2.0 ** -25, 2.0 ** -24, 5.96e-8, -0.0, np.inf, -np.inf], np.float32)])
+    with np.errstate(over="ignore", invalid="ignore"):
+        exp = x.astype(np.float16)
+    got, bits = orc.f16_round(x)
+    nan = np.isnan(x)
+    assert np.array_equal(bits[~nan], exp.view(np.uint16)[~nan])
+    assert np.isnan(got[nan]).all()
+    assert np.array_equal(got[~nan], exp.astype(np.float32)[~nan])
+
+
+def test_film_get_image_semantics(cornell64):
+    """film.rs:647-707: weight-normalise, output matrix, the fp16 clamp as written (a too-large g clamps r and stays,
+    so it becomes +inf in f16), NaN -> 0 (image.rs:649), bottom-up raster order (image.rs:1350)."""
+    M = np.array(list(cornell64.desc.film.output_rgb_from_sensor_rgb), np.float32).reshape(3, 3)
+    Minv = np.linalg.inv(M.astype(np.float64))
+    want = np.array([[0.25, 0.5, 1.0], [1e5, 1.0, 2.0], [1.0, 1e5, 2.0], [1.0, 2.0, 1e5], [np.nan, 1.0, 1.0], [0.1, 0.2, 0.3]])
+    film = np.zeros((6, 4)); film[:, :3] = (want @ Minv.T) * 2.0; film[:, 3] = 2.0
+    film[5, 3] = 0.0; film[5, :3] = want[5] @ Minv.T                                         # zero weight: no division
+    img = orc.film_get_image(cornell64, film, 3, 2, fp16=True).reshape(-1, 3)
+    assert np.allclose(img[0], [0.25, 0.5, 1.0], rtol=2e-3)
+    assert img[1, 0] == 65504.0 and abs(img[1, 1] - 1.0) < 0.05           # f32 cancellation through the 3x3 matrix
+    assert img[2, 0] == 65504.0 and np.isinf(img[2, 1])                                      # the reference's g/r slip
+    assert img[3, 2] == 65504.0 and abs(img[3, 0] - 1.0) < 0.05
+    assert img[4, 0] == 0.0                                                                   # NaN -> 0
+    assert np.allclose(img[5], [0.1, 0.2, 0.3], rtol=2e-3)
+    f32img = orc.film_get_image(cornell64, film, 3, 2, fp16=False).reshape(-1, 3)
+    assert np.array_equal(f32img[[0, 5]], orc.develop(cornell64, film)[[0, 5]])
+    flip = orc.film_get_image(cornell64, film, 3, 2, fp16=True, bottom_up=True)
+    assert np.array_equal(flip[0], img.reshape(2, 3, 3)[1], equal_nan=True) and np.array_equal(flip[1], img.reshape(2, 3, 3)[0], equal_nan=True)
