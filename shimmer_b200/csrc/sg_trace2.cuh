@@ -267,4 +267,71 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
     L.cur = lane_pop<ANY, COUNT, INST>(L, S, n_nodes, io, idx);
 }
 
+// ---- postponed-leaf variant (triangle-only kernels) -------------------------------------------------------------
+// A lane that reaches a leaf does not stop for it: the leaf is parked in `pend` (with its box entry distance) and the lane
+// keeps traversing; only a SECOND leaf blocks it (that one goes back on the stack and is re-popped, and thereby re-tested
+// against the then-current t_max, after the parked leaf has been tested).  Leaves are still tested in exactly the
+// reference's order, and a parked leaf is re-validated with `entry < t_max` before its triangles are tested -- a leaf's
+// entry distance is >= every ancestor's (child bounds are subsets and the slab arithmetic is monotone), so that one
+// comparison is equivalent to the reference having culled any box on the way down with the updated t_max.  Hits, ties
+// and `t` are therefore identical to aggregate.rs:71-203; only the set of boxes looked at grows a little (stale t_max
+// while a leaf is parked), which is why the COUNT builds (reference-order visit counters) keep the in-order loop.
+static constexpr uint32_t kBlockedRef = 0x7ffffffeu;
+
+template <bool ANY>
+SGD uint32_t lane_pop_t(Lane& L, const Stack& S, float& t_out) {
+    while (L.sp > 0) {
+        --L.sp;
+        uint32_t ref; float t = 0.0f;
+        S.get<ANY>(L.sp, ref, t);
+        if (ANY || t < L.t_max) { t_out = t; return ref; }
+    }
+    return kEmptyRef;
+}
+// Park / block on leaves until `ref` is an interior node, kBlockedRef or kEmptyRef.
+template <bool ANY>
+SGD void lane_settle(Lane& L, const Stack& S, uint32_t ref, float t, uint32_t& pend, float& pend_t) {
+    while (ref & kLeafBit) {
+        if (pend == kEmptyRef) { pend = ref; pend_t = t; ref = lane_pop_t<ANY>(L, S, t); }
+        else { S.put<ANY>(L.sp, ref, t); L.sp++; ref = kBlockedRef; }
+    }
+    L.cur = ref;
+}
+template <bool ANY>
+SGD void lane_step_interior_post(const TraceScene& ts, Lane& L, const Stack& S, uint32_t& pend, float& pend_t) {
+    const float4* nd = ts.node64 + 4 * (size_t)L.cur;
+    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+    const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
+    const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);
+    const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
+    float t0, t1;
+    const bool ok0 = slab_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L.o, L.inv_dir, L.nx, L.ny, L.nz, t0);
+    const bool ok1 = slab_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L.o, L.inv_dir, L.nx, L.ny, L.nz, t1);
+    const bool near_ok = neg ? ok1 : ok0, far_ok = neg ? ok0 : ok1;
+    float near_t = neg ? t1 : t0; const float far_t = neg ? t0 : t1;
+    if (far_ok && (ANY ? far_t < L.t_max : far_t <= L.t_max * 1.0009765625f)) { S.put<ANY>(L.sp, far_ref, far_t); L.sp++; }   // see lane_step_interior
+    uint32_t nxt = near_ref;
+    if (!(near_ok && near_t < L.t_max)) nxt = lane_pop_t<ANY>(L, S, near_t);
+    lane_settle<ANY>(L, S, nxt, near_t, pend, pend_t);
+}
+// Tests the parked leaf's primitives (aggregate.rs:99-110).  Returns true when an any-hit ray is done.
+template <bool ANY>
+SGD bool lane_test_pending(const TraceScene& ts, Lane& L, uint32_t pend, float pend_t) {
+    if (!ANY && !(pend_t < L.t_max)) return false;                      // the reference would have culled its box by now
+    uint32_t pi = pend & ~kLeafBit;
+    for (;;) {
+        const float4* tv = ts.tri_verts + 3 * (size_t)pi;
+        const float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+        float b0, b1, b2, t;
+        if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
+            L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
+            if (ANY) return true;
+            L.t_max = t;
+        }
+        if (__float_as_uint(v2.w) & kLastInLeaf) break;
+        ++pi;
+    }
+    return false;
+}
+
 }  // namespace sg

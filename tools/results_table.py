@@ -64,7 +64,8 @@ def main():
         opts = Options(seed=0, pixel_samples=spp)
         film = torch.zeros((W * H, 4), dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
-        integ.render_device(opts, film.data_ptr(), sample_range=(0, min(spp, 8)), stream=stream)      # warm-up
+        warm = min(spp, ((1 << 26) + W * H - 1) // (W * H) + 1)                                      # fills the wavefront: all buffers allocated
+        integ.render_device(opts, film.data_ptr(), sample_range=(0, warm), stream=stream)             # warm-up
         torch.cuda.synchronize(); film.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); integ.render_device(opts, film.data_ptr(), stream=stream); e1.record(); torch.cuda.synchronize()
