@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 4
+#define SG_ABI_VERSION 5
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -56,6 +56,7 @@ typedef struct SgBvhNode {
 /* One entry per `Primitive::{Simple,Geometric}` in BVH leaf order
  * (`ordered_primitives`, src/aggregate.rs:236-266; src/primitive.rs:30-35). */
 #define SG_PRIM_INSTANCE 0xffffffffu   /* SgPrimitive.mesh of a `Primitive::Transformed`: tri = index into instances */
+#define SG_PRIM_SPHERE   0xfffffffeu   /* SgPrimitive.mesh of a `Shape::Sphere` (shape/sphere.rs): tri = index into spheres */
 typedef struct SgPrimitive {
     uint32_t mesh;      /* index into SgSceneDesc.meshes, or SG_PRIM_INSTANCE   */
     uint32_t tri;       /* Triangle::tri_index within that mesh (triangle.rs:49), or the instance index */
@@ -82,6 +83,20 @@ typedef struct SgInstance {
  * the inverse, :159-163) and maps interaction vectors/normals through the INVERSE transform (transform.rs:573-609).
  * Default: reproduce exactly that.  SG_SCENE_FIX_INSTANCING selects the pbrt semantics instead. */
 enum { SG_SCENE_FIX_INSTANCING = 1 };
+
+/* `Sphere` (src/shape/sphere.rs:26-45) as `Sphere::new` stores it (:69-92): z_min/z_max clamped to [-radius, radius],
+ * theta_z_min/max = acos(clamp(z/radius)), phi_max in radians; flags: SG_MESH_REVERSE_ORIENTATION | SG_MESH_SWAPS_HANDEDNESS.
+ * The shape works in object space (interval arithmetic on the transformed ray, sphere.rs:95-186) and maps the hit back
+ * with Transform::apply(SurfaceInteraction) -- the same routine instancing uses, so SG_SCENE_FIX_INSTANCING also selects
+ * the pbrt semantics (vectors through M, normals through M^-T) for spheres.  Transforms must be affine.
+ * Area lights on spheres are not on the GPU path yet (SgPrimitive.light must be -1). */
+typedef struct SgSphere {
+    float    render_from_object[16];
+    float    object_from_render[16];
+    float    radius, z_min, z_max, theta_z_min, theta_z_max, phi_max;
+    uint32_t flags;
+    uint32_t pad;
+} SgSphere;
 
 /* `TriangleMesh` (src/shape/mesh.rs:9-20); vertices already in render space
  * (mesh.rs:43-46).  Attribute arrays are scene-global; a mesh addresses
@@ -236,6 +251,7 @@ typedef struct SgSceneDesc {
     uint32_t n_top_primitives;                              /* top-level primitives;                  0 = n_primitives      */
     uint32_t n_objects;    const SgObject*    objects;
     uint32_t n_instances;  const SgInstance*  instances;
+    uint32_t n_spheres;    const SgSphere*    spheres;     /* top-level primitives only                                    */
     uint32_t scene_flags;                                   /* SG_SCENE_*                                                   */
     uint32_t n_meshes;     const SgMesh*      meshes;
     uint32_t n_indices;    const uint32_t*    indices;     /* 3 per triangle               */

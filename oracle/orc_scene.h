@@ -118,7 +118,10 @@ struct Scene {
     }
 };
 
-struct Hit { int32_t prim; int32_t inst; TriHit th; };
+struct Hit { int32_t prim; int32_t inst; TriHit th; };   // sphere hits: th.b0..b2 = QuadricIntersection::p_obj, th.t = t_hit
+}  // namespace orc
+#include "orc_sphere.h"
+namespace orc {
 
 // Transform::apply_ray_inverse transform.rs:701-723 (inverse = true) / Transform::apply_ray :515-532 (inverse = false)
 // with Some(t_max): origin through the Point3fi transform of an EXACT point (:631-700 / :385-457 -- note the inverse
@@ -168,6 +171,14 @@ inline bool primitive_intersect(const Scene& sc, uint32_t pi, const Ray& ray, Fl
         Hit h2;
         if (!bvh_intersect_range(sc, O.first_node, O.n_nodes, O.first_prim, O.n_prims, r2, tm, any_hit, &h2, ctr)) return false;
         h->prim = h2.prim; h->inst = (int32_t)pr.tri; h->th = h2.th;
+        return true;
+    }
+    if (pr.mesh == SG_PRIM_SPHERE) {                          // Shape::Sphere behind a Simple/GeometricPrimitive
+        QuadricHit q;
+        if (ctr) ctr->tris++;
+        if (!sphere_basic_intersect(D->spheres[pr.tri], ray, t_max, &q)) return false;
+        h->prim = (int32_t)pi; h->inst = -1;
+        h->th.t = q.t; h->th.b0 = q.p_obj.x; h->th.b1 = q.p_obj.y; h->th.b2 = q.p_obj.z;
         return true;
     }
     V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);
@@ -404,8 +415,7 @@ inline SurfaceInteraction interaction_from_intersection(const Scene& sc, uint32_
 // normal through `t = self.inverse()`: vectors by M^-1, normals by apply_normal_helper(t.m_inv = M) = M^T.  With
 // SG_SCENE_FIX_INSTANCING vectors go through M and normals through (M^-1)^T (pbrt).  pi: forward Point3fi transform of an
 // inexact point (:385-457).
-inline void transform_interaction(const SgSceneDesc* D, const SgInstance& I, SurfaceInteraction& si) {
-    const float* M = I.render_from_primitive; const float* Mi = I.primitive_from_render;
+inline void transform_interaction_m(const SgSceneDesc* D, const float* M, const float* Mi, SurfaceInteraction& si) {
     bool fix = (D->scene_flags & SG_SCENE_FIX_INSTANCING) != 0;
     auto vec = [&](V3 v) { const float* m = fix ? M : Mi; return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
     auto nrm = [&](V3 n) { const float* m = fix ? Mi : M; return v3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z); };
@@ -431,5 +441,9 @@ inline void transform_interaction(const SgSceneDesc* D, const SgInstance& I, Sur
     si.sdpdu = vec(si.sdpdu); si.sdpdv = vec(si.sdpdv);
     si.sdndu = nrm(si.sdndu); si.sdndv = nrm(si.sdndv);
 }
+inline void transform_interaction(const SgSceneDesc* D, const SgInstance& I, SurfaceInteraction& si) {
+    transform_interaction_m(D, I.render_from_primitive, I.primitive_from_render, si);
+}
 
 }  // namespace orc
+#include "orc_sphere_surface.h"

@@ -3,7 +3,8 @@
 // Sphere shape: src/shape/sphere.rs restated, with the interval arithmetic it runs in (src/interval.rs,
 // src/float.rs:92-130) and the Point3fi / Vector3fi transforms (src/transform.rs:385-513).
 #pragma once
-#include "orc_scene.h"
+#include "orc_math.h"
+#include "../include/shimmer_gpu.h"
 
 namespace orc {
 
@@ -48,7 +49,7 @@ struct V3i { Ival x, y, z; };
 inline V3 v3i_mid(const V3i& v) { return v3(iv_mid(v.x), iv_mid(v.y), iv_mid(v.z)); }
 
 // Transform::apply(Point3fi) transform.rs:385-457 for an EXACT input point and an affine matrix (wp == 1)
-inline V3i xform_point_exact_fi(const float* m, V3 p) {
+inline V3i sph_xform_point_fi(const float* m, V3 p) {
     const Float x = p.x, y = p.y, z = p.z;
     const Float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
     const Float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
@@ -59,7 +60,7 @@ inline V3i xform_point_exact_fi(const float* m, V3 p) {
     V3i r = {iv_from_value_and_error(xp, ex), iv_from_value_and_error(yp, ey), iv_from_value_and_error(zp, ez)}; return r;
 }
 // Transform::apply(Vector3fi) transform.rs:459-513 for an EXACT input vector
-inline V3i xform_vector_exact_fi(const float* m, V3 v) {
+inline V3i sph_xform_vector_fi(const float* m, V3 v) {
     const Float x = v.x, y = v.y, z = v.z;
     const Float ex = gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z));
     const Float ey = gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z));
@@ -86,8 +87,8 @@ inline bool sphere_clipped(const SgSphere& S, V3 p, Float phi) {        // :143-
 }
 // Sphere::basic_intersect sphere.rs:95-186
 inline bool sphere_basic_intersect(const SgSphere& S, const Ray& ray, Float t_max, QuadricHit* out) {
-    const V3i oi = xform_point_exact_fi(S.object_from_render, ray.o);
-    const V3i di = xform_vector_exact_fi(S.object_from_render, ray.d);
+    const V3i oi = sph_xform_point_fi(S.object_from_render, ray.o);
+    const V3i di = sph_xform_vector_fi(S.object_from_render, ray.d);
     const Ival a = iv_add(iv_add(iv_sqr(di.x), iv_sqr(di.y)), iv_sqr(di.z));
     const Ival b = iv_scale(2.0f, iv_add(iv_add(iv_mul(di.x, oi.x), iv_mul(di.y, oi.y)), iv_mul(di.z, oi.z)));
     const Ival rr = iv(S.radius);
@@ -116,63 +117,6 @@ inline bool sphere_basic_intersect(const SgSphere& S, const Ray& ray, Float t_ma
     }
     out->t = iv_mid(t_shape); out->p_obj = p_hit; out->phi = phi;
     return true;
-}
-
-// Sphere::interaction_from_intersection sphere.rs:188-268 followed by render_from_object.apply(si) (transform.rs:573-609,
-// shared with instancing: transform_interaction_m).  `wo` is the render-space -ray.d.
-inline SurfaceInteraction sphere_interaction(const SgSceneDesc* D, const SgSphere& S, V3 p_hit, Float phi, V3 wo) {
-    const Float u = phi / S.phi_max;
-    const Float cos_theta = p_hit.z / S.radius;
-    const Float theta = safe_asin(cos_theta);                           // sic: math.rs:272-274 `safe_acos` calls asin
-    const Float v = (theta - S.theta_z_min) / (S.theta_z_max - S.theta_z_min);
-    const Float z_radius = std::sqrt(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
-    const Float cos_phi = p_hit.x / z_radius, sin_phi = p_hit.y / z_radius;
-    const V3 dpdu = v3(-S.phi_max * p_hit.y, S.phi_max * p_hit.x, 0.0f);
-    const Float sin_theta = safe_sqrt(1.0f - cos_theta * cos_theta);
-    const Float dth = S.theta_z_max - S.theta_z_min;
-    const V3 dpdv = dth * v3(p_hit.z * cos_phi, p_hit.z * sin_phi, -S.radius * sin_theta);
-    const V3 d2pduu = (-S.phi_max * S.phi_max) * v3(p_hit.x, p_hit.y, 0.0f);
-    const V3 d2pduv = (dth * p_hit.z * S.phi_max) * v3(-sin_phi, cos_phi, 0.0f);
-    const V3 d2pdvv = (-(dth * dth)) * v3(p_hit.x, p_hit.y, p_hit.z);
-    const Float e1 = dot(dpdu, dpdu), f1 = dot(dpdu, dpdv), g1 = dot(dpdv, dpdv);
-    const V3 n = normalize(cross(dpdu, dpdv));
-    const Float e = dot(n, d2pduu), f = dot(n, d2pduv), g = dot(n, d2pdvv);
-    const Float egf2 = difference_of_products(e1, g1, f1, f1);
-    const Float inv = egf2 == 0.0f ? 0.0f : 1.0f / egf2;
-    const V3 dndu = ((f * f1 - e * g1) * inv) * dpdu + ((e * f1 - f * e1) * inv) * dpdv;
-    const V3 dndv = ((g * f1 - f * g1) * inv) * dpdu + ((f * f1 - g * e1) * inv) * dpdv;
-    const V3 p_error = gamma_n(5) * vabs(p_hit);
-    const bool flip = ((S.flags & SG_MESH_REVERSE_ORIENTATION) != 0) ^ ((S.flags & SG_MESH_SWAPS_HANDEDNESS) != 0);
-    // wo_object = object_from_render.apply(wo)
-    const float* Mi = S.object_from_render;
-    const V3 wo_obj = v3(Mi[0] * wo.x + Mi[1] * wo.y + Mi[2] * wo.z, Mi[4] * wo.x + Mi[5] * wo.y + Mi[6] * wo.z, Mi[8] * wo.x + Mi[9] * wo.y + Mi[10] * wo.z);
-    SurfaceInteraction si;                                              // SurfaceInteraction::new interaction.rs:111-148
-    si.pi = p3fi_from_value_and_error(p_hit, p_error);
-    si.uv.x = u; si.uv.y = v; si.wo = wo_obj;
-    si.dpdu = dpdu; si.dpdv = dpdv;
-    si.n = flip ? -n : n;
-    si.sn = si.n; si.sdpdu = dpdu; si.sdpdv = dpdv; si.sdndu = dndu; si.sdndv = dndv;
-    si.material = -1; si.light = -1;
-    transform_interaction_m(D, S.render_from_object, S.object_from_render, si);
-    return si;
-}
-
-// Transform::apply(Bounds3f) transform.rs:557-571 of the object-space box (sphere.rs:273-279): the host-side bounds a
-// BVH builder needs; exported for the host tests.
-inline void sphere_bounds(const SgSphere& S, float bmin[3], float bmax[3]) {
-    const float* M = S.render_from_object;
-    const Float lo[3] = {-S.radius, -S.radius, S.z_min}, hi[3] = {S.radius, S.radius, S.z_max};
-    bool first = true;
-    for (int c = 0; c < 8; ++c) {
-        const V3 p = v3((c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]);
-        const V3 q = v3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
-        const Float qa[3] = {q.x, q.y, q.z};
-        for (int a = 0; a < 3; ++a) {
-            if (first) { bmin[a] = qa[a]; bmax[a] = qa[a]; }
-            else { bmin[a] = fmin_(bmin[a], qa[a]); bmax[a] = fmax_(bmax[a], qa[a]); }
-        }
-        first = false;
-    }
 }
 
 }  // namespace orc

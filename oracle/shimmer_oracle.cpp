@@ -105,7 +105,11 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
         }
         const SgPrimitive& prim = D->primitives[hit.prim];
         SurfaceInteraction si;
-        if (hit.inst >= 0) {                                                       // TransformedPrimitive::intersect primitive.rs:155-169
+        if (prim.mesh == SG_PRIM_SPHERE) {                                         // Sphere::intersect sphere.rs:286-293
+            V3 p_obj = v3(hit.th.b0, hit.th.b1, hit.th.b2);
+            Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
+            si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -ray.d);
+        } else if (hit.inst >= 0) {                                                       // TransformedPrimitive::intersect primitive.rs:155-169
             const SgInstance& I = D->instances[hit.inst];
             const float* mi = I.primitive_from_render;
             V3 d2 = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
@@ -249,6 +253,13 @@ void orc_trace(const SgSceneDesc* desc, int64_t n, const float* o, const float* 
             if (any_hit) { oh.prim = 0; continue; }
             oh.prim = h.prim; oh.t = h.th.t; oh.b0 = h.th.b0; oh.b1 = h.th.b1; oh.b2 = h.th.b2;
             const SgPrimitive& pr = desc->primitives[h.prim];
+            if (pr.mesh == SG_PRIM_SPHERE) {
+                V3 p_obj = v3(h.th.b0, h.th.b1, h.th.b2);
+                Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
+                SurfaceInteraction ssi = sphere_interaction(desc, desc->spheres[pr.tri], p_obj, phi, -r.d);
+                oh.ng[0] = ssi.n.x; oh.ng[1] = ssi.n.y; oh.ng[2] = ssi.n.z;
+                continue;
+            }
             SurfaceInteraction si = interaction_from_intersection(sc, pr.mesh, pr.tri, h.th, -r.d);
             // geometric normal as produced by triangle.rs:407-412 (before any shading-normal face-forwarding)
             V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);

@@ -24,7 +24,11 @@ static constexpr float kMachineEps = 1.1920929e-07f * 0.5f;     // float.rs:16
 // gamma(n) = n*eps/2 / (1 - n*eps/2), float.rs:88-90 -- evaluated in f32 exactly like the reference
 SGD float gamma_n(int n) { return ((float)n * kMachineEps) / (1.0f - (float)n * kMachineEps); }
 
+// NaN stays NaN: the reference's bit increment keeps x86's / ARM's default NaN (0xFFC00000 / 0x7FC00000) a NaN, whereas
+// CUDA's canonical NaN 0x7FFFFFFF + 1 would wrap to -0.0 (seen in the sphere's interval arithmetic, where the reference
+// relies on f32::min/max ignoring NaN bounds).
 SGD float next_up(float v) {                                    // float.rs:53-68
+    if (isnan(v)) return v;
     if (isinf(v) && v > 0.0f) return v;
     if (v == -0.0f) v = 0.0f;
     uint32_t u = __float_as_uint(v);
@@ -32,6 +36,7 @@ SGD float next_up(float v) {                                    // float.rs:53-6
     return __uint_as_float(u);
 }
 SGD float next_down(float v) {                                  // float.rs:72-86
+    if (isnan(v)) return v;
     if (isinf(v) && v < 0.0f) return v;
     if (v == 0.0f) v = -0.0f;
     uint32_t u = __float_as_uint(v);

@@ -51,6 +51,7 @@ struct DScene {
     const float* rgb2spec_data;
     uint32_t rgb2spec_res, n_textures;
     const DInstance* instances;         // object instancing
+    const struct DSphere* spheres;      // sphere shapes (sg_sphere.cuh)
     uint32_t n_instances, scene_flags;
     uint32_t n_nodes, n_prims, n_lights, n_materials;
     int32_t n_infinite;          // number of SG_LIGHT_UNIFORM_INFINITE lights

@@ -285,9 +285,8 @@ template <> SGD void surf_tex_store<true>(SurfTex* x, float2 uv, float3 dpdu, fl
 // (`t = self.inverse()`); with SG_SCENE_FIX_INSTANCING vectors go through M and normals through (M^-1)^T.  pi: forward
 // Point3fi transform of an inexact point (:385-457).  Returns interaction.wo in `wo_si`.
 template <bool TEX>
-__device__ __noinline__ void transform_interaction(const DScene& sc, const DInstance& I, float3 rd, Surf& s, SurfTex* x, float3& wo_si) {
+__device__ __noinline__ void transform_interaction(const DScene& sc, const float* M, const float* Mi, float3 rd, Surf& s, SurfTex* x, float3& wo_si) {
     const bool fix = (sc.scene_flags & SG_SCENE_FIX_INSTANCING) != 0;
-    const float* M = I.m; const float* Mi = I.mi;
     const float* mv = fix ? M : Mi; const float* mn = fix ? Mi : M;
     auto vec = [&](float3 v) { return f3(mv[0] * v.x + mv[1] * v.y + mv[2] * v.z, mv[4] * v.x + mv[5] * v.y + mv[6] * v.z, mv[8] * v.x + mv[9] * v.y + mv[10] * v.z); };
     auto nrm = [&](float3 n) { return f3(mn[0] * n.x + mn[4] * n.y + mn[8] * n.z, mn[1] * n.x + mn[5] * n.y + mn[9] * n.z, mn[2] * n.x + mn[6] * n.y + mn[10] * n.z); };

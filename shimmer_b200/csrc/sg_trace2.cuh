@@ -19,6 +19,7 @@
 //     the tree depth computed at upload.
 #pragma once
 #include "sg_scene.cuh"
+#include "sg_sphere.cuh"
 
 namespace sg {
 
@@ -62,6 +63,7 @@ struct TraceScene {
     int interior_burst;
     int prefetch;
     const DInstance* instances; // object instancing (INST kernels only)
+    const DSphere* spheres;     // sphere shapes (INST kernels only: the "general" kernels handle everything that is not a triangle)
     uint32_t scene_flags;
 };
 
@@ -255,7 +257,16 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
         }
         if (COUNT) n_tris++;
         float b0, b1, b2, t;
-        if (intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t)) {
+        bool hit_prim;
+        if (INST && (__float_as_uint(v2.w) & kSphereBit)) {
+            // Shape::Sphere (top level only): works on the render-space ray, re-read through `io`; the hit record carries p_obj
+            float3 o, d; float tm;
+            io.load(idx, o, d, tm);
+            float3 p_obj;
+            hit_prim = sphere_basic_intersect(ts.spheres[__float_as_uint(v2.w) & ~(kSphereBit | kLastInLeaf)], o, d, L.t_max, p_obj, t);
+            b0 = p_obj.x; b1 = p_obj.y; b2 = p_obj.z;
+        } else hit_prim = intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
+        if (hit_prim) {
             L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
             if constexpr (INST) { L.hit.inst = L.inst; L.inst_hit = true; }
             if (ANY) { L.cur = kEmptyRef; return; }

@@ -11,6 +11,7 @@
 #include "sg_shading.cuh"
 #include "sg_texture.cuh"
 #include "sg_trace2.cuh"
+#include "sg_sphere_surface.cuh"
 
 namespace sg {
 
@@ -448,11 +449,18 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             float p_b = pbe.x, eta_scale = pbe.y;
 
             SurfTex sx;
-            Surf s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
+            Surf s;
             float3 wo_si = wo;                                   // SurfaceInteraction::wo (what sample_ld reads, integrator.rs:905-917)
-            if (st.hit_inst != nullptr) {                        // TransformedPrimitive::intersect primitive.rs:155-169
-                const int inst = st.hit_inst[path];
-                if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst], rd, s, &sx, wo_si);
+            if (st.hit_inst != nullptr && (geo.mesh & kSphereBit)) {     // Sphere::intersect sphere.rs:286-293: hit_b carries p_obj
+                const DSphere& S = sc.spheres[geo.mesh & ~kSphereBit];
+                s = make_surface_sphere<TEX>(S, f3(hb.x, hb.y, hb.z), &sx);
+                transform_interaction<TEX>(sc, S.m, S.mi, rd, s, &sx, wo_si);
+            } else {
+                s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
+                if (st.hit_inst != nullptr) {                    // TransformedPrimitive::intersect primitive.rs:155-169
+                    const int inst = st.hit_inst[path];
+                    if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, &sx, wo_si);
+                }
             }
 
             // emission + MIS against light sampling, :798-813
@@ -683,6 +691,15 @@ struct RaysIO {
                 h.prim = hit.prim; h.t = hit.t; h.b0 = hit.b0; h.b1 = hit.b1; h.b2 = hit.b2;
                 const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 1),
                              v2 = __ldg(sc.tri_verts + 3 * (size_t)hit.prim + 2);
+                if (__float_as_uint(v2.w) & kSphereBit) {                            // geometric normal of the render-space interaction
+                    const DSphere& S = sc.spheres[__float_as_uint(v2.w) & ~(kSphereBit | kLastInLeaf)];
+                    Surf ss = make_surface_sphere<false>(S, f3(hit.b0, hit.b1, hit.b2), nullptr);
+                    float3 wo_si, rd = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+                    transform_interaction<false>(sc, S.m, S.mi, rd, ss, nullptr, wo_si);
+                    h.ng[0] = ss.n.x; h.ng[1] = ss.n.y; h.ng[2] = ss.n.z;
+                    out[i] = h;
+                    return;
+                }
                 const float3 p0 = f3(v0.x, v0.y, v0.z), p1 = f3(v1.x, v1.y, v1.z), p2 = f3(v2.x, v2.y, v2.z);
                 float3 ng = normalize3(cross3(p0 - p2, p1 - p2));                    // triangle.rs:407-412
                 const uint32_t mflags = sc.meshes[__float_as_uint(v2.w) & ~kLastInLeaf].flags;

@@ -145,8 +145,8 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
     if (!desc || !out) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (desc->abi_version != SG_ABI_VERSION) return fail(SG_ERR_INVALID_ARGUMENT, "SgSceneDesc.abi_version mismatch");
-    if (desc->n_primitives > 0 && (!desc->nodes || !desc->primitives || !desc->meshes || !desc->indices || !desc->p))
-        return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
+    if (desc->n_primitives > 0 && (!desc->nodes || !desc->primitives)) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
+    if (desc->n_spheres && !desc->spheres) return fail(SG_ERR_INVALID_ARGUMENT, "sphere array missing");
     if (desc->n_primitives >= (1u << 31)) return fail(SG_ERR_UNSUPPORTED, "too many primitives");
     // validate references so device code never reads out of bounds
     const uint32_t n_top_nodes = desc->n_top_nodes ? desc->n_top_nodes : desc->n_nodes;
@@ -160,6 +160,18 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             if (p.tri >= desc->n_instances) return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references an out-of-range instance");
             continue;
         }
+        if (p.mesh == SG_PRIM_SPHERE) {
+            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "spheres inside object definitions are not on the GPU path yet");
+            if (p.tri >= desc->n_spheres || p.material >= desc->n_materials) return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references an out-of-range sphere/material");
+            if (p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights on spheres are not on the GPU path yet");
+            const SgSphere& sp = desc->spheres[p.tri];
+            const float* r3 = sp.render_from_object + 12; const float* q3 = sp.object_from_render + 12;
+            if (r3[0] != 0.0f || r3[1] != 0.0f || r3[2] != 0.0f || r3[3] != 1.0f || q3[0] != 0.0f || q3[1] != 0.0f || q3[2] != 0.0f || q3[3] != 1.0f)
+                return fail(SG_ERR_UNSUPPORTED, "sphere transforms must be affine");
+            if (!(sp.radius > 0.0f)) return fail(SG_ERR_INVALID_ARGUMENT, "sphere radius must be positive");
+            continue;
+        }
+        if (!desc->meshes || !desc->indices || !desc->p) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
         if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
             p.light >= (int32_t)desc->n_lights)
             return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references out-of-range mesh/triangle/material/light");
@@ -234,6 +246,14 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (p.mesh == SG_PRIM_INSTANCE) {                   // TransformedPrimitive: no vertices; kind 7, instance id in word 1
             const uint32_t w[3] = {kKindInstance << 28, p.tri, 0u};
             for (int k = 0; k < 3; ++k) { float wf; std::memcpy(&wf, &w[k], 4); tv[3 * (size_t)i + k] = make_float4(0.0f, 0.0f, 0.0f, wf); }
+            continue;
+        }
+        if (p.mesh == SG_PRIM_SPHERE) {                     // Shape::Sphere: material + kind like a triangle, sphere index | kSphereBit in word 2
+            if (p.material >= (1u << 23)) { g_err = "more than 2^23 materials"; return bail(SG_ERR_UNSUPPORTED); }
+            const uint32_t w[3] = {p.material | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, p.tri | kSphereBit};
+            const float* M = desc->spheres[p.tri].render_from_object;
+            for (int k = 0; k < 3; ++k) { float wf; std::memcpy(&wf, &w[k], 4); tv[3 * (size_t)i + k] = make_float4(M[3], M[7], M[11], wf); }
+            s->kinds_present[desc->materials[p.material].kind] = true;
             continue;
         }
         const SgMesh& m = desc->meshes[p.mesh];
@@ -334,7 +354,19 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         s->smem_closest = (size_t)s->ts.smem_levels * kTraceThreads * 8;
         s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
     }
-    s->instanced = desc->n_instances > 0;
+    s->instanced = desc->n_instances > 0 || desc->n_spheres > 0;        // anything that is not a triangle -> the general kernels
+    {
+        std::vector<DSphere> dsph(desc->n_spheres);
+        for (uint32_t i = 0; i < desc->n_spheres; ++i) {
+            const SgSphere& sp = desc->spheres[i]; DSphere& D = dsph[i];
+            std::memcpy(D.m, sp.render_from_object, 12 * sizeof(float)); std::memcpy(D.mi, sp.object_from_render, 12 * sizeof(float));
+            D.radius = sp.radius; D.z_min = sp.z_min; D.z_max = sp.z_max; D.theta_z_min = sp.theta_z_min; D.theta_z_max = sp.theta_z_max;
+            D.phi_max = sp.phi_max; D.flags = sp.flags; D.pad = 0;
+        }
+        DSphere* d_sph = nullptr;
+        if ((rc = upload(dsph.data(), dsph.size(), &d_sph, s->owned)) != SG_OK) return bail(rc);
+        s->ts.spheres = d_sph; d.spheres = d_sph;
+    }
     {
         DInstance* d_inst = nullptr;
         if ((rc = upload(dinst.data(), dinst.size(), &d_inst, s->owned)) != SG_OK) return bail(rc);

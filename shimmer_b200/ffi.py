@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 4
+SG_ABI_VERSION = 5
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -36,6 +36,7 @@ class SgPrimitive(C.Structure):
 
 
 SG_PRIM_INSTANCE = 0xffffffff
+SG_PRIM_SPHERE = 0xfffffffe
 SG_SCENE_FIX_INSTANCING = 1
 
 
@@ -102,6 +103,12 @@ class SgFilm(C.Structure):
                 ("max_component_value", C.c_float), ("output_rgb_from_sensor_rgb", C.c_float * 9)]
 
 
+class SgSphere(C.Structure):
+    _fields_ = [("render_from_object", C.c_float * 16), ("object_from_render", C.c_float * 16),
+                ("radius", C.c_float), ("z_min", C.c_float), ("z_max", C.c_float), ("theta_z_min", C.c_float),
+                ("theta_z_max", C.c_float), ("phi_max", C.c_float), ("flags", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class SgSceneDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32),
                 ("n_nodes", C.c_uint32), ("nodes", C.POINTER(SgBvhNode)),
@@ -109,6 +116,7 @@ class SgSceneDesc(C.Structure):
                 ("n_top_nodes", C.c_uint32), ("n_top_primitives", C.c_uint32),
                 ("n_objects", C.c_uint32), ("objects", C.POINTER(SgObject)),
                 ("n_instances", C.c_uint32), ("instances", C.POINTER(SgInstance)),
+                ("n_spheres", C.c_uint32), ("spheres", C.POINTER(SgSphere)),
                 ("scene_flags", C.c_uint32),
                 ("n_meshes", C.c_uint32), ("meshes", C.POINTER(SgMesh)),
                 ("n_indices", C.c_uint32), ("indices", C.POINTER(C.c_uint32)),

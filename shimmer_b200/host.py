@@ -237,6 +237,7 @@ class SceneBuilder:
         self.textures = []       # dicts: levels (list of HxWxC f32 arrays) + SgTexture parameters
         self.n_objects = 0       # object definitions (ObjectBegin/End); meshes carry an `object` id or None
         self.instances = []      # (object id, render_from_instance Transform)
+        self.spheres = []        # dicts: Sphere::new fields + material (top-level shapes, after the meshes)
         self.fix_instancing = False
         self.camera = None
         self.film = None
@@ -432,6 +433,23 @@ class SceneBuilder:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
+    def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False):
+        """Shape "sphere": Sphere::create / Sphere::new (shape/sphere.rs:48-92).  `object_from_world` is the CTM
+        (render_from_object = render_from_world * CTM).  Top-level, non-emissive spheres only."""
+        ctm = object_from_world if object_from_world is not None else Transform.identity()
+        rfo = self.render_from_world * ctm
+        r = f32(radius)
+        zlo = f32(min(-radius if z_min is None else z_min, radius if z_max is None else z_max))
+        zhi = f32(max(-radius if z_min is None else z_min, radius if z_max is None else z_max))
+        clamp = lambda v, lo, hi: f32(min(max(v, lo), hi))
+        flags = (ffi.SG_MESH_REVERSE_ORIENTATION if reverse_orientation else 0) | (ffi.SG_MESH_SWAPS_HANDEDNESS if rfo.swaps_handedness() else 0)
+        self.spheres.append(dict(rfo=rfo, radius=r, z_min=clamp(zlo, -r, r), z_max=clamp(zhi, -r, r),
+                                 theta_z_min=f32(np.arccos(clamp(zlo / r, f32(-1.0), f32(1.0)))),
+                                 theta_z_max=f32(np.arccos(clamp(zhi / r, f32(-1.0), f32(1.0)))),
+                                 phi_max=f32(f32(np.pi) / f32(180.0)) * clamp(f32(phi_max), f32(0.0), f32(360.0)),
+                                 flags=flags, material=material))
+        return len(self.spheres) - 1
+
     def add_point_light(self, pos, I, scale=1.0):
         """PointLight::create (light.rs:421-453)."""
         sc = f32(scale) / spectrum_to_photometric(I)
@@ -564,8 +582,29 @@ class SceneBuilder:
             corners = np.array([[(hi if (c >> a) & 1 else lo)[a] for a in range(3)] for c in range(8)], np.float32)   # Transform::apply(Bounds3f) transform.rs:557-570
             pc = xf.apply_points_f32(corners)
             inst_bounds[ii, :3] = pc.min(axis=0); inst_bounds[ii, 3:] = pc.max(axis=0)
-        top_bounds = np.concatenate([bounds[top_sel], inst_bounds]) if len(self.instances) else bounds[top_sel]
+        # spheres: Sphere::bounds (sphere.rs:273-279) = Transform::apply(Bounds3f) of the object-space box (transform.rs:557-570)
+        sph_rows = (ffi.SgSphere * max(len(self.spheres), 1))()
+        sph_bounds = np.empty((len(self.spheres), 6), np.float32)
+        for si_, sp in enumerate(self.spheres):
+            r = sph_rows[si_]
+            if not np.array_equal(sp["rfo"].m[3], [0.0, 0.0, 0.0, 1.0]):
+                raise ValueError("sphere transforms must be affine")
+            r.render_from_object[:] = sp["rfo"].m32().ravel().tolist(); r.object_from_render[:] = sp["rfo"].m_inv.astype(np.float32).ravel().tolist()
+            r.radius, r.z_min, r.z_max = float(sp["radius"]), float(sp["z_min"]), float(sp["z_max"])
+            r.theta_z_min, r.theta_z_max, r.phi_max, r.flags = float(sp["theta_z_min"]), float(sp["theta_z_max"]), float(sp["phi_max"]), sp["flags"]
+            lo = np.array([-sp["radius"], -sp["radius"], sp["z_min"]], np.float32); hi = np.array([sp["radius"], sp["radius"], sp["z_max"]], np.float32)
+            corners = np.array([[(hi if (c >> a) & 1 else lo)[a] for a in range(3)] for c in range(8)], np.float32)
+            pc = sp["rfo"].apply_points_f32(corners)
+            sph_bounds[si_, :3] = pc.min(axis=0); sph_bounds[si_, 3:] = pc.max(axis=0)
+        A["spheres"] = sph_rows
+        top_bounds = bounds[top_sel]
         top_prim_in = prim_in[top_sel]
+        if len(self.spheres):
+            sp_in = np.zeros((len(self.spheres), 4), np.int64)
+            sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]; sp_in[:, 3] = -1
+            top_prim_in = np.concatenate([top_prim_in, sp_in]); top_bounds = np.concatenate([top_bounds, sph_bounds])
+        if len(self.instances):
+            top_bounds = np.concatenate([top_bounds, inst_bounds])
         if len(self.instances):
             ip = np.zeros((len(self.instances), 4), np.int64)
             ip[:, 0] = ffi.SG_PRIM_INSTANCE; ip[:, 1] = np.arange(len(self.instances)); ip[:, 3] = -1
@@ -635,6 +674,7 @@ class SceneBuilder:
         d.n_top_nodes, d.n_top_primitives = n_top_nodes, n_top_prims
         d.n_objects = self.n_objects; d.objects = A["objects"]
         d.n_instances = len(self.instances); d.instances = A["instances"]
+        d.n_spheres = len(self.spheres); d.spheres = A["spheres"]
         d.scene_flags = ffi.SG_SCENE_FIX_INSTANCING if self.fix_instancing else 0
         d.n_meshes = len(self.meshes); d.meshes = A["meshes"]
         d.n_indices = 3 * nt; d.indices = _as_ptr(A["idx"], C.c_uint32)
@@ -657,6 +697,6 @@ class SceneBuilder:
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
         d.film = self.film
         inst_tris = sum(int(obj_rows[o].n_prims) for o, _ in self.instances)
-        out.meta = dict(n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights),
+        out.meta = dict(n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights), n_spheres=len(self.spheres),
                         resolution=tuple(self.film.full_resolution), window=tuple(self.film.pixel_bounds))
         return out

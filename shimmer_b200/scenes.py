@@ -265,6 +265,37 @@ def instanced_scene(n_theta=224, n_phi=224, grid=10, resolution=(1920, 1080), cr
     return b
 
 
+SPHERE_KINDS = ("spheres", "spherestex")
+
+
+def sphere_tiny_scene(kind="spheres", resolution=(32, 32), fix=False):
+    """Shape "sphere" (shape/sphere.rs): a diffuse sphere, a glass sphere (translated + uniformly scaled), a copper partial
+    sphere (zmin/zmax/phimax clipped, rotated + non-uniformly scaled: every quirk of Transform::apply(SurfaceInteraction)
+    shows) over a ground quad; `spherestex` puts image textures (uv from phi/theta, dndu/dndv from the fundamental forms) on
+    the spheres."""
+    b = SceneBuilder()
+    b.fix_instancing = fix
+    b.set_camera(pos=(0.0, 1.5, -4.5), look=(0.0, 0.6, 0.0), up=(0, 1, 0), fov=42.0, resolution=resolution)
+    white = b.diffuse(_white())
+    if kind == "spherestex":
+        m0 = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="trilinear", su=4.0, sv=2.0))
+        m2 = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="ewa", su=3.0, sv=3.0),
+                       displacement_tex=b.image_texture(procedural_image(32, 1), filter="bilinear", su=8.0, sv=4.0, scale=0.03))
+    else:
+        m0 = b.diffuse(_green())
+        m2 = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.2)
+    glass = b.dielectric(("const", 1.5))
+    b.add_sphere(0.6, m0, object_from_world=Transform.translate((-1.3, 0.6, 0.4)) * Transform.rotate(-90.0, (1, 0, 0)))
+    b.add_sphere(1.0, glass, object_from_world=Transform.translate((0.1, 0.55, -0.6)) * Transform.scale(0.55, 0.55, 0.55))
+    b.add_sphere(0.7, m2, z_min=-0.45, z_max=0.6, phi_max=300.0,
+                 object_from_world=Transform.translate((1.4, 0.75, 0.5)) * Transform.rotate(-70.0, (1, 0.2, 0)) * Transform.scale(1.0, 0.8, 1.15))
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, white, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    lp, li = _quad((-0.6, 2.8, -0.6), (0.6, 2.8, -0.6), (0.6, 2.8, 0.6), (-0.6, 2.8, 0.6))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b
+
+
 TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
 INSTANCED_KINDS = ("inst", "instrot", "instfix", "insttex")
 
@@ -323,6 +354,8 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
     textures (RGB + one-channel, every filter / wrap mode), bump mapping and specular ray-differential propagation."""
     if kind in INSTANCED_KINDS:
         return instanced_tiny_scene(kind, resolution)
+    if kind in SPHERE_KINDS:
+        return sphere_tiny_scene(kind, resolution)
     b = SceneBuilder()
     b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
     white = b.diffuse(_white())

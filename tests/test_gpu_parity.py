@@ -303,3 +303,89 @@ def test_converged_image_against_reference_rng_mode():
     assert rmse <= 0.01, rmse
     assert abs(lum(img_g) - lum(img_r)) / lum(img_r) <= 0.01
     assert np.all(film[:, 3] == spp)
+
+
+# ---- spheres ------------------------------------------------------------------------------
+def _sphere_only(mults):
+    from shimmer_b200.host import SceneBuilder, Transform
+    b = SceneBuilder(); b.set_camera((0, 0, -20), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+    m = b.diffuse(("const", 0.5))
+    for mu in mults:
+        b.add_sphere(1.0, m, object_from_world=Transform.translate((mu, 0, 0)))
+    return b
+
+
+def test_reference_bvh_sphere_vectors_on_gpu():
+    """The reference's own traversal tests (aggregate.rs:604-702) through sg_trace: t = 4 on the single unit sphere,
+    t = 5.5 +- 1e-5 on the set of spheres, normal -x, predicate true; the ray offset by z = 1.001 misses."""
+    b = _sphere_only([0.0]); sc = b.build()
+    rs = lambda p: b.render_from_world.apply_points_f32(np.array([p], np.float32))
+    integ = create_integrator("wavefront", {}, sc)
+    h = integ.trace(rs([-5, 0, 0]), [[1, 0, 0]], [np.inf])
+    assert h["prim"][0] == 0 and abs(h["t"][0] - 4.0) <= 4 * np.spacing(np.float32(4.0)) and abs(h["b0"][0] + 1.0) <= 1e-6
+    assert np.dot(h["ng"][0], [-1, 0, 0]) == 1.0
+    integ.close()
+    b = _sphere_only([-3.5, 0.0, 5.0]); sc = b.build()
+    integ = create_integrator("wavefront", {}, sc)
+    o = rs([-10, 0, 0]); d = [[1, 0, 0]]
+    h = integ.trace(o, d, [np.inf])
+    assert abs(h["t"][0] - 5.5) <= 1e-5 and np.dot(h["ng"][0], [-1, 0, 0]) == 1.0
+    assert integ.trace(o, d, [np.inf], any_hit=True)["prim"][0] == 0
+    o2 = rs([-10, 0, 1.001])
+    assert integ.trace(o2, d, [np.inf])["prim"][0] == -1 and integ.trace(o2, d, [np.inf], any_hit=True)["prim"][0] == -1
+    ref, _ = orc.trace(sc, o, d, [np.inf])
+    assert h["t"][0] == ref["t"][0] and h["prim"][0] == ref["prim"][0]
+    integ.close()
+
+
+def test_sphere_raycast_parity():
+    """Random + aimed rays on the sphere scene (full, scaled, clipped/rotated spheres + triangles): primitive, t and p_obj
+    bit-exact (pure interval arithmetic); rays whose hit sits on a phimax clip boundary may flip on atan2f's last bit."""
+    b = scenes.sphere_tiny_scene("spheres"); sc = b.build()
+    integ = create_integrator("wavefront", {}, sc)
+    rng = np.random.default_rng(6)
+    n = 1 << 16
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1]) + 0.05
+    centres = np.array([[-1.3, 0.6, 0.4], [0.1, 0.55, -0.6], [1.4, 0.75, 0.5]], np.float32)
+    d = (centres[rng.integers(0, 3, n)] + rng.uniform(-0.8, 0.8, (n, 3)).astype(np.float32) - o).astype(np.float32)
+    o[: n // 10] = centres[rng.integers(0, 3, n // 10)] + rng.uniform(-0.2, 0.2, (n // 10, 3)).astype(np.float32)
+    d[n // 2:] = rng.standard_normal((n - n // 2, 3)).astype(np.float32)
+    o = b.render_from_world.apply_points_f32(o)
+    for tmax in (np.inf, 2.5):
+        t = np.full(n, tmax, np.float32)
+        got, gst = integ.trace(o, d, t, want_stats=True)
+        ref, rst = orc.trace(sc, o, d, t)
+        same = got["prim"] == ref["prim"]
+        assert same.mean() > 0.9999
+        hit = same & (ref["prim"] >= 0)
+        for f in ("t", "b0", "b1", "b2"):
+            assert np.array_equal(got[f][hit], ref[f][hit]), f
+        assert np.allclose(got["ng"][hit], ref["ng"][hit], rtol=1e-5, atol=1e-6)
+        assert (sc.arrays["prims"]["mesh"][ref["prim"][hit]] == ffi.SG_PRIM_SPHERE).mean() > 0.3
+        any_g = integ.trace(o, d, np.minimum(t, np.float32(0.9999)), any_hit=True)
+        any_r, _ = orc.trace(sc, o, d, np.minimum(t, np.float32(0.9999)), any_hit=True)
+        assert (any_g["prim"] == any_r["prim"]).mean() > 0.9999
+    integ.close()
+
+
+@pytest.mark.parametrize("kind", list(scenes.SPHERE_KINDS))
+def test_sphere_scene_films(kind):
+    sc = scenes.tiny_scene(kind, resolution=(24, 24)).build()
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 8, "seed": 3})
+    film = integ.render(Options()).copy()
+    ref, rst, _ = orc.render(sc, orc.make_params(seed=3, spp=8))
+    _film_close(film, ref, frac=0.99)
+    assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-3 * rst.closest_hit_rays
+    integ.close()
+
+
+def test_sphere_validation_errors():
+    import ctypes as C
+    b = _sphere_only([0.0]); sc = b.build()
+    lib = ffi.load_library(); h = C.c_void_p()
+    prims = sc.arrays["prims"].copy(); prims["light"][0] = 0
+    bad = ffi.SgSceneDesc.from_buffer_copy(sc.desc); bad.primitives = prims.ctypes.data_as(C.POINTER(ffi.SgPrimitive))
+    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) != 0 and b"spheres" in lib.sg_last_error()
+    prims = sc.arrays["prims"].copy(); prims["tri"][0] = 7
+    bad = ffi.SgSceneDesc.from_buffer_copy(sc.desc); bad.primitives = prims.ctypes.data_as(C.POINTER(ffi.SgPrimitive))
+    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) != 0
