@@ -229,8 +229,22 @@ def main():
         alg_bytes_per_launch = bytes_per_ray * n_closest / n_launch
         achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
         peak, peak_src = peaks()
+        # DRAM traffic + issue-slot figures of the same kernel from the committed `ncu --set full` capture (never measured live:
+        # a number taken under a profiler is not a bench value); only attached when the capture was made on this workload
+        traffic = issue = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_trace_full_ncu.json")))
+            if args.workload == "mesh1m" and not args.spp and not args.res:
+                k0 = cap["launches"][0]
+                traffic = k0["dram_read_bytes"] + k0["dram_write_bytes"]
+                issue = {"issue_active_pct": k0["issue_active_pct"], "lanes_per_inst": k0["lanes_per_inst"], "warp_inst": k0["warp_inst"],
+                         "launch": "depth-0 closest-hit launch, 67.1 M rays", "source": "profiles/r01_trace_full_ncu.json (ncu --set full)"}
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_trace<closest-hit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes read+written by the depth-0 closest-hit launch (ncu); "
+                    "its algorithmic bytes are bytes_per_ray x 67.1 M rays = %.3g: the scene is L2-resident" % (bytes_per_ray * 67108864.0),
+                    "issue": issue, "peak_source": peak_src,
                     "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                     "rays_per_launch": n_closest / n_launch, "avg_launch_ms": avg_launch_ms, "launches_per_step": n_launch,
                     "kernel_share_of_step": st_t["closest_ms"] / max(st_t["render_ms"], 1e-9),
@@ -255,7 +269,9 @@ def main():
                            "l2": "working set (path state %.2f GB + scene) exceeds the 126 MB L2; no explicit flush" % (min(npix * spp, integ.max_paths_in_flight or (1 << 26)) * 276 / 1e9),
                            "scene_build_s": build_s, "scene_upload_s": upload_s},
                 "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(__import__("shimmer_b200").ffi.SgRenderParams),
-                        "d2h_bytes_per_step": npix * 32, "note": "sg_render: host film buffer, scene resident (uploaded once)"},
+                        "d2h_bytes_per_step": npix * 32, "note": "sg_render: host film buffer, scene resident (uploaded once)",
+                        "value_incl_scene_upload": paths_total / (float(e2e_t[0]) + args.steps * upload_s) / 1e6,
+                        "scene_upload_bytes": int(sc.meta.get("upload_bytes", 0))},
                 "gpu_launches": launches_total, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -49,41 +49,43 @@ SGD uint32_t f2u_sat(float f) { return __float2uint_rz(f); }                    
 struct TexView {
     const DScene& sc; const SgTexture& t;
     SGD SgImageLevel level(int l) const { return sc.image_levels[t.first_level + l]; }
-    // Image::get_channel_wrapped image.rs:452-475 + remap_pixel_coords :134-177
-    SGD float channel(const SgImageLevel& L, int x, int y, int c) const {
+    // Image::get_channel_wrapped image.rs:452-475 + remap_pixel_coords :134-177.  The wrap is evaluated ONCE per texel for
+    // all its channels (the reference redoes it per channel with the same integers): returns false for a black border texel.
+    SGD bool remap(const SgImageLevel& L, int& x, int& y) const {
         if (x < 0 || x >= L.res[0]) {
-            if (t.wrap == SG_WRAP_BLACK) return 0.0f;
+            if (t.wrap == SG_WRAP_BLACK) return false;
             x = t.wrap == SG_WRAP_CLAMP ? min(max(x, 0), L.res[0] - 1) : modulo_i(x, L.res[0]);
         }
         if (y < 0 || y >= L.res[1]) {
-            if (t.wrap == SG_WRAP_BLACK) return 0.0f;
+            if (t.wrap == SG_WRAP_BLACK) return false;
             y = t.wrap == SG_WRAP_CLAMP ? min(max(y, 0), L.res[1] - 1) : modulo_i(y, L.res[1]);
         }
-        return __ldg(sc.texels + (size_t)L.offset + ((size_t)y * L.res[0] + x) * t.n_channels + c);
+        return true;
     }
-    // Image::bilerp_channel_wrapped image.rs:619-646
-    SGD float bilerp_channel(const SgImageLevel& L, float2 st, int c) const {
+    // texel value: RGB (texel_rgb mipmap.rs:203-219) or Float replicated (texel_float :221-225)
+    template <bool RGB> SGD float3 texel(const SgImageLevel& L, int x, int y) const {
+        if (!remap(L, x, y)) return f3(0.0f, 0.0f, 0.0f);
+        const float* q = sc.texels + (size_t)L.offset + ((size_t)y * L.res[0] + x) * t.n_channels;
+        if (RGB && t.n_channels == 3) return f3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+        const float v = __ldg(q); return f3(v, v, v);
+    }
+    // Image::bilerp_channel_wrapped image.rs:619-646, all channels of the four taps at once (per-channel arithmetic unchanged)
+    template <bool RGB> SGD float3 bilerp(const SgImageLevel& L, float2 st) const {
         const float x = st.x * (float)L.res[0] - 0.5f, y = st.y * (float)L.res[1] - 0.5f;
         const int xi = f2i_sat(floorf(x)), yi = f2i_sat(floorf(y));
         const float dx = x - (float)xi, dy = y - (float)yi;
-        const float v0 = channel(L, xi, yi, c), v1 = channel(L, xi + 1, yi, c), v2 = channel(L, xi, yi + 1, c), v3 = channel(L, xi + 1, yi + 1, c);
-        return (1.0f - dx) * (1.0f - dy) * v0 + dx * (1.0f - dy) * v1 + (1.0f - dx) * dy * v2 + dx * dy * v3;
+        const float3 v0 = texel<RGB>(L, xi, yi), v1 = texel<RGB>(L, xi + 1, yi), v2 = texel<RGB>(L, xi, yi + 1), v3 = texel<RGB>(L, xi + 1, yi + 1);
+        const float w0 = (1.0f - dx) * (1.0f - dy), w1 = dx * (1.0f - dy), w2 = (1.0f - dx) * dy, w3 = dx * dy;
+        return f3(w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x, w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y,
+                  w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z);
     }
 };
 
-// texel value: RGB (texel_rgb mipmap.rs:203-219) or Float replicated (texel_float :221-225)
 SGD float3 tex_lerp(float t, float3 a, float3 b) { return a * (1.0f - t) + b * t; }
 
-template <bool RGB> SGD float3 tex_texel(const TexView& tv, int l, int x, int y) {
-    const SgImageLevel L = tv.level(l);
-    if (RGB && tv.t.n_channels == 3) return f3(tv.channel(L, x, y, 0), tv.channel(L, x, y, 1), tv.channel(L, x, y, 2));
-    const float v = tv.channel(L, x, y, 0); return f3(v, v, v);
-}
-template <bool RGB> SGD float3 tex_bilerp(const TexView& tv, int l, float2 st) {                 // mipmap.rs:298-331
-    const SgImageLevel L = tv.level(l);
-    if (RGB && tv.t.n_channels == 3) return f3(tv.bilerp_channel(L, st, 0), tv.bilerp_channel(L, st, 1), tv.bilerp_channel(L, st, 2));
-    const float v = tv.bilerp_channel(L, st, 0); return f3(v, v, v);
-}
+template <bool RGB> SGD float3 tex_texel(const TexView& tv, int l, int x, int y) { return tv.texel<RGB>(tv.level(l), x, y); }
+// one out-of-line copy per texel type: MIPMap::filter reaches it from four places and the shade kernels are I-cache bound
+template <bool RGB> __device__ __noinline__ float3 tex_bilerp(const TexView& tv, int l, float2 st) { return tv.bilerp<RGB>(tv.level(l), st); }   // mipmap.rs:298-331
 // TexelType::ewa mipmap.rs:233-293
 template <bool RGB> __device__ __noinline__ float3 tex_ewa(const TexView& tv, int l, float2 st, float2 d0, float2 d1) {
     if (l >= tv.t.n_levels) return tex_texel<RGB>(tv, tv.t.n_levels - 1, 0, 0);
@@ -109,9 +111,7 @@ template <bool RGB> __device__ __noinline__ float3 tex_ewa(const TexView& tv, in
             if (r2 < 1.0f) {
                 const uint32_t index = min(f2u_sat(r2 * 128.0f), 127u);
                 const float w = __ldg(tv.sc.mip_lut + index);
-                float3 tx;
-                if (RGB && tv.t.n_channels == 3) tx = f3(tv.channel(L, is, it, 0), tv.channel(L, is, it, 1), tv.channel(L, is, it, 2));
-                else { const float v = tv.channel(L, is, it, 0); tx = f3(v, v, v); }
+                const float3 tx = tv.texel<RGB>(L, is, it);
                 sum = sum + tx * w;
                 sum_wts += w;
             }

@@ -697,6 +697,7 @@ class SceneBuilder:
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
         d.film = self.film
         inst_tris = sum(int(obj_rows[o].n_prims) for o, _ in self.instances)
-        out.meta = dict(n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights), n_spheres=len(self.spheres),
+        upload_bytes = sum(int(getattr(v, "nbytes", 0) or (C.sizeof(v) if isinstance(v, C.Array) else 0)) for v in A.values() if v is not None)
+        out.meta = dict(upload_bytes=upload_bytes, n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights), n_spheres=len(self.spheres),
                         resolution=tuple(self.film.full_resolution), window=tuple(self.film.pixel_bounds))
         return out
