@@ -89,7 +89,7 @@ enum { SG_SCENE_FIX_INSTANCING = 1 };
  * The shape works in object space (interval arithmetic on the transformed ray, sphere.rs:95-186) and maps the hit back
  * with Transform::apply(SurfaceInteraction) -- the same routine instancing uses, so SG_SCENE_FIX_INSTANCING also selects
  * the pbrt semantics (vectors through M, normals through M^-T) for spheres.  Transforms must be affine.
- * Area lights on spheres are not on the GPU path yet (SgPrimitive.light must be -1). */
+ * An emissive sphere's SgPrimitive.light points at an SG_LIGHT_DIFFUSE_AREA_SPHERE light whose `tri` is the sphere index. */
 typedef struct SgSphere {
     float    render_from_object[16];
     float    object_from_render[16];
@@ -202,7 +202,8 @@ typedef struct SgTexture {
 typedef enum SgLightKind {
     SG_LIGHT_DIFFUSE_AREA = 0,     /* DiffuseAreaLight light.rs:524-694 over one Triangle */
     SG_LIGHT_POINT = 1,            /* PointLight light.rs:403-519                         */
-    SG_LIGHT_UNIFORM_INFINITE = 2  /* UniformInfiniteLight light.rs:697-803               */
+    SG_LIGHT_UNIFORM_INFINITE = 2, /* UniformInfiniteLight light.rs:697-803               */
+    SG_LIGHT_DIFFUSE_AREA_SPHERE = 3 /* DiffuseAreaLight over a Sphere (sphere.rs:299-457): tri = index into spheres, area = Sphere::area() */
 } SgLightKind;
 typedef struct SgLight {
     int32_t kind;

@@ -662,12 +662,96 @@ inline Float tri_pdf_with_context(const Scene& sc, uint32_t mesh_id, uint32_t tr
     }
     return pdf;
 }
+// ---- Sphere as an emitter: sphere.rs:299-457 ----
+inline Float sphere_area(const SgSphere& S) { return S.phi_max * S.radius * (S.z_max - S.z_min); }            // :295-297
+inline V3 sphere_center(const SgSphere& S) { return v3(S.render_from_object[3], S.render_from_object[7], S.render_from_object[11]); }   // apply(Point3f::ZERO)
+// Sphere::sample :299-333 (area sampling, used when the reference point is inside the sphere)
+inline void sphere_sample_area(const SgSphere& S, V2 u, ShapeSample* ss) {
+    const Float z = 1.0f - 2.0f * u.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * PI_F * u.y;             // sample_uniform_sphere sampling.rs:280-289
+    V3 p_obj = v3(0, 0, 0) + v3(r * std::cos(phi), r * std::sin(phi), z) * S.radius;
+    const Float sc_ = S.radius / length(p_obj);
+    p_obj = v3(p_obj.x * sc_, p_obj.y * sc_, p_obj.z * sc_);
+    const V3 p_err = gamma_n(5) * vabs(p_obj);
+    const float* Mi = S.object_from_render; const float* M = S.render_from_object;
+    V3 n = normalize(v3(Mi[0] * p_obj.x + Mi[4] * p_obj.y + Mi[8] * p_obj.z, Mi[1] * p_obj.x + Mi[5] * p_obj.y + Mi[9] * p_obj.z,
+                        Mi[2] * p_obj.x + Mi[6] * p_obj.y + Mi[10] * p_obj.z));                          // apply(Normal3f) transform.rs:377-383,779-786
+    if (S.flags & SG_MESH_REVERSE_ORIENTATION) n = n * -1.0f;
+    // render_from_object.apply(Point3fi::from_value_and_error(p_obj, p_err)) : transform.rs:385-457
+    const P3fi pin = p3fi_from_value_and_error(p_obj, p_err);
+    const V3 pm = p3fi_mid(pin), pe = p3fi_error(pin);
+    const bool exact = p3fi_is_exact(pin);
+    Float qa[3], ea[3];
+    for (int r_ = 0; r_ < 3; ++r_) {
+        qa[r_] = (M[4 * r_] * pm.x + M[4 * r_ + 1] * pm.y) + (M[4 * r_ + 2] * pm.z + M[4 * r_ + 3]);
+        const Float a = gamma_n(3) * (std::fabs(M[4 * r_] * pm.x) + std::fabs(M[4 * r_ + 1] * pm.y) + std::fabs(M[4 * r_ + 2] * pm.z) + std::fabs(M[4 * r_ + 3]));
+        ea[r_] = exact ? a : (gamma_n(3) + 1.0f) * (std::fabs(M[4 * r_]) * pe.x + std::fabs(M[4 * r_ + 1]) * pe.y + std::fabs(M[4 * r_ + 2]) * pe.z) + a;
+    }
+    ss->pi = p3fi_from_value_and_error(v3(qa[0], qa[1], qa[2]), v3(ea[0], ea[1], ea[2])); ss->n = n; ss->pdf = 1.0f / sphere_area(S);
+}
+// Sphere::sample_with_context :339-420
+inline bool sphere_sample_with_context(const SgSphere& S, const LightSampleContext& ctx, V2 u, ShapeSample* ss) {
+    const V3 pc = sphere_center(S), cp = ctx.p();
+    const V3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);                                        // offset_ray_origin_pt shape.rs:275-277
+    if (distance_squared(p_origin, pc) <= sqr(S.radius)) {
+        sphere_sample_area(S, u, ss);
+        V3 wi = p3fi_mid(ss->pi) - cp;
+        if (length_squared(wi) == 0.0f) return false;
+        wi = normalize(wi);
+        ss->pdf /= abs_dot(ss->n, -wi) / distance_squared(cp, p3fi_mid(ss->pi));
+        if (std::isinf(ss->pdf)) return false;
+        return true;
+    }
+    const Float sin_theta_max = S.radius / std::sqrt(distance_squared(cp, pc));
+    const Float sin2_theta_max = sqr(sin_theta_max);
+    const Float cos_theta_max = safe_sqrt(1.0f - sin2_theta_max);
+    Float one_minus_cos_theta_max = 1.0f - cos_theta_max;
+    Float cos_theta = (cos_theta_max - 1.0f) * u.x + 1.0f;
+    Float sin2_theta = 1.0f - sqr(cos_theta);
+    if (sin2_theta_max < 0.00068523f) {
+        sin2_theta = sin2_theta_max * u.x;
+        cos_theta = std::sqrt(1.0f - sin2_theta);
+        one_minus_cos_theta_max = sin2_theta_max / 2.0f;
+    }
+    const Float cos_alpha = sin2_theta / sin_theta_max + cos_theta * safe_sqrt(1.0f - sin2_theta / sqr(sin_theta_max));
+    const Float sin_alpha = safe_sqrt(1.0f - sqr(cos_alpha));
+    const Float phi = u.y * 2.0f * PI_F;
+    const V3 w = v3(clampf(sin_alpha, -1.0f, 1.0f) * std::cos(phi), clampf(sin_alpha, -1.0f, 1.0f) * std::sin(phi), clampf(cos_alpha, -1.0f, 1.0f));   // vector.rs:1024-1032
+    const V3 fz = normalize(pc - cp); V3 fx, fy; coordinate_system(fz, &fx, &fy);                        // Frame::from_z frame.rs:24-27
+    const V3 mw = -w;
+    V3 n = mw.x * fx + mw.y * fy + mw.z * fz;                                                            // from_local_v frame.rs:51-53
+    if (S.flags & SG_MESH_REVERSE_ORIENTATION) n = n * -1.0f;                                            // sic: flipped BEFORE the point is placed (:388-389)
+    const V3 p = pc + v3(n.x, n.y, n.z) * S.radius;
+    ss->pi = p3fi_from_value_and_error(p, gamma_n(5) * vabs(p)); ss->n = n;
+    ss->pdf = 1.0f / (2.0f * PI_F * one_minus_cos_theta_max);
+    return true;
+}
+// Sphere::pdf_with_context :422-456
+inline Float sphere_pdf_with_context(const SgSceneDesc* D, const SgSphere& S, const LightSampleContext& ctx, V3 wi) {
+    const V3 pc = sphere_center(S), cp = ctx.p();
+    const V3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);
+    if (distance_squared(p_origin, pc) <= S.radius * S.radius) {
+        Ray ray; ray.o = offset_ray_origin(ctx.pi, ctx.n, wi); ray.d = wi;
+        QuadricHit q;
+        if (!sphere_basic_intersect(S, ray, F_INF, &q)) return 0.0f;
+        const SurfaceInteraction isect = sphere_interaction(D, S, q.p_obj, q.phi, -wi);
+        const Float pdf = (1.0f / sphere_area(S)) / abs_dot(isect.n, -wi) / distance_squared(cp, isect.p());   // sic: (a / b) / c, :436-438
+        if (std::isinf(pdf)) return 0.0f;
+        return pdf;
+    }
+    const Float sin2_theta_max = S.radius * S.radius / distance_squared(cp, pc);
+    const Float cos_theta_max = safe_sqrt(1.0f - sin2_theta_max);
+    Float one_minus_cos_theta_max = 1.0f - cos_theta_max;
+    if (sin2_theta_max < 0.00068523f) one_minus_cos_theta_max = sin2_theta_max / 2.0f;
+    return 1.0f / (2.90f * PI_F * one_minus_cos_theta_max);                                              // sic: 2.90, :455
+}
+
 // Light::sample_li with allow_incomplete_pdf = true (integrator.rs:933): light.rs:632-661, :461-484, :742-768
 inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V2 u, const Wavelengths& lambda, LightLiSample* ls) {
     const SgSceneDesc* D = sc.d;
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA) {
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {
         ShapeSample ss;
-        if (!tri_sample_with_context(sc, lt.mesh, lt.tri, ctx, u, &ss)) return false;
+        if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) { if (!sphere_sample_with_context(D->spheres[lt.tri], ctx, u, &ss)) return false; }
+        else if (!tri_sample_with_context(sc, lt.mesh, lt.tri, ctx, u, &ss)) return false;
         V3 sp = p3fi_mid(ss.pi);
         if (ss.pdf == 0.0f || length_squared(sp - ctx.p()) == 0.0f) return false;
         V3 wi = normalize(sp - ctx.p());
@@ -686,6 +770,7 @@ inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampl
 }
 inline Float light_pdf_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V3 wi) {   // allow_incomplete_pdf = true
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, lt.mesh, lt.tri, ctx, wi);     // light.rs:663-666
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc.d, sc.d->spheres[lt.tri], ctx, wi);
     return 0.0f;                                                                                       // :486-494, :770-781
 }
 

@@ -2,6 +2,7 @@
 // perspective camera and film accumulation.  Each function cites the reference routine
 // (paths relative to /root/reference/src) whose arithmetic it reproduces.
 #pragma once
+#include "sg_sphere.cuh"
 #include "sg_scene.cuh"
 
 namespace sg {
@@ -697,12 +698,18 @@ SGD float tri_pdf_with_context(const DScene& sc, const TriGeo& g, const LightCtx
     }
     return pdf;
 }
+// Sphere emitters (sphere.rs:299-457): defined in sg_sphere_surface.cuh (they need the sphere's SurfaceInteraction)
+__device__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf);
+__device__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi);
 // Light::sample_li with allow_incomplete_pdf = true (integrator.rs:933)
 SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls) {
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA) {                                  // light.rs:632-661
-        const TriGeo g = geo_from_light(sc, light_id, lt);
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {   // light.rs:632-661
         P3fi pi; float3 n; float pdf;
-        if (!tri_sample_with_context(sc, g, ctx, u, pi, n, pdf)) return false;
+        if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) { if (!sphere_sample_with_context(sc.spheres[lt.tri], ctx, u, pi, n, pdf)) return false; }
+        else {
+            const TriGeo g = geo_from_light(sc, light_id, lt);
+            if (!tri_sample_with_context(sc, g, ctx, u, pi, n, pdf)) return false;
+        }
         float3 sp = p3fi_mid(pi), cp = p3fi_mid(ctx.pi);
         if (pdf == 0.0f || len2(sp - cp) == 0.0f) return false;
         float3 wi = normalize3(sp - cp);
@@ -721,6 +728,7 @@ SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt,
 }
 SGD float light_pdf_li(const DScene& sc, const SgLight& lt, const TriGeo& g, const LightCtx& ctx, float3 wi) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, g, ctx, wi);                   // light.rs:663-666
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc, sc.spheres[lt.tri], ctx, wi);
     return 0.0f;                                                             // :486-494, :770-781 (allow_incomplete_pdf)
 }
 

@@ -40,4 +40,87 @@ SGD Surf make_surface_sphere(const DSphere& S, float3 p_hit, SurfTex* x) {
     return s;
 }
 
+// ---- Sphere as an emitter: sphere.rs:295-457 ----
+SGD float sphere_area(const DSphere& S) { return S.phi_max * S.radius * (S.z_max - S.z_min); }
+SGD float3 sphere_center(const DSphere& S) { return f3(S.m[3], S.m[7], S.m[11]); }                           // render_from_object.apply(Point3f::ZERO)
+// Sphere::sample_with_context :339-420 (inside: Sphere::sample :299-333 + area -> solid angle; outside: cone sampling)
+__device__ __noinline__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf) {
+    const float3 pc = sphere_center(S), cp = p3fi_mid(ctx.pi);
+    const float3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);
+    if (dist2(p_origin, pc) <= sqr(S.radius)) {
+        const float z = 1.0f - 2.0f * u.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * kPi * u.y;            // sample_uniform_sphere sampling.rs:280-289
+        float3 p_obj = f3(0.0f, 0.0f, 0.0f) + f3(r * cosf(phi), r * sinf(phi), z) * S.radius;
+        const float sc_ = S.radius / len3(p_obj);
+        p_obj = f3(p_obj.x * sc_, p_obj.y * sc_, p_obj.z * sc_);
+        const float* Mi = S.mi; const float* M = S.m;
+        float3 n = normalize3(f3(Mi[0] * p_obj.x + Mi[4] * p_obj.y + Mi[8] * p_obj.z, Mi[1] * p_obj.x + Mi[5] * p_obj.y + Mi[9] * p_obj.z,
+                                 Mi[2] * p_obj.x + Mi[6] * p_obj.y + Mi[10] * p_obj.z));
+        if (S.flags & SG_MESH_REVERSE_ORIENTATION) n = n * -1.0f;
+        const P3fi pin = p3fi_make(p_obj, gamma_n(5) * abs3(p_obj));
+        const float3 pm = p3fi_mid(pin), pe = p3fi_err(pin);
+        const bool exact = pin.lo.x == pin.hi.x && pin.lo.y == pin.hi.y && pin.lo.z == pin.hi.z;              // is_exact: zero width
+        float qa[3], ea[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            qa[k] = (M[4 * k] * pm.x + M[4 * k + 1] * pm.y) + (M[4 * k + 2] * pm.z + M[4 * k + 3]);
+            const float a = gamma_n(3) * (fabsf(M[4 * k] * pm.x) + fabsf(M[4 * k + 1] * pm.y) + fabsf(M[4 * k + 2] * pm.z) + fabsf(M[4 * k + 3]));
+            ea[k] = exact ? a : (gamma_n(3) + 1.0f) * (fabsf(M[4 * k]) * pe.x + fabsf(M[4 * k + 1]) * pe.y + fabsf(M[4 * k + 2]) * pe.z) + a;
+        }
+        out_pi = p3fi_make(f3(qa[0], qa[1], qa[2]), f3(ea[0], ea[1], ea[2])); out_n = n;
+        float pdf = 1.0f / sphere_area(S);
+        const float3 sp = p3fi_mid(out_pi);
+        float3 wi = sp - cp;
+        if (len2(wi) == 0.0f) return false;
+        wi = normalize3(wi);
+        pdf /= absdot3(n, -wi) / dist2(cp, sp);
+        if (isinf(pdf)) return false;
+        out_pdf = pdf;
+        return true;
+    }
+    const float sin_theta_max = S.radius / sqrtf(dist2(cp, pc));
+    const float sin2_theta_max = sqr(sin_theta_max);
+    const float cos_theta_max = safe_sqrt(1.0f - sin2_theta_max);
+    float one_minus_cos_theta_max = 1.0f - cos_theta_max;
+    float cos_theta = (cos_theta_max - 1.0f) * u.x + 1.0f;
+    float sin2_theta = 1.0f - sqr(cos_theta);
+    if (sin2_theta_max < 0.00068523f) {
+        sin2_theta = sin2_theta_max * u.x;
+        cos_theta = sqrtf(1.0f - sin2_theta);
+        one_minus_cos_theta_max = sin2_theta_max / 2.0f;
+    }
+    const float cos_alpha = sin2_theta / sin_theta_max + cos_theta * safe_sqrt(1.0f - sin2_theta / sqr(sin_theta_max));
+    const float sin_alpha = safe_sqrt(1.0f - sqr(cos_alpha));
+    const float phi = u.y * 2.0f * kPi;
+    const float3 w = f3(clampf(sin_alpha, -1.0f, 1.0f) * cosf(phi), clampf(sin_alpha, -1.0f, 1.0f) * sinf(phi), clampf(cos_alpha, -1.0f, 1.0f));
+    const float3 fz = normalize3(pc - cp); float3 fx, fy; coord_system(fz, fx, fy);                             // Frame::from_z
+    const float3 mw = -w;
+    float3 n = mw.x * fx + mw.y * fy + mw.z * fz;
+    if (S.flags & SG_MESH_REVERSE_ORIENTATION) n = n * -1.0f;                                                    // sic: before the point is placed
+    const float3 p = pc + f3(n.x, n.y, n.z) * S.radius;
+    out_pi = p3fi_make(p, gamma_n(5) * abs3(p)); out_n = n;
+    out_pdf = 1.0f / (2.0f * kPi * one_minus_cos_theta_max);
+    return true;
+}
+// Sphere::pdf_with_context :422-456
+__device__ __noinline__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi) {
+    const float3 pc = sphere_center(S), cp = p3fi_mid(ctx.pi);
+    const float3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);
+    if (dist2(p_origin, pc) <= S.radius * S.radius) {
+        const float3 o = offset_ray_origin(ctx.pi, ctx.n, wi);
+        float3 p_obj; float t;
+        if (!sphere_basic_intersect(S, o, wi, INFINITY, p_obj, t)) return 0.0f;
+        Surf s = make_surface_sphere<false>(S, p_obj, nullptr);
+        float3 wo_si;
+        transform_interaction<false>(sc, S.m, S.mi, wi, s, nullptr, wo_si);
+        const float pdf = (1.0f / sphere_area(S)) / absdot3(s.n, -wi) / dist2(cp, p3fi_mid(s.pi));               // sic: (a / b) / c
+        if (isinf(pdf)) return 0.0f;
+        return pdf;
+    }
+    const float sin2_theta_max = S.radius * S.radius / dist2(cp, pc);
+    const float cos_theta_max = safe_sqrt(1.0f - sin2_theta_max);
+    float one_minus_cos_theta_max = 1.0f - cos_theta_max;
+    if (sin2_theta_max < 0.00068523f) one_minus_cos_theta_max = sin2_theta_max / 2.0f;
+    return 1.0f / (2.90f * kPi * one_minus_cos_theta_max);                                                      // sic: 2.90
+}
+
 }  // namespace sg

@@ -163,7 +163,8 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (p.mesh == SG_PRIM_SPHERE) {
             if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "spheres inside object definitions are not on the GPU path yet");
             if (p.tri >= desc->n_spheres || p.material >= desc->n_materials) return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references an out-of-range sphere/material");
-            if (p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights on spheres are not on the GPU path yet");
+            if (p.light >= (int32_t)desc->n_lights || (p.light >= 0 && (desc->lights[p.light].kind != SG_LIGHT_DIFFUSE_AREA_SPHERE || desc->lights[p.light].tri != p.tri)))
+                return fail(SG_ERR_INVALID_ARGUMENT, "an emissive sphere must point at an SG_LIGHT_DIFFUSE_AREA_SPHERE light over that sphere");
             const SgSphere& sp = desc->spheres[p.tri];
             const float* r3 = sp.render_from_object + 12; const float* q3 = sp.object_from_render + 12;
             if (r3[0] != 0.0f || r3[1] != 0.0f || r3[2] != 0.0f || r3[3] != 1.0f || q3[0] != 0.0f || q3[1] != 0.0f || q3[2] != 0.0f || q3[3] != 1.0f)
@@ -184,6 +185,11 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     }
     for (uint32_t i = 0; i < desc->n_instances; ++i)
         if (desc->instances[i].object >= desc->n_objects) return fail(SG_ERR_INVALID_ARGUMENT, "instance " + std::to_string(i) + " references an out-of-range object");
+    for (uint32_t i = 0; i < desc->n_lights; ++i) {
+        const SgLight& L = desc->lights[i];
+        if (L.kind < SG_LIGHT_DIFFUSE_AREA || L.kind > SG_LIGHT_DIFFUSE_AREA_SPHERE) return fail(SG_ERR_UNSUPPORTED, "light kind " + std::to_string(L.kind) + " is not on the GPU path");
+        if (L.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE && L.tri >= desc->n_spheres) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + " references an out-of-range sphere");
+    }
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
         if (m.kind < 0 || m.kind > SG_MATERIAL_COATED_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");

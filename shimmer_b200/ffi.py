@@ -20,7 +20,7 @@ SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
 SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
 SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE = 0, 1, 2, 3
 SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
-SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE = 0, 1, 2
+SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE, SG_LIGHT_DIFFUSE_AREA_SPHERE = 0, 1, 2, 3
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
 SG_OPT_DISABLE_TEXTURE_FILTERING, SG_OPT_FORCE_DIFFUSE = 4, 8
 SG_RENDER_COUNT_VISITS, SG_RENDER_TIME_KERNELS, SG_RENDER_OVERWRITE_FILM = 1, 2, 4

@@ -433,9 +433,11 @@ class SceneBuilder:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
-    def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False):
+    def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False,
+                   area_light=None):
         """Shape "sphere": Sphere::create / Sphere::new (shape/sphere.rs:48-92).  `object_from_world` is the CTM
-        (render_from_object = render_from_world * CTM).  Top-level, non-emissive spheres only."""
+        (render_from_object = render_from_world * CTM).  Top-level spheres only.  `area_light` = dict(L=spectrum tuple,
+        scale=float, two_sided=bool) -> one DiffuseAreaLight over the sphere (scene.rs:609-622)."""
         ctm = object_from_world if object_from_world is not None else Transform.identity()
         rfo = self.render_from_world * ctm
         r = f32(radius)
@@ -447,7 +449,7 @@ class SceneBuilder:
                                  theta_z_min=f32(np.arccos(clamp(zlo / r, f32(-1.0), f32(1.0)))),
                                  theta_z_max=f32(np.arccos(clamp(zhi / r, f32(-1.0), f32(1.0)))),
                                  phi_max=f32(f32(np.pi) / f32(180.0)) * clamp(f32(phi_max), f32(0.0), f32(360.0)),
-                                 flags=flags, material=material))
+                                 flags=flags, material=material, area_light=area_light))
         return len(self.spheres) - 1
 
     def add_point_light(self, pos, I, scale=1.0):
@@ -517,6 +519,20 @@ class SceneBuilder:
                 L.two_sided = 1 if al.get("two_sided", False) else 0
                 L.mesh, L.tri, L.area = mi, t, float(area[t])
                 lights.append(L)
+        sphere_light = {}
+        for si_, sp in enumerate(self.spheres):                       # spheres follow the meshes in shape order
+            al = sp.get("area_light")
+            if al is None:
+                continue
+            sc = f32(al.get("scale", 1.0)) / spectrum_to_photometric(al["L"])
+            dense = spectrum_dense(al["L"])
+            r = ffi.SgSpectrum(); r.kind, r.n, r.lambda_min, r.off_a = ffi.SG_SPECTRUM_DENSE, len(dense), LAMBDA_MIN, off
+            pool.append(dense); off += len(dense); recs.append(r)
+            L = ffi.SgLight(); L.kind = ffi.SG_LIGHT_DIFFUSE_AREA_SPHERE; L.spectrum = len(recs) - 1; L.scale = float(sc)
+            L.two_sided = 1 if al.get("two_sided", False) else 0
+            L.mesh, L.tri = 0, si_
+            L.area = float(f32(sp["phi_max"]) * f32(sp["radius"]) * (f32(sp["z_max"]) - f32(sp["z_min"])))       # Sphere::area sphere.rs:295-297
+            sphere_light[si_] = len(lights); lights.append(L)
         # geometry arrays
         any_n = any(m["n"] is not None for m in self.meshes)
         any_uv = any(m["uv"] is not None for m in self.meshes)
@@ -601,7 +617,8 @@ class SceneBuilder:
         top_prim_in = prim_in[top_sel]
         if len(self.spheres):
             sp_in = np.zeros((len(self.spheres), 4), np.int64)
-            sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]; sp_in[:, 3] = -1
+            sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]
+            sp_in[:, 3] = [sphere_light.get(i, -1) for i in range(len(self.spheres))]
             top_prim_in = np.concatenate([top_prim_in, sp_in]); top_bounds = np.concatenate([top_bounds, sph_bounds])
         if len(self.instances):
             top_bounds = np.concatenate([top_bounds, inst_bounds])

@@ -265,7 +265,7 @@ def instanced_scene(n_theta=224, n_phi=224, grid=10, resolution=(1920, 1080), cr
     return b
 
 
-SPHERE_KINDS = ("spheres", "spherestex")
+SPHERE_KINDS = ("spheres", "spherestex", "spherelight")
 
 
 def sphere_tiny_scene(kind="spheres", resolution=(32, 32), fix=False):
@@ -277,6 +277,21 @@ def sphere_tiny_scene(kind="spheres", resolution=(32, 32), fix=False):
     b.fix_instancing = fix
     b.set_camera(pos=(0.0, 1.5, -4.5), look=(0.0, 0.6, 0.0), up=(0, 1, 0), fov=42.0, resolution=resolution)
     white = b.diffuse(_white())
+    if kind == "spherelight":
+        # emissive spheres (sphere.rs:339-456): a small bright one seen from outside (cone sampling, the 2.90 pdf), a partial
+        # one, and a large dim two-sided shell around the whole scene (reference point INSIDE: area sampling + pdf by intersection)
+        b.add_sphere(0.6, b.diffuse(_green()), object_from_world=Transform.translate((-1.0, 0.6, 0.3)))
+        b.add_sphere(0.5, b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.15),
+                     object_from_world=Transform.translate((0.9, 0.5, -0.3)))
+        b.add_sphere(0.25, white, object_from_world=Transform.translate((0.2, 2.2, 0.4)),
+                     area_light=dict(L=named_spectrum("stdillum-D65"), scale=60.0, two_sided=False))
+        b.add_sphere(0.2, white, z_min=-0.1, z_max=0.2, phi_max=270.0, object_from_world=Transform.translate((-1.6, 1.4, -0.8)) * Transform.rotate(40.0, (0, 1, 0)),
+                     area_light=dict(L=named_spectrum("stdillum-D65"), scale=25.0, two_sided=True))
+        b.add_sphere(9.0, white, object_from_world=Transform.translate((0.0, 1.0, 0.0)),
+                     area_light=dict(L=named_spectrum("stdillum-D65"), scale=0.15, two_sided=True))
+        gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+        b.add_mesh(gp, gi, white)
+        return b
     if kind == "spherestex":
         m0 = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="trilinear", su=4.0, sv=2.0))
         m2 = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="ewa", su=3.0, sv=3.0),

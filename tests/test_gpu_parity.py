@@ -383,9 +383,19 @@ def test_sphere_validation_errors():
     import ctypes as C
     b = _sphere_only([0.0]); sc = b.build()
     lib = ffi.load_library(); h = C.c_void_p()
-    prims = sc.arrays["prims"].copy(); prims["light"][0] = 0
+    prims = sc.arrays["prims"].copy(); prims["light"][0] = 0                      # no such light
     bad = ffi.SgSceneDesc.from_buffer_copy(sc.desc); bad.primitives = prims.ctypes.data_as(C.POINTER(ffi.SgPrimitive))
-    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) != 0 and b"spheres" in lib.sg_last_error()
+    assert lib.sg_scene_create(C.byref(bad), C.byref(h)) != 0 and b"sphere" in lib.sg_last_error()
     prims = sc.arrays["prims"].copy(); prims["tri"][0] = 7
     bad = ffi.SgSceneDesc.from_buffer_copy(sc.desc); bad.primitives = prims.ctypes.data_as(C.POINTER(ffi.SgPrimitive))
     assert lib.sg_scene_create(C.byref(bad), C.byref(h)) != 0
+
+
+def test_reference_sphere_predicates_on_gpu():
+    """shape.rs:299-342 (`sphere_basic`, `sphere_partial_basic`) through sg_trace(any_hit)."""
+    from test_oracle_sphere import REF_SPHERE_PREDICATES, _unit_sphere_world
+    for zmin, zmax, o, d, want in REF_SPHERE_PREDICATES:
+        integ = create_integrator("wavefront", {}, _unit_sphere_world(zmin, zmax))
+        h = integ.trace(np.array([o], np.float32), np.array([d], np.float32), [np.inf], any_hit=True)
+        assert (h["prim"][0] >= 0) == want, (zmin, zmax, o, d)
+        integ.close()

@@ -90,3 +90,69 @@ def test_sphere_scene_renders_and_modes_agree():
         b, _, _ = orc.render(sc, orc.make_params(seed=1, spp=64), stream_mode=1)
         assert np.isfinite(a).all() and a[:, :3].sum() > 0 and st.closest_hit_rays > 24 * 24 * 64
         assert abs(a[:, :3].sum() - b[:, :3].sum()) / b[:, :3].sum() < 0.05
+
+
+def _unit_sphere_world(z_min=None, z_max=None):
+    """Sphere::new(Transform::default(), Transform::default(), false, 1, zmin, zmax, 360) exactly: rendering space
+    "world" makes render_from_object the identity like in the reference's shape tests."""
+    b = SceneBuilder(rendering_space="world"); b.set_camera((0, 0, -20), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+    b.add_sphere(1.0, b.diffuse(("const", 0.5)), z_min=z_min, z_max=z_max)
+    assert np.array_equal(b.render_from_world.m, np.eye(4))
+    return b.build()
+
+
+REF_SPHERE_PREDICATES = [   # (zmin, zmax, origin, direction, expected)  -- shape/shape.rs:299-342
+    (None, None, (0, 0, -2), (0, 0, 1), True), (None, None, (0, 0, -2), (0, 0, -1), False), (None, None, (0, 1.0001, -2), (0, 0, 1), False),
+    (-0.5, 0.5, (0, -2, 0), (0, 1, 0), True), (-0.5, 0.5, (0, -2, 0), (0, -1, 0), False),
+    (-0.5, 0.5, (0, 0, 0.5001), (0, 1, 0), False), (-0.5, 0.5, (0, 0, -0.5001), (0, 1, 0), False)]
+
+
+def test_reference_sphere_basic_and_partial_predicates():
+    """shape.rs `sphere_basic` / `sphere_partial_basic`: intersect_predicate of the unit sphere (full, and clipped to
+    |z| <= 0.5) for the seven rays the reference asserts."""
+    for zmin, zmax, o, d, want in REF_SPHERE_PREDICATES:
+        sc = _unit_sphere_world(zmin, zmax)
+        h, _ = orc.trace(sc, np.array([o], np.float32), np.array([d], np.float32), [np.inf], any_hit=True)
+        assert (h["prim"][0] >= 0) == want, (zmin, zmax, o, d)
+
+
+def test_sphere_light_sampling_is_self_consistent():
+    """Sphere::sample_with_context / pdf_with_context (sphere.rs:339-456) through the light interface.  Outside the sphere:
+    the sample lies on the sphere, inside the subtended cone, with the cone pdf 1/(2 pi (1 - cos theta_max)); pdf_li returns
+    that pdf times 2/2.90 (the reference's constant, :455); the cone pdf integrates to 1 (Monte Carlo).  Inside the sphere
+    (the big shell): area sampling, pdf = dist^2 / (area |cos|); pdf_li is ((1/area)/|cos|)/dist^2 as written (:436-438)."""
+    import ctypes as C
+    b = scenes.sphere_tiny_scene("spherelight"); sc = b.build()
+    L = orc.lib(); rng = np.random.default_rng(2)
+    lights = sc.arrays["lights"]; spheres = sc.arrays["spheres"]
+    lam = orc.fa([450, 520, 600, 680]); out = np.zeros(14, np.float32)
+    small = [i for i in range(sc.meta["n_lights"]) if spheres[lights[i].tri].radius < 1.0 and spheres[lights[i].tri].phi_max > 6.0][0]
+    shell = [i for i in range(sc.meta["n_lights"]) if spheres[lights[i].tri].radius > 5.0][0]
+    S = spheres[lights[small].tri]; centre = np.array([S.render_from_object[3], S.render_from_object[7], S.render_from_object[11]], np.float64)
+    p = (centre + np.array([1.1, -1.7, 0.6])).astype(np.float32); n = orc.fa([0, 1, 0])
+    dist = np.linalg.norm(p - centre); cos_max = np.sqrt(1 - (S.radius / dist) ** 2); cone_pdf = 1 / (2 * np.pi * (1 - cos_max))
+    for _ in range(200):
+        u = orc.fa(rng.random(2))
+        assert L.orc_light_sample(sc.ptr(), small, p.ctypes.data, n.ctypes.data, n.ctypes.data, u.ctypes.data, lam.ctypes.data, out.ctypes.data) == 1
+        wi, pdf, pl = out[4:7].astype(np.float64), out[7], out[8:11].astype(np.float64)
+        assert abs(np.linalg.norm(pl - centre) - S.radius) < 1e-5 and abs(pdf - cone_pdf) < 1e-4 * cone_pdf
+        assert np.dot(wi, (centre - p) / dist) >= cos_max - 1e-5                       # inside the cone
+        p2 = L.orc_light_pdf(sc.ptr(), small, p.ctypes.data, n.ctypes.data, n.ctypes.data, orc.fa(wi).ctypes.data)
+        assert abs(p2 - pdf * 2.0 / 2.90) < 1e-4 * pdf
+    # inside the shell
+    S = spheres[lights[shell].tri]; centre = np.array([S.render_from_object[3], S.render_from_object[7], S.render_from_object[11]], np.float64)
+    area = S.phi_max * S.radius * (S.z_max - S.z_min)
+    assert abs(area - 4 * np.pi * S.radius ** 2) < 1e-3 * area and abs(lights[shell].area - area) < 1e-3 * area
+    p = (centre + np.array([0.5, -0.3, 1.0])).astype(np.float32)
+    acc = 0.0; cnt = 0
+    for _ in range(2000):
+        u = orc.fa(rng.random(2))
+        if L.orc_light_sample(sc.ptr(), shell, p.ctypes.data, n.ctypes.data, n.ctypes.data, u.ctypes.data, lam.ctypes.data, out.ctypes.data) != 1:
+            continue
+        wi, pdf, pl, nl = out[4:7].astype(np.float64), out[7], out[8:11].astype(np.float64), out[11:14].astype(np.float64)
+        d2 = np.sum((pl - p) ** 2); cosl = abs(np.dot(nl, -wi))
+        assert abs(np.linalg.norm(pl - centre) - S.radius) < 1e-4 and abs(pdf - d2 / (area * cosl)) < 2e-3 * pdf
+        p2 = L.orc_light_pdf(sc.ptr(), shell, p.ctypes.data, n.ctypes.data, n.ctypes.data, orc.fa(wi).ctypes.data)
+        assert abs(p2 - (1 / area) / cosl / d2) < 5e-3 * p2
+        acc += 1.0 / pdf; cnt += 1
+    assert cnt > 1900 and abs(acc / cnt - 4 * np.pi) < 0.05 * 4 * np.pi             # solid-angle pdf integrates over the full sphere of directions
