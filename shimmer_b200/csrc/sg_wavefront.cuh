@@ -426,14 +426,50 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
     const uint32_t* queue = q.shade[qk];
     uint32_t* q_next = q.ray[(depth + 1) & 1];
     const int lane = threadIdx.x & 31;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
-        const uint32_t i = base + lane;
+    // Work distribution: a CTA takes chunks of 128 x ITEMS queue entries.  Textured scenes (ITEMS = 8) first sort the chunk by
+    // material in shared memory (counting sort over 64 hash buckets), so that the 32 lanes of a warp run the same texture
+    // filter and bump-map code: shade queues are binned by material KIND only, and a warp of mixed EWA / bilinear / untextured
+    // lanes runs at a few active lanes per instruction.  Nothing in the result depends on the processing order.
+    constexpr int ITEMS = TEX ? 8 : 1;
+    constexpr uint32_t kChunk = 128u * ITEMS;
+    __shared__ uint32_t s_sorted[TEX ? 1024 : 1];
+    __shared__ uint32_t s_hist[64], s_off[64];
+    for (uint32_t chunk = blockIdx.x * kChunk; chunk < n; chunk += gridDim.x * kChunk) {
+      if constexpr (TEX) {
+        if (threadIdx.x < 64) s_hist[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t e_path[ITEMS], e_slot[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t i = chunk + k * 128u + threadIdx.x;
+            e_slot[k] = 0xffffffffu; e_path[k] = 0u;
+            if (i < n) {
+                e_path[k] = queue[i];
+                const uint32_t mat = __float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)st.hit_prim[e_path[k]]).w) & 0x7fffffu;
+                const uint32_t bucket = (mat ^ (mat >> 6)) & 63u;
+                e_slot[k] = (bucket << 16) | atomicAdd(&s_hist[bucket], 1u);          // rank inside the bucket (chunk <= 1024 entries)
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                                                      // exclusive scan of the 64 bucket counts
+            const uint32_t a = s_hist[2 * lane], b = s_hist[2 * lane + 1];
+            uint32_t incl = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            s_off[2 * lane] = incl - a - b; s_off[2 * lane + 1] = incl - b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) if (e_slot[k] != 0xffffffffu) s_sorted[s_off[e_slot[k] >> 16] + (e_slot[k] & 0xffffu)] = e_path[k];
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int it = 0; it < ITEMS; ++it) {
+        const uint32_t i = chunk + it * 128u + threadIdx.x;
         bool want_shadow = false, want_next = false;
         uint32_t path = 0;
         if (i < n) {
-            path = queue[i];
+            path = TEX ? s_sorted[it * 128u + threadIdx.x] : queue[i];
             const float4 rd4 = st.ray_d[path];
             const float3 rd = f3(rd4.x, rd4.y, rd4.z);
             const float3 wo = -rd;
@@ -636,6 +672,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 if (want_next) q_next[qb + __popc(mask & ((1u << lane) - 1u))] = path;
             }
         }
+      }
+      if constexpr (TEX) __syncthreads();                                            // s_sorted / s_hist are reused by the next chunk
     }
 }
 

@@ -399,3 +399,47 @@ def test_reference_sphere_predicates_on_gpu():
         h = integ.trace(np.array([o], np.float32), np.array([d], np.float32), [np.inf], any_hit=True)
         assert (h["prim"][0] >= 0) == want, (zmin, zmax, o, d)
         integ.close()
+
+
+# ---- BASELINE.json's full sizes ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mesh1m", "instanced"])
+def test_fullsize_raycast_parity(name):
+    """SURVEY 8d ray-cast parity set at the FULL C2 (1.0 M triangles) and C4 (10 M instanced triangles, fixed-instancing
+    mode) scenes: 2^20 rays, first-hit primitive / instance, t, barycentrics bit-exact; visit counters equal the oracle's."""
+    sc = scenes.CONFIGS[name]["builder"](resolution=(64, 64)).build()
+    integ = create_integrator("wavefront", {}, sc)
+    n = 1 << 20
+    o, d = _ray_set(sc, n, seed=7)
+    tmax = np.full(n, np.inf, np.float32)
+    got, gst = integ.trace(o, d, tmax, want_stats=True)
+    ref, rst = orc.trace(sc, o, d, tmax)
+    assert _assert_hits_equal(got, ref) == 4
+    assert gst.nodes_visited == rst.nodes_visited and gst.tris_tested == rst.tris_tested
+    assert (ref["prim"] >= 0).mean() > 0.2
+    any_g = integ.trace(o, (d * np.float32(5.0)).astype(np.float32), np.full(n, np.float32(0.9999)), any_hit=True)
+    any_r, _ = orc.trace(sc, o, (d * np.float32(5.0)).astype(np.float32), np.full(n, np.float32(0.9999)), any_hit=True)
+    assert np.array_equal(any_g["prim"], any_r["prim"])
+    integ.close()
+
+
+def test_fullsize_film_properties():
+    """C2 at its full configuration (1024x1024, 64 spp): size-independent film properties -- every pixel's weight sum is
+    exactly spp, the two halves of the sample range add up to the full render (the multi-GPU decomposition), and a 48x48
+    window agrees with the oracle rendered on that window at full spp."""
+    import torch
+    cfg = scenes.CONFIGS["mesh1m"]; W, H = cfg["resolution"]; spp = cfg["spp"]
+    sc = cfg["builder"](resolution=(W, H)).build()
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": spp})
+    opts = Options(seed=0, pixel_samples=spp)
+    full = torch.zeros((W * H, 4), dtype=torch.float64, device="cuda"); halves = torch.zeros_like(full)
+    integ.render_device(opts, full.data_ptr())
+    integ.render_device(opts, halves.data_ptr(), sample_range=(0, spp // 2)); integ.render_device(opts, halves.data_ptr(), sample_range=(spp // 2, spp))
+    torch.cuda.synchronize()
+    assert bool((full[:, 3] == spp).all())
+    assert torch.allclose(full, halves, rtol=1e-9, atol=1e-12)
+    x0, y0, c = 488, 560, 48
+    scc = cfg["builder"](resolution=(W, H), crop=(x0, y0, x0 + c, y0 + c)).build()
+    ref, _, _ = orc.render(scc, orc.make_params(seed=0, spp=spp))
+    win = full.cpu().numpy().reshape(H, W, 4)[y0:y0 + c, x0:x0 + c].reshape(-1, 4)
+    _film_close(win, ref, frac=0.995)
+    integ.close()
