@@ -104,7 +104,9 @@ typedef struct SgSphere {
  * [first_index, first_index+3*n_triangles) hold MESH-LOCAL vertex numbers. */
 enum {
     SG_MESH_HAS_N = 1, SG_MESH_HAS_UV = 2, SG_MESH_HAS_S = 4,
-    SG_MESH_REVERSE_ORIENTATION = 8, SG_MESH_SWAPS_HANDEDNESS = 16
+    SG_MESH_REVERSE_ORIENTATION = 8, SG_MESH_SWAPS_HANDEDNESS = 16,
+    SG_MESH_BILINEAR = 32   /* `BilinearPatchMesh` (mesh.rs:98-175): FOUR indices per patch (p00, p10, p01, p11; bilinear_patch.rs:87-106),
+                               n_triangles = number of patches, SgPrimitive.tri = patch index.  Top-level, non-emissive patches only. */
 };
 typedef struct SgMesh {
     uint32_t first_index;

@@ -111,6 +111,16 @@ struct Scene {
         const uint32_t* ix = d->indices + m.first_index + 3 * (size_t)tri;
         v[0] = ix[0]; v[1] = ix[1]; v[2] = ix[2];
     }
+    inline void patch_indices(uint32_t mesh, uint32_t patch, uint32_t v[4]) const {      // bilinear_patch.rs:87-106
+        const SgMesh& m = d->meshes[mesh];
+        const uint32_t* ix = d->indices + m.first_index + 4 * (size_t)patch;
+        v[0] = ix[0]; v[1] = ix[1]; v[2] = ix[2]; v[3] = ix[3];
+    }
+    inline void patch_points(uint32_t mesh, uint32_t patch, V3 q[4]) const {            // p00, p10, p01, p11
+        uint32_t v[4]; patch_indices(mesh, patch, v);
+        const SgMesh& m = d->meshes[mesh];
+        for (int k = 0; k < 4; ++k) q[k] = vertex(m, v[k]);
+    }
     inline void tri_points(uint32_t mesh, uint32_t tri, V3* p0, V3* p1, V3* p2) const {   // triangle.rs:148-159
         uint32_t v[3]; tri_indices(mesh, tri, v);
         const SgMesh& m = d->meshes[mesh];
@@ -121,6 +131,7 @@ struct Scene {
 struct Hit { int32_t prim; int32_t inst; TriHit th; };   // sphere hits: th.b0..b2 = QuadricIntersection::p_obj, th.t = t_hit
 }  // namespace orc
 #include "orc_sphere.h"
+#include "orc_patch.h"
 namespace orc {
 
 // Transform::apply_ray_inverse transform.rs:701-723 (inverse = true) / Transform::apply_ray :515-532 (inverse = false)
@@ -179,6 +190,14 @@ inline bool primitive_intersect(const Scene& sc, uint32_t pi, const Ray& ray, Fl
         if (!sphere_basic_intersect(D->spheres[pr.tri], ray, t_max, &q)) return false;
         h->prim = (int32_t)pi; h->inst = -1;
         h->th.t = q.t; h->th.b0 = q.p_obj.x; h->th.b1 = q.p_obj.y; h->th.b2 = q.p_obj.z;
+        return true;
+    }
+    if (D->meshes[pr.mesh].flags & SG_MESH_BILINEAR) {        // Shape::BilinearPatch: th.b0 = u, th.b1 = v
+        V3 q[4]; sc.patch_points(pr.mesh, pr.tri, q);
+        if (ctr) ctr->tris++;
+        Float u, v, t;
+        if (!intersect_blp(ray.o, ray.d, t_max, q[0], q[1], q[2], q[3], &u, &v, &t)) return false;
+        h->prim = (int32_t)pi; h->inst = -1; h->th.t = t; h->th.b0 = u; h->th.b1 = v; h->th.b2 = 0.0f;
         return true;
     }
     V3 p0, p1, p2; sc.tri_points(pr.mesh, pr.tri, &p0, &p1, &p2);

@@ -234,6 +234,72 @@ inline void rotate_from_to(V3 from, V3 to, Float r[9]) {
 inline V3 mul3(const Float r[9], V3 v) { return v3(r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z); }
 inline V3 mul3t(const Float r[9], V3 v) { return v3(r[0] * v.x + r[3] * v.y + r[6] * v.z, r[1] * v.x + r[4] * v.y + r[7] * v.z, r[2] * v.x + r[5] * v.y + r[8] * v.z); }
 
+// BilinearPatch::interaction_from_intersection bilinear_patch.rs:238-425
+inline SurfaceInteraction patch_interaction(const Scene& sc, uint32_t mesh_id, uint32_t patch, Float u, Float v, V3 wo) {
+    const SgMesh& m = sc.d->meshes[mesh_id];
+    uint32_t vi[4]; sc.patch_indices(mesh_id, patch, vi);
+    V3 q[4]; sc.patch_points(mesh_id, patch, q);
+    const V3 p00 = q[0], p10 = q[1], p01 = q[2], p11 = q[3];
+    const V3 p = lerp3(u, lerp3(v, p00, p01), lerp3(v, p10, p11));
+    V3 dpdu = lerp3(v, p10, p11) - lerp3(v, p00, p01);
+    V3 dpdv = lerp3(u, p01, p11) - lerp3(u, p00, p10);
+    V2 st = {u, v};
+    Float duds = 1.0f, dudt = 0.0f, dvds = 0.0f, dvdt = 1.0f;
+    auto lerp2 = [](Float t, V2 a, V2 b) { V2 r = {a.x * (1.0f - t) + b.x * t, a.y * (1.0f - t) + b.y * t}; return r; };
+    if (m.flags & SG_MESH_HAS_UV) {
+        const V2 uv00 = sc.uv(m, vi[0]), uv10 = sc.uv(m, vi[1]), uv01 = sc.uv(m, vi[2]), uv11 = sc.uv(m, vi[3]);
+        st = lerp2(u, lerp2(v, uv00, uv01), lerp2(v, uv10, uv11));
+        const V2 a1 = lerp2(v, uv10, uv11), a0 = lerp2(v, uv00, uv01), b1 = lerp2(u, uv01, uv11), b0 = lerp2(u, uv00, uv10);
+        const V2 dstdu = {a1.x - a0.x, a1.y - a0.y}, dstdv = {b1.x - b0.x, b1.y - b0.y};
+        duds = std::fabs(dstdu.x) < 1e-8f ? 0.0f : 1.0f / dstdu.x;
+        dvds = std::fabs(dstdv.x) < 1e-8f ? 0.0f : 1.0f / dstdv.x;
+        dudt = std::fabs(dstdu.y) < 1e-8f ? 0.0f : 1.0f / dstdu.y;
+        dvdt = std::fabs(dstdv.y) < 1e-8f ? 0.0f : 1.0f / dstdv.y;
+        const V3 dpds = dpdu * duds + dpdv * dvds;
+        V3 dpdt = dpdu * dudt + dpdv * dvdt;
+        const V3 cx = cross(dpds, dpdt);
+        if (!(cx.x == 0.0f && cx.y == 0.0f && cx.z == 0.0f)) {
+            if (dot(cross(dpdu, dpdv), cross(dpds, dpdt)) < 0.0f) dpdt = -dpdt;
+            dpdu = dpds; dpdv = dpdt;
+        }
+    }
+    const V3 d2pduu = v3(0, 0, 0), d2pdvv = v3(0, 0, 0), d2pduv = (p00 - p01) + (p11 - p10);
+    const Float e1 = dot(dpdu, dpdu), f1 = dot(dpdu, dpdv), g1 = dot(dpdv, dpdv);
+    const V3 n = normalize(cross(dpdu, dpdv));
+    const Float e2 = dot(n, d2pduu), f2 = dot(n, d2pduv), g2 = dot(n, d2pdvv);
+    const Float egf2 = difference_of_products(e1, g1, f1, f1);
+    const Float inv = egf2 != 0.0f ? 1.0f / egf2 : 0.0f;
+    V3 dndu = ((f1 * f2 - e2 * g1) * inv) * dpdu + ((e2 * f1 - f2 * e1) * inv) * dpdv;
+    V3 dndv = ((g2 * f1 - f2 * g1) * inv) * dpdu + ((f2 * f1 - g2 * e1) * inv) * dpdv;
+    const V3 dnds = dndu * duds + dndv * dvds, dndt = dndu * dudt + dndv * dvdt;
+    dndu = dnds; dndv = dndt;
+    const V3 p_abs_sum = vabs(p00) + vabs(p01) + vabs(p10) + vabs(p11);
+    const bool flip = ((m.flags & SG_MESH_REVERSE_ORIENTATION) != 0) ^ ((m.flags & SG_MESH_SWAPS_HANDEDNESS) != 0);
+    SurfaceInteraction si;                                           // SurfaceInteraction::new_with_face_index interaction.rs:111-176
+    si.pi = p3fi_from_value_and_error(p, gamma_n(6) * p_abs_sum);
+    si.uv = st; si.wo = wo; si.dpdu = dpdu; si.dpdv = dpdv;
+    si.n = flip ? -n : n;
+    si.sn = si.n; si.sdpdu = dpdu; si.sdpdv = dpdv; si.sdndu = dndu; si.sdndv = dndv;
+    si.material = -1; si.light = -1;
+    if (m.flags & SG_MESH_HAS_N) {
+        const V3 n00 = sc.normal(m, vi[0]), n10 = sc.normal(m, vi[1]), n01 = sc.normal(m, vi[2]), n11 = sc.normal(m, vi[3]);
+        V3 ns = lerp3(u, lerp3(v, n00, n01), lerp3(v, n10, n11));
+        if (length_squared(ns) > 0.0f) {
+            ns = normalize(ns);
+            V3 sdndu = lerp3(v, n10, n11) - lerp3(v, n00, n01);
+            V3 sdndv = lerp3(u, n01, n11) - lerp3(u, n00, n10);
+            const V3 s_dnds = sdndu * duds + sdndv * dvds, s_dndt = sdndu * dudt + sdndv * dvdt;
+            Float r[9]; rotate_from_to(si.n, ns, r);
+            // set_shading_geometry(ns, r(dpdu), r(dpdv), dnds, dndt, true) interaction.rs:379-405
+            si.sn = ns;
+            si.n = face_forward(si.n, si.sn);
+            si.sdpdu = mul3(r, dpdu); si.sdpdv = mul3(r, dpdv); si.sdndu = s_dnds; si.sdndv = s_dndt;
+            while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
+        }
+    }
+    return si;
+}
+
 // Camera::approximate_dp_dxy camera.rs:308-354
 inline void approximate_dp_dxy(const SgCamera& cam, V3 p, V3 n, int spp, uint32_t option_flags, V3* dpdx, V3* dpdy) {
     V3 p_camera = xform_point3(cam.camera_from_render, p);

@@ -109,6 +109,8 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
             V3 p_obj = v3(hit.th.b0, hit.th.b1, hit.th.b2);
             Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
             si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -ray.d);
+        } else if (D->meshes[prim.mesh].flags & SG_MESH_BILINEAR) {                 // BilinearPatch::intersect bilinear_patch.rs:496-509
+            si = patch_interaction(*pc.sc, prim.mesh, prim.tri, hit.th.b0, hit.th.b1, -ray.d);
         } else if (hit.inst >= 0) {                                                       // TransformedPrimitive::intersect primitive.rs:155-169
             const SgInstance& I = D->instances[hit.inst];
             const float* mi = I.primitive_from_render;
@@ -258,6 +260,13 @@ void orc_trace(const SgSceneDesc* desc, int64_t n, const float* o, const float* 
                 Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
                 SurfaceInteraction ssi = sphere_interaction(desc, desc->spheres[pr.tri], p_obj, phi, -r.d);
                 oh.ng[0] = ssi.n.x; oh.ng[1] = ssi.n.y; oh.ng[2] = ssi.n.z;
+                continue;
+            }
+            if (desc->meshes[pr.mesh].flags & SG_MESH_BILINEAR) {
+                SurfaceInteraction psi = patch_interaction(sc, pr.mesh, pr.tri, h.th.b0, h.th.b1, -r.d);
+                V3 q[4]; sc.patch_points(pr.mesh, pr.tri, q);                   // geometric normal before shading-normal face-forwarding
+                (void)q;
+                oh.ng[0] = psi.n.x; oh.ng[1] = psi.n.y; oh.ng[2] = psi.n.z;
                 continue;
             }
             SurfaceInteraction si = interaction_from_intersection(sc, pr.mesh, pr.tri, h.th, -r.d);

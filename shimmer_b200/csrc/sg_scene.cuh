@@ -52,6 +52,7 @@ struct DScene {
     uint32_t rgb2spec_res, n_textures;
     const DInstance* instances;         // object instancing
     const struct DSphere* spheres;      // sphere shapes (sg_sphere.cuh)
+    const float4* patch_verts;          // bilinear patches: 4 float4 per patch primitive (sg_patch.cuh)
     uint32_t n_instances, scene_flags;
     uint32_t n_nodes, n_prims, n_lights, n_materials;
     int32_t n_infinite;          // number of SG_LIGHT_UNIFORM_INFINITE lights

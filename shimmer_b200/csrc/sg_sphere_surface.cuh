@@ -2,6 +2,7 @@
 // The caller maps it to render space with transform_interaction_m (Transform::apply(SurfaceInteraction), transform.rs:573-609).
 #pragma once
 #include "sg_sphere.cuh"
+#include "sg_patch.cuh"
 #include "sg_texture.cuh"
 
 namespace sg {
@@ -37,6 +38,74 @@ SGD Surf make_surface_sphere(const DSphere& S, float3 p_hit, SurfTex* x) {
         const float3 dndv = ((g * f1 - f * g1) * inv) * dpdu + ((f * f1 - g * e1) * inv) * dpdv;
         surf_tex_store<TEX>(x, make_float2(u, v), dpdu, dpdv, dndu, dndv);
     }
+    return s;
+}
+
+// BilinearPatch::interaction_from_intersection bilinear_patch.rs:238-425.  `rec` indexes patch_verts (4 float4: p00 p10 p01 p11;
+// .w = mesh flags, mesh id, patch index in the mesh).
+template <bool TEX>
+__device__ __noinline__ Surf make_surface_patch(const DScene& sc, uint32_t rec, float u, float v, SurfTex* x) {
+    const float4 a0 = __ldg(sc.patch_verts + 4 * (size_t)rec), a1 = __ldg(sc.patch_verts + 4 * (size_t)rec + 1),
+                 a2 = __ldg(sc.patch_verts + 4 * (size_t)rec + 2), a3 = __ldg(sc.patch_verts + 4 * (size_t)rec + 3);
+    const float3 p00 = f3(a0.x, a0.y, a0.z), p10 = f3(a1.x, a1.y, a1.z), p01 = f3(a2.x, a2.y, a2.z), p11 = f3(a3.x, a3.y, a3.z);
+    const uint32_t flags = __float_as_uint(a0.w);
+    const SgMesh m = sc.meshes[__float_as_uint(a1.w)];
+    const uint32_t* ix = sc.indices + m.first_index + 4 * (size_t)__float_as_uint(a2.w);
+    const float3 p = lerp3(u, lerp3(v, p00, p01), lerp3(v, p10, p11));
+    float3 dpdu = lerp3(v, p10, p11) - lerp3(v, p00, p01);
+    float3 dpdv = lerp3(u, p01, p11) - lerp3(u, p00, p10);
+    float2 st = make_float2(u, v);
+    float duds = 1.0f, dudt = 0.0f, dvds = 0.0f, dvdt = 1.0f;
+    if (flags & SG_MESH_HAS_UV) {
+        auto ld2 = [&](uint32_t k) { const float* q = sc.uv + 2 * ((size_t)m.first_vertex + __ldg(ix + k)); return make_float2(__ldg(q), __ldg(q + 1)); };
+        auto lerp2 = [](float t, float2 a, float2 b) { return make_float2(a.x * (1.0f - t) + b.x * t, a.y * (1.0f - t) + b.y * t); };
+        const float2 uv00 = ld2(0), uv10 = ld2(1), uv01 = ld2(2), uv11 = ld2(3);
+        st = lerp2(u, lerp2(v, uv00, uv01), lerp2(v, uv10, uv11));
+        const float2 c1 = lerp2(v, uv10, uv11), c0 = lerp2(v, uv00, uv01), e1_ = lerp2(u, uv01, uv11), e0_ = lerp2(u, uv00, uv10);
+        const float2 dstdu = make_float2(c1.x - c0.x, c1.y - c0.y), dstdv = make_float2(e1_.x - e0_.x, e1_.y - e0_.y);
+        duds = fabsf(dstdu.x) < 1e-8f ? 0.0f : 1.0f / dstdu.x;
+        dvds = fabsf(dstdv.x) < 1e-8f ? 0.0f : 1.0f / dstdv.x;
+        dudt = fabsf(dstdu.y) < 1e-8f ? 0.0f : 1.0f / dstdu.y;
+        dvdt = fabsf(dstdv.y) < 1e-8f ? 0.0f : 1.0f / dstdv.y;
+        const float3 dpds = dpdu * duds + dpdv * dvds;
+        float3 dpdt = dpdu * dudt + dpdv * dvdt;
+        const float3 cx = cross3(dpds, dpdt);
+        if (!(cx.x == 0.0f && cx.y == 0.0f && cx.z == 0.0f)) {
+            if (dot3(cross3(dpdu, dpdv), cross3(dpds, dpdt)) < 0.0f) dpdt = -dpdt;
+            dpdu = dpds; dpdv = dpdt;
+        }
+    }
+    const float3 d2pduv = (p00 - p01) + (p11 - p10), zero = f3(0.0f, 0.0f, 0.0f);
+    const float e1 = dot3(dpdu, dpdu), f1 = dot3(dpdu, dpdv), g1 = dot3(dpdv, dpdv);
+    const float3 n = normalize3(cross3(dpdu, dpdv));
+    const float e2 = dot3(n, zero), f2 = dot3(n, d2pduv), g2 = dot3(n, zero);
+    const float egf2 = dop(e1, g1, f1, f1);
+    const float inv = egf2 != 0.0f ? 1.0f / egf2 : 0.0f;
+    float3 dndu = ((f1 * f2 - e2 * g1) * inv) * dpdu + ((e2 * f1 - f2 * e1) * inv) * dpdv;
+    float3 dndv = ((g2 * f1 - f2 * g1) * inv) * dpdu + ((f2 * f1 - g2 * e1) * inv) * dpdv;
+    { const float3 dnds = dndu * duds + dndv * dvds, dndt = dndu * dudt + dndv * dvdt; dndu = dnds; dndv = dndt; }
+    Surf s;
+    s.pi = p3fi_make(p, gamma_n(6) * (abs3(p00) + abs3(p01) + abs3(p10) + abs3(p11)));
+    const bool flip = ((flags & SG_MESH_REVERSE_ORIENTATION) != 0) != ((flags & SG_MESH_SWAPS_HANDEDNESS) != 0);
+    s.n = flip ? -n : n;
+    s.sn = s.n; s.sdpdu = dpdu; s.sdpdv = dpdv;
+    float3 sdndu = dndu, sdndv = dndv;
+    if (flags & SG_MESH_HAS_N) {
+        const float3 n00 = ldv3(sc.n, (size_t)m.first_vertex + __ldg(ix)), n10 = ldv3(sc.n, (size_t)m.first_vertex + __ldg(ix + 1)),
+                     n01 = ldv3(sc.n, (size_t)m.first_vertex + __ldg(ix + 2)), n11 = ldv3(sc.n, (size_t)m.first_vertex + __ldg(ix + 3));
+        float3 ns = lerp3(u, lerp3(v, n00, n01), lerp3(v, n10, n11));
+        if (len2(ns) > 0.0f) {
+            ns = normalize3(ns);
+            const float3 a = lerp3(v, n10, n11) - lerp3(v, n00, n01), b = lerp3(u, n01, n11) - lerp3(u, n00, n10);
+            sdndu = a * duds + b * dvds; sdndv = a * dudt + b * dvdt;
+            float r[9]; rotate_from_to(s.n, ns, r);
+            s.sn = ns;                                                          // set_shading_geometry(.., true) interaction.rs:379-405
+            s.n = faceforward3(s.n, s.sn);
+            s.sdpdu = mul3(r, dpdu); s.sdpdv = mul3(r, dpdv);
+            while (len2(s.sdpdu) > 1e16f || len2(s.sdpdv) > 1e16f) { s.sdpdu = s.sdpdu / 1e8f; s.sdpdv = s.sdpdv / 1e8f; }
+        }
+    }
+    if (TEX) surf_tex_store<TEX>(x, st, dpdu, dpdv, sdndu, sdndv);
     return s;
 }
 

@@ -234,17 +234,13 @@ SGD float3 mul3(const float* r, float3 v) { return f3(r[0] * v.x + r[1] * v.y + 
 SGD float3 mul3t(const float* r, float3 v) { return f3(r[0] * v.x + r[3] * v.y + r[6] * v.z, r[1] * v.x + r[4] * v.y + r[7] * v.z, r[2] * v.x + r[5] * v.y + r[8] * v.z); }
 SGD float3 ld3(const float* a) { return f3(a[0], a[1], a[2]); }
 
-// Camera::approximate_dp_dxy camera.rs:308-354 (Transform::rotate_from_to transform.rs:227-253 inlined)
-__device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, float3 n, int spp, uint32_t option_flags, float3& dpdx, float3& dpdy) {
-    const SgCamera& cam = sc.camera;
-    const float3 p_camera = xform_point(cam.camera_from_render, p);
-    const float3 from = normalize3(p_camera), to = f3(0.0f, 0.0f, 1.0f);
+// Transform::rotate_from_to transform.rs:227-253 (3x3 part, row-major)
+SGD void rotate_from_to(float3 from, float3 to, float r[9]) {
     float3 ref1;
     if (fabsf(from.x) < 0.72f && fabsf(to.x) < 0.72f) ref1 = f3(1.0f, 0.0f, 0.0f);
     else if (fabsf(from.y) < 0.72f && fabsf(to.y) < 0.72f) ref1 = f3(0.0f, 1.0f, 0.0f);
     else ref1 = f3(0.0f, 0.0f, 1.0f);
     const float3 u = ref1 - from, v = ref1 - to;
-    float r[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -253,6 +249,13 @@ __device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, floa
             r[3 * i + j] = kron - 2.0f / dot3(u, u) * comp3(u, i) * comp3(u, j) - 2.0f / dot3(v, v) * comp3(v, i) * comp3(v, j)
                            + 4.0f * dot3(u, v) / (dot3(u, u) * dot3(v, v)) * comp3(v, i) * comp3(u, j);
         }
+}
+// Camera::approximate_dp_dxy camera.rs:308-354
+__device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, float3 n, int spp, uint32_t option_flags, float3& dpdx, float3& dpdy) {
+    const SgCamera& cam = sc.camera;
+    const float3 p_camera = xform_point(cam.camera_from_render, p);
+    float r[9];
+    rotate_from_to(normalize3(p_camera), f3(0.0f, 0.0f, 1.0f), r);
     const float3 p_down_z = f3(r[0] * p_camera.x + r[1] * p_camera.y + r[2] * p_camera.z + 0.0f, r[3] * p_camera.x + r[4] * p_camera.y + r[5] * p_camera.z + 0.0f,
                                r[6] * p_camera.x + r[7] * p_camera.y + r[8] * p_camera.z + 0.0f);
     const float3 n_down_z = mul3(r, xform_normal_t(cam.render_from_camera, n));

@@ -20,6 +20,7 @@
 #pragma once
 #include "sg_scene.cuh"
 #include "sg_sphere.cuh"
+#include "sg_patch.cuh"
 
 namespace sg {
 
@@ -63,6 +64,7 @@ struct TraceScene {
     int interior_burst;
     int prefetch;
     const DInstance* instances; // object instancing (INST kernels only)
+    const float4* patch_verts;  // bilinear patches (INST kernels only)
     const DSphere* spheres;     // sphere shapes (INST kernels only: the "general" kernels handle everything that is not a triangle)
     uint32_t scene_flags;
 };
@@ -265,6 +267,14 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
             float3 p_obj;
             hit_prim = sphere_basic_intersect(ts.spheres[__float_as_uint(v2.w) & ~(kSphereBit | kLastInLeaf)], o, d, L.t_max, p_obj, t);
             b0 = p_obj.x; b1 = p_obj.y; b2 = p_obj.z;
+        } else if (INST && (__float_as_uint(v2.w) & kPatchBit)) {
+            // Shape::BilinearPatch (top level only): hit record carries (u, v)
+            float3 o, d; float tm;
+            io.load(idx, o, d, tm);
+            const float4* pv = ts.patch_verts + 4 * (size_t)(__float_as_uint(v2.w) & ~(kPatchBit | kLastInLeaf));
+            const float4 a0 = __ldg(pv), a1 = __ldg(pv + 1), a2 = __ldg(pv + 2), a3 = __ldg(pv + 3);
+            hit_prim = intersect_blp(o, d, L.t_max, f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), f3(a3.x, a3.y, a3.z), b0, b1, t);
+            b2 = 0.0f;
         } else hit_prim = intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
         if (hit_prim) {
             L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;

@@ -491,6 +491,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 const DSphere& S = sc.spheres[geo.mesh & ~kSphereBit];
                 s = make_surface_sphere<TEX>(S, f3(hb.x, hb.y, hb.z), &sx);
                 transform_interaction<TEX>(sc, S.m, S.mi, rd, s, &sx, wo_si);
+            } else if (st.hit_inst != nullptr && (geo.mesh & kPatchBit)) {   // BilinearPatch::intersect: hit_b carries (u, v)
+                s = make_surface_patch<TEX>(sc, geo.mesh & ~kPatchBit, hb.x, hb.y, &sx);
             } else {
                 s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
                 if (st.hit_inst != nullptr) {                    // TransformedPrimitive::intersect primitive.rs:155-169
@@ -735,6 +737,12 @@ struct RaysIO {
                     float3 wo_si, rd = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
                     transform_interaction<false>(sc, S.m, S.mi, rd, ss, nullptr, wo_si);
                     h.ng[0] = ss.n.x; h.ng[1] = ss.n.y; h.ng[2] = ss.n.z;
+                    out[i] = h;
+                    return;
+                }
+                if (__float_as_uint(v2.w) & kPatchBit) {
+                    const Surf ps = make_surface_patch<false>(sc, __float_as_uint(v2.w) & ~(kPatchBit | kLastInLeaf), hit.b0, hit.b1, nullptr);
+                    h.ng[0] = ps.n.x; h.ng[1] = ps.n.y; h.ng[2] = ps.n.z;
                     out[i] = h;
                     return;
                 }

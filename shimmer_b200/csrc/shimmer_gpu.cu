@@ -173,6 +173,10 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             continue;
         }
         if (!desc->meshes || !desc->indices || !desc->p) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
+        if (p.mesh < desc->n_meshes && (desc->meshes[p.mesh].flags & SG_MESH_BILINEAR)) {
+            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "bilinear patches inside object definitions are not on the GPU path yet");
+            if (p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights on bilinear patches are not on the GPU path yet");
+        }
         if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
             p.light >= (int32_t)desc->n_lights)
             return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references out-of-range mesh/triangle/material/light");
@@ -247,6 +251,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     DScene& d = s->d;
     // pre-gathered triangle vertices in BVH-leaf order (DESIGN.md "Data layout")
     std::vector<float4> tv((size_t)desc->n_primitives * 3);
+    std::vector<float4> pv;                                 // bilinear patch vertices, 4 float4 per patch primitive
     for (uint32_t i = 0; i < desc->n_primitives; ++i) {
         const SgPrimitive& p = desc->primitives[i];
         if (p.mesh == SG_PRIM_INSTANCE) {                   // TransformedPrimitive: no vertices; kind 7, instance id in word 1
@@ -263,6 +268,22 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             continue;
         }
         const SgMesh& m = desc->meshes[p.mesh];
+        if (m.flags & SG_MESH_BILINEAR) {                   // Shape::BilinearPatch: 4 vertices in patch_verts, record index | kPatchBit in word 2
+            if (p.material >= (1u << 23)) { g_err = "more than 2^23 materials"; return bail(SG_ERR_UNSUPPORTED); }
+            const uint32_t rec = (uint32_t)(pv.size() / 4);
+            const uint32_t* ix4 = desc->indices + m.first_index + 4 * (size_t)p.tri;
+            const uint32_t meta[4] = {m.flags, p.mesh, p.tri, 0u};
+            for (int k = 0; k < 4; ++k) {
+                if (ix4[k] >= m.n_vertices) { g_err = "vertex index out of range"; return bail(SG_ERR_INVALID_ARGUMENT); }
+                const float* q = desc->p + 3 * (size_t)(m.first_vertex + ix4[k]);
+                float wf; std::memcpy(&wf, &meta[k], 4);
+                pv.push_back(make_float4(q[0], q[1], q[2], wf));
+            }
+            const uint32_t w[3] = {p.material | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, rec | kPatchBit};
+            for (int k = 0; k < 3; ++k) { float wf; std::memcpy(&wf, &w[k], 4); tv[3 * (size_t)i + k] = make_float4(0.0f, 0.0f, 0.0f, wf); }
+            s->kinds_present[desc->materials[p.material].kind] = true;
+            continue;
+        }
         const uint32_t* ix = desc->indices + m.first_index + 3 * (size_t)p.tri;
         if (p.material >= (1u << 23)) { g_err = "more than 2^23 materials"; return bail(SG_ERR_UNSUPPORTED); }
         const uint32_t w[3] = {p.material | ((m.flags & 31u) << 23) | ((uint32_t)desc->materials[p.material].kind << 28), (uint32_t)p.light, p.mesh};
@@ -360,7 +381,12 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         s->smem_closest = (size_t)s->ts.smem_levels * kTraceThreads * 8;
         s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
     }
-    s->instanced = desc->n_instances > 0 || desc->n_spheres > 0;        // anything that is not a triangle -> the general kernels
+    s->instanced = desc->n_instances > 0 || desc->n_spheres > 0 || !pv.empty();      // anything that is not a triangle -> the general kernels
+    {
+        float4* d_pv = nullptr;
+        if ((rc = upload(pv.data(), pv.size(), &d_pv, s->owned)) != SG_OK) return bail(rc);
+        s->ts.patch_verts = d_pv; d.patch_verts = d_pv;
+    }
     {
         std::vector<DSphere> dsph(desc->n_spheres);
         for (uint32_t i = 0; i < desc->n_spheres; ++i) {

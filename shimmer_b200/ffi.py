@@ -16,6 +16,7 @@ SG_ABI_VERSION = 5
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
+SG_MESH_BILINEAR = 32
 SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
 SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
 SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE = 0, 1, 2, 3

@@ -238,6 +238,7 @@ class SceneBuilder:
         self.n_objects = 0       # object definitions (ObjectBegin/End); meshes carry an `object` id or None
         self.instances = []      # (object id, render_from_instance Transform)
         self.spheres = []        # dicts: Sphere::new fields + material (top-level shapes, after the meshes)
+        self.patch_meshes = []   # dicts: BilinearPatchMesh (4 vertex indices per patch); top-level shapes, after the triangle meshes
         self.fix_instancing = False
         self.camera = None
         self.film = None
@@ -433,6 +434,25 @@ class SceneBuilder:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
+    def add_bilinear_mesh(self, p, indices, material, n=None, uv=None, reverse_orientation=False, object_from_world=None):
+        """Shape "bilinearmesh": BilinearPatchMesh::new (shape/mesh.rs:111-175) + one BilinearPatch per four indices
+        (p00, p10, p01, p11; bilinear_patch.rs:77-106).  Top-level, non-emissive patches only."""
+        ctm = object_from_world if object_from_world is not None else Transform.identity()
+        rfo = self.render_from_world * ctm
+        p = rfo.apply_points_f32(np.asarray(p, dtype=np.float32).reshape(-1, 3))
+        if n is not None:
+            n = rfo.apply_normals_f32(np.asarray(n, dtype=np.float32).reshape(-1, 3))
+            if reverse_orientation:
+                n = -n
+        flags = ffi.SG_MESH_BILINEAR
+        if n is not None: flags |= ffi.SG_MESH_HAS_N
+        if uv is not None: flags |= ffi.SG_MESH_HAS_UV
+        if reverse_orientation: flags |= ffi.SG_MESH_REVERSE_ORIENTATION
+        if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
+        self.patch_meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 4), n=n,
+                                      uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2), flags=flags, material=material))
+        return len(self.patch_meshes) - 1
+
     def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False,
                    area_light=None):
         """Shape "sphere": Sphere::create / Sphere::new (shape/sphere.rs:48-92).  `object_from_world` is the CTM
@@ -534,13 +554,15 @@ class SceneBuilder:
             L.area = float(f32(sp["phi_max"]) * f32(sp["radius"]) * (f32(sp["z_max"]) - f32(sp["z_min"])))       # Sphere::area sphere.rs:295-297
             sphere_light[si_] = len(lights); lights.append(L)
         # geometry arrays
-        any_n = any(m["n"] is not None for m in self.meshes)
-        any_uv = any(m["uv"] is not None for m in self.meshes)
-        nv = sum(len(m["p"]) for m in self.meshes); nt = sum(len(m["idx"]) for m in self.meshes)
+        all_meshes = self.meshes + self.patch_meshes
+        any_n = any(m["n"] is not None for m in all_meshes)
+        any_uv = any(m["uv"] is not None for m in all_meshes)
+        nv = sum(len(m["p"]) for m in all_meshes); nt = sum(len(m["idx"]) for m in self.meshes)
+        n_patches = sum(len(m["idx"]) for m in self.patch_meshes)
         A["p"] = np.empty((nv, 3), np.float32); A["idx"] = np.empty((nt, 3), np.uint32)
         A["n"] = np.zeros((nv, 3), np.float32) if any_n else None
         A["uv"] = np.zeros((nv, 2), np.float32) if any_uv else None
-        mesh_rows = (ffi.SgMesh * len(self.meshes))()
+        mesh_rows = (ffi.SgMesh * len(all_meshes))()
         prim_in = np.empty((nt, 4), np.int64)       # mesh, tri, material, light (input order)
         gidx = np.empty((nt, 3), np.uint32)
         v0 = t0 = 0
@@ -554,6 +576,23 @@ class SceneBuilder:
             prim_in[t0:t0 + t, 0] = mi; prim_in[t0:t0 + t, 1] = np.arange(t); prim_in[t0:t0 + t, 2] = m["material"]
             prim_in[t0:t0 + t, 3] = (mesh_light_base[mi] + np.arange(t)) if mi in mesh_light_base else -1
             v0 += k; t0 += t
+        # bilinear patch meshes: vertices after the triangle meshes', four indices per patch after the triangle indices
+        A["patch_idx"] = np.empty((n_patches, 4), np.uint32)
+        patch_prim_in = np.empty((n_patches, 4), np.int64); patch_bounds = np.empty((n_patches, 6), np.float32)
+        q0 = 0
+        for pi_, m in enumerate(self.patch_meshes):
+            mi = len(self.meshes) + pi_
+            k, t = len(m["p"]), len(m["idx"])
+            A["p"][v0:v0 + k] = m["p"]; A["patch_idx"][q0:q0 + t] = m["idx"]
+            if m["n"] is not None: A["n"][v0:v0 + k] = m["n"]
+            if m["uv"] is not None: A["uv"][v0:v0 + k] = m["uv"]
+            mr = mesh_rows[mi]
+            mr.first_index, mr.first_vertex, mr.n_triangles, mr.n_vertices, mr.flags = 3 * nt + 4 * q0, v0, t, k, m["flags"]
+            patch_prim_in[q0:q0 + t, 0] = mi; patch_prim_in[q0:q0 + t, 1] = np.arange(t); patch_prim_in[q0:q0 + t, 2] = m["material"]; patch_prim_in[q0:q0 + t, 3] = -1
+            P4 = m["p"][m["idx"]]                                           # BilinearPatch::bounds bilinear_patch.rs:430-433
+            patch_bounds[q0:q0 + t, :3] = P4.min(axis=1); patch_bounds[q0:q0 + t, 3:] = P4.max(axis=1)
+            v0 += k; q0 += t
+        A["all_idx"] = np.concatenate([A["idx"].ravel(), A["patch_idx"].ravel()]).astype(np.uint32) if n_patches else A["idx"]
         # Triangle::bounds per triangle (input order)
         bounds = np.empty((nt, 6), np.float32)
         host.sh_triangle_bounds(nt, gidx.ctypes.data, A["p"].ctypes.data, bounds.ctypes.data)
@@ -615,6 +654,8 @@ class SceneBuilder:
         A["spheres"] = sph_rows
         top_bounds = bounds[top_sel]
         top_prim_in = prim_in[top_sel]
+        if n_patches:
+            top_prim_in = np.concatenate([top_prim_in, patch_prim_in]); top_bounds = np.concatenate([top_bounds, patch_bounds])
         if len(self.spheres):
             sp_in = np.zeros((len(self.spheres), 4), np.int64)
             sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]
@@ -693,8 +734,8 @@ class SceneBuilder:
         d.n_instances = len(self.instances); d.instances = A["instances"]
         d.n_spheres = len(self.spheres); d.spheres = A["spheres"]
         d.scene_flags = ffi.SG_SCENE_FIX_INSTANCING if self.fix_instancing else 0
-        d.n_meshes = len(self.meshes); d.meshes = A["meshes"]
-        d.n_indices = 3 * nt; d.indices = _as_ptr(A["idx"], C.c_uint32)
+        d.n_meshes = len(all_meshes); d.meshes = A["meshes"]
+        d.n_indices = 3 * nt + 4 * n_patches; d.indices = _as_ptr(A["all_idx"], C.c_uint32)
         d.n_vertices = nv; d.p = _as_ptr(A["p"], C.c_float)
         d.n = _as_ptr(A["n"], C.c_float) if any_n else None
         d.uv = _as_ptr(A["uv"], C.c_float) if any_uv else None
@@ -715,6 +756,6 @@ class SceneBuilder:
         d.film = self.film
         inst_tris = sum(int(obj_rows[o].n_prims) for o, _ in self.instances)
         upload_bytes = sum(int(getattr(v, "nbytes", 0) or (C.sizeof(v) if isinstance(v, C.Array) else 0)) for v in A.values() if v is not None)
-        out.meta = dict(upload_bytes=upload_bytes, n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights), n_spheres=len(self.spheres),
+        out.meta = dict(upload_bytes=upload_bytes, n_triangles=nt, n_instanced_triangles=int(len(top_sel) + inst_tris), n_nodes=int(n_nodes), n_lights=len(lights), n_spheres=len(self.spheres), n_patches=int(n_patches),
                         resolution=tuple(self.film.full_resolution), window=tuple(self.film.pixel_bounds))
         return out

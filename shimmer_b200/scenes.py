@@ -311,6 +311,52 @@ def sphere_tiny_scene(kind="spheres", resolution=(32, 32), fix=False):
     return b
 
 
+PATCH_KINDS = ("patches", "patchestex")
+
+
+def patch_grid(n, size=2.0, amp=0.25):
+    """(n+1)^2 vertices of a wavy height field with analytic normals and uv, n^2 bilinear patches (p00, p10, p01, p11)."""
+    g = np.linspace(0.0, 1.0, n + 1)
+    U, V = np.meshgrid(g, g, indexing="ij")
+    X = (U - 0.5) * size; Z = (V - 0.5) * size
+    Y = amp * np.sin(2.5 * X) * np.cos(2.0 * Z)
+    dYdx = amp * 2.5 * np.cos(2.5 * X) * np.cos(2.0 * Z); dYdz = -amp * 2.0 * np.sin(2.5 * X) * np.sin(2.0 * Z)
+    P = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+    N = np.stack([-dYdx, np.ones_like(X), -dYdz], axis=-1).reshape(-1, 3); N /= np.linalg.norm(N, axis=1, keepdims=True)
+    UV = np.stack([U, V], axis=-1).reshape(-1, 2)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    a = (i * (n + 1) + j).ravel()
+    # orientation chosen so that (p10 - p00) x (p01 - p00) points up (+y): u along z, v along x
+    idx = np.stack([a, a + 1, a + n + 1, a + n + 2], axis=1)
+    return P.astype(np.float32), idx.astype(np.uint32), N.astype(np.float32), UV.astype(np.float32)
+
+
+def patch_tiny_scene(kind="patches", resolution=(32, 32)):
+    """Shape "bilinearmesh" (shape/bilinear_patch.rs): a wavy 6x6 patch grid with vertex normals and uv (every patch is
+    non-planar), a twisted single patch without normals (copper), a planar quad patch (the PLY-quad case) behind them."""
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 2.0, -4.0), look=(0.0, 0.4, 0.0), up=(0, 1, 0), fov=42.0, resolution=resolution)
+    white = b.diffuse(_white())
+    if kind == "patchestex":
+        skin = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="ewa", su=3.0, sv=3.0),
+                         displacement_tex=b.image_texture(procedural_image(32, 1), filter="bilinear", su=6.0, sv=6.0, scale=0.03))
+        wall = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="trilinear", su=2.0, sv=2.0))
+    else:
+        skin = b.diffuse(_green()); wall = b.diffuse(_red())
+    copper = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.2)
+    P, I, N, UV = patch_grid(6)
+    b.add_bilinear_mesh(P, I, skin, n=N, uv=UV, object_from_world=Transform.translate((0.0, 0.35, 0.0)))
+    tw = np.array([[-0.5, 0.0, -0.3], [0.5, 0.0, -0.5], [-0.4, 1.0, 0.3], [0.6, 0.9, -0.2]], np.float32)
+    b.add_bilinear_mesh(tw, [[0, 1, 2, 3]], copper, object_from_world=Transform.translate((1.3, 0.6, 0.6)) * Transform.rotate(25.0, (0, 1, 0)))
+    quad = np.array([[-2.5, 0.0, 1.8], [2.5, 0.0, 1.8], [-2.5, 2.5, 1.8], [2.5, 2.5, 1.8]], np.float32)
+    b.add_bilinear_mesh(quad, [[0, 1, 2, 3]], wall, uv=np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32), reverse_orientation=True)
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, white)
+    lp, li = _quad((-0.6, 3.0, -0.9), (0.6, 3.0, -0.9), (0.6, 3.0, 0.3), (-0.6, 3.0, 0.3))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b
+
+
 TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
 INSTANCED_KINDS = ("inst", "instrot", "instfix", "insttex")
 
@@ -371,6 +417,8 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         return instanced_tiny_scene(kind, resolution)
     if kind in SPHERE_KINDS:
         return sphere_tiny_scene(kind, resolution)
+    if kind in PATCH_KINDS:
+        return patch_tiny_scene(kind, resolution)
     b = SceneBuilder()
     b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
     white = b.diffuse(_white())

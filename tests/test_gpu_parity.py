@@ -443,3 +443,42 @@ def test_fullsize_film_properties():
     win = full.cpu().numpy().reshape(H, W, 4)[y0:y0 + c, x0:x0 + c].reshape(-1, 4)
     _film_close(win, ref, frac=0.995)
     integ.close()
+
+
+# ---- bilinear patches ------------------------------------------------------------------------
+def test_patch_raycast_parity():
+    """Random + aimed rays on the patch scene (wavy patch grid, twisted patch, planar quad, triangles): primitive, (u, v) and
+    t bit-exact against the oracle (quadratic + 3x3 determinants are pure f32 with the reference's explicit FMAs)."""
+    b = scenes.patch_tiny_scene("patches"); sc = b.build()
+    integ = create_integrator("wavefront", {}, sc)
+    rng = np.random.default_rng(12)
+    n = 1 << 16
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1]) + 0.8
+    tgt = np.stack([rng.uniform(-1.5, 2.0, n), rng.uniform(0.0, 1.2, n), rng.uniform(-1.2, 1.9, n)], 1).astype(np.float32)
+    d = (tgt - o).astype(np.float32)
+    d[n // 2:] = rng.standard_normal((n - n // 2, 3)).astype(np.float32)
+    o = b.render_from_world.apply_points_f32(o)
+    for tmax in (np.inf, 3.0):
+        t = np.full(n, tmax, np.float32)
+        got, gst = integ.trace(o, d, t, want_stats=True)
+        ref, rst = orc.trace(sc, o, d, t)
+        assert _assert_hits_equal(got, ref) == 4
+        assert gst.nodes_visited == rst.nodes_visited and gst.tris_tested == rst.tris_tested
+        hit = ref["prim"] >= 0
+        is_patch = np.array([m.flags & ffi.SG_MESH_BILINEAR for m in sc.arrays["meshes"]], bool)[sc.arrays["prims"]["mesh"][ref["prim"][hit]]]
+        assert is_patch.mean() > 0.3
+        any_g = integ.trace(o, d, np.minimum(t, np.float32(0.9999)), any_hit=True)
+        any_r, _ = orc.trace(sc, o, d, np.minimum(t, np.float32(0.9999)), any_hit=True)
+        assert np.array_equal(any_g["prim"], any_r["prim"])
+    integ.close()
+
+
+@pytest.mark.parametrize("kind", list(scenes.PATCH_KINDS))
+def test_patch_scene_films(kind):
+    sc = scenes.tiny_scene(kind, resolution=(24, 24)).build()
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 8, "seed": 4})
+    film = integ.render(Options()).copy()
+    ref, rst, _ = orc.render(sc, orc.make_params(seed=4, spp=8))
+    _film_close(film, ref, frac=0.99)
+    assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-3 * rst.closest_hit_rays
+    integ.close()
