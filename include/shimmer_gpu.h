@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 5
+#define SG_ABI_VERSION 6
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -144,8 +144,9 @@ typedef enum SgMaterialKind {
     SG_MATERIAL_DIFFUSE = 0,    /* DiffuseMaterial    material.rs:298-338  spec_a = reflectance          */
     SG_MATERIAL_CONDUCTOR = 1,  /* ConductorMaterial  material.rs:453-526  spec_a = eta, spec_b = k      */
     SG_MATERIAL_DIELECTRIC = 2, /* DielectricMaterial material.rs:600-662  spec_a = eta (`Spectrum`)     */
-    SG_MATERIAL_COATED_DIFFUSE = 3 /* CoatedDiffuseMaterial material.rs:913-992: spec_a = reflectance, spec_b = albedo,
+    SG_MATERIAL_COATED_DIFFUSE = 3, /* CoatedDiffuseMaterial material.rs:913-992: spec_a = reflectance, spec_b = albedo,
                                       spec_c = eta, thickness, g, max_depth, n_samples (LayeredBxDF bxdf.rs:883-1620) */
+    SG_MATERIAL_THIN_DIELECTRIC = 4 /* ThinDielectricMaterial material.rs:666-760 / ThinDielectricBxDF bxdf.rs:797-880: spec_a = eta */
 } SgMaterialKind;
 enum {
     SG_MAT_REMAP_ROUGHNESS = 1,  /* `remaproughness`, default true                      */
@@ -221,6 +222,12 @@ typedef struct SgLight {
 } SgLight;
 
 /* ---- camera (src/camera.rs:830-1114 PerspectiveCamera) --------------------- */
+/* SG_CAMERA_ORTHOGRAPHIC = `OrthographicCamera` (camera.rs:657-827): ray origin camera_from_raster(p_film), direction +z,
+ * auxiliary origins shifted by dx_camera / dy_camera, no depth of field (the reference has a TODO there).  Reproduced as
+ * written: `generate_ray_differential` (:760-784), the entry the integrator calls, returns the ray in CAMERA space -- it
+ * never applies render_from_camera (generate_ray :737-758 does) -- so images are only right when render space == camera
+ * space up to translation-free axes; host code that wants the intended camera passes render_from_camera = identity scenes. */
+typedef enum SgCameraKind { SG_CAMERA_PERSPECTIVE = 0, SG_CAMERA_ORTHOGRAPHIC = 1 } SgCameraKind;
 typedef struct SgCamera {
     float camera_from_raster[16];     /* row-major 4x4, ProjectiveCameraBase camera.rs:632 */
     float render_from_camera[16];     /* CameraTransform camera.rs:518                     */
@@ -233,6 +240,8 @@ typedef struct SgCamera {
     float shutter_close;
     float min_pos_differential_x[3], min_pos_differential_y[3];
     float min_dir_differential_x[3], min_dir_differential_y[3];
+    int32_t kind;                     /* SgCameraKind                                       */
+    int32_t pad;
 } SgCamera;
 
 /* ---- film (src/film.rs RgbFilm + PixelSensor) ------------------------------ */

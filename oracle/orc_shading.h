@@ -342,6 +342,7 @@ struct BSDF {
         case SG_MATERIAL_DIFFUSE: return spec_is_zero(r) ? BX_UNSET : (BX_DIFFUSE | BX_REFLECTION);                 // bxdf.rs:256-262
         case SG_MATERIAL_CONDUCTOR: return mf.effectively_smooth() ? (BX_SPECULAR | BX_REFLECTION) : (BX_GLOSSY | BX_REFLECTION);   // :447-453
         case SG_MATERIAL_COATED_DIFFUSE: return lay.flags();
+        case SG_MATERIAL_THIN_DIELECTRIC: return BX_REFLECTION | BX_TRANSMISSION | BX_SPECULAR;                    // bxdf.rs:873-875
         default: {                                                                                                 // :778-790
             int f = (eta == 1.0f) ? BX_TRANSMISSION : (BX_REFLECTION | BX_TRANSMISSION);
             return f | (mf.effectively_smooth() ? BX_SPECULAR : BX_GLOSSY);
@@ -351,6 +352,7 @@ struct BSDF {
     // local-space f
     Spec f_local(V3 wo, V3 wi) const {
         if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.f(wo, wi, r); }
+        if (kind == SG_MATERIAL_THIN_DIELECTRIC) return spec_const(0.0f);       // bxdf.rs:808-810
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // bxdf.rs:196-202
             if (!same_hemisphere(wo, wi)) return spec_const(0.0f);
@@ -388,6 +390,7 @@ struct BSDF {
     }
     Float pdf_local(V3 wo, V3 wi) const {
         if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.pdf(wo, wi, r); }
+        if (kind == SG_MATERIAL_THIN_DIELECTRIC) return 0.0f;                   // bxdf.rs:863-871
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // :240-254
             if (!same_hemisphere(wo, wi)) return 0.0f;
@@ -422,6 +425,20 @@ struct BSDF {
     bool sample_local(V3 wo, Float uc, V2 u, BSDFSample* bs) const {
         bs->eta = 1.0f; bs->proportional = false;
         if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.sample_f(wo, uc, u, r, bs, &bs->proportional); }
+        if (kind == SG_MATERIAL_THIN_DIELECTRIC) {                              // ThinDielectricBxDF::sample_f bxdf.rs:812-861
+            Float R = fresnel_dielectric(abs_cos_theta(wo), eta), T = 1.0f - R;
+            if (R < 1.0f) { R += sqr(T) * R / (1.0f - sqr(R)); T = 1.0f - R; }
+            const Float pr = R, pt = T;
+            if (pr == 0.0f && pt == 0.0f) return false;
+            if (uc < pr / (pr + pt)) {
+                V3 wi = v3(-wo.x, -wo.y, wo.z);
+                bs->f = spec_const(R / abs_cos_theta(wi)); bs->wi = wi; bs->pdf = pr / (pr + pt); bs->flags = BX_SPECULAR | BX_REFLECTION;
+            } else {
+                V3 wi = -wo;
+                bs->f = spec_const(T / abs_cos_theta(wi)); bs->wi = wi; bs->pdf = pt / (pr + pt); bs->flags = BX_SPECULAR | BX_TRANSMISSION;
+            }
+            return true;
+        }
         switch (kind) {
         case SG_MATERIAL_DIFFUSE: {                                             // :204-238
             V3 wi = sample_cosine_hemisphere(u);
@@ -818,6 +835,15 @@ struct CameraSample { V2 p_film, p_lens; Float time; Float filter_weight; };
 inline Ray camera_generate_ray(const SgCamera& cam, const CameraSample& cs, AuxRays* aux = nullptr) {
     V3 p_film = v3(cs.p_film.x, cs.p_film.y, 0.0f);
     V3 p_camera = xform_point(cam.camera_from_raster, p_film);
+    if (cam.kind == SG_CAMERA_ORTHOGRAPHIC) {                // OrthographicCamera::generate_ray_differential camera.rs:760-784
+        Ray ro; ro.o = p_camera; ro.d = v3(0, 0, 1);         // sic: returned in CAMERA space (no render_from_camera)
+        if (aux) {
+            aux->has = true;
+            aux->rxo = ro.o + v3(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2]); aux->rxd = ro.d;
+            aux->ryo = ro.o + v3(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2]); aux->ryd = ro.d;
+        }
+        return ro;
+    }
     Ray r; r.o = v3(0, 0, 0); r.d = normalize(p_camera);
     if (cam.lens_radius > 0.0f) {
         V2 pl = sample_uniform_disk_concentric(cs.p_lens);

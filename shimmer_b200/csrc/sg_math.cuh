@@ -24,11 +24,7 @@ static constexpr float kMachineEps = 1.1920929e-07f * 0.5f;     // float.rs:16
 // gamma(n) = n*eps/2 / (1 - n*eps/2), float.rs:88-90 -- evaluated in f32 exactly like the reference
 SGD float gamma_n(int n) { return ((float)n * kMachineEps) / (1.0f - (float)n * kMachineEps); }
 
-// NaN stays NaN: the reference's bit increment keeps x86's / ARM's default NaN (0xFFC00000 / 0x7FC00000) a NaN, whereas
-// CUDA's canonical NaN 0x7FFFFFFF + 1 would wrap to -0.0 (seen in the sphere's interval arithmetic, where the reference
-// relies on f32::min/max ignoring NaN bounds).
 SGD float next_up(float v) {                                    // float.rs:53-68
-    if (isnan(v)) return v;
     if (isinf(v) && v > 0.0f) return v;
     if (v == -0.0f) v = 0.0f;
     uint32_t u = __float_as_uint(v);
@@ -36,13 +32,19 @@ SGD float next_up(float v) {                                    // float.rs:53-6
     return __uint_as_float(u);
 }
 SGD float next_down(float v) {                                  // float.rs:72-86
-    if (isnan(v)) return v;
     if (isinf(v) && v < 0.0f) return v;
     if (v == 0.0f) v = -0.0f;
     uint32_t u = __float_as_uint(v);
     u = (v > 0.0f) ? u - 1u : u + 1u;
     return __uint_as_float(u);
 }
+// NaN-preserving variants for the interval arithmetic of the sphere (sg_sphere.cuh): the reference's bit increment keeps
+// x86's / ARM's default NaN (0xFFC00000 / 0x7FC00000) a NaN, whereas CUDA's canonical NaN 0x7FFFFFFF + 1 would wrap to
+// -0.0; Sphere::basic_intersect relies on f32::min/max ignoring NaN interval bounds for axis-aligned rays.  The hot
+// shading paths (offset_ray_origin, Point3fi construction) keep the two-instruction-cheaper versions above: they only see
+// NaN when the path is already degenerate.
+SGD float next_up_n(float v) { return isnan(v) ? v : next_up(v); }
+SGD float next_down_n(float v) { return isnan(v) ? v : next_down(v); }
 SGD float sqr(float x) { return x * x; }
 SGD float clampf(float x, float lo, float hi) { float r = x; if (r < lo) r = lo; if (r > hi) r = hi; return r; }   // f32::clamp
 SGD float dop(float a, float b, float c, float d) {             // math.rs:173-178

@@ -334,6 +334,7 @@ template <int KIND> struct BSDF {
     SGD float3 from_local(float3 v) const { return v.x * fx + v.y * fy + v.z * fz; }               // frame.rs:51-53
     SGD int flags() const {
         if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.flags();
+        if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return BX_REFLECTION | BX_TRANSMISSION | BX_SPECULAR;   // bxdf.rs:873-875
         if (KIND == SG_MATERIAL_DIFFUSE) return spec_zero(r) ? 0 : (BX_DIFFUSE | BX_REFLECTION);     // bxdf.rs:256-262
         if (KIND == SG_MATERIAL_CONDUCTOR) return (mf.smooth() ? BX_SPECULAR : BX_GLOSSY) | BX_REFLECTION;   // :447-453
         int f = (eta == 1.0f) ? BX_TRANSMISSION : (BX_REFLECTION | BX_TRANSMISSION);               // :778-790
@@ -341,6 +342,7 @@ template <int KIND> struct BSDF {
     }
     SGD Spec f_local(float3 wo, float3 wi) const {
         if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.f(wo, wi, layer_rng());
+        if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return spec1(0.0f);                                 // bxdf.rs:808-810
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :196-202
             if (!same_hemisphere(wo, wi)) return spec1(0.0f);
             return r * kInvPi;
@@ -374,6 +376,7 @@ template <int KIND> struct BSDF {
     }
     SGD float pdf_local(float3 wo, float3 wi) const {
         if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.pdf(wo, wi, layer_rng());
+        if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return 0.0f;                                        // bxdf.rs:863-871
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :240-254
             if (!same_hemisphere(wo, wi)) return 0.0f;
             return fabsf(wi.z) * kInvPi;
@@ -405,6 +408,20 @@ template <int KIND> struct BSDF {
     SGD bool sample_local(float3 wo, float uc, float2 u, BSDFSample& bs, bool& prop) const {
         bs.eta = 1.0f; prop = false;
         if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.sample_f(wo, uc, u, layer_rng(), bs, prop);
+        if (KIND == SG_MATERIAL_THIN_DIELECTRIC) {                                                   // ThinDielectricBxDF::sample_f bxdf.rs:812-861
+            float R = fresnel_dielectric(fabsf(wo.z), eta), T = 1.0f - R;
+            if (R < 1.0f) { R += sqr(T) * R / (1.0f - sqr(R)); T = 1.0f - R; }
+            const float pr = R, pt = T;
+            if (pr == 0.0f && pt == 0.0f) return false;
+            if (uc < pr / (pr + pt)) {
+                const float3 wi = f3(-wo.x, -wo.y, wo.z);
+                bs.f = spec1(R / fabsf(wi.z)); bs.wi = wi; bs.pdf = pr / (pr + pt); bs.flags = BX_SPECULAR | BX_REFLECTION;
+            } else {
+                const float3 wi = -wo;
+                bs.f = spec1(T / fabsf(wi.z)); bs.wi = wi; bs.pdf = pt / (pr + pt); bs.flags = BX_SPECULAR | BX_TRANSMISSION;
+            }
+            return true;
+        }
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :204-238
             float3 wi = sample_cosine_hemisphere(u);
             if (wo.z < 0.0f) wi.z *= -1.0f;
@@ -785,6 +802,11 @@ SGD void camera_stage(const DScene& sc, uint32_t option_flags, int px, int py, R
     }
     weight = 1.0f;
     float3 p_camera = xform_point(sc.camera.camera_from_raster, f3(p_film.x, p_film.y, 0.0f));
+    if (sc.camera.kind == SG_CAMERA_ORTHOGRAPHIC) {                    // OrthographicCamera::generate_ray_differential camera.rs:760-784
+        o = p_camera; d = f3(0.0f, 0.0f, 1.0f);                        // sic: stays in CAMERA space (see SgCameraKind)
+        if (aux) camera_aux(sc, p_camera, p_lens, o, aux);
+        return;
+    }
     o = f3(0.0f, 0.0f, 0.0f);
     d = normalize3(p_camera);
     if (sc.camera.lens_radius > 0.0f) {

@@ -21,39 +21,39 @@ struct DSphere {
 struct Ival { float lo, hi; };
 SGD Ival iv(float v) { Ival r; r.lo = v; r.hi = v; return r; }
 SGD Ival iv_new(float a, float b) { Ival r; r.lo = fminf(a, b); r.hi = fmaxf(a, b); return r; }                 // interval.rs:34-41
-SGD Ival iv_ve(float v, float e) { Ival r; ival(v, e, r.lo, r.hi); return r; }                                 // :47-56
+SGD Ival iv_ve(float v, float e) { Ival r; if (e == 0.0f) { r.lo = v; r.hi = v; } else { r.lo = next_down_n(v - e); r.hi = next_up_n(v + e); } return r; }                                 // :47-56
 SGD float iv_mid(Ival a) { return (a.lo + a.hi) / 2.0f; }
 SGD bool iv_in_range(Ival a, float v) { return v >= a.lo && v <= a.hi; }
-SGD Ival iv_add(Ival a, Ival b) { Ival r; r.lo = next_down(a.lo + b.lo); r.hi = next_up(a.hi + b.hi); return r; }   // :353-355
-SGD Ival iv_sub(Ival a, Ival b) { Ival r; r.lo = next_down(a.lo - b.lo); r.hi = next_up(a.hi - b.hi); return r; }   // :362-367 (sic: low-low, high-high)
+SGD Ival iv_add(Ival a, Ival b) { Ival r; r.lo = next_down_n(a.lo + b.lo); r.hi = next_up_n(a.hi + b.hi); return r; }   // :353-355
+SGD Ival iv_sub(Ival a, Ival b) { Ival r; r.lo = next_down_n(a.lo - b.lo); r.hi = next_up_n(a.hi - b.hi); return r; }   // :362-367 (sic: low-low, high-high)
 SGD Ival iv_mul(Ival a, Ival b) {                                                                              // :374-392, fold(NAN, min/max)
     const float p0 = a.lo * b.lo, p1 = a.hi * b.lo, p2 = a.lo * b.hi, p3 = a.hi * b.hi;
     Ival r;
-    r.lo = fminf(fminf(fminf(next_down(p0), next_down(p1)), next_down(p2)), next_down(p3));
-    r.hi = fmaxf(fmaxf(fmaxf(next_up(p0), next_up(p1)), next_up(p2)), next_up(p3));
+    r.lo = fminf(fminf(fminf(next_down_n(p0), next_down_n(p1)), next_down_n(p2)), next_down_n(p3));
+    r.hi = fmaxf(fmaxf(fmaxf(next_up_n(p0), next_up_n(p1)), next_up_n(p2)), next_up_n(p3));
     return r;
 }
 SGD Ival iv_div(Ival a, Ival b) {                                                                              // :399-425
     Ival r;
     if (iv_in_range(b, 0.0f)) { r.lo = -INFINITY; r.hi = INFINITY; return r; }
     const float q0 = a.lo / b.lo, q1 = a.hi / b.lo, q2 = a.lo / b.hi, q3 = a.hi / b.hi;
-    r.lo = fminf(fminf(fminf(next_down(q0), next_down(q1)), next_down(q2)), next_down(q3));
-    r.hi = fmaxf(fmaxf(fmaxf(next_up(q0), next_up(q1)), next_up(q2)), next_up(q3));
+    r.lo = fminf(fminf(fminf(next_down_n(q0), next_down_n(q1)), next_down_n(q2)), next_down_n(q3));
+    r.hi = fmaxf(fmaxf(fmaxf(next_up_n(q0), next_up_n(q1)), next_up_n(q2)), next_up_n(q3));
     return r;
 }
 SGD Ival iv_scale(float f, Ival a) {                                                                           // Float * Interval :451-457
-    if (f > 0.0f) return iv_new(next_down(f * a.lo), next_up(f * a.hi));
-    return iv_new(next_down(f * a.hi), next_up(f * a.lo));
+    if (f > 0.0f) return iv_new(next_down_n(f * a.lo), next_up_n(f * a.hi));
+    return iv_new(next_down_n(f * a.hi), next_up_n(f * a.lo));
 }
 SGD Ival iv_sqr(Ival a) {                                                                                      // :99-117
     float alow = fabsf(a.lo), ahigh = fabsf(a.hi);
     if (alow > ahigh) { const float t = alow; alow = ahigh; ahigh = t; }
     Ival r;
-    r.lo = iv_in_range(a, 0.0f) ? 0.0f : next_down(alow * alow);
-    r.hi = next_up(ahigh * ahigh);
+    r.lo = iv_in_range(a, 0.0f) ? 0.0f : next_down_n(alow * alow);
+    r.hi = next_up_n(ahigh * ahigh);
     return r;
 }
-SGD Ival iv_sqrt(Ival a) { Ival r; r.lo = next_down(sqrtf(a.lo)); r.hi = next_up(sqrtf(a.hi)); return r; }      // :498-505
+SGD Ival iv_sqrt(Ival a) { Ival r; r.lo = next_down_n(sqrtf(a.lo)); r.hi = next_up_n(sqrtf(a.hi)); return r; }      // :498-505
 
 struct V3i { Ival x, y, z; };
 SGD float3 v3i_mid(const V3i& v) { return f3(iv_mid(v.x), iv_mid(v.y), iv_mid(v.z)); }

@@ -23,6 +23,11 @@ SGD void camera_aux(const DScene& sc, float3 p_camera, float2 p_lens, float3 o_c
     const SgCamera& cam = sc.camera;
     const float3 dxc = f3(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2]), dyc = f3(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2]);
     float3 rxo, rxd, ryo, ryd;
+    if (cam.kind == SG_CAMERA_ORTHOGRAPHIC) {                          // camera.rs:775-778: shifted origins, same direction, camera space
+        aux->has = true;
+        aux->rxo = o_cam + dxc; aux->rxd = f3(0.0f, 0.0f, 1.0f); aux->ryo = o_cam + dyc; aux->ryd = f3(0.0f, 0.0f, 1.0f);
+        return;
+    }
     if (cam.lens_radius > 0.0f) {
         float2 pl = sample_disk_concentric(p_lens);
         pl.x = cam.lens_radius * pl.x; pl.y = cam.lens_radius * pl.y;

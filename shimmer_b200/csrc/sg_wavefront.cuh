@@ -55,9 +55,9 @@ SGD void aux_store(const PathState& st, uint32_t path, const AuxRays& r) {
     st.aux2[path] = make_float4(r.ryo.z, r.ryd.x, r.ryd.y, r.ryd.z);
 }
 
-enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_NKINDS = 5 };
+enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_THIN = 5, Q_NKINDS = 6 };
 // per-depth counter block (uint32 x 16)
-enum { C_NRAY = 0, C_NSHADE = 1 /*..5*/, C_NSHADOW = 6, C_CUR_CLOSEST = 7, C_CUR_SHADOW = 8, C_STRIDE = 16 };
+enum { C_NRAY = 0, C_NSHADE = 1 /*..6*/, C_NSHADOW = 7, C_CUR_CLOSEST = 8, C_CUR_SHADOW = 9, C_STRIDE = 16 };
 
 struct Queues {
     uint32_t* ray[2];
@@ -410,6 +410,25 @@ __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DSce
 // sample_ld, 3 = sample_f, 4 = pdf after sample_f); does not advance the path stream.  Same as the oracle.
 SGD uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s0 ^ (site * 0x9e3779b97f4a7c15ULL)); }
 
+// Hit -> SurfaceInteraction for scenes that hold more than top-level triangles: Sphere::intersect (sphere.rs:286-293; hit_b
+// carries p_obj), BilinearPatch::intersect (bilinear_patch.rs:496-509; hit_b carries (u, v)), TransformedPrimitive::intersect
+// (primitive.rs:155-169) or a plain triangle.
+template <bool TEX>
+__device__ __noinline__ Surf surface_general(const DScene& sc, const TriGeo& geo, float4 hb, float3 rd, int inst, SurfTex* sx, float3& wo_si) {
+    Surf s;
+    if (geo.mesh & kSphereBit) {
+        const DSphere& S = sc.spheres[geo.mesh & ~kSphereBit];
+        s = make_surface_sphere<TEX>(S, f3(hb.x, hb.y, hb.z), sx);
+        transform_interaction<TEX>(sc, S.m, S.mi, rd, s, sx, wo_si);
+    } else if (geo.mesh & kPatchBit) {
+        s = make_surface_patch<TEX>(sc, geo.mesh & ~kPatchBit, hb.x, hb.y, sx);
+    } else {
+        s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, sx);
+        if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, sx, wo_si);
+    }
+    return s;
+}
+
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
 #ifndef SG_SHADE_MIN_BLOCKS
@@ -487,19 +506,10 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             SurfTex sx;
             Surf s;
             float3 wo_si = wo;                                   // SurfaceInteraction::wo (what sample_ld reads, integrator.rs:905-917)
-            if (st.hit_inst != nullptr && (geo.mesh & kSphereBit)) {     // Sphere::intersect sphere.rs:286-293: hit_b carries p_obj
-                const DSphere& S = sc.spheres[geo.mesh & ~kSphereBit];
-                s = make_surface_sphere<TEX>(S, f3(hb.x, hb.y, hb.z), &sx);
-                transform_interaction<TEX>(sc, S.m, S.mi, rd, s, &sx, wo_si);
-            } else if (st.hit_inst != nullptr && (geo.mesh & kPatchBit)) {   // BilinearPatch::intersect: hit_b carries (u, v)
-                s = make_surface_patch<TEX>(sc, geo.mesh & ~kPatchBit, hb.x, hb.y, &sx);
-            } else {
-                s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
-                if (st.hit_inst != nullptr) {                    // TransformedPrimitive::intersect primitive.rs:155-169
-                    const int inst = st.hit_inst[path];
-                    if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, &sx, wo_si);
-                }
-            }
+            // scenes with instances / spheres / patches resolve the hit out of line, so that triangle-only scenes (hit_inst ==
+            // nullptr) keep a small kernel: the shade kernels are sensitive to instruction-cache footprint
+            if (st.hit_inst == nullptr) s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
+            else s = surface_general<TEX>(sc, geo, hb, rd, st.hit_inst[path], &sx, wo_si);
 
             // emission + MIS against light sampling, :798-813
             if (light_id >= 0) {
@@ -654,7 +664,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 st.flags[path] = (uint32_t)pdepth | (specular_bounce ? kFlagSpecular : 0u) | (any_non_specular ? kFlagNonSpecular : 0u) |
                                  (TEX && aux.has ? kFlagAux : 0u);
             }
-            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE) st.lpdf[path] = lam.pdf;   // terminate_secondary
+            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC) st.lpdf[path] = lam.pdf;   // terminate_secondary
             want_next = alive;
         }
         __syncwarp();

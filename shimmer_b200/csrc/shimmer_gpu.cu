@@ -56,7 +56,7 @@ struct SgScene {
     Workspace ws;
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
-    bool kinds_present[4] = {false, false, false, false};
+    bool kinds_present[5] = {false, false, false, false, false};
     bool instanced = false;         // object instances: k_trace<.., INST = true> and the hit_inst path-state array
     bool tex_path = false;          // image textures or a non-zero constant displacement: k_shade<KIND, true>
     double* d_film = nullptr; size_t film_pixels = 0;
@@ -147,6 +147,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     if (desc->abi_version != SG_ABI_VERSION) return fail(SG_ERR_INVALID_ARGUMENT, "SgSceneDesc.abi_version mismatch");
     if (desc->n_primitives > 0 && (!desc->nodes || !desc->primitives)) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
     if (desc->n_spheres && !desc->spheres) return fail(SG_ERR_INVALID_ARGUMENT, "sphere array missing");
+    if (desc->camera.kind != SG_CAMERA_PERSPECTIVE && desc->camera.kind != SG_CAMERA_ORTHOGRAPHIC) return fail(SG_ERR_UNSUPPORTED, "camera kind is not on the GPU path");
     if (desc->n_primitives >= (1u << 31)) return fail(SG_ERR_UNSUPPORTED, "too many primitives");
     // validate references so device code never reads out of bounds
     const uint32_t n_top_nodes = desc->n_top_nodes ? desc->n_top_nodes : desc->n_nodes;
@@ -196,7 +197,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     }
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
-        if (m.kind < 0 || m.kind > SG_MATERIAL_COATED_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.kind < 0 || m.kind > SG_MATERIAL_THIN_DIELECTRIC) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
         if (m.kind == SG_MATERIAL_COATED_DIFFUSE && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra || m.spec_c < 0 || m.spec_c >= (int32_t)desc->n_spectra ||
                                                      m.max_depth < 0 || m.n_samples < 1))
             return fail(SG_ERR_INVALID_ARGUMENT, "coated diffuse material parameters out of range");
@@ -531,7 +532,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
                 if (s->tex_path) k_shade<KIND, true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
                 else k_shade<KIND, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
                 ++launches; }
-            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE)
+            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE) SHADE(SG_MATERIAL_THIN_DIELECTRIC)
 #undef SHADE
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }

@@ -12,14 +12,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 5
+SG_ABI_VERSION = 6
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
 SG_MESH_BILINEAR = 32
+SG_CAMERA_PERSPECTIVE, SG_CAMERA_ORTHOGRAPHIC = 0, 1
 SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
 SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
-SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE = 0, 1, 2, 3
+SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE, SG_MATERIAL_THIN_DIELECTRIC = 0, 1, 2, 3, 4
 SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
 SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE, SG_LIGHT_DIFFUSE_AREA_SPHERE = 0, 1, 2, 3
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
@@ -95,7 +96,8 @@ class SgCamera(C.Structure):
                 ("lens_radius", C.c_float), ("focal_distance", C.c_float), ("shutter_open", C.c_float),
                 ("shutter_close", C.c_float),
                 ("min_pos_differential_x", C.c_float * 3), ("min_pos_differential_y", C.c_float * 3),
-                ("min_dir_differential_x", C.c_float * 3), ("min_dir_differential_y", C.c_float * 3)]
+                ("min_dir_differential_x", C.c_float * 3), ("min_dir_differential_y", C.c_float * 3),
+                ("kind", C.c_int32), ("pad", C.c_int32)]
 
 
 class SgFilm(C.Structure):

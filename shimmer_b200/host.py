@@ -301,6 +301,11 @@ class SceneBuilder:
                                    flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
         return len(self.materials) - 1
 
+    def thin_dielectric(self, eta):
+        """ThinDielectricMaterial::create (material.rs:666-700): `eta` spectrum only."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_THIN_DIELECTRIC, spec_a=self.spectrum(eta), spec_b=-1, flags=0, ur=0.0, vr=0.0))
+        return len(self.materials) - 1
+
     def coated_diffuse(self, reflectance, eta=("const", 1.5), roughness=0.0, thickness=0.01, albedo=("const", 0.0), g=0.0,
                        max_depth=10, n_samples=1, remap=True, reflectance_tex=None, displacement_tex=None):
         """CoatedDiffuseMaterial::create (material.rs:820-903); displacement defaults to None."""
@@ -314,7 +319,8 @@ class SceneBuilder:
         return len(self.materials) - 1
 
     # -- camera / film -----------------------------------------------------------------------
-    def set_camera(self, pos, look, up, fov, resolution, lens_radius=0.0, focal_distance=1e6, crop=None):
+    def set_camera(self, pos, look, up, fov, resolution, lens_radius=0.0, focal_distance=1e6, crop=None, kind="perspective",
+                   screen_window=None):
         """PerspectiveCamera::create/new (camera.rs:839-963) + CameraTransform::new (:506-523) +
         ProjectiveCameraBase::new (:595-642)."""
         W, H = resolution
@@ -331,7 +337,10 @@ class SceneBuilder:
         render_from_camera = self.render_from_world * world_from_camera
         frame = W / H
         screen = (-frame, frame, -1.0, 1.0) if frame > 1.0 else (-1.0, 1.0, -1.0 / frame, 1.0 / frame)
-        screen_from_camera = Transform.perspective(fov, 1e-2, 1000.0)
+        if screen_window is not None:                       # `screenwindow` (camera.rs:691-707)
+            screen = (screen_window[0], screen_window[1], screen_window[2], screen_window[3])
+        # OrthographicCamera::new: Transform::orthographic(0, 1) = identity (camera.rs:718, transform.rs:125-128)
+        screen_from_camera = Transform.identity() if kind == "orthographic" else Transform.perspective(fov, 1e-2, 1000.0)
         ndc_from_screen = Transform.scale(1.0 / (screen[1] - screen[0]), 1.0 / (screen[3] - screen[2]), 1.0) * \
             Transform.translate((-screen[0], -screen[3], 0.0))
         raster_from_ndc = Transform.scale(W, -H, 1.0)
@@ -351,7 +360,15 @@ class SceneBuilder:
         cam.dy_camera[:] = dy_camera.astype(np.float32).tolist()
         cam.lens_radius = lens_radius; cam.focal_distance = focal_distance
         cam.shutter_open = 0.0; cam.shutter_close = 1.0
-        self._find_minimum_differentials(cam, W, H)
+        if kind == "orthographic":                          # camera.rs:727-735: vector transforms of X / Y, fixed differentials
+            cam.kind = ffi.SG_CAMERA_ORTHOGRAPHIC
+            m32 = camera_from_raster.m32()
+            cam.dx_camera[:] = m32[:3, 0].tolist(); cam.dy_camera[:] = m32[:3, 1].tolist()
+            cam.min_pos_differential_x[:] = m32[:3, 0].tolist(); cam.min_pos_differential_y[:] = m32[:3, 1].tolist()
+            cam.min_dir_differential_x[:] = [0.0, 0.0, 0.0]; cam.min_dir_differential_y[:] = [0.0, 0.0, 0.0]
+        else:
+            cam.kind = ffi.SG_CAMERA_PERSPECTIVE
+            self._find_minimum_differentials(cam, W, H)
         self.camera = cam
         film = ffi.SgFilm()
         film.full_resolution[:] = [W, H]

@@ -419,6 +419,22 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         return sphere_tiny_scene(kind, resolution)
     if kind in PATCH_KINDS:
         return patch_tiny_scene(kind, resolution)
+    if kind == "ortho":
+        # OrthographicCamera (camera.rs:657-827) looking down +z with up = y: render_from_camera is the identity in the
+        # camera-world rendering space, where the reference's camera-space ray (see SgCameraKind) is also the right one.
+        b = SceneBuilder()
+        b.set_camera(pos=(0.0, 0.8, -3.0), look=(0.0, 0.8, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution, kind="orthographic",
+                     screen_window=(-1.8, 1.8, -1.8, 1.8))
+        ground = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="trilinear", su=3.0, sv=3.0))
+        P, I, Nn, UV = uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)
+        b.add_mesh(P, I, b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0), n=Nn, uv=UV)
+        gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+        b.add_mesh(gp, gi, ground, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+        wp, wi = _quad((-3, 0.0, 2.0), (-3, 3, 2.0), (3, 3, 2.0), (3, 0.0, 2.0))
+        b.add_mesh(wp, wi, ground, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+        lp, li = _quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
+        b.add_mesh(lp, li, b.diffuse(_white()), area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+        return b
     b = SceneBuilder()
     b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
     white = b.diffuse(_white())
@@ -432,6 +448,8 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         mat = b.dielectric(named_spectrum("glass-BK7"))
     elif kind == "roughglass":
         mat = b.dielectric(("const", 1.5), roughness=0.2)
+    elif kind == "thinglass":
+        mat = b.thin_dielectric(named_spectrum("glass-BK7"))
     elif kind == "coated":
         mat = b.coated_diffuse(_red())
     elif kind == "coatedrough":

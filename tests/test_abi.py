@@ -37,7 +37,7 @@ def test_struct_sizes_match_the_header_layout():
     assert C.sizeof(ffi.SgMaterial) == 64
     assert C.sizeof(ffi.SgTexture) == 64 and C.sizeof(ffi.SgImageLevel) == 16
     assert C.sizeof(ffi.SgLight) == 64
-    assert C.sizeof(ffi.SgObject) == 16 and C.sizeof(ffi.SgInstance) == 144 and C.sizeof(ffi.SgSceneDesc) == 672 and C.sizeof(ffi.SgSphere) == 160
+    assert C.sizeof(ffi.SgObject) == 16 and C.sizeof(ffi.SgInstance) == 144 and C.sizeof(ffi.SgSceneDesc) == 680 and C.sizeof(ffi.SgSphere) == 160
     assert C.sizeof(ffi.SgFilmPixel) == 32
     assert C.sizeof(ffi.SgHit) == 32
     assert C.sizeof(ffi.SgRenderParams) == 40

@@ -170,7 +170,7 @@ def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
     assert rmse < 0.01
 
 
-@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough"] + list(scenes.TEXTURED_KINDS)
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough", "ortho", "thinglass"] + list(scenes.TEXTURED_KINDS)
                          + list(scenes.INSTANCED_KINDS))
 def test_tiny_scene_films(kind):
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
@@ -481,4 +481,16 @@ def test_patch_scene_films(kind):
     ref, rst, _ = orc.render(sc, orc.make_params(seed=4, spp=8))
     _film_close(film, ref, frac=0.99)
     assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-3 * rst.closest_hit_rays
+    integ.close()
+
+
+def test_orthographic_camera_rays_bit_exact():
+    sc = scenes.tiny_scene("ortho", resolution=(16, 16)).build()
+    integ = create_integrator("wavefront", {}, sc, {"pixelsamples": 4})
+    rng = np.random.default_rng(1)
+    xy = rng.integers(0, 16, (512, 2)).astype(np.int32); si = rng.integers(0, 4, 512).astype(np.int32)
+    opts = Options(seed=9, pixel_samples=4)
+    rays, lam = integ.camera_rays(opts, xy, si)
+    r2, l2 = orc.camera_rays(sc, orc.make_params(seed=9, spp=4), xy, si)
+    assert np.array_equal(rays, r2) and np.allclose(lam, l2, rtol=2e-6)
     integ.close()

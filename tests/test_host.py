@@ -112,3 +112,19 @@ def test_mesh_scene_generator_is_deterministic_and_sized():
 def test_full_size_c2_triangle_count_formula():
     # BASELINE.json configs[1]: 708 x 708 lat-long grid ~ 1.0 M triangles
     assert 2 * 708 * 707 + 4 == 1001116
+
+
+def test_orthographic_camera_rays_closed_form():
+    """OrthographicCamera::generate_ray_differential (camera.rs:760-784): origin = camera_from_raster(p_film) on the z = 0
+    plane of the screen window, direction +z, for every pixel; the oracle returns it in camera space as the reference does."""
+    import orc
+    from shimmer_b200 import scenes
+    sc = scenes.tiny_scene("ortho", resolution=(16, 16)).build()
+    assert sc.desc.camera.kind == 1
+    xy = np.array([[x, y] for y in range(16) for x in range(16)], np.int32); si = np.zeros(len(xy), np.int32)
+    rays, lam = orc.camera_rays(sc, orc.make_params(seed=3, spp=1, flags=1), xy, si)       # SG_OPT_DISABLE_PIXEL_JITTER: pixel centres
+    assert np.array_equal(rays[:, 3:], np.tile(np.float32([0, 0, 1]), (256, 1)))
+    want_x = -1.8 + (xy[:, 0] + 0.5) / 16 * 3.6; want_y = 1.8 - (xy[:, 1] + 0.5) / 16 * 3.6
+    assert np.allclose(rays[:, 0], want_x, atol=1e-5) and np.allclose(rays[:, 1], want_y, atol=1e-5) and np.allclose(rays[:, 2], 0.0, atol=1e-6)
+    film, st, _ = orc.render(sc, orc.make_params(seed=1, spp=16))
+    assert np.isfinite(film).all() and film[:, :3].sum() > 0
