@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 6
+#define SG_ABI_VERSION 7
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -146,12 +146,22 @@ typedef enum SgMaterialKind {
     SG_MATERIAL_DIELECTRIC = 2, /* DielectricMaterial material.rs:600-662  spec_a = eta (`Spectrum`)     */
     SG_MATERIAL_COATED_DIFFUSE = 3, /* CoatedDiffuseMaterial material.rs:913-992: spec_a = reflectance, spec_b = albedo,
                                       spec_c = eta, thickness, g, max_depth, n_samples (LayeredBxDF bxdf.rs:883-1620) */
-    SG_MATERIAL_THIN_DIELECTRIC = 4 /* ThinDielectricMaterial material.rs:666-760 / ThinDielectricBxDF bxdf.rs:797-880: spec_a = eta */
+    SG_MATERIAL_THIN_DIELECTRIC = 4, /* ThinDielectricMaterial material.rs:666-760 / ThinDielectricBxDF bxdf.rs:797-880: spec_a = eta */
+    SG_MATERIAL_COATED_CONDUCTOR = 5, /* CoatedConductorMaterial material.rs:995-1283 / CoatedConductorBxDF bxdf.rs:460-516 (LayeredBxDF<Dielectric,
+                                        Conductor>): interface = u/v_roughness, spec_c (eta), thickness, g, spec_b (albedo), max_depth, n_samples;
+                                        conductor = spec_a (eta) + spec_d (k), or SG_MAT_CONDUCTOR_REFLECTANCE: spec_a = reflectance;
+                                        u/v_roughness2 = conductor roughness (IGNORED when remaproughness is set: material.rs:1237-1241
+                                        derives the conductor alpha from the INTERFACE roughness -- reproduced) */
+    SG_MATERIAL_MIX = 6             /* MixMaterial material.rs:1286-1330: mix_materials[2], amount = mix_amount or tex_mix_amount.  Resolved per
+                                       hit before shading (interaction.rs:206-221).  The reference draws its random number from a per-thread
+                                       SmallRng::from_entropy() (integrator.rs:255); here it comes from a generator seeded by the path stream's
+                                       state (same rule as the LayeredBxDF's), so renders stay reproducible. */
 } SgMaterialKind;
 enum {
     SG_MAT_REMAP_ROUGHNESS = 1,  /* `remaproughness`, default true                      */
-    SG_MAT_HAS_DISPLACEMENT = 2  /* material stores Some(displacement) -> bump_map runs
+    SG_MAT_HAS_DISPLACEMENT = 2, /* material stores Some(displacement) -> bump_map runs
                                     (always true for Diffuse: material.rs:280)           */
+    SG_MAT_CONDUCTOR_REFLECTANCE = 4 /* coated conductor given by `reflectance` (material.rs:1225-1233): spec_a = reflectance, no k */
 };
 typedef struct SgMaterial {
     int32_t kind;
@@ -169,6 +179,14 @@ typedef struct SgMaterial {
     int32_t tex_reflectance;  /* SpectrumImageTexture for `reflectance` (diffuse / coated diffuse) or -1 -> spec_a */
     int32_t tex_displacement; /* FloatImageTexture for `displacement` (bump_map, material.rs:1477-1509) or -1     */
     int32_t pad2[2];
+    int32_t spec_d;           /* coated conductor: conductor k                                                              */
+    float   u_roughness2;     /* coated conductor: `conductor.uroughness` / `conductor.vroughness`                          */
+    float   v_roughness2;
+    int32_t normal_map;       /* three-channel image texture id (level 0 is read with Image::bilerp_channel_wrapped, repeat) or -1;
+                                 only consulted when the material has NO displacement (interaction.rs:229-244, material.rs:1453-1474) */
+    int32_t mix_materials[2]; /* SG_MATERIAL_MIX: the two materials (may be mixes themselves; cycles are rejected)          */
+    float   mix_amount;       /* `amount` (0.5) when tex_mix_amount < 0                                                     */
+    int32_t tex_mix_amount;   /* FloatImageTexture for `amount` or -1                                                       */
 } SgMaterial;
 
 /* ---- image textures (src/texture.rs:393-404,700-808,896-936, src/mipmap.rs:121-331, src/image.rs:134-177,619-646) ------
@@ -198,15 +216,28 @@ typedef struct SgTexture {
     int32_t  invert;
     float    su, sv, du, dv;   /* UVMapping (texture.rs:896-936)         */
     int32_t  spectrum_type;    /* SgSpectrumType (three-channel spectrum textures) */
-    int32_t  pad[3];
+    int32_t  mapping;          /* index into SgSceneDesc.texture_mappings, or -1 = UVMapping with su, sv, du, dv above */
+    int32_t  pad[2];
 } SgTexture;
+/* `SphericalMapping`, `CylindricalMapping`, `PlanarMapping` (texture.rs:938-1035) as written there -- including the spherical
+ * mapping's st = (theta/pi, theta/2pi) (both from theta, :960-963) and the cylindrical s = pi + atan2(y, x)/2pi (:991). */
+typedef enum SgTextureMappingKind { SG_MAPPING_SPHERICAL = 1, SG_MAPPING_CYLINDRICAL = 2, SG_MAPPING_PLANAR = 3 } SgTextureMappingKind;
+typedef struct SgTextureMapping {
+    int32_t kind;                     /* SgTextureMappingKind                                   */
+    float   texture_from_render[16];  /* Transform::m, row-major (affine)                       */
+    float   vs[3], vt[3];             /* planar: `v1`, `v2`                                     */
+    float   ds, dt;                   /* planar: `udelta`, `vdelta`                             */
+    int32_t pad[3];
+} SgTextureMapping;
 
 /* ---- lights (src/light.rs) ------------------------------------------------- */
 typedef enum SgLightKind {
     SG_LIGHT_DIFFUSE_AREA = 0,     /* DiffuseAreaLight light.rs:524-694 over one Triangle */
     SG_LIGHT_POINT = 1,            /* PointLight light.rs:403-519                         */
     SG_LIGHT_UNIFORM_INFINITE = 2, /* UniformInfiniteLight light.rs:697-803               */
-    SG_LIGHT_DIFFUSE_AREA_SPHERE = 3 /* DiffuseAreaLight over a Sphere (sphere.rs:299-457): tri = index into spheres, area = Sphere::area() */
+    SG_LIGHT_DIFFUSE_AREA_SPHERE = 3, /* DiffuseAreaLight over a Sphere (sphere.rs:299-457): tri = index into spheres, area = Sphere::area() */
+    SG_LIGHT_IMAGE_INFINITE = 4    /* ImageInfinitelight light.rs:805-981: tri = index into env_maps, spectrum = the image colour space's
+                                      illuminant (dense), scale as computed by Light::create (light.rs:181-223) */
 } SgLightKind;
 typedef struct SgLight {
     int32_t kind;
@@ -220,6 +251,36 @@ typedef struct SgLight {
     float   scene_radius; /* infinite: preprocess() result (light.rs:797-802)              */
     float   pad[2];
 } SgLight;
+
+/* `PiecewiseConstant2D` over [0,1]^2 (sampling.rs:101-179) exactly as `new` builds it: per row v the conditional
+ * `func` (|f|, nu floats) and `cdf` (nu + 1 floats), then the marginal over the row integrals (func nv floats, cdf nv + 1 floats,
+ * `func_int`).  All arrays live in SgSceneDesc.spectrum_pool (float offsets).  The row integral `conditional_v[v].func_int`
+ * equals marg_func[v]. */
+typedef struct SgDistribution2D {
+    int32_t  nu, nv;
+    uint32_t func_off;        /* nv rows of nu floats          */
+    uint32_t cdf_off;         /* nv rows of nu + 1 floats      */
+    uint32_t marg_func_off;   /* nv floats                     */
+    uint32_t marg_cdf_off;    /* nv + 1 floats                 */
+    float    marg_integral;   /* marginal.func_int             */
+    uint32_t pad;
+} SgDistribution2D;
+/* The environment map of an `ImageInfinitelight` (light.rs:805-981): a square RGB image in the equal-area octahedral
+ * parameterisation, res x res x 3 linear f32 texels at texel_offset in SgSceneDesc.texels (row 0 first), looked up with
+ * `lookup_nearest_channel_wrapped(.., OctahedralSphere)` (image.rs:134-162,590-601) and turned into a spectrum per lookup by
+ * RgbIlluminantSpectrum::new (spectrum.rs:566-606; needs the rgb2spec table).  `distribution` is built from
+ * Image::get_default_sampling_distribution (image.rs:1379-1405: channel average per pixel), `compensated` from the same values
+ * minus their mean, clamped at 0 (light.rs:941-948); the path integrator samples the compensated one (allow_incomplete_pdf),
+ * SimplePath the plain one. */
+typedef struct SgEnvMap {
+    float    render_from_light[16];
+    float    light_from_render[16];
+    uint64_t texel_offset;
+    int32_t  res;
+    int32_t  pad;
+    SgDistribution2D distribution;
+    SgDistribution2D compensated;
+} SgEnvMap;
 
 /* ---- camera (src/camera.rs:830-1114 PerspectiveCamera) --------------------- */
 /* SG_CAMERA_ORTHOGRAPHIC = `OrthographicCamera` (camera.rs:657-827): ray origin camera_from_raster(p_film), direction +z,
@@ -282,6 +343,8 @@ typedef struct SgSceneDesc {
     /* rgb2spec coefficient table of the scene colour space (rgb_to_spectra.rs:16-45; third-party `rgb2spec` 0.1.1,
      * RGB2Spec{res, scale[res], data[3*res^3*3]}); required iff a three-channel texture exists */
     uint32_t rgb2spec_res; const float* rgb2spec_scale; const float* rgb2spec_data;
+    uint32_t n_texture_mappings; const SgTextureMapping* texture_mappings;
+    uint32_t n_env_maps;   const SgEnvMap*    env_maps;     /* texels / spectrum_pool hold their data */
     SgCamera camera;
     SgFilm   film;
 } SgSceneDesc;
@@ -304,7 +367,13 @@ typedef struct SgRenderParams {
     uint32_t option_flags;      /* SG_OPT_*                                                 */
     int32_t  max_paths_in_flight; /* wavefront width; 0 = library default (64 Mi paths, 18.5 GB) */
     int32_t  flags;             /* SG_RENDER_*                                              */
+    int32_t  integrator;        /* SgIntegratorKind: the `Integrator` registry name (integrator.rs:16-42) */
+    int32_t  integrator_flags;  /* SG_SIMPLEPATH_* (`samplelights`, `samplebsdf`, both default true: integrator.rs:24-31) */
 } SgRenderParams;
+/* "path" = PathIntegrator (integrator.rs:730-963), "simplepath" = SimplePathIntegrator (:570-728: no MIS, no Russian roulette,
+ * light sampling with complete pdfs), "randomwalk" = RandomWalkIntegrator (:458-568: uniform sphere sampling, no light sampling). */
+typedef enum SgIntegratorKind { SG_INTEGRATOR_PATH = 0, SG_INTEGRATOR_SIMPLE_PATH = 1, SG_INTEGRATOR_RANDOM_WALK = 2 } SgIntegratorKind;
+enum { SG_SIMPLEPATH_SAMPLE_LIGHTS = 1, SG_SIMPLEPATH_SAMPLE_BSDF = 2 };
 enum {
     SG_RENDER_COUNT_VISITS = 1,   /* count BVH nodes / triangles tested (slower; roofline accounting) */
     SG_RENDER_TIME_KERNELS = 2,   /* CUDA events around every traversal launch -> closest_ms/shadow_ms */
@@ -391,6 +460,9 @@ int sg_camera_rays(SgScene* scene, const SgRenderParams* params, int64_t n,
  * :393-404, value replicated) for n lookups of texture `tex`: the texture-filtering parity entry.
  * q: u v dudx dudy dvdx dvdy per lookup (TextureEvalContext); lambda: 4 wavelengths per lookup; out: 4 floats. */
 int sg_texture_eval(SgScene* scene, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out);
+/* Same with the full `TextureEvalContext` (texture.rs): pdp = p, dpdx, dpdy in render space (9 floats per lookup), which the
+ * spherical / cylindrical / planar mappings read (texture.rs:938-1035). */
+int sg_texture_eval_p(SgScene* scene, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda, float* out);
 
 /* Replaces `RgbFilm::get_pixel_rgb` (film.rs:720-738): rgb_sum/weight_sum then
  * output_rgb_from_sensor_rgb; out: 3 floats per pixel. */

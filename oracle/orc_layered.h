@@ -115,6 +115,52 @@ inline bool diffuse_sample(Spec r, V3 wo, V2 u, int sflags, BSDFSample* bs) {
     return true;
 }
 
+// ---- ConductorBxDF with sample flags (bxdf.rs:328-458): the bottom interface of CoatedConductorBxDF ----
+inline Spec fresnel_complex_spectral(Float c, Spec eta, Spec k) {                             // scattering.rs:94-105
+    Spec F; for (int i = 0; i < 4; ++i) F.v[i] = fresnel_complex(c, cx(eta.v[i], k.v[i]));
+    return F;
+}
+inline int conductor_flags(const TR& mf) { return mf.effectively_smooth() ? (BX_SPECULAR | BX_REFLECTION) : (BX_GLOSSY | BX_REFLECTION); }
+inline Spec conductor_f(const TR& mf, Spec eta, Spec k, V3 wo, V3 wi) {                       // :349-376
+    if (!same_hemisphere(wo, wi)) return spec_const(0.0f);
+    if (mf.effectively_smooth()) return spec_const(0.0f);
+    Float cto = abs_cos_theta(wo), cti = abs_cos_theta(wi);
+    if (cti == 0.0f || cto == 0.0f) return spec_const(0.0f);
+    V3 wm = wi + wo;
+    if (length_squared(wm) == 0.0f) return spec_const(0.0f);
+    wm = normalize(wm);
+    Spec F = fresnel_complex_spectral(abs_dot(wo, wm), eta, k);
+    return mf.d(wm) * F * mf.g(wo, wi) / (4.0f * cto * cti);
+}
+inline Float conductor_pdf(const TR& mf, V3 wo, V3 wi, int sflags) {                          // :424-445
+    if (!(sflags & SF_REFLECTION) || !same_hemisphere(wo, wi) || mf.effectively_smooth()) return 0.0f;
+    V3 wm = wo + wi;
+    if (length_squared(wm) == 0.0f) return 0.0f;
+    wm = face_forward(normalize(wm), v3(0, 0, 1));
+    return mf.pdf(wo, wm) / (4.0f * abs_dot(wo, wm));
+}
+inline bool conductor_sample(const TR& mf, Spec eta, Spec k, V3 wo, V2 u, int sflags, BSDFSample* bs) {   // :378-422
+    bs->eta = 1.0f;
+    if (!(sflags & SF_REFLECTION)) return false;
+    if (mf.effectively_smooth()) {
+        V3 wi = v3(-wo.x, -wo.y, wo.z);
+        bs->f = fresnel_complex_spectral(abs_cos_theta(wi), eta, k) / abs_cos_theta(wi);
+        bs->wi = wi; bs->pdf = 1.0f; bs->flags = BX_SPECULAR | BX_REFLECTION;
+        return true;
+    }
+    if (wo.z == 0.0f) return false;
+    V3 wm = mf.sample_wm(wo, u);
+    V3 wi = reflect(wo, wm);
+    if (!same_hemisphere(wo, wi)) return false;
+    Float pdf = mf.pdf(wo, wm) / (4.0f * abs_dot(wo, wm));
+    Float cto = abs_cos_theta(wo), cti = abs_cos_theta(wi);
+    if (cti == 0.0f || cto == 0.0f) return false;
+    Spec F = fresnel_complex_spectral(abs_dot(wo, wm), eta, k);
+    bs->f = mf.d(wm) * F * mf.g(wo, wi) / (4.0f * cto * cti);
+    bs->wi = wi; bs->pdf = pdf; bs->flags = BX_GLOSSY | BX_REFLECTION;
+    return true;
+}
+
 // scattering.rs:231-236
 inline Float henyey_greenstein(Float cos_t, Float g) {
     g = clampf(g, -0.99f, 0.99f);
@@ -139,15 +185,19 @@ inline Float sample_exponential(Float x, Float a) { return a * std::exp(-a * x);
 
 struct Layered {
     Float eta; TR mf;            // top: DielectricBxDF
-    Spec r;                      // bottom: DiffuseBxDF
+    Spec r;                      // bottom: DiffuseBxDF (CoatedDiffuse)
+    bool cond = false;           // bottom: ConductorBxDF (CoatedConductor, bxdf.rs:460-463) with ce, ck, mfb
+    Spec ce, ck; TR mfb;
     Spec albedo; Float thickness, g; int max_depth, n_samples;
 
     // TopOrBottomBxDF dispatch (bxdf.rs:1622-1700)
-    int i_flags(bool top) const { return top ? dielectric_flags(eta, mf) : diffuse_flags(r); }
-    Spec i_f(bool top, V3 wo, V3 wi, bool radiance) const { return top ? dielectric_f(eta, mf, wo, wi, radiance) : diffuse_f(r, wo, wi); }
-    Float i_pdf(bool top, V3 wo, V3 wi, int sf) const { return top ? dielectric_pdf(eta, mf, wo, wi, sf) : diffuse_pdf(wo, wi, sf); }
+    int i_flags(bool top) const { return top ? dielectric_flags(eta, mf) : (cond ? conductor_flags(mfb) : diffuse_flags(r)); }
+    Spec i_f(bool top, V3 wo, V3 wi, bool radiance) const {
+        return top ? dielectric_f(eta, mf, wo, wi, radiance) : (cond ? conductor_f(mfb, ce, ck, wo, wi) : diffuse_f(r, wo, wi));
+    }
+    Float i_pdf(bool top, V3 wo, V3 wi, int sf) const { return top ? dielectric_pdf(eta, mf, wo, wi, sf) : (cond ? conductor_pdf(mfb, wo, wi, sf) : diffuse_pdf(wo, wi, sf)); }
     bool i_sample(bool top, V3 wo, Float uc, V2 u, bool radiance, int sf, BSDFSample* bs) const {
-        return top ? dielectric_sample(eta, mf, wo, uc, u, radiance, sf, bs) : diffuse_sample(r, wo, u, sf, bs);
+        return top ? dielectric_sample(eta, mf, wo, uc, u, radiance, sf, bs) : (cond ? conductor_sample(mfb, ce, ck, wo, u, sf, bs) : diffuse_sample(r, wo, u, sf, bs));
     }
     static Float tr(Float dz, V3 w) {          // bxdf.rs:923-931: `abs(dz) <= Float::MIN` can never hold
         if (std::fabs(dz) <= -3.40282347e+38f) return 1.0f;

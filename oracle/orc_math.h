@@ -25,6 +25,7 @@ typedef float Float;                                   // float.rs:1-4 (use_f64 
 static const Float PI_F = 3.14159265358979323846f;     // float.rs:14
 static const Float INV_PI = 0.31830988618379067154f;   // math.rs consts
 static const Float INV_4PI = 0.07957747154594766788f;
+static const Float INV_2PI = 0.15915494309189533577f;
 static const Float PI_OVER_2 = 1.57079632679489661923f;
 static const Float PI_OVER_4 = 0.78539816339744830961f;
 static const Float F_INF = std::numeric_limits<Float>::infinity();

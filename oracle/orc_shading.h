@@ -341,7 +341,7 @@ struct BSDF {
         switch (kind) {
         case SG_MATERIAL_DIFFUSE: return spec_is_zero(r) ? BX_UNSET : (BX_DIFFUSE | BX_REFLECTION);                 // bxdf.rs:256-262
         case SG_MATERIAL_CONDUCTOR: return mf.effectively_smooth() ? (BX_SPECULAR | BX_REFLECTION) : (BX_GLOSSY | BX_REFLECTION);   // :447-453
-        case SG_MATERIAL_COATED_DIFFUSE: return lay.flags();
+        case SG_MATERIAL_COATED_DIFFUSE: case SG_MATERIAL_COATED_CONDUCTOR: return lay.flags();
         case SG_MATERIAL_THIN_DIELECTRIC: return BX_REFLECTION | BX_TRANSMISSION | BX_SPECULAR;                    // bxdf.rs:873-875
         default: {                                                                                                 // :778-790
             int f = (eta == 1.0f) ? BX_TRANSMISSION : (BX_REFLECTION | BX_TRANSMISSION);
@@ -351,7 +351,7 @@ struct BSDF {
     }
     // local-space f
     Spec f_local(V3 wo, V3 wi) const {
-        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.f(wo, wi, r); }
+        if (kind == SG_MATERIAL_COATED_DIFFUSE || kind == SG_MATERIAL_COATED_CONDUCTOR) { Rng r = layer_rng(); return lay.f(wo, wi, r); }
         if (kind == SG_MATERIAL_THIN_DIELECTRIC) return spec_const(0.0f);       // bxdf.rs:808-810
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // bxdf.rs:196-202
@@ -389,7 +389,7 @@ struct BSDF {
         }
     }
     Float pdf_local(V3 wo, V3 wi) const {
-        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.pdf(wo, wi, r); }
+        if (kind == SG_MATERIAL_COATED_DIFFUSE || kind == SG_MATERIAL_COATED_CONDUCTOR) { Rng r = layer_rng(); return lay.pdf(wo, wi, r); }
         if (kind == SG_MATERIAL_THIN_DIELECTRIC) return 0.0f;                   // bxdf.rs:863-871
         switch (kind) {
         case SG_MATERIAL_DIFFUSE:                                               // :240-254
@@ -424,7 +424,7 @@ struct BSDF {
     }
     bool sample_local(V3 wo, Float uc, V2 u, BSDFSample* bs) const {
         bs->eta = 1.0f; bs->proportional = false;
-        if (kind == SG_MATERIAL_COATED_DIFFUSE) { Rng r = layer_rng(); return lay.sample_f(wo, uc, u, r, bs, &bs->proportional); }
+        if (kind == SG_MATERIAL_COATED_DIFFUSE || kind == SG_MATERIAL_COATED_CONDUCTOR) { Rng r = layer_rng(); return lay.sample_f(wo, uc, u, r, bs, &bs->proportional); }
         if (kind == SG_MATERIAL_THIN_DIELECTRIC) {                              // ThinDielectricBxDF::sample_f bxdf.rs:812-861
             Float R = fresnel_dielectric(abs_cos_theta(wo), eta), T = 1.0f - R;
             if (R < 1.0f) { R += sqr(T) * R / (1.0f - sqr(R)); T = 1.0f - R; }
@@ -536,24 +536,41 @@ namespace orc {
 
 // SurfaceInteraction::get_bsdf (interaction.rs:187-278) + Material::get_bsdf
 // (material.rs:301-322, 456-511, 603-648, 917-963).
-inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& lambda, const AuxRays& aux, const SgRenderParams* rp) {
-    const SgMaterial& m = D->materials[si.material];
+// `mix_seed` seeds the generator MixMaterial::choose_material draws from (material.rs:1309-1330); the reference uses a
+// per-thread SmallRng::from_entropy() (integrator.rs:255) -- here: layer_seed(path stream, site 5), see SG_MATERIAL_MIX.
+inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& lambda, const AuxRays& aux, const SgRenderParams* rp, uint64_t mix_seed = 0) {
     // compute_differentials feeds image-texture filtering, the bump-map step and specular ray differentials; scenes
     // without image textures never read its results (constant textures ignore the footprint)
     if (D->n_textures > 0) compute_differentials(D, si, aux, rp->samples_per_pixel, rp->option_flags);
-    if (m.flags & SG_MAT_HAS_DISPLACEMENT) {
-        // bump_map (material.rs:1477-1509) then set_shading_geometry(ns, dpdu, dpdv, dndu, dndv, false) interaction.rs:229-250
+    if (D->materials[si.material].kind == SG_MATERIAL_MIX) {                     // interaction.rs:206-221
+        Rng mr; mr.seed_from_u64(mix_seed);
+        const TexCoordCtx mc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
+        for (int guard = 0; guard < 64 && D->materials[si.material].kind == SG_MATERIAL_MIX; ++guard) {
+            const SgMaterial& mm = D->materials[si.material];
+            const Float amt = mm.tex_mix_amount >= 0 ? eval_float_texture(D, mm.tex_mix_amount, mc) : mm.mix_amount;
+            if (amt <= 0.0f) si.material = mm.mix_materials[0];
+            else if (amt >= 1.0f) si.material = mm.mix_materials[1];
+            else { const Float u = mr.get_1d(); si.material = amt < u ? mm.mix_materials[0] : mm.mix_materials[1]; }
+        }
+    }
+    const SgMaterial& m = D->materials[si.material];
+    if ((m.flags & SG_MAT_HAS_DISPLACEMENT) || m.normal_map >= 0) {              // interaction.rs:225-250
+        // bump_map (material.rs:1477-1509) or, only without a displacement, normal_map (:1453-1474); then
+        // set_shading_geometry(ns, dpdu, dpdv, dndu, dndv, false)
         V3 dpdu, dpdv;
-        if (m.tex_displacement >= 0 || m.displacement != 0.0f) bump_map(D, m.tex_displacement, m.displacement, si, &dpdu, &dpdv);
-        else { dpdu = si.sdpdu; dpdv = si.sdpdv; }    // constant 0: dpdu + 0/du*n + 0*dndu
+        if (m.flags & SG_MAT_HAS_DISPLACEMENT) {
+            if (m.tex_displacement >= 0 || m.displacement != 0.0f) bump_map(D, m.tex_displacement, m.displacement, si, &dpdu, &dpdv);
+            else { dpdu = si.sdpdu; dpdv = si.sdpdv; }    // constant 0: dpdu + 0/du*n + 0*dndu
+        } else normal_map(D, m.normal_map, si, &dpdu, &dpdv);
         V3 ns = normalize(cross(dpdu, dpdv));                                   // interaction.rs:246
         si.sn = face_forward(ns, si.n);                                          // :379-405
         si.sdpdu = dpdu; si.sdpdv = dpdv;
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
-    TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy};
+    TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
     BSDF b;
     b.kind = m.kind; b.r = spec_const(0.0f); b.k = spec_const(0.0f); b.eta = 1.0f; b.mf = TR::make(0.0f, 0.0f);
+    b.lay.mf = TR::make(0.0f, 0.0f); b.lay.mfb = TR::make(0.0f, 0.0f);
     if (m.kind == SG_MATERIAL_DIFFUSE) {
         b.r = spec_clamp(m.tex_reflectance >= 0 ? eval_spectrum_texture(D, m.tex_reflectance, tc, lambda) : spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
     } else if (m.kind == SG_MATERIAL_CONDUCTOR) {
@@ -576,6 +593,31 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         b.lay.g = clampf(m.g, -1.0f, 1.0f);
         b.lay.max_depth = m.max_depth; b.lay.n_samples = m.n_samples;
         b.mf = b.lay.mf;
+    } else if (m.kind == SG_MATERIAL_COATED_CONDUCTOR) {                     // material.rs:1188-1260
+        Float iur = m.u_roughness, ivr = m.v_roughness;
+        if (m.flags & SG_MAT_REMAP_ROUGHNESS) { iur = std::sqrt(iur); ivr = std::sqrt(ivr); }
+        b.lay.mf = TR::make(iur, ivr);
+        b.lay.thickness = m.thickness;
+        Float ieta = spectrum_get(D, m.spec_c, lambda.lambda[0]);
+        if (D->spectra[m.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lambda);
+        if (ieta == 0.0f) ieta = 1.0f;
+        b.lay.eta = ieta;
+        Spec ce, ck;
+        if (!(m.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = spectrum_sample(D, m.spec_a, lambda); ck = spectrum_sample(D, m.spec_d, lambda); }
+        else {                                                               // :1225-1233
+            Spec r = spec_clamp(spectrum_sample(D, m.spec_a, lambda), 0.0f, 0.9999f);
+            ce = spec_const(1.0f);
+            for (int i = 0; i < 4; ++i) ck.v[i] = 2.0f * std::sqrt(r.v[i]) / std::sqrt(fmax_(0.0f, 1.0f - r.v[i]));
+        }
+        ce = ce / ieta; ck = ck / ieta;
+        Float cur = m.u_roughness2, cvr = m.v_roughness2;
+        if (m.flags & SG_MAT_REMAP_ROUGHNESS) { cur = std::sqrt(iur); cvr = std::sqrt(ivr); }   // sic: roughness_to_alpha(iurough), material.rs:1237-1241
+        b.lay.cond = true; b.lay.ce = ce; b.lay.ck = ck; b.lay.mfb = TR::make(cur, cvr);
+        b.lay.r = spec_const(0.0f);
+        b.lay.albedo = spec_clamp(spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
+        b.lay.g = clampf(m.g, -1.0f, 1.0f);
+        b.lay.max_depth = m.max_depth; b.lay.n_samples = m.n_samples;
+        b.mf = b.lay.mf;
     } else {
         Float sampled_eta = spectrum_get(D, m.spec_a, lambda.lambda[0]);
         if (D->spectra[m.spec_a].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lambda);
@@ -587,6 +629,10 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
     b.fx = normalize(si.sdpdu); b.fz = si.sn; b.fy = cross(b.fz, b.fx);
     return b;
 }
+
+}  // namespace orc
+#include "orc_envmap.h"
+namespace orc {
 
 // ---- lights ----------------------------------------------------------------------
 struct LightSampleContext { P3fi pi; V3 n, ns; V3 p() const { return p3fi_mid(pi); } };
@@ -762,8 +808,15 @@ inline Float sphere_pdf_with_context(const SgSceneDesc* D, const SgSphere& S, co
     return 1.0f / (2.90f * PI_F * one_minus_cos_theta_max);                                              // sic: 2.90, :455
 }
 
-// Light::sample_li with allow_incomplete_pdf = true (integrator.rs:933): light.rs:632-661, :461-484, :742-768
-inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V2 u, const Wavelengths& lambda, LightLiSample* ls) {
+// sample_uniform_sphere sampling.rs:280-289
+inline V3 sample_uniform_sphere(V2 u) {
+    const Float z = 1.0f - 2.0f * u.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * PI_F * u.y;
+    return v3(r * std::cos(phi), r * std::sin(phi), z);
+}
+// Light::sample_li: light.rs:632-661 (area), :461-484 (point), :740-766 (uniform infinite), :847-880 (image infinite).
+// `allow_incomplete` is true from PathIntegrator::sample_ld (integrator.rs:933) and false from SimplePathIntegrator (:652-656).
+inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V2 u, const Wavelengths& lambda, LightLiSample* ls,
+                            bool allow_incomplete = true) {
     const SgSceneDesc* D = sc.d;
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {
         ShapeSample ss;
@@ -782,13 +835,35 @@ inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampl
         ls->l = lt.scale * spectrum_sample(D, lt.spectrum, lambda) / distance_squared(p, ctx.p());
         ls->wi = wi; ls->pdf = 1.0f; ls->p_light = p3fi_exact(p); ls->n_light = v3(0, 0, 0);
         return true;
+    } else if (lt.kind == SG_LIGHT_IMAGE_INFINITE) {                                                  // light.rs:847-880
+        const SgEnvMap& E = D->env_maps[lt.tri];
+        Float map_pdf;
+        const V2 uv = pc2d_sample(D, allow_incomplete ? E.compensated : E.distribution, u, &map_pdf);
+        if (map_pdf == 0.0f) return false;
+        const V3 wi = xform_vector3(E.render_from_light, equal_area_square_to_sphere(uv));
+        ls->l = env_image_le(D, lt, uv, lambda); ls->wi = wi; ls->pdf = map_pdf / (4.0f * PI_F);
+        ls->p_light = p3fi_exact(ctx.p() + wi * (2.0f * lt.scene_radius)); ls->n_light = v3(0, 0, 0);
+        return true;
+    } else if (lt.kind == SG_LIGHT_UNIFORM_INFINITE && !allow_incomplete) {                            // light.rs:750-765
+        const V3 wi = sample_uniform_sphere(u);
+        ls->l = lt.scale * spectrum_sample(D, lt.spectrum, lambda); ls->wi = wi; ls->pdf = INV_4PI;   // uniform_hemisphere_pdf() == 1/(4 pi), sampling.rs:306-308
+        ls->p_light = p3fi_exact(ctx.p() + wi * (2.0f * lt.scene_radius)); ls->n_light = v3(0, 0, 0);
+        return true;
     }
     return false;   // UniformInfiniteLight::sample_li returns None when allow_incomplete_pdf (light.rs:748-750)
 }
-inline Float light_pdf_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V3 wi) {   // allow_incomplete_pdf = true
+inline Float light_pdf_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V3 wi, bool allow_incomplete = true) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, lt.mesh, lt.tri, ctx, wi);     // light.rs:663-666
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc.d, sc.d->spheres[lt.tri], ctx, wi);
+    if (lt.kind == SG_LIGHT_IMAGE_INFINITE) return env_pdf_li(sc.d, lt, wi, allow_incomplete);           // :882-892
+    if (lt.kind == SG_LIGHT_UNIFORM_INFINITE && !allow_incomplete) return INV_4PI;                       // :768-780
     return 0.0f;                                                                                       // :486-494, :770-781
+}
+// Light::le for the infinite lights: light.rs:792-794, :907-911
+inline bool light_is_infinite(const SgLight& lt) { return lt.kind == SG_LIGHT_UNIFORM_INFINITE || lt.kind == SG_LIGHT_IMAGE_INFINITE; }
+inline Spec light_le(const SgSceneDesc* D, const SgLight& lt, V3 ray_d, const Wavelengths& lambda) {
+    if (lt.kind == SG_LIGHT_IMAGE_INFINITE) return env_le(D, lt, ray_d, lambda);
+    return lt.scale * spectrum_sample(D, lt.spectrum, lambda);
 }
 
 // ---- camera ------------------------------------------------------------------------

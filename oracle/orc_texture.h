@@ -167,7 +167,22 @@ inline Float sigmoid_poly_get(const Float c[3], Float lambda) {
     return 0.5f + x / (2.0f * std::sqrt(1.0f + x * x));
 }
 
-struct TexCoordCtx { V2 uv; Float dudx, dudy, dvdx, dvdy; };
+inline V3 xform_vector3(const float m[16], V3 v) {
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+inline V3 xform_normal_t(const float m[16], V3 n) {              // apply_normal_helper transform.rs:779-786 (transposed 3x3)
+    return v3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
+}
+inline V3 xform_point3(const float m[16], V3 p) {                // apply_point_helper transform.rs:753-767
+    Float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    Float yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    Float zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    Float wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (wp == 1.0f) return v3(xp, yp, zp);
+    return v3(xp, yp, zp) / wp;
+}
+// TextureEvalContext (texture.rs): uv + screen-space derivatives; p / dpdx / dpdy feed the non-UV mappings only
+struct TexCoordCtx { V2 uv; Float dudx, dudy, dvdx, dvdy; V3 p = {0, 0, 0}, dpdx = {0, 0, 0}, dpdy = {0, 0, 0}; };
 
 inline void uv_map(const SgTexture& t, const TexCoordCtx& c, V2* st, V2* dst0, V2* dst1) {            // texture.rs:918-936
     Float dsdx = t.su * c.dudx, dsdy = t.su * c.dudy, dtdx = t.sv * c.dvdx, dtdy = t.sv * c.dvdy;
@@ -175,17 +190,44 @@ inline void uv_map(const SgTexture& t, const TexCoordCtx& c, V2* st, V2* dst0, V
     st->y = 1.0f - st->y;                                                                           // :396-399, :780-781
     dst0->x = dsdx; dst0->y = dtdx; dst1->x = dsdy; dst1->y = dtdy;
 }
+// SphericalMapping / CylindricalMapping / PlanarMapping ::map texture.rs:943-1035, then the t flip of the image textures
+inline void tex_map(const SgSceneDesc* D, const SgTexture& t, const TexCoordCtx& c, V2* st, V2* dst0, V2* dst1) {
+    if (t.mapping < 0) { uv_map(t, c, st, dst0, dst1); return; }
+    const SgTextureMapping& M = D->texture_mappings[t.mapping];
+    const V3 pt = xform_point3(M.texture_from_render, c.p);
+    const V3 dpdx = xform_vector3(M.texture_from_render, c.dpdx), dpdy = xform_vector3(M.texture_from_render, c.dpdy);
+    V3 dsdp, dtdp;
+    if (M.kind == SG_MAPPING_SPHERICAL) {
+        const Float x2y2 = sqr(pt.x) + sqr(pt.y), sqrtx2y2 = std::sqrt(x2y2);
+        dsdp = v3(-pt.y, pt.x, 0.0f) / (2.0f * PI_F * x2y2);
+        dtdp = 1.0f / (PI_F * (x2y2 + sqr(pt.z))) * v3(pt.x * pt.z / sqrtx2y2, pt.y * pt.z / sqrtx2y2, -sqrtx2y2);
+        const V3 vec = normalize(pt - v3(0, 0, 0));
+        const Float theta = safe_asin(vec.z);                                   // spherical_theta = safe_acos, which calls asin (math.rs:272-274)
+        st->x = theta * INV_PI; st->y = theta * INV_2PI;                         // sic: both from theta (texture.rs:960-963)
+    } else if (M.kind == SG_MAPPING_CYLINDRICAL) {
+        const Float x2y2 = sqr(pt.x) + sqr(pt.y);
+        dsdp = v3(-pt.y, pt.x, 0.0f) / (2.0f * PI_F * x2y2);
+        dtdp = v3(0, 0, 1);
+        st->x = PI_F + std::atan2(pt.y, pt.x) * INV_2PI; st->y = pt.z;          // sic: texture.rs:990-993
+    } else {
+        dsdp = v3(M.vs[0], M.vs[1], M.vs[2]); dtdp = v3(M.vt[0], M.vt[1], M.vt[2]);
+        st->x = M.ds + dot(pt, dsdp); st->y = M.dt + dot(pt, dtdp);
+    }
+    dst0->x = dot(dsdp, dpdx); dst1->x = dot(dsdp, dpdy);                       // dsdx, dsdy
+    dst0->y = dot(dtdp, dpdx); dst1->y = dot(dtdp, dpdy);                       // dtdx, dtdy
+    st->y = 1.0f - st->y;                                                        // :396-399, :780-781
+}
 // FloatImageTexture::evaluate texture.rs:393-404
 inline Float eval_float_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c) {
     TexView tv = {D, &D->textures[tex]};
-    V2 st, d0, d1; uv_map(*tv.t, c, &st, &d0, &d1);
+    V2 st, d0, d1; tex_map(D, *tv.t, c, &st, &d0, &d1);
     Float v = tex_filter<false>(tv, st, d0, d1).r * tv.t->scale;
     return tv.t->invert ? fmax_(0.0f, 1.0f - v) : v;
 }
 // SpectrumImageTexture::evaluate texture.rs:777-808
 inline Spec eval_spectrum_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c, const Wavelengths& lambda) {
     TexView tv = {D, &D->textures[tex]};
-    V2 st, d0, d1; uv_map(*tv.t, c, &st, &d0, &d1);
+    V2 st, d0, d1; tex_map(D, *tv.t, c, &st, &d0, &d1);
     Texel rgb = tex_filter<true>(tv, st, d0, d1) * tv.t->scale;
     if (tv.t->invert) { rgb.r = 1.0f - rgb.r; rgb.g = 1.0f - rgb.g; rgb.b = 1.0f - rgb.b; }
     rgb.r = fmax_(0.0f, rgb.r); rgb.g = fmax_(0.0f, rgb.g); rgb.b = fmax_(0.0f, rgb.b);                 // clamp_zero
@@ -204,20 +246,6 @@ inline Spec eval_spectrum_texture(const SgSceneDesc* D, int tex, const TexCoordC
 }
 
 // ---- screen-space differentials -------------------------------------------------------------------
-inline V3 xform_vector3(const float m[16], V3 v) {
-    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
-}
-inline V3 xform_normal_t(const float m[16], V3 n) {              // apply_normal_helper transform.rs:779-786 (transposed 3x3)
-    return v3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
-}
-inline V3 xform_point3(const float m[16], V3 p) {                // apply_point_helper transform.rs:753-767
-    Float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
-    Float yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
-    Float zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
-    Float wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
-    if (wp == 1.0f) return v3(xp, yp, zp);
-    return v3(xp, yp, zp) / wp;
-}
 // Transform::rotate_from_to transform.rs:227-253 (3x3 part, row-major)
 inline void rotate_from_to(V3 from, V3 to, Float r[9]) {
     V3 ref1;
@@ -356,19 +384,33 @@ inline void compute_differentials(const SgSceneDesc* D, SurfaceInteraction& si, 
 
 // bump_map material.rs:1477-1509 for a FloatImageTexture (tex >= 0) or the constant displacement `cdisp`
 inline void bump_map(const SgSceneDesc* D, int tex, Float cdisp, const SurfaceInteraction& si, V3* dpdu_out, V3* dpdv_out) {
-    TexCoordCtx c = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy};
+    TexCoordCtx c = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
     Float du = 0.5f * (std::fabs(si.dudx) + std::fabs(si.dudy));
     if (du == 0.0f) du = 0.0005f;
     Float dv = 0.5f * (std::fabs(si.dvdx) + std::fabs(si.dvdy));
     if (dv == 0.0f) dv = 0.0005f;
     Float u_displace, v_displace, displace;
     if (tex >= 0) {
-        TexCoordCtx cu = c; cu.uv.x = si.uv.x + du; cu.uv.y = si.uv.y + 0.0f;
-        TexCoordCtx cv = c; cv.uv.x = si.uv.x + 0.0f; cv.uv.y = si.uv.y + dv;
+        TexCoordCtx cu = c; cu.uv.x = si.uv.x + du; cu.uv.y = si.uv.y + 0.0f; cu.p = si.p() + du * si.sdpdu;
+        TexCoordCtx cv = c; cv.uv.x = si.uv.x + 0.0f; cv.uv.y = si.uv.y + dv; cv.p = si.p() + dv * si.sdpdv;
         u_displace = eval_float_texture(D, tex, cu); v_displace = eval_float_texture(D, tex, cv); displace = eval_float_texture(D, tex, c);
     } else u_displace = v_displace = displace = cdisp;
     *dpdu_out = si.sdpdu + (u_displace - displace) / du * si.sn + displace * si.sdndu;
     *dpdv_out = si.sdpdv + (v_displace - displace) / dv * si.sn + displace * si.sdndv;
+}
+
+// normal_map material.rs:1453-1474: level 0 of a three-channel image, Image::bilerp_channel_wrapped with WrapMode::Repeat
+inline void normal_map(const SgSceneDesc* D, int tex, const SurfaceInteraction& si, V3* dpdu_out, V3* dpdv_out) {
+    SgTexture t = D->textures[tex]; t.wrap = SG_WRAP_REPEAT;
+    TexView tv = {D, &t};
+    V2 uv; uv.x = si.uv.x; uv.y = 1.0f - si.uv.y;
+    const Texel px = tex_bilerp<true>(tv, 0, uv);
+    V3 ns = normalize(v3(2.0f * px.r - 1.0f, 2.0f * px.g - 1.0f, 2.0f * px.b - 1.0f));
+    const V3 fx = normalize(si.sdpdu), fz = si.sn, fy = cross(fz, fx);            // Frame::from_xz frame.rs:14-17
+    ns = ns.x * fx + ns.y * fy + ns.z * fz;
+    const Float ulen = length(si.sdpdu), vlen = length(si.sdpdv);
+    const V3 dpdu = normalize(gram_schmidt(si.sdpdu, ns)) * ulen;
+    *dpdu_out = dpdu; *dpdv_out = normalize(cross(ns, dpdu)) * vlen;
 }
 
 // SurfaceInteraction::spawn_ray_with_differentials interaction.rs:434-502 (auxiliary part)

@@ -42,6 +42,8 @@ struct PathCtx {
 // sample_f) WITHOUT advancing the path stream.  Same definition in sg_wavefront.cuh.
 static inline uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s[0] ^ (site * 0x9e3779b97f4a7c15ULL)); }
 
+static SurfaceInteraction hit_interaction(const Scene& sc, const Hit& hit, const Ray& ray);
+
 static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, BSDF& bsdf, const Wavelengths& lambda, Rng& rng) {
     const SgSceneDesc* D = pc.sc->d;
     LightSampleContext ctx; ctx.pi = intr.pi; ctx.n = intr.n; ctx.ns = intr.sn;
@@ -92,8 +94,8 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
         if (!found) {
             for (uint32_t i = 0; i < D->n_lights; ++i) {                          // :779-792
                 const SgLight& lt = D->lights[i];
-                if (lt.kind != SG_LIGHT_UNIFORM_INFINITE) continue;
-                Spec le = lt.scale * spectrum_sample(D, lt.spectrum, lambda);     // light.rs:792-794
+                if (!light_is_infinite(lt)) continue;
+                Spec le = light_le(D, lt, ray.d, lambda);                         // light.rs:792-794, :907-911
                 if (depth == 0 || specular_bounce) L = L + beta * le;
                 else {
                     Float p_l = (1.0f / (Float)D->n_lights) * light_pdf_li(*pc.sc, lt, prev_ctx, ray.d);
@@ -103,23 +105,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
             }
             break;
         }
-        const SgPrimitive& prim = D->primitives[hit.prim];
-        SurfaceInteraction si;
-        if (prim.mesh == SG_PRIM_SPHERE) {                                         // Sphere::intersect sphere.rs:286-293
-            V3 p_obj = v3(hit.th.b0, hit.th.b1, hit.th.b2);
-            Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
-            si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -ray.d);
-        } else if (D->meshes[prim.mesh].flags & SG_MESH_BILINEAR) {                 // BilinearPatch::intersect bilinear_patch.rs:496-509
-            si = patch_interaction(*pc.sc, prim.mesh, prim.tri, hit.th.b0, hit.th.b1, -ray.d);
-        } else if (hit.inst >= 0) {                                                       // TransformedPrimitive::intersect primitive.rs:155-169
-            const SgInstance& I = D->instances[hit.inst];
-            const float* mi = I.primitive_from_render;
-            V3 d2 = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
-                       mi[8] * ray.d.x + mi[9] * ray.d.y + mi[10] * ray.d.z);
-            si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -d2);
-            transform_interaction(D, I, si);
-        } else si = interaction_from_intersection(*pc.sc, prim.mesh, prim.tri, hit.th, -ray.d);
-        si.material = (int32_t)prim.material; si.light = prim.light;
+        SurfaceInteraction si = hit_interaction(*pc.sc, hit, ray);                 // sphere.rs:286-293, bilinear_patch.rs:496-509, primitive.rs:155-169, triangle.rs:529-535
         if (si.light >= 0) {                                                       // :798-813
             const SgLight& lt = D->lights[si.light];
             Spec le = light_l(D, lt, si.n, -ray.d, lambda);
@@ -132,8 +118,8 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
                 }
             }
         }
-        BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp);                          // :816
-        if (pc.rp->regularize && any_non_specular_bounces) { bsdf.mf.regularize(); bsdf.lay.mf.regularize(); }  // :825-828
+        BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp, layer_seed(rng, 5));      // :816
+        if (pc.rp->regularize && any_non_specular_bounces) { bsdf.mf.regularize(); bsdf.lay.mf.regularize(); bsdf.lay.mfb.regularize(); }  // :825-828 (LayeredBxDF::regularize: top + bottom, bxdf.rs:1616-1619)
         if (depth == pc.rp->max_depth) break;
         depth += 1;
         if (bsdf.flags() & (BX_DIFFUSE | BX_GLOSSY)) {                            // :837-841
@@ -167,6 +153,131 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
     return L;
 }
 
+// Hit -> SurfaceInteraction (shared by the three integrators): Primitive::intersect results of the shapes on this path
+static SurfaceInteraction hit_interaction(const Scene& sc, const Hit& hit, const Ray& ray) {
+    const SgSceneDesc* D = sc.d;
+    const SgPrimitive& prim = D->primitives[hit.prim];
+    SurfaceInteraction si;
+    if (prim.mesh == SG_PRIM_SPHERE) {
+        V3 p_obj = v3(hit.th.b0, hit.th.b1, hit.th.b2);
+        Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
+        si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -ray.d);
+    } else if (D->meshes[prim.mesh].flags & SG_MESH_BILINEAR) {
+        si = patch_interaction(sc, prim.mesh, prim.tri, hit.th.b0, hit.th.b1, -ray.d);
+    } else if (hit.inst >= 0) {
+        const SgInstance& I = D->instances[hit.inst];
+        const float* mi = I.primitive_from_render;
+        V3 d2 = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
+                   mi[8] * ray.d.x + mi[9] * ray.d.y + mi[10] * ray.d.z);
+        si = interaction_from_intersection(sc, prim.mesh, prim.tri, hit.th, -d2);
+        transform_interaction(D, I, si);
+    } else si = interaction_from_intersection(sc, prim.mesh, prim.tri, hit.th, -ray.d);
+    si.material = (int32_t)prim.material; si.light = prim.light;
+    return si;
+}
+// sample_uniform_hemisphere sampling.rs:295-304 (around +z of the space it is used in)
+static V3 sample_uniform_hemisphere(V2 u) {
+    const Float z = u.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * PI_F * u.y;
+    return v3(r * std::cos(phi), r * std::sin(phi), z);
+}
+
+// SimplePathIntegrator::li integrator.rs:585-727: no MIS, no Russian roulette; lights sampled with COMPLETE pdfs
+// (allow_incomplete_pdf = false, :652-656) from the un-nudged LightSampleContext::from(&isect).
+static Spec simple_path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda, Rng& rng) {
+    const SgSceneDesc* D = pc.sc->d;
+    const bool sample_lights = (pc.rp->integrator_flags & SG_SIMPLEPATH_SAMPLE_LIGHTS) != 0, sample_bsdf = (pc.rp->integrator_flags & SG_SIMPLEPATH_SAMPLE_BSDF) != 0;
+    Spec L = spec_const(0.0f), beta = spec_const(1.0f);
+    bool specular_bounce = true;
+    int depth = 0;
+    while (!spec_is_zero(beta)) {
+        Hit hit;
+        if (pc.ctr) pc.ctr->closest++;
+        if (!bvh_intersect(*pc.sc, ray, F_INF, false, &hit, pc.ctr)) {
+            if (!sample_lights || specular_bounce)
+                for (uint32_t i = 0; i < D->n_lights; ++i) if (light_is_infinite(D->lights[i])) L = L + beta * light_le(D, D->lights[i], ray.d, lambda);
+            break;
+        }
+        SurfaceInteraction si = hit_interaction(*pc.sc, hit, ray);
+        if ((!sample_lights || specular_bounce) && si.light >= 0) L = L + beta * light_l(D, D->lights[si.light], si.n, -ray.d, lambda);
+        if (depth == pc.rp->max_depth) break;
+        depth += 1;
+        BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp, layer_seed(rng, 5));
+        const V3 wo = -ray.d;
+        if (sample_lights && D->n_lights > 0) {                                      // UniformLightSampler::sample_light light_sampler.rs:91-103
+            const Float ul = rng.get_1d();
+            Float fl = ul * (Float)D->n_lights;
+            uint32_t li = fl != fl ? 0u : (fl <= 0.0f ? 0u : (fl >= 4294967296.0f ? 0xffffffffu : (uint32_t)fl));
+            if (li > D->n_lights - 1) li = D->n_lights - 1;
+            const Float p_choose = 1.0f / (Float)D->n_lights;
+            V2 u_light; u_light.x = rng.get_1d(); u_light.y = rng.get_1d();
+            LightSampleContext ctx; ctx.pi = si.pi; ctx.n = si.n; ctx.ns = si.sn;
+            LightLiSample ls;
+            if (light_sample_li(*pc.sc, D->lights[li], ctx, u_light, lambda, &ls, false) && !spec_is_zero(ls.l) && ls.pdf > 0.0f) {
+                bsdf.layer_seed = layer_seed(rng, 1);
+                const Spec f = bsdf.f(wo, ls.wi) * abs_dot(ls.wi, si.sn);
+                if (!spec_is_zero(f)) {
+                    Ray sray = spawn_ray_to_both_offset(si.pi, si.n, ls.p_light, ls.n_light);
+                    Hit h;
+                    if (pc.ctr) pc.ctr->shadow++;
+                    if (!bvh_intersect(*pc.sc, sray, 1.0f - 0.0001f, true, &h, pc.ctr)) L = L + beta * f * ls.l / (p_choose * ls.pdf);
+                }
+            }
+        } else if (sample_lights) (void)rng.get_1d();                                // sample_light(u) still draws u; no light -> None before get_2d
+        if (sample_bsdf) {
+            const Float u = rng.get_1d();
+            V2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+            BSDFSample bs;
+            bsdf.layer_seed = layer_seed(rng, 3);
+            if (!bsdf.sample_f(wo, u, u2, &bs)) break;
+            beta = beta * (bs.f * abs_dot(bs.wi, si.sn) / bs.pdf);
+            specular_bounce = (bs.flags & BX_SPECULAR) != 0;
+            ray.o = offset_ray_origin(si.pi, si.n, bs.wi); ray.d = bs.wi;
+        } else {
+            const int flags = bsdf.flags();
+            const bool refl = flags & BX_REFLECTION, trans = flags & BX_TRANSMISSION;
+            V2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+            V3 wi; const Float pdf = INV_4PI;                                        // uniform_sphere_pdf and (sic) uniform_hemisphere_pdf, sampling.rs:291-293,306-308
+            if (refl && trans) wi = sample_uniform_sphere(u2);
+            else {
+                wi = sample_uniform_hemisphere(u2);
+                if ((refl && dot(wo, si.n) * dot(wi, si.n) < 0.0f) || (trans && dot(wo, si.n) * dot(wi, si.n) > 0.0f)) wi = -wi;
+            }
+            bsdf.layer_seed = layer_seed(rng, 3);
+            beta = beta * (bsdf.f(wo, wi) * abs_dot(wi, si.sn) / pdf);
+            specular_bounce = false;
+            ray.o = offset_ray_origin(si.pi, si.n, wi); ray.d = wi;
+        }
+        aux.has = false;                                                             // Interaction::spawn_ray: a plain Ray, no differentials
+    }
+    return L;
+}
+
+// RandomWalkIntegrator::li_random_walk integrator.rs:493-567, recursion as written
+static Spec random_walk_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda, Rng& rng, int depth) {
+    const SgSceneDesc* D = pc.sc->d;
+    Hit hit;
+    if (pc.ctr) pc.ctr->closest++;
+    if (!bvh_intersect(*pc.sc, ray, F_INF, false, &hit, pc.ctr)) {
+        Spec le = spec_const(0.0f);
+        for (uint32_t i = 0; i < D->n_lights; ++i) if (light_is_infinite(D->lights[i])) le = le + light_le(D, D->lights[i], ray.d, lambda);
+        return le;
+    }
+    SurfaceInteraction si = hit_interaction(*pc.sc, hit, ray);
+    const V3 wo = -ray.d;
+    const Spec le = si.light >= 0 ? light_l(D, D->lights[si.light], si.n, wo, lambda) : spec_const(0.0f);
+    if (depth == pc.rp->max_depth) return le;
+    BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp, layer_seed(rng, 5));
+    V2 u; u.x = rng.get_1d(); u.y = rng.get_1d();
+    const V3 wp = sample_uniform_sphere(u);
+    bsdf.layer_seed = layer_seed(rng, 1);
+    const Spec f = bsdf.f(wo, wp);
+    if (spec_is_zero(f)) return le;
+    const Spec fcos = f * abs_dot(wp, si.sn);
+    Ray next; next.o = offset_ray_origin(si.pi, si.n, wp); next.d = wp;
+    AuxRays none;
+    return le + fcos * random_walk_li(pc, next, none, lambda, rng, depth + 1) / (1.0f / (4.0f * PI_F));
+}
+
 // evaluate_pixel_sample integrator.rs:326-396 + get_camera_sample sampling.rs:347-371 + BoxFilter::sample filter.rs:99-105
 static void camera_stage(const SgSceneDesc* D, const SgRenderParams* rp, int px, int py, Rng& rng, Wavelengths* lambda, Ray* ray, Float* weight, AuxRays* aux = nullptr) {
     Float lu = (rp->option_flags & SG_OPT_DISABLE_WAVELENGTH_JITTER) ? 0.5f : rng.get_1d();
@@ -197,7 +308,10 @@ static void eval_sample(const PathCtx& pc, int px, int py, Rng& rng, SgFilmPixel
     const SgSceneDesc* D = pc.sc->d;
     Wavelengths lambda; Ray ray; Float weight; AuxRays aux;
     camera_stage(D, pc.rp, px, py, rng, &lambda, &ray, &weight, D->n_textures > 0 ? &aux : nullptr);
-    Spec L = path_li(pc, ray, aux, lambda, rng);          // camera_ray.weight == 1 (camera.rs:997-1000)
+    Spec L;                                               // camera_ray.weight == 1 (camera.rs:997-1000)
+    if (pc.rp->integrator == SG_INTEGRATOR_SIMPLE_PATH) L = simple_path_li(pc, ray, aux, lambda, rng);
+    else if (pc.rp->integrator == SG_INTEGRATOR_RANDOM_WALK) L = random_walk_li(pc, ray, aux, lambda, rng, 0);
+    else L = path_li(pc, ray, aux, lambda, rng);
     int W = D->film.pixel_bounds[2] - D->film.pixel_bounds[0];
     SgFilmPixel* pxl = film + (size_t)(py - D->film.pixel_bounds[1]) * W + (px - D->film.pixel_bounds[0]);
     film_add_sample(D, pxl, L, lambda, weight);
@@ -473,6 +587,19 @@ void orc_texture_eval(const SgSceneDesc* d, int tex, int as_float, int64_t n, co
         }
     }
 }
+// same with a full TextureEvalContext: pdp = p, dpdx, dpdy (9 floats per lookup) for the non-UV mappings (texture.rs:938-1035)
+void orc_texture_eval_p(const SgSceneDesc* d, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda4, float* out4) {
+    for (int64_t i = 0; i < n; ++i) {
+        TexCoordCtx c; c.uv.x = q[6 * i]; c.uv.y = q[6 * i + 1]; c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
+        c.p = v3(pdp[9 * i], pdp[9 * i + 1], pdp[9 * i + 2]); c.dpdx = v3(pdp[9 * i + 3], pdp[9 * i + 4], pdp[9 * i + 5]); c.dpdy = v3(pdp[9 * i + 6], pdp[9 * i + 7], pdp[9 * i + 8]);
+        if (as_float) { Float v = eval_float_texture(d, tex, c); for (int k = 0; k < 4; ++k) out4[4 * i + k] = v; }
+        else {
+            Wavelengths w; for (int k = 0; k < 4; ++k) { w.lambda[k] = lambda4[4 * i + k]; w.pdf[k] = 1.0f; }
+            Spec s = eval_spectrum_texture(d, tex, c, w);
+            for (int k = 0; k < 4; ++k) out4[4 * i + k] = s.v[k];
+        }
+    }
+}
 void orc_approximate_dp_dxy(const SgSceneDesc* d, const float* p, const float* n, int spp, uint32_t option_flags, float* out6) {
     V3 dpdx, dpdy;
     approximate_dp_dxy(d->camera, v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2]), spp, option_flags, &dpdx, &dpdy);
@@ -543,6 +670,33 @@ float orc_light_pdf(const SgSceneDesc* desc, int light, const float* ctx_p, cons
     Scene sc(desc);
     LightSampleContext ctx; ctx.pi = p3fi_exact(v3(ctx_p[0], ctx_p[1], ctx_p[2])); ctx.n = v3(ctx_n[0], ctx_n[1], ctx_n[2]); ctx.ns = v3(ctx_ns[0], ctx_ns[1], ctx_ns[2]);
     return light_pdf_li(sc, desc->lights[light], ctx, v3(wi[0], wi[1], wi[2]));
+}
+// allow_incomplete_pdf = false variants (SimplePathIntegrator, integrator.rs:652-656) and Light::le of the infinite lights
+int orc_light_sample_complete(const SgSceneDesc* desc, int light, const float* ctx_p, const float* u2, const float* lambda4, float* out) {
+    Scene sc(desc);
+    LightSampleContext ctx; ctx.pi = p3fi_exact(v3(ctx_p[0], ctx_p[1], ctx_p[2])); ctx.n = v3(0, 0, 0); ctx.ns = v3(0, 0, 0);
+    Wavelengths w; for (int i = 0; i < 4; ++i) { w.lambda[i] = lambda4[i]; w.pdf[i] = 1.0f; }
+    LightLiSample ls; V2 u = {u2[0], u2[1]};
+    if (!light_sample_li(sc, desc->lights[light], ctx, u, w, &ls, false)) return 0;
+    for (int i = 0; i < 4; ++i) out[i] = ls.l.v[i];
+    out[4] = ls.wi.x; out[5] = ls.wi.y; out[6] = ls.wi.z; out[7] = ls.pdf;
+    return 1;
+}
+float orc_light_pdf_complete(const SgSceneDesc* desc, int light, const float* wi) {
+    Scene sc(desc);
+    LightSampleContext ctx; ctx.pi = p3fi_exact(v3(0, 0, 0)); ctx.n = v3(0, 0, 0); ctx.ns = v3(0, 0, 0);
+    return light_pdf_li(sc, desc->lights[light], ctx, v3(wi[0], wi[1], wi[2]), false);
+}
+void orc_light_le(const SgSceneDesc* desc, int light, const float* ray_d, const float* lambda4, float* out4) {
+    Wavelengths w; for (int i = 0; i < 4; ++i) { w.lambda[i] = lambda4[i]; w.pdf[i] = 1.0f; }
+    Spec s = light_le(desc, desc->lights[light], v3(ray_d[0], ray_d[1], ray_d[2]), w);
+    for (int i = 0; i < 4; ++i) out4[i] = s.v[i];
+}
+void orc_equal_area_square_to_sphere(const float* p2, float* out3) {
+    V2 p = {p2[0], p2[1]}; V3 w = equal_area_square_to_sphere(p); out3[0] = w.x; out3[1] = w.y; out3[2] = w.z;
+}
+void orc_equal_area_sphere_to_square(const float* d3, float* out2) {
+    V2 p = equal_area_sphere_to_square(v3(d3[0], d3[1], d3[2])); out2[0] = p.x; out2[1] = p.y;
 }
 
 }  // extern "C"

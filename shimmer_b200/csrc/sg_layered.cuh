@@ -116,6 +116,48 @@ SGD bool diffuse_sample(Spec r, float3 wo, float2 u, int sflags, BSDFSample& bs)
     return true;
 }
 
+// ---- ConductorBxDF with sample flags (bxdf.rs:328-458): the bottom interface of CoatedConductorBxDF ----
+SGD int conductor_flags(const TR& mf) { return (mf.smooth() ? BX_SPECULAR : BX_GLOSSY) | BX_REFLECTION; }
+SGD Spec conductor_f(const TR& mf, Spec eta, Spec k, float3 wo, float3 wi) {                    // :349-376
+    if (!same_hemisphere(wo, wi)) return spec1(0.0f);
+    if (mf.smooth()) return spec1(0.0f);
+    const float cto = fabsf(wo.z), cti = fabsf(wi.z);
+    if (cti == 0.0f || cto == 0.0f) return spec1(0.0f);
+    float3 wm = wi + wo;
+    if (len2(wm) == 0.0f) return spec1(0.0f);
+    wm = normalize3(wm);
+    const Spec F = fresnel_complex_spectral(absdot3(wo, wm), eta, k);
+    return mf.d(wm) * F * mf.g(wo, wi) / (4.0f * cto * cti);
+}
+SGD float conductor_pdf(const TR& mf, float3 wo, float3 wi, int sflags) {                       // :424-445
+    if (!(sflags & SF_REFLECTION) || !same_hemisphere(wo, wi) || mf.smooth()) return 0.0f;
+    float3 wm = wo + wi;
+    if (len2(wm) == 0.0f) return 0.0f;
+    wm = faceforward3(normalize3(wm), f3(0.0f, 0.0f, 1.0f));
+    return mf.pdf(wo, wm) / (4.0f * absdot3(wo, wm));
+}
+SGD bool conductor_sample(const TR& mf, Spec eta, Spec k, float3 wo, float2 u, int sflags, BSDFSample& bs) {   // :378-422
+    bs.eta = 1.0f;
+    if (!(sflags & SF_REFLECTION)) return false;
+    if (mf.smooth()) {
+        const float3 wi = f3(-wo.x, -wo.y, wo.z);
+        bs.f = fresnel_complex_spectral(fabsf(wi.z), eta, k) / fabsf(wi.z);
+        bs.wi = wi; bs.pdf = 1.0f; bs.flags = BX_SPECULAR | BX_REFLECTION;
+        return true;
+    }
+    if (wo.z == 0.0f) return false;
+    const float3 wm = mf.sample_wm(wo, u);
+    const float3 wi = reflect3(wo, wm);
+    if (!same_hemisphere(wo, wi)) return false;
+    const float pdf = mf.pdf(wo, wm) / (4.0f * absdot3(wo, wm));
+    const float cto = fabsf(wo.z), cti = fabsf(wi.z);
+    if (cti == 0.0f || cto == 0.0f) return false;
+    const Spec F = fresnel_complex_spectral(absdot3(wo, wm), eta, k);
+    bs.f = mf.d(wm) * F * mf.g(wo, wi) / (4.0f * cto * cti);
+    bs.wi = wi; bs.pdf = pdf; bs.flags = BX_GLOSSY | BX_REFLECTION;
+    return true;
+}
+
 static constexpr float kInv4Pi = 0.07957747154594766788f;
 SGD float henyey_greenstein(float cos_t, float g) {                       // scattering.rs:231-236
     g = clampf(g, -0.99f, 0.99f);
@@ -137,16 +179,29 @@ SGD float sample_henyey_greenstein(float3 wo, float g, float2 u, float3& wi) {  
 // sampling.rs:789-792: the reference evaluates the exponential PDF, not its inverse CDF (kept)
 SGD float sample_exponential(float x, float a) { return a * expf(-a * x); }
 
-struct Layered {
+// COND = false: CoatedDiffuseBxDF (bottom = DiffuseBxDF r); COND = true: CoatedConductorBxDF (bottom = ConductorBxDF ce, ck, mfb; bxdf.rs:460-463)
+template <bool COND>
+struct LayeredT {
     float eta; TR mf;            // top: DielectricBxDF
     Spec r;                      // bottom: DiffuseBxDF
+    Spec ce, ck; TR mfb;         // bottom: ConductorBxDF
     Spec albedo; float thickness, g; int max_depth, n_samples;
 
-    SGD int i_flags(bool top) const { return top ? dielectric_flags(eta, mf) : diffuse_flags(r); }
-    SGD Spec i_f(bool top, float3 wo, float3 wi, bool radiance) const { return top ? dielectric_f(eta, mf, wo, wi, radiance) : diffuse_f(r, wo, wi); }
-    SGD float i_pdf(bool top, float3 wo, float3 wi, int sf) const { return top ? dielectric_pdf(eta, mf, wo, wi, sf) : diffuse_pdf(wo, wi, sf); }
+    SGD int i_flags(bool top) const {
+        if (top) return dielectric_flags(eta, mf);
+        if constexpr (COND) return conductor_flags(mfb); else return diffuse_flags(r);
+    }
+    SGD Spec i_f(bool top, float3 wo, float3 wi, bool radiance) const {
+        if (top) return dielectric_f(eta, mf, wo, wi, radiance);
+        if constexpr (COND) return conductor_f(mfb, ce, ck, wo, wi); else return diffuse_f(r, wo, wi);
+    }
+    SGD float i_pdf(bool top, float3 wo, float3 wi, int sf) const {
+        if (top) return dielectric_pdf(eta, mf, wo, wi, sf);
+        if constexpr (COND) return conductor_pdf(mfb, wo, wi, sf); else return diffuse_pdf(wo, wi, sf);
+    }
     SGD bool i_sample(bool top, float3 wo, float uc, float2 u, bool radiance, int sf, BSDFSample& bs) const {
-        return top ? dielectric_sample(eta, mf, wo, uc, u, radiance, sf, bs) : diffuse_sample(r, wo, u, sf, bs);
+        if (top) return dielectric_sample(eta, mf, wo, uc, u, radiance, sf, bs);
+        if constexpr (COND) return conductor_sample(mfb, ce, ck, wo, u, sf, bs); else return diffuse_sample(r, wo, u, sf, bs);
     }
     SGD static float tr(float dz, float3 w) {                             // bxdf.rs:923-931 (`<= Float::MIN` never holds)
         if (fabsf(dz) <= -3.40282347e+38f) return 1.0f;

@@ -50,12 +50,14 @@ struct DScene {
     const float* rgb2spec_scale;        // rgb2spec table of the scene colour space
     const float* rgb2spec_data;
     uint32_t rgb2spec_res, n_textures;
+    const SgTextureMapping* texture_mappings;   // spherical / cylindrical / planar mappings (sg_texture.cuh)
+    const SgEnvMap* env_maps;           // ImageInfinitelight images + sampling distributions (sg_envmap.cuh)
     const DInstance* instances;         // object instancing
     const struct DSphere* spheres;      // sphere shapes (sg_sphere.cuh)
     const float4* patch_verts;          // bilinear patches: 4 float4 per patch primitive (sg_patch.cuh)
     uint32_t n_instances, scene_flags;
     uint32_t n_nodes, n_prims, n_lights, n_materials;
-    int32_t n_infinite;          // number of SG_LIGHT_UNIFORM_INFINITE lights
+    int32_t n_infinite;          // number of infinite lights (uniform + image)
     int32_t infinite_ids[4];
     SgCamera camera;
     SgFilm film;

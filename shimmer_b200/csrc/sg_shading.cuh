@@ -324,7 +324,8 @@ template <int KIND> struct BSDF {
     Spec r, k;            // diffuse: r ; conductor: eta (in r), k
     float eta;            // dielectric
     TR mf;
-    Layered lay;          // CoatedDiffuse only
+    static constexpr bool LAYERED = KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_COATED_CONDUCTOR;
+    LayeredT<KIND == SG_MATERIAL_COATED_CONDUCTOR> lay;   // CoatedDiffuse / CoatedConductor only
     uint64_t layer_seed;  // seeds the LayeredBxDF's private generator for the next f / sample_f / pdf call
     bool proportional;    // BSDFSample::pdf_is_proportional of the last sample_f
     float3 fx, fy, fz;    // Frame::from_xz(normalize(dpdus), ns), bsdf.rs:22-28
@@ -333,7 +334,7 @@ template <int KIND> struct BSDF {
     SGD float3 to_local(float3 v) const { return f3(dot3(v, fx), dot3(v, fy), dot3(v, fz)); }      // frame.rs:39-41
     SGD float3 from_local(float3 v) const { return v.x * fx + v.y * fy + v.z * fz; }               // frame.rs:51-53
     SGD int flags() const {
-        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.flags();
+        if (LAYERED) return lay.flags();
         if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return BX_REFLECTION | BX_TRANSMISSION | BX_SPECULAR;   // bxdf.rs:873-875
         if (KIND == SG_MATERIAL_DIFFUSE) return spec_zero(r) ? 0 : (BX_DIFFUSE | BX_REFLECTION);     // bxdf.rs:256-262
         if (KIND == SG_MATERIAL_CONDUCTOR) return (mf.smooth() ? BX_SPECULAR : BX_GLOSSY) | BX_REFLECTION;   // :447-453
@@ -341,7 +342,7 @@ template <int KIND> struct BSDF {
         return f | (mf.smooth() ? BX_SPECULAR : BX_GLOSSY);
     }
     SGD Spec f_local(float3 wo, float3 wi) const {
-        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.f(wo, wi, layer_rng());
+        if (LAYERED) return lay.f(wo, wi, layer_rng());
         if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return spec1(0.0f);                                 // bxdf.rs:808-810
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :196-202
             if (!same_hemisphere(wo, wi)) return spec1(0.0f);
@@ -375,7 +376,7 @@ template <int KIND> struct BSDF {
         }
     }
     SGD float pdf_local(float3 wo, float3 wi) const {
-        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.pdf(wo, wi, layer_rng());
+        if (LAYERED) return lay.pdf(wo, wi, layer_rng());
         if (KIND == SG_MATERIAL_THIN_DIELECTRIC) return 0.0f;                                        // bxdf.rs:863-871
         if (KIND == SG_MATERIAL_DIFFUSE) {                                                          // :240-254
             if (!same_hemisphere(wo, wi)) return 0.0f;
@@ -407,7 +408,7 @@ template <int KIND> struct BSDF {
     }
     SGD bool sample_local(float3 wo, float uc, float2 u, BSDFSample& bs, bool& prop) const {
         bs.eta = 1.0f; prop = false;
-        if (KIND == SG_MATERIAL_COATED_DIFFUSE) return lay.sample_f(wo, uc, u, layer_rng(), bs, prop);
+        if (LAYERED) return lay.sample_f(wo, uc, u, layer_rng(), bs, prop);
         if (KIND == SG_MATERIAL_THIN_DIELECTRIC) {                                                   // ThinDielectricBxDF::sample_f bxdf.rs:812-861
             float R = fresnel_dielectric(fabsf(wo.z), eta), T = 1.0f - R;
             if (R < 1.0f) { R += sqr(T) * R / (1.0f - sqr(R)); T = 1.0f - R; }
@@ -718,8 +719,13 @@ SGD float tri_pdf_with_context(const DScene& sc, const TriGeo& g, const LightCtx
 // Sphere emitters (sphere.rs:299-457): defined in sg_sphere_surface.cuh (they need the sphere's SurfaceInteraction)
 __device__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf);
 __device__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi);
-// Light::sample_li with allow_incomplete_pdf = true (integrator.rs:933)
-SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls) {
+// Infinite lights (uniform: light.rs:697-803, image: :805-981): defined in sg_envmap.cuh, out of line
+__device__ bool infinite_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, bool allow_incomplete, LightSample& ls);
+__device__ float infinite_pdf_li(const DScene& sc, const SgLight& lt, float3 wi, bool allow_incomplete);
+__device__ Spec infinite_le(const DScene& sc, const SgLight& lt, float3 ray_d, const Wavelengths& lam);
+// Light::sample_li; allow_incomplete_pdf = true from PathIntegrator::sample_ld (integrator.rs:933), false from SimplePath (:652-656)
+SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls,
+                         bool allow_incomplete = true) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {   // light.rs:632-661
         P3fi pi; float3 n; float pdf;
         if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) { if (!sphere_sample_with_context(sc.spheres[lt.tri], ctx, u, pi, n, pdf)) return false; }
@@ -741,12 +747,13 @@ SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt,
         ls.pdf = 1.0f; ls.p_light = p3fi_exact(p); ls.n_light = f3(0.0f, 0.0f, 0.0f);
         return true;
     }
+    if (lt.kind == SG_LIGHT_IMAGE_INFINITE || !allow_incomplete) return infinite_sample_li(sc, lt, ctx, u, lam, allow_incomplete, ls);
     return false;                                                            // UniformInfiniteLight: None, light.rs:748-750
 }
 SGD float light_pdf_li(const DScene& sc, const SgLight& lt, const TriGeo& g, const LightCtx& ctx, float3 wi) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, g, ctx, wi);                   // light.rs:663-666
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc, sc.spheres[lt.tri], ctx, wi);
-    return 0.0f;                                                             // :486-494, :770-781 (allow_incomplete_pdf)
+    return 0.0f;                                                             // :486-494 (infinite lights: infinite_pdf_li)
 }
 
 // ---------------- camera (camera.rs:1003-1079, transform.rs:385-457,515-532,753-776) ----------------

@@ -193,7 +193,9 @@ SGD float sigmoid_poly_get(const float c[3], float lambda) {
     return 0.5f + x / (2.0f * sqrtf(1.0f + x * x));
 }
 
-struct TexCoordCtx { float2 uv; float dudx, dudy, dvdx, dvdy; };
+// TextureEvalContext (texture.rs): uv + screen-space derivatives.  `pdp` -> {p, dpdx, dpdy} for the non-UV mappings
+// (texture.rs:938-1035); null in scenes without SgTextureMapping rows, so the UV-only kernels carry nothing extra.
+struct TexCoordCtx { float2 uv; float dudx, dudy, dvdx, dvdy; const float3* pdp = nullptr; };
 
 SGD void uv_map(const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {   // texture.rs:918-936
     const float dsdx = t.su * c.dudx, dsdy = t.su * c.dudy, dtdx = t.sv * c.dvdx, dtdy = t.sv * c.dvdy;
@@ -201,11 +203,43 @@ SGD void uv_map(const SgTexture& t, const TexCoordCtx& c, float2& st, float2& ds
     st.y = 1.0f - st.y;
     dst0 = make_float2(dsdx, dtdx); dst1 = make_float2(dsdy, dtdy);
 }
+// SphericalMapping / CylindricalMapping / PlanarMapping ::map texture.rs:943-1035 (as written there), then the t flip of the
+// image textures (:396-399, :780-781)
+__device__ __noinline__ void general_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {
+    const SgTextureMapping& M = sc.texture_mappings[t.mapping];
+    const float3 p = c.pdp ? c.pdp[0] : f3(0.0f, 0.0f, 0.0f);
+    const float3 pt = xform_point(M.texture_from_render, p);
+    const float3 dpdx = xform_vector(M.texture_from_render, c.pdp ? c.pdp[1] : f3(0.0f, 0.0f, 0.0f));
+    const float3 dpdy = xform_vector(M.texture_from_render, c.pdp ? c.pdp[2] : f3(0.0f, 0.0f, 0.0f));
+    float3 dsdp, dtdp;
+    if (M.kind == SG_MAPPING_SPHERICAL) {
+        const float x2y2 = sqr(pt.x) + sqr(pt.y), sqrtx2y2 = sqrtf(x2y2);
+        dsdp = f3(-pt.y, pt.x, 0.0f) / (2.0f * kPi * x2y2);
+        dtdp = 1.0f / (kPi * (x2y2 + sqr(pt.z))) * f3(pt.x * pt.z / sqrtx2y2, pt.y * pt.z / sqrtx2y2, -sqrtx2y2);
+        const float3 vec = normalize3(pt - f3(0.0f, 0.0f, 0.0f));
+        const float theta = safe_asin(vec.z);                                   // spherical_theta = safe_acos, which calls asin (math.rs:272-274)
+        st = make_float2(theta * kInvPi, theta * 0.15915494309189533577f);       // sic: both from theta (texture.rs:960-963)
+    } else if (M.kind == SG_MAPPING_CYLINDRICAL) {
+        const float x2y2 = sqr(pt.x) + sqr(pt.y);
+        dsdp = f3(-pt.y, pt.x, 0.0f) / (2.0f * kPi * x2y2);
+        dtdp = f3(0.0f, 0.0f, 1.0f);
+        st = make_float2(kPi + atan2f(pt.y, pt.x) * 0.15915494309189533577f, pt.z);   // sic: texture.rs:990-993
+    } else {
+        dsdp = f3(M.vs[0], M.vs[1], M.vs[2]); dtdp = f3(M.vt[0], M.vt[1], M.vt[2]);
+        st = make_float2(M.ds + dot3(pt, dsdp), M.dt + dot3(pt, dtdp));
+    }
+    dst0 = make_float2(dot3(dsdp, dpdx), dot3(dtdp, dpdx));                     // (dsdx, dtdx)
+    dst1 = make_float2(dot3(dsdp, dpdy), dot3(dtdp, dpdy));                     // (dsdy, dtdy)
+    st.y = 1.0f - st.y;
+}
+SGD void tex_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {
+    if (t.mapping < 0) uv_map(t, c, st, dst0, dst1); else general_map(sc, t, c, st, dst0, dst1);
+}
 // FloatImageTexture::evaluate texture.rs:393-404
 __device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
-    float2 st, d0, d1; uv_map(t, c, st, d0, d1);
+    float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
     const float v = tex_filter<false>(tv, st, d0, d1).x * t.scale;
     return t.invert ? fmaxf(0.0f, 1.0f - v) : v;
 }
@@ -213,7 +247,7 @@ __device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, cons
 __device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
-    float2 st, d0, d1; uv_map(t, c, st, d0, d1);
+    float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
     float3 rgb = tex_filter<true>(tv, st, d0, d1) * t.scale;
     if (t.invert) rgb = f3(1.0f - rgb.x, 1.0f - rgb.y, 1.0f - rgb.z);
     rgb = f3(fmaxf(0.0f, rgb.x), fmaxf(0.0f, rgb.y), fmaxf(0.0f, rgb.z));                        // clamp_zero
@@ -351,7 +385,9 @@ SGD void compute_differentials(const DScene& sc, const Surf& s, SurfTex& x, cons
 // bump_map material.rs:1477-1509 for a FloatImageTexture (tex >= 0) or the constant displacement `cdisp`; writes the
 // displaced shading.dpdu / dpdv (the caller then rebuilds the shading normal, interaction.rs:229-250)
 SGD void bump_map(const DScene& sc, int tex, float cdisp, Surf& s, const SurfTex& x) {
-    const TexCoordCtx c{x.uv, x.dudx, x.dudy, x.dvdx, x.dvdy};
+    float3 pdp[3] = {p3fi_mid(s.pi), x.dpdx, x.dpdy};
+    const bool mapped = sc.texture_mappings != nullptr;                         // shifted_ctx.p only matters to the non-UV mappings
+    const TexCoordCtx c{x.uv, x.dudx, x.dudy, x.dvdx, x.dvdy, mapped ? pdp : nullptr};
     float du = 0.5f * (fabsf(x.dudx) + fabsf(x.dudy));
     if (du == 0.0f) du = 0.0005f;
     float dv = 0.5f * (fabsf(x.dvdx) + fabsf(x.dvdy));
@@ -360,11 +396,29 @@ SGD void bump_map(const DScene& sc, int tex, float cdisp, Surf& s, const SurfTex
     if (tex >= 0) {
         TexCoordCtx cu = c; cu.uv = make_float2(x.uv.x + du, x.uv.y + 0.0f);
         TexCoordCtx cv = c; cv.uv = make_float2(x.uv.x + 0.0f, x.uv.y + dv);
-        u_displace = eval_float_texture(sc, tex, cu); v_displace = eval_float_texture(sc, tex, cv); displace = eval_float_texture(sc, tex, c);
+        displace = eval_float_texture(sc, tex, c);
+        const float3 p0 = pdp[0];
+        if (mapped) pdp[0] = p0 + du * s.sdpdu;                                  // material.rs:1488
+        u_displace = eval_float_texture(sc, tex, cu);
+        if (mapped) pdp[0] = p0 + dv * s.sdpdv;                                  // :1499
+        v_displace = eval_float_texture(sc, tex, cv);
     } else u_displace = v_displace = displace = cdisp;
     const float3 dpdu = s.sdpdu + (u_displace - displace) / du * s.sn + displace * x.dndu;
     const float3 dpdv = s.sdpdv + (v_displace - displace) / dv * s.sn + displace * x.dndv;
     s.sdpdu = dpdu; s.sdpdv = dpdv;
+}
+
+// normal_map material.rs:1453-1474: level 0 of a three-channel image through Image::bilerp_channel_wrapped with WrapMode::Repeat
+__device__ __noinline__ void normal_map(const DScene& sc, int tex, Surf& s, const SurfTex& x) {
+    SgTexture t = sc.textures[tex]; t.wrap = SG_WRAP_REPEAT;
+    const TexView tv{sc, t};
+    const float3 px = tex_bilerp<true>(tv, 0, make_float2(x.uv.x, 1.0f - x.uv.y));
+    float3 ns = normalize3(f3(2.0f * px.x - 1.0f, 2.0f * px.y - 1.0f, 2.0f * px.z - 1.0f));
+    const float3 fx = normalize3(s.sdpdu), fz = s.sn, fy = cross3(fz, fx);      // Frame::from_xz frame.rs:14-17
+    ns = ns.x * fx + ns.y * fy + ns.z * fz;
+    const float ulen = len3(s.sdpdu), vlen = len3(s.sdpdv);
+    const float3 dpdu = normalize3(gram_schmidt3(s.sdpdu, ns)) * ulen;
+    s.sdpdu = dpdu; s.sdpdv = normalize3(cross3(ns, dpdu)) * vlen;
 }
 
 // SurfaceInteraction::spawn_ray_with_differentials interaction.rs:434-502 (auxiliary rays only)

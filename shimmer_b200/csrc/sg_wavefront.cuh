@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include "sg_shading.cuh"
 #include "sg_texture.cuh"
+#include "sg_envmap.cuh"
 #include "sg_trace2.cuh"
 #include "sg_sphere_surface.cuh"
 
@@ -21,6 +22,7 @@ struct PathState {
     float4* hit_b;      // b0 b1 b2 t
     int*    hit_prim;
     int*    hit_inst;   // instance index of the hit or -1; allocated only for scenes with object instances
+    uint32_t* mat_override;  // material chosen by MixMaterial::choose_material for the current hit; allocated only for scenes with Mix materials
     float4* L;
     float4* beta;
     float4* lambda;
@@ -55,9 +57,9 @@ SGD void aux_store(const PathState& st, uint32_t path, const AuxRays& r) {
     st.aux2[path] = make_float4(r.ryo.z, r.ryd.x, r.ryd.y, r.ryd.z);
 }
 
-enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_THIN = 5, Q_NKINDS = 6 };
+enum { Q_MISS = 0, Q_DIFFUSE = 1, Q_CONDUCTOR = 2, Q_DIELECTRIC = 3, Q_COATED = 4, Q_THIN = 5, Q_COATED_CONDUCTOR = 6, Q_MIX = 7, Q_NKINDS = 8 };
 // per-depth counter block (uint32 x 16)
-enum { C_NRAY = 0, C_NSHADE = 1 /*..6*/, C_NSHADOW = 7, C_CUR_CLOSEST = 8, C_CUR_SHADOW = 9, C_STRIDE = 16 };
+enum { C_NRAY = 0, C_NSHADE = 1 /*..8*/, C_NSHADOW = 9, C_CUR_CLOSEST = 10, C_CUR_SHADOW = 11, C_STRIDE = 16 };
 
 struct Queues {
     uint32_t* ray[2];
@@ -77,6 +79,8 @@ struct RenderConst {
     int32_t  full_res_x;
     int32_t  n_samples;          // sample_end - sample_begin of this call
     int32_t  path_order;         // 0 = sample-major row-major (debug), 1 = pixel-major tiled
+    int32_t  integrator;         // SgIntegratorKind
+    int32_t  integrator_flags;   // SG_SIMPLEPATH_*
 };
 
 // Path order of a wavefront.  Wavefront slot g -> (pixel, sample): pixel-major, so the samples of one pixel
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
 }
 
 // ---- escaped rays: infinite lights, integrator.rs:776-794 ----
-__global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DScene sc, PathState st, Queues q, int depth) {
+__global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     const uint32_t* C = q.counters + depth * C_STRIDE;
     const uint32_t n = C[C_NSHADE + Q_MISS];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -392,12 +396,16 @@ __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DSce
         Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
         Spec L = st.L[path]; const Spec beta = st.beta[path];
         const float p_b = st.pb_eta[path].x;
+        const float4 rd4 = st.ray_d[path];
+        const float3 rd = f3(rd4.x, rd4.y, rd4.z);
         for (int k = 0; k < sc.n_infinite; ++k) {
             const SgLight lt = sc.lights[sc.infinite_ids[k]];
-            Spec le = lt.scale * spectrum_sample(sc, lt.spectrum, lam);          // UniformInfiniteLight::le light.rs:792-794
-            if (pdepth == 0 || specular_bounce) L = L + beta * le;
+            Spec le = infinite_le(sc, lt, rd, lam);                              // light.rs:792-794, :907-911
+            if (rc.integrator != SG_INTEGRATOR_PATH) {                           // SimplePath integrator.rs:613-620 (specular_bounce starts true), RandomWalk :506-512
+                if (rc.integrator == SG_INTEGRATOR_RANDOM_WALK || !(rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_LIGHTS) || pdepth == 0 || specular_bounce) L = L + beta * le;
+            } else if (pdepth == 0 || specular_bounce) L = L + beta * le;
             else {
-                float p_l = (1.0f / (float)sc.n_lights) * 0.0f;                  // pdf_li(.., allow_incomplete_pdf = true) = 0, light.rs:770-781
+                float p_l = (1.0f / (float)sc.n_lights) * infinite_pdf_li(sc, lt, rd, true);   // uniform: 0 (light.rs:770-781); image: compensated pdf (:882-892)
                 float w_b = power_heuristic(p_b, p_l);
                 L = L + beta * w_b * le;
             }
@@ -429,6 +437,66 @@ __device__ __noinline__ Surf surface_general(const DScene& sc, const TriGeo& geo
     return s;
 }
 
+// ---- MixMaterial resolution (interaction.rs:206-221, MixMaterial::choose_material material.rs:1309-1330) ----
+// Runs between the closest-hit kernel and the shade kernels of a depth: every path whose hit carries a Mix material gets its
+// final material (st.mat_override) and is appended to that material kind's shade queue.  The stochastic choice draws from a
+// generator seeded by the path stream's state (site 5; the stream itself does not advance) -- see SG_MATERIAL_MIX.
+template <bool TEX>
+__global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+    uint32_t* C = q.counters + depth * C_STRIDE;
+    const uint32_t n = C[C_NSHADE + Q_MIX];
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        int kind = -1; uint32_t path = 0;
+        if (i < n) {
+            path = q.shade[Q_MIX][i];
+            uint32_t material_id; int light_id;
+            const TriGeo geo = geo_from_prim(sc, (uint32_t)st.hit_prim[path], material_id, light_id);
+            float3 pdp[3];
+            TexCoordCtx tc{make_float2(0.0f, 0.0f), 0.0f, 0.0f, 0.0f, 0.0f};
+            bool have_ctx = false;
+            Rng mr; mr.seed_from_u64(mix64(st.rng_a[path].x ^ (5ull * 0x9e3779b97f4a7c15ULL)));      // layer_seed(rng, 5)
+            for (int guard = 0; guard < 64 && sc.materials[material_id].kind == SG_MATERIAL_MIX; ++guard) {
+                const SgMaterial mm = sc.materials[material_id];
+                float amt = mm.mix_amount;
+                if (TEX && mm.tex_mix_amount >= 0) {
+                    if (!have_ctx) {                                                               // the hit's TextureEvalContext, as k_shade builds it
+                        const float4 rd4 = st.ray_d[path]; const float3 rd = f3(rd4.x, rd4.y, rd4.z);
+                        const float4 hb = st.hit_b[path];
+                        SurfTex sx; Surf s; float3 wo_si = -rd;
+                        if (st.hit_inst == nullptr) s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
+                        else s = surface_general<TEX>(sc, geo, hb, rd, st.hit_inst[path], &sx, wo_si);
+                        AuxRays aux; aux.has = false;
+                        if (st.flags[path] & kFlagAux) aux = aux_load(st, path);
+                        compute_differentials(sc, s, sx, aux, rc.spp, rc.option_flags);
+                        tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
+                        if (sc.texture_mappings != nullptr) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; tc.pdp = pdp; }
+                        have_ctx = true;
+                    }
+                    amt = eval_float_texture(sc, mm.tex_mix_amount, tc);
+                }
+                if (amt <= 0.0f) material_id = (uint32_t)mm.mix_materials[0];
+                else if (amt >= 1.0f) material_id = (uint32_t)mm.mix_materials[1];
+                else { const float u = mr.get_1d(); material_id = (uint32_t)(amt < u ? mm.mix_materials[0] : mm.mix_materials[1]); }
+            }
+            st.mat_override[path] = material_id;
+            kind = 1 + sc.materials[material_id].kind;
+        }
+#pragma unroll 1
+        for (int k = 1; k < Q_MIX; ++k) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, kind == k);
+            if (mask) {
+                uint32_t qbase = 0;
+                const int leader = __ffs(mask) - 1;
+                if (lane == leader) qbase = atomicAdd(C + C_NSHADE + k, (uint32_t)__popc(mask));
+                qbase = __shfl_sync(0xffffffffu, qbase, leader);
+                if (kind == k) q.shade[k][qbase + __popc(mask & ((1u << lane) - 1u))] = path;
+            }
+        }
+    }
+}
+
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
 #ifndef SG_SHADE_MIN_BLOCKS
@@ -436,7 +504,9 @@ __device__ __noinline__ Surf surface_general(const DScene& sc, const TriGeo& geo
 #endif
 // TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture
 // lookups, bump mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.
-template <int KIND, bool TEX>
+// PATH = false: the SimplePathIntegrator (integrator.rs:570-728) / RandomWalkIntegrator (:458-568) bodies, chosen at run time by
+// rc.integrator; instantiated with TEX = true only (that variant is a superset: it also renders untextured scenes).
+template <int KIND, bool TEX, bool PATH = true>
 __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
@@ -511,12 +581,16 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             if (st.hit_inst == nullptr) s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
             else s = surface_general<TEX>(sc, geo, hb, rd, st.hit_inst[path], &sx, wo_si);
 
+            const bool simple = !PATH && rc.integrator == SG_INTEGRATOR_SIMPLE_PATH, walk = !PATH && !simple;
+            const bool sample_lights = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_LIGHTS) != 0, sample_bsdf_dir = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_BSDF) != 0;
             // emission + MIS against light sampling, :798-813
             if (light_id >= 0) {
                 const SgLight lt = sc.lights[light_id];
                 Spec le = light_l(sc, lt, s.n, wo, lam);
                 if (!spec_zero(le)) {
-                    if (pdepth == 0 || specular_bounce) L = L + beta * le;
+                    if (!PATH) {                                         // SimplePath :625-629 (specular_bounce starts true), RandomWalk :519-520
+                        if (walk || !sample_lights || pdepth == 0 || specular_bounce) L = L + beta * le;
+                    } else if (pdepth == 0 || specular_bounce) L = L + beta * le;
                     else {
                         LightCtx pc;
                         const float4 c0 = st.ctx0[path], c1 = st.ctx1[path], c2 = st.ctx2[path];
@@ -530,18 +604,25 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             }
 
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
-            const SgMaterial mat = sc.materials[material_id];
+            SgMaterial mat = sc.materials[material_id];
+            if (mat.kind == SG_MATERIAL_MIX) mat = sc.materials[st.mat_override[path]];             // resolved by k_resolve_mix (interaction.rs:206-221)
             AuxRays aux; aux.has = false;
             if (TEX) {
                 if (sc.n_textures > 0) {
                     if (fl & kFlagAux) aux = aux_load(st, path);
                     compute_differentials(sc, s, sx, aux, rc.spp, rc.option_flags);                 // interaction.rs:201
                 }
-                if ((mat.flags & SG_MAT_HAS_DISPLACEMENT) && (mat.tex_displacement >= 0 || mat.displacement != 0.0f))
-                    bump_map(sc, mat.tex_displacement, mat.displacement, s, sx);
+                if (mat.flags & SG_MAT_HAS_DISPLACEMENT) {
+                    if (mat.tex_displacement >= 0 || mat.displacement != 0.0f) bump_map(sc, mat.tex_displacement, mat.displacement, s, sx);
+                } else if (mat.normal_map >= 0) normal_map(sc, mat.normal_map, s, sx);              // only without a displacement: interaction.rs:229-244
             }
-            if (mat.flags & SG_MAT_HAS_DISPLACEMENT) apply_constant_bump(s);
-            TexCoordCtx tc; if (TEX) tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
+            if ((mat.flags & SG_MAT_HAS_DISPLACEMENT) || (TEX && mat.normal_map >= 0)) apply_constant_bump(s);
+            float3 pdp[3];
+            TexCoordCtx tc;
+            if (TEX) {
+                tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
+                if (sc.texture_mappings != nullptr) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; tc.pdp = pdp; }
+            }
             BSDF<KIND> bsdf;
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
@@ -561,6 +642,31 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 bsdf.lay.albedo = spec_clamp(spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
                 bsdf.lay.g = clampf(mat.g, -1.0f, 1.0f);
                 bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
+            } else if (KIND == SG_MATERIAL_COATED_CONDUCTOR) {                                 // material.rs:1188-1260
+                float iur = mat.u_roughness, ivr = mat.v_roughness;
+                if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { iur = sqrtf(iur); ivr = sqrtf(ivr); }
+                bsdf.lay.mf = TR::make(iur, ivr);
+                bsdf.lay.thickness = mat.thickness;
+                float ieta = spectrum_get(sc, mat.spec_c, lam.lambda.x);
+                if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
+                if (ieta == 0.0f) ieta = 1.0f;
+                bsdf.lay.eta = ieta;
+                Spec ce, ck;
+                if (!(mat.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = spectrum_sample(sc, mat.spec_a, lam); ck = spectrum_sample(sc, mat.spec_d, lam); }
+                else {                                                                         // :1225-1233
+                    const Spec r = spec_clamp(spectrum_sample(sc, mat.spec_a, lam), 0.0f, 0.9999f);
+                    ce = spec1(1.0f);
+                    ck = make_float4(2.0f * sqrtf(r.x) / sqrtf(fmaxf(0.0f, 1.0f - r.x)), 2.0f * sqrtf(r.y) / sqrtf(fmaxf(0.0f, 1.0f - r.y)),
+                                     2.0f * sqrtf(r.z) / sqrtf(fmaxf(0.0f, 1.0f - r.z)), 2.0f * sqrtf(r.w) / sqrtf(fmaxf(0.0f, 1.0f - r.w)));
+                }
+                bsdf.lay.ce = ce / ieta; bsdf.lay.ck = ck / ieta;
+                float cur = mat.u_roughness2, cvr = mat.v_roughness2;
+                if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { cur = sqrtf(iur); cvr = sqrtf(ivr); } // sic: roughness_to_alpha(iurough), material.rs:1237-1241
+                bsdf.lay.mfb = TR::make(cur, cvr);
+                bsdf.lay.r = spec1(0.0f);
+                bsdf.lay.albedo = spec_clamp(spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                bsdf.lay.g = clampf(mat.g, -1.0f, 1.0f);
+                bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
             } else {
                 float ur = mat.u_roughness, vr = mat.v_roughness;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }     // roughness_to_alpha
@@ -575,13 +681,81 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 bsdf.mf = TR::make(ur, vr);
             }
             bsdf.fx = normalize3(s.sdpdu); bsdf.fz = s.sn; bsdf.fy = cross3(bsdf.fz, bsdf.fx);
-            if (rc.regularize && any_non_specular) { bsdf.mf.regularize(); if (KIND == SG_MATERIAL_COATED_DIFFUSE) bsdf.lay.mf.regularize(); }   // :825-828
+            if (PATH && rc.regularize && any_non_specular) {                                    // :825-828
+                bsdf.mf.regularize();
+                if (KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_COATED_CONDUCTOR) bsdf.lay.mf.regularize();
+                if (KIND == SG_MATERIAL_COATED_CONDUCTOR) bsdf.lay.mfb.regularize();          // LayeredBxDF::regularize bxdf.rs:1616-1619
+            }
 
             bool alive = pdepth != rc.max_depth;                                               // :830-833
             if (alive) {
                 pdepth += 1;
                 Rng rng; { ulonglong2 a = st.rng_a[path], b = st.rng_b[path]; rng.s0 = a.x; rng.s1 = a.y; rng.s2 = b.x; rng.s3 = b.y; }
                 const int bflags = bsdf.flags();
+                if constexpr (!PATH) {
+                    if (simple && sample_lights) {                                             // integrator.rs:644-672
+                        const float ul = rng.get_1d();
+                        if (sc.n_lights > 0) {
+                            float2 u_light; u_light.x = rng.get_1d(); u_light.y = rng.get_1d();
+                            uint32_t li = __float2uint_rz(ul * (float)sc.n_lights);
+                            if (li > sc.n_lights - 1) li = sc.n_lights - 1;
+                            const float p_choose = 1.0f / (float)sc.n_lights;
+                            const SgLight lt = sc.lights[li];
+                            LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;           // LightSampleContext::from(&isect): no nudge
+                            LightSample ls;
+                            if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls, false) && !spec_zero(ls.l) && ls.pdf > 0.0f) {
+                                bsdf.layer_seed = layer_seed(rng, 1);
+                                const Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);          // wo = -ray.d (:646), not intr.wo
+                                if (!spec_zero(f)) {
+                                    float3 pf = offset_ray_origin(s.pi, s.n, p3fi_mid(ls.p_light) - p3fi_mid(s.pi));
+                                    float3 pt = offset_ray_origin(ls.p_light, ls.n_light, pf - p3fi_mid(ls.p_light));
+                                    float3 sd = pt - pf;
+                                    st.sh_o[path] = make_float4(pf.x, pf.y, pf.z, 0.0f);
+                                    st.sh_d[path] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                                    st.sh_L[path] = beta * f * ls.l / (p_choose * ls.pdf);     // :669
+                                    want_shadow = true;
+                                }
+                            }
+                        }
+                    }
+                    float3 wi_new = f3(0.0f, 0.0f, 0.0f);
+                    if (simple && sample_bsdf_dir) {                                           // :675-691
+                        const float u = rng.get_1d();
+                        float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+                        BSDFSample bs; bool prop = false;
+                        bsdf.layer_seed = layer_seed(rng, 3);
+                        alive = bsdf.sample_f(wo, u, u2, bs, prop);
+                        if (alive) { beta = beta * (bs.f * absdot3(bs.wi, s.sn) / bs.pdf); specular_bounce = (bs.flags & BX_SPECULAR) != 0; wi_new = bs.wi; }
+                    } else if (simple) {                                                       // :692-721 uniform sphere / hemisphere sampling
+                        const bool refl = bflags & BX_REFLECTION, trans = bflags & BX_TRANSMISSION;
+                        float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+                        const float phi = 2.0f * kPi * u2.y;
+                        if (refl && trans) { const float z = 1.0f - 2.0f * u2.x, r = safe_sqrt(1.0f - z * z); wi_new = f3(r * cosf(phi), r * sinf(phi), z); }
+                        else {
+                            const float z = u2.x, r = safe_sqrt(1.0f - z * z); wi_new = f3(r * cosf(phi), r * sinf(phi), z);   // sample_uniform_hemisphere sampling.rs:295-304
+                            if ((refl && dot3(wo, s.n) * dot3(wi_new, s.n) < 0.0f) || (trans && dot3(wo, s.n) * dot3(wi_new, s.n) > 0.0f)) wi_new = -wi_new;
+                        }
+                        bsdf.layer_seed = layer_seed(rng, 3);
+                        beta = beta * (bsdf.f(wo, wi_new) * absdot3(wi_new, s.sn) / kInv4Pi);    // uniform_hemisphere_pdf() == 1/(4 pi) too (sampling.rs:306-308)
+                        specular_bounce = false;
+                    } else {                                                                   // RandomWalk :535-566
+                        float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+                        const float z = 1.0f - 2.0f * u2.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * kPi * u2.y;
+                        wi_new = f3(r * cosf(phi), r * sinf(phi), z);
+                        bsdf.layer_seed = layer_seed(rng, 1);
+                        const Spec f = bsdf.f(wo, wi_new);
+                        if (spec_zero(f)) alive = false;
+                        else beta = beta * (f * absdot3(wi_new, s.sn)) / (1.0f / (4.0f * kPi));
+                        specular_bounce = false;
+                    }
+                    if (alive && simple && spec_zero(beta)) alive = false;                     // `while !beta.is_zero()` :606
+                    if (alive) {
+                        const float3 no = offset_ray_origin(s.pi, s.n, wi_new);                // Interaction::spawn_ray: no differentials
+                        st.ray_o[path] = make_float4(no.x, no.y, no.z, 0.0f);
+                        st.ray_d[path] = make_float4(wi_new.x, wi_new.y, wi_new.z, 0.0f);
+                        aux.has = false;
+                    }
+                } else {
                 // ---- sample_ld :897-963 ----
                 if (bflags & (BX_DIFFUSE | BX_GLOSSY)) {
                     LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;
@@ -655,6 +829,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                         }
                     }
                 }
+                }   // PATH
                 st.rng_a[path] = make_ulonglong2(rng.s0, rng.s1); st.rng_b[path] = make_ulonglong2(rng.s2, rng.s3);
             }
             st.L[path] = L;
@@ -664,7 +839,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 st.flags[path] = (uint32_t)pdepth | (specular_bounce ? kFlagSpecular : 0u) | (any_non_specular ? kFlagNonSpecular : 0u) |
                                  (TEX && aux.has ? kFlagAux : 0u);
             }
-            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC) st.lpdf[path] = lam.pdf;   // terminate_secondary
+            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC || KIND == SG_MATERIAL_COATED_CONDUCTOR) st.lpdf[path] = lam.pdf;   // terminate_secondary
             want_next = alive;
         }
         __syncwarp();
@@ -802,10 +977,16 @@ __global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc,
     l[0] = lam.lambda.x; l[1] = lam.lambda.y; l[2] = lam.lambda.z; l[3] = lam.lambda.w;
     l[4] = lam.pdf.x; l[5] = lam.pdf.y; l[6] = lam.pdf.z; l[7] = lam.pdf.w;
 }
-__global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* lambda, float* out) {
+__global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* pdp_in, const float* lambda, float* out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     TexCoordCtx c; c.uv = make_float2(q[6 * i], q[6 * i + 1]); c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
+    float3 pdp[3];
+    if (pdp_in) {
+        const float* r = pdp_in + 9 * i;
+        pdp[0] = f3(r[0], r[1], r[2]); pdp[1] = f3(r[3], r[4], r[5]); pdp[2] = f3(r[6], r[7], r[8]);
+        c.pdp = pdp;
+    }
     Spec s;
     if (as_float) s = spec1(eval_float_texture(sc, tex, c));
     else {

@@ -56,8 +56,9 @@ struct SgScene {
     Workspace ws;
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
-    bool kinds_present[5] = {false, false, false, false, false};
+    bool kinds_present[8] = {false, false, false, false, false, false, false, false};
     bool instanced = false;         // object instances: k_trace<.., INST = true> and the hit_inst path-state array
+    bool has_mix = false;           // Mix materials: k_resolve_mix + the mat_override path-state array
     bool tex_path = false;          // image textures or a non-zero constant displacement: k_shade<KIND, true>
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
@@ -84,7 +85,8 @@ int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
     WS(ray_o); WS(ray_d); WS(hit_b); WS(hit_prim); WS(L); WS(beta); WS(lambda); WS(lpdf); WS(rng_a); WS(rng_b);
     WS(pixel); WS(flags); WS(pb_eta); WS(ctx0); WS(ctx1); WS(ctx2); WS(sh_o); WS(sh_d); WS(sh_L);
     if (s->d.n_textures > 0) { WS(aux0); WS(aux1); WS(aux2); }
-    if (s->instanced) { WS(hit_inst); }      // ray differentials only feed image-texture filtering
+    if (s->instanced) { WS(hit_inst); }
+    if (s->has_mix) { WS(mat_override); }      // ray differentials only feed image-texture filtering
 #undef WS
     if ((rc = ws_alloc(w, &w.q.ray[0], n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.ray[1], n)) != SG_OK) return rc;
@@ -192,20 +194,56 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (desc->instances[i].object >= desc->n_objects) return fail(SG_ERR_INVALID_ARGUMENT, "instance " + std::to_string(i) + " references an out-of-range object");
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
         const SgLight& L = desc->lights[i];
-        if (L.kind < SG_LIGHT_DIFFUSE_AREA || L.kind > SG_LIGHT_DIFFUSE_AREA_SPHERE) return fail(SG_ERR_UNSUPPORTED, "light kind " + std::to_string(L.kind) + " is not on the GPU path");
+        if (L.kind < SG_LIGHT_DIFFUSE_AREA || L.kind > SG_LIGHT_IMAGE_INFINITE) return fail(SG_ERR_UNSUPPORTED, "light kind " + std::to_string(L.kind) + " is not on the GPU path");
         if (L.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE && L.tri >= desc->n_spheres) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + " references an out-of-range sphere");
+        if (L.kind == SG_LIGHT_IMAGE_INFINITE && (L.tri >= desc->n_env_maps || !desc->env_maps)) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + " references an out-of-range environment map");
+        if (L.spectrum < 0 || L.spectrum >= (int32_t)desc->n_spectra) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + ": spectrum id out of range");
+    }
+    for (uint32_t i = 0; i < desc->n_env_maps; ++i) {
+        const SgEnvMap& E = desc->env_maps[i];
+        if (E.res < 1 || !desc->texels || E.texel_offset + (uint64_t)E.res * (uint64_t)E.res * 3 > desc->n_texels)
+            return fail(SG_ERR_INVALID_ARGUMENT, "environment map " + std::to_string(i) + ": image outside the texel pool");
+        for (const SgDistribution2D* D2 : {&E.distribution, &E.compensated}) {
+            const uint64_t nu = (uint64_t)D2->nu, nv = (uint64_t)D2->nv;
+            if (D2->nu < 1 || D2->nv < 1 || D2->func_off + nu * nv > desc->n_pool || D2->cdf_off + (nu + 1) * nv > desc->n_pool ||
+                D2->marg_func_off + nv > desc->n_pool || D2->marg_cdf_off + nv + 1 > desc->n_pool)
+                return fail(SG_ERR_INVALID_ARGUMENT, "environment map " + std::to_string(i) + ": sampling distribution outside spectrum_pool");
+        }
     }
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
-        if (m.kind < 0 || m.kind > SG_MATERIAL_THIN_DIELECTRIC) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.kind < 0 || m.kind > SG_MATERIAL_MIX) return fail(SG_ERR_UNSUPPORTED, "material kind " + std::to_string(m.kind) + " is not on the GPU path");
+        if (m.kind == SG_MATERIAL_MIX) continue;                 // validated below
+        if (m.kind == SG_MATERIAL_COATED_CONDUCTOR && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra || m.spec_c < 0 || m.spec_c >= (int32_t)desc->n_spectra ||
+                                                       m.max_depth < 0 || m.n_samples < 1 ||
+                                                       (!(m.flags & SG_MAT_CONDUCTOR_REFLECTANCE) && (m.spec_d < 0 || m.spec_d >= (int32_t)desc->n_spectra))))
+            return fail(SG_ERR_INVALID_ARGUMENT, "coated conductor material parameters out of range");
         if (m.kind == SG_MATERIAL_COATED_DIFFUSE && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra || m.spec_c < 0 || m.spec_c >= (int32_t)desc->n_spectra ||
                                                      m.max_depth < 0 || m.n_samples < 1))
             return fail(SG_ERR_INVALID_ARGUMENT, "coated diffuse material parameters out of range");
         if (m.spec_a < 0 || m.spec_a >= (int32_t)desc->n_spectra || (m.kind == SG_MATERIAL_CONDUCTOR && (m.spec_b < 0 || m.spec_b >= (int32_t)desc->n_spectra)))
             return fail(SG_ERR_INVALID_ARGUMENT, "material spectrum id out of range");
     }
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {                 // Mix: valid children, no cycles, resolves within 64 steps
+        const SgMaterial& m = desc->materials[i];
+        if (m.kind != SG_MATERIAL_MIX) continue;
+        for (int c = 0; c < 2; ++c) {
+            int32_t cur = m.mix_materials[c]; int steps = 0;
+            for (;;) {
+                if (cur < 0 || cur >= (int32_t)desc->n_materials) return fail(SG_ERR_INVALID_ARGUMENT, "mix material " + std::to_string(i) + " references an out-of-range material");
+                if (desc->materials[cur].kind != SG_MATERIAL_MIX) break;
+                if (++steps > 32) return fail(SG_ERR_INVALID_ARGUMENT, "mix material " + std::to_string(i) + ": nesting deeper than 32 (or cyclic)");
+                cur = desc->materials[cur].mix_materials[0];     // left spine; the right spines are checked from their own rows
+            }
+        }
+        if (m.tex_mix_amount >= (int32_t)desc->n_textures || (m.tex_mix_amount >= 0 && desc->textures[m.tex_mix_amount].n_channels != 1))
+            return fail(SG_ERR_INVALID_ARGUMENT, "mix material " + std::to_string(i) + ": `amount` texture must be a one-channel image");
+    }
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
+        if (m.kind == SG_MATERIAL_MIX) continue;
+        if (m.normal_map >= (int32_t)desc->n_textures || (m.normal_map >= 0 && desc->textures[m.normal_map].n_channels != 3))
+            return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + ": normal maps must be three-channel images");
         for (int32_t t : {m.tex_reflectance, m.tex_displacement})
             if (t >= (int32_t)desc->n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + " references an out-of-range texture");
         if (m.tex_reflectance >= 0 && m.kind != SG_MATERIAL_DIFFUSE && m.kind != SG_MATERIAL_COATED_DIFFUSE)
@@ -222,6 +260,9 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (t.wrap < SG_WRAP_REPEAT || t.wrap > SG_WRAP_CLAMP || t.filter < SG_FILTER_POINT || t.filter > SG_FILTER_EWA ||
             t.spectrum_type < SG_SPECTRUM_TYPE_ALBEDO || t.spectrum_type > SG_SPECTRUM_TYPE_UNBOUNDED)
             return fail(SG_ERR_UNSUPPORTED, "texture " + std::to_string(i) + ": wrap / filter / spectrum type not on the GPU path");
+        if (t.mapping >= (int32_t)desc->n_texture_mappings || (t.mapping >= 0 && (!desc->texture_mappings || desc->texture_mappings[t.mapping].kind < SG_MAPPING_SPHERICAL ||
+                                                                            desc->texture_mappings[t.mapping].kind > SG_MAPPING_PLANAR)))
+            return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": texture mapping out of range");
         if (t.filter == SG_FILTER_EWA && !desc->mip_filter_lut) return fail(SG_ERR_INVALID_ARGUMENT, "EWA filtering needs mip_filter_lut");
         for (int32_t l = 0; l < t.n_levels; ++l) {
             const SgImageLevel& L = desc->image_levels[t.first_level + l];
@@ -232,6 +273,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (last.res[0] != 1 || last.res[1] != 1) return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": the last MIP level must be 1x1 (image.rs:783)");
         need_rgb2spec |= t.n_channels == 3;
     }
+    need_rgb2spec |= desc->n_env_maps > 0;
     if (need_rgb2spec && (desc->rgb2spec_res < 2 || !desc->rgb2spec_scale || !desc->rgb2spec_data))
         return fail(SG_ERR_INVALID_ARGUMENT, "three-channel textures need the rgb2spec table of the scene colour space");
     auto check_bvh = [&](uint32_t node_base, uint32_t nn, uint32_t np) -> bool {          // offsets are relative to the BVH's own ranges
@@ -425,18 +467,23 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     UP(lights, desc->lights, desc->n_lights, SgLight);
     UP(textures, desc->textures, desc->n_textures, SgTexture);
     UP(image_levels, desc->image_levels, desc->n_textures ? desc->n_image_levels : 0, SgImageLevel);
-    UP(texels, desc->texels, desc->n_textures ? desc->n_texels : 0, float);
+    UP(texels, desc->texels, (desc->n_textures || desc->n_env_maps) ? desc->n_texels : 0, float);
+    UP(texture_mappings, desc->texture_mappings, desc->n_texture_mappings, SgTextureMapping);
+    UP(env_maps, desc->env_maps, desc->n_env_maps, SgEnvMap);
     UP(mip_lut, desc->mip_filter_lut, desc->mip_filter_lut ? 128 : 0, float);
     UP(rgb2spec_scale, desc->rgb2spec_scale, need_rgb2spec ? desc->rgb2spec_res : 0, float);
     UP(rgb2spec_data, desc->rgb2spec_data, need_rgb2spec ? (size_t)9 * desc->rgb2spec_res * desc->rgb2spec_res * desc->rgb2spec_res : 0, float);
 #undef UP
+    for (uint32_t i = 0; i < desc->n_materials; ++i) if (desc->materials[i].kind == SG_MATERIAL_MIX) s->has_mix = true;
+    if (s->has_mix)                                         // any material may come out of a mix: launch every kind that exists in the table
+        for (uint32_t i = 0; i < desc->n_materials; ++i) if (desc->materials[i].kind != SG_MATERIAL_MIX) s->kinds_present[desc->materials[i].kind] = true;
     d.n_textures = desc->n_textures; d.rgb2spec_res = need_rgb2spec ? desc->rgb2spec_res : 0;
     s->tex_path = desc->n_textures > 0;
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if ((desc->materials[i].flags & SG_MAT_HAS_DISPLACEMENT) && desc->materials[i].displacement != 0.0f) s->tex_path = true;
     d.n_nodes = desc->n_nodes; d.n_prims = desc->n_primitives; d.n_lights = desc->n_lights; d.n_materials = desc->n_materials;
     d.n_infinite = 0;
-    for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_UNIFORM_INFINITE) {
+    for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_UNIFORM_INFINITE || desc->lights[i].kind == SG_LIGHT_IMAGE_INFINITE) {
         if (d.n_infinite >= 4) { g_err = "more than 4 infinite lights"; return bail(SG_ERR_UNSUPPORTED); }
         d.infinite_ids[d.n_infinite++] = (int32_t)i;
     }
@@ -504,6 +551,9 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.full_res_x = s->d.film.full_resolution[0];
     k.n_samples = rp->sample_end - rp->sample_begin;
     { const char* v = std::getenv("SG_PATH_ORDER"); k.path_order = v ? std::atoi(v) : 1; }
+    if (rp->integrator < SG_INTEGRATOR_PATH || rp->integrator > SG_INTEGRATOR_RANDOM_WALK) return fail(SG_ERR_INVALID_ARGUMENT, "unknown integrator kind");
+    k.integrator = rp->integrator; k.integrator_flags = rp->integrator_flags;
+    const bool path_integrator = rp->integrator == SG_INTEGRATOR_PATH;
     if (k.n_samples == 0) k.n_samples = 1;
     const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
     const int n_depths = rp->max_depth + 1;
@@ -527,12 +577,18 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
-            if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, depth); ++launches; }
+            if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            if (s->has_mix) {
+                if (s->tex_path) k_resolve_mix<true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
+                else k_resolve_mix<false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
+                ++launches;
+            }
 #define SHADE(KIND) if (s->kinds_present[KIND]) { \
-                if (s->tex_path) k_shade<KIND, true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
+                if (!path_integrator) k_shade<KIND, true, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
+                else if (s->tex_path) k_shade<KIND, true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
                 else k_shade<KIND, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
                 ++launches; }
-            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE) SHADE(SG_MATERIAL_THIN_DIELECTRIC)
+            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE) SHADE(SG_MATERIAL_THIN_DIELECTRIC) SHADE(SG_MATERIAL_COATED_CONDUCTOR)
 #undef SHADE
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
@@ -706,23 +762,27 @@ int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_
     return SG_OK;
 }
 
-int sg_texture_eval(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out) {
+int sg_texture_eval_p(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda, float* out) {
     if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
     if (!s || n < 0 || (n > 0 && (!q || !lambda || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (tex < 0 || (uint32_t)tex >= s->d.n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture id out of range");
     if (n == 0) return SG_OK;
-    float *d_q = nullptr, *d_l = nullptr, *d_o = nullptr;
-    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_l); cudaFree(d_o); };
+    float *d_q = nullptr, *d_l = nullptr, *d_o = nullptr, *d_p = nullptr;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_l); cudaFree(d_o); cudaFree(d_p); };
 #define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
     CUX(cudaMalloc((void**)&d_q, (size_t)n * 24)); CUX(cudaMalloc((void**)&d_l, (size_t)n * 16)); CUX(cudaMalloc((void**)&d_o, (size_t)n * 16));
     CUX(cudaMemcpy(d_q, q, (size_t)n * 24, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_l, lambda, (size_t)n * 16, cudaMemcpyHostToDevice));
-    k_texture_eval<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, tex, as_float, (long long)n, d_q, d_l, d_o);
+    if (pdp) { CUX(cudaMalloc((void**)&d_p, (size_t)n * 36)); CUX(cudaMemcpy(d_p, pdp, (size_t)n * 36, cudaMemcpyHostToDevice)); }
+    k_texture_eval<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, tex, as_float, (long long)n, d_q, d_p, d_l, d_o);
     CUX(cudaStreamSynchronize(g_stream));
     CUX(cudaMemcpy(out, d_o, (size_t)n * 16, cudaMemcpyDeviceToHost));
 #undef CUX
     cleanup();
     return SG_OK;
+}
+int sg_texture_eval(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out) {
+    return sg_texture_eval_p(s, tex, as_float, n, q, nullptr, lambda, out);
 }
 
 int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_rgb) {

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 6
+SG_ABI_VERSION = 7
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -21,8 +21,12 @@ SG_CAMERA_PERSPECTIVE, SG_CAMERA_ORTHOGRAPHIC = 0, 1
 SG_MESH_REVERSE_ORIENTATION, SG_MESH_SWAPS_HANDEDNESS = 8, 16
 SG_SPECTRUM_CONSTANT, SG_SPECTRUM_DENSE, SG_SPECTRUM_PIECEWISE_LINEAR, SG_SPECTRUM_BLACKBODY = 0, 1, 2, 3
 SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_COATED_DIFFUSE, SG_MATERIAL_THIN_DIELECTRIC = 0, 1, 2, 3, 4
-SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT = 1, 2
-SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE, SG_LIGHT_DIFFUSE_AREA_SPHERE = 0, 1, 2, 3
+SG_MATERIAL_COATED_CONDUCTOR, SG_MATERIAL_MIX = 5, 6
+SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT, SG_MAT_CONDUCTOR_REFLECTANCE = 1, 2, 4
+SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE, SG_LIGHT_DIFFUSE_AREA_SPHERE, SG_LIGHT_IMAGE_INFINITE = 0, 1, 2, 3, 4
+SG_MAPPING_SPHERICAL, SG_MAPPING_CYLINDRICAL, SG_MAPPING_PLANAR = 1, 2, 3
+SG_INTEGRATOR_PATH, SG_INTEGRATOR_SIMPLE_PATH, SG_INTEGRATOR_RANDOM_WALK = 0, 1, 2
+SG_SIMPLEPATH_SAMPLE_LIGHTS, SG_SIMPLEPATH_SAMPLE_BSDF = 1, 2
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
 SG_OPT_DISABLE_TEXTURE_FILTERING, SG_OPT_FORCE_DIFFUSE = 4, 8
 SG_RENDER_COUNT_VISITS, SG_RENDER_TIME_KERNELS, SG_RENDER_OVERWRITE_FILM = 1, 2, 4
@@ -65,7 +69,9 @@ class SgMaterial(C.Structure):
     _fields_ = [("kind", C.c_int32), ("spec_a", C.c_int32), ("spec_b", C.c_int32), ("flags", C.c_int32),
                 ("u_roughness", C.c_float), ("v_roughness", C.c_float), ("displacement", C.c_float), ("spec_c", C.c_int32),
                 ("thickness", C.c_float), ("g", C.c_float), ("max_depth", C.c_int32), ("n_samples", C.c_int32),
-                ("tex_reflectance", C.c_int32), ("tex_displacement", C.c_int32), ("pad2", C.c_int32 * 2)]
+                ("tex_reflectance", C.c_int32), ("tex_displacement", C.c_int32), ("pad2", C.c_int32 * 2),
+                ("spec_d", C.c_int32), ("u_roughness2", C.c_float), ("v_roughness2", C.c_float), ("normal_map", C.c_int32),
+                ("mix_materials", C.c_int32 * 2), ("mix_amount", C.c_float), ("tex_mix_amount", C.c_int32)]
 
 
 class SgImageLevel(C.Structure):
@@ -76,7 +82,22 @@ class SgTexture(C.Structure):
     _fields_ = [("n_channels", C.c_int32), ("n_levels", C.c_int32), ("first_level", C.c_uint32), ("wrap", C.c_int32),
                 ("filter", C.c_int32), ("max_anisotropy", C.c_float), ("scale", C.c_float), ("invert", C.c_int32),
                 ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float),
-                ("spectrum_type", C.c_int32), ("pad", C.c_int32 * 3)]
+                ("spectrum_type", C.c_int32), ("mapping", C.c_int32), ("pad", C.c_int32 * 2)]
+
+
+class SgTextureMapping(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("texture_from_render", C.c_float * 16), ("vs", C.c_float * 3), ("vt", C.c_float * 3),
+                ("ds", C.c_float), ("dt", C.c_float), ("pad", C.c_int32 * 3)]
+
+
+class SgDistribution2D(C.Structure):
+    _fields_ = [("nu", C.c_int32), ("nv", C.c_int32), ("func_off", C.c_uint32), ("cdf_off", C.c_uint32),
+                ("marg_func_off", C.c_uint32), ("marg_cdf_off", C.c_uint32), ("marg_integral", C.c_float), ("pad", C.c_uint32)]
+
+
+class SgEnvMap(C.Structure):
+    _fields_ = [("render_from_light", C.c_float * 16), ("light_from_render", C.c_float * 16), ("texel_offset", C.c_uint64),
+                ("res", C.c_int32), ("pad", C.c_int32), ("distribution", SgDistribution2D), ("compensated", SgDistribution2D)]
 
 
 SG_WRAP_REPEAT, SG_WRAP_BLACK, SG_WRAP_CLAMP = 0, 1, 2
@@ -134,13 +155,16 @@ class SgSceneDesc(C.Structure):
                 ("n_texels", C.c_uint64), ("texels", C.POINTER(C.c_float)),
                 ("mip_filter_lut", C.POINTER(C.c_float)),
                 ("rgb2spec_res", C.c_uint32), ("rgb2spec_scale", C.POINTER(C.c_float)), ("rgb2spec_data", C.POINTER(C.c_float)),
+                ("n_texture_mappings", C.c_uint32), ("texture_mappings", C.POINTER(SgTextureMapping)),
+                ("n_env_maps", C.c_uint32), ("env_maps", C.POINTER(SgEnvMap)),
                 ("camera", SgCamera), ("film", SgFilm)]
 
 
 class SgRenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("samples_per_pixel", C.c_int32), ("sample_begin", C.c_int32),
                 ("sample_end", C.c_int32), ("max_depth", C.c_int32), ("regularize", C.c_int32),
-                ("option_flags", C.c_uint32), ("max_paths_in_flight", C.c_int32), ("flags", C.c_int32)]
+                ("option_flags", C.c_uint32), ("max_paths_in_flight", C.c_int32), ("flags", C.c_int32),
+                ("integrator", C.c_int32), ("integrator_flags", C.c_int32)]
 
 
 class SgFilmPixel(C.Structure):
@@ -166,7 +190,7 @@ class SgHit(C.Structure):
 # every symbol include/shimmer_gpu.h declares; tests/test_abi.py checks the library exports all
 ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
                "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
-               "sg_film_develop", "sg_texture_eval", "sg_film_get_image"]
+               "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_film_get_image"]
 
 
 class ShimmerGpuError(RuntimeError):
@@ -207,6 +231,7 @@ def load_library():
     lib.sg_film_develop.argtypes = [vp, vp, i64, vp]; lib.sg_film_develop.restype = C.c_int
     lib.sg_film_get_image.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, vp]; lib.sg_film_get_image.restype = C.c_int
     lib.sg_texture_eval.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp]; lib.sg_texture_eval.restype = C.c_int
+    lib.sg_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp, vp]; lib.sg_texture_eval_p.restype = C.c_int
     _lib = lib
     return lib
 

@@ -207,6 +207,46 @@ def srgb_output_matrix():
     return np.linalg.inv(xyz_from_rgb).astype(np.float32)
 
 
+def _equal_area_square_to_sphere(px, py):
+    """math.rs:453-484 as written (`vp - up / r + 1.0`), f32; host-side use only (the `illuminance` scale, light.rs:190-207)."""
+    u, v = f32(2.0) * f32(px) - f32(1.0), f32(2.0) * f32(py) - f32(1.0)
+    up, vp = abs(u), abs(v)
+    sd = f32(1.0) - (up + vp)
+    r = f32(1.0) - abs(sd)
+    phi = (f32(1.0) if r == 0.0 else f32(f32(vp - f32(up / r)) + f32(1.0))) * f32(np.pi) / f32(4.0)
+    z = f32(math.copysign(f32(1.0) - r * r, sd))
+    c, s_ = f32(math.copysign(np.cos(phi, dtype=np.float32), u)), f32(math.copysign(np.sin(phi, dtype=np.float32), v))
+    k = f32(np.sqrt(max(f32(0.0), f32(2.0) - r * r), dtype=np.float32))
+    return np.array([c * r * k, s_ * r * k, z], np.float32)
+
+
+def piecewise_constant_1d(f, lo=0.0, hi=1.0):
+    """PiecewiseConstant1D::new_bounded (sampling.rs:27-65), f32 running sums in the reference's order -> (func, cdf, func_int)."""
+    func = np.abs(np.asarray(f, dtype=np.float32))
+    n = len(func)
+    step = f32(hi) - f32(lo)
+    terms = (func * step / f32(n)).astype(np.float32)          # func[i-1] * (max - min) / n
+    cdf = np.zeros(n + 1, np.float32)
+    cdf[1:] = np.cumsum(terms, dtype=np.float32)               # sequential f32 adds (numpy's cumsum is a running sum)
+    func_int = f32(cdf[n])
+    if func_int == 0.0:
+        cdf[1:] = (np.arange(1, n + 1, dtype=np.float32) / f32(n)).astype(np.float32)
+    else:
+        cdf[1:] = (cdf[1:] / func_int).astype(np.float32)
+    return func, cdf, func_int
+
+
+def piecewise_constant_2d(func2d):
+    """PiecewiseConstant2D::new over [0,1]^2 (sampling.rs:120-151) -> (func[nv,nu], cdf[nv,nu+1], marg_func[nv], marg_cdf[nv+1], marg_int)."""
+    func2d = np.asarray(func2d, dtype=np.float32)
+    nv, nu = func2d.shape
+    fn = np.empty((nv, nu), np.float32); cdf = np.empty((nv, nu + 1), np.float32); ints = np.empty(nv, np.float32)
+    for v in range(nv):
+        fn[v], cdf[v], ints[v] = piecewise_constant_1d(func2d[v])
+    mf, mcdf, mint = piecewise_constant_1d(ints)
+    return fn, cdf, mf, mcdf, mint
+
+
 # ----------------------------------------------------------------------------------------------
 # Scene builder
 # ----------------------------------------------------------------------------------------------
@@ -239,6 +279,8 @@ class SceneBuilder:
         self.instances = []      # (object id, render_from_instance Transform)
         self.spheres = []        # dicts: Sphere::new fields + material (top-level shapes, after the meshes)
         self.patch_meshes = []   # dicts: BilinearPatchMesh (4 vertex indices per patch); top-level shapes, after the triangle meshes
+        self.env_maps = []       # dicts: ImageInfinitelight images + render_from_light (light.rs:805-981)
+        self.mappings = []       # SgTextureMapping rows (spherical / cylindrical / planar, texture.rs:938-1035)
         self.fix_instancing = False
         self.camera = None
         self.film = None
@@ -254,7 +296,7 @@ class SceneBuilder:
         return len(self.spectra) - 1
 
     def image_texture(self, image, filter="bilinear", wrap="repeat", max_anisotropy=8.0, scale=1.0, invert=False,
-                      su=1.0, sv=1.0, du=0.0, dv=0.0, spectrum_type="albedo"):
+                      su=1.0, sv=1.0, du=0.0, dv=0.0, spectrum_type="albedo", mapping=None):
         """ImageTextureBase::new (texture.rs:283-330) + MIPMap::new -> Image::generate_pyramid (image.rs:699-787).
         `image`: H x W (one channel) or H x W x 3 array of LINEAR values, row 0 = top of the image (what
         Image::get_channel returns after colour decoding).  Power-of-two sizes only: the reference first
@@ -277,8 +319,19 @@ class SceneBuilder:
                                   filter={"point": 0, "bilinear": 1, "trilinear": 2, "ewa": 3, "EWA": 3}[filter],
                                   wrap={"repeat": 0, "black": 1, "clamp": 2}[wrap], max_anisotropy=max_anisotropy, scale=scale,
                                   invert=1 if invert else 0, su=su, sv=sv, du=du, dv=dv,
-                                  spectrum_type={"albedo": 0, "unbounded": 1}[spectrum_type]))
+                                  spectrum_type={"albedo": 0, "unbounded": 1}[spectrum_type],
+                                  mapping=-1 if mapping is None else mapping))
         return len(self.textures) - 1
+
+    def texture_mapping(self, kind, texture_from_world=None, v1=(1.0, 0.0, 0.0), v2=(0.0, 1.0, 0.0), udelta=0.0, vdelta=0.0):
+        """TextureMapping2D::create (texture.rs:853-893) for "spherical" / "cylindrical" / "planar":
+        texture_from_render = (render_from_texture)^-1 with render_from_texture = render_from_world * CTM; the planar
+        mapping keeps `v1`, `v2`, `udelta`, `vdelta`.  `texture_from_world` is the INVERSE CTM (a Transform) or None."""
+        tfw = texture_from_world if texture_from_world is not None else Transform.identity()
+        tfr = tfw * self.render_from_world.inverse()
+        self.mappings.append(dict(kind={"spherical": ffi.SG_MAPPING_SPHERICAL, "cylindrical": ffi.SG_MAPPING_CYLINDRICAL,
+                                        "planar": ffi.SG_MAPPING_PLANAR}[kind], tfr=tfr, vs=v1, vt=v2, ds=udelta, dt=vdelta))
+        return len(self.mappings) - 1
 
     def diffuse(self, reflectance, reflectance_tex=None, displacement_tex=None):
         """DiffuseMaterial::create (material.rs:259-283): displacement is ALWAYS Some(0.0) unless a texture is given.
@@ -289,16 +342,42 @@ class SceneBuilder:
                                    tex_displacement=-1 if displacement_tex is None else displacement_tex))
         return len(self.materials) - 1
 
-    def conductor(self, eta, k, roughness=0.0, remap=True):
-        """ConductorMaterial::create (material.rs:362-431), eta/k form."""
+    def conductor(self, eta, k, roughness=0.0, remap=True, normal_map=None):
+        """ConductorMaterial::create (material.rs:362-431), eta/k form.  `normal_map`: three-channel image_texture() id."""
         self.materials.append(dict(kind=ffi.SG_MATERIAL_CONDUCTOR, spec_a=self.spectrum(eta), spec_b=self.spectrum(k),
-                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
+                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness,
+                                   normal_map=-1 if normal_map is None else normal_map))
         return len(self.materials) - 1
 
-    def dielectric(self, eta, roughness=0.0, remap=True):
+    def dielectric(self, eta, roughness=0.0, remap=True, normal_map=None):
         """DielectricMaterial::create (material.rs:538-581)."""
         self.materials.append(dict(kind=ffi.SG_MATERIAL_DIELECTRIC, spec_a=self.spectrum(eta), spec_b=-1,
-                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness))
+                                   flags=(ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0), ur=roughness, vr=roughness,
+                                   normal_map=-1 if normal_map is None else normal_map))
+        return len(self.materials) - 1
+
+    def coated_conductor(self, conductor_eta=None, conductor_k=None, reflectance=None, interface_eta=("const", 1.5), interface_roughness=0.0,
+                         conductor_roughness=0.0, thickness=0.01, albedo=("const", 0.0), g=0.0, max_depth=10, n_samples=1, remap=True,
+                         normal_map=None):
+        """CoatedConductorMaterial::create (material.rs:1030-1180): conductor given by eta + k spectra (defaults metal-Cu) or
+        by `reflectance`."""
+        if reflectance is None and conductor_eta is None:
+            conductor_eta, conductor_k = named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k")
+        fl = (ffi.SG_MAT_REMAP_ROUGHNESS if remap else 0) | (ffi.SG_MAT_CONDUCTOR_REFLECTANCE if reflectance is not None else 0)
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_COATED_CONDUCTOR,
+                                   spec_a=self.spectrum(reflectance if reflectance is not None else conductor_eta),
+                                   spec_d=-1 if reflectance is not None else self.spectrum(conductor_k),
+                                   spec_b=self.spectrum(albedo), spec_c=self.spectrum(interface_eta), flags=fl,
+                                   ur=interface_roughness, vr=interface_roughness, ur2=conductor_roughness, vr2=conductor_roughness,
+                                   thickness=thickness, g=g, max_depth=max_depth, n_samples=n_samples,
+                                   normal_map=-1 if normal_map is None else normal_map))
+        return len(self.materials) - 1
+
+    def mix(self, material_a, material_b, amount=0.5, amount_tex=None):
+        """MixMaterial::create (material.rs:1296-1307): `amount` float (0.5) or a one-channel image texture."""
+        self.materials.append(dict(kind=ffi.SG_MATERIAL_MIX, spec_a=-1, spec_b=-1, flags=0, ur=0.0, vr=0.0,
+                                   mix_materials=(material_a, material_b), mix_amount=amount,
+                                   tex_mix_amount=-1 if amount_tex is None else amount_tex))
         return len(self.materials) - 1
 
     def thin_dielectric(self, eta):
@@ -502,6 +581,45 @@ class SceneBuilder:
         self.extra_lights.append(dict(kind=ffi.SG_LIGHT_UNIFORM_INFINITE, spectrum=self.spectrum(("dense", spectrum_dense(L))),
                                       scale=float(sc), pos=np.zeros(3, np.float32)))
 
+    def add_image_infinite_light(self, image, scale=1.0, illuminance=None, light_from_world=None):
+        """Light::create "infinite" with a `filename` (light.rs:164-232) + ImageInfinitelight::new (:916-964).  `image`: square
+        N x N x 3 array of LINEAR sRGB values in the equal-area octahedral parameterisation (what Image::read + select_channels
+        hands over).  `light_from_world` is the CTM (render_from_light = render_from_world * CTM)."""
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        if img.ndim != 3 or img.shape[2] != 3 or img.shape[0] != img.shape[1]:
+            raise ValueError("environment maps must be square RGB images (light.rs:934-937)")
+        N = img.shape[0]
+        ill = named_spectrum("stdillum-D65")                   # the sRGB colour space's illuminant (colorspace.rs:134-141)
+        sc = f32(scale) / spectrum_to_photometric(ill)
+        if illuminance is not None and illuminance > 0.0:      # light.rs:181-211
+            lum = np.array([0.2126, 0.7152, 0.0722], np.float32)   # luminance_vector of sRGB (approximate: host-side constant)
+            acc = f32(0.0)
+            for y in range(N):
+                v = (f32(y) + f32(0.5)) / f32(N)
+                for x in range(N):
+                    u = (f32(x) + f32(0.5)) / f32(N)
+                    w = _equal_area_square_to_sphere(u, v)
+                    if w[2] <= 0.0:
+                        continue
+                    for c in range(3):
+                        acc = f32(acc + f32(f32(img[y, x, c] * lum[c]) * f32(w[2])))
+            acc = f32(acc * f32(f32(2.0 * np.float32(np.pi)) / f32(N * N)))
+            sc = f32(sc * f32(f32(illuminance) / acc))
+        ctm = light_from_world if light_from_world is not None else Transform.identity()
+        rfl = self.render_from_world * ctm
+        # Image::get_default_sampling_distribution (image.rs:1379-1405): channel average per pixel
+        d = ((img[:, :, 0] + img[:, :, 1]) + img[:, :, 2]) / f32(3.0)
+        avg = f32(0.0)
+        for v in d.ravel():                                    # Iterator::sum::<f32>() (light.rs:942)
+            avg = f32(avg + v)
+        avg = f32(avg / f32(d.size))
+        comp = np.maximum(d - avg, f32(0.0)).astype(np.float32)
+        if not comp.any():
+            comp[:] = 1.0
+        self.env_maps.append(dict(image=img, rfl=rfl, dist=d.astype(np.float32), comp=comp))
+        self.extra_lights.append(dict(kind=ffi.SG_LIGHT_IMAGE_INFINITE, spectrum=self.spectrum(("dense", spectrum_dense(ill))),
+                                      scale=float(sc), pos=np.zeros(3, np.float32), tri=len(self.env_maps) - 1))
+
     # -- flatten ---------------------------------------------------------------------------------
     def build(self):
         out = SceneDesc()
@@ -537,6 +655,7 @@ class SceneBuilder:
         for el in self.extra_lights:
             L = ffi.SgLight(); L.kind = el["kind"]; L.spectrum = el["spectrum"]; L.scale = el["scale"]
             L.pos[:] = [float(x) for x in el["pos"]]
+            L.tri = el.get("tri", 0)
             lights.append(L)
         mesh_light_base = {}
         for mi, m in enumerate(self.meshes):
@@ -708,8 +827,23 @@ class SceneBuilder:
         inside = bool(np.all(center >= bmin) and np.all(center <= bmax))
         radius = float(np.sqrt(np.sum((center - bmax).astype(np.float32) ** 2, dtype=np.float32))) if inside else 0.0
         for L in lights:
-            if L.kind == ffi.SG_LIGHT_UNIFORM_INFINITE:
+            if L.kind in (ffi.SG_LIGHT_UNIFORM_INFINITE, ffi.SG_LIGHT_IMAGE_INFINITE):
                 L.scene_center[:] = center.tolist(); L.scene_radius = radius
+        env_rows = (ffi.SgEnvMap * max(len(self.env_maps), 1))()
+        for ei, em in enumerate(self.env_maps):
+            E = env_rows[ei]
+            E.render_from_light[:] = em["rfl"].m32().ravel().tolist(); E.light_from_render[:] = em["rfl"].m_inv.astype(np.float32).ravel().tolist()
+            E.res = em["image"].shape[0]
+            for name, func2d in (("distribution", em["dist"]), ("compensated", em["comp"])):
+                fn, cdf, mf, mcdf, mint = piecewise_constant_2d(func2d)
+                D2 = getattr(E, name)
+                D2.nu, D2.nv = func2d.shape[1], func2d.shape[0]
+                D2.func_off = off; pool.append(fn.ravel()); off += fn.size
+                D2.cdf_off = off; pool.append(cdf.ravel()); off += cdf.size
+                D2.marg_func_off = off; pool.append(mf); off += mf.size
+                D2.marg_cdf_off = off; pool.append(mcdf); off += mcdf.size
+                D2.marg_integral = float(mint)
+        A["env_maps"] = env_rows
         A["pool"] = np.concatenate(pool).astype(np.float32) if pool else np.zeros(1, np.float32)
         A["spectra"] = (ffi.SgSpectrum * len(recs))(*recs)
         mats = (ffi.SgMaterial * max(len(self.materials), 1))()
@@ -719,6 +853,10 @@ class SceneBuilder:
             mats[i].spec_c = m.get("spec_c", -1); mats[i].thickness = m.get("thickness", 0.0); mats[i].g = m.get("g", 0.0)
             mats[i].max_depth = m.get("max_depth", 0); mats[i].n_samples = m.get("n_samples", 0)
             mats[i].tex_reflectance = m.get("tex_reflectance", -1); mats[i].tex_displacement = m.get("tex_displacement", -1)
+            mats[i].spec_d = m.get("spec_d", -1); mats[i].u_roughness2 = m.get("ur2", 0.0); mats[i].v_roughness2 = m.get("vr2", 0.0)
+            mats[i].normal_map = m.get("normal_map", -1)
+            mm = m.get("mix_materials", (-1, -1)); mats[i].mix_materials[0], mats[i].mix_materials[1] = mm
+            mats[i].mix_amount = m.get("mix_amount", 0.0); mats[i].tex_mix_amount = m.get("tex_mix_amount", -1)
         A["materials"] = mats
         A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
         A["meshes"] = mesh_rows
@@ -730,14 +868,26 @@ class SceneBuilder:
             r.n_channels, r.n_levels, r.first_level = t["n_channels"], len(t["levels"]), len(level_rows)
             r.wrap, r.filter, r.max_anisotropy, r.scale, r.invert = t["wrap"], t["filter"], t["max_anisotropy"], t["scale"], t["invert"]
             r.su, r.sv, r.du, r.dv, r.spectrum_type = t["su"], t["sv"], t["du"], t["dv"], t["spectrum_type"]
+            r.mapping = t.get("mapping", -1)
             for lv in t["levels"]:
                 L = ffi.SgImageLevel(); L.offset = toff; L.res[:] = [lv.shape[1], lv.shape[0]]
                 level_rows.append(L); texel_chunks.append(np.ascontiguousarray(lv, np.float32).ravel()); toff += lv.size
         A["textures"] = tex_rows
+        map_rows = (ffi.SgTextureMapping * max(len(self.mappings), 1))()
+        for mi_, mp in enumerate(self.mappings):
+            r = map_rows[mi_]
+            r.kind = mp["kind"]; r.texture_from_render[:] = mp["tfr"].m32().ravel().tolist()
+            r.vs[:] = [float(x) for x in mp["vs"]]; r.vt[:] = [float(x) for x in mp["vt"]]; r.ds, r.dt = mp["ds"], mp["dt"]
+        A["texture_mappings"] = map_rows
+        for em in self.env_maps:                               # environment maps live in the texel pool after the MIP levels
+            em["texel_offset"] = toff
+            texel_chunks.append(em["image"].ravel()); toff += em["image"].size
+        for ei, em in enumerate(self.env_maps):
+            A["env_maps"][ei].texel_offset = em["texel_offset"]
         A["image_levels"] = (ffi.SgImageLevel * max(len(level_rows), 1))(*level_rows)
         A["texels"] = np.concatenate(texel_chunks) if texel_chunks else np.zeros(1, np.float32)
         A["mip_lut"] = np.ascontiguousarray(tables()["MIP_FILTER_LUT"], np.float32)
-        need_rgb = any(t["n_channels"] == 3 for t in self.textures)
+        need_rgb = any(t["n_channels"] == 3 for t in self.textures) or len(self.env_maps) > 0
         if need_rgb:
             from . import rgb2spec
             sc_, dt_ = rgb2spec.build_table(16)
@@ -768,6 +918,8 @@ class SceneBuilder:
         if need_rgb:
             d.rgb2spec_res = len(A["rgb2spec_scale"]); d.rgb2spec_scale = _as_ptr(A["rgb2spec_scale"], C.c_float)
             d.rgb2spec_data = _as_ptr(A["rgb2spec_data"], C.c_float)
+        d.n_texture_mappings = len(self.mappings); d.texture_mappings = A["texture_mappings"]
+        d.n_env_maps = len(self.env_maps); d.env_maps = A["env_maps"]
         d.camera = self.camera
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids
         d.film = self.film

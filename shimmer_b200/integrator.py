@@ -64,7 +64,9 @@ class WavefrontPathIntegrator(Integrator):
     """GPU replacement of `ImageTileIntegrator` + `PathIntegrator` (integrator.rs:119-321,730-963).
 
     parameters: the integrator's ParameterDictionary -- `maxdepth` (5), `regularize` (false),
-    `lightsampler` ("uniform"; anything else raises, light_sampler.rs:30-33).
+    `lightsampler` ("uniform"; anything else raises, light_sampler.rs:30-33); `integrator` picks the
+    RayPathLiEvaluator (integrator.rs:398-403): "path" (default), "simplepath" (+ `samplelights`, `samplebsdf`, both
+    true by default, integrator.rs:131-141) or "randomwalk".
     sampler: dict with `pixelsamples` (4) and `seed` (sampler.rs:95-99)."""
 
     def __init__(self, scene, parameters=None, sampler=None, device=0, max_paths_in_flight=0):
@@ -75,6 +77,13 @@ class WavefrontPathIntegrator(Integrator):
         ls = parameters.get("lightsampler", "uniform")
         if ls != "uniform":
             raise ffi.ShimmerGpuError(f"Unknown light sampler: {ls}")
+        li = parameters.get("integrator", "path")
+        kinds = {"path": ffi.SG_INTEGRATOR_PATH, "simplepath": ffi.SG_INTEGRATOR_SIMPLE_PATH, "randomwalk": ffi.SG_INTEGRATOR_RANDOM_WALK}
+        if li not in kinds:
+            raise ffi.ShimmerGpuError(f"Unknown integrator {li}")
+        self.integrator = kinds[li]
+        self.integrator_flags = (ffi.SG_SIMPLEPATH_SAMPLE_LIGHTS if parameters.get("samplelights", True) else 0) | \
+                                (ffi.SG_SIMPLEPATH_SAMPLE_BSDF if parameters.get("samplebsdf", True) else 0)
         self.samples_per_pixel = int(sampler.get("pixelsamples", 4))
         self.sampler_seed = sampler.get("seed", None)
         self.scene = scene
@@ -99,6 +108,7 @@ class WavefrontPathIntegrator(Integrator):
         p.sample_begin, p.sample_end = sample_range if sample_range else (0, spp)
         p.max_depth = self.max_depth; p.regularize = int(self.regularize)
         p.option_flags = options.flags(); p.max_paths_in_flight = self.max_paths_in_flight; p.flags = flags
+        p.integrator = self.integrator; p.integrator_flags = self.integrator_flags
         return p
 
     # -- Integrator::render ------------------------------------------------------------------
@@ -142,6 +152,20 @@ class WavefrontPathIntegrator(Integrator):
         out = np.zeros((n, 4), np.float32)
         ffi.check(self._lib.sg_texture_eval(self._handle, int(tex), 1 if as_float else 0, n, q.ctypes.data, lam.ctypes.data,
                                             out.ctypes.data), "sg_texture_eval")
+        return out
+
+    def texture_eval_p(self, tex, p, q=None, dpdx=None, dpdy=None, lambda4=None, as_float=False):
+        """Texture lookups with the full TextureEvalContext (p, dpdx, dpdy in render space): the non-UV mappings
+        (texture.rs:938-1035)."""
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3); n = len(p)
+        q = np.ascontiguousarray(np.zeros((n, 6)) if q is None else q, np.float32).reshape(-1, 6)
+        z = np.zeros((n, 3), np.float32)
+        pdp = np.ascontiguousarray(np.concatenate([p, z if dpdx is None else np.asarray(dpdx, np.float32).reshape(-1, 3),
+                                                   z if dpdy is None else np.asarray(dpdy, np.float32).reshape(-1, 3)], axis=1), np.float32)
+        lam = np.ascontiguousarray(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4, np.float32).reshape(-1, 4)
+        out = np.zeros((n, 4), np.float32)
+        ffi.check(self._lib.sg_texture_eval_p(self._handle, int(tex), 1 if as_float else 0, n, q.ctypes.data, pdp.ctypes.data,
+                                              lam.ctypes.data, out.ctypes.data), "sg_texture_eval_p")
         return out
 
     def develop(self, film=None):

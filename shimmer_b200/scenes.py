@@ -410,6 +410,89 @@ def instanced_tiny_scene(kind="inst", resolution=(32, 32), flatten=False):
     return b
 
 
+VARIETY_KINDS = ("envmap", "envonly", "envrot", "coatedcond", "coatedcondrough", "coatedcondrefl", "normalmap", "texsph", "texcyl", "texplanar",
+                 "mix", "mixtex", "mixnested")
+
+
+def procedural_envmap(n=32):
+    """A square equal-area octahedral environment map (linear RGB): dim blue-grey sky, one bright warm blob and a dimmer
+    cool one, so that the compensated distribution (light.rs:941-948) is sparse."""
+    y, x = np.meshgrid((np.arange(n) + 0.5) / n, (np.arange(n) + 0.5) / n, indexing="ij")
+    img = np.empty((n, n, 3), np.float32)
+    base = 0.15 + 0.1 * np.sin(5.0 * x) * np.cos(3.0 * y)
+    img[:, :, 0] = base; img[:, :, 1] = base * 1.1; img[:, :, 2] = base * 1.4
+    b1 = np.exp(-((x - 0.62) ** 2 + (y - 0.40) ** 2) / 0.004); b2 = np.exp(-((x - 0.30) ** 2 + (y - 0.55) ** 2) / 0.01)
+    img[:, :, 0] += 14.0 * b1 + 1.0 * b2; img[:, :, 1] += 11.0 * b1 + 2.0 * b2; img[:, :, 2] += 6.0 * b1 + 4.0 * b2
+    return img.astype(np.float32)
+
+
+def procedural_normal_map(n=32):
+    """Tangent-space normal map (RGB = 0.5 + 0.5 n) of a bumpy surface."""
+    y, x = np.meshgrid((np.arange(n) + 0.5) / n, (np.arange(n) + 0.5) / n, indexing="ij")
+    nx = 0.35 * np.sin(2 * np.pi * 3 * x); ny = 0.35 * np.cos(2 * np.pi * 2 * y)
+    nz = np.sqrt(np.maximum(1.0 - nx * nx - ny * ny, 0.05))
+    return (0.5 + 0.5 * np.stack([nx, ny, nz], axis=2)).astype(np.float32)
+
+
+def variety_tiny_scene(kind, resolution=(32, 32)):
+    """SURVEY 8f next-4 scenes: image-infinite lights, CoatedConductor, normal maps, non-UV texture mappings, Mix."""
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
+    white = b.diffuse(_white())
+    guv = np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32)
+    ground = white
+    area_light = True
+    if kind in ("envmap", "envonly", "envrot"):
+        xf = Transform.rotate(35.0, (0.3, 1.0, 0.2)) if kind == "envrot" else None
+        b.add_image_infinite_light(procedural_envmap(32), scale=1.0 if kind != "envonly" else 2.0, light_from_world=xf,
+                                   illuminance=3.0 if kind == "envrot" else None)
+        mat = b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0) if kind == "envmap" else b.diffuse(_green())
+        if kind == "envrot":
+            mat = b.dielectric(("const", 1.5), roughness=0.1)
+        area_light = kind != "envonly"
+    elif kind == "coatedcond":
+        mat = b.coated_conductor()
+    elif kind == "coatedcondrough":
+        mat = b.coated_conductor(conductor_eta=named_spectrum("metal-Au-eta"), conductor_k=named_spectrum("metal-Au-k"), interface_roughness=0.2,
+                                 conductor_roughness=0.4, albedo=("const", 0.3), g=-0.2, thickness=0.03, interface_eta=named_spectrum("glass-BK7"))
+    elif kind == "coatedcondrefl":
+        mat = b.coated_conductor(reflectance=_red(), interface_roughness=0.05, remap=False, conductor_roughness=0.3)
+    elif kind == "normalmap":
+        nm = b.image_texture(procedural_normal_map(32))
+        mat = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.15, normal_map=nm)
+    elif kind in ("texsph", "texcyl", "texplanar"):
+        rgb_img = procedural_image(64, 3)
+        if kind == "texsph":
+            mp = b.texture_mapping("spherical", texture_from_world=Transform.translate((0.0, -0.6, 0.0)))
+        elif kind == "texcyl":
+            mp = b.texture_mapping("cylindrical", texture_from_world=Transform.rotate(90.0, (1, 0, 0)) * Transform.translate((0.0, -0.6, 0.0)))
+        else:
+            mp = b.texture_mapping("planar", v1=(0.7, 0.0, 0.2), v2=(0.0, 0.3, 0.9), udelta=0.1, vdelta=0.25)
+        mat = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="trilinear" if kind != "texplanar" else "ewa", mapping=mp))
+        ground = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(32, 1), filter="bilinear", mapping=mp))
+    elif kind == "mix":
+        mat = b.mix(b.diffuse(_green()), b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.05), amount=0.4)
+        ground = b.mix(white, b.diffuse(_red()), amount=0.7)
+    elif kind == "mixtex":
+        amt = b.image_texture(procedural_image(32, 1), filter="bilinear", su=2.0, sv=2.0)
+        mat = b.mix(b.diffuse(_green()), b.dielectric(("const", 1.5)), amount_tex=amt)
+        ground = b.mix(white, b.coated_diffuse(_red()), amount_tex=amt)
+    elif kind == "mixnested":
+        inner = b.mix(b.diffuse(_green()), b.diffuse(_red()), amount=0.5)
+        mat = b.mix(inner, b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0), amount=0.3)
+        ground = b.mix(white, white, amount=1.5)
+    else:
+        raise ValueError(kind)
+    P, I, Nn, UV = uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)
+    b.add_mesh(P, I, mat, n=Nn, uv=UV)
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, ground, uv=guv)
+    if area_light:
+        lp, li = _quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
+        b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b
+
+
 def tiny_scene(kind="diffuse", resolution=(32, 32)):
     """A few dozen triangles exercising one material each; used by the fast parity tests.  The `tex*` kinds add image
     textures (RGB + one-channel, every filter / wrap mode), bump mapping and specular ray-differential propagation."""
@@ -419,6 +502,8 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         return sphere_tiny_scene(kind, resolution)
     if kind in PATCH_KINDS:
         return patch_tiny_scene(kind, resolution)
+    if kind in VARIETY_KINDS:
+        return variety_tiny_scene(kind, resolution)
     if kind == "ortho":
         # OrthographicCamera (camera.rs:657-827) looking down +z with up = y: render_from_camera is the identity in the
         # camera-world rendering space, where the reference's camera-space ray (see SgCameraKind) is also the right one.

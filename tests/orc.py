@@ -56,10 +56,15 @@ def lib():
     L.orc_bounds_intersect.argtypes = [vp, vp, vp, vp, C.c_float]; L.orc_bounds_intersect.restype = C.c_int
     L.orc_light_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]; L.orc_light_sample.restype = C.c_int
     L.orc_light_pdf.argtypes = [vp, C.c_int, vp, vp, vp, vp]; L.orc_light_pdf.restype = C.c_float
+    L.orc_light_sample_complete.argtypes = [vp, C.c_int, vp, vp, vp, vp]; L.orc_light_sample_complete.restype = C.c_int
+    L.orc_light_pdf_complete.argtypes = [vp, C.c_int, vp]; L.orc_light_pdf_complete.restype = C.c_float
+    L.orc_light_le.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.orc_equal_area_square_to_sphere.argtypes = [vp, vp]; L.orc_equal_area_sphere_to_square.argtypes = [vp, vp]
     L.orc_rotate_from_to.argtypes = [vp, vp, vp]
     L.orc_sigmoid_poly_get.argtypes = [vp, C.c_float]; L.orc_sigmoid_poly_get.restype = C.c_float
     L.orc_rgb2spec_fetch.argtypes = [vp, vp, vp]
     L.orc_texture_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
+    L.orc_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp]
     L.orc_approximate_dp_dxy.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp]
     _lib = L
     return L
@@ -69,8 +74,11 @@ def fa(x):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
-def make_params(seed=0, spp=4, sample_range=None, max_depth=5, regularize=False, flags=0):
+def make_params(seed=0, spp=4, sample_range=None, max_depth=5, regularize=False, flags=0, integrator="path", sample_lights=True,
+                sample_bsdf=True):
     p = ffi.SgRenderParams()
+    p.integrator = {"path": ffi.SG_INTEGRATOR_PATH, "simplepath": ffi.SG_INTEGRATOR_SIMPLE_PATH, "randomwalk": ffi.SG_INTEGRATOR_RANDOM_WALK}[integrator]
+    p.integrator_flags = (ffi.SG_SIMPLEPATH_SAMPLE_LIGHTS if sample_lights else 0) | (ffi.SG_SIMPLEPATH_SAMPLE_BSDF if sample_bsdf else 0)
     p.seed = seed; p.samples_per_pixel = spp
     p.sample_begin, p.sample_end = sample_range if sample_range else (0, spp)
     p.max_depth = max_depth; p.regularize = int(regularize); p.option_flags = flags
@@ -131,4 +139,16 @@ def texture_eval(scene, tex, q, lambda4=None, as_float=False):
     lam = fa(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4).reshape(-1, 4)
     out = np.zeros((n, 4), np.float32)
     lib().orc_texture_eval(scene.ptr(), tex, 1 if as_float else 0, n, q.ctypes.data, lam.ctypes.data, out.ctypes.data)
+    return out
+
+
+def texture_eval_p(scene, tex, p, q=None, dpdx=None, dpdy=None, lambda4=None, as_float=False):
+    """Texture lookups with a full TextureEvalContext (p, dpdx, dpdy in render space) -- the non-UV mappings."""
+    p = fa(p).reshape(-1, 3); n = len(p)
+    q = fa(np.zeros((n, 6)) if q is None else q).reshape(-1, 6)
+    pdp = fa(np.concatenate([p, np.zeros((n, 3)) if dpdx is None else fa(dpdx).reshape(-1, 3),
+                             np.zeros((n, 3)) if dpdy is None else fa(dpdy).reshape(-1, 3)], axis=1))
+    lam = fa(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4).reshape(-1, 4)
+    out = np.zeros((n, 4), np.float32)
+    lib().orc_texture_eval_p(scene.ptr(), int(tex), 1 if as_float else 0, n, q.ctypes.data, pdp.ctypes.data, lam.ctypes.data, out.ctypes.data)
     return out
