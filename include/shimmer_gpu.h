@@ -106,7 +106,8 @@ enum {
     SG_MESH_HAS_N = 1, SG_MESH_HAS_UV = 2, SG_MESH_HAS_S = 4,
     SG_MESH_REVERSE_ORIENTATION = 8, SG_MESH_SWAPS_HANDEDNESS = 16,
     SG_MESH_BILINEAR = 32   /* `BilinearPatchMesh` (mesh.rs:98-175): FOUR indices per patch (p00, p10, p01, p11; bilinear_patch.rs:87-106),
-                               n_triangles = number of patches, SgPrimitive.tri = patch index.  Top-level, non-emissive patches only. */
+                               n_triangles = number of patches, SgPrimitive.tri = patch index.  Top-level patches only; an emissive patch's
+                               SgPrimitive.light points at an SG_LIGHT_DIFFUSE_AREA_PATCH light over that patch. */
 };
 typedef struct SgMesh {
     uint32_t first_index;
@@ -236,6 +237,9 @@ typedef enum SgLightKind {
     SG_LIGHT_POINT = 1,            /* PointLight light.rs:403-519                         */
     SG_LIGHT_UNIFORM_INFINITE = 2, /* UniformInfiniteLight light.rs:697-803               */
     SG_LIGHT_DIFFUSE_AREA_SPHERE = 3, /* DiffuseAreaLight over a Sphere (sphere.rs:299-457): tri = index into spheres, area = Sphere::area() */
+    SG_LIGHT_DIFFUSE_AREA_PATCH = 5, /* DiffuseAreaLight over a BilinearPatch (bilinear_patch.rs:517-783): mesh = the SG_MESH_BILINEAR mesh, tri = patch
+                                        index, area = BilinearPatch::new's area (:40-76).  Rectangular patches are sampled by solid angle
+                                        (sample_spherical_rectangle, sampling.rs:501-579), others by area with the bilinear warp */
     SG_LIGHT_IMAGE_INFINITE = 4    /* ImageInfinitelight light.rs:805-981: tri = index into env_maps, spectrum = the image colour space's
                                       illuminant (dense), scale as computed by Light::create (light.rs:181-223) */
 } SgLightKind;

@@ -808,6 +808,10 @@ inline Float sphere_pdf_with_context(const SgSceneDesc* D, const SgSphere& S, co
     return 1.0f / (2.90f * PI_F * one_minus_cos_theta_max);                                              // sic: 2.90, :455
 }
 
+}  // namespace orc
+#include "orc_patch_light.h"
+namespace orc {
+
 // sample_uniform_sphere sampling.rs:280-289
 inline V3 sample_uniform_sphere(V2 u) {
     const Float z = 1.0f - 2.0f * u.x, r = safe_sqrt(1.0f - z * z), phi = 2.0f * PI_F * u.y;
@@ -818,9 +822,10 @@ inline V3 sample_uniform_sphere(V2 u) {
 inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V2 u, const Wavelengths& lambda, LightLiSample* ls,
                             bool allow_incomplete = true) {
     const SgSceneDesc* D = sc.d;
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE || lt.kind == SG_LIGHT_DIFFUSE_AREA_PATCH) {
         ShapeSample ss;
         if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) { if (!sphere_sample_with_context(D->spheres[lt.tri], ctx, u, &ss)) return false; }
+        else if (lt.kind == SG_LIGHT_DIFFUSE_AREA_PATCH) { if (!patch_sample_with_context(sc, lt.mesh, lt.tri, ctx, u, &ss)) return false; }
         else if (!tri_sample_with_context(sc, lt.mesh, lt.tri, ctx, u, &ss)) return false;
         V3 sp = p3fi_mid(ss.pi);
         if (ss.pdf == 0.0f || length_squared(sp - ctx.p()) == 0.0f) return false;
@@ -855,6 +860,7 @@ inline bool light_sample_li(const Scene& sc, const SgLight& lt, const LightSampl
 inline Float light_pdf_li(const Scene& sc, const SgLight& lt, const LightSampleContext& ctx, V3 wi, bool allow_incomplete = true) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, lt.mesh, lt.tri, ctx, wi);     // light.rs:663-666
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc.d, sc.d->spheres[lt.tri], ctx, wi);
+    if (lt.kind == SG_LIGHT_DIFFUSE_AREA_PATCH) return patch_pdf_with_context(sc, lt.mesh, lt.tri, ctx, wi);
     if (lt.kind == SG_LIGHT_IMAGE_INFINITE) return env_pdf_li(sc.d, lt, wi, allow_incomplete);           // :882-892
     if (lt.kind == SG_LIGHT_UNIFORM_INFINITE && !allow_incomplete) return INV_4PI;                       // :768-780
     return 0.0f;                                                                                       // :486-494, :770-781

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "--shared", "-Xcompiler", "-fPIC"]
+              "--shared", "-Xcompiler", "-fPIC", "--compress-mode=size"]
 
 
 def _stale(target, sources):
@@ -21,15 +21,29 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+# translation units of libshimmer_gpu.so: the C ABI + traversal kernels, and seven groups of shade-kernel instantiations
+# (csrc/sg_kernels.h).  They are compiled in parallel (one nvcc process each) and linked into one shared library.
+GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade_tu.cu", ["-DSG_TU=%d" % i]) for i in range(1, 8)]
+
+
 def build_gpu(force=False, verbose=False):
     out = os.path.join(HERE, "libshimmer_gpu.so")
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(HERE, "..", "include", "shimmer_gpu.h"))
     if not force and not _stale(out, srcs):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "shimmer_gpu.cu")]
-    subprocess.run(cmd, check=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for name, src, defs in GPU_UNITS:
+        obj = os.path.join(objdir, name + ".o")
+        procs.append((name, obj, subprocess.Popen([nvcc] + flags + defs + ["-c", "-o", obj, os.path.join(CSRC, src)])))
+    failed = [name for name, _, p in procs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for: " + ", ".join(failed))
+    subprocess.run([nvcc, "--shared", "-o", out] + [obj for _, obj, _ in procs], check=True)
     return out
 
 

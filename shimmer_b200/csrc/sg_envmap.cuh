@@ -64,7 +64,7 @@ SGD float pc2d_pdf(const DScene& sc, const SgDistribution2D& d, float2 pr) {    
     return __ldg(sc.pool + d.func_off + (size_t)iv * d.nu + iu) / d.marg_integral;
 }
 // ImageInfinitelight::image_le light.rs:966-976
-__device__ __noinline__ Spec env_image_le(const DScene& sc, const SgLight& lt, float2 uv, const Wavelengths& lam) {
+static __device__ __noinline__ Spec env_image_le(const DScene& sc, const SgLight& lt, float2 uv, const Wavelengths& lam) {
     const SgEnvMap& E = sc.env_maps[lt.tri];
     const int R = E.res;
     int px = f2i_sat(uv.x * (float)R), py = f2i_sat(uv.y * (float)R);                                // `as i32`: truncation, saturating, NaN -> 0
@@ -83,7 +83,7 @@ __device__ __noinline__ Spec env_image_le(const DScene& sc, const SgLight& lt, f
     return lt.scale * (s * spectrum_sample(sc, lt.spectrum, lam));
 }
 // Light::le of the infinite lights: light.rs:792-794 (uniform), :907-911 (image)
-__device__ __noinline__ Spec infinite_le(const DScene& sc, const SgLight& lt, float3 ray_d, const Wavelengths& lam) {
+static __device__ __noinline__ Spec infinite_le(const DScene& sc, const SgLight& lt, float3 ray_d, const Wavelengths& lam) {
     if (lt.kind == SG_LIGHT_IMAGE_INFINITE) {
         const float3 wl = xform_vector(sc.env_maps[lt.tri].light_from_render, ray_d);
         return env_image_le(sc, lt, equal_area_sphere_to_square(wl), lam);
@@ -91,7 +91,7 @@ __device__ __noinline__ Spec infinite_le(const DScene& sc, const SgLight& lt, fl
     return lt.scale * spectrum_sample(sc, lt.spectrum, lam);
 }
 // ImageInfinitelight::pdf_li light.rs:882-892 / UniformInfiniteLight::pdf_li :768-780
-__device__ __noinline__ float infinite_pdf_li(const DScene& sc, const SgLight& lt, float3 wi, bool allow_incomplete) {
+static __device__ __noinline__ float infinite_pdf_li(const DScene& sc, const SgLight& lt, float3 wi, bool allow_incomplete) {
     if (lt.kind == SG_LIGHT_IMAGE_INFINITE) {
         const SgEnvMap& E = sc.env_maps[lt.tri];
         const float2 uv = equal_area_sphere_to_square(xform_vector(E.light_from_render, wi));
@@ -100,7 +100,7 @@ __device__ __noinline__ float infinite_pdf_li(const DScene& sc, const SgLight& l
     return allow_incomplete ? 0.0f : kInv4Pi;
 }
 // ImageInfinitelight::sample_li light.rs:847-880 / UniformInfiniteLight::sample_li :740-766
-__device__ __noinline__ bool infinite_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, bool allow_incomplete,
+static __device__ __noinline__ bool infinite_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, bool allow_incomplete,
                                                 LightSample& ls) {
     const float3 cp = p3fi_mid(ctx.pi);
     if (lt.kind == SG_LIGHT_IMAGE_INFINITE) {

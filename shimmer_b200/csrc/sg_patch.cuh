@@ -26,7 +26,7 @@ SGD float det3_cols(float3 c0, float3 c1, float3 c2) {           // matrix rows 
 SGD float3 lerp3(float t, float3 a, float3 b) { return a * (1.0f - t) + b * t; }                               // math.rs:246-252
 SGD float max_abs_comp(float3 v) { return fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))); }
 
-__device__ __noinline__ bool intersect_blp(float3 ro, float3 rd, float t_max, float3 p00, float3 p10, float3 p01, float3 p11, float& u_out, float& v_out, float& t_out) {
+static __device__ __noinline__ bool intersect_blp(float3 ro, float3 rd, float t_max, float3 p00, float3 p10, float3 p01, float3 p11, float& u_out, float& v_out, float& t_out) {
     const float a = dot3(cross3(p10 - p00, p01 - p11), rd);
     const float c = dot3(cross3(p00 - ro, rd), p01 - p00);
     const float b = dot3(cross3(p10 - ro, rd), p11 - p10) - (a + c);

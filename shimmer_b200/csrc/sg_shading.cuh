@@ -516,14 +516,14 @@ SGD float3 ldv3(const float* a, size_t i) { return f3(__ldg(a + 3 * i), __ldg(a 
 // Triangle geometry handle.  Vertices come from the pre-gathered tri_verts / light_verts records
 // (one cache line, already touched by the traversal kernel); the index/attribute arrays are only
 // read for meshes that carry normals, uvs or tangents.
-struct TriGeo { float3 p0, p1, p2; uint32_t flags; uint32_t mesh; uint32_t tri; uint32_t prim; };
+struct TriGeo { float3 p0, p1, p2; uint32_t flags; uint32_t mesh; uint32_t tri; uint32_t prim; uint32_t kind; };   // kind: SgMaterialKind of the primitive's material (hits only)
 static constexpr uint32_t kTriUnknown = 0xffffffffu;
 SGD TriGeo geo_from_prim(const DScene& sc, uint32_t prim_id, uint32_t& material, int& light) {
     const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim_id), v1 = __ldg(sc.tri_verts + 3 * (size_t)prim_id + 1),
                  v2 = __ldg(sc.tri_verts + 3 * (size_t)prim_id + 2);
     const uint32_t w0 = __float_as_uint(v0.w);
     TriGeo g; g.p0 = f3(v0.x, v0.y, v0.z); g.p1 = f3(v1.x, v1.y, v1.z); g.p2 = f3(v2.x, v2.y, v2.z);
-    g.flags = (w0 >> 23) & 31u; g.mesh = __float_as_uint(v2.w) & 0x7fffffffu; g.tri = kTriUnknown; g.prim = prim_id;
+    g.flags = (w0 >> 23) & 31u; g.mesh = __float_as_uint(v2.w) & 0x7fffffffu; g.tri = kTriUnknown; g.prim = prim_id; g.kind = (w0 >> 28) & 7u;
     material = w0 & 0x7fffffu; light = (int)__float_as_uint(v1.w);
     return g;
 }
@@ -531,7 +531,7 @@ SGD TriGeo geo_from_light(const DScene& sc, uint32_t light_id, const SgLight& lt
     const float4 v0 = __ldg(sc.light_verts + 3 * (size_t)light_id), v1 = __ldg(sc.light_verts + 3 * (size_t)light_id + 1),
                  v2 = __ldg(sc.light_verts + 3 * (size_t)light_id + 2);
     TriGeo g; g.p0 = f3(v0.x, v0.y, v0.z); g.p1 = f3(v1.x, v1.y, v1.z); g.p2 = f3(v2.x, v2.y, v2.z);
-    g.flags = __float_as_uint(v0.w); g.mesh = lt.mesh; g.tri = lt.tri; g.prim = 0;
+    g.flags = __float_as_uint(v0.w); g.mesh = lt.mesh; g.tri = lt.tri; g.prim = 0; g.kind = 0;
     return g;
 }
 SGD void geo_indices(const DScene& sc, const TriGeo& g, uint32_t& i0, uint32_t& i1, uint32_t& i2, size_t& fv) {
@@ -717,43 +717,44 @@ SGD float tri_pdf_with_context(const DScene& sc, const TriGeo& g, const LightCtx
     return pdf;
 }
 // Sphere emitters (sphere.rs:299-457): defined in sg_sphere_surface.cuh (they need the sphere's SurfaceInteraction)
-__device__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf);
-__device__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi);
-// Infinite lights (uniform: light.rs:697-803, image: :805-981): defined in sg_envmap.cuh, out of line
-__device__ bool infinite_sample_li(const DScene& sc, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, bool allow_incomplete, LightSample& ls);
-__device__ float infinite_pdf_li(const DScene& sc, const SgLight& lt, float3 wi, bool allow_incomplete);
-__device__ Spec infinite_le(const DScene& sc, const SgLight& lt, float3 ray_d, const Wavelengths& lam);
-// Light::sample_li; allow_incomplete_pdf = true from PathIntegrator::sample_ld (integrator.rs:933), false from SimplePath (:652-656)
+static __device__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf);
+static __device__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi);
+// Everything that is not a triangle emitter goes through ONE out-of-line call per routine (defined in sg_patch_light.cuh, after
+// the sphere / patch / environment-map code it dispatches to): the shade kernels' register allocation is sensitive to the number
+// of call sites on the hot path, and triangle area lights are the common case.
+// (they take the light's index, not the SgLight copy the caller holds: a by-reference struct argument would pin all 64 bytes in local memory)
+static __device__ bool light_sample_li_other(const DScene& sc, uint32_t light_id, const LightCtx& ctx, float2 u, const Wavelengths& lam,
+                                      bool allow_incomplete, LightSample& ls);
+static __device__ float light_pdf_li_other(const DScene& sc, uint32_t light_id, uint32_t hit_mesh_word, const LightCtx& ctx, float3 wi);
+static __device__ float infinite_pdf_li(const DScene& sc, const SgLight& lt, float3 wi, bool allow_incomplete);
+static __device__ Spec infinite_le(const DScene& sc, const SgLight& lt, float3 ray_d, const Wavelengths& lam);
+// Light::sample_li; allow_incomplete_pdf = true from PathIntegrator::sample_ld (integrator.rs:933), false from SimplePath (:652-656).
+// GENERAL = false: the lean shade kernels, which only ever run on scenes whose lights are triangle emitters (plus uniform infinite
+// lights, which sample_li never samples with incomplete pdfs, light.rs:748-750) -- no call site at all: even a never-taken
+// out-of-line call costs those kernels ~3 % (measured on C2: register allocation around the call).
+template <bool GENERAL = true>
 SGD bool light_sample_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const LightCtx& ctx, float2 u, const Wavelengths& lam, LightSample& ls,
                          bool allow_incomplete = true) {
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA || lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) {   // light.rs:632-661
-        P3fi pi; float3 n; float pdf;
-        if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) { if (!sphere_sample_with_context(sc.spheres[lt.tri], ctx, u, pi, n, pdf)) return false; }
-        else {
-            const TriGeo g = geo_from_light(sc, light_id, lt);
-            if (!tri_sample_with_context(sc, g, ctx, u, pi, n, pdf)) return false;
-        }
-        float3 sp = p3fi_mid(pi), cp = p3fi_mid(ctx.pi);
-        if (pdf == 0.0f || len2(sp - cp) == 0.0f) return false;
-        float3 wi = normalize3(sp - cp);
-        Spec le = light_l(sc, lt, n, -wi, lam);
-        if (spec_zero(le)) return false;
-        ls.l = le; ls.wi = wi; ls.pdf = pdf; ls.p_light = pi; ls.n_light = n;
-        return true;
-    } else if (lt.kind == SG_LIGHT_POINT) {                                  // light.rs:461-484
-        float3 p = f3(lt.pos[0], lt.pos[1], lt.pos[2]), cp = p3fi_mid(ctx.pi);
-        ls.wi = normalize3(p - cp);
-        ls.l = lt.scale * spectrum_sample(sc, lt.spectrum, lam) / dist2(p, cp);
-        ls.pdf = 1.0f; ls.p_light = p3fi_exact(p); ls.n_light = f3(0.0f, 0.0f, 0.0f);
-        return true;
+    if (lt.kind != SG_LIGHT_DIFFUSE_AREA) {
+        if constexpr (GENERAL) return light_sample_li_other(sc, light_id, ctx, u, lam, allow_incomplete, ls);
+        else return false;
     }
-    if (lt.kind == SG_LIGHT_IMAGE_INFINITE || !allow_incomplete) return infinite_sample_li(sc, lt, ctx, u, lam, allow_incomplete, ls);
-    return false;                                                            // UniformInfiniteLight: None, light.rs:748-750
+    P3fi pi; float3 n; float pdf;                                            // DiffuseAreaLight::sample_li light.rs:632-661 over a Triangle
+    const TriGeo g = geo_from_light(sc, light_id, lt);
+    if (!tri_sample_with_context(sc, g, ctx, u, pi, n, pdf)) return false;
+    float3 sp = p3fi_mid(pi), cp = p3fi_mid(ctx.pi);
+    if (pdf == 0.0f || len2(sp - cp) == 0.0f) return false;
+    float3 wi = normalize3(sp - cp);
+    Spec le = light_l(sc, lt, n, -wi, lam);
+    if (spec_zero(le)) return false;
+    ls.l = le; ls.wi = wi; ls.pdf = pdf; ls.p_light = pi; ls.n_light = n;
+    return true;
 }
-SGD float light_pdf_li(const DScene& sc, const SgLight& lt, const TriGeo& g, const LightCtx& ctx, float3 wi) {
+template <bool GENERAL = true>
+SGD float light_pdf_li(const DScene& sc, uint32_t light_id, const SgLight& lt, const TriGeo& g, const LightCtx& ctx, float3 wi) {
     if (lt.kind == SG_LIGHT_DIFFUSE_AREA) return tri_pdf_with_context(sc, g, ctx, wi);                   // light.rs:663-666
-    if (lt.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE) return sphere_pdf_with_context(sc, sc.spheres[lt.tri], ctx, wi);
-    return 0.0f;                                                             // :486-494 (infinite lights: infinite_pdf_li)
+    if constexpr (GENERAL) return light_pdf_li_other(sc, light_id, g.mesh, ctx, wi);
+    else return 0.0f;
 }
 
 // ---------------- camera (camera.rs:1003-1079, transform.rs:385-457,515-532,753-776) ----------------

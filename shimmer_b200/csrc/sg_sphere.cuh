@@ -85,7 +85,7 @@ SGD bool sphere_clipped(const DSphere& S, float3 p) {                           
     return (S.z_min > -S.radius && p.z < S.z_min) || (S.z_max < S.radius && p.z > S.z_max) || sphere_phi(p) > S.phi_max;
 }
 // Sphere::basic_intersect sphere.rs:95-186; (o, d) is the render-space ray.  Out: QuadricIntersection{t_hit, p_obj}.
-__device__ __noinline__ bool sphere_basic_intersect(const DSphere& S, float3 o, float3 d, float t_max, float3& p_obj, float& t_hit) {
+static __device__ __noinline__ bool sphere_basic_intersect(const DSphere& S, float3 o, float3 d, float t_max, float3& p_obj, float& t_hit) {
     const V3i oi = sph_point_fi(S.mi, o), di = sph_vector_fi(S.mi, d);
     const Ival a = iv_add(iv_add(iv_sqr(di.x), iv_sqr(di.y)), iv_sqr(di.z));
     const Ival b = iv_scale(2.0f, iv_add(iv_add(iv_mul(di.x, oi.x), iv_mul(di.y, oi.y)), iv_mul(di.z, oi.z)));

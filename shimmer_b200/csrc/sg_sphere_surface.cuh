@@ -113,7 +113,7 @@ __device__ __noinline__ Surf make_surface_patch(const DScene& sc, uint32_t rec, 
 SGD float sphere_area(const DSphere& S) { return S.phi_max * S.radius * (S.z_max - S.z_min); }
 SGD float3 sphere_center(const DSphere& S) { return f3(S.m[3], S.m[7], S.m[11]); }                           // render_from_object.apply(Point3f::ZERO)
 // Sphere::sample_with_context :339-420 (inside: Sphere::sample :299-333 + area -> solid angle; outside: cone sampling)
-__device__ __noinline__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf) {
+static __device__ __noinline__ bool sphere_sample_with_context(const DSphere& S, const LightCtx& ctx, float2 u, P3fi& out_pi, float3& out_n, float& out_pdf) {
     const float3 pc = sphere_center(S), cp = p3fi_mid(ctx.pi);
     const float3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);
     if (dist2(p_origin, pc) <= sqr(S.radius)) {
@@ -171,7 +171,7 @@ __device__ __noinline__ bool sphere_sample_with_context(const DSphere& S, const 
     return true;
 }
 // Sphere::pdf_with_context :422-456
-__device__ __noinline__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi) {
+static __device__ __noinline__ float sphere_pdf_with_context(const DScene& sc, const DSphere& S, const LightCtx& ctx, float3 wi) {
     const float3 pc = sphere_center(S), cp = p3fi_mid(ctx.pi);
     const float3 p_origin = offset_ray_origin(ctx.pi, ctx.n, pc - cp);
     if (dist2(p_origin, pc) <= S.radius * S.radius) {

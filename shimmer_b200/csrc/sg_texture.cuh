@@ -205,7 +205,7 @@ SGD void uv_map(const SgTexture& t, const TexCoordCtx& c, float2& st, float2& ds
 }
 // SphericalMapping / CylindricalMapping / PlanarMapping ::map texture.rs:943-1035 (as written there), then the t flip of the
 // image textures (:396-399, :780-781)
-__device__ __noinline__ void general_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {
+static __device__ __noinline__ void general_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {
     const SgTextureMapping& M = sc.texture_mappings[t.mapping];
     const float3 p = c.pdp ? c.pdp[0] : f3(0.0f, 0.0f, 0.0f);
     const float3 pt = xform_point(M.texture_from_render, p);
@@ -236,7 +236,7 @@ SGD void tex_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, flo
     if (t.mapping < 0) uv_map(t, c, st, dst0, dst1); else general_map(sc, t, c, st, dst0, dst1);
 }
 // FloatImageTexture::evaluate texture.rs:393-404
-__device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
+static __device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
     float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
@@ -244,7 +244,7 @@ __device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, cons
     return t.invert ? fmaxf(0.0f, 1.0f - v) : v;
 }
 // SpectrumImageTexture::evaluate texture.rs:777-808
-__device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
+static __device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
     float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
@@ -290,7 +290,7 @@ SGD void rotate_from_to(float3 from, float3 to, float r[9]) {
         }
 }
 // Camera::approximate_dp_dxy camera.rs:308-354
-__device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, float3 n, int spp, uint32_t option_flags, float3& dpdx, float3& dpdy) {
+static __device__ __noinline__ void approximate_dp_dxy(const DScene& sc, float3 p, float3 n, int spp, uint32_t option_flags, float3& dpdx, float3& dpdy) {
     const SgCamera& cam = sc.camera;
     const float3 p_camera = xform_point(cam.camera_from_render, p);
     float r[9];
@@ -409,7 +409,7 @@ SGD void bump_map(const DScene& sc, int tex, float cdisp, Surf& s, const SurfTex
 }
 
 // normal_map material.rs:1453-1474: level 0 of a three-channel image through Image::bilerp_channel_wrapped with WrapMode::Repeat
-__device__ __noinline__ void normal_map(const DScene& sc, int tex, Surf& s, const SurfTex& x) {
+static __device__ __noinline__ void normal_map(const DScene& sc, int tex, Surf& s, const SurfTex& x) {
     SgTexture t = sc.textures[tex]; t.wrap = SG_WRAP_REPEAT;
     const TexView tv{sc, t};
     const float3 px = tex_bilerp<true>(tv, 0, make_float2(x.uv.x, 1.0f - x.uv.y));

@@ -67,6 +67,7 @@ struct TraceScene {
     const float4* patch_verts;  // bilinear patches (INST kernels only)
     const DSphere* spheres;     // sphere shapes (INST kernels only: the "general" kernels handle everything that is not a triangle)
     uint32_t scene_flags;
+    uint32_t queue_mask;        // bit k: shade queue k (sg_wavefront.cuh Q_*) can receive hits in this scene -- the retire step skips the others
 };
 
 // Per-thread traversal stack: the first `levels` entries live in shared memory (level-major, so a warp's

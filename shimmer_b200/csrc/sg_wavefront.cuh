@@ -13,6 +13,7 @@
 #include "sg_envmap.cuh"
 #include "sg_trace2.cuh"
 #include "sg_sphere_surface.cuh"
+#include "sg_patch_light.cuh"
 
 namespace sg {
 
@@ -127,7 +128,7 @@ static constexpr int kTraceThreads = SG_TRACE_THREADS;
 #endif
 
 // ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
-__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
+static __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
                                                   unsigned long long first_item, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) q.counters[C_NRAY] = count;
@@ -316,7 +317,7 @@ SGD void trace_persistent_post(const TraceScene& ts, IO& io, CursorT n, CursorT*
 }
 
 struct ClosestIO {
-    const DScene& sc; PathState st; Queues q; uint32_t* C; const uint32_t* queue;
+    const DScene& sc; PathState st; Queues q; uint32_t* C; const uint32_t* queue; uint32_t queue_mask;
     uint32_t path;
     SGD void load(uint32_t i, float3& o, float3& d, float& tmax) {
         path = queue[i];
@@ -335,6 +336,7 @@ struct ClosestIO {
         }
 #pragma unroll
         for (int k = 0; k < Q_NKINDS; ++k) {
+            if (!((queue_mask >> k) & 1u)) continue;                         // warp-uniform: material kinds the scene does not use cost no vote
             const uint32_t mask = __ballot_sync(0xffffffffu, kind == k);
             if (mask) {
                 uint32_t qbase = 0;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
         if constexpr (POST) trace_persistent_post<true>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem);
         else trace_persistent<true, COUNT, INST>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, cnt_nodes, cnt_tris);
     } else {
-        ClosestIO io{sc, st, q, C, q.ray[depth & 1], 0};
+        ClosestIO io{sc, st, q, C, q.ray[depth & 1], ts.queue_mask, 0};
         if constexpr (POST) trace_persistent_post<false>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem);
         else trace_persistent<false, COUNT, INST>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
     }
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
 }
 
 // ---- escaped rays: infinite lights, integrator.rs:776-794 ----
-__global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+static __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     const uint32_t* C = q.counters + depth * C_STRIDE;
     const uint32_t n = C[C_NSHADE + Q_MISS];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -502,11 +504,13 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS 4
 #endif
-// TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture
-// lookups, bump mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.
+// TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture lookups, bump /
+// normal mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.  TEX = false is the lean variant
+// for untextured scenes lit by triangle emitters: no call sites on its hot path.
 // PATH = false: the SimplePathIntegrator (integrator.rs:570-728) / RandomWalkIntegrator (:458-568) bodies, chosen at run time by
 // rc.integrator; instantiated with TEX = true only (that variant is a superset: it also renders untextured scenes).
-template <int KIND, bool TEX, bool PATH = true>
+// LG = the scene has lights that are not triangle emitters (see light_sample_li<GENERAL>); LG implies TEX.
+template <int KIND, bool TEX, bool PATH = true, bool LG = TEX>
 __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                         const float4 c0 = st.ctx0[path], c1 = st.ctx1[path], c2 = st.ctx2[path];
                         pc.pi.lo = f3(c0.x, c0.y, c0.z); pc.pi.hi = f3(c0.w, c1.x, c1.y);
                         pc.n = f3(c1.z, c1.w, c2.x); pc.ns = f3(c2.y, c2.z, c2.w);
-                        float p_l = (1.0f / (float)sc.n_lights) * light_pdf_li(sc, lt, geo, pc, rd);
+                        float p_l = (1.0f / (float)sc.n_lights) * light_pdf_li<LG>(sc, (uint32_t)light_id, lt, geo, pc, rd);
                         float w_l = power_heuristic(p_b, p_l);
                         L = L + beta * w_l * le;
                     }
@@ -604,8 +608,8 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             }
 
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
-            SgMaterial mat = sc.materials[material_id];
-            if (mat.kind == SG_MATERIAL_MIX) mat = sc.materials[st.mat_override[path]];             // resolved by k_resolve_mix (interaction.rs:206-221)
+            if (geo.kind == SG_MATERIAL_MIX) material_id = st.mat_override[path];                   // resolved by k_resolve_mix (interaction.rs:206-221)
+            const SgMaterial mat = sc.materials[material_id];
             AuxRays aux; aux.has = false;
             if (TEX) {
                 if (sc.n_textures > 0) {
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                             const SgLight lt = sc.lights[li];
                             LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;           // LightSampleContext::from(&isect): no nudge
                             LightSample ls;
-                            if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls, false) && !spec_zero(ls.l) && ls.pdf > 0.0f) {
+                            if (light_sample_li<true>(sc, li, lt, ctx, u_light, lam, ls, false) && !spec_zero(ls.l) && ls.pdf > 0.0f) {
                                 bsdf.layer_seed = layer_seed(rng, 1);
                                 const Spec f = bsdf.f(wo, ls.wi) * absdot3(ls.wi, s.sn);          // wo = -ray.d (:646), not intr.wo
                                 if (!spec_zero(f)) {
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                         const float p_choose = 1.0f / (float)sc.n_lights;
                         const SgLight lt = sc.lights[li];
                         LightSample ls;
-                        if (light_sample_li(sc, li, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
+                        if (light_sample_li<LG>(sc, li, lt, ctx, u_light, lam, ls) && !spec_zero(ls.l) && ls.pdf != 0.0f) {
                             bsdf.layer_seed = layer_seed(rng, 1);
                             Spec f = bsdf.f(wo_si, ls.wi) * absdot3(ls.wi, s.sn);
                             if (!spec_zero(f)) {
@@ -868,7 +872,7 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
 // `rgb_sum[c] += (w * rgb[c]) as f64; weight_sum += w` with f64 atomics (RED.ADD.F64): samples of one pixel live
 // in different wavefront slots.  Paths are pixel-major, so a warp usually holds 32 samples of ONE pixel: those
 // are summed in f64 across the warp first (one atomic per channel per warp instead of 32 same-address ones).
-__global__ void __launch_bounds__(256) k_film(const __grid_constant__ DScene sc, PathState st, uint32_t count, double* film) {
+static __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DScene sc, PathState st, uint32_t count, double* film) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < count;
     float rgb[3] = {0.0f, 0.0f, 0.0f};
@@ -894,7 +898,7 @@ __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DScene sc,
     }
 }
 
-__global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
+static __global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
     unsigned long long c = 0, s = 0;
     for (int d = 0; d < n_depths; ++d) { c += counters[d * C_STRIDE + C_NRAY]; s += counters[d * C_STRIDE + C_NSHADOW]; }
     stats->closest += c; stats->shadow += s;
@@ -958,12 +962,12 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
 }
 
 // ---- KAT kernels ----
-__global__ void k_sampler_fill(uint64_t seed, int raw, uint32_t pixel, uint32_t sample, long long n, float* out) {
+static __global__ void k_sampler_fill(uint64_t seed, int raw, uint32_t pixel, uint32_t sample, long long n, float* out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     Rng r; r.seed_from_u64(raw ? seed : stream_key(seed, pixel, sample));
     for (long long i = 0; i < n; ++i) out[i] = r.get_1d();
 }
-__global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc, long long n, const int* pixel_xy, const int* sample_index,
+static __global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc, long long n, const int* pixel_xy, const int* sample_index,
                               float* out_rays, float* out_lambda) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -977,7 +981,7 @@ __global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderConst rc,
     l[0] = lam.lambda.x; l[1] = lam.lambda.y; l[2] = lam.lambda.z; l[3] = lam.lambda.w;
     l[4] = lam.pdf.x; l[5] = lam.pdf.y; l[6] = lam.pdf.z; l[7] = lam.pdf.w;
 }
-__global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* pdp_in, const float* lambda, float* out) {
+static __global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* pdp_in, const float* lambda, float* out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     TexCoordCtx c; c.uv = make_float2(q[6 * i], q[6 * i + 1]); c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
@@ -996,7 +1000,7 @@ __global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int a
     out[4 * i] = s.x; out[4 * i + 1] = s.y; out[4 * i + 2] = s.z; out[4 * i + 3] = s.w;
 }
 // RgbFilm::get_pixel_rgb film.rs:720-738
-__global__ void k_film_develop(const __grid_constant__ DScene sc, const double* film, long long n, float* out) {
+static __global__ void k_film_develop(const __grid_constant__ DScene sc, const double* film, long long n, float* out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float rgb[3] = {(float)film[4 * i], (float)film[4 * i + 1], (float)film[4 * i + 2]};
@@ -1006,7 +1010,7 @@ __global__ void k_film_develop(const __grid_constant__ DScene sc, const double* 
     for (int r = 0; r < 3; ++r) out[3 * i + r] = M[3 * r] * rgb[0] + M[3 * r + 1] * rgb[1] + M[3 * r + 2] * rgb[2];
 }
 // RgbFilm::get_image film.rs:647-707 + Image::set_channel image.rs:648-661 (see sg_film_get_image in shimmer_gpu.h)
-__global__ void k_film_image(const __grid_constant__ DScene sc, const double* film, int w, int h, uint32_t flags, float* out) {
+static __global__ void k_film_image(const __grid_constant__ DScene sc, const double* film, int w, int h, uint32_t flags, float* out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)w * h) return;
     float rgb[3] = {(float)film[4 * i], (float)film[4 * i + 1], (float)film[4 * i + 2]};

@@ -2,7 +2,7 @@
 // Host side: scene upload (one-time staging into HBM), wavefront scheduling on one CUDA
 // stream with device-side queue counters (no host sync inside a batch), film readback.
 // There is NO CPU fallback: every entry point either runs the sm_100a kernels or fails.
-#include "sg_wavefront.cuh"
+#include "sg_kernels.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,8 +58,9 @@ struct SgScene {
     unsigned long long* d_cursor = nullptr;
     bool kinds_present[8] = {false, false, false, false, false, false, false, false};
     bool instanced = false;         // object instances: k_trace<.., INST = true> and the hit_inst path-state array
+    bool general_lights = false;    // sphere / patch / point / image-infinite lights: k_shade<KIND, true, true, true>
     bool has_mix = false;           // Mix materials: k_resolve_mix + the mat_override path-state array
-    bool tex_path = false;          // image textures or a non-zero constant displacement: k_shade<KIND, true>
+    bool tex_path = false;          // image textures, a non-zero constant displacement or non-triangle emitters: k_shade<KIND, true>
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
     uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
@@ -178,7 +179,9 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (!desc->meshes || !desc->indices || !desc->p) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
         if (p.mesh < desc->n_meshes && (desc->meshes[p.mesh].flags & SG_MESH_BILINEAR)) {
             if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "bilinear patches inside object definitions are not on the GPU path yet");
-            if (p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights on bilinear patches are not on the GPU path yet");
+            if (p.light >= (int32_t)desc->n_lights || (p.light >= 0 && (desc->lights[p.light].kind != SG_LIGHT_DIFFUSE_AREA_PATCH || desc->lights[p.light].mesh != p.mesh ||
+                                                                     desc->lights[p.light].tri != p.tri)))
+                return fail(SG_ERR_INVALID_ARGUMENT, "an emissive bilinear patch must point at an SG_LIGHT_DIFFUSE_AREA_PATCH light over that patch");
         }
         if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
             p.light >= (int32_t)desc->n_lights)
@@ -194,7 +197,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (desc->instances[i].object >= desc->n_objects) return fail(SG_ERR_INVALID_ARGUMENT, "instance " + std::to_string(i) + " references an out-of-range object");
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
         const SgLight& L = desc->lights[i];
-        if (L.kind < SG_LIGHT_DIFFUSE_AREA || L.kind > SG_LIGHT_IMAGE_INFINITE) return fail(SG_ERR_UNSUPPORTED, "light kind " + std::to_string(L.kind) + " is not on the GPU path");
+        if (L.kind < SG_LIGHT_DIFFUSE_AREA || L.kind > SG_LIGHT_DIFFUSE_AREA_PATCH) return fail(SG_ERR_UNSUPPORTED, "light kind " + std::to_string(L.kind) + " is not on the GPU path");
         if (L.kind == SG_LIGHT_DIFFUSE_AREA_SPHERE && L.tri >= desc->n_spheres) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + " references an out-of-range sphere");
         if (L.kind == SG_LIGHT_IMAGE_INFINITE && (L.tri >= desc->n_env_maps || !desc->env_maps)) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + " references an out-of-range environment map");
         if (L.spectrum < 0 || L.spectrum >= (int32_t)desc->n_spectra) return fail(SG_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + ": spectrum id out of range");
@@ -477,10 +480,15 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     for (uint32_t i = 0; i < desc->n_materials; ++i) if (desc->materials[i].kind == SG_MATERIAL_MIX) s->has_mix = true;
     if (s->has_mix)                                         // any material may come out of a mix: launch every kind that exists in the table
         for (uint32_t i = 0; i < desc->n_materials; ++i) if (desc->materials[i].kind != SG_MATERIAL_MIX) s->kinds_present[desc->materials[i].kind] = true;
+    s->ts.queue_mask = 1u;                                 // Q_MISS
+    for (int k = 0; k < 8; ++k) if (s->kinds_present[k]) s->ts.queue_mask |= 1u << (1 + k);
+    if (s->has_mix) s->ts.queue_mask |= 1u << Q_MIX;
     d.n_textures = desc->n_textures; d.rgb2spec_res = need_rgb2spec ? desc->rgb2spec_res : 0;
     s->tex_path = desc->n_textures > 0;
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if ((desc->materials[i].flags & SG_MAT_HAS_DISPLACEMENT) && desc->materials[i].displacement != 0.0f) s->tex_path = true;
+    for (uint32_t i = 0; i < desc->n_lights; ++i)               // lights only the general shade kernels handle (k_shade<.., LG = true>)
+        if (desc->lights[i].kind != SG_LIGHT_DIFFUSE_AREA && desc->lights[i].kind != SG_LIGHT_UNIFORM_INFINITE) s->general_lights = true;
     d.n_nodes = desc->n_nodes; d.n_prims = desc->n_primitives; d.n_lights = desc->n_lights; d.n_materials = desc->n_materials;
     d.n_infinite = 0;
     for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_UNIFORM_INFINITE || desc->lights[i].kind == SG_LIGHT_IMAGE_INFINITE) {
@@ -500,6 +508,18 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
                 float wf = 0.0f; if (k == 0) { uint32_t fl = m.flags; std::memcpy(&wf, &fl, 4); }
                 lv[3 * (size_t)i + k] = make_float4(q[0], q[1], q[2], wf);
             }
+        }
+        // patch emitters: the record of the light's patch in patch_verts (records were assigned in primitive order above)
+        {
+            uint32_t rec = 0; uint32_t found = 0, wanted = 0;
+            for (uint32_t i = 0; i < desc->n_lights; ++i) if (desc->lights[i].kind == SG_LIGHT_DIFFUSE_AREA_PATCH) ++wanted;
+            for (uint32_t i = 0; i < desc->n_primitives && wanted; ++i) {
+                const SgPrimitive& p = desc->primitives[i];
+                if (p.mesh == SG_PRIM_INSTANCE || p.mesh == SG_PRIM_SPHERE || !(desc->meshes[p.mesh].flags & SG_MESH_BILINEAR)) continue;
+                if (p.light >= 0) { float wf; std::memcpy(&wf, &rec, 4); lv[3 * (size_t)p.light].w = wf; ++found; }
+                ++rec;
+            }
+            if (found != wanted) { g_err = "every SG_LIGHT_DIFFUSE_AREA_PATCH light needs exactly one patch primitive that points at it"; return bail(SG_ERR_INVALID_ARGUMENT); }
         }
         float4* d_lv = nullptr;
         if ((rc = upload(lv.data(), lv.size(), &d_lv, s->owned)) != SG_OK) return bail(rc);
@@ -578,18 +598,12 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             ++launches; ++closest_launches;
             if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
-            if (s->has_mix) {
-                if (s->tex_path) k_resolve_mix<true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
-                else k_resolve_mix<false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
+            if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
+            for (int kind = 0; kind <= SG_MATERIAL_COATED_CONDUCTOR; ++kind) {
+                if (!s->kinds_present[kind]) continue;
+                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
                 ++launches;
             }
-#define SHADE(KIND) if (s->kinds_present[KIND]) { \
-                if (!path_integrator) k_shade<KIND, true, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
-                else if (s->tex_path) k_shade<KIND, true><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
-                else k_shade<KIND, false><<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); \
-                ++launches; }
-            SHADE(SG_MATERIAL_DIFFUSE) SHADE(SG_MATERIAL_CONDUCTOR) SHADE(SG_MATERIAL_DIELECTRIC) SHADE(SG_MATERIAL_COATED_DIFFUSE) SHADE(SG_MATERIAL_THIN_DIELECTRIC) SHADE(SG_MATERIAL_COATED_CONDUCTOR)
-#undef SHADE
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
                 kern_shadow<<<grid_shadow, kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);

@@ -24,6 +24,7 @@ SG_MATERIAL_DIFFUSE, SG_MATERIAL_CONDUCTOR, SG_MATERIAL_DIELECTRIC, SG_MATERIAL_
 SG_MATERIAL_COATED_CONDUCTOR, SG_MATERIAL_MIX = 5, 6
 SG_MAT_REMAP_ROUGHNESS, SG_MAT_HAS_DISPLACEMENT, SG_MAT_CONDUCTOR_REFLECTANCE = 1, 2, 4
 SG_LIGHT_DIFFUSE_AREA, SG_LIGHT_POINT, SG_LIGHT_UNIFORM_INFINITE, SG_LIGHT_DIFFUSE_AREA_SPHERE, SG_LIGHT_IMAGE_INFINITE = 0, 1, 2, 3, 4
+SG_LIGHT_DIFFUSE_AREA_PATCH = 5
 SG_MAPPING_SPHERICAL, SG_MAPPING_CYLINDRICAL, SG_MAPPING_PLANAR = 1, 2, 3
 SG_INTEGRATOR_PATH, SG_INTEGRATOR_SIMPLE_PATH, SG_INTEGRATOR_RANDOM_WALK = 0, 1, 2
 SG_SIMPLEPATH_SAMPLE_LIGHTS, SG_SIMPLEPATH_SAMPLE_BSDF = 1, 2

@@ -220,6 +220,35 @@ def _equal_area_square_to_sphere(px, py):
     return np.array([c * r * k, s_ * r * k, z], np.float32)
 
 
+def bilinear_patch_is_rectangle(P4):
+    """BilinearPatch::is_rectangle (bilinear_patch.rs:108-143); P4 = p00, p10, p01, p11 (f32)."""
+    p00, p10, p01, p11 = (np.asarray(x, np.float32) for x in P4)
+    if (p00 == p01).all() or (p01 == p11).all() or (p11 == p10).all() or (p10 == p00).all():
+        return False
+    n = np.cross(p10 - p00, p01 - p00).astype(np.float32); n /= np.linalg.norm(n)
+    d = (p11 - p00); d = d / np.linalg.norm(d)
+    if abs(float(np.dot(d, n))) > 1e-5:
+        return False
+    pc = (p00 + p01 + p10 + p11) * f32(0.25)
+    d2 = [float(np.sum((q - pc) ** 2)) for q in (p00, p01, p10, p11)]
+    return all(abs(d2[i] - d2[0]) / d2[0] <= 1e-4 for i in range(1, 4))
+
+
+def bilinear_patch_area(P4):
+    """BilinearPatch::new (bilinear_patch.rs:40-76): exact for rectangles, a 3x3 quad approximation otherwise.  Only `phi()` reads it."""
+    p00, p10, p01, p11 = (np.asarray(x, np.float32) for x in P4)
+    if bilinear_patch_is_rectangle(P4):
+        return f32(np.linalg.norm(p00 - p01)) * f32(np.linalg.norm(p00 - p10))
+    NA = 3
+    lerp = lambda t, a, b: a * f32(1.0 - t) + b * f32(t)
+    g = [[lerp(i / NA, lerp(j / NA, p00, p01), lerp(j / NA, p10, p11)) for j in range(NA + 1)] for i in range(NA + 1)]
+    area = f32(0.0)
+    for i in range(NA):
+        for j in range(NA):
+            area = f32(area + f32(0.5) * f32(np.linalg.norm(np.cross(g[i + 1][j + 1] - g[i][j], g[i + 1][j] - g[i][j + 1]))))
+    return area
+
+
 def piecewise_constant_1d(f, lo=0.0, hi=1.0):
     """PiecewiseConstant1D::new_bounded (sampling.rs:27-65), f32 running sums in the reference's order -> (func, cdf, func_int)."""
     func = np.abs(np.asarray(f, dtype=np.float32))
@@ -530,9 +559,10 @@ class SceneBuilder:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
-    def add_bilinear_mesh(self, p, indices, material, n=None, uv=None, reverse_orientation=False, object_from_world=None):
+    def add_bilinear_mesh(self, p, indices, material, n=None, uv=None, reverse_orientation=False, object_from_world=None, area_light=None):
         """Shape "bilinearmesh": BilinearPatchMesh::new (shape/mesh.rs:111-175) + one BilinearPatch per four indices
-        (p00, p10, p01, p11; bilinear_patch.rs:77-106).  Top-level, non-emissive patches only."""
+        (p00, p10, p01, p11; bilinear_patch.rs:77-106).  Top-level patches only.  `area_light` = dict(L=spectrum tuple, scale=float,
+        two_sided=bool) -> one DiffuseAreaLight per patch (scene.rs:609-622)."""
         ctm = object_from_world if object_from_world is not None else Transform.identity()
         rfo = self.render_from_world * ctm
         p = rfo.apply_points_f32(np.asarray(p, dtype=np.float32).reshape(-1, 3))
@@ -546,7 +576,8 @@ class SceneBuilder:
         if reverse_orientation: flags |= ffi.SG_MESH_REVERSE_ORIENTATION
         if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
         self.patch_meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 4), n=n,
-                                      uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2), flags=flags, material=material))
+                                      uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2), flags=flags, material=material,
+                                      area_light=area_light))
         return len(self.patch_meshes) - 1
 
     def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False,
@@ -675,6 +706,21 @@ class SceneBuilder:
                 L.two_sided = 1 if al.get("two_sided", False) else 0
                 L.mesh, L.tri, L.area = mi, t, float(area[t])
                 lights.append(L)
+        patch_light_base = {}
+        for pi_, m in enumerate(self.patch_meshes):                   # bilinear meshes follow the triangle meshes in shape order
+            al = m.get("area_light")
+            if al is None:
+                continue
+            sc = f32(al.get("scale", 1.0)) / spectrum_to_photometric(al["L"])
+            dense = spectrum_dense(al["L"])
+            r = ffi.SgSpectrum(); r.kind, r.n, r.lambda_min, r.off_a = ffi.SG_SPECTRUM_DENSE, len(dense), LAMBDA_MIN, off
+            pool.append(dense); off += len(dense); recs.append(r); sid = len(recs) - 1
+            patch_light_base[pi_] = len(lights)
+            for t in range(len(m["idx"])):
+                L = ffi.SgLight(); L.kind = ffi.SG_LIGHT_DIFFUSE_AREA_PATCH; L.spectrum = sid; L.scale = float(sc)
+                L.two_sided = 1 if al.get("two_sided", False) else 0
+                L.mesh, L.tri, L.area = len(self.meshes) + pi_, t, float(bilinear_patch_area(m["p"][m["idx"][t]]))
+                lights.append(L)
         sphere_light = {}
         for si_, sp in enumerate(self.spheres):                       # spheres follow the meshes in shape order
             al = sp.get("area_light")
@@ -724,7 +770,8 @@ class SceneBuilder:
             if m["uv"] is not None: A["uv"][v0:v0 + k] = m["uv"]
             mr = mesh_rows[mi]
             mr.first_index, mr.first_vertex, mr.n_triangles, mr.n_vertices, mr.flags = 3 * nt + 4 * q0, v0, t, k, m["flags"]
-            patch_prim_in[q0:q0 + t, 0] = mi; patch_prim_in[q0:q0 + t, 1] = np.arange(t); patch_prim_in[q0:q0 + t, 2] = m["material"]; patch_prim_in[q0:q0 + t, 3] = -1
+            patch_prim_in[q0:q0 + t, 0] = mi; patch_prim_in[q0:q0 + t, 1] = np.arange(t); patch_prim_in[q0:q0 + t, 2] = m["material"]
+            patch_prim_in[q0:q0 + t, 3] = (patch_light_base[pi_] + np.arange(t)) if pi_ in patch_light_base else -1
             P4 = m["p"][m["idx"]]                                           # BilinearPatch::bounds bilinear_patch.rs:430-433
             patch_bounds[q0:q0 + t, :3] = P4.min(axis=1); patch_bounds[q0:q0 + t, 3:] = P4.max(axis=1)
             v0 += k; q0 += t

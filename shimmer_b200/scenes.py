@@ -311,7 +311,7 @@ def sphere_tiny_scene(kind="spheres", resolution=(32, 32), fix=False):
     return b
 
 
-PATCH_KINDS = ("patches", "patchestex")
+PATCH_KINDS = ("patches", "patchestex", "patchlight", "patchlightbent")
 
 
 def patch_grid(n, size=2.0, amp=0.25):
@@ -352,6 +352,18 @@ def patch_tiny_scene(kind="patches", resolution=(32, 32)):
     b.add_bilinear_mesh(quad, [[0, 1, 2, 3]], wall, uv=np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32), reverse_orientation=True)
     gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
     b.add_mesh(gp, gi, white)
+    if kind == "patchlight":        # a rectangular emissive patch: sampled by solid angle (sample_spherical_rectangle, bilinear_patch.rs:666-736)
+        lq = np.array([[-0.6, 3.0, -0.9], [0.6, 3.0, -0.9], [-0.6, 3.0, 0.3], [0.6, 3.0, 0.3]], np.float32)
+        b.add_bilinear_mesh(lq, [[0, 1, 2, 3]], white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+        return b
+    if kind == "patchlightbent":    # a twisted two-sided emitter with uv + normals (area sampling with the bilinear warp) and a tiny
+        lq = np.array([[-0.7, 2.8, -0.9], [0.6, 3.1, -0.8], [-0.6, 3.0, 0.4], [0.7, 2.7, 0.2]], np.float32)     # far rectangle (solid angle <= 1e-4)
+        ln = np.tile(np.array([[0.0, -1.0, 0.0]], np.float32), (4, 1))
+        b.add_bilinear_mesh(lq, [[0, 1, 2, 3]], white, n=ln, uv=np.array([[0.1, 0.0], [0.9, 0.1], [0.0, 1.0], [1.0, 0.8]], np.float32),
+                            area_light=dict(L=named_spectrum("stdillum-D65"), scale=25.0, two_sided=True))
+        fq = np.array([[-0.02, 14.0, -0.02], [0.02, 14.0, -0.02], [-0.02, 14.0, 0.02], [0.02, 14.0, 0.02]], np.float32)
+        b.add_bilinear_mesh(fq, [[0, 1, 2, 3]], white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=4000.0, two_sided=False))
+        return b
     lp, li = _quad((-0.6, 3.0, -0.9), (0.6, 3.0, -0.9), (0.6, 3.0, 0.3), (-0.6, 3.0, 0.3))
     b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
     return b

@@ -50,7 +50,7 @@ INTEGRATOR_CASES = [("simplepath", True, True), ("simplepath", False, True), ("s
 
 
 @pytest.mark.parametrize("integ_name,sl,sb", INTEGRATOR_CASES)
-@pytest.mark.parametrize("kind", ["cornell", "mirror", "envmap", "glass", "texewa", "instfix", "coated", "mixtex", "spherelight"])
+@pytest.mark.parametrize("kind", ["cornell", "mirror", "envmap", "glass", "texewa", "instfix", "coated", "mixtex", "spherelight", "patchlightbent"])
 def test_simplepath_and_randomwalk_film_parity(kind, integ_name, sl, sb):
     """SimplePathIntegrator / RandomWalkIntegrator (integrator.rs:458-728) on the device vs the oracle, same random streams."""
     sc = (scenes.cornell_box(resolution=(16, 16)) if kind == "cornell" else scenes.tiny_scene(kind, resolution=(16, 16))).build()
