@@ -482,6 +482,17 @@ int sg_film_develop(SgScene* scene, const SgFilmPixel* film, int64_t n_pixels, f
 enum SgImageFlags { SG_IMAGE_FP16 = 1, SG_IMAGE_BOTTOM_UP = 2 };
 int sg_film_get_image(SgScene* scene, const SgFilmPixel* film, int32_t width, int32_t height, uint32_t flags, float* out_rgb);
 
+/* Replaces `Image::generate_pyramid` (image.rs:699-787; called by MIPMap::new, mipmap.rs:19-106) including `Image::float_resize_up`
+ * (:1007-1111) for images whose resolution is not a power of two: the stage right before the texture lookups of the hot path.
+ * sg_image_pyramid_layout fills `levels` (capacity >= 32; offsets in floats from the start of the output buffer) and the total
+ * texel count; sg_image_generate_pyramid takes width x height x n_channels LINEAR f32 texels (row 0 first; what
+ * Image::convert_to_format(Float) holds) and writes every level back to back into `out_texels` (host memory).
+ * wrap: SG_WRAP_REPEAT or SG_WRAP_CLAMP (the reference asserts on `black` while resizing, image.rs:826-828).  Resizing requires
+ * BOTH dimensions to grow (image.rs:1009-1010): e.g. 64 x 50 is rejected like the reference's assert.  The layout can be copied
+ * into SgImageLevel rows (add the texture's base offset) and the texels into SgSceneDesc.texels. */
+int sg_image_pyramid_layout(int32_t width, int32_t height, int32_t n_channels, int32_t* n_levels, SgImageLevel* levels, uint64_t* n_texels);
+int sg_image_generate_pyramid(const float* image, int32_t width, int32_t height, int32_t n_channels, int32_t wrap, float* out_texels);
+
 #ifdef __cplusplus
 }
 #endif

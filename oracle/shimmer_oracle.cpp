@@ -16,6 +16,7 @@
 #include <chrono>
 #include <vector>
 #include <cstdio>
+#include <algorithm>
 
 using namespace orc;
 
@@ -599,6 +600,83 @@ void orc_texture_eval_p(const SgSceneDesc* d, int tex, int as_float, int64_t n, 
             for (int k = 0; k < 4; ++k) out4[4 * i + k] = s.v[k];
         }
     }
+}
+// ---- Image::generate_pyramid (image.rs:699-787) with Image::float_resize_up (:1007-1111) / resample_weights (:1113-1141) ----
+// `image`: width x height x n_channels linear f32 texels (what convert_to_format(Float) yields).  Levels are written back to back
+// into `out`; returns the number of levels.  As written: resample_weights evaluates the windowed sinc at `first_pixel + 0.5` for
+// all four taps (pbrt: first_pixel + j + 0.5), so after normalisation every tap weighs ~0.25.
+static inline Float orc_sin_over_x(Float x) { if (1.0f - x * x == 1.0f) return 1.0f; return std::sin(x) / x; }      // math.rs:413-420
+static inline Float orc_sinc(Float x) { return orc_sin_over_x(PI_F * x); }
+static inline Float orc_windowed_sinc(Float x, Float radius, Float tau) { if (std::fabs(x) > radius) return 0.0f; return orc_sinc(x) * orc_sinc(x / tau); }
+struct OrcResampleWeight { int32_t first_pixel; Float weight[4]; };
+static std::vector<OrcResampleWeight> orc_resample_weights(int old_res, int new_res) {
+    std::vector<OrcResampleWeight> wt(new_res);
+    const Float filter_radius = 2.0f, tau = 2.0f;
+    for (int i = 0; i < new_res; ++i) {
+        const Float center = ((Float)i + 0.5f) * (Float)old_res / (Float)new_res;
+        wt[i].first_pixel = std::max(0, f2i(std::floor(center - filter_radius + 0.5f)));
+        for (int j = 0; j < 4; ++j) { const Float pos = (Float)wt[i].first_pixel + 0.5f; wt[i].weight[j] = orc_windowed_sinc(pos - center, filter_radius, tau); }
+        const Float inv = 1.0f / (wt[i].weight[0] + wt[i].weight[1] + wt[i].weight[2] + wt[i].weight[3]);
+        for (int j = 0; j < 4; ++j) wt[i].weight[j] *= inv;
+    }
+    return wt;
+}
+static inline uint32_t orc_next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+int32_t orc_image_pyramid_levels(int32_t width, int32_t height, int32_t* res_xy /* 2 per level, may be null */) {
+    uint32_t w = (uint32_t)width, h = (uint32_t)height;
+    if ((w & (w - 1)) || (h & (h - 1))) { w = orc_next_pow2(w); h = orc_next_pow2(h); }
+    const int32_t n_levels = 1 + (int32_t)std::log2((Float)std::max(w, h));
+    int32_t rx = (int32_t)w, ry = (int32_t)h;
+    for (int32_t l = 0; l < n_levels; ++l) {
+        if (res_xy) { res_xy[2 * l] = rx; res_xy[2 * l + 1] = ry; }
+        rx = std::max(1, (rx + 1) / 2); ry = std::max(1, (ry + 1) / 2);
+    }
+    return n_levels;
+}
+int32_t orc_image_generate_pyramid(const float* image, int32_t width, int32_t height, int32_t nc, int32_t wrap, float* out) {
+    std::vector<float> cur(image, image + (size_t)width * height * nc);
+    int32_t rx = width, ry = height;
+    if (((uint32_t)rx & ((uint32_t)rx - 1)) || ((uint32_t)ry & ((uint32_t)ry - 1))) {                    // float_resize_up
+        const int32_t nx = (int32_t)orc_next_pow2((uint32_t)rx), ny = (int32_t)orc_next_pow2((uint32_t)ry);
+        // the reference asserts new_res > resolution in BOTH dimensions (image.rs:1009-1010)
+        const std::vector<OrcResampleWeight> xw = orc_resample_weights(rx, nx), yw = orc_resample_weights(ry, ny);
+        auto texel = [&](int32_t x, int32_t y, int c) -> Float {                                          // copy_rect_out + remap_pixel_coords (:134-177)
+            int32_t p[2] = {x, y}; const int32_t res[2] = {rx, ry};
+            for (int k = 0; k < 2; ++k) {
+                if (p[k] >= 0 && p[k] < res[k]) continue;
+                if (wrap == SG_WRAP_CLAMP) p[k] = p[k] < 0 ? 0 : res[k] - 1;
+                else { int32_t r = p[k] - (p[k] / res[k]) * res[k]; p[k] = r < 0 ? r + res[k] : r; }        // repeat (black panics in the reference)
+            }
+            return cur[((size_t)p[1] * rx + p[0]) * nc + c];
+        };
+        std::vector<float> rs((size_t)nx * ny * nc);
+        for (int32_t y = 0; y < ny; ++y) for (int32_t x = 0; x < nx; ++x) for (int c = 0; c < nc; ++c) {
+            const OrcResampleWeight& wx = xw[x]; const OrcResampleWeight& wy = yw[y];
+            Float col[4];
+            for (int j = 0; j < 4; ++j) {
+                const int32_t yy = wy.first_pixel + j;
+                col[j] = wx.weight[0] * texel(wx.first_pixel, yy, c) + wx.weight[1] * texel(wx.first_pixel + 1, yy, c) +
+                         wx.weight[2] * texel(wx.first_pixel + 2, yy, c) + wx.weight[3] * texel(wx.first_pixel + 3, yy, c);
+            }
+            rs[((size_t)y * nx + x) * nc + c] = fmax_(0.0f, wy.weight[0] * col[0] + wy.weight[1] * col[1] + wy.weight[2] * col[2] + wy.weight[3] * col[3]);
+        }
+        cur.swap(rs); rx = nx; ry = ny;
+    }
+    const int32_t n_levels = 1 + (int32_t)std::log2((Float)std::max(rx, ry));
+    size_t off = 0;
+    for (int32_t l = 0; l < n_levels; ++l) {
+        std::memcpy(out + off, cur.data(), cur.size() * sizeof(float)); off += cur.size();
+        if (l == n_levels - 1) break;
+        const int32_t nx = std::max(1, (rx + 1) / 2), ny = std::max(1, (ry + 1) / 2);
+        std::vector<float> nxt((size_t)nx * ny * nc);
+        const size_t d1 = rx == 1 ? 0 : (size_t)nc, d2 = ry == 1 ? 0 : (size_t)nc * rx;                   // src_deltas :737-753
+        for (int32_t y = 0; y < ny; ++y) for (int32_t x = 0; x < nx; ++x) for (int c = 0; c < nc; ++c) {
+            const size_t src = ((size_t)(2 * y) * rx + 2 * x) * nc + c;
+            nxt[((size_t)y * nx + x) * nc + c] = 0.25f * (cur[src] + cur[src + d1] + cur[src + d2] + cur[src + d1 + d2]);
+        }
+        cur.swap(nxt); rx = nx; ry = ny;
+    }
+    return n_levels;
 }
 void orc_approximate_dp_dxy(const SgSceneDesc* d, const float* p, const float* n, int spp, uint32_t option_flags, float* out6) {
     V3 dpdx, dpdy;

@@ -8,4 +8,4 @@ Layout (only what the hot path needs):
   integrator.py  mirror of the reference's Integrator API (`create_integrator`, `.render(options)`)
 """
 from .ffi import ShimmerGpuError  # noqa: F401
-from .integrator import Options, WavefrontPathIntegrator, create_integrator, render_gpu  # noqa: F401
+from .integrator import Options, WavefrontPathIntegrator, create_integrator, generate_pyramid, render_gpu  # noqa: F401

@@ -3,6 +3,8 @@
 // stream with device-side queue counters (no host sync inside a batch), film readback.
 // There is NO CPU fallback: every entry point either runs the sm_100a kernels or fails.
 #include "sg_kernels.h"
+#include "sg_image.cuh"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -830,6 +832,64 @@ int sg_film_get_image(SgScene* s, const SgFilmPixel* film, int32_t w, int32_t h,
     k_film_image<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(s->d, d_f, w, h, flags, d_o);
     CUX(cudaStreamSynchronize(g_stream));
     CUX(cudaMemcpy(out_rgb, d_o, n * 12, cudaMemcpyDeviceToHost));
+#undef CUX
+    cleanup();
+    return SG_OK;
+}
+
+static uint32_t next_pow2_u32(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+static bool is_pow2_u32(uint32_t v) { return v && !(v & (v - 1)); }
+
+int sg_image_pyramid_layout(int32_t width, int32_t height, int32_t nc, int32_t* n_levels, SgImageLevel* levels, uint64_t* n_texels) {
+    if (width < 1 || height < 1 || nc < 1 || nc > 4 || !n_levels || !n_texels) return fail(SG_ERR_INVALID_ARGUMENT, "sg_image_pyramid_layout: bad arguments");
+    uint32_t w = (uint32_t)width, h = (uint32_t)height;
+    if (!is_pow2_u32(w) || !is_pow2_u32(h)) {
+        const uint32_t nw = next_pow2_u32(w), nh = next_pow2_u32(h);
+        if (!(nw > w && nh > h)) return fail(SG_ERR_UNSUPPORTED, "float_resize_up needs both dimensions to grow (image.rs:1009-1010 asserts)");
+        w = nw; h = nh;
+    }
+    const int32_t n = 1 + (int32_t)std::log2((float)std::max(w, h));                                // image.rs:719
+    if (n > 32) return fail(SG_ERR_UNSUPPORTED, "image too large");
+    uint64_t off = 0; int32_t rx = (int32_t)w, ry = (int32_t)h;
+    for (int32_t l = 0; l < n; ++l) {
+        if (levels) { levels[l].offset = (uint32_t)off; levels[l].res[0] = rx; levels[l].res[1] = ry; levels[l].pad = 0; }
+        off += (uint64_t)rx * ry * nc;
+        rx = std::max(1, (rx + 1) / 2); ry = std::max(1, (ry + 1) / 2);
+    }
+    if (off >= (1ull << 32)) return fail(SG_ERR_UNSUPPORTED, "pyramid exceeds the 32-bit texel offsets of SgImageLevel");
+    *n_levels = n; *n_texels = off;
+    return SG_OK;
+}
+
+int sg_image_generate_pyramid(const float* image, int32_t width, int32_t height, int32_t nc, int32_t wrap, float* out_texels) {
+    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!image || !out_texels) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    if (wrap != SG_WRAP_REPEAT && wrap != SG_WRAP_CLAMP) return fail(SG_ERR_UNSUPPORTED, "pyramid construction supports the repeat and clamp wrap modes (image.rs:826-828 asserts on black)");
+    int32_t n_levels = 0; uint64_t n_texels = 0; SgImageLevel levels[32];
+    int rc = sg_image_pyramid_layout(width, height, nc, &n_levels, levels, &n_texels);
+    if (rc != SG_OK) return rc;
+    float *d_in = nullptr, *d_out = nullptr; ResampleWeight *d_xw = nullptr, *d_yw = nullptr;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_xw); cudaFree(d_yw); };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(e__ == cudaErrorMemoryAllocation ? SG_ERR_OUT_OF_MEMORY : SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    const size_t n_in = (size_t)width * height * nc;
+    CUX(cudaMalloc((void**)&d_in, n_in * 4)); CUX(cudaMalloc((void**)&d_out, n_texels * 4));
+    CUX(cudaMemcpyAsync(d_in, image, n_in * 4, cudaMemcpyHostToDevice, g_stream));
+    const int rx0 = levels[0].res[0], ry0 = levels[0].res[1];
+    if (rx0 != width || ry0 != height) {                                                              // float_resize_up
+        CUX(cudaMalloc((void**)&d_xw, (size_t)rx0 * sizeof(ResampleWeight))); CUX(cudaMalloc((void**)&d_yw, (size_t)ry0 * sizeof(ResampleWeight)));
+        k_resample_weights<<<(rx0 + 127) / 128, 128, 0, g_stream>>>(width, rx0, d_xw);
+        k_resample_weights<<<(ry0 + 127) / 128, 128, 0, g_stream>>>(height, ry0, d_yw);
+        const long long n0 = (long long)rx0 * ry0 * nc;
+        k_resize_up<<<(unsigned)((n0 + 255) / 256), 256, 0, g_stream>>>(d_in, width, height, nc, wrap, d_xw, d_yw, rx0, ry0, d_out);
+    } else CUX(cudaMemcpyAsync(d_out, d_in, n_in * 4, cudaMemcpyDeviceToDevice, g_stream));
+    for (int32_t l = 0; l + 1 < n_levels; ++l) {
+        const long long nn = (long long)levels[l + 1].res[0] * levels[l + 1].res[1] * nc;
+        k_downsample<<<(unsigned)((nn + 255) / 256), 256, 0, g_stream>>>(d_out + levels[l].offset, levels[l].res[0], levels[l].res[1], nc,
+                                                                          levels[l + 1].res[0], levels[l + 1].res[1], d_out + levels[l + 1].offset);
+    }
+    CUX(cudaGetLastError());
+    CUX(cudaMemcpyAsync(out_texels, d_out, n_texels * 4, cudaMemcpyDeviceToHost, g_stream));
+    CUX(cudaStreamSynchronize(g_stream));
 #undef CUX
     cleanup();
     return SG_OK;

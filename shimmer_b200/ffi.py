@@ -191,7 +191,8 @@ class SgHit(C.Structure):
 # every symbol include/shimmer_gpu.h declares; tests/test_abi.py checks the library exports all
 ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
                "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
-               "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_film_get_image"]
+               "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_film_get_image", "sg_image_pyramid_layout",
+               "sg_image_generate_pyramid"]
 
 
 class ShimmerGpuError(RuntimeError):
@@ -233,6 +234,8 @@ def load_library():
     lib.sg_film_get_image.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, vp]; lib.sg_film_get_image.restype = C.c_int
     lib.sg_texture_eval.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp]; lib.sg_texture_eval.restype = C.c_int
     lib.sg_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp, vp]; lib.sg_texture_eval_p.restype = C.c_int
+    lib.sg_image_pyramid_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]; lib.sg_image_pyramid_layout.restype = C.c_int
+    lib.sg_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; lib.sg_image_generate_pyramid.restype = C.c_int
     _lib = lib
     return lib
 

@@ -325,18 +325,23 @@ class SceneBuilder:
         return len(self.spectra) - 1
 
     def image_texture(self, image, filter="bilinear", wrap="repeat", max_anisotropy=8.0, scale=1.0, invert=False,
-                      su=1.0, sv=1.0, du=0.0, dv=0.0, spectrum_type="albedo", mapping=None):
+                      su=1.0, sv=1.0, du=0.0, dv=0.0, spectrum_type="albedo", mapping=None, levels=None):
         """ImageTextureBase::new (texture.rs:283-330) + MIPMap::new -> Image::generate_pyramid (image.rs:699-787).
         `image`: H x W (one channel) or H x W x 3 array of LINEAR values, row 0 = top of the image (what
         Image::get_channel returns after colour decoding).  Power-of-two sizes only: the reference first
         resamples other sizes with a Lanczos filter (image.rs float_resize_up), which this host stand-in omits."""
-        img = np.asarray(image, dtype=np.float32)
-        if img.ndim == 2:
-            img = img[:, :, None]
+        if levels is not None:                   # a finished pyramid, e.g. from shimmer_b200.generate_pyramid (sg_image_generate_pyramid)
+            levels = [np.ascontiguousarray(l, np.float32).reshape(l.shape[0], l.shape[1], -1) for l in levels]
+            img = levels[0]
+        else:
+            img = np.asarray(image, dtype=np.float32)
+            if img.ndim == 2:
+                img = img[:, :, None]
         H, W, Cn = img.shape
-        if Cn not in (1, 3) or (W & (W - 1)) or (H & (H - 1)):
-            raise ValueError("image textures must be one- or three-channel with power-of-two resolution")
-        levels = [img]
+        if Cn not in (1, 3) or (levels is None and ((W & (W - 1)) or (H & (H - 1)))):
+            raise ValueError("image textures must be one- or three-channel; other resolutions than powers of two need levels= "
+                             "(shimmer_b200.generate_pyramid resamples them on the device like image.rs float_resize_up)")
+        levels = [img] if levels is None else levels
         while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:           # 2x2 box filter, image.rs:733-768
             a = levels[-1]
             h, w = a.shape[:2]

@@ -215,6 +215,23 @@ def sampler_fill(seed, n, pixel_index=0, sample_index=0, raw=False, device=0):
     return out
 
 
+def generate_pyramid(image, wrap="repeat", device=0):
+    """`Image::generate_pyramid` on the device (image.rs:699-787, incl. the resize of non-power-of-two images): `image` is an
+    (H, W) or (H, W, C) array of LINEAR values; returns the list of (h, w, C) f32 levels, level 0 first -- what
+    SceneBuilder.image_texture(levels=...) takes."""
+    lib = _ensure_init(device)
+    img = np.ascontiguousarray(image, np.float32)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    h, w, c = img.shape
+    n_levels = C.c_int32(); n_texels = C.c_uint64(); rows = (ffi.SgImageLevel * 32)()
+    ffi.check(lib.sg_image_pyramid_layout(w, h, c, C.byref(n_levels), rows, C.byref(n_texels)), "sg_image_pyramid_layout")
+    out = np.zeros(n_texels.value, np.float32)
+    ffi.check(lib.sg_image_generate_pyramid(img.ctypes.data, w, h, c, {"repeat": ffi.SG_WRAP_REPEAT, "clamp": ffi.SG_WRAP_CLAMP, "black": ffi.SG_WRAP_BLACK}[wrap],
+                                            out.ctypes.data), "sg_image_generate_pyramid")
+    return [out[r.offset:r.offset + r.res[0] * r.res[1] * c].reshape(r.res[1], r.res[0], c).copy() for r in rows[:n_levels.value]]
+
+
 def create_integrator(name, parameters, scene, sampler=None, device=0, **kw):
     """integrator.rs:16-42 with the GPU entry added.  "path" stays the CPU integrator inside
     shimmer; here only the GPU backend exists, so any other name raises (the reference panics

@@ -65,6 +65,8 @@ def lib():
     L.orc_rgb2spec_fetch.argtypes = [vp, vp, vp]
     L.orc_texture_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
     L.orc_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp]
+    L.orc_image_pyramid_levels.argtypes = [C.c_int32, C.c_int32, vp]; L.orc_image_pyramid_levels.restype = C.c_int32
+    L.orc_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; L.orc_image_generate_pyramid.restype = C.c_int32
     L.orc_approximate_dp_dxy.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp]
     _lib = L
     return L
@@ -152,3 +154,20 @@ def texture_eval_p(scene, tex, p, q=None, dpdx=None, dpdy=None, lambda4=None, as
     out = np.zeros((n, 4), np.float32)
     lib().orc_texture_eval_p(scene.ptr(), int(tex), 1 if as_float else 0, n, q.ctypes.data, pdp.ctypes.data, lam.ctypes.data, out.ctypes.data)
     return out
+
+
+def generate_pyramid(image, wrap="repeat"):
+    """Image::generate_pyramid (image.rs:699-787) incl. the resize of non-power-of-two images -> list of (H, W, C) f32 levels."""
+    img = fa(image)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    h, w, c = img.shape
+    res = np.zeros(64, np.int32)
+    n = lib().orc_image_pyramid_levels(w, h, res.ctypes.data)
+    sizes = [(int(res[2 * l + 1]), int(res[2 * l])) for l in range(n)]
+    out = np.zeros(sum(a * b for a, b in sizes) * c, np.float32)
+    lib().orc_image_generate_pyramid(img.ctypes.data, w, h, c, {"repeat": 0, "black": 1, "clamp": 2}[wrap], out.ctypes.data)
+    levels, off = [], 0
+    for a, b in sizes:
+        levels.append(out[off:off + a * b * c].reshape(a, b, c).copy()); off += a * b * c
+    return levels

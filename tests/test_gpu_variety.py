@@ -9,7 +9,7 @@ import pytest
 
 import orc
 from shimmer_b200 import Options, create_integrator, scenes
-from shimmer_b200.host import SceneBuilder, Transform
+from shimmer_b200.host import SceneBuilder, Transform, named_spectrum as host_named
 from test_gpu_parity import _film_close
 
 pytestmark = pytest.mark.gpu
@@ -125,3 +125,51 @@ def test_invalid_variety_inputs_are_rejected():
     sc = scenes.tiny_scene("diffuse", resolution=(8, 8)).build()
     with pytest.raises(ShimmerGpuError, match="Unknown integrator"):
         create_integrator("wavefront", {"integrator": "bdpt"}, sc)
+
+
+@pytest.mark.parametrize("shape,wrap", [((64, 64, 3), "repeat"), ((32, 128, 1), "clamp"), ((37, 50, 3), "repeat"), ((100, 37, 1), "clamp"),
+                                        ((5, 3, 3), "repeat"), ((1, 1, 3), "repeat"), ((300, 500, 3), "clamp")])
+def test_device_mip_pyramid_matches_generate_pyramid(shape, wrap):
+    """sg_image_generate_pyramid vs the oracle's Image::generate_pyramid (image.rs:699-787) + float_resize_up (:1007-1111).  The 2x2
+    box-filter levels are pure IEEE adds: bit-exact given the same level 0; the resize weights go through sinf (different libms)."""
+    from shimmer_b200 import generate_pyramid
+    rng = np.random.default_rng(7)
+    img = rng.random(shape).astype(np.float32) ** 2
+    got = generate_pyramid(img, wrap)
+    exp = orc.generate_pyramid(img, wrap)
+    assert [g.shape for g in got] == [e.shape for e in exp] and got[-1].shape[:2] == (1, 1)
+    pow2 = all((s & (s - 1)) == 0 for s in shape[:2])
+    if pow2:
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+        assert np.array_equal(got[0], img.reshape(got[0].shape))
+    else:
+        for g, e in zip(got, exp):
+            assert np.allclose(g, e, rtol=2e-6, atol=2e-7)
+        # the box-filter chain itself is exact: rebuild it from the device's own level 0
+        for l in range(len(got) - 1):
+            a = got[l]; h, w = a.shape[:2]
+            y0 = np.arange(0, h, 2); x0 = np.arange(0, w, 2); y1 = y0 + (1 if h > 1 else 0); x1 = x0 + (1 if w > 1 else 0)
+            nxt = np.float32(0.25) * (((a[y0][:, x0] + a[y0][:, x1]) + a[y1][:, x0]) + a[y1][:, x1])
+            assert np.array_equal(nxt.astype(np.float32), got[l + 1])
+
+
+def test_device_pyramid_feeds_a_texture_and_rejects_what_the_reference_asserts_on():
+    from shimmer_b200 import generate_pyramid, ShimmerGpuError
+    img = scenes.procedural_image(64, 3)[:50, :37].copy()                   # 37 x 50: not a power of two
+    levels = generate_pyramid(img, "repeat")
+    b = SceneBuilder(); b.set_camera((0, 1.0, -3), (0, 0.5, 0), (0, 1, 0), 45.0, (16, 16))
+    tex = b.image_texture(None, filter="trilinear", levels=levels)
+    gp, gi = scenes._quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, b.diffuse(scenes._white(), reflectance_tex=tex), uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    lp, li = scenes._quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
+    b.add_mesh(lp, li, b.diffuse(scenes._white()), area_light=dict(L=host_named("stdillum-D65"), scale=30.0, two_sided=False))
+    sc = b.build()
+    integ = create_integrator("wavefront", {}, sc, {"pixelsamples": 4, "seed": 2})
+    film = integ.render(Options()).copy()
+    ref, _, _ = orc.render(sc, orc.make_params(seed=2, spp=4))
+    _film_close(film, ref, frac=0.99)
+    integ.close()
+    with pytest.raises(ShimmerGpuError, match="both dimensions"):
+        generate_pyramid(np.zeros((50, 64, 3), np.float32))                 # 64 is already a power of two: image.rs:1009 asserts
+    with pytest.raises(ShimmerGpuError, match="repeat and clamp"):
+        generate_pyramid(np.zeros((5, 3, 3), np.float32), "black")

@@ -258,3 +258,24 @@ def test_variety_scene_golden_film(kind):
     film, st, _ = orc.render(sc, orc.make_params(seed=5, spp=4))
     assert st.closest_hit_rays == gold["closest_hit_rays"] and st.shadow_rays == gold["shadow_rays"]
     assert np.allclose(film.sum(axis=0), gold["film_sum"], rtol=1e-9) and np.isfinite(film).all()
+
+
+def test_generate_pyramid_oracle_properties():
+    """Image::generate_pyramid (image.rs:699-787): power-of-two images keep level 0, every level is the 2x2 mean of the one below
+    (odd sizes never occur after the resize), the last level is 1x1; resample_weights as written gives four equal taps, so the
+    resized image is a 4x4 box average: a constant image stays constant and the mean is preserved to rounding."""
+    img = scenes.procedural_image(32, 3)
+    lv = orc.generate_pyramid(img)
+    assert len(lv) == 6 and np.array_equal(lv[0], img) and lv[-1].shape == (1, 1, 3)
+    assert np.allclose(lv[-1].ravel(), img.reshape(-1, 3).mean(axis=0), rtol=1e-5)
+    odd = np.full((37, 50, 1), 0.3, np.float32)
+    lo = orc.generate_pyramid(odd, "clamp")
+    assert [l.shape for l in lo][:2] == [(64, 64, 1), (32, 32, 1)] and np.allclose(lo[0], 0.3, rtol=1e-6)
+    rng = np.random.default_rng(2)
+    r = rng.random((20, 9, 3)).astype(np.float32)
+    lr = orc.generate_pyramid(r, "repeat")
+    assert lr[0].shape == (32, 16, 3) and (lr[0] >= 0).all() and abs(lr[0].mean() - r.mean()) < 0.03
+    from shimmer_b200.host import SceneBuilder
+    b = SceneBuilder(); b.set_camera((0, 0, -3), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+    t = b.image_texture(None, levels=lr)
+    assert b.textures[t]["n_channels"] == 3 and len(b.textures[t]["levels"]) == 6
