@@ -35,7 +35,16 @@ struct PathCtx {
     const Scene* sc;
     const SgRenderParams* rp;
     Counters* ctr;
+    std::vector<float>* ray_log = nullptr;     // debug (orc_path_rays): o, d, t_max, any_hit, hit prim, hit t per traced ray
 };
+static inline bool logged_intersect(const PathCtx& pc, const Ray& ray, Float t_max, bool any_hit, Hit* hit) {
+    const bool found = bvh_intersect(*pc.sc, ray, t_max, any_hit, hit, pc.ctr);
+    if (pc.ray_log) {
+        const float rec[10] = {ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, t_max, any_hit ? 1.0f : 0.0f, found ? (float)hit->prim : -1.0f, found ? hit->th.t : 0.0f};
+        pc.ray_log->insert(pc.ray_log->end(), rec, rec + 10);
+    }
+    return found;
+}
 
 // PathIntegrator::sample_ld integrator.rs:897-963
 // Seed for the LayeredBxDF's private generator (the reference uses from_entropy, bxdf.rs:1011): derived from the
@@ -71,7 +80,7 @@ static Spec sample_ld(const PathCtx& pc, const SurfaceInteraction& intr, BSDF& b
     Ray sray = spawn_ray_to_both_offset(intr.pi, intr.n, ls.p_light, ls.n_light);   // IntegratorBase::unoccluded :114-116
     Hit h;
     if (pc.ctr) pc.ctr->shadow++;
-    if (bvh_intersect(*pc.sc, sray, 1.0f - 0.0001f, true, &h, pc.ctr)) return spec_const(0.0f);
+    if (logged_intersect(pc, sray, 1.0f - 0.0001f, true, &h)) return spec_const(0.0f);
     Float p_l = p_choose * ls.pdf;
     if (lt.kind == SG_LIGHT_POINT) return ls.l * f / p_l;
     bsdf.layer_seed = layer_seed(rng, 2);
@@ -91,7 +100,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
     for (;;) {
         Hit hit;
         if (pc.ctr) pc.ctr->closest++;
-        bool found = bvh_intersect(*pc.sc, ray, F_INF, false, &hit, pc.ctr);
+        bool found = logged_intersect(pc, ray, F_INF, false, &hit);
         if (!found) {
             for (uint32_t i = 0; i < D->n_lights; ++i) {                          // :779-792
                 const SgLight& lt = D->lights[i];
@@ -158,21 +167,23 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
 static SurfaceInteraction hit_interaction(const Scene& sc, const Hit& hit, const Ray& ray) {
     const SgSceneDesc* D = sc.d;
     const SgPrimitive& prim = D->primitives[hit.prim];
+    // TransformedPrimitive::intersect (primitive.rs:155-169): the shape is intersected with the instance-space ray, so its
+    // interaction is built there (wo = -(M^-1 d)) and then mapped to render space with Transform::apply(SurfaceInteraction)
+    V3 d = ray.d;
+    if (hit.inst >= 0) {
+        const float* mi = D->instances[hit.inst].primitive_from_render;
+        d = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
+               mi[8] * ray.d.x + mi[9] * ray.d.y + mi[10] * ray.d.z);
+    }
     SurfaceInteraction si;
-    if (prim.mesh == SG_PRIM_SPHERE) {
+    if (prim.mesh == SG_PRIM_SPHERE) {                                         // Sphere::intersect sphere.rs:286-293
         V3 p_obj = v3(hit.th.b0, hit.th.b1, hit.th.b2);
         Float phi = std::atan2(p_obj.y, p_obj.x); if (phi < 0.0f) phi += 2.0f * PI_F;
-        si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -ray.d);
-    } else if (D->meshes[prim.mesh].flags & SG_MESH_BILINEAR) {
-        si = patch_interaction(sc, prim.mesh, prim.tri, hit.th.b0, hit.th.b1, -ray.d);
-    } else if (hit.inst >= 0) {
-        const SgInstance& I = D->instances[hit.inst];
-        const float* mi = I.primitive_from_render;
-        V3 d2 = v3(mi[0] * ray.d.x + mi[1] * ray.d.y + mi[2] * ray.d.z, mi[4] * ray.d.x + mi[5] * ray.d.y + mi[6] * ray.d.z,
-                   mi[8] * ray.d.x + mi[9] * ray.d.y + mi[10] * ray.d.z);
-        si = interaction_from_intersection(sc, prim.mesh, prim.tri, hit.th, -d2);
-        transform_interaction(D, I, si);
-    } else si = interaction_from_intersection(sc, prim.mesh, prim.tri, hit.th, -ray.d);
+        si = sphere_interaction(D, D->spheres[prim.tri], p_obj, phi, -d);
+    } else if (D->meshes[prim.mesh].flags & SG_MESH_BILINEAR) {                 // BilinearPatch::intersect bilinear_patch.rs:496-509
+        si = patch_interaction(sc, prim.mesh, prim.tri, hit.th.b0, hit.th.b1, -d);
+    } else si = interaction_from_intersection(sc, prim.mesh, prim.tri, hit.th, -d);   // triangle.rs:529-535
+    if (hit.inst >= 0) transform_interaction(D, D->instances[hit.inst], si);
     si.material = (int32_t)prim.material; si.light = prim.light;
     return si;
 }
@@ -677,6 +688,19 @@ int32_t orc_image_generate_pyramid(const float* image, int32_t width, int32_t he
         cur.swap(nxt); rx = nx; ry = ny;
     }
     return n_levels;
+}
+// debug: every ray the path integrator traces for one (pixel, sample): 10 floats per ray (see PathCtx::ray_log); returns the count
+int64_t orc_path_rays(const SgSceneDesc* desc, const SgRenderParams* rp, int px, int py, int sample, int64_t max_rays, float* out) {
+    Scene sc(desc);
+    std::vector<float> log;
+    PathCtx pc{&sc, rp, nullptr, &log};
+    Rng rng; rng.seed_from_u64(stream_key(rp->seed, (uint32_t)(py * desc->film.full_resolution[0] + px), (uint32_t)sample));
+    std::vector<SgFilmPixel> film((size_t)(desc->film.pixel_bounds[2] - desc->film.pixel_bounds[0]) * (desc->film.pixel_bounds[3] - desc->film.pixel_bounds[1]));
+    std::memset(film.data(), 0, film.size() * sizeof(SgFilmPixel));
+    eval_sample(pc, px, py, rng, film.data());
+    const int64_t n = std::min<int64_t>((int64_t)log.size() / 10, max_rays);
+    std::memcpy(out, log.data(), (size_t)n * 10 * sizeof(float));
+    return n;
 }
 void orc_approximate_dp_dxy(const SgSceneDesc* d, const float* p, const float* n, int spp, uint32_t option_flags, float* out6) {
     V3 dpdx, dpdy;

@@ -322,18 +322,20 @@ template <> SGD void surf_tex_store<true>(SurfTex* x, float2 uv, float3 dpdu, fl
     x->dudx = x->dudy = x->dvdx = x->dvdy = 0.0f; x->dpdx = f3(0.0f, 0.0f, 0.0f); x->dpdy = f3(0.0f, 0.0f, 0.0f);
 }
 
-// Transform::apply(SurfaceInteraction) (transform.rs:573-609) for a hit inside an object instance.  `s` / `x` were built
-// in the instance's space with wo = -(M^-1 d).  The reference maps vectors through M^-1 and normals through M^T
+// Transform::apply(SurfaceInteraction) (transform.rs:573-609) for a hit inside an object instance (or a sphere's own
+// object space).  `s` / `x` were built in that space; `rd` is the ray direction of the ENCLOSING space, so the interaction's
+// wo is -(M^-1 rd) -- unless `wo_in` is given (nested case: a sphere / patch inside an instance already has its wo).  The reference maps vectors through M^-1 and normals through M^T
 // (`t = self.inverse()`); with SG_SCENE_FIX_INSTANCING vectors go through M and normals through (M^-1)^T.  pi: forward
 // Point3fi transform of an inexact point (:385-457).  Returns interaction.wo in `wo_si`.
 template <bool TEX>
-__device__ __noinline__ void transform_interaction(const DScene& sc, const float* M, const float* Mi, float3 rd, Surf& s, SurfTex* x, float3& wo_si) {
+__device__ __noinline__ void transform_interaction(const DScene& sc, const float* M, const float* Mi, float3 rd, Surf& s, SurfTex* x, float3& wo_si,
+                                                   const float3* wo_in = nullptr) {
     const bool fix = (sc.scene_flags & SG_SCENE_FIX_INSTANCING) != 0;
     const float* mv = fix ? M : Mi; const float* mn = fix ? Mi : M;
     auto vec = [&](float3 v) { return f3(mv[0] * v.x + mv[1] * v.y + mv[2] * v.z, mv[4] * v.x + mv[5] * v.y + mv[6] * v.z, mv[8] * v.x + mv[9] * v.y + mv[10] * v.z); };
     auto nrm = [&](float3 n) { return f3(mn[0] * n.x + mn[4] * n.y + mn[8] * n.z, mn[1] * n.x + mn[5] * n.y + mn[9] * n.z, mn[2] * n.x + mn[6] * n.y + mn[10] * n.z); };
     const float3 d2 = f3(Mi[0] * rd.x + Mi[1] * rd.y + Mi[2] * rd.z, Mi[4] * rd.x + Mi[5] * rd.y + Mi[6] * rd.z, Mi[8] * rd.x + Mi[9] * rd.y + Mi[10] * rd.z);
-    wo_si = normalize3(vec(-d2));
+    wo_si = normalize3(vec(wo_in ? *wo_in : -d2));
     const float3 p = p3fi_mid(s.pi), e = p3fi_err(s.pi);
     const bool exact = s.pi.lo.x == s.pi.hi.x && s.pi.lo.y == s.pi.hi.y && s.pi.lo.z == s.pi.hi.z;
     float pp[3], ee[3];

@@ -262,16 +262,19 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
         float b0, b1, b2, t;
         bool hit_prim;
         if (INST && (__float_as_uint(v2.w) & kSphereBit)) {
-            // Shape::Sphere (top level only): works on the render-space ray, re-read through `io`; the hit record carries p_obj
+            // Shape::Sphere: works on the current space's ray (the render-space ray re-read through `io`, moved into the instance
+            // when the lane is inside one); the hit record carries p_obj
             float3 o, d; float tm;
             io.load(idx, o, d, tm);
+            if (L.inst >= 0) instance_ray(ts.instances[L.inst], !ANY || (ts.scene_flags & SG_SCENE_FIX_INSTANCING) != 0, o, d, tm);
             float3 p_obj;
             hit_prim = sphere_basic_intersect(ts.spheres[__float_as_uint(v2.w) & ~(kSphereBit | kLastInLeaf)], o, d, L.t_max, p_obj, t);
             b0 = p_obj.x; b1 = p_obj.y; b2 = p_obj.z;
         } else if (INST && (__float_as_uint(v2.w) & kPatchBit)) {
-            // Shape::BilinearPatch (top level only): hit record carries (u, v)
+            // Shape::BilinearPatch: hit record carries (u, v)
             float3 o, d; float tm;
             io.load(idx, o, d, tm);
+            if (L.inst >= 0) instance_ray(ts.instances[L.inst], !ANY || (ts.scene_flags & SG_SCENE_FIX_INSTANCING) != 0, o, d, tm);
             const float4* pv = ts.patch_verts + 4 * (size_t)(__float_as_uint(v2.w) & ~(kPatchBit | kLastInLeaf));
             const float4 a0 = __ldg(pv), a1 = __ldg(pv + 1), a2 = __ldg(pv + 2), a3 = __ldg(pv + 3);
             hit_prim = intersect_blp(o, d, L.t_max, f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), f3(a3.x, a3.y, a3.z), b0, b1, t);

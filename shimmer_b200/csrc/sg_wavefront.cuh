@@ -426,12 +426,20 @@ SGD uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s0 ^ (
 template <bool TEX>
 __device__ __noinline__ Surf surface_general(const DScene& sc, const TriGeo& geo, float4 hb, float3 rd, int inst, SurfTex* sx, float3& wo_si) {
     Surf s;
+    // inside an instance the shape was intersected with the instance-space ray (primitive.rs:155-169)
+    float3 rdi = rd;
+    if (inst >= 0 && (geo.mesh & (kSphereBit | kPatchBit))) {
+        const float* Mi = sc.instances[inst].mi;
+        rdi = f3(Mi[0] * rd.x + Mi[1] * rd.y + Mi[2] * rd.z, Mi[4] * rd.x + Mi[5] * rd.y + Mi[6] * rd.z, Mi[8] * rd.x + Mi[9] * rd.y + Mi[10] * rd.z);
+    }
     if (geo.mesh & kSphereBit) {
         const DSphere& S = sc.spheres[geo.mesh & ~kSphereBit];
         s = make_surface_sphere<TEX>(S, f3(hb.x, hb.y, hb.z), sx);
-        transform_interaction<TEX>(sc, S.m, S.mi, rd, s, sx, wo_si);
+        transform_interaction<TEX>(sc, S.m, S.mi, rdi, s, sx, wo_si);
+        if (inst >= 0) { const float3 w1 = wo_si; transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, sx, wo_si, &w1); }
     } else if (geo.mesh & kPatchBit) {
         s = make_surface_patch<TEX>(sc, geo.mesh & ~kPatchBit, hb.x, hb.y, sx);
+        if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, sx, wo_si);
     } else {
         s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, sx);
         if (inst >= 0) transform_interaction<TEX>(sc, sc.instances[inst].m, sc.instances[inst].mi, rd, s, sx, wo_si);

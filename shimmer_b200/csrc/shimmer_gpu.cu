@@ -167,7 +167,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             continue;
         }
         if (p.mesh == SG_PRIM_SPHERE) {
-            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "spheres inside object definitions are not on the GPU path yet");
+            if (i >= n_top_prims && p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights inside object definitions are not supported (pbrt-v4 scene format)");
             if (p.tri >= desc->n_spheres || p.material >= desc->n_materials) return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references an out-of-range sphere/material");
             if (p.light >= (int32_t)desc->n_lights || (p.light >= 0 && (desc->lights[p.light].kind != SG_LIGHT_DIFFUSE_AREA_SPHERE || desc->lights[p.light].tri != p.tri)))
                 return fail(SG_ERR_INVALID_ARGUMENT, "an emissive sphere must point at an SG_LIGHT_DIFFUSE_AREA_SPHERE light over that sphere");
@@ -180,7 +180,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         }
         if (!desc->meshes || !desc->indices || !desc->p) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
         if (p.mesh < desc->n_meshes && (desc->meshes[p.mesh].flags & SG_MESH_BILINEAR)) {
-            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "bilinear patches inside object definitions are not on the GPU path yet");
+            if (i >= n_top_prims && p.light >= 0) return fail(SG_ERR_UNSUPPORTED, "area lights inside object definitions are not supported (pbrt-v4 scene format)");
             if (p.light >= (int32_t)desc->n_lights || (p.light >= 0 && (desc->lights[p.light].kind != SG_LIGHT_DIFFUSE_AREA_PATCH || desc->lights[p.light].mesh != p.mesh ||
                                                                      desc->lights[p.light].tri != p.tri)))
                 return fail(SG_ERR_INVALID_ARGUMENT, "an emissive bilinear patch must point at an SG_LIGHT_DIFFUSE_AREA_PATCH light over that patch");

@@ -564,7 +564,8 @@ class SceneBuilder:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
 
-    def add_bilinear_mesh(self, p, indices, material, n=None, uv=None, reverse_orientation=False, object_from_world=None, area_light=None):
+    def add_bilinear_mesh(self, p, indices, material, n=None, uv=None, reverse_orientation=False, object_from_world=None, area_light=None,
+                          object=None):
         """Shape "bilinearmesh": BilinearPatchMesh::new (shape/mesh.rs:111-175) + one BilinearPatch per four indices
         (p00, p10, p01, p11; bilinear_patch.rs:77-106).  Top-level patches only.  `area_light` = dict(L=spectrum tuple, scale=float,
         two_sided=bool) -> one DiffuseAreaLight per patch (scene.rs:609-622)."""
@@ -582,11 +583,13 @@ class SceneBuilder:
         if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
         self.patch_meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 4), n=n,
                                       uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2), flags=flags, material=material,
-                                      area_light=area_light))
+                                      area_light=area_light, object=object))
+        if object is not None and area_light is not None:
+            raise ValueError("area lights are not supported inside object definitions")
         return len(self.patch_meshes) - 1
 
     def add_sphere(self, radius, material, z_min=None, z_max=None, phi_max=360.0, object_from_world=None, reverse_orientation=False,
-                   area_light=None):
+                   area_light=None, object=None):
         """Shape "sphere": Sphere::create / Sphere::new (shape/sphere.rs:48-92).  `object_from_world` is the CTM
         (render_from_object = render_from_world * CTM).  Top-level spheres only.  `area_light` = dict(L=spectrum tuple,
         scale=float, two_sided=bool) -> one DiffuseAreaLight over the sphere (scene.rs:609-622)."""
@@ -601,7 +604,9 @@ class SceneBuilder:
                                  theta_z_min=f32(np.arccos(clamp(zlo / r, f32(-1.0), f32(1.0)))),
                                  theta_z_max=f32(np.arccos(clamp(zhi / r, f32(-1.0), f32(1.0)))),
                                  phi_max=f32(f32(np.pi) / f32(180.0)) * clamp(f32(phi_max), f32(0.0), f32(360.0)),
-                                 flags=flags, material=material, area_light=area_light))
+                                 flags=flags, material=material, area_light=area_light, object=object))
+        if object is not None and area_light is not None:
+            raise ValueError("area lights are not supported inside object definitions")
         return len(self.spheres) - 1
 
     def add_point_light(self, pos, I, scale=1.0):
@@ -802,29 +807,22 @@ class SceneBuilder:
         # object definitions: one BvhAggregate each when they hold more than one primitive (scene.rs:818-830)
         obj_rows = (ffi.SgObject * max(self.n_objects, 1))()
         obj_nodes, obj_prims, obj_root_bounds = [], [], []
+        patch_obj = np.full(n_patches, -1, np.int64)
+        q0 = 0
+        for m in self.patch_meshes:
+            if m.get("object") is not None: patch_obj[q0:q0 + len(m["idx"])] = m["object"]
+            q0 += len(m["idx"])
+        sphere_obj = np.array([-1 if sp.get("object") is None else sp["object"] for sp in self.spheres], np.int64).reshape(-1)
+        pending_objects = []                                 # filled in once sphere rows / bounds exist (below)
         for o in range(self.n_objects):
-            sel = np.nonzero(tri_obj == o)[0]
-            if len(sel) == 0:
-                raise ValueError("empty object definition")
-            if len(sel) > 1:
-                nd, od = build_bvh(bounds[sel])
-                obj_nodes.append(nd); obj_prims.append(prim_in[sel][od])
-                obj_root_bounds.append(np.concatenate([nd[0]["bmin"], nd[0]["bmax"]]))
-            else:
-                obj_nodes.append(np.zeros(0, dtype=np.dtype(ffi.SgBvhNode))); obj_prims.append(prim_in[sel])
-                obj_root_bounds.append(bounds[sel[0]])
+            pending_objects.append(o)
         # top level: shapes first, then one TransformedPrimitive per instance (scene.rs:806,849-866)
         top_sel = np.nonzero(tri_obj < 0)[0]
         inst_rows = (ffi.SgInstance * max(len(self.instances), 1))()
-        inst_bounds = np.empty((len(self.instances), 6), np.float32)
         for ii, (o, xf) in enumerate(self.instances):
             r = inst_rows[ii]
             r.render_from_primitive[:] = xf.m32().ravel().tolist(); r.primitive_from_render[:] = xf.m_inv.astype(np.float32).ravel().tolist()
             r.object = o
-            lo, hi = obj_root_bounds[o][:3], obj_root_bounds[o][3:]
-            corners = np.array([[(hi if (c >> a) & 1 else lo)[a] for a in range(3)] for c in range(8)], np.float32)   # Transform::apply(Bounds3f) transform.rs:557-570
-            pc = xf.apply_points_f32(corners)
-            inst_bounds[ii, :3] = pc.min(axis=0); inst_bounds[ii, 3:] = pc.max(axis=0)
         # spheres: Sphere::bounds (sphere.rs:273-279) = Transform::apply(Bounds3f) of the object-space box (transform.rs:557-570)
         sph_rows = (ffi.SgSphere * max(len(self.spheres), 1))()
         sph_bounds = np.empty((len(self.spheres), 6), np.float32)
@@ -840,15 +838,37 @@ class SceneBuilder:
             pc = sp["rfo"].apply_points_f32(corners)
             sph_bounds[si_, :3] = pc.min(axis=0); sph_bounds[si_, 3:] = pc.max(axis=0)
         A["spheres"] = sph_rows
+        sp_in = np.zeros((len(self.spheres), 4), np.int64)
+        if len(self.spheres):
+            sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]
+            sp_in[:, 3] = [sphere_light.get(i, -1) for i in range(len(self.spheres))]
+        # object definitions: one BvhAggregate each when they hold more than one primitive (scene.rs:818-830); shape order inside a
+        # definition: triangle meshes, bilinear meshes, spheres (the builder's order, as at the top level)
+        for o in pending_objects:
+            sel_t, sel_p, sel_s = np.nonzero(tri_obj == o)[0], np.nonzero(patch_obj == o)[0], np.nonzero(sphere_obj == o)[0]
+            o_prims = np.concatenate([prim_in[sel_t], patch_prim_in[sel_p], sp_in[sel_s]])
+            o_bounds = np.concatenate([bounds[sel_t], patch_bounds[sel_p], sph_bounds[sel_s]])
+            if len(o_prims) == 0:
+                raise ValueError("empty object definition")
+            if len(o_prims) > 1:
+                nd, od = build_bvh(o_bounds)
+                obj_nodes.append(nd); obj_prims.append(o_prims[od])
+                obj_root_bounds.append(np.concatenate([nd[0]["bmin"], nd[0]["bmax"]]))
+            else:
+                obj_nodes.append(np.zeros(0, dtype=np.dtype(ffi.SgBvhNode))); obj_prims.append(o_prims)
+                obj_root_bounds.append(o_bounds[0])
+        inst_bounds = np.empty((len(self.instances), 6), np.float32)
+        for ii, (o, xf) in enumerate(self.instances):
+            lo, hi = obj_root_bounds[o][:3], obj_root_bounds[o][3:]
+            corners = np.array([[(hi if (c >> a) & 1 else lo)[a] for a in range(3)] for c in range(8)], np.float32)   # Transform::apply(Bounds3f) transform.rs:557-570
+            pc = xf.apply_points_f32(corners)
+            inst_bounds[ii, :3] = pc.min(axis=0); inst_bounds[ii, 3:] = pc.max(axis=0)
         top_bounds = bounds[top_sel]
         top_prim_in = prim_in[top_sel]
         if n_patches:
-            top_prim_in = np.concatenate([top_prim_in, patch_prim_in]); top_bounds = np.concatenate([top_bounds, patch_bounds])
+            top_prim_in = np.concatenate([top_prim_in, patch_prim_in[patch_obj < 0]]); top_bounds = np.concatenate([top_bounds, patch_bounds[patch_obj < 0]])
         if len(self.spheres):
-            sp_in = np.zeros((len(self.spheres), 4), np.int64)
-            sp_in[:, 0] = ffi.SG_PRIM_SPHERE; sp_in[:, 1] = np.arange(len(self.spheres)); sp_in[:, 2] = [sp["material"] for sp in self.spheres]
-            sp_in[:, 3] = [sphere_light.get(i, -1) for i in range(len(self.spheres))]
-            top_prim_in = np.concatenate([top_prim_in, sp_in]); top_bounds = np.concatenate([top_bounds, sph_bounds])
+            top_prim_in = np.concatenate([top_prim_in, sp_in[sphere_obj < 0]]); top_bounds = np.concatenate([top_bounds, sph_bounds[sphere_obj < 0]])
         if len(self.instances):
             top_bounds = np.concatenate([top_bounds, inst_bounds])
         if len(self.instances):

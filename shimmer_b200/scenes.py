@@ -371,6 +371,7 @@ def patch_tiny_scene(kind="patches", resolution=(32, 32)):
 
 TEXTURED_KINDS = ("tex", "texewa", "texbump", "texcoated")
 INSTANCED_KINDS = ("inst", "instrot", "instfix", "insttex")
+INSTANCED_SHAPE_KINDS = ("instshapes", "instshapesfix", "instshapestex")     # spheres + bilinear patches inside object definitions
 
 
 def instanced_tiny_scene(kind="inst", resolution=(32, 32), flatten=False):
@@ -415,6 +416,60 @@ def instanced_tiny_scene(kind="inst", resolution=(32, 32), flatten=False):
             b.add_instance(sphere_obj, xf)
         for xf in txf:
             b.add_instance(tri_obj, xf)
+    gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, white, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    lp, li = _quad((-0.6, 2.8, -0.6), (0.6, 2.8, -0.6), (0.6, 2.8, 0.6), (-0.6, 2.8, 0.6))
+    b.add_mesh(lp, li, white, area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b
+
+
+def instanced_shapes_tiny_scene(kind="instshapes", resolution=(32, 32), flatten=False):
+    """Object definitions that hold shapes other than triangles (scene.rs:814-866 accepts any Shape): one definition with a partial
+    sphere (own transform), a twisted bilinear patch and a triangle mesh behind its own BvhAggregate, and a one-primitive definition
+    that is a bare sphere.  `instshapes`: literal TransformedPrimitive semantics with rotated / scaled instances; `instshapesfix`:
+    SG_SCENE_FIX_INSTANCING; `instshapestex`: textured (uv of spheres / patches through the instance transform)."""
+    b = SceneBuilder()
+    b.fix_instancing = kind == "instshapesfix"
+    b.set_camera(pos=(0.0, 1.4, -4.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=resolution)
+    white = b.diffuse(_white())
+    if kind == "instshapestex":
+        mat = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(64, 3), filter="ewa", su=2.0, sv=2.0))
+        metal = b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0)
+    else:
+        mat = b.diffuse(_green())
+        metal = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.15)
+    glass = b.dielectric(("const", 1.5))
+    sph_xf = Transform.translate((0.0, 0.1, 0.0)) * Transform.rotate(-70.0, (1, 0, 0))
+    patch_xf = Transform.translate((0.0, 0.0, 0.5))
+    tw = np.array([[-0.5, -0.3, -0.2], [0.5, -0.3, -0.4], [-0.4, 0.5, 0.3], [0.6, 0.4, -0.1]], np.float32)
+    tuv = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32)
+    TP = np.array([[-0.4, -0.35, -0.3], [0.4, -0.35, -0.3], [0.0, -0.35, 0.4], [0.0, 0.2, 0.0]], np.float32)
+    TI = np.array([[0, 1, 3], [1, 2, 3], [2, 0, 3]], np.uint32)
+    xfs = [Transform.translate((-1.2, 0.6, 0.3)) * Transform.rotate(35.0, (0, 1, 0.3)) * Transform.scale(1.0, 1.4, 0.8),
+           Transform.translate((0.0, 0.7, 0.0)) * Transform.scale(1.3, 1.3, 1.3),
+           Transform.translate((1.2, 0.55, -0.2)) * Transform.rotate(-50.0, (1, 0.2, 0))]
+    ball_xfs = [Transform.translate((0.6, 1.6, 0.4)) * Transform.scale(1.0, 0.6, 1.0), Transform.translate((-0.7, 1.5, -0.4))]
+    if flatten:                                                   # the same shapes at the top level with composed transforms
+        for xf in xfs:
+            b.add_mesh(TP, TI, glass, object_from_world=xf)
+        for xf in xfs:
+            b.add_bilinear_mesh(tw, [[0, 1, 2, 3]], metal, uv=tuv, object_from_world=xf * patch_xf)
+        for xf in xfs:
+            b.add_sphere(0.35, mat, z_min=-0.2, z_max=0.3, phi_max=300.0, object_from_world=xf * sph_xf)
+        for xf in ball_xfs:
+            b.add_sphere(0.3, metal, object_from_world=xf)
+    else:
+        group = b.begin_object()
+        b.add_sphere(0.35, mat, z_min=-0.2, z_max=0.3, phi_max=300.0, object=group, object_from_world=sph_xf)
+        b.add_bilinear_mesh(tw, [[0, 1, 2, 3]], metal, uv=tuv, object=group, object_from_world=patch_xf)
+        b.add_mesh(TP, TI, glass, object=group)
+        ball = b.begin_object()                                   # a one-primitive definition: a bare sphere, no aggregate
+        b.add_sphere(0.3, metal, object=ball)
+        for xf in xfs:
+            b.add_instance(group, xf)
+        for xf in ball_xfs:
+            b.add_instance(ball, xf)
+    b.add_sphere(0.25, glass, object_from_world=Transform.translate((0.0, 0.25, -1.2)))          # a top-level sphere next to the instances
     gp, gi = _quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
     b.add_mesh(gp, gi, white, uv=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
     lp, li = _quad((-0.6, 2.8, -0.6), (0.6, 2.8, -0.6), (0.6, 2.8, 0.6), (-0.6, 2.8, 0.6))
@@ -516,6 +571,8 @@ def tiny_scene(kind="diffuse", resolution=(32, 32)):
         return patch_tiny_scene(kind, resolution)
     if kind in VARIETY_KINDS:
         return variety_tiny_scene(kind, resolution)
+    if kind in INSTANCED_SHAPE_KINDS:
+        return instanced_shapes_tiny_scene(kind, resolution)
     if kind == "ortho":
         # OrthographicCamera (camera.rs:657-827) looking down +z with up = y: render_from_camera is the identity in the
         # camera-world rendering space, where the reference's camera-space ray (see SgCameraKind) is also the right one.

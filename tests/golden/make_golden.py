@@ -19,7 +19,7 @@ from shimmer_b200 import scenes  # noqa: E402
 
 def main():
     out = {}
-    for kind in ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough", "ortho", "thinglass"] + list(scenes.TEXTURED_KINDS) + list(scenes.INSTANCED_KINDS) + list(scenes.VARIETY_KINDS):
+    for kind in ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough", "ortho", "thinglass"] + list(scenes.TEXTURED_KINDS) + list(scenes.INSTANCED_KINDS) + list(scenes.VARIETY_KINDS) + list(scenes.INSTANCED_SHAPE_KINDS):
         sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
         film, st, _ = orc.render(sc, orc.make_params(seed=5, spp=4))
         out[kind] = dict(closest_hit_rays=int(st.closest_hit_rays), shadow_rays=int(st.shadow_rays),

@@ -67,6 +67,7 @@ def lib():
     L.orc_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp]
     L.orc_image_pyramid_levels.argtypes = [C.c_int32, C.c_int32, vp]; L.orc_image_pyramid_levels.restype = C.c_int32
     L.orc_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; L.orc_image_generate_pyramid.restype = C.c_int32
+    L.orc_path_rays.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp]; L.orc_path_rays.restype = C.c_int64
     L.orc_approximate_dp_dxy.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp]
     _lib = L
     return L
@@ -171,3 +172,10 @@ def generate_pyramid(image, wrap="repeat"):
     for a, b in sizes:
         levels.append(out[off:off + a * b * c].reshape(a, b, c).copy()); off += a * b * c
     return levels
+
+
+def path_rays(scene, params, px, py, sample, max_rays=64):
+    """Debug: the rays one (pixel, sample) path traces in the oracle -> (n, 10) array: o, d, t_max, any_hit, hit prim, hit t."""
+    out = np.zeros((max_rays, 10), np.float32)
+    n = lib().orc_path_rays(scene.ptr(), C.byref(params), px, py, sample, max_rays, out.ctypes.data)
+    return out[:n]

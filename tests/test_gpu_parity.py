@@ -368,6 +368,51 @@ def test_sphere_raycast_parity():
     integ.close()
 
 
+@pytest.mark.parametrize("kind", list(scenes.INSTANCED_SHAPE_KINDS))
+def test_shapes_inside_instances_raycast_parity(kind):
+    """Spheres and bilinear patches inside object definitions: the two-level traversal tests them with the instance-space ray
+    (inverse transform for closest hits, the reference's FORWARD transform for shadow rays unless SG_SCENE_FIX_INSTANCING).
+    Primitive, instance-space t and the hit record bit-exact against the oracle."""
+    b = scenes.instanced_shapes_tiny_scene(kind); sc = b.build()
+    integ = create_integrator("wavefront", {}, sc)
+    rng = np.random.default_rng(12)
+    n = 1 << 16
+    o = rng.uniform(-2.5, 2.5, (n, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1]) + 0.05
+    centres = np.array([[-1.2, 0.6, 0.3], [0.0, 0.7, 0.0], [1.2, 0.55, -0.2], [0.6, 1.6, 0.4], [-0.7, 1.5, -0.4]], np.float32)
+    d = (centres[rng.integers(0, 5, n)] + rng.uniform(-0.6, 0.6, (n, 3)).astype(np.float32) - o).astype(np.float32)
+    d[n // 2:] = rng.standard_normal((n - n // 2, 3)).astype(np.float32)
+    o = b.render_from_world.apply_points_f32(o)
+    t = np.full(n, np.inf, np.float32)
+    got = integ.trace(o, d, t); ref, _ = orc.trace(sc, o, d, t)
+    same = got["prim"] == ref["prim"]
+    assert same.mean() > 0.9999
+    hit = same & (ref["prim"] >= 0)
+    for f in ("t", "b0", "b1", "b2"):
+        assert np.array_equal(got[f][hit], ref[f][hit]), f
+    kinds = sc.arrays["prims"]["mesh"][ref["prim"][hit]]
+    in_object = ref["prim"][hit] >= sc.desc.n_top_primitives
+    assert (in_object & (kinds == ffi.SG_PRIM_SPHERE)).mean() > 0.05 and in_object.mean() > 0.2
+    any_g = integ.trace(o, d, np.full(n, 0.9999, np.float32), any_hit=True)
+    any_r, _ = orc.trace(sc, o, d, np.full(n, 0.9999, np.float32), any_hit=True)
+    assert (any_g["prim"] == any_r["prim"]).mean() > 0.9999
+    integ.close()
+
+
+@pytest.mark.parametrize("kind", list(scenes.INSTANCED_SHAPE_KINDS))
+def test_shapes_inside_instances_films(kind):
+    """Films of the scenes with spheres / patches inside object definitions.  Like the top-level sphere scenes they carry the
+    partial-sphere clip test (atan2f) and therefore a per-mille of paths that take another branch than the oracle's (same rate as
+    `spheres`: ~1 % of pixels at 16 spp); the first three path vertices agree everywhere (max_depth <= 2: zero differing pixels)."""
+    sc = scenes.tiny_scene(kind, resolution=(24, 24)).build()
+    for md, frac in ((2, 0.999), (5, 0.97)):      # instshapestex adds EWA footprints that react to last-bit uv differences
+        integ = create_integrator("wavefront", {"maxdepth": md}, sc, {"pixelsamples": 8, "seed": 3})
+        film = integ.render(Options()).copy()
+        ref, rst, _ = orc.render(sc, orc.make_params(seed=3, spp=8, max_depth=md))
+        _film_close(film, ref, frac=frac, rtol=2e-3 if md == 2 else 5e-3)
+        assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-3 * rst.closest_hit_rays
+        integ.close()
+
+
 @pytest.mark.parametrize("kind", list(scenes.SPHERE_KINDS))
 def test_sphere_scene_films(kind):
     sc = scenes.tiny_scene(kind, resolution=(24, 24)).build()

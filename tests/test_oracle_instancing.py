@@ -56,6 +56,29 @@ def test_reference_mode_closest_hits_are_right_for_translations_but_shadows_are_
     assert (sa["prim"] != sb["prim"]).mean() > 0.01                                # the forward-transform quirk is visible
 
 
+def test_shapes_inside_object_definitions_equal_the_flattened_scene_in_fixed_mode():
+    """Object definitions may hold spheres and bilinear patches (scene.rs:814-866 takes any Shape): with SG_SCENE_FIX_INSTANCING the
+    instanced scene must trace like the same shapes placed at the top level with composed transforms."""
+    inst = scenes.instanced_shapes_tiny_scene("instshapesfix", (24, 24)).build()
+    flat = scenes.instanced_shapes_tiny_scene("instshapesfix", (24, 24), flatten=True).build()
+    assert inst.desc.n_objects == 2 and inst.arrays["objects"][1].n_nodes == 0 and inst.desc.n_spheres == 3 and flat.desc.n_spheres == 6
+    o, d = _rays(20000, 5, flat)
+    tmax = np.full(len(o), np.inf, np.float32)
+    a, _ = orc.trace(inst, o, d, tmax); b, _ = orc.trace(flat, o, d, tmax)
+    assert ((a["prim"] >= 0) != (b["prim"] >= 0)).mean() < 2e-3
+    both = (a["prim"] >= 0) & (b["prim"] >= 0)
+    assert both.mean() > 0.3 and np.allclose(a["t"][both], b["t"][both], rtol=5e-4, atol=2e-5)
+    sa, _ = orc.trace(inst, o, d * np.float32(2.5), np.full(len(o), 0.9999, np.float32), any_hit=True)
+    sb, _ = orc.trace(flat, o, d * np.float32(2.5), np.full(len(o), 0.9999, np.float32), any_hit=True)
+    assert (sa["prim"] != sb["prim"]).mean() < 2e-3
+    fa, _, _ = orc.render(inst, orc.make_params(seed=1, spp=64)); fb, _, _ = orc.render(flat, orc.make_params(seed=1, spp=64))
+    assert abs(fa[:, :3].sum() - fb[:, :3].sum()) / fb[:, :3].sum() < 0.02
+    # the literal mode differs (forward transform on shadow rays, inverse on interaction vectors)
+    lit = scenes.instanced_shapes_tiny_scene("instshapes", (24, 24)).build()
+    sl, _ = orc.trace(lit, o, d * np.float32(2.5), np.full(len(o), 0.9999, np.float32), any_hit=True)
+    assert (sl["prim"] != sb["prim"]).mean() > 0.01
+
+
 def test_single_primitive_object_has_no_aggregate():
     sc = scenes.instanced_tiny_scene("inst", (8, 8)).build()
     objs = sc.arrays["objects"]
@@ -63,7 +86,7 @@ def test_single_primitive_object_has_no_aggregate():
     assert sc.desc.n_top_primitives == 4 + 6 and sc.desc.n_instances == 6
 
 
-@pytest.mark.parametrize("kind", scenes.INSTANCED_KINDS)
+@pytest.mark.parametrize("kind", scenes.INSTANCED_KINDS + scenes.INSTANCED_SHAPE_KINDS)
 def test_instanced_scene_golden_film(kind):
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_films.json")))[kind]
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
