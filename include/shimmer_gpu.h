@@ -69,7 +69,9 @@ typedef struct SgPrimitive {
  * SgSceneDesc.nodes at [first_node, first_node + n_nodes) with second-child offsets RELATIVE to first_node and leaf
  * primitive offsets RELATIVE to first_prim; its primitives are SgSceneDesc.primitives[first_prim, first_prim + n_prims)
  * in that BVH's leaf order.  n_nodes == 0: the definition is one bare primitive (no aggregate).  The top-level
- * BvhAggregate is nodes[0, n_top_nodes) over primitives[0, n_top_primitives); only it may hold instance primitives. */
+ * BvhAggregate is nodes[0, n_top_nodes) over primitives[0, n_top_primitives); only it may hold instance primitives.
+ * A definition may hold triangles, bilinear patches and spheres (their transforms / vertices are relative to the
+ * definition's space); emissive shapes inside definitions are rejected (pbrt-v4 scene format). */
 typedef struct SgObject {
     uint32_t first_node, n_nodes, first_prim, n_prims;
 } SgObject;
@@ -106,7 +108,7 @@ enum {
     SG_MESH_HAS_N = 1, SG_MESH_HAS_UV = 2, SG_MESH_HAS_S = 4,
     SG_MESH_REVERSE_ORIENTATION = 8, SG_MESH_SWAPS_HANDEDNESS = 16,
     SG_MESH_BILINEAR = 32   /* `BilinearPatchMesh` (mesh.rs:98-175): FOUR indices per patch (p00, p10, p01, p11; bilinear_patch.rs:87-106),
-                               n_triangles = number of patches, SgPrimitive.tri = patch index.  Top-level patches only; an emissive patch's
+                               n_triangles = number of patches, SgPrimitive.tri = patch index.  Patches may sit inside object definitions; an emissive (top-level) patch's
                                SgPrimitive.light points at an SG_LIGHT_DIFFUSE_AREA_PATCH light over that patch. */
 };
 typedef struct SgMesh {
@@ -328,7 +330,7 @@ typedef struct SgSceneDesc {
     uint32_t n_top_primitives;                              /* top-level primitives;                  0 = n_primitives      */
     uint32_t n_objects;    const SgObject*    objects;
     uint32_t n_instances;  const SgInstance*  instances;
-    uint32_t n_spheres;    const SgSphere*    spheres;     /* top-level primitives only                                    */
+    uint32_t n_spheres;    const SgSphere*    spheres;     /* referenced by SG_PRIM_SPHERE primitives (top level or inside objects) */
     uint32_t scene_flags;                                   /* SG_SCENE_*                                                   */
     uint32_t n_meshes;     const SgMesh*      meshes;
     uint32_t n_indices;    const uint32_t*    indices;     /* 3 per triangle               */
