@@ -23,6 +23,7 @@ using namespace orc;
 namespace {
 
 struct PathCounters { Counters c; };
+float g_debug_perturb = 0.0f;
 
 // Ray::spawn_ray_to_both_offset ray.rs:83-99 via Interaction::spawn_ray_to_interaction interaction.rs:81-85
 inline Ray spawn_ray_to_both_offset(const P3fi& p_from, V3 n_from, const P3fi& p_to, V3 n_to) {
@@ -151,6 +152,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
         prev_ctx.pi = si.pi; prev_ctx.n = si.n; prev_ctx.ns = si.sn;
         if (D->n_textures > 0) aux = spawn_differentials(si, aux, bs.wi, bs.flags, bs.eta);   // spawn_ray_with_differentials :434-502
         ray.o = offset_ray_origin(si.pi, si.n, bs.wi); ray.d = bs.wi;             // spawn_ray interaction.rs:72-79
+        if (g_debug_perturb != 0.0f && depth == 1) ray.d.x *= 1.0f + g_debug_perturb;  // debug only (orc_set_debug_perturb): sensitivity experiments
         if (std::isfinite(eta_scale)) {                                           // :878-891
             Spec rr_beta = beta * eta_scale;
             if (spec_max(rr_beta) < 1.0f && depth > 1) {
@@ -702,6 +704,7 @@ int64_t orc_path_rays(const SgSceneDesc* desc, const SgRenderParams* rp, int px,
     std::memcpy(out, log.data(), (size_t)n * 10 * sizeof(float));
     return n;
 }
+void orc_set_debug_perturb(float rel) { g_debug_perturb = rel; }
 void orc_approximate_dp_dxy(const SgSceneDesc* d, const float* p, const float* n, int spp, uint32_t option_flags, float* out6) {
     V3 dpdx, dpdy;
     approximate_dp_dxy(d->camera, v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2]), spp, option_flags, &dpdx, &dpdy);

@@ -68,6 +68,7 @@ def lib():
     L.orc_image_pyramid_levels.argtypes = [C.c_int32, C.c_int32, vp]; L.orc_image_pyramid_levels.restype = C.c_int32
     L.orc_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; L.orc_image_generate_pyramid.restype = C.c_int32
     L.orc_path_rays.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp]; L.orc_path_rays.restype = C.c_int64
+    L.orc_set_debug_perturb.argtypes = [C.c_float]
     L.orc_approximate_dp_dxy.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, vp]
     _lib = L
     return L

@@ -156,3 +156,27 @@ def test_sphere_light_sampling_is_self_consistent():
         assert abs(p2 - (1 / area) / cosl / d2) < 5e-3 * p2
         acc += 1.0 / pdf; cnt += 1
     assert cnt > 1900 and abs(acc / cnt - 4 * np.pi) < 0.05 * 4 * np.pi             # solid-angle pdf integrates over the full sphere of directions
+
+
+def test_sphere_scenes_are_sensitive_to_one_ulp_and_triangle_scenes_are_not():
+    """Why the GPU film tests allow ~1-3 % differing pixels on scenes with rotated / scaled spheres: the reference algorithm itself
+    is discontinuous at the ulp level there.  Scaling the x component of every first-bounce ray direction by (1 + 2^-23) in the ORACLE
+    changes several per cent of the pixels of the sphere scene by more than 2e-3, and none of the triangle scene -- Sphere::
+    basic_intersect decides hits with interval bounds (sphere.rs:95-186: `discrim.lower_bound() < 0`, `t0.lower_bound() <= 0`), so
+    a last-bit change of a ray moves paths across those tests.  The CUDA path differs from the oracle by libm last bits
+    (sin / cos / atan2 in the samplers), i.e. by exactly such perturbations; it stays below the oracle's own sensitivity."""
+    import ctypes as C
+    L = orc.lib()
+    p = orc.make_params(seed=5, spp=16)
+    def changed(kind):
+        sc = scenes.tiny_scene(kind, resolution=(32, 32)).build()
+        base, _, _ = orc.render(sc, p)
+        L.orc_set_debug_perturb(C.c_float(1.1920929e-07))
+        try:
+            f, _, _ = orc.render(sc, p)
+        finally:
+            L.orc_set_debug_perturb(C.c_float(0.0))
+        lg, lr = f[:, :3].sum(axis=1), base[:, :3].sum(axis=1)
+        return int((np.abs(lg - lr) / np.maximum(lr, 0.05 * lr.mean()) > 2e-3).sum())
+    assert changed("diffuse") == 0 and changed("conductor") == 0
+    assert changed("spheres") >= 10          # observed: 45 of 1024 pixels (the CUDA path differs from the oracle in 10)
