@@ -401,15 +401,16 @@ def test_shapes_inside_instances_raycast_parity(kind):
 @pytest.mark.parametrize("kind", list(scenes.INSTANCED_SHAPE_KINDS))
 def test_shapes_inside_instances_films(kind):
     """Films of the scenes with spheres / patches inside object definitions.  Like the top-level sphere scenes they carry the
-    partial-sphere clip test (atan2f) and therefore a per-mille of paths that take another branch than the oracle's (same rate as
-    `spheres`: ~1 % of pixels at 16 spp); the first three path vertices agree everywhere (max_depth <= 2: zero differing pixels)."""
+    interval-arithmetic sphere test, which is ulp-chaotic in the reference itself (tests/test_oracle_sphere.py::
+    test_sphere_scenes_are_sensitive_to_one_ulp...): a per-mille of paths takes another branch than the oracle's (same rate as `spheres`:
+    ~1 % of pixels at 16 spp); the first three path vertices agree everywhere (max_depth <= 2: zero differing pixels)."""
     sc = scenes.tiny_scene(kind, resolution=(24, 24)).build()
     for md, frac in ((2, 0.999), (5, 0.97)):      # instshapestex adds EWA footprints that react to last-bit uv differences
         integ = create_integrator("wavefront", {"maxdepth": md}, sc, {"pixelsamples": 8, "seed": 3})
         film = integ.render(Options()).copy()
         ref, rst, _ = orc.render(sc, orc.make_params(seed=3, spp=8, max_depth=md))
         _film_close(film, ref, frac=frac, rtol=2e-3 if md == 2 else 5e-3)
-        assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 1e-3 * rst.closest_hit_rays
+        assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= (1e-4 if md == 2 else 3e-3) * rst.closest_hit_rays + 1
         integ.close()
 
 
