@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 7
+#define SG_ABI_VERSION 8
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -220,8 +220,29 @@ typedef struct SgTexture {
     float    su, sv, du, dv;   /* UVMapping (texture.rs:896-936)         */
     int32_t  spectrum_type;    /* SgSpectrumType (three-channel spectrum textures) */
     int32_t  mapping;          /* index into SgSceneDesc.texture_mappings, or -1 = UVMapping with su, sv, du, dv above */
-    int32_t  pad[2];
+    int32_t  kind;             /* SgTextureKind; 0 = image texture (every field above), else only n_channels and `node` are read */
+    int32_t  node;             /* index into SgSceneDesc.texture_nodes for the non-image kinds                           */
 } SgTexture;
+/* The non-image members of `enum FloatTexture` / `enum SpectrumTexture` (texture.rs:88-94,411-417).  A texture row with
+ * n_channels == 1 is a FloatTexture, any other channel count a SpectrumTexture; operands are texture ids of the required
+ * type (spectrum operands may also be one-channel rows: they evaluate to a constant spectrum like a one-channel image,
+ * texture.rs:803-807).  Nesting depth (operand of an operand ...) is at most SG_MAX_TEXTURE_DEPTH below the root. */
+typedef enum SgTextureKind {
+    SG_TEXTURE_IMAGE = 0,          /* FloatImageTexture :393-404 / SpectrumImageTexture :777-808                         */
+    SG_TEXTURE_CONSTANT = 1,       /* FloatConstantTexture :138-177 (`value`) / SpectrumConstantTexture :485-535 (`spectrum`) */
+    SG_TEXTURE_SCALED = 2,         /* Float/SpectrumScaledTexture :180-213,:537-583: scale == 0 ? 0 : tex * scale        */
+    SG_TEXTURE_MIX = 3,            /* Float/SpectrumMixTexture :215-262,:585-651: tex1 skipped when amount == 1, tex2 when amount == 0 */
+    SG_TEXTURE_DIRECTION_MIX = 4   /* Float/SpectrumDirectionMixTexture :264-310,:653-...: amount = dot(ctx.n, dir), NOT normalised or clamped */
+} SgTextureKind;
+#define SG_MAX_TEXTURE_DEPTH 3
+typedef struct SgTextureNode {
+    int32_t tex1;        /* SCALED: `tex`;  MIX / DIRECTION_MIX: `tex1`                          */
+    int32_t tex2;        /* SCALED: `scale` (float texture);  MIX / DIRECTION_MIX: `tex2`        */
+    int32_t amount;      /* MIX: `amount` (float texture)                                         */
+    int32_t spectrum;    /* CONSTANT spectrum texture: spectrum id                                */
+    float   value;       /* CONSTANT float texture                                                */
+    float   dir[3];      /* DIRECTION_MIX: `dir` as given (default 0 1 0, render space)           */
+} SgTextureNode;
 /* `SphericalMapping`, `CylindricalMapping`, `PlanarMapping` (texture.rs:938-1035) as written there -- including the spherical
  * mapping's st = (theta/pi, theta/2pi) (both from theta, :960-963) and the cylindrical s = pi + atan2(y, x)/2pi (:991). */
 typedef enum SgTextureMappingKind { SG_MAPPING_SPHERICAL = 1, SG_MAPPING_CYLINDRICAL = 2, SG_MAPPING_PLANAR = 3 } SgTextureMappingKind;
@@ -351,6 +372,7 @@ typedef struct SgSceneDesc {
     uint32_t rgb2spec_res; const float* rgb2spec_scale; const float* rgb2spec_data;
     uint32_t n_texture_mappings; const SgTextureMapping* texture_mappings;
     uint32_t n_env_maps;   const SgEnvMap*    env_maps;     /* texels / spectrum_pool hold their data */
+    uint32_t n_texture_nodes; const SgTextureNode* texture_nodes;   /* operands of the non-image textures */
     SgCamera camera;
     SgFilm   film;
 } SgSceneDesc;
@@ -469,6 +491,8 @@ int sg_texture_eval(SgScene* scene, int tex, int as_float, int64_t n, const floa
 /* Same with the full `TextureEvalContext` (texture.rs): pdp = p, dpdx, dpdy in render space (9 floats per lookup), which the
  * spherical / cylindrical / planar mappings read (texture.rs:938-1035). */
 int sg_texture_eval_p(SgScene* scene, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda, float* out);
+/* Same with `TextureEvalContext::n` as well (3 floats per lookup), which the direction-mix textures read (texture.rs:299,:690). */
+int sg_texture_eval_ctx(SgScene* scene, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* nrm, const float* lambda, float* out);
 
 /* Replaces `RgbFilm::get_pixel_rgb` (film.rs:720-738): rgb_sum/weight_sum then
  * output_rgb_from_sensor_rgb; out: 3 floats per pixel. */

@@ -544,7 +544,7 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
     if (D->n_textures > 0) compute_differentials(D, si, aux, rp->samples_per_pixel, rp->option_flags);
     if (D->materials[si.material].kind == SG_MATERIAL_MIX) {                     // interaction.rs:206-221
         Rng mr; mr.seed_from_u64(mix_seed);
-        const TexCoordCtx mc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
+        const TexCoordCtx mc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy, si.n};
         for (int guard = 0; guard < 64 && D->materials[si.material].kind == SG_MATERIAL_MIX; ++guard) {
             const SgMaterial& mm = D->materials[si.material];
             const Float amt = mm.tex_mix_amount >= 0 ? eval_float_texture(D, mm.tex_mix_amount, mc) : mm.mix_amount;
@@ -567,7 +567,7 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         si.sdpdu = dpdu; si.sdpdv = dpdv;
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
-    TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
+    TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy, si.n};
     BSDF b;
     b.kind = m.kind; b.r = spec_const(0.0f); b.k = spec_const(0.0f); b.eta = 1.0f; b.mf = TR::make(0.0f, 0.0f);
     b.lay.mf = TR::make(0.0f, 0.0f); b.lay.mfb = TR::make(0.0f, 0.0f);

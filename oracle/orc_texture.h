@@ -182,7 +182,7 @@ inline V3 xform_point3(const float m[16], V3 p) {                // apply_point_
     return v3(xp, yp, zp) / wp;
 }
 // TextureEvalContext (texture.rs): uv + screen-space derivatives; p / dpdx / dpdy feed the non-UV mappings only
-struct TexCoordCtx { V2 uv; Float dudx, dudy, dvdx, dvdy; V3 p = {0, 0, 0}, dpdx = {0, 0, 0}, dpdy = {0, 0, 0}; };
+struct TexCoordCtx { V2 uv; Float dudx, dudy, dvdx, dvdy; V3 p = {0, 0, 0}, dpdx = {0, 0, 0}, dpdy = {0, 0, 0}, n = {0, 0, 0}; };
 
 inline void uv_map(const SgTexture& t, const TexCoordCtx& c, V2* st, V2* dst0, V2* dst1) {            // texture.rs:918-936
     Float dsdx = t.su * c.dudx, dsdy = t.su * c.dudy, dtdx = t.sv * c.dvdx, dtdy = t.sv * c.dvdy;
@@ -218,14 +218,14 @@ inline void tex_map(const SgSceneDesc* D, const SgTexture& t, const TexCoordCtx&
     st->y = 1.0f - st->y;                                                        // :396-399, :780-781
 }
 // FloatImageTexture::evaluate texture.rs:393-404
-inline Float eval_float_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c) {
+inline Float eval_float_image(const SgSceneDesc* D, int tex, const TexCoordCtx& c) {
     TexView tv = {D, &D->textures[tex]};
     V2 st, d0, d1; tex_map(D, *tv.t, c, &st, &d0, &d1);
     Float v = tex_filter<false>(tv, st, d0, d1).r * tv.t->scale;
     return tv.t->invert ? fmax_(0.0f, 1.0f - v) : v;
 }
 // SpectrumImageTexture::evaluate texture.rs:777-808
-inline Spec eval_spectrum_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c, const Wavelengths& lambda) {
+inline Spec eval_spectrum_image(const SgSceneDesc* D, int tex, const TexCoordCtx& c, const Wavelengths& lambda) {
     TexView tv = {D, &D->textures[tex]};
     V2 st, d0, d1; tex_map(D, *tv.t, c, &st, &d0, &d1);
     Texel rgb = tex_filter<true>(tv, st, d0, d1) * tv.t->scale;
@@ -243,6 +243,63 @@ inline Spec eval_spectrum_texture(const SgSceneDesc* D, int tex, const TexCoordC
     for (int i = 0; i < 4; ++i) s.v[i] = sigmoid_poly_get(coef, lambda.lambda[i]);
     if (tv.t->spectrum_type == SG_SPECTRUM_TYPE_UNBOUNDED) for (int i = 0; i < 4; ++i) s.v[i] = scale * s.v[i];
     return s;
+}
+
+// `impl FloatTextureI for FloatTexture` texture.rs:142-152 and its members :175-310
+inline Float eval_float_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c) {
+    const SgTexture& t = D->textures[tex];
+    if (t.kind == SG_TEXTURE_IMAGE) return eval_float_image(D, tex, c);
+    const SgTextureNode& nd = D->texture_nodes[t.node];
+    switch (t.kind) {
+    case SG_TEXTURE_CONSTANT: return nd.value;                                   // :175-179
+    case SG_TEXTURE_SCALED: {                                                    // :206-213
+        const Float sc = eval_float_texture(D, nd.tex2, c);
+        if (sc == 0.0f) return 0.0f;
+        return eval_float_texture(D, nd.tex1, c) * sc;
+    }
+    case SG_TEXTURE_MIX: {                                                       // :246-261
+        const Float amt = eval_float_texture(D, nd.amount, c);
+        Float t1 = 0.0f, t2 = 0.0f;
+        if (amt != 1.0f) t1 = eval_float_texture(D, nd.tex1, c);
+        if (amt != 0.0f) t2 = eval_float_texture(D, nd.tex2, c);
+        return t1 * (1.0f - amt) + t2 * amt;
+    }
+    default: {                                                                   // DirectionMix :295-310 (note the tests are 0 / 1 swapped w.r.t. Mix)
+        const Float amt = dot(c.n, v3(nd.dir[0], nd.dir[1], nd.dir[2]));
+        Float t1 = 0.0f, t2 = 0.0f;
+        if (amt != 0.0f) t1 = eval_float_texture(D, nd.tex1, c);
+        if (amt != 1.0f) t2 = eval_float_texture(D, nd.tex2, c);
+        return amt * t1 + (1.0f - amt) * t2;
+    }
+    }
+}
+// `impl SpectrumTextureI for SpectrumTexture` texture.rs:467-483 and its members :509-513,:567-583,:631-651,:810-826
+inline Spec eval_spectrum_texture(const SgSceneDesc* D, int tex, const TexCoordCtx& c, const Wavelengths& lambda) {
+    const SgTexture& t = D->textures[tex];
+    if (t.kind == SG_TEXTURE_IMAGE) return eval_spectrum_image(D, tex, c, lambda);
+    const SgTextureNode& nd = D->texture_nodes[t.node];
+    switch (t.kind) {
+    case SG_TEXTURE_CONSTANT: return nd.spectrum >= 0 ? spectrum_sample(D, nd.spectrum, lambda) : spec_const(nd.value);
+    case SG_TEXTURE_SCALED: {
+        const Float sc = eval_float_texture(D, nd.tex2, c);
+        if (sc == 0.0f) return spec_const(0.0f);
+        return eval_spectrum_texture(D, nd.tex1, c, lambda) * sc;
+    }
+    case SG_TEXTURE_MIX: {
+        const Float amt = eval_float_texture(D, nd.amount, c);
+        Spec t1 = spec_const(0.0f), t2 = spec_const(0.0f);
+        if (amt != 1.0f) t1 = eval_spectrum_texture(D, nd.tex1, c, lambda);
+        if (amt != 0.0f) t2 = eval_spectrum_texture(D, nd.tex2, c, lambda);
+        return t1 * (1.0f - amt) + t2 * amt;
+    }
+    default: {
+        const Float amt = dot(c.n, v3(nd.dir[0], nd.dir[1], nd.dir[2]));
+        Spec t1 = spec_const(0.0f), t2 = spec_const(0.0f);
+        if (amt != 0.0f) t1 = eval_spectrum_texture(D, nd.tex1, c, lambda);
+        if (amt != 1.0f) t2 = eval_spectrum_texture(D, nd.tex2, c, lambda);
+        return amt * t1 + (1.0f - amt) * t2;
+    }
+    }
 }
 
 // ---- screen-space differentials -------------------------------------------------------------------
@@ -384,7 +441,7 @@ inline void compute_differentials(const SgSceneDesc* D, SurfaceInteraction& si, 
 
 // bump_map material.rs:1477-1509 for a FloatImageTexture (tex >= 0) or the constant displacement `cdisp`
 inline void bump_map(const SgSceneDesc* D, int tex, Float cdisp, const SurfaceInteraction& si, V3* dpdu_out, V3* dpdv_out) {
-    TexCoordCtx c = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy};
+    TexCoordCtx c = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy, si.n};
     Float du = 0.5f * (std::fabs(si.dudx) + std::fabs(si.dudy));
     if (du == 0.0f) du = 0.0005f;
     Float dv = 0.5f * (std::fabs(si.dvdx) + std::fabs(si.dvdy));

@@ -614,6 +614,20 @@ void orc_texture_eval_p(const SgSceneDesc* d, int tex, int as_float, int64_t n, 
         }
     }
 }
+// same with TextureEvalContext::n too (3 floats per lookup; pdp may be null): the direction-mix textures (texture.rs:295-310,:810-826)
+void orc_texture_eval_ctx(const SgSceneDesc* d, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* nrm, const float* lambda4, float* out4) {
+    for (int64_t i = 0; i < n; ++i) {
+        TexCoordCtx c; c.uv.x = q[6 * i]; c.uv.y = q[6 * i + 1]; c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
+        if (pdp) { c.p = v3(pdp[9 * i], pdp[9 * i + 1], pdp[9 * i + 2]); c.dpdx = v3(pdp[9 * i + 3], pdp[9 * i + 4], pdp[9 * i + 5]); c.dpdy = v3(pdp[9 * i + 6], pdp[9 * i + 7], pdp[9 * i + 8]); }
+        if (nrm) c.n = v3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+        if (as_float) { Float v = eval_float_texture(d, tex, c); for (int k = 0; k < 4; ++k) out4[4 * i + k] = v; }
+        else {
+            Wavelengths w; for (int k = 0; k < 4; ++k) { w.lambda[k] = lambda4[4 * i + k]; w.pdf[k] = 1.0f; }
+            Spec s = eval_spectrum_texture(d, tex, c, w);
+            for (int k = 0; k < 4; ++k) out4[4 * i + k] = s.v[k];
+        }
+    }
+}
 // ---- Image::generate_pyramid (image.rs:699-787) with Image::float_resize_up (:1007-1111) / resample_weights (:1113-1141) ----
 // `image`: width x height x n_channels linear f32 texels (what convert_to_format(Float) yields).  Levels are written back to back
 // into `out`; returns the number of levels.  As written: resample_weights evaluates the windowed sinc at `first_pixel + 0.5` for

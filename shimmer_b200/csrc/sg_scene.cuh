@@ -51,6 +51,7 @@ struct DScene {
     const float* rgb2spec_data;
     uint32_t rgb2spec_res, n_textures;
     const SgTextureMapping* texture_mappings;   // spherical / cylindrical / planar mappings (sg_texture.cuh)
+    const SgTextureNode* texture_nodes;         // operands of the constant / scaled / mix / direction-mix textures (sg_texture.cuh)
     const SgEnvMap* env_maps;           // ImageInfinitelight images + sampling distributions (sg_envmap.cuh)
     const DInstance* instances;         // object instancing
     const struct DSphere* spheres;      // sphere shapes (sg_sphere.cuh)

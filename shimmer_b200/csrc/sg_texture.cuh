@@ -193,9 +193,11 @@ SGD float sigmoid_poly_get(const float c[3], float lambda) {
     return 0.5f + x / (2.0f * sqrtf(1.0f + x * x));
 }
 
-// TextureEvalContext (texture.rs): uv + screen-space derivatives.  `pdp` -> {p, dpdx, dpdy} for the non-UV mappings
-// (texture.rs:938-1035); null in scenes without SgTextureMapping rows, so the UV-only kernels carry nothing extra.
+// TextureEvalContext (texture.rs): uv + screen-space derivatives.  `pdp` -> {p, dpdx, dpdy, n}: p / dpdx / dpdy for the non-UV
+// mappings (texture.rs:938-1035), n for the direction-mix textures (:299,:813); null in scenes without SgTextureMapping or
+// SgTextureNode rows, so the UV-only image-texture kernels carry nothing extra.
 struct TexCoordCtx { float2 uv; float dudx, dudy, dvdx, dvdy; const float3* pdp = nullptr; };
+SGD bool tex_needs_ctx(const DScene& sc) { return sc.texture_mappings != nullptr || sc.texture_nodes != nullptr; }
 
 SGD void uv_map(const SgTexture& t, const TexCoordCtx& c, float2& st, float2& dst0, float2& dst1) {   // texture.rs:918-936
     const float dsdx = t.su * c.dudx, dsdy = t.su * c.dudy, dtdx = t.sv * c.dvdx, dtdy = t.sv * c.dvdy;
@@ -236,7 +238,7 @@ SGD void tex_map(const DScene& sc, const SgTexture& t, const TexCoordCtx& c, flo
     if (t.mapping < 0) uv_map(t, c, st, dst0, dst1); else general_map(sc, t, c, st, dst0, dst1);
 }
 // FloatImageTexture::evaluate texture.rs:393-404
-static __device__ __noinline__ float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
+static __device__ __noinline__ float eval_float_image(const DScene& sc, int tex, const TexCoordCtx& c) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
     float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
@@ -244,7 +246,7 @@ static __device__ __noinline__ float eval_float_texture(const DScene& sc, int te
     return t.invert ? fmaxf(0.0f, 1.0f - v) : v;
 }
 // SpectrumImageTexture::evaluate texture.rs:777-808
-static __device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
+static __device__ __noinline__ Spec eval_spectrum_image(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
     const SgTexture t = sc.textures[tex];
     const TexView tv{sc, t};
     float2 st, d0, d1; tex_map(sc, t, c, st, d0, d1);
@@ -263,6 +265,75 @@ static __device__ __noinline__ Spec eval_spectrum_texture(const DScene& sc, int 
                          sigmoid_poly_get(coef, lam.lambda.w));
     if (t.spectrum_type == SG_SPECTRUM_TYPE_UNBOUNDED) s = scale * s;
     return s;
+}
+
+// The non-image members of `enum FloatTexture` / `enum SpectrumTexture` (texture.rs:88-94,411-417): constant, scaled, mix and
+// direction-mix textures evaluate their operands recursively in the reference; here the recursion is unrolled at compile time to
+// SG_MAX_TEXTURE_DEPTH levels (sg_scene_create rejects deeper trees), so no device stack frames of unknown size exist.
+template <int DEPTH> struct TexTree {
+    // `impl FloatTextureI for FloatTexture` texture.rs:142-152; members :175-179, :206-213, :246-261, :295-310
+    static __device__ __noinline__ float eval_float(const DScene& sc, int tex, const TexCoordCtx& c) {
+        const int kind = sc.textures[tex].kind;
+        if (kind == SG_TEXTURE_IMAGE) return eval_float_image(sc, tex, c);
+        const SgTextureNode nd = sc.texture_nodes[sc.textures[tex].node];
+        if (kind == SG_TEXTURE_CONSTANT) return nd.value;
+        if constexpr (DEPTH > 0) {
+            using Sub = TexTree<DEPTH - 1>;
+            if (kind == SG_TEXTURE_SCALED) {
+                const float scl = Sub::eval_float(sc, nd.tex2, c);
+                if (scl == 0.0f) return 0.0f;
+                return Sub::eval_float(sc, nd.tex1, c) * scl;
+            }
+            float amt, t1 = 0.0f, t2 = 0.0f;
+            if (kind == SG_TEXTURE_MIX) {
+                amt = Sub::eval_float(sc, nd.amount, c);
+                if (amt != 1.0f) t1 = Sub::eval_float(sc, nd.tex1, c);
+                if (amt != 0.0f) t2 = Sub::eval_float(sc, nd.tex2, c);
+                return t1 * (1.0f - amt) + t2 * amt;
+            }
+            amt = dot3(c.pdp ? c.pdp[3] : f3(0.0f, 0.0f, 0.0f), f3(nd.dir[0], nd.dir[1], nd.dir[2]));      // DirectionMix: 0 / 1 tests swapped w.r.t. Mix, as written
+            if (amt != 0.0f) t1 = Sub::eval_float(sc, nd.tex1, c);
+            if (amt != 1.0f) t2 = Sub::eval_float(sc, nd.tex2, c);
+            return amt * t1 + (1.0f - amt) * t2;
+        }
+        return 0.0f;
+    }
+    // `impl SpectrumTextureI for SpectrumTexture` texture.rs:467-483; members :509-513, :567-583, :631-651, :810-826
+    static __device__ __noinline__ Spec eval_spectrum(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
+        const int kind = sc.textures[tex].kind;
+        if (kind == SG_TEXTURE_IMAGE) return eval_spectrum_image(sc, tex, c, lam);
+        const SgTextureNode nd = sc.texture_nodes[sc.textures[tex].node];
+        if (kind == SG_TEXTURE_CONSTANT) return nd.spectrum >= 0 ? spectrum_sample(sc, nd.spectrum, lam) : spec1(nd.value);
+        if constexpr (DEPTH > 0) {
+            using Sub = TexTree<DEPTH - 1>;
+            if (kind == SG_TEXTURE_SCALED) {
+                const float scl = Sub::eval_float(sc, nd.tex2, c);
+                if (scl == 0.0f) return spec1(0.0f);
+                return Sub::eval_spectrum(sc, nd.tex1, c, lam) * scl;
+            }
+            float amt; Spec t1 = spec1(0.0f), t2 = spec1(0.0f);
+            if (kind == SG_TEXTURE_MIX) {
+                amt = Sub::eval_float(sc, nd.amount, c);
+                if (amt != 1.0f) t1 = Sub::eval_spectrum(sc, nd.tex1, c, lam);
+                if (amt != 0.0f) t2 = Sub::eval_spectrum(sc, nd.tex2, c, lam);
+                return t1 * (1.0f - amt) + t2 * amt;
+            }
+            amt = dot3(c.pdp ? c.pdp[3] : f3(0.0f, 0.0f, 0.0f), f3(nd.dir[0], nd.dir[1], nd.dir[2]));
+            if (amt != 0.0f) t1 = Sub::eval_spectrum(sc, nd.tex1, c, lam);
+            if (amt != 1.0f) t2 = Sub::eval_spectrum(sc, nd.tex2, c, lam);
+            return amt * t1 + (1.0f - amt) * t2;
+        }
+        return spec1(0.0f);
+    }
+};
+// Scenes without SgTextureNode rows (every BASELINE config) take the image path directly: one predictable branch.
+SGD float eval_float_texture(const DScene& sc, int tex, const TexCoordCtx& c) {
+    if (sc.texture_nodes == nullptr) return eval_float_image(sc, tex, c);
+    return TexTree<SG_MAX_TEXTURE_DEPTH>::eval_float(sc, tex, c);
+}
+SGD Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, const Wavelengths& lam) {
+    if (sc.texture_nodes == nullptr) return eval_spectrum_image(sc, tex, c, lam);
+    return TexTree<SG_MAX_TEXTURE_DEPTH>::eval_spectrum(sc, tex, c, lam);
 }
 
 // ---- screen-space differentials ----
@@ -387,8 +458,8 @@ SGD void compute_differentials(const DScene& sc, const Surf& s, SurfTex& x, cons
 // bump_map material.rs:1477-1509 for a FloatImageTexture (tex >= 0) or the constant displacement `cdisp`; writes the
 // displaced shading.dpdu / dpdv (the caller then rebuilds the shading normal, interaction.rs:229-250)
 SGD void bump_map(const DScene& sc, int tex, float cdisp, Surf& s, const SurfTex& x) {
-    float3 pdp[3] = {p3fi_mid(s.pi), x.dpdx, x.dpdy};
-    const bool mapped = sc.texture_mappings != nullptr;                         // shifted_ctx.p only matters to the non-UV mappings
+    float3 pdp[4] = {p3fi_mid(s.pi), x.dpdx, x.dpdy, s.n};
+    const bool mapped = tex_needs_ctx(sc);                                      // shifted_ctx.p only matters to the non-UV mappings, n to direction mixes
     const TexCoordCtx c{x.uv, x.dudx, x.dudy, x.dvdx, x.dvdy, mapped ? pdp : nullptr};
     float du = 0.5f * (fabsf(x.dudx) + fabsf(x.dudy));
     if (du == 0.0f) du = 0.0005f;

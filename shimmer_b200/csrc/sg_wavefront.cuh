@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
             path = q.shade[Q_MIX][i];
             uint32_t material_id; int light_id;
             const TriGeo geo = geo_from_prim(sc, (uint32_t)st.hit_prim[path], material_id, light_id);
-            float3 pdp[3];
+            float3 pdp[4];
             TexCoordCtx tc{make_float2(0.0f, 0.0f), 0.0f, 0.0f, 0.0f, 0.0f};
             bool have_ctx = false;
             Rng mr; mr.seed_from_u64(mix64(st.rng_a[path].x ^ (5ull * 0x9e3779b97f4a7c15ULL)));      // layer_seed(rng, 5)
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
                         if (st.flags[path] & kFlagAux) aux = aux_load(st, path);
                         compute_differentials(sc, s, sx, aux, rc.spp, rc.option_flags);
                         tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
-                        if (sc.texture_mappings != nullptr) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; tc.pdp = pdp; }
+                        if (tex_needs_ctx(sc)) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; pdp[3] = s.n; tc.pdp = pdp; }
                         have_ctx = true;
                     }
                     amt = eval_float_texture(sc, mm.tex_mix_amount, tc);
@@ -629,11 +629,11 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 } else if (mat.normal_map >= 0) normal_map(sc, mat.normal_map, s, sx);              // only without a displacement: interaction.rs:229-244
             }
             if ((mat.flags & SG_MAT_HAS_DISPLACEMENT) || (TEX && mat.normal_map >= 0)) apply_constant_bump(s);
-            float3 pdp[3];
+            float3 pdp[4];
             TexCoordCtx tc;
             if (TEX) {
                 tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
-                if (sc.texture_mappings != nullptr) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; tc.pdp = pdp; }
+                if (tex_needs_ctx(sc)) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; pdp[3] = s.n; tc.pdp = pdp; }
             }
             BSDF<KIND> bsdf;
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
@@ -989,16 +989,17 @@ static __global__ void k_camera_rays(const __grid_constant__ DScene sc, RenderCo
     l[0] = lam.lambda.x; l[1] = lam.lambda.y; l[2] = lam.lambda.z; l[3] = lam.lambda.w;
     l[4] = lam.pdf.x; l[5] = lam.pdf.y; l[6] = lam.pdf.z; l[7] = lam.pdf.w;
 }
-static __global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* pdp_in, const float* lambda, float* out) {
+static __global__ void k_texture_eval(const __grid_constant__ DScene sc, int tex, int as_float, long long n, const float* q, const float* pdp_in, const float* nrm_in, const float* lambda, float* out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     TexCoordCtx c; c.uv = make_float2(q[6 * i], q[6 * i + 1]); c.dudx = q[6 * i + 2]; c.dudy = q[6 * i + 3]; c.dvdx = q[6 * i + 4]; c.dvdy = q[6 * i + 5];
-    float3 pdp[3];
+    float3 pdp[4] = {f3(0.0f, 0.0f, 0.0f), f3(0.0f, 0.0f, 0.0f), f3(0.0f, 0.0f, 0.0f), f3(0.0f, 0.0f, 0.0f)};
     if (pdp_in) {
         const float* r = pdp_in + 9 * i;
         pdp[0] = f3(r[0], r[1], r[2]); pdp[1] = f3(r[3], r[4], r[5]); pdp[2] = f3(r[6], r[7], r[8]);
-        c.pdp = pdp;
     }
+    if (nrm_in) pdp[3] = f3(nrm_in[3 * i], nrm_in[3 * i + 1], nrm_in[3 * i + 2]);
+    if (pdp_in || nrm_in) c.pdp = pdp;
     Spec s;
     if (as_float) s = spec1(eval_float_texture(sc, tex, c));
     else {

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <functional>
 #include <vector>
 #include <new>
 #include <thread>
@@ -247,7 +248,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const SgMaterial& m = desc->materials[i];
         if (m.kind == SG_MATERIAL_MIX) continue;
-        if (m.normal_map >= (int32_t)desc->n_textures || (m.normal_map >= 0 && desc->textures[m.normal_map].n_channels != 3))
+        if (m.normal_map >= (int32_t)desc->n_textures || (m.normal_map >= 0 && (desc->textures[m.normal_map].n_channels != 3 || desc->textures[m.normal_map].kind != SG_TEXTURE_IMAGE)))
             return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + ": normal maps must be three-channel images");
         for (int32_t t : {m.tex_reflectance, m.tex_displacement})
             if (t >= (int32_t)desc->n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + " references an out-of-range texture");
@@ -257,9 +258,31 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             return fail(SG_ERR_UNSUPPORTED, "displacement textures must be one-channel images");
     }
     bool need_rgb2spec = false;
+    // depth of a texture tree below row i (image / constant rows: 0); -1 = malformed (bad ids, wrong operand type, cycle, too deep)
+    std::function<int(int32_t, bool, int)> tex_depth = [&](int32_t id, bool want_float, int budget) -> int {
+        if (id < 0 || (uint32_t)id >= desc->n_textures || budget < 0) return -1;
+        const SgTexture& t = desc->textures[id];
+        if (want_float && t.n_channels != 1) return -1;
+        if (t.kind == SG_TEXTURE_IMAGE) return 0;
+        if (t.kind < SG_TEXTURE_CONSTANT || t.kind > SG_TEXTURE_DIRECTION_MIX || !desc->texture_nodes || t.node < 0 || (uint32_t)t.node >= desc->n_texture_nodes) return -1;
+        const SgTextureNode& nd = desc->texture_nodes[t.node];
+        if (t.kind == SG_TEXTURE_CONSTANT) return (t.n_channels == 1 || nd.spectrum < 0 || (uint32_t)nd.spectrum < desc->n_spectra) ? 0 : -1;
+        const bool is_float = t.n_channels == 1;
+        const int a = tex_depth(nd.tex1, is_float, budget - 1);
+        const int b = tex_depth(nd.tex2, t.kind == SG_TEXTURE_SCALED ? true : is_float, budget - 1);
+        const int c = t.kind == SG_TEXTURE_MIX ? tex_depth(nd.amount, true, budget - 1) : 0;
+        if (a < 0 || b < 0 || c < 0) return -1;
+        return 1 + std::max(a, std::max(b, c));
+    };
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
         const SgTexture& t = desc->textures[i];
-        if (!desc->textures || !desc->image_levels || !desc->texels) return fail(SG_ERR_INVALID_ARGUMENT, "texture arrays missing");
+        if (!desc->textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture arrays missing");
+        if (t.kind != SG_TEXTURE_IMAGE) {
+            if (t.n_channels < 1 || tex_depth((int32_t)i, false, SG_MAX_TEXTURE_DEPTH) < 0)
+                return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": bad kind / node / operand ids or types, a cycle, or operands nested deeper than SG_MAX_TEXTURE_DEPTH");
+            continue;
+        }
+        if (!desc->image_levels || !desc->texels) return fail(SG_ERR_INVALID_ARGUMENT, "texture arrays missing");
         if ((t.n_channels != 1 && t.n_channels != 3) || t.n_levels < 1 || (uint64_t)t.first_level + (uint64_t)t.n_levels > desc->n_image_levels)
             return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": bad channel count or level range");
         if (t.wrap < SG_WRAP_REPEAT || t.wrap > SG_WRAP_CLAMP || t.filter < SG_FILTER_POINT || t.filter > SG_FILTER_EWA ||
@@ -474,6 +497,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     UP(image_levels, desc->image_levels, desc->n_textures ? desc->n_image_levels : 0, SgImageLevel);
     UP(texels, desc->texels, (desc->n_textures || desc->n_env_maps) ? desc->n_texels : 0, float);
     UP(texture_mappings, desc->texture_mappings, desc->n_texture_mappings, SgTextureMapping);
+    UP(texture_nodes, desc->texture_nodes, desc->n_texture_nodes, SgTextureNode);
     UP(env_maps, desc->env_maps, desc->n_env_maps, SgEnvMap);
     UP(mip_lut, desc->mip_filter_lut, desc->mip_filter_lut ? 128 : 0, float);
     UP(rgb2spec_scale, desc->rgb2spec_scale, need_rgb2spec ? desc->rgb2spec_res : 0, float);
@@ -778,27 +802,31 @@ int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_
     return SG_OK;
 }
 
-int sg_texture_eval_p(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda, float* out) {
+int sg_texture_eval_ctx(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* nrm, const float* lambda, float* out) {
     if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
     if (!s || n < 0 || (n > 0 && (!q || !lambda || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (tex < 0 || (uint32_t)tex >= s->d.n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture id out of range");
     if (n == 0) return SG_OK;
-    float *d_q = nullptr, *d_l = nullptr, *d_o = nullptr, *d_p = nullptr;
-    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_l); cudaFree(d_o); cudaFree(d_p); };
+    float *d_q = nullptr, *d_l = nullptr, *d_o = nullptr, *d_p = nullptr, *d_n = nullptr;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_l); cudaFree(d_o); cudaFree(d_p); cudaFree(d_n); };
 #define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(SG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
     CUX(cudaMalloc((void**)&d_q, (size_t)n * 24)); CUX(cudaMalloc((void**)&d_l, (size_t)n * 16)); CUX(cudaMalloc((void**)&d_o, (size_t)n * 16));
     CUX(cudaMemcpy(d_q, q, (size_t)n * 24, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_l, lambda, (size_t)n * 16, cudaMemcpyHostToDevice));
     if (pdp) { CUX(cudaMalloc((void**)&d_p, (size_t)n * 36)); CUX(cudaMemcpy(d_p, pdp, (size_t)n * 36, cudaMemcpyHostToDevice)); }
-    k_texture_eval<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, tex, as_float, (long long)n, d_q, d_p, d_l, d_o);
+    if (nrm) { CUX(cudaMalloc((void**)&d_n, (size_t)n * 12)); CUX(cudaMemcpy(d_n, nrm, (size_t)n * 12, cudaMemcpyHostToDevice)); }
+    k_texture_eval<<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(s->d, tex, as_float, (long long)n, d_q, d_p, d_n, d_l, d_o);
     CUX(cudaStreamSynchronize(g_stream));
     CUX(cudaMemcpy(out, d_o, (size_t)n * 16, cudaMemcpyDeviceToHost));
 #undef CUX
     cleanup();
     return SG_OK;
 }
+int sg_texture_eval_p(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* lambda, float* out) {
+    return sg_texture_eval_ctx(s, tex, as_float, n, q, pdp, nullptr, lambda, out);
+}
 int sg_texture_eval(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* lambda, float* out) {
-    return sg_texture_eval_p(s, tex, as_float, n, q, nullptr, lambda, out);
+    return sg_texture_eval_ctx(s, tex, as_float, n, q, nullptr, nullptr, lambda, out);
 }
 
 int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_rgb) {

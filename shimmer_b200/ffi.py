@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 7
+SG_ABI_VERSION = 8
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -83,7 +83,16 @@ class SgTexture(C.Structure):
     _fields_ = [("n_channels", C.c_int32), ("n_levels", C.c_int32), ("first_level", C.c_uint32), ("wrap", C.c_int32),
                 ("filter", C.c_int32), ("max_anisotropy", C.c_float), ("scale", C.c_float), ("invert", C.c_int32),
                 ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float),
-                ("spectrum_type", C.c_int32), ("mapping", C.c_int32), ("pad", C.c_int32 * 2)]
+                ("spectrum_type", C.c_int32), ("mapping", C.c_int32), ("kind", C.c_int32), ("node", C.c_int32)]
+
+
+SG_TEXTURE_IMAGE, SG_TEXTURE_CONSTANT, SG_TEXTURE_SCALED, SG_TEXTURE_MIX, SG_TEXTURE_DIRECTION_MIX = range(5)
+SG_MAX_TEXTURE_DEPTH = 3
+
+
+class SgTextureNode(C.Structure):
+    _fields_ = [("tex1", C.c_int32), ("tex2", C.c_int32), ("amount", C.c_int32), ("spectrum", C.c_int32),
+                ("value", C.c_float), ("dir", C.c_float * 3)]
 
 
 class SgTextureMapping(C.Structure):
@@ -158,6 +167,7 @@ class SgSceneDesc(C.Structure):
                 ("rgb2spec_res", C.c_uint32), ("rgb2spec_scale", C.POINTER(C.c_float)), ("rgb2spec_data", C.POINTER(C.c_float)),
                 ("n_texture_mappings", C.c_uint32), ("texture_mappings", C.POINTER(SgTextureMapping)),
                 ("n_env_maps", C.c_uint32), ("env_maps", C.POINTER(SgEnvMap)),
+                ("n_texture_nodes", C.c_uint32), ("texture_nodes", C.POINTER(SgTextureNode)),
                 ("camera", SgCamera), ("film", SgFilm)]
 
 
@@ -191,7 +201,7 @@ class SgHit(C.Structure):
 # every symbol include/shimmer_gpu.h declares; tests/test_abi.py checks the library exports all
 ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
                "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
-               "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_film_get_image", "sg_image_pyramid_layout",
+               "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_texture_eval_ctx", "sg_film_get_image", "sg_image_pyramid_layout",
                "sg_image_generate_pyramid"]
 
 
@@ -234,6 +244,7 @@ def load_library():
     lib.sg_film_get_image.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, vp]; lib.sg_film_get_image.restype = C.c_int
     lib.sg_texture_eval.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp]; lib.sg_texture_eval.restype = C.c_int
     lib.sg_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp, vp]; lib.sg_texture_eval_p.restype = C.c_int
+    lib.sg_texture_eval_ctx.argtypes = [vp, C.c_int, C.c_int, i64, vp, vp, vp, vp, vp]; lib.sg_texture_eval_ctx.restype = C.c_int
     lib.sg_image_pyramid_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]; lib.sg_image_pyramid_layout.restype = C.c_int
     lib.sg_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; lib.sg_image_generate_pyramid.restype = C.c_int
     _lib = lib

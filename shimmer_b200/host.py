@@ -357,6 +357,34 @@ class SceneBuilder:
                                   mapping=-1 if mapping is None else mapping))
         return len(self.textures) - 1
 
+    # -- the non-image members of FloatTexture / SpectrumTexture (texture.rs:88-94,411-417) --------------------
+    def _node_texture(self, kind, is_spectrum, **node):
+        self.textures.append(dict(kind=kind, n_channels=3 if is_spectrum else 1, node=node))
+        return len(self.textures) - 1
+
+    def _is_spectrum_texture(self, tex):
+        return self.textures[tex]["n_channels"] != 1
+
+    def constant_texture(self, value=None, spectrum=None):
+        """FloatConstantTexture (texture.rs:154-179; `value`) or SpectrumConstantTexture (:485-535; `spectrum` = spectrum id)."""
+        if spectrum is not None:
+            return self._node_texture(ffi.SG_TEXTURE_CONSTANT, True, spectrum=int(spectrum))
+        return self._node_texture(ffi.SG_TEXTURE_CONSTANT, False, value=float(value))
+
+    def scaled_texture(self, tex, scale):
+        """Float/SpectrumScaledTexture (texture.rs:180-213,:537-583): `scale` is a float texture id."""
+        return self._node_texture(ffi.SG_TEXTURE_SCALED, self._is_spectrum_texture(tex), tex1=tex, tex2=scale)
+
+    def mix_texture(self, tex1, tex2, amount):
+        """Float/SpectrumMixTexture (texture.rs:215-262,:585-651): `amount` is a float texture id."""
+        return self._node_texture(ffi.SG_TEXTURE_MIX, self._is_spectrum_texture(tex1) or self._is_spectrum_texture(tex2),
+                                  tex1=tex1, tex2=tex2, amount=amount)
+
+    def direction_mix_texture(self, tex1, tex2, dir=(0.0, 1.0, 0.0)):
+        """Float/SpectrumDirectionMixTexture (texture.rs:264-310,:653-826): amount = dot(n, dir), `dir` in render space as given."""
+        return self._node_texture(ffi.SG_TEXTURE_DIRECTION_MIX, self._is_spectrum_texture(tex1) or self._is_spectrum_texture(tex2),
+                                  tex1=tex1, tex2=tex2, dir=tuple(float(x) for x in dir))
+
     def texture_mapping(self, kind, texture_from_world=None, v1=(1.0, 0.0, 0.0), v2=(0.0, 1.0, 0.0), udelta=0.0, vdelta=0.0):
         """TextureMapping2D::create (texture.rs:853-893) for "spherical" / "cylindrical" / "planar":
         texture_from_render = (render_from_texture)^-1 with render_from_texture = render_from_world * CTM; the planar
@@ -935,8 +963,16 @@ class SceneBuilder:
         # image textures: every MIP level, linear f32 texels, channels interleaved
         tex_rows = (ffi.SgTexture * max(len(self.textures), 1))()
         level_rows, texel_chunks, toff = [], [], 0
+        node_rows = []
         for ti, t in enumerate(self.textures):
             r = tex_rows[ti]
+            if t.get("kind", 0) != ffi.SG_TEXTURE_IMAGE:
+                nd = ffi.SgTextureNode(); nn = t["node"]
+                nd.tex1, nd.tex2, nd.amount, nd.spectrum = nn.get("tex1", -1), nn.get("tex2", -1), nn.get("amount", -1), nn.get("spectrum", -1)
+                nd.value = nn.get("value", 0.0); nd.dir[:] = list(nn.get("dir", (0.0, 1.0, 0.0)))
+                r.n_channels, r.kind, r.node, r.mapping = t["n_channels"], t["kind"], len(node_rows), -1
+                node_rows.append(nd)
+                continue
             r.n_channels, r.n_levels, r.first_level = t["n_channels"], len(t["levels"]), len(level_rows)
             r.wrap, r.filter, r.max_anisotropy, r.scale, r.invert = t["wrap"], t["filter"], t["max_anisotropy"], t["scale"], t["invert"]
             r.su, r.sv, r.du, r.dv, r.spectrum_type = t["su"], t["sv"], t["du"], t["dv"], t["spectrum_type"]
@@ -945,6 +981,7 @@ class SceneBuilder:
                 L = ffi.SgImageLevel(); L.offset = toff; L.res[:] = [lv.shape[1], lv.shape[0]]
                 level_rows.append(L); texel_chunks.append(np.ascontiguousarray(lv, np.float32).ravel()); toff += lv.size
         A["textures"] = tex_rows
+        A["texture_nodes"] = (ffi.SgTextureNode * max(len(node_rows), 1))(*node_rows)
         map_rows = (ffi.SgTextureMapping * max(len(self.mappings), 1))()
         for mi_, mp in enumerate(self.mappings):
             r = map_rows[mi_]
@@ -959,7 +996,7 @@ class SceneBuilder:
         A["image_levels"] = (ffi.SgImageLevel * max(len(level_rows), 1))(*level_rows)
         A["texels"] = np.concatenate(texel_chunks) if texel_chunks else np.zeros(1, np.float32)
         A["mip_lut"] = np.ascontiguousarray(tables()["MIP_FILTER_LUT"], np.float32)
-        need_rgb = any(t["n_channels"] == 3 for t in self.textures) or len(self.env_maps) > 0
+        need_rgb = any(t["n_channels"] == 3 and t.get("kind", 0) == ffi.SG_TEXTURE_IMAGE for t in self.textures) or len(self.env_maps) > 0
         if need_rgb:
             from . import rgb2spec
             sc_, dt_ = rgb2spec.build_table(16)
@@ -991,6 +1028,7 @@ class SceneBuilder:
             d.rgb2spec_res = len(A["rgb2spec_scale"]); d.rgb2spec_scale = _as_ptr(A["rgb2spec_scale"], C.c_float)
             d.rgb2spec_data = _as_ptr(A["rgb2spec_data"], C.c_float)
         d.n_texture_mappings = len(self.mappings); d.texture_mappings = A["texture_mappings"]
+        d.n_texture_nodes = len(node_rows); d.texture_nodes = A["texture_nodes"] if node_rows else None
         d.n_env_maps = len(self.env_maps); d.env_maps = A["env_maps"]
         d.camera = self.camera
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids

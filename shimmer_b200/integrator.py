@@ -154,6 +154,20 @@ class WavefrontPathIntegrator(Integrator):
                                             out.ctypes.data), "sg_texture_eval")
         return out
 
+    def texture_eval_ctx(self, tex, q, n, p=None, lambda4=None, as_float=False):
+        """Texture lookups with TextureEvalContext::n (and optionally p): the direction-mix textures (texture.rs:295-310,:810-826)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 6); cnt = len(q)
+        nrm = np.ascontiguousarray(n, np.float32).reshape(-1, 3)
+        pdp = None
+        if p is not None:
+            pdp = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 3), np.zeros((cnt, 6), np.float32)], axis=1), np.float32)
+        lam = np.ascontiguousarray(np.tile([450.0, 520.0, 600.0, 680.0], (cnt, 1)) if lambda4 is None else lambda4, np.float32).reshape(-1, 4)
+        out = np.zeros((cnt, 4), np.float32)
+        ffi.check(self._lib.sg_texture_eval_ctx(self._handle, int(tex), 1 if as_float else 0, cnt, q.ctypes.data,
+                                                None if pdp is None else pdp.ctypes.data, nrm.ctypes.data, lam.ctypes.data, out.ctypes.data),
+                  "sg_texture_eval_ctx")
+        return out
+
     def texture_eval_p(self, tex, p, q=None, dpdx=None, dpdy=None, lambda4=None, as_float=False):
         """Texture lookups with the full TextureEvalContext (p, dpdx, dpdy in render space): the non-UV mappings
         (texture.rs:938-1035)."""

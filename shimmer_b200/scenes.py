@@ -478,7 +478,7 @@ def instanced_shapes_tiny_scene(kind="instshapes", resolution=(32, 32), flatten=
 
 
 VARIETY_KINDS = ("envmap", "envonly", "envrot", "coatedcond", "coatedcondrough", "coatedcondrefl", "normalmap", "texsph", "texcyl", "texplanar",
-                 "mix", "mixtex", "mixnested")
+                 "mix", "mixtex", "mixnested", "textree", "textreemix")
 
 
 def procedural_envmap(n=32):
@@ -548,6 +548,27 @@ def variety_tiny_scene(kind, resolution=(32, 32)):
         inner = b.mix(b.diffuse(_green()), b.diffuse(_red()), amount=0.5)
         mat = b.mix(inner, b.conductor(named_spectrum("metal-Ag-eta"), named_spectrum("metal-Ag-k"), roughness=0.0), amount=0.3)
         ground = b.mix(white, white, amount=1.5)
+    elif kind == "textree":
+        # the non-image textures (texture.rs:180-310,:537-826): sphere reflectance = mix(rgb image, scaled(constant spectrum, float image),
+        # amount = direction_mix(0.1, 0.95, +y)); ground reflectance = direction_mix(constant spectrum, one-channel image, tilted dir)
+        # with a displacement = scaled(float image, constant 0.03)
+        mono = b.image_texture(procedural_image(32, 1), filter="bilinear", su=3.0, sv=3.0)
+        rgb = b.image_texture(procedural_image(64, 3), filter="trilinear")
+        red = b.constant_texture(spectrum=b.spectrum(_red()))
+        amt = b.direction_mix_texture(b.constant_texture(0.1), b.constant_texture(0.95), dir=(0.0, 1.0, 0.0))
+        mat = b.diffuse(_white(), reflectance_tex=b.mix_texture(rgb, b.scaled_texture(red, mono), amt))
+        gtex = b.direction_mix_texture(b.constant_texture(spectrum=b.spectrum(_green())), mono, dir=(0.3, 0.8, 0.1))
+        ground = b.diffuse(_white(), reflectance_tex=gtex, displacement_tex=b.scaled_texture(mono, b.constant_texture(0.03)))
+    elif kind == "textreemix":
+        # a three-level float tree as the MixMaterial amount and a scaled-by-zero / amount-0 / amount-1 short-circuit on the ground
+        mono = b.image_texture(procedural_image(32, 1), filter="bilinear", su=2.0, sv=2.0)
+        inner = b.mix_texture(b.scaled_texture(mono, b.constant_texture(0.8)), b.constant_texture(0.9), mono)
+        amt = b.scaled_texture(inner, b.constant_texture(1.1))
+        mat = b.mix(b.diffuse(_green()), b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.1), amount_tex=amt)
+        rgb = b.image_texture(procedural_image(64, 3), filter="ewa")
+        zero = b.scaled_texture(rgb, b.constant_texture(0.0))
+        gtex = b.mix_texture(b.mix_texture(zero, rgb, b.constant_texture(1.0)), zero, b.constant_texture(0.0))
+        ground = b.diffuse(_white(), reflectance_tex=gtex)
     else:
         raise ValueError(kind)
     P, I, Nn, UV = uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)

@@ -65,6 +65,7 @@ def lib():
     L.orc_rgb2spec_fetch.argtypes = [vp, vp, vp]
     L.orc_texture_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
     L.orc_texture_eval_p.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp]
+    L.orc_texture_eval_ctx.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
     L.orc_image_pyramid_levels.argtypes = [C.c_int32, C.c_int32, vp]; L.orc_image_pyramid_levels.restype = C.c_int32
     L.orc_image_generate_pyramid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]; L.orc_image_generate_pyramid.restype = C.c_int32
     L.orc_path_rays.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp]; L.orc_path_rays.restype = C.c_int64
@@ -155,6 +156,18 @@ def texture_eval_p(scene, tex, p, q=None, dpdx=None, dpdy=None, lambda4=None, as
     lam = fa(np.tile([450.0, 520.0, 600.0, 680.0], (n, 1)) if lambda4 is None else lambda4).reshape(-1, 4)
     out = np.zeros((n, 4), np.float32)
     lib().orc_texture_eval_p(scene.ptr(), int(tex), 1 if as_float else 0, n, q.ctypes.data, pdp.ctypes.data, lam.ctypes.data, out.ctypes.data)
+    return out
+
+
+def texture_eval_ctx(scene, tex, q, n, p=None, lambda4=None, as_float=False):
+    """Texture lookups with TextureEvalContext::n (and optionally p) -- the direction-mix textures."""
+    q = fa(q).reshape(-1, 6); cnt = len(q)
+    nrm = fa(n).reshape(-1, 3)
+    pdp = None if p is None else fa(np.concatenate([fa(p).reshape(-1, 3), np.zeros((cnt, 6), np.float32)], axis=1))
+    lam = fa(np.tile([450.0, 520.0, 600.0, 680.0], (cnt, 1)) if lambda4 is None else lambda4).reshape(-1, 4)
+    out = np.zeros((cnt, 4), np.float32)
+    lib().orc_texture_eval_ctx(scene.ptr(), int(tex), 1 if as_float else 0, cnt, q.ctypes.data, None if pdp is None else pdp.ctypes.data,
+                               nrm.ctypes.data, lam.ctypes.data, out.ctypes.data)
     return out
 
 

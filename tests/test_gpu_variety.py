@@ -173,3 +173,57 @@ def test_device_pyramid_feeds_a_texture_and_rejects_what_the_reference_asserts_o
         generate_pyramid(np.zeros((50, 64, 3), np.float32))                 # 64 is already a power of two: image.rs:1009 asserts
     with pytest.raises(ShimmerGpuError, match="repeat and clamp"):
         generate_pyramid(np.zeros((5, 3, 3), np.float32), "black")
+
+
+def test_composite_texture_lookup_parity():
+    """sg_texture_eval_ctx vs the oracle for the non-image textures (texture.rs:180-310,:537-826): constant, scaled, mix and
+    direction-mix, float and spectrum typed, nested three deep, including the short circuits that keep a +inf operand from
+    turning the result into NaN.  Leaves are point / bilinear images, whose lookups are exact f32 arithmetic up to the level
+    choice (log2f), hence the small allowance; everything above the leaves must then agree bit for bit."""
+    from test_oracle_variety import composite_texture_scene, composite_texture_queries
+    b, T = composite_texture_scene()
+    sc = b.build()
+    integ = create_integrator("wavefront", {}, sc, {"pixelsamples": 1})
+    q, nrm, lam = composite_texture_queries(n=4096)
+    for name, tex in T.items():
+        for as_float in ([True] if sc.arrays["textures"][tex].n_channels == 1 else []) + [False]:
+            got = integ.texture_eval_ctx(tex, q, nrm, lambda4=lam, as_float=as_float)
+            exp = orc.texture_eval_ctx(sc, tex, q, nrm, lambda4=lam, as_float=as_float)
+            same = ((got == exp) | (np.isnan(got) & np.isnan(exp))).all(axis=1)
+            close = same | np.isclose(got, exp, rtol=2e-5, atol=2e-6).all(axis=1)
+            assert close.mean() > 0.998 and same.mean() > 0.98, (name, as_float, same.mean(), close.mean())
+            if name.startswith("c") or name.startswith("sc_scale0"):
+                assert same.all(), name
+    integ.close()
+
+
+def test_malformed_texture_trees_are_rejected():
+    from shimmer_b200 import ffi, ShimmerGpuError
+    def scene_with(build):
+        b = SceneBuilder(); b.set_camera((0, 0, -3), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+        mono = b.image_texture(scenes.procedural_image(8, 1)); rgb = b.image_texture(scenes.procedural_image(8, 3))
+        t = build(b, mono, rgb)
+        m = b.diffuse(("const", 0.5), reflectance_tex=t)
+        b.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32), m)
+        return b.build()
+    def too_deep(b, mono, rgb):
+        t = mono
+        for _ in range(ffi.SG_MAX_TEXTURE_DEPTH + 1):
+            t = b.scaled_texture(t, mono)
+        return t
+    with pytest.raises(ShimmerGpuError, match="SG_MAX_TEXTURE_DEPTH"):
+        create_integrator("wavefront", {}, scene_with(too_deep))
+    def ok_depth(b, mono, rgb):
+        t = rgb
+        for _ in range(ffi.SG_MAX_TEXTURE_DEPTH):
+            t = b.scaled_texture(t, mono)
+        return t
+    create_integrator("wavefront", {}, scene_with(ok_depth)).close()
+    sc = scene_with(lambda b, mono, rgb: b.scaled_texture(rgb, mono))
+    sc.arrays["texture_nodes"][0].tex1 = sc.desc.n_textures - 1                # its own row: a cycle
+    with pytest.raises(ShimmerGpuError, match="cycle"):
+        create_integrator("wavefront", {}, sc)
+    sc = scene_with(lambda b, mono, rgb: b.scaled_texture(rgb, mono))
+    sc.arrays["texture_nodes"][0].tex2 = 1                                      # `scale` must be a float texture
+    with pytest.raises(ShimmerGpuError, match="operand"):
+        create_integrator("wavefront", {}, sc)

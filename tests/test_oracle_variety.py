@@ -279,3 +279,96 @@ def test_generate_pyramid_oracle_properties():
     b = SceneBuilder(); b.set_camera((0, 0, -3), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
     t = b.image_texture(None, levels=lr)
     assert b.textures[t]["n_channels"] == 3 and len(b.textures[t]["levels"]) == 6
+
+
+# ---- the non-image members of FloatTexture / SpectrumTexture (texture.rs:180-310, :537-826) --------------------------------
+f32 = np.float32
+
+
+def composite_texture_scene():
+    """One scene holding every non-image texture kind, float and spectrum typed; shared with the GPU lookup-parity test."""
+    b = SceneBuilder(); b.set_camera((0, 0, -3), (0, 0, 0), (0, 1, 0), 40.0, (8, 8))
+    T = {}
+    T["mono"] = b.image_texture(scenes.procedural_image(32, 1), filter="bilinear", su=2.0, sv=3.0)
+    T["mono2"] = b.image_texture(scenes.procedural_image(16, 1), filter="point", wrap="clamp")
+    T["rgb"] = b.image_texture(scenes.procedural_image(64, 3), filter="bilinear")
+    T["c03"], T["c0"], T["c1"], T["cinf"] = b.constant_texture(0.3), b.constant_texture(0.0), b.constant_texture(1.0), b.constant_texture(float("inf"))
+    T["cspec"] = b.constant_texture(spectrum=b.spectrum(named_spectrum("metal-Cu-k")))
+    T["f_scaled"] = b.scaled_texture(T["mono"], T["c03"])
+    T["f_mix"] = b.mix_texture(T["mono"], T["mono2"], T["c03"])
+    T["f_mix_tex_amount"] = b.mix_texture(T["c03"], T["mono"], T["mono2"])
+    T["f_dir"] = b.direction_mix_texture(T["mono"], T["mono2"], dir=(0.2, 0.9, -0.4))
+    T["f_deep"] = b.scaled_texture(b.mix_texture(b.scaled_texture(T["mono"], T["mono2"]), T["c03"], T["mono"]), T["c03"])   # depth 3
+    T["s_scaled"] = b.scaled_texture(T["rgb"], T["mono"])
+    T["s_mix"] = b.mix_texture(T["rgb"], T["cspec"], T["mono2"])
+    T["s_dir"] = b.direction_mix_texture(T["cspec"], T["rgb"], dir=(0.0, 1.0, 0.0))
+    T["s_mono_operand"] = b.mix_texture(T["rgb"], T["mono"], T["c03"])           # a one-channel row as a spectrum operand (texture.rs:803-807)
+    # short circuits: the skipped operand is +inf, so evaluating it anyway would give NaN (inf * 0)
+    T["sc_scale0"] = b.scaled_texture(T["cinf"], T["c0"])
+    T["sc_mix1"] = b.mix_texture(T["cinf"], T["mono"], T["c1"])
+    T["sc_mix0"] = b.mix_texture(T["mono"], T["cinf"], T["c0"])
+    T["sc_dir"] = b.direction_mix_texture(T["cinf"], T["mono"], dir=(0.0, 1.0, 0.0))   # skipped where dot(n, dir) == 0
+    T["sc_dir1"] = b.direction_mix_texture(T["mono"], T["cinf"], dir=(0.0, 1.0, 0.0))  # skipped where dot(n, dir) == 1
+    m = b.diffuse(("const", 0.5), reflectance_tex=T["s_mix"], displacement_tex=T["f_scaled"])
+    b.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32), m)
+    return b, T
+
+
+def composite_texture_queries(n=2048, seed=21):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, 6), np.float32); q[:, :2] = rng.random((n, 2)) * 3.0 - 1.0
+    q[:, 2:] = (rng.random((n, 4)) - 0.5) * (10.0 ** rng.uniform(-4, -1.0, (n, 1)))
+    nrm = rng.standard_normal((n, 3)).astype(np.float32); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    nrm[: n // 8] = [1.0, 0.0, 0.0]                       # dot(n, +y) == 0
+    nrm[n // 8: n // 4] = [0.0, 1.0, 0.0]                 # dot(n, +y) == 1
+    lam = rng.uniform(360.0, 830.0, (n, 4)).astype(np.float32)
+    return q, nrm, lam
+
+
+def test_composite_textures_follow_the_reference_formulas():
+    b, T = composite_texture_scene()
+    sc = b.build()
+    q, nrm, lam = composite_texture_queries()
+    n = len(q)
+    f = lambda name: orc.texture_eval_ctx(sc, T[name], q, nrm, lambda4=lam, as_float=True)[:, 0]
+    s = lambda name: orc.texture_eval_ctx(sc, T[name], q, nrm, lambda4=lam, as_float=False)
+    mono, mono2, rgb, cspec = f("mono"), f("mono2"), s("rgb"), s("cspec")
+    one = f32(1.0)
+    assert np.array_equal(f("c03"), np.full(n, f32(0.3))) and np.array_equal(s("c03"), np.full((n, 4), f32(0.3)))
+    assert np.ptp(cspec, axis=0).max() > 0.0                                      # a real spectrum, sampled per wavelength
+    assert np.array_equal(f("f_scaled"), np.where(f32(0.3) == 0, 0, mono * f32(0.3)))                          # texture.rs:206-213
+    assert np.array_equal(f("f_mix"), mono * (one - f32(0.3)) + mono2 * f32(0.3))                              # :246-261
+    amt = mono2
+    t1 = np.where(amt != 1.0, f32(0.3), f32(0.0)); t2 = np.where(amt != 0.0, mono, f32(0.0))
+    assert np.array_equal(f("f_mix_tex_amount"), t1 * (one - amt) + t2 * amt)
+    d = np.array([0.2, 0.9, -0.4], np.float32)
+    amt = (nrm.astype(np.float64) @ d.astype(np.float64)).astype(np.float32)      # dot3 is fma-based: compare with a tolerance
+    assert np.allclose(f("f_dir"), amt * mono + (one - amt) * mono2, rtol=1e-5, atol=1e-6)                     # :295-310 (amt * t1: reversed w.r.t. Mix)
+    a_in = np.where(mono2 == 0, f32(0.0), mono * mono2)                          # scaled(mono, mono2)
+    inner = np.where(mono != 1, a_in, f32(0.0)) * (one - mono) + np.where(mono != 0, f32(0.3), f32(0.0)) * mono   # mix(., 0.3, amount = mono)
+    assert np.array_equal(f("f_deep"), inner * f32(0.3))
+    assert np.array_equal(s("s_scaled"), np.where(mono[:, None] == 0, 0, rgb * mono[:, None]))                 # :567-583
+    a2 = mono2[:, None]
+    assert np.array_equal(s("s_mix"), np.where(a2 != 1, rgb, 0) * (one - a2) + np.where(a2 != 0, cspec, 0) * a2)   # :631-651
+    ay = nrm[:, 1:2]                                                               # dot(n, (0,1,0)) == n.y exactly
+    assert np.array_equal(s("s_dir"), ay * np.where(ay != 0, cspec, 0) + (one - ay) * np.where(ay != 1, rgb, 0))    # :810-826
+    assert np.array_equal(s("s_mono_operand"), rgb * (one - f32(0.3)) + mono[:, None] * f32(0.3))
+    # short circuits exactly as written: the +inf operand is never touched where the reference skips it
+    assert np.array_equal(f("sc_scale0"), np.zeros(n, np.float32))
+    assert np.array_equal(f("sc_mix1"), mono) and np.array_equal(f("sc_mix0"), mono)
+    perp, par = slice(0, n // 8), slice(n // 8, n // 4)
+    assert np.array_equal(f("sc_dir")[perp], mono[perp]) and np.isinf(f("sc_dir")[par]).all()
+    assert np.array_equal(f("sc_dir1")[par], mono[par]) and np.isinf(f("sc_dir1")[perp]).all()
+
+
+def test_composite_texture_scene_renders_and_bumps():
+    """The textree scene uses a direction-mix reflectance and a scaled displacement: both change the film."""
+    base = scenes.tiny_scene("textree", resolution=(16, 16))
+    sc = base.build()
+    film, st, _ = orc.render(sc, orc.make_params(seed=5, spp=4))
+    assert np.isfinite(film).all() and film[:, :3].sum() > 0
+    flat = scenes.tiny_scene("textree", resolution=(16, 16))
+    for m in flat.materials:
+        m["tex_displacement"] = -1
+    film2, _, _ = orc.render(flat.build(), orc.make_params(seed=5, spp=4))
+    assert not np.array_equal(film, film2)
