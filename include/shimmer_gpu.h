@@ -192,6 +192,22 @@ typedef struct SgMaterial {
     int32_t tex_mix_amount;   /* FloatImageTexture for `amount` or -1                                                       */
 } SgMaterial;
 
+/* Texture-valued material parameters.  Every parameter the reference's materials read through `tex_eval.evaluate_float` /
+ * `evaluate_spectrum` (material.rs:456-499, 603-635, 917-963, 1188-1260) may be any texture (image, constant, scaled, mix,
+ * direction mix); the common case -- a `*ConstantTexture` -- stays in SgMaterial.  Optional table, one row per material
+ * (SgSceneDesc.material_textures, NULL = none): a texture id replaces the SgMaterial field of the same name, -1 keeps it.
+ * Float parameters need float textures (n_channels == 1).  `reflectance` of Diffuse / CoatedDiffuse, `displacement` and the mix
+ * `amount` keep their ids in SgMaterial (tex_reflectance, tex_displacement, tex_mix_amount). */
+typedef struct SgMaterialTextures {
+    int32_t u_roughness, v_roughness;   /* `uroughness` / `vroughness` (`roughness`): conductor, dielectric, coated interface        */
+    int32_t spec_a;                     /* conductor `eta`; coated conductor `conductor.eta` (or `reflectance` with SG_MAT_CONDUCTOR_REFLECTANCE) */
+    int32_t spec_b;                     /* conductor `k`; coated diffuse / coated conductor `albedo`                                  */
+    int32_t spec_d;                     /* coated conductor `conductor.k`                                                             */
+    int32_t thickness, g;               /* coated diffuse / coated conductor `thickness`, `g`                                         */
+    int32_t u_roughness2, v_roughness2; /* coated conductor `conductor.uroughness` / `conductor.vroughness`                           */
+    int32_t pad[3];
+} SgMaterialTextures;
+
 /* ---- image textures (src/texture.rs:393-404,700-808,896-936, src/mipmap.rs:121-331, src/image.rs:134-177,619-646) ------
  * The host owns image decoding and pyramid generation (image.rs:699-846); it passes every MIP
  * level as linear f32 texels (what `Image::get_channel` returns after colour-decoding), channels
@@ -373,6 +389,7 @@ typedef struct SgSceneDesc {
     uint32_t n_texture_mappings; const SgTextureMapping* texture_mappings;
     uint32_t n_env_maps;   const SgEnvMap*    env_maps;     /* texels / spectrum_pool hold their data */
     uint32_t n_texture_nodes; const SgTextureNode* texture_nodes;   /* operands of the non-image textures */
+    const SgMaterialTextures* material_textures;            /* n_materials rows or NULL (no texture-valued parameters)      */
     SgCamera camera;
     SgFilm   film;
 } SgSceneDesc;

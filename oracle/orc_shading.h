@@ -553,21 +553,36 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
             else { const Float u = mr.get_1d(); si.material = amt < u ? mm.mix_materials[0] : mm.mix_materials[1]; }
         }
     }
-    const SgMaterial& m = D->materials[si.material];
-    if ((m.flags & SG_MAT_HAS_DISPLACEMENT) || m.normal_map >= 0) {              // interaction.rs:225-250
+    const SgMaterial& m0 = D->materials[si.material];
+    if ((m0.flags & SG_MAT_HAS_DISPLACEMENT) || m0.normal_map >= 0) {              // interaction.rs:225-250
         // bump_map (material.rs:1477-1509) or, only without a displacement, normal_map (:1453-1474); then
         // set_shading_geometry(ns, dpdu, dpdv, dndu, dndv, false)
         V3 dpdu, dpdv;
-        if (m.flags & SG_MAT_HAS_DISPLACEMENT) {
-            if (m.tex_displacement >= 0 || m.displacement != 0.0f) bump_map(D, m.tex_displacement, m.displacement, si, &dpdu, &dpdv);
+        if (m0.flags & SG_MAT_HAS_DISPLACEMENT) {
+            if (m0.tex_displacement >= 0 || m0.displacement != 0.0f) bump_map(D, m0.tex_displacement, m0.displacement, si, &dpdu, &dpdv);
             else { dpdu = si.sdpdu; dpdv = si.sdpdv; }    // constant 0: dpdu + 0/du*n + 0*dndu
-        } else normal_map(D, m.normal_map, si, &dpdu, &dpdv);
+        } else normal_map(D, m0.normal_map, si, &dpdu, &dpdv);
         V3 ns = normalize(cross(dpdu, dpdv));                                   // interaction.rs:246
         si.sn = face_forward(ns, si.n);                                          // :379-405
         si.sdpdu = dpdu; si.sdpdv = dpdv;
         while (length_squared(si.sdpdu) > 1e16f || length_squared(si.sdpdv) > 1e16f) { si.sdpdu = si.sdpdu / 1e8f; si.sdpdv = si.sdpdv / 1e8f; }
     }
     TexCoordCtx tc = {si.uv, si.dudx, si.dudy, si.dvdx, si.dvdy, si.p(), si.dpdx, si.dpdy, si.n};
+    // texture-valued parameters (SgMaterialTextures): tex_eval.evaluate_float / evaluate_spectrum of material.rs:456-499, 603-635, 917-963, 1188-1260
+    SgMaterial m = D->materials[si.material];
+    Spec tex_a, tex_b, tex_d; bool has_a = false, has_b = false, has_d = false;
+    if (D->material_textures) {
+        const SgMaterialTextures& mt = D->material_textures[si.material];
+        if (mt.u_roughness >= 0) m.u_roughness = eval_float_texture(D, mt.u_roughness, tc);
+        if (mt.v_roughness >= 0) m.v_roughness = eval_float_texture(D, mt.v_roughness, tc);
+        if (mt.thickness >= 0) m.thickness = eval_float_texture(D, mt.thickness, tc);
+        if (mt.g >= 0) m.g = eval_float_texture(D, mt.g, tc);
+        if (mt.u_roughness2 >= 0) m.u_roughness2 = eval_float_texture(D, mt.u_roughness2, tc);
+        if (mt.v_roughness2 >= 0) m.v_roughness2 = eval_float_texture(D, mt.v_roughness2, tc);
+        if (mt.spec_a >= 0) { tex_a = eval_spectrum_texture(D, mt.spec_a, tc, lambda); has_a = true; }
+        if (mt.spec_b >= 0) { tex_b = eval_spectrum_texture(D, mt.spec_b, tc, lambda); has_b = true; }
+        if (mt.spec_d >= 0) { tex_d = eval_spectrum_texture(D, mt.spec_d, tc, lambda); has_d = true; }
+    }
     BSDF b;
     b.kind = m.kind; b.r = spec_const(0.0f); b.k = spec_const(0.0f); b.eta = 1.0f; b.mf = TR::make(0.0f, 0.0f);
     b.lay.mf = TR::make(0.0f, 0.0f); b.lay.mfb = TR::make(0.0f, 0.0f);
@@ -576,8 +591,8 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
     } else if (m.kind == SG_MATERIAL_CONDUCTOR) {
         Float ur = m.u_roughness, vr = m.v_roughness;
         if (m.flags & SG_MAT_REMAP_ROUGHNESS) { ur = std::sqrt(ur); vr = std::sqrt(vr); }   // roughness_to_alpha scattering.rs:197-199
-        b.r = spectrum_sample(D, m.spec_a, lambda);
-        b.k = spectrum_sample(D, m.spec_b, lambda);
+        b.r = has_a ? tex_a : spectrum_sample(D, m.spec_a, lambda);
+        b.k = has_b ? tex_b : spectrum_sample(D, m.spec_b, lambda);
         b.mf = TR::make(ur, vr);
     } else if (m.kind == SG_MATERIAL_COATED_DIFFUSE) {                       // material.rs:917-963
         b.lay.r = spec_clamp(m.tex_reflectance >= 0 ? eval_spectrum_texture(D, m.tex_reflectance, tc, lambda) : spectrum_sample(D, m.spec_a, lambda), 0.0f, 1.0f);
@@ -589,7 +604,7 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         if (D->spectra[m.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lambda);
         if (sampled_eta == 0.0f) sampled_eta = 1.0f;
         b.lay.eta = sampled_eta;
-        b.lay.albedo = spec_clamp(spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
+        b.lay.albedo = spec_clamp(has_b ? tex_b : spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
         b.lay.g = clampf(m.g, -1.0f, 1.0f);
         b.lay.max_depth = m.max_depth; b.lay.n_samples = m.n_samples;
         b.mf = b.lay.mf;
@@ -603,9 +618,9 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         if (ieta == 0.0f) ieta = 1.0f;
         b.lay.eta = ieta;
         Spec ce, ck;
-        if (!(m.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = spectrum_sample(D, m.spec_a, lambda); ck = spectrum_sample(D, m.spec_d, lambda); }
+        if (!(m.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = has_a ? tex_a : spectrum_sample(D, m.spec_a, lambda); ck = has_d ? tex_d : spectrum_sample(D, m.spec_d, lambda); }
         else {                                                               // :1225-1233
-            Spec r = spec_clamp(spectrum_sample(D, m.spec_a, lambda), 0.0f, 0.9999f);
+            Spec r = spec_clamp(has_a ? tex_a : spectrum_sample(D, m.spec_a, lambda), 0.0f, 0.9999f);
             ce = spec_const(1.0f);
             for (int i = 0; i < 4; ++i) ck.v[i] = 2.0f * std::sqrt(r.v[i]) / std::sqrt(fmax_(0.0f, 1.0f - r.v[i]));
         }
@@ -614,7 +629,7 @@ inline BSDF get_bsdf(const SgSceneDesc* D, SurfaceInteraction& si, Wavelengths& 
         if (m.flags & SG_MAT_REMAP_ROUGHNESS) { cur = std::sqrt(iur); cvr = std::sqrt(ivr); }   // sic: roughness_to_alpha(iurough), material.rs:1237-1241
         b.lay.cond = true; b.lay.ce = ce; b.lay.ck = ck; b.lay.mfb = TR::make(cur, cvr);
         b.lay.r = spec_const(0.0f);
-        b.lay.albedo = spec_clamp(spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
+        b.lay.albedo = spec_clamp(has_b ? tex_b : spectrum_sample(D, m.spec_b, lambda), 0.0f, 1.0f);
         b.lay.g = clampf(m.g, -1.0f, 1.0f);
         b.lay.max_depth = m.max_depth; b.lay.n_samples = m.n_samples;
         b.mf = b.lay.mf;

@@ -52,6 +52,7 @@ struct DScene {
     uint32_t rgb2spec_res, n_textures;
     const SgTextureMapping* texture_mappings;   // spherical / cylindrical / planar mappings (sg_texture.cuh)
     const SgTextureNode* texture_nodes;         // operands of the constant / scaled / mix / direction-mix textures (sg_texture.cuh)
+    const SgMaterialTextures* material_textures; // texture-valued material parameters, one row per material, or null
     const SgEnvMap* env_maps;           // ImageInfinitelight images + sampling distributions (sg_envmap.cuh)
     const DInstance* instances;         // object instancing
     const struct DSphere* spheres;      // sphere shapes (sg_sphere.cuh)

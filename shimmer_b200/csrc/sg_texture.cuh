@@ -336,6 +336,23 @@ SGD Spec eval_spectrum_texture(const DScene& sc, int tex, const TexCoordCtx& c, 
     return TexTree<SG_MAX_TEXTURE_DEPTH>::eval_spectrum(sc, tex, c, lam);
 }
 
+// Texture-valued material parameters (SgMaterialTextures): what the reference's materials read through tex_eval.evaluate_float /
+// evaluate_spectrum (material.rs:456-499, 603-635, 917-963, 1188-1260).  The caller fills `v` with the SgMaterial constants; rows
+// with a texture id overwrite them.  Out of line and only reached in scenes that carry the table.
+struct MatTexValues { float ur, vr, thickness, g, ur2, vr2; Spec a, b, d; uint32_t mask; };      // mask: 1 = a, 2 = b, 4 = d hold texture values
+static __device__ __noinline__ void resolve_material_textures(const DScene& sc, uint32_t material_id, const TexCoordCtx& tc, const Wavelengths& lam, MatTexValues& v) {
+    const SgMaterialTextures mt = sc.material_textures[material_id];
+    if (mt.u_roughness >= 0) v.ur = eval_float_texture(sc, mt.u_roughness, tc);
+    if (mt.v_roughness >= 0) v.vr = eval_float_texture(sc, mt.v_roughness, tc);
+    if (mt.thickness >= 0) v.thickness = eval_float_texture(sc, mt.thickness, tc);
+    if (mt.g >= 0) v.g = eval_float_texture(sc, mt.g, tc);
+    if (mt.u_roughness2 >= 0) v.ur2 = eval_float_texture(sc, mt.u_roughness2, tc);
+    if (mt.v_roughness2 >= 0) v.vr2 = eval_float_texture(sc, mt.v_roughness2, tc);
+    if (mt.spec_a >= 0) { v.a = eval_spectrum_texture(sc, mt.spec_a, tc, lam); v.mask |= 1u; }
+    if (mt.spec_b >= 0) { v.b = eval_spectrum_texture(sc, mt.spec_b, tc, lam); v.mask |= 2u; }
+    if (mt.spec_d >= 0) { v.d = eval_spectrum_texture(sc, mt.spec_d, tc, lam); v.mask |= 4u; }
+}
+
 // ---- screen-space differentials ----
 SGD float3 xform_normal_t(const float* m, float3 n) {             // apply_normal_helper transform.rs:779-786
     return f3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);

@@ -301,6 +301,14 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (last.res[0] != 1 || last.res[1] != 1) return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": the last MIP level must be 1x1 (image.rs:783)");
         need_rgb2spec |= t.n_channels == 3;
     }
+    if (desc->material_textures) for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const SgMaterialTextures& mt = desc->material_textures[i];
+        for (int32_t t : {mt.u_roughness, mt.v_roughness, mt.thickness, mt.g, mt.u_roughness2, mt.v_roughness2})
+            if (t >= (int32_t)desc->n_textures || (t >= 0 && desc->textures[t].n_channels != 1))
+                return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + ": a float parameter references a missing or non-float texture");
+        for (int32_t t : {mt.spec_a, mt.spec_b, mt.spec_d})
+            if (t >= (int32_t)desc->n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "material " + std::to_string(i) + ": a spectrum parameter references an out-of-range texture");
+    }
     need_rgb2spec |= desc->n_env_maps > 0;
     if (need_rgb2spec && (desc->rgb2spec_res < 2 || !desc->rgb2spec_scale || !desc->rgb2spec_data))
         return fail(SG_ERR_INVALID_ARGUMENT, "three-channel textures need the rgb2spec table of the scene colour space");
@@ -498,6 +506,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     UP(texels, desc->texels, (desc->n_textures || desc->n_env_maps) ? desc->n_texels : 0, float);
     UP(texture_mappings, desc->texture_mappings, desc->n_texture_mappings, SgTextureMapping);
     UP(texture_nodes, desc->texture_nodes, desc->n_texture_nodes, SgTextureNode);
+    UP(material_textures, desc->material_textures, desc->material_textures ? desc->n_materials : 0, SgMaterialTextures);
     UP(env_maps, desc->env_maps, desc->n_env_maps, SgEnvMap);
     UP(mip_lut, desc->mip_filter_lut, desc->mip_filter_lut ? 128 : 0, float);
     UP(rgb2spec_scale, desc->rgb2spec_scale, need_rgb2spec ? desc->rgb2spec_res : 0, float);

@@ -75,6 +75,12 @@ class SgMaterial(C.Structure):
                 ("mix_materials", C.c_int32 * 2), ("mix_amount", C.c_float), ("tex_mix_amount", C.c_int32)]
 
 
+class SgMaterialTextures(C.Structure):
+    _fields_ = [("u_roughness", C.c_int32), ("v_roughness", C.c_int32), ("spec_a", C.c_int32), ("spec_b", C.c_int32), ("spec_d", C.c_int32),
+                ("thickness", C.c_int32), ("g", C.c_int32), ("u_roughness2", C.c_int32), ("v_roughness2", C.c_int32), ("pad", C.c_int32 * 3)]
+    NAMES = ("u_roughness", "v_roughness", "spec_a", "spec_b", "spec_d", "thickness", "g", "u_roughness2", "v_roughness2")
+
+
 class SgImageLevel(C.Structure):
     _fields_ = [("offset", C.c_uint32), ("res", C.c_int32 * 2), ("pad", C.c_uint32)]
 
@@ -168,6 +174,7 @@ class SgSceneDesc(C.Structure):
                 ("n_texture_mappings", C.c_uint32), ("texture_mappings", C.POINTER(SgTextureMapping)),
                 ("n_env_maps", C.c_uint32), ("env_maps", C.POINTER(SgEnvMap)),
                 ("n_texture_nodes", C.c_uint32), ("texture_nodes", C.POINTER(SgTextureNode)),
+                ("material_textures", C.POINTER(SgMaterialTextures)),
                 ("camera", SgCamera), ("film", SgFilm)]
 
 

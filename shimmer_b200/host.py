@@ -385,6 +385,16 @@ class SceneBuilder:
         return self._node_texture(ffi.SG_TEXTURE_DIRECTION_MIX, self._is_spectrum_texture(tex1) or self._is_spectrum_texture(tex2),
                                   tex1=tex1, tex2=tex2, dir=tuple(float(x) for x in dir))
 
+    def set_material_textures(self, material, **tex):
+        """Texture-valued parameters of `material` (SgMaterialTextures): u_roughness, v_roughness, spec_a (conductor eta / coated
+        conductor.eta or reflectance), spec_b (conductor k / coated albedo), spec_d (coated conductor.k), thickness, g, u_roughness2,
+        v_roughness2 = texture ids.  What material.rs reads through tex_eval.evaluate_float / evaluate_spectrum."""
+        bad = set(tex) - set(ffi.SgMaterialTextures.NAMES)
+        if bad:
+            raise ValueError("unknown material texture parameter(s): %s" % sorted(bad))
+        self.materials[material].setdefault("param_textures", {}).update({k: int(v) for k, v in tex.items()})
+        return material
+
     def texture_mapping(self, kind, texture_from_world=None, v1=(1.0, 0.0, 0.0), v2=(0.0, 1.0, 0.0), udelta=0.0, vdelta=0.0):
         """TextureMapping2D::create (texture.rs:853-893) for "spherical" / "cylindrical" / "planar":
         texture_from_render = (render_from_texture)^-1 with render_from_texture = render_from_world * CTM; the planar
@@ -958,6 +968,13 @@ class SceneBuilder:
             mm = m.get("mix_materials", (-1, -1)); mats[i].mix_materials[0], mats[i].mix_materials[1] = mm
             mats[i].mix_amount = m.get("mix_amount", 0.0); mats[i].tex_mix_amount = m.get("tex_mix_amount", -1)
         A["materials"] = mats
+        A["material_textures"] = None
+        if any(m.get("param_textures") for m in self.materials):
+            mt_rows = (ffi.SgMaterialTextures * len(self.materials))()
+            for i, m in enumerate(self.materials):
+                for nm in ffi.SgMaterialTextures.NAMES:
+                    setattr(mt_rows[i], nm, m.get("param_textures", {}).get(nm, -1))
+            A["material_textures"] = mt_rows
         A["lights"] = (ffi.SgLight * max(len(lights), 1))(*lights)
         A["meshes"] = mesh_rows
         # image textures: every MIP level, linear f32 texels, channels interleaved
@@ -1029,6 +1046,7 @@ class SceneBuilder:
             d.rgb2spec_data = _as_ptr(A["rgb2spec_data"], C.c_float)
         d.n_texture_mappings = len(self.mappings); d.texture_mappings = A["texture_mappings"]
         d.n_texture_nodes = len(node_rows); d.texture_nodes = A["texture_nodes"] if node_rows else None
+        d.material_textures = A["material_textures"]
         d.n_env_maps = len(self.env_maps); d.env_maps = A["env_maps"]
         d.camera = self.camera
         self.film.r_bar, self.film.g_bar, self.film.b_bar = film_ids

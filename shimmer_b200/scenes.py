@@ -478,7 +478,7 @@ def instanced_shapes_tiny_scene(kind="instshapes", resolution=(32, 32), flatten=
 
 
 VARIETY_KINDS = ("envmap", "envonly", "envrot", "coatedcond", "coatedcondrough", "coatedcondrefl", "normalmap", "texsph", "texcyl", "texplanar",
-                 "mix", "mixtex", "mixnested", "textree", "textreemix")
+                 "mix", "mixtex", "mixnested", "textree", "textreemix", "texparams", "texparams2")
 
 
 def procedural_envmap(n=32):
@@ -569,6 +569,29 @@ def variety_tiny_scene(kind, resolution=(32, 32)):
         zero = b.scaled_texture(rgb, b.constant_texture(0.0))
         gtex = b.mix_texture(b.mix_texture(zero, rgb, b.constant_texture(1.0)), zero, b.constant_texture(0.0))
         ground = b.diffuse(_white(), reflectance_tex=gtex)
+    elif kind == "texparams":
+        # texture-valued material parameters (SgMaterialTextures): a conductor whose roughness comes from an image and whose eta / k
+        # blend copper into gold across the surface; a coated-diffuse ground with textured thickness, g, albedo and roughness
+        mono = b.image_texture(procedural_image(32, 1), filter="bilinear", su=2.0, sv=2.0)
+        rgb = b.image_texture(procedural_image(64, 3), filter="trilinear", su=4.0, sv=4.0)
+        cs = lambda name: b.constant_texture(spectrum=b.spectrum(named_spectrum(name)))
+        mat = b.conductor(named_spectrum("metal-Cu-eta"), named_spectrum("metal-Cu-k"), roughness=0.3)
+        b.set_material_textures(mat, u_roughness=b.scaled_texture(mono, b.constant_texture(0.4)), v_roughness=b.constant_texture(0.05),
+                                spec_a=b.mix_texture(cs("metal-Cu-eta"), cs("metal-Au-eta"), mono), spec_b=b.mix_texture(cs("metal-Cu-k"), cs("metal-Au-k"), mono))
+        ground = b.coated_diffuse(_red(), roughness=0.1, thickness=0.02, albedo=("const", 0.2), g=0.1)
+        b.set_material_textures(ground, u_roughness=mono, v_roughness=mono, thickness=b.scaled_texture(mono, b.constant_texture(0.05)),
+                                g=b.constant_texture(-0.3), spec_b=b.scaled_texture(rgb, b.constant_texture(0.5)))
+    elif kind == "texparams2":
+        # rough glass with an image roughness over a coated conductor whose conductor eta / k / roughness and interface roughness are textures
+        mono = b.image_texture(procedural_image(32, 1), filter="bilinear", su=3.0, sv=1.0)
+        cs = lambda name: b.constant_texture(spectrum=b.spectrum(named_spectrum(name)))
+        mat = b.dielectric(("const", 1.5), roughness=0.2)
+        b.set_material_textures(mat, u_roughness=b.scaled_texture(mono, b.constant_texture(0.3)), v_roughness=b.scaled_texture(mono, b.constant_texture(0.15)))
+        ground = b.coated_conductor(conductor_eta=named_spectrum("metal-Au-eta"), conductor_k=named_spectrum("metal-Au-k"), interface_roughness=0.1,
+                                    conductor_roughness=0.2, remap=False)
+        b.set_material_textures(ground, u_roughness=b.constant_texture(0.02), spec_a=b.direction_mix_texture(cs("metal-Ag-eta"), cs("metal-Cu-eta"), dir=(0.0, 1.0, 0.0)),
+                                spec_d=cs("metal-Cu-k"), u_roughness2=b.scaled_texture(mono, b.constant_texture(0.5)), v_roughness2=mono,
+                                thickness=b.constant_texture(0.03), spec_b=b.constant_texture(0.1))
     else:
         raise ValueError(kind)
     P, I, Nn, UV = uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)

@@ -37,11 +37,11 @@ def test_struct_sizes_match_the_header_layout():
     assert C.sizeof(ffi.SgMaterial) == 96
     assert C.sizeof(ffi.SgTexture) == 64 and C.sizeof(ffi.SgImageLevel) == 16
     assert C.sizeof(ffi.SgLight) == 64
-    assert C.sizeof(ffi.SgObject) == 16 and C.sizeof(ffi.SgInstance) == 144 and C.sizeof(ffi.SgSceneDesc) == 728 and C.sizeof(ffi.SgSphere) == 160
+    assert C.sizeof(ffi.SgObject) == 16 and C.sizeof(ffi.SgInstance) == 144 and C.sizeof(ffi.SgSceneDesc) == 736 and C.sizeof(ffi.SgSphere) == 160
     assert C.sizeof(ffi.SgFilmPixel) == 32
     assert C.sizeof(ffi.SgHit) == 32
     assert C.sizeof(ffi.SgRenderParams) == 48
-    assert C.sizeof(ffi.SgTextureMapping) == 112 and C.sizeof(ffi.SgTextureNode) == 32 and C.sizeof(ffi.SgDistribution2D) == 32 and C.sizeof(ffi.SgEnvMap) == 208
+    assert C.sizeof(ffi.SgTextureMapping) == 112 and C.sizeof(ffi.SgTextureNode) == 32 and C.sizeof(ffi.SgMaterialTextures) == 48 and C.sizeof(ffi.SgDistribution2D) == 32 and C.sizeof(ffi.SgEnvMap) == 208
     assert np.dtype(ffi.SgBvhNode).itemsize == 32
 
 

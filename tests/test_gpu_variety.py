@@ -227,3 +227,19 @@ def test_malformed_texture_trees_are_rejected():
     sc.arrays["texture_nodes"][0].tex2 = 1                                      # `scale` must be a float texture
     with pytest.raises(ShimmerGpuError, match="operand"):
         create_integrator("wavefront", {}, sc)
+
+
+@pytest.mark.parametrize("kind", ["conductor", "dielectric", "coated", "coatedconductor"])
+def test_constant_parameter_textures_equal_the_plain_constants_on_gpu(kind):
+    """SgMaterialTextures on the device: constant textures given through the table render what the same constants in SgMaterial
+    render, and both match the oracle (material.rs:456-499, 603-635, 917-963, 1188-1260)."""
+    from test_oracle_variety import _param_scene
+    films = []
+    for via in (False, True):
+        sc = _param_scene(kind, via)
+        integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 8, "seed": 7})
+        films.append(integ.render(Options()).copy())
+        integ.close()
+    assert np.allclose(films[0], films[1], rtol=1e-6, atol=1e-9)
+    ref, _, _ = orc.render(_param_scene(kind, True), orc.make_params(seed=7, spp=8))
+    _film_close(films[1], ref, frac=0.99)

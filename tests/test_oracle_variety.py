@@ -372,3 +372,50 @@ def test_composite_texture_scene_renders_and_bumps():
         m["tex_displacement"] = -1
     film2, _, _ = orc.render(flat.build(), orc.make_params(seed=5, spp=4))
     assert not np.array_equal(film, film2)
+
+
+def _param_scene(kind, via_textures):
+    """One sphere + ground + light; the sphere material's parameters given as plain constants or as constant textures."""
+    b = SceneBuilder(); b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=(16, 16))
+    cu_eta, cu_k, au_eta, au_k = (named_spectrum(n) for n in ("metal-Cu-eta", "metal-Cu-k", "metal-Au-eta", "metal-Au-k"))
+    ct = lambda v: b.constant_texture(v)
+    cs = lambda spec: b.constant_texture(spectrum=b.spectrum(spec))
+    if kind == "conductor":
+        mat = b.conductor(*((au_eta, au_k) if not via_textures else (cu_eta, cu_k)), roughness=0.25 if not via_textures else 0.9)
+        if via_textures:
+            b.set_material_textures(mat, u_roughness=ct(0.25), v_roughness=ct(0.25), spec_a=cs(au_eta), spec_b=cs(au_k))
+    elif kind == "dielectric":
+        mat = b.dielectric(("const", 1.5), roughness=0.3 if not via_textures else 0.0)
+        if via_textures:
+            b.set_material_textures(mat, u_roughness=ct(0.3), v_roughness=ct(0.3))
+    elif kind == "coated":
+        args = dict(roughness=0.2, thickness=0.05, albedo=("const", 0.3), g=-0.4) if not via_textures else dict(roughness=0.7, thickness=0.5, albedo=("const", 0.0), g=0.0)
+        mat = b.coated_diffuse(scenes._red(), **args)
+        if via_textures:
+            b.set_material_textures(mat, u_roughness=ct(0.2), v_roughness=ct(0.2), thickness=ct(0.05), spec_b=ct(0.3), g=ct(-0.4))
+    else:
+        args = dict(conductor_eta=au_eta, conductor_k=au_k, interface_roughness=0.1, conductor_roughness=0.3, thickness=0.02, albedo=("const", 0.2), g=0.3, remap=False)
+        if via_textures:
+            args = dict(conductor_eta=cu_eta, conductor_k=cu_k, interface_roughness=0.6, conductor_roughness=0.0, thickness=0.3, albedo=("const", 0.0), g=0.0, remap=False)
+        mat = b.coated_conductor(**args)
+        if via_textures:
+            b.set_material_textures(mat, u_roughness=ct(0.1), v_roughness=ct(0.1), u_roughness2=ct(0.3), v_roughness2=ct(0.3), thickness=ct(0.02),
+                                    spec_b=ct(0.2), g=ct(0.3), spec_a=cs(au_eta), spec_d=cs(au_k))
+    P, I, Nn, UV = scenes.uv_sphere(10, 14, center=(0.0, 0.6, 0.0), radius=0.6)
+    b.add_mesh(P, I, mat, n=Nn, uv=UV)
+    gp, gi = scenes._quad((-3, 0.0, -3), (-3, 0.0, 3), (3, 0.0, 3), (3, 0.0, -3))
+    b.add_mesh(gp, gi, b.diffuse(scenes._white()))
+    lp, li = scenes._quad((-0.5, 2.5, -0.5), (0.5, 2.5, -0.5), (0.5, 2.5, 0.5), (-0.5, 2.5, 0.5))
+    b.add_mesh(lp, li, b.diffuse(scenes._white()), area_light=dict(L=named_spectrum("stdillum-D65"), scale=30.0, two_sided=False))
+    return b.build()
+
+
+@pytest.mark.parametrize("kind", ["conductor", "dielectric", "coated", "coatedconductor"])
+def test_constant_parameter_textures_equal_the_plain_constants(kind):
+    """SgMaterialTextures: a *ConstantTexture given through the texture table renders what the same constant in SgMaterial renders
+    (the reference makes no distinction: both are `tex_eval.evaluate_*` of a constant texture, material.rs:456-499, 603-635, 917-963,
+    1188-1260).  The texture variant starts from deliberately different SgMaterial values, so every override must take effect."""
+    plain, _, _ = orc.render(_param_scene(kind, False), orc.make_params(seed=7, spp=8))
+    textured, st, _ = orc.render(_param_scene(kind, True), orc.make_params(seed=7, spp=8))
+    assert np.isfinite(plain).all() and plain[:, :3].sum() > 0
+    assert np.allclose(textured, plain, rtol=1e-6, atol=1e-9)
