@@ -141,8 +141,8 @@ typedef struct SgSpectrum {
 } SgSpectrum;
 
 /* ---- materials (src/material.rs) -------------------------------------------
- * Textures on this path are the reference's `*ConstantTexture`s
- * (texture.rs), i.e. a spectrum id or a float. */
+ * Parameters held directly in SgMaterial are the reference's `*ConstantTexture`s (texture.rs), i.e. a spectrum id or a
+ * float; any other texture goes through the texture table (tex_* ids below, SgMaterialTextures for the remaining parameters). */
 typedef enum SgMaterialKind {
     SG_MATERIAL_DIFFUSE = 0,    /* DiffuseMaterial    material.rs:298-338  spec_a = reflectance          */
     SG_MATERIAL_CONDUCTOR = 1,  /* ConductorMaterial  material.rs:453-526  spec_a = eta, spec_b = k      */
@@ -179,8 +179,8 @@ typedef struct SgMaterial {
     float   g;             /* coated diffuse: HG asymmetry (0)                    */
     int32_t max_depth;     /* coated diffuse: `maxdepth` (10)                     */
     int32_t n_samples;     /* coated diffuse: `nsamples` (1)                      */
-    int32_t tex_reflectance;  /* SpectrumImageTexture for `reflectance` (diffuse / coated diffuse) or -1 -> spec_a */
-    int32_t tex_displacement; /* FloatImageTexture for `displacement` (bump_map, material.rs:1477-1509) or -1     */
+    int32_t tex_reflectance;  /* SpectrumTexture id for `reflectance` (diffuse / coated diffuse) or -1 -> spec_a */
+    int32_t tex_displacement; /* FloatTexture id for `displacement` (bump_map, material.rs:1477-1509) or -1     */
     int32_t pad2[2];
     int32_t spec_d;           /* coated conductor: conductor k                                                              */
     float   u_roughness2;     /* coated conductor: `conductor.uroughness` / `conductor.vroughness`                          */
@@ -189,7 +189,7 @@ typedef struct SgMaterial {
                                  only consulted when the material has NO displacement (interaction.rs:229-244, material.rs:1453-1474) */
     int32_t mix_materials[2]; /* SG_MATERIAL_MIX: the two materials (may be mixes themselves; cycles are rejected)          */
     float   mix_amount;       /* `amount` (0.5) when tex_mix_amount < 0                                                     */
-    int32_t tex_mix_amount;   /* FloatImageTexture for `amount` or -1                                                       */
+    int32_t tex_mix_amount;   /* FloatTexture id for `amount` or -1                                                            */
 } SgMaterial;
 
 /* Texture-valued material parameters.  Every parameter the reference's materials read through `tex_eval.evaluate_float` /
