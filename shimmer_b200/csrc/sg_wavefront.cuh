@@ -635,9 +635,17 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
                 tc = TexCoordCtx{sx.uv, sx.dudx, sx.dudy, sx.dvdx, sx.dvdy};
                 if (tex_needs_ctx(sc)) { pdp[0] = p3fi_mid(s.pi); pdp[1] = sx.dpdx; pdp[2] = sx.dpdy; pdp[3] = s.n; tc.pdp = pdp; }
             }
-            MatTexValues mv; mv.mask = 0u;
-            mv.ur = mat.u_roughness; mv.vr = mat.v_roughness; mv.thickness = mat.thickness; mv.g = mat.g; mv.ur2 = mat.u_roughness2; mv.vr2 = mat.v_roughness2;
-            if (TEX && KIND != SG_MATERIAL_DIFFUSE && sc.material_textures != nullptr) resolve_material_textures(sc, material_id, tc, lam, mv);
+            // texture-valued parameters (SgMaterialTextures).  The scalars are plain values outside the branch, so kernels of scenes
+            // without the table keep them in registers; `mv` (whose address escapes) is only touched inside it, and its spectra are
+            // only read back where ov_mask says a texture supplied them.
+            MatTexValues mv;
+            float p_ur = mat.u_roughness, p_vr = mat.v_roughness, p_thickness = mat.thickness, p_g = mat.g, p_ur2 = mat.u_roughness2, p_vr2 = mat.v_roughness2;
+            uint32_t ov_mask = 0u;
+            if (TEX && KIND != SG_MATERIAL_DIFFUSE && sc.material_textures != nullptr) {
+                mv.mask = 0u; mv.ur = p_ur; mv.vr = p_vr; mv.thickness = p_thickness; mv.g = p_g; mv.ur2 = p_ur2; mv.vr2 = p_vr2;
+                resolve_material_textures(sc, material_id, tc, lam, mv);
+                p_ur = mv.ur; p_vr = mv.vr; p_thickness = mv.thickness; p_g = mv.g; p_ur2 = mv.ur2; p_vr2 = mv.vr2; ov_mask = mv.mask;
+            }
             BSDF<KIND> bsdf;
             bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
@@ -646,47 +654,47 @@ __global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid
             } else if (KIND == SG_MATERIAL_COATED_DIFFUSE) {                                    // material.rs:917-963
                 bsdf.lay.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
                                                                         : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);
-                float ur = mv.ur, vr = mv.vr;
+                float ur = p_ur, vr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }
                 bsdf.lay.mf = TR::make(ur, vr);
-                bsdf.lay.thickness = mv.thickness;
+                bsdf.lay.thickness = p_thickness;
                 float se = spectrum_get(sc, mat.spec_c, lam.lambda.x);
                 if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
                 if (se == 0.0f) se = 1.0f;
                 bsdf.lay.eta = se;
-                bsdf.lay.albedo = spec_clamp((mv.mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
-                bsdf.lay.g = clampf(mv.g, -1.0f, 1.0f);
+                bsdf.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                bsdf.lay.g = clampf(p_g, -1.0f, 1.0f);
                 bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
             } else if (KIND == SG_MATERIAL_COATED_CONDUCTOR) {                                 // material.rs:1188-1260
-                float iur = mv.ur, ivr = mv.vr;
+                float iur = p_ur, ivr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { iur = sqrtf(iur); ivr = sqrtf(ivr); }
                 bsdf.lay.mf = TR::make(iur, ivr);
-                bsdf.lay.thickness = mv.thickness;
+                bsdf.lay.thickness = p_thickness;
                 float ieta = spectrum_get(sc, mat.spec_c, lam.lambda.x);
                 if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
                 if (ieta == 0.0f) ieta = 1.0f;
                 bsdf.lay.eta = ieta;
                 Spec ce, ck;
-                if (!(mat.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = (mv.mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); ck = (mv.mask & 4u) ? mv.d : spectrum_sample(sc, mat.spec_d, lam); }
+                if (!(mat.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = (ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); ck = (ov_mask & 4u) ? mv.d : spectrum_sample(sc, mat.spec_d, lam); }
                 else {                                                                         // :1225-1233
-                    const Spec r = spec_clamp((mv.mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 0.9999f);
+                    const Spec r = spec_clamp((ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 0.9999f);
                     ce = spec1(1.0f);
                     ck = make_float4(2.0f * sqrtf(r.x) / sqrtf(fmaxf(0.0f, 1.0f - r.x)), 2.0f * sqrtf(r.y) / sqrtf(fmaxf(0.0f, 1.0f - r.y)),
                                      2.0f * sqrtf(r.z) / sqrtf(fmaxf(0.0f, 1.0f - r.z)), 2.0f * sqrtf(r.w) / sqrtf(fmaxf(0.0f, 1.0f - r.w)));
                 }
                 bsdf.lay.ce = ce / ieta; bsdf.lay.ck = ck / ieta;
-                float cur = mv.ur2, cvr = mv.vr2;
+                float cur = p_ur2, cvr = p_vr2;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { cur = sqrtf(iur); cvr = sqrtf(ivr); } // sic: roughness_to_alpha(iurough), material.rs:1237-1241
                 bsdf.lay.mfb = TR::make(cur, cvr);
                 bsdf.lay.r = spec1(0.0f);
-                bsdf.lay.albedo = spec_clamp((mv.mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
-                bsdf.lay.g = clampf(mv.g, -1.0f, 1.0f);
+                bsdf.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                bsdf.lay.g = clampf(p_g, -1.0f, 1.0f);
                 bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
             } else {
-                float ur = mv.ur, vr = mv.vr;
+                float ur = p_ur, vr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }     // roughness_to_alpha
                 if (KIND == SG_MATERIAL_CONDUCTOR) {
-                    bsdf.r = (mv.mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); bsdf.k = (mv.mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam);
+                    bsdf.r = (ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); bsdf.k = (ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam);
                 } else {
                     float se = spectrum_get(sc, mat.spec_a, lam.lambda.x);                      // material.rs:609-624
                     if (sc.spectra[mat.spec_a].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
