@@ -540,3 +540,23 @@ def test_orthographic_camera_rays_bit_exact():
     r2, l2 = orc.camera_rays(sc, orc.make_params(seed=9, spp=4), xy, si)
     assert np.array_equal(rays, r2) and np.allclose(lam, l2, rtol=2e-6)
     integ.close()
+
+
+@pytest.mark.parametrize("kind", ["tex", "texewa", "diffuse"])
+def test_thin_lens_camera_parity(kind):
+    """lens_radius > 0 (camera.rs:1026-1038, auxiliary rays :1044-1068): camera rays and the film of a textured scene (whose
+    footprints come from the lens-aware auxiliary rays) against the oracle."""
+    from test_oracle_render import _lens_scene
+    sc = _lens_scene(kind, lens_radius=0.15, focal_distance=3.0)
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 8, "seed": 6})
+    rng = np.random.default_rng(2)
+    xy = rng.integers(0, 16, (1024, 2)).astype(np.int32); si = rng.integers(0, 8, 1024).astype(np.int32)
+    rays, lam = integ.camera_rays(Options(seed=6, pixel_samples=8), xy, si)
+    r2, l2 = orc.camera_rays(sc, orc.make_params(seed=6, spp=8), xy, si)
+    assert np.allclose(rays, r2, rtol=2e-6, atol=2e-7) and np.allclose(lam, l2, rtol=2e-6)   # the concentric disk map calls sin / cos (different libms)
+    assert (rays == r2).mean() > 0.5
+    film = integ.render(Options()).copy()
+    ref, rst, _ = orc.render(sc, orc.make_params(seed=6, spp=8))
+    _film_close(film, ref, frac=0.99)
+    assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 2
+    integ.close()
