@@ -512,6 +512,11 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS 4
 #endif
+// textured variants (C4): resident blocks per SM measured on one box, same build otherwise -- 3 (168 regs): 176.1, 4 (128): 186.8,
+// 5 (96): 188.4, 6 (80): 186.5 Mpaths/s.  Occupancy buys more than the extra spills cost; the curve is flat from 4 to 6.
+#ifndef SG_SHADE_MIN_BLOCKS_TEX
+#define SG_SHADE_MIN_BLOCKS_TEX 5
+#endif
 // TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture lookups, bump /
 // normal mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.  TEX = false is the lean variant
 // for untextured scenes lit by triangle emitters: no call sites on its hot path.
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
 // rc.integrator; instantiated with TEX = true only (that variant is a superset: it also renders untextured scenes).
 // LG = the scene has lights that are not triangle emitters (see light_sample_li<GENERAL>); LG implies TEX.
 template <int KIND, bool TEX, bool PATH = true, bool LG = TEX>
-__global__ void __launch_bounds__(128, SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+__global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
     const int qk = 1 + KIND;
