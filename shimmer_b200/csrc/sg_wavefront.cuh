@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
 
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
+// lean variants: 4 blocks per SM (<= 128 registers, which the diffuse / conductor kernels do not even reach); 5 (96 registers) was
+// measured slower -- C2 557.5 -> 545.4, C3 543.6 -> 522.9 Mpaths/s.
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS 4
 #endif
