@@ -123,6 +123,7 @@ static constexpr int kTraceThreads = SG_TRACE_THREADS;
 #ifndef SG_TRACE_POSTPONE
 #define SG_TRACE_POSTPONE 0
 #endif
+// 7 blocks (72 registers) for the instanced variants: 836 vs 843 Mrays/s closest-hit on C4 -- no gain over 8, kept at 8.
 #ifndef SG_TRACE_MIN_BLOCKS_INST
 #define SG_TRACE_MIN_BLOCKS_INST 8
 #endif
