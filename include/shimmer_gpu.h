@@ -400,7 +400,7 @@ enum {
     SG_OPT_DISABLE_PIXEL_JITTER = 1,
     SG_OPT_DISABLE_WAVELENGTH_JITTER = 2,
     SG_OPT_DISABLE_TEXTURE_FILTERING = 4,
-    SG_OPT_FORCE_DIFFUSE = 8
+    SG_OPT_FORCE_DIFFUSE = 8      /* interaction.rs:258-273: every BSDF -> DiffuseBxDF(rho_hd(wo, 1 sample)); path integrator only */
 };
 typedef struct SgRenderParams {
     uint64_t seed;              /* IndependentSampler seed                                  */

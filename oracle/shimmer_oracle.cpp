@@ -52,6 +52,22 @@ static inline bool logged_intersect(const PathCtx& pc, const Ray& ray, Float t_m
 // path stream's current state and the call site (1 = f in sample_ld, 2 = pdf in sample_ld, 3 = sample_f, 4 = pdf after
 // sample_f) WITHOUT advancing the path stream.  Same definition in sg_wavefront.cuh.
 static inline uint64_t layer_seed(const Rng& rng, uint64_t site) { return mix64(rng.s[0] ^ (site * 0x9e3779b97f4a7c15ULL)); }
+// Options::force_diffuse, interaction.rs:258-273: the material's BSDF is replaced by DiffuseBxDF(rho_hd(wo, [get_1d], [get_2d])) on the same
+// shading frame.  BxDFI::rho_hd bxdf.rs:49-71 with one sample: 0 when wo.z == 0, else f |cos wi| / pdf of one BxDF-level sample_f
+// (no BSDF-level rejection tests), kept only when pdf > 0.  A layered BxDF's private generator is seeded at site 6.
+static inline void force_diffuse(BSDF& b, V3 wo_render, Rng& rng) {
+    b.layer_seed = layer_seed(rng, 6);
+    const Float uc = rng.get_1d();
+    V2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
+    Spec r = spec_const(0.0f);
+    const V3 wo = b.to_local(wo_render);
+    if (wo.z != 0.0f) {
+        BSDFSample bs;
+        if (b.sample_local(wo, uc, u2, &bs) && bs.pdf > 0.0f) r = r + bs.f * abs_cos_theta(bs.wi) / bs.pdf;
+        r = r / 1.0f;
+    }
+    b.kind = SG_MATERIAL_DIFFUSE; b.r = r; b.k = spec_const(0.0f); b.eta = 1.0f; b.mf = TR::make(0.0f, 0.0f);
+}
 
 static SurfaceInteraction hit_interaction(const Scene& sc, const Hit& hit, const Ray& ray);
 
@@ -130,6 +146,7 @@ static Spec path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths& lambda
             }
         }
         BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp, layer_seed(rng, 5));      // :816
+        if (pc.rp->option_flags & SG_OPT_FORCE_DIFFUSE) force_diffuse(bsdf, si.wo, rng);
         if (pc.rp->regularize && any_non_specular_bounces) { bsdf.mf.regularize(); bsdf.lay.mf.regularize(); bsdf.lay.mfb.regularize(); }  // :825-828 (LayeredBxDF::regularize: top + bottom, bxdf.rs:1616-1619)
         if (depth == pc.rp->max_depth) break;
         depth += 1;
@@ -216,6 +233,7 @@ static Spec simple_path_li(const PathCtx& pc, Ray ray, AuxRays aux, Wavelengths&
         if (depth == pc.rp->max_depth) break;
         depth += 1;
         BSDF bsdf = get_bsdf(D, si, lambda, aux, pc.rp, layer_seed(rng, 5));
+        if (pc.rp->option_flags & SG_OPT_FORCE_DIFFUSE) force_diffuse(bsdf, si.wo, rng);
         const V3 wo = -ray.d;
         if (sample_lights && D->n_lights > 0) {                                      // UniformLightSampler::sample_light light_sampler.rs:91-103
             const Float ul = rng.get_1d();

@@ -15,10 +15,13 @@ ShadeKernel shade_kernel_general_a(int kind);   // k_shade<KIND, true, true, tru
 ShadeKernel shade_kernel_general_b(int kind);   //                                                          KIND in {CoatedDiffuse, CoatedConductor}                           (SG_TU 3)
 ShadeKernel shade_kernel_other_a(int kind);     // k_shade<KIND, true, false> (SimplePath / RandomWalk), first kind group     (SG_TU 4)
 ShadeKernel shade_kernel_other_b(int kind);     //                                                         second kind group   (SG_TU 5)
+ShadeKernel shade_kernel_force_diffuse_a(int kind);   // k_shade<KIND, true, true, true, FD = true>: Options::force_diffuse (path integrator)  (SG_TU 8)
+ShadeKernel shade_kernel_force_diffuse_b(int kind);   //                                                                                  (SG_TU 9)
 ShadeKernel resolve_mix_kernel(bool tex);       // k_resolve_mix<TEX>                                                          (SG_TU 2)
 
 inline bool shade_kind_in_group_b(int kind) { return kind == SG_MATERIAL_COATED_DIFFUSE || kind == SG_MATERIAL_COATED_CONDUCTOR; }
-inline ShadeKernel shade_kernel(int kind, bool textured, bool general_lights, bool path_integrator) {
+inline ShadeKernel shade_kernel(int kind, bool textured, bool general_lights, bool path_integrator, bool force_diffuse = false) {
+    if (force_diffuse) return shade_kind_in_group_b(kind) ? shade_kernel_force_diffuse_b(kind) : shade_kernel_force_diffuse_a(kind);
     if (!path_integrator) return shade_kind_in_group_b(kind) ? shade_kernel_other_b(kind) : shade_kernel_other_a(kind);
     if (general_lights) return shade_kind_in_group_b(kind) ? shade_kernel_general_b(kind) : shade_kernel_general_a(kind);
     if (textured) return shade_kind_in_group_b(kind) ? shade_kernel_textured_b(kind) : shade_kernel_textured_a(kind);

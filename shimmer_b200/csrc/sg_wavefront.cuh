@@ -526,7 +526,10 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
 // PATH = false: the SimplePathIntegrator (integrator.rs:570-728) / RandomWalkIntegrator (:458-568) bodies, chosen at run time by
 // rc.integrator; instantiated with TEX = true only (that variant is a superset: it also renders untextured scenes).
 // LG = the scene has lights that are not triangle emitters (see light_sample_li<GENERAL>); LG implies TEX.
-template <int KIND, bool TEX, bool PATH = true, bool LG = TEX>
+// FD = Options::force_diffuse (interaction.rs:258-273): a separate set of instantiations (general superset only), so the regular
+// kernels carry none of it.
+template <bool FD, class A, class B> SGD auto& pick_bsdf(A& a, B& b) { if constexpr (FD) return b; else return a; }
+template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false>
 __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
@@ -654,34 +657,34 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 resolve_material_textures(sc, material_id, tc, lam, mv);
                 p_ur = mv.ur; p_vr = mv.vr; p_thickness = mv.thickness; p_g = mv.g; p_ur2 = mv.ur2; p_vr2 = mv.vr2; ov_mask = mv.mask;
             }
-            BSDF<KIND> bsdf;
-            bsdf.r = spec1(0.0f); bsdf.k = spec1(0.0f); bsdf.eta = 1.0f; bsdf.mf = TR::make(0.0f, 0.0f);
+            BSDF<KIND> mb;
+            mb.r = spec1(0.0f); mb.k = spec1(0.0f); mb.eta = 1.0f; mb.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
-                bsdf.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
+                mb.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
                                                                     : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);          // material.rs:307-310
             } else if (KIND == SG_MATERIAL_COATED_DIFFUSE) {                                    // material.rs:917-963
-                bsdf.lay.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
+                mb.lay.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
                                                                         : spectrum_sample(sc, mat.spec_a, lam), 0.0f, 1.0f);
                 float ur = p_ur, vr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }
-                bsdf.lay.mf = TR::make(ur, vr);
-                bsdf.lay.thickness = p_thickness;
+                mb.lay.mf = TR::make(ur, vr);
+                mb.lay.thickness = p_thickness;
                 float se = spectrum_get(sc, mat.spec_c, lam.lambda.x);
                 if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
                 if (se == 0.0f) se = 1.0f;
-                bsdf.lay.eta = se;
-                bsdf.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
-                bsdf.lay.g = clampf(p_g, -1.0f, 1.0f);
-                bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
+                mb.lay.eta = se;
+                mb.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                mb.lay.g = clampf(p_g, -1.0f, 1.0f);
+                mb.lay.max_depth = mat.max_depth; mb.lay.n_samples = mat.n_samples;
             } else if (KIND == SG_MATERIAL_COATED_CONDUCTOR) {                                 // material.rs:1188-1260
                 float iur = p_ur, ivr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { iur = sqrtf(iur); ivr = sqrtf(ivr); }
-                bsdf.lay.mf = TR::make(iur, ivr);
-                bsdf.lay.thickness = p_thickness;
+                mb.lay.mf = TR::make(iur, ivr);
+                mb.lay.thickness = p_thickness;
                 float ieta = spectrum_get(sc, mat.spec_c, lam.lambda.x);
                 if (sc.spectra[mat.spec_c].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
                 if (ieta == 0.0f) ieta = 1.0f;
-                bsdf.lay.eta = ieta;
+                mb.lay.eta = ieta;
                 Spec ce, ck;
                 if (!(mat.flags & SG_MAT_CONDUCTOR_REFLECTANCE)) { ce = (ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); ck = (ov_mask & 4u) ? mv.d : spectrum_sample(sc, mat.spec_d, lam); }
                 else {                                                                         // :1225-1233
@@ -690,33 +693,52 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                     ck = make_float4(2.0f * sqrtf(r.x) / sqrtf(fmaxf(0.0f, 1.0f - r.x)), 2.0f * sqrtf(r.y) / sqrtf(fmaxf(0.0f, 1.0f - r.y)),
                                      2.0f * sqrtf(r.z) / sqrtf(fmaxf(0.0f, 1.0f - r.z)), 2.0f * sqrtf(r.w) / sqrtf(fmaxf(0.0f, 1.0f - r.w)));
                 }
-                bsdf.lay.ce = ce / ieta; bsdf.lay.ck = ck / ieta;
+                mb.lay.ce = ce / ieta; mb.lay.ck = ck / ieta;
                 float cur = p_ur2, cvr = p_vr2;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { cur = sqrtf(iur); cvr = sqrtf(ivr); } // sic: roughness_to_alpha(iurough), material.rs:1237-1241
-                bsdf.lay.mfb = TR::make(cur, cvr);
-                bsdf.lay.r = spec1(0.0f);
-                bsdf.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
-                bsdf.lay.g = clampf(p_g, -1.0f, 1.0f);
-                bsdf.lay.max_depth = mat.max_depth; bsdf.lay.n_samples = mat.n_samples;
+                mb.lay.mfb = TR::make(cur, cvr);
+                mb.lay.r = spec1(0.0f);
+                mb.lay.albedo = spec_clamp((ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam), 0.0f, 1.0f);
+                mb.lay.g = clampf(p_g, -1.0f, 1.0f);
+                mb.lay.max_depth = mat.max_depth; mb.lay.n_samples = mat.n_samples;
             } else {
                 float ur = p_ur, vr = p_vr;
                 if (mat.flags & SG_MAT_REMAP_ROUGHNESS) { ur = sqrtf(ur); vr = sqrtf(vr); }     // roughness_to_alpha
                 if (KIND == SG_MATERIAL_CONDUCTOR) {
-                    bsdf.r = (ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); bsdf.k = (ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam);
+                    mb.r = (ov_mask & 1u) ? mv.a : spectrum_sample(sc, mat.spec_a, lam); mb.k = (ov_mask & 2u) ? mv.b : spectrum_sample(sc, mat.spec_b, lam);
                 } else {
                     float se = spectrum_get(sc, mat.spec_a, lam.lambda.x);                      // material.rs:609-624
                     if (sc.spectra[mat.spec_a].kind != SG_SPECTRUM_CONSTANT) terminate_secondary(lam);
                     if (se == 0.0f) se = 1.0f;
-                    bsdf.eta = se;
+                    mb.eta = se;
                 }
-                bsdf.mf = TR::make(ur, vr);
+                mb.mf = TR::make(ur, vr);
             }
-            bsdf.fx = normalize3(s.sdpdu); bsdf.fz = s.sn; bsdf.fy = cross3(bsdf.fz, bsdf.fx);
+            mb.fx = normalize3(s.sdpdu); mb.fz = s.sn; mb.fy = cross3(mb.fz, mb.fx);
+            // Options::force_diffuse: DiffuseBxDF(rho_hd(si.wo, [get_1d], [get_2d])) on the same frame (interaction.rs:258-273, bxdf.rs:49-71:
+            // one BxDF-level sample, no BSDF-level rejection tests, kept when pdf > 0); sampled BEFORE any regularisation, as there.
+            BSDF<SG_MATERIAL_DIFFUSE> db;
+            if constexpr (FD) {
+                Rng frng; { ulonglong2 ra = st.rng_a[path], rb = st.rng_b[path]; frng.s0 = ra.x; frng.s1 = ra.y; frng.s2 = rb.x; frng.s3 = rb.y; }
+                mb.layer_seed = layer_seed(frng, 6);
+                const float fuc = frng.get_1d();
+                float2 fu2; fu2.x = frng.get_1d(); fu2.y = frng.get_1d();
+                st.rng_a[path] = make_ulonglong2(frng.s0, frng.s1); st.rng_b[path] = make_ulonglong2(frng.s2, frng.s3);
+                Spec fr = spec1(0.0f);
+                const float3 wol = mb.to_local(wo_si);
+                if (wol.z != 0.0f) {
+                    BSDFSample fbs; bool fprop = false;
+                    if (mb.sample_local(wol, fuc, fu2, fbs, fprop) && fbs.pdf > 0.0f) fr = fr + fbs.f * fabsf(fbs.wi.z) / fbs.pdf;
+                    fr = fr / 1.0f;
+                }
+                db.r = fr; db.k = spec1(0.0f); db.eta = 1.0f; db.mf = TR::make(0.0f, 0.0f); db.fx = mb.fx; db.fy = mb.fy; db.fz = mb.fz;
+            }
             if (PATH && rc.regularize && any_non_specular) {                                    // :825-828
-                bsdf.mf.regularize();
-                if (KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_COATED_CONDUCTOR) bsdf.lay.mf.regularize();
-                if (KIND == SG_MATERIAL_COATED_CONDUCTOR) bsdf.lay.mfb.regularize();          // LayeredBxDF::regularize bxdf.rs:1616-1619
+                mb.mf.regularize();
+                if (KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_COATED_CONDUCTOR) mb.lay.mf.regularize();
+                if (KIND == SG_MATERIAL_COATED_CONDUCTOR) mb.lay.mfb.regularize();          // LayeredBxDF::regularize bxdf.rs:1616-1619
             }
+            auto& bsdf = pick_bsdf<FD>(mb, db);
 
             bool alive = pdepth != rc.max_depth;                                               // :830-833
             if (alive) {

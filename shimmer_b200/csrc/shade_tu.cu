@@ -1,4 +1,4 @@
-// Shade-kernel instantiations, one group per translation unit (see sg_kernels.h): nvcc -DSG_TU=1..7 -c shade_tu.cu
+// Shade-kernel instantiations, one group per translation unit (see sg_kernels.h): nvcc -DSG_TU=1..9 -c shade_tu.cu
 #include "sg_kernels.h"
 
 namespace sg {
@@ -27,8 +27,26 @@ ShadeKernel shade_kernel_other_b(int kind) { switch (kind) { SG_CASE_B(true, fal
 ShadeKernel shade_kernel_textured_a(int kind) { switch (kind) { SG_CASE_A(true, true, false) } return nullptr; }
 #elif SG_TU == 7
 ShadeKernel shade_kernel_textured_b(int kind) { switch (kind) { SG_CASE_B(true, true, false) } return nullptr; }
+#elif SG_TU == 8
+ShadeKernel shade_kernel_force_diffuse_a(int kind) {
+    switch (kind) {
+    case SG_MATERIAL_DIFFUSE: return k_shade<SG_MATERIAL_DIFFUSE, true, true, true, true>;
+    case SG_MATERIAL_CONDUCTOR: return k_shade<SG_MATERIAL_CONDUCTOR, true, true, true, true>;
+    case SG_MATERIAL_DIELECTRIC: return k_shade<SG_MATERIAL_DIELECTRIC, true, true, true, true>;
+    case SG_MATERIAL_THIN_DIELECTRIC: return k_shade<SG_MATERIAL_THIN_DIELECTRIC, true, true, true, true>;
+    }
+    return nullptr;
+}
+#elif SG_TU == 9
+ShadeKernel shade_kernel_force_diffuse_b(int kind) {
+    switch (kind) {
+    case SG_MATERIAL_COATED_DIFFUSE: return k_shade<SG_MATERIAL_COATED_DIFFUSE, true, true, true, true>;
+    case SG_MATERIAL_COATED_CONDUCTOR: return k_shade<SG_MATERIAL_COATED_CONDUCTOR, true, true, true, true>;
+    }
+    return nullptr;
+}
 #else
-#error "compile with -DSG_TU=1..7"
+#error "compile with -DSG_TU=1..9"
 #endif
 
 }  // namespace sg

@@ -586,7 +586,8 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     if (!s || !rp || !d_film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (rp->sample_end < rp->sample_begin || rp->sample_begin < 0) return fail(SG_ERR_INVALID_ARGUMENT, "bad sample range");
     if (rp->max_depth < 0 || rp->max_depth > 254) return fail(SG_ERR_INVALID_ARGUMENT, "max_depth out of range");
-    if (rp->option_flags & SG_OPT_FORCE_DIFFUSE) return fail(SG_ERR_UNSUPPORTED, "force_diffuse is not on the GPU path");
+    const bool force_diffuse = (rp->option_flags & SG_OPT_FORCE_DIFFUSE) != 0;
+    if (force_diffuse && rp->integrator != SG_INTEGRATOR_PATH) return fail(SG_ERR_UNSUPPORTED, "force_diffuse is on the GPU path for the path integrator only");
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
     const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
     const uint64_t npix = s->n_pixels();
@@ -636,7 +637,7 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             for (int kind = 0; kind <= SG_MATERIAL_COATED_CONDUCTOR; ++kind) {
                 if (!s->kinds_present[kind]) continue;
-                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
+                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
                 ++launches;
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {

@@ -240,8 +240,10 @@ def test_options_and_depth_limits(cornell_gpu, cornell64):
     ref, _, _ = orc.render(cornell64, orc.make_params(seed=0, spp=2, max_depth=0))
     assert np.allclose(f, ref, rtol=1e-5, atol=1e-12)
     integ.close()
-    with pytest.raises(ffi.ShimmerGpuError):
-        cornell_gpu.render(Options(force_diffuse=True))                     # not on the GPU path: error, not fallback
+    sp = create_integrator("wavefront", {"integrator": "simplepath"}, cornell64, {"pixelsamples": 2})
+    with pytest.raises(ffi.ShimmerGpuError, match="path integrator only"):
+        sp.render(Options(force_diffuse=True))                              # SimplePath / RandomWalk + force_diffuse: error, not fallback
+    sp.close()
 
 
 def test_scene_validation_errors(cornell64):
@@ -559,4 +561,23 @@ def test_thin_lens_camera_parity(kind):
     ref, rst, _ = orc.render(sc, orc.make_params(seed=6, spp=8))
     _film_close(film, ref, frac=0.99)
     assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 2
+    integ.close()
+
+
+@pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "thinglass", "tex", "texbump", "coatedcond", "mix", "texparams"])
+def test_force_diffuse_films(kind):
+    """Options::force_diffuse (interaction.rs:258-273): every BSDF replaced by DiffuseBxDF(rho_hd(wo, one sample)) on the same frame,
+    three extra draws from the path's generator per hit -- the CUDA path (its own kernel instantiations) against the oracle on the
+    same streams."""
+    sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
+    integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 8, "seed": 5})
+    film = integ.render(Options(force_diffuse=True)).copy()
+    p = orc.make_params(seed=5, spp=8); p.option_flags = ffi.SG_OPT_FORCE_DIFFUSE
+    ref, rst, _ = orc.render(sc, p)
+    _film_close(film, ref, frac=0.99)
+    assert abs(int(integ.stats.closest_hit_rays) - int(rst.closest_hit_rays)) <= 2
+    assert abs(int(integ.stats.shadow_rays) - int(rst.shadow_rays)) <= 2
+    plain = integ.render(Options()).copy()
+    integ.film[:] = 0
+    assert not np.array_equal(plain, film)
     integ.close()
