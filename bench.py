@@ -203,14 +203,28 @@ def main():
 
     # ---- e2e: the user-facing call with HOST buffers (sg_render: params in, film D2H inside the timed region)
     host_film = integ.film
+    host_pinned = torch.empty((npix, 4), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
+
+    def e2e_step():
+        if world == 1:
+            integ.render(opts, sample_range=my_range, flags=4)      # SG_RENDER_OVERWRITE_FILM: film of this step only
+            return
+        # N > 1: the whole job's film has to land in rank 0's host memory -- device render, the NCCL film reduce, one D2H on rank 0
+        film.zero_()
+        integ.render_device(opts, film.data_ptr(), sample_range=my_range, stream=stream)
+        reduce_film(film, dst=0)
+        if rank == 0:
+            host_pinned.copy_(film, non_blocking=True)
+        torch.cuda.synchronize()
+
     for _ in range(max(args.warmup, 3)):                      # untimed warm-up of the host path too: the first sg_render allocates the
-        integ.render(opts, sample_range=my_range, flags=4)    # pinned staging buffer and first-touches the caller's film pages (~35 ms once)
+        e2e_step()                                            # pinned staging buffer and first-touches the caller's film pages (~35 ms once)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        integ.render(opts, sample_range=my_range, flags=4)      # SG_RENDER_OVERWRITE_FILM: film of this step only
+        e2e_step()
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -273,7 +287,9 @@ def main():
                            "l2": "working set (path state %.2f GB + scene) exceeds the 126 MB L2; no explicit flush" % (min(npix * spp, integ.max_paths_in_flight or (1 << 26)) * 276 / 1e9),
                            "scene_build_s": build_s, "scene_upload_s": upload_s},
                 "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(__import__("shimmer_b200").ffi.SgRenderParams),
-                        "d2h_bytes_per_step": npix * 32, "note": "sg_render: host film buffer, scene resident (uploaded once)",
+                        "d2h_bytes_per_step": npix * 32,
+                        "note": ("sg_render: host film buffer, scene resident (uploaded once)" if world == 1 else
+                                 "sg_render_device on every rank + NCCL film reduce + D2H of the reduced film into rank 0's pinned host buffer; scene resident"),
                         "value_incl_scene_upload": paths_total / (float(e2e_t[0]) + args.steps * upload_s) / 1e6,
                         "scene_upload_bytes": int(sc.meta.get("upload_bytes", 0))},
                 "gpu_launches": launches_total, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
