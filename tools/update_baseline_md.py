@@ -45,7 +45,11 @@ for name, d in sorted(sc, key=lambda x: (x[1]["config"]["workload"][:4], x[1]["n
     b1 = base1.get(wl)
     eff = d["value"] / (b1 * d["n_gpus"]) if b1 else float("nan")
     label = "C2 mesh1m (weak)" if wl == "mesh1m" else "C5 composite 4K, 1024 spp total (strong: %d x %d spp)" % (d["n_gpus"], d["config"]["spp_per_gpu"])
-    out.append("| %s | %d | %d | %.1f | %.0f | %.1f | %.1f | %.3f |" % (label, d["n_gpus"], d["config"]["spp_per_gpu"], d["value"], d["mrays_per_s"], d["ms_per_step"], d["e2e"]["value"], eff))
+    old_def = d["n_gpus"] > 1 and d["e2e"].get("note", "").startswith("sg_render:")
+    out.append("| %s | %d | %d | %.1f | %.0f | %.1f | %.1f%s | %.3f |" % (label, d["n_gpus"], d["config"]["spp_per_gpu"], d["value"], d["mrays_per_s"], d["ms_per_step"], d["e2e"]["value"], " (*)" if old_def else "", eff))
+out.append("")
+out.append("e2e at N > 1 = `sg_render_device` on every rank + the NCCL film reduce + one D2H of the reduced film into rank 0's pinned host buffer (the whole")
+out.append("job's film in host memory).  Rows marked (*) were measured before that definition, as per-rank `sg_render` calls without the reduce.")
 out.append("")
 if bench:
     r = bench["roofline"]
