@@ -16,8 +16,14 @@
  *     duration of sg_scene_create (it is copied to HBM once)
  *   - all floats are IEEE f32 (`Float = f32`, src/float.rs:1-4); the film is f64
  *     (`RgbFilmPixel`, src/film.rs:470-479)
- *   - one process drives one GPU (sg_init selects it); multi-GPU runs one
- *     process per GPU and reduces the film with NCCL (see DESIGN.md section e)
+ *   - multi-GPU lives behind this boundary in two forms:
+ *       single process, n GPUs : sg_init_multi(devices, n) -- every scene is replicated on
+ *         every device, sg_render splits the sample range across them and sums the films onto
+ *         devices[0] with ONE in-library ncclReduce (communicator from ncclCommInitAll);
+ *       one process per GPU    : sg_init(device) + sg_comm_init_rank(id, rank, n) -- the same
+ *         split / reduce over an ncclCommInitRank communicator (torchrun, MPI-style launches).
+ *     NCCL is loaded lazily (dlopen libnccl.so.2) by the first sg_init_multi / sg_comm_* call,
+ *     so single-GPU hosts do not need it.
  */
 #ifndef SHIMMER_GPU_H
 #define SHIMMER_GPU_H
@@ -28,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 8
+#define SG_ABI_VERSION 9
 
 typedef enum SgStatus {
     SG_OK = 0,
@@ -36,7 +42,8 @@ typedef enum SgStatus {
     SG_ERR_CUDA = -2,
     SG_ERR_OUT_OF_MEMORY = -3,
     SG_ERR_UNSUPPORTED = -4,
-    SG_ERR_NOT_INITIALIZED = -5
+    SG_ERR_NOT_INITIALIZED = -5,
+    SG_ERR_NCCL = -6
 } SgStatus;
 
 /* ---- acceleration structure ------------------------------------------------
@@ -422,7 +429,15 @@ enum { SG_SIMPLEPATH_SAMPLE_LIGHTS = 1, SG_SIMPLEPATH_SAMPLE_BSDF = 2 };
 enum {
     SG_RENDER_COUNT_VISITS = 1,   /* count BVH nodes / triangles tested (slower; roofline accounting) */
     SG_RENDER_TIME_KERNELS = 2,   /* CUDA events around every traversal launch -> closest_ms/shadow_ms */
-    SG_RENDER_OVERWRITE_FILM = 4  /* sg_render: store the film instead of adding to the caller's sums  */
+    SG_RENDER_OVERWRITE_FILM = 4, /* sg_render: store the film instead of adding to the caller's sums  */
+    /* multi-GPU (the tile fan-out of integrator.rs:235-245, by sample range instead of by tile): */
+    SG_RENDER_SPLIT_SAMPLES = 8,  /* with a process communicator (sg_comm_init_rank): this rank renders ITS share of
+                                     [sample_begin, sample_end) -- rank r of n gets a contiguous range, remainder to the low
+                                     ranks (sg_sample_range_for_rank).  Implied for sg_render after sg_init_multi.             */
+    SG_RENDER_REDUCE_FILM = 16    /* with a process communicator: after the render, ONE ncclReduce (f64 sum) of the film onto
+                                     rank 0, in stream order.  sg_render: only rank 0's `film` is written (other ranks may pass
+                                     NULL); sg_render_device: d_film is reduced in place.  Implied for sg_render after
+                                     sg_init_multi.                                                                            */
 };
 
 /* `RgbFilmPixel` without the (unused on this path) splat: film.rs:470-479. */
@@ -446,6 +461,12 @@ typedef struct SgStats {
     uint64_t shadow_launches;
     double   closest_ms;        /* device time of the closest-hit kernels (reserved bit 1)  */
     double   shadow_ms;         /* device time of the any-hit kernels     (reserved bit 1)  */
+    /* multi-GPU: render_ms is the slowest device's wavefront loop; ray / path counters are summed over the devices this
+     * process drives (one process per GPU: this rank's only) */
+    double   reduce_ms;         /* device time of the NCCL film reduce on the root (includes waiting for the slowest rank) */
+    double   d2h_ms;            /* sg_render: device -> pinned host copy of the (reduced) film                              */
+    uint32_t n_devices;         /* devices that rendered in this call (single process) or ranks of the communicator         */
+    uint32_t rank;              /* this process's rank in the communicator (0 without one)                                  */
 } SgStats;
 
 /* `ShapeIntersection` reduced to what parity needs (shape.rs:221-225 +
@@ -459,9 +480,31 @@ typedef struct SgHit {
 
 typedef struct SgScene SgScene;
 
-/* Selects the CUDA device of this process and creates the library's stream. */
+/* Selects the CUDA device of this process and creates the library's stream.  Calling it again with another device moves
+ * the library there (scenes created before stay on their device and must be destroyed first). */
 int sg_init(int device);
+/* Single process, n GPUs (`sg_init(const int* devices, int n)`): one stream per device and one in-process NCCL
+ * communicator (ncclCommInitAll).  Afterwards sg_scene_create replicates the scene on every device and sg_render splits
+ * [sample_begin, sample_end) across them (rayon's tile fan-out, integrator.rs:235-245, becomes a sample-range fan-out),
+ * sums the films onto devices[0] with one ncclReduce and copies the result to the caller's host film.  Every other entry
+ * point (sg_render_device, sg_trace, ...) runs on devices[0].  n == 1 is sg_init(devices[0]). */
+int sg_init_multi(const int* devices, int n);
+int sg_device_count(void);      /* devices this process drives (0 before sg_init) */
 int sg_shutdown(void);
+
+/* One process per GPU: a communicator across processes.  Rank 0 calls sg_comm_get_unique_id and hands the
+ * SG_COMM_ID_BYTES bytes to the other ranks by any means (a file, MPI, torch.distributed broadcast, a socket);
+ * then EVERY rank calls sg_comm_init_rank (collective).  sg_comm_destroy is collective too. */
+#define SG_COMM_ID_BYTES 128
+int sg_comm_get_unique_id(void* id_out);
+int sg_comm_init_rank(const void* id, int rank, int n_ranks);
+int sg_comm_destroy(void);
+int sg_comm_rank(int* rank, int* n_ranks);   /* 0 / 1 without a communicator */
+/* The sample-index range rank `rank` of `n_ranks` renders out of [begin, end): contiguous, remainder to the low ranks. */
+int sg_sample_range_for_rank(int32_t begin, int32_t end, int rank, int n_ranks, int32_t* out_begin, int32_t* out_end);
+/* In-place ncclReduce (sum of f64) of a device film onto rank 0 of the process communicator, on `stream`
+ * (a no-op without a communicator or with one rank).  n_pixels SgFilmPixel records. */
+int sg_film_reduce_device(void* d_film, int64_t n_pixels, void* stream);
 const char* sg_last_error(void);
 int sg_abi_version(void);
 
@@ -475,7 +518,9 @@ int sg_scene_destroy(SgScene* scene);
  * ADDS them into `film` (row-major (y-y0)*W+(x-x0), vec2d.rs:24-28).
  * sg_render: `film` is host memory (copied back inside the call).
  * sg_render_device: `film` is device memory of this process's GPU, zeroed by
- * the caller; `stream` is a cudaStream_t (NULL = library stream). */
+ * the caller; `stream` is the cudaStream_t the caller's own work on d_film is ordered on -- every kernel (and the
+ * optional reduce) is enqueued there.  NULL is the CUDA legacy default stream (what a handle of 0 means everywhere
+ * else, e.g. torch.cuda.current_stream().cuda_stream on torch's default stream), NOT a private library stream. */
 int sg_render(SgScene* scene, const SgRenderParams* params, SgFilmPixel* film, SgStats* stats);
 int sg_render_device(SgScene* scene, const SgRenderParams* params, void* d_film, SgStats* stats, void* stream);
 

@@ -135,24 +135,27 @@ struct Hit { int32_t prim; int32_t inst; TriHit th; };   // sphere hits: th.b0..
 namespace orc {
 
 // Transform::apply_ray_inverse transform.rs:701-723 (inverse = true) / Transform::apply_ray :515-532 (inverse = false)
-// with Some(t_max): origin through the Point3fi transform of an EXACT point (:631-700 / :385-457 -- note the inverse
-// variant's error term omits the translation column), shifted to the edge of its error bounds; t_max reduced by dt.
+// with Some(t_max): the inverse variant sends the origin through the Point3fi transform of an EXACT point (:631-700; its error
+// term omits the translation column) and shifts it to the edge of its error bounds, t_max reduced by dt; the forward variant
+// transforms a plain Point3f, so its interval has zero width and dt == 0.
 inline Ray instance_ray(const SgInstance& I, const Ray& r, bool inverse, Float* t_max) {
     const float* m = inverse ? I.primitive_from_render : I.render_from_primitive;
     Float x = r.o.x, y = r.o.y, z = r.o.z;
-    Float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
-    Float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
-    Float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
-    Float wp = (m[12] * x + m[13] * y) + (m[14] * z + m[15]);
-    V3 err;
-    if (inverse) err = v3(gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z)),
-                          gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z)),
-                          gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z)));
-    else err = v3(gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3])),
-                  gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7])),
-                  gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])));
-    P3fi o = p3fi_from_value_and_error(v3(xp, yp, zp), err);
-    (void)wp;                    // instance transforms are affine (last row 0 0 0 1): the `/ wp` branch (:453-457) is never taken
+    P3fi o;
+    if (inverse) {               // apply_ray_inverse: apply_inverse(Point3fi::from(o)), error term without the translation column
+        Float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
+        Float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
+        Float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
+        V3 err = v3(gamma_n(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z)),
+                    gamma_n(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z)),
+                    gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z)));
+        o = p3fi_from_value_and_error(v3(xp, yp, zp), err);
+    } else {                     // apply_ray (:516-517): `self.apply(val.o)` is the Point3f overload (apply_point_helper :753-767, summed left
+                                 // to right); `.into()` gives a ZERO-width interval, so dt below is 0 and only the interval add + midpoint remain
+        V3 pp = v3(((m[0] * x + m[1] * y) + m[2] * z) + m[3], ((m[4] * x + m[5] * y) + m[6] * z) + m[7], ((m[8] * x + m[9] * y) + m[10] * z) + m[11]);
+        o = p3fi_from_value_and_error(pp, v3(0.0f, 0.0f, 0.0f));
+    }
+    // instance transforms are affine (last row 0 0 0 1): the `/ wp` branches (:453-457, :761-766) are never taken
     V3 d = v3(m[0] * r.d.x + m[1] * r.d.y + m[2] * r.d.z, m[4] * r.d.x + m[5] * r.d.y + m[6] * r.d.z, m[8] * r.d.x + m[9] * r.d.y + m[10] * r.d.z);
     Float ls = length_squared(d);
     if (ls > 0.0f) {

@@ -911,9 +911,13 @@ inline P3fi xform_point_exact_fi(const float m[16], V3 p) {
                 gamma_n(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])));
     return p3fi_from_value_and_error(v3(xp, yp, zp), err);
 }
-// Transform::apply_ray transform.rs:515-532 (t_max = None)
+// Transform::apply_ray transform.rs:515-532 (t_max = None): `self.apply(val.o)` is the Point3f overload (apply_point_helper
+// :753-767, summed left to right) and `.into()` makes a zero-width Point3fi -> o.error() == 0, dt == 0; the interval addition
+// o + (d * dt) and the midpoint of `o.into()` remain.
 inline Ray xform_ray(const float m[16], Ray r) {
-    P3fi o = xform_point_exact_fi(m, r.o);
+    const Float x = r.o.x, y = r.o.y, z = r.o.z;
+    V3 pp = v3(((m[0] * x + m[1] * y) + m[2] * z) + m[3], ((m[4] * x + m[5] * y) + m[6] * z) + m[7], ((m[8] * x + m[9] * y) + m[10] * z) + m[11]);
+    P3fi o = p3fi_from_value_and_error(pp, v3(0.0f, 0.0f, 0.0f));
     V3 d = xform_vector(m, r.d);
     Float ls = length_squared(d);
     if (ls > 0.0f) {

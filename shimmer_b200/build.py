@@ -43,7 +43,8 @@ def build_gpu(force=False, verbose=False):
     failed = [name for name, _, p in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
-    subprocess.run([nvcc, "--shared", "-o", out] + [obj for _, obj, _ in procs], check=True)
+    # NCCL is dlopen'ed at run time (csrc/shimmer_gpu.cu: nccl_load), so the library links against nothing but cudart and libdl
+    subprocess.run([nvcc, "--shared", "-o", out] + [obj for _, obj, _ in procs] + ["-ldl"], check=True)
     return out
 
 

@@ -770,15 +770,15 @@ SGD float3 xform_vector(const float* m, float3 v) {
     return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
 }
 SGD void xform_ray(const float* m, float3& o, float3& d) {
-    // Transform::apply(Point3fi) on an exact point (exact branch), then the origin shift of apply_ray
-    float x = o.x, y = o.y, z = o.z;
-    float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
-    float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
-    float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
-    float3 err = f3(gamma_n(3) * (fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z) + fabsf(m[3])),
-                    gamma_n(3) * (fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z) + fabsf(m[7])),
-                    gamma_n(3) * (fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z) + fabsf(m[11])));
-    P3fi oi = p3fi_make(f3(xp, yp, zp), err);
+    // Transform::apply_ray (transform.rs:515-532): `self.apply(val.o)` is the Point3f overload (apply_point_helper :753-767, summed
+    // left to right) and `.into()` makes a ZERO-width Point3fi, so the error-bound shift is dt = 0; what remains of it is the
+    // interval addition o + (d * dt) (lo rounded down, hi rounded up, interval.rs:353-356) and the midpoint taken by `o.into()`.
+    // Only apply_ray_inverse (:701-723) carries a real error term.
+    const float x = o.x, y = o.y, z = o.z;
+    const float xp = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+    const float yp = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+    const float zp = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+    P3fi oi = p3fi_exact(f3(xp, yp, zp));
     float3 dd = xform_vector(m, d);
     float ls = len2(dd);
     if (ls > 0.0f) {

@@ -122,21 +122,22 @@ SGD void lane_begin(const TraceScene& ts, Lane& L, float3 o, float3 d, float t_m
     }
 }
 
-// Pops the next node whose entry distance is still in range; kEmptyRef when the stack runs dry.
-// Transform::apply_ray_inverse (transform.rs:701-723, inverse = true) / apply_ray (:515-532) with Some(t_max): the
-// origin goes through the Point3fi transform of an exact point (the inverse variant's error term omits the translation
-// column, :650-662), is shifted to the edge of its error box, and t_max shrinks by dt.
+// Transform::apply_ray_inverse (transform.rs:701-723, inverse = true) / apply_ray (:515-532, inverse = false) with Some(t_max):
+// the origin is shifted to the edge of its error box and t_max shrinks by dt -- a real shift for the inverse variant only.
 SGD void instance_ray(const DInstance& I, bool inverse, float3& o, float3& d, float& t_max) {
     const float* m = inverse ? I.mi : I.m;
     const float x = o.x, y = o.y, z = o.z;
-    const float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
-    const float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
-    const float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
-    float3 err = f3(fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z), fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z),
-                    fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z));
-    if (!inverse) err = f3(err.x + fabsf(m[3]), err.y + fabsf(m[7]), err.z + fabsf(m[11]));
-    err = f3(gamma_n(3) * err.x, gamma_n(3) * err.y, gamma_n(3) * err.z);
-    P3fi oi = p3fi_make(f3(xp, yp, zp), err);
+    P3fi oi;
+    if (inverse) {          // apply_ray_inverse: Point3fi transform of an exact point, error term without the translation column (:650-662)
+        const float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
+        const float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
+        const float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
+        const float3 err = f3(gamma_n(3) * (fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z)), gamma_n(3) * (fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z)),
+                              gamma_n(3) * (fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z)));
+        oi = p3fi_make(f3(xp, yp, zp), err);
+    } else {                // apply_ray (:515-532): the Point3f overload (apply_point_helper, left to right) -> zero-width interval, dt = 0
+        oi = p3fi_exact(f3(((m[0] * x + m[1] * y) + m[2] * z) + m[3], ((m[4] * x + m[5] * y) + m[6] * z) + m[7], ((m[8] * x + m[9] * y) + m[10] * z) + m[11]));
+    }
     const float3 dd = f3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z);
     const float ls = len2(dd);
     if (ls > 0.0f) {

@@ -892,7 +892,11 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 st.flags[path] = (uint32_t)pdepth | (specular_bounce ? kFlagSpecular : 0u) | (any_non_specular ? kFlagNonSpecular : 0u) |
                                  (TEX && aux.has ? kFlagAux : 0u);
             }
-            if (KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC || KIND == SG_MATERIAL_COATED_CONDUCTOR) st.lpdf[path] = lam.pdf;   // terminate_secondary
+            // terminate_secondary (get_bsdf of a dispersive material).  SimplePath / RandomWalk return at `depth == max_depth` BEFORE
+            // get_bsdf (integrator.rs:520-523, :628-631), so their last vertex leaves the wavelengths alone; PathIntegrator::li builds
+            // the BSDF first and tests the depth afterwards (:815-833).
+            if ((KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC || KIND == SG_MATERIAL_COATED_CONDUCTOR) &&
+                (PATH || (int)(fl & 0xffu) != rc.max_depth)) st.lpdf[path] = lam.pdf;
             want_next = alive;
         }
         __syncwarp();

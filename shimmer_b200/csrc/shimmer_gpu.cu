@@ -14,17 +14,74 @@
 #include <new>
 #include <thread>
 #include <algorithm>
+#include <mutex>
+#include <dlfcn.h>
+#include <nccl.h>          // types and prototypes only: the library is dlopen'ed on first use (see Nccl below)
 
 using namespace sg;
 
 namespace {
 
 thread_local std::string g_err;
-int g_device = -1;
-cudaStream_t g_stream = nullptr;
-int g_num_sms = 0;
+// One entry per GPU this process drives.  g_dev[0] is the primary device: every entry point that is not a multi-GPU
+// render runs there.  A scene replica remembers the index of its device.
+struct Device { int id = -1; cudaStream_t stream = nullptr; int num_sms = 0; ncclComm_t comm = nullptr; };
+std::vector<Device> g_dev;
+#define g_device (g_dev.empty() ? -1 : g_dev[0].id)
+#define g_stream (g_dev[0].stream)
+// process communicator (one process per GPU): sg_comm_init_rank
+ncclComm_t g_proc_comm = nullptr; int g_proc_rank = 0, g_proc_nranks = 1;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// NCCL entry points resolved at run time: a single-GPU host does not need libnccl, and inside a process that already
+// carries one (e.g. torch's bundled copy) the same library instance is used.
+struct Nccl {
+    void* h = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclReduce) Reduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+} g_nccl;
+int nccl_load() {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (g_nccl.h) return SG_OK;
+    // SG_NCCL_LIB overrides the library; otherwise a copy the process already carries (e.g. torch's bundled one) is reused --
+    // the loader keys on the SONAME, so loading a second, older libnccl.so.2 first would break whoever needs the newer one.
+    void* h = nullptr;
+    if (const char* path = std::getenv("SG_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { if (h) break; h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); }
+    if (!h) return fail(SG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define NCCL_SYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) return fail(SG_ERR_NCCL, std::string("libnccl lacks ") + name)
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommInitAll, "ncclCommInitAll");
+    NCCL_SYM(CommDestroy, "ncclCommDestroy"); NCCL_SYM(Reduce, "ncclReduce"); NCCL_SYM(GroupStart, "ncclGroupStart");
+    NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    g_nccl.h = h;
+    return SG_OK;
+}
+#define NC(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) { \
+    return fail(SG_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r__)); } } while (0)
+
+// Entry points run on the device their scene lives on (default: the primary) and leave the caller's current device alone.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev_index) { cudaGetDevice(&prev); if (dev_index >= 0 && dev_index < (int)g_dev.size() && prev != g_dev[dev_index].id) cudaSetDevice(g_dev[dev_index].id); }
+    ~DeviceGuard() { int cur = -1; cudaGetDevice(&cur); if (prev >= 0 && cur != prev) cudaSetDevice(prev); }
+};
+#define ENTER(dev_index) if (g_dev.empty()) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called"); DeviceGuard guard__(dev_index)
+
+// destroys CUDA events on every exit path of a function
+struct EventBag {
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t make() { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; ev.push_back(e); return e; }
+    ~EventBag() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
 #define CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     return fail(e__ == cudaErrorMemoryAllocation ? SG_ERR_OUT_OF_MEMORY : SG_ERR_CUDA, \
                 std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
@@ -52,6 +109,8 @@ struct Workspace {
 }  // namespace
 
 struct SgScene {
+    int dev = 0;                    // index into g_dev of the device that holds this replica
+    std::vector<SgScene*> peers;    // replicas on g_dev[1..] (sg_init_multi); owned by the primary
     DScene d{};
     TraceScene ts{};
     size_t smem_closest = 0, smem_shadow = 0;
@@ -112,11 +171,11 @@ TraceRaysKernel trace_rays_kernel(bool any, bool count, bool inst) {
     return count ? (inst ? k_trace_rays<false, true, true> : k_trace_rays<false, true, false>) : (inst ? k_trace_rays<false, false, true> : k_trace_rays<false, false, false>);
 }
 
-int persistent_grid(const void* kernel, int threads, size_t smem) {
+int persistent_grid(int num_sms, const void* kernel, int threads, size_t smem) {
     int per_sm = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    return g_num_sms * per_sm;      // grid = SM count x resident CTAs: one full wave, persistent
+    return num_sms * per_sm;        // grid = SM count x resident CTAs: one full wave, persistent
 }
 
 }  // namespace
@@ -126,7 +185,7 @@ extern "C" {
 int sg_abi_version(void) { return SG_ABI_VERSION; }
 const char* sg_last_error(void) { return g_err.c_str(); }
 
-int sg_init(int device) {
+static int device_open(int device, Device& D) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return fail(SG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -135,24 +194,126 @@ int sg_init(int device) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(SG_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; found ") + prop.name);
-    g_num_sms = prop.multiProcessorCount;
-    if (!g_stream) CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    g_device = device;
+    D.id = device; D.num_sms = prop.multiProcessorCount; D.comm = nullptr;
+    CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
     return SG_OK;
 }
+static void devices_close() {
+    for (Device& D : g_dev) {
+        if (D.id >= 0) cudaSetDevice(D.id);
+        if (D.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D.comm);
+        if (D.stream) cudaStreamDestroy(D.stream);
+    }
+    g_dev.clear();
+}
+
+int sg_init_multi(const int* devices, int n) {
+    if (!devices || n < 1) return fail(SG_ERR_INVALID_ARGUMENT, "sg_init_multi: need at least one device");
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) if (devices[i] == devices[j]) return fail(SG_ERR_INVALID_ARGUMENT, "sg_init_multi: duplicate device");
+    bool same = (int)g_dev.size() == n;
+    for (int i = 0; same && i < n; ++i) same = g_dev[i].id == devices[i];
+    if (same) { CU(cudaSetDevice(g_dev[0].id)); return SG_OK; }
+    devices_close();                        // a different device set: streams (and the communicator) belong to the old one
+    std::vector<Device> devs(n);
+    for (int i = 0; i < n; ++i) {
+        const int rc = device_open(devices[i], devs[i]);
+        if (rc != SG_OK) { g_dev.assign(devs.begin(), devs.begin() + i); devices_close(); return rc; }
+    }
+    g_dev = devs;
+    if (n > 1) {
+        int rc = nccl_load();
+        if (rc != SG_OK) { devices_close(); return rc; }
+        std::vector<ncclComm_t> comms(n, nullptr);
+        const ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, devices);
+        if (r != ncclSuccess) { devices_close(); return fail(SG_ERR_NCCL, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r)); }
+        for (int i = 0; i < n; ++i) g_dev[i].comm = comms[i];
+    }
+    CU(cudaSetDevice(g_dev[0].id));
+    return SG_OK;
+}
+int sg_init(int device) { return sg_init_multi(&device, 1); }
+int sg_device_count(void) { return (int)g_dev.size(); }
 
 int sg_shutdown(void) {
-    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
-    g_device = -1;
+    if (g_proc_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(g_proc_comm); }
+    g_proc_comm = nullptr; g_proc_rank = 0; g_proc_nranks = 1;
+    devices_close();
     return SG_OK;
 }
 
+int sg_comm_get_unique_id(void* id_out) {
+    if (!id_out) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(ncclUniqueId) == SG_COMM_ID_BYTES, "SG_COMM_ID_BYTES must match ncclUniqueId");
+    int rc = nccl_load();
+    if (rc != SG_OK) return rc;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return SG_OK;
+}
+int sg_comm_init_rank(const void* id_in, int rank, int n_ranks) {
+    ENTER(0);
+    if (!id_in || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SG_ERR_INVALID_ARGUMENT, "sg_comm_init_rank: bad rank / n_ranks");
+    if (g_dev.size() != 1) return fail(SG_ERR_INVALID_ARGUMENT, "a process communicator needs a single-device process (sg_init, not sg_init_multi)");
+    if (g_proc_comm) return fail(SG_ERR_INVALID_ARGUMENT, "a process communicator already exists (sg_comm_destroy first)");
+    int rc = nccl_load();
+    if (rc != SG_OK) return rc;
+    CU(cudaSetDevice(g_dev[0].id));
+    ncclUniqueId id; std::memcpy(&id, id_in, sizeof id);
+    NC(g_nccl.CommInitRank(&g_proc_comm, n_ranks, id, rank));
+    g_proc_rank = rank; g_proc_nranks = n_ranks;
+    return SG_OK;
+}
+int sg_comm_destroy(void) {
+    if (g_proc_comm) { cudaSetDevice(g_dev.empty() ? 0 : g_dev[0].id); cudaDeviceSynchronize(); NC(g_nccl.CommDestroy(g_proc_comm)); }
+    g_proc_comm = nullptr; g_proc_rank = 0; g_proc_nranks = 1;
+    return SG_OK;
+}
+int sg_comm_rank(int* rank, int* n_ranks) {
+    if (rank) *rank = g_proc_rank;
+    if (n_ranks) *n_ranks = g_proc_nranks;
+    return SG_OK;
+}
+int sg_sample_range_for_rank(int32_t begin, int32_t end, int rank, int n_ranks, int32_t* out_begin, int32_t* out_end) {
+    if (!out_begin || !out_end || end < begin || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SG_ERR_INVALID_ARGUMENT, "sg_sample_range_for_rank: bad arguments");
+    const int32_t n = end - begin, base = n / n_ranks, rem = n % n_ranks;
+    *out_begin = begin + rank * base + std::min(rank, rem);
+    *out_end = *out_begin + base + (rank < rem ? 1 : 0);
+    return SG_OK;
+}
+int sg_film_reduce_device(void* d_film, int64_t n_pixels, void* stream_v) {
+    ENTER(0);
+    if (!d_film || n_pixels < 0) return fail(SG_ERR_INVALID_ARGUMENT, "sg_film_reduce_device: bad arguments");
+    if (!g_proc_comm || g_proc_nranks == 1 || n_pixels == 0) return SG_OK;
+    NC(g_nccl.Reduce(d_film, d_film, (size_t)n_pixels * 4, ncclDouble, ncclSum, 0, g_proc_comm, (cudaStream_t)stream_v));
+    return SG_OK;
+}
+
+static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out);
 int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (g_dev.empty()) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
     if (!desc || !out) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    SgScene* primary = nullptr;
+    int rc = scene_create_on(desc, 0, &primary);
+    if (rc != SG_OK) return rc;
+    for (int i = 1; i < (int)g_dev.size(); ++i) {           // sg_init_multi: one replica per device, staged once
+        SgScene* peer = nullptr;
+        rc = scene_create_on(desc, i, &peer);
+        if (rc != SG_OK) { const std::string msg = g_err; sg_scene_destroy(primary); g_err = msg; return rc; }
+        primary->peers.push_back(peer);
+    }
+    *out = primary;
+    return SG_OK;
+}
+static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out) {
+    DeviceGuard guard__(dev_index);
     if (desc->abi_version != SG_ABI_VERSION) return fail(SG_ERR_INVALID_ARGUMENT, "SgSceneDesc.abi_version mismatch");
     if (desc->n_primitives > 0 && (!desc->nodes || !desc->primitives)) return fail(SG_ERR_INVALID_ARGUMENT, "geometry arrays missing");
     if (desc->n_spheres && !desc->spheres) return fail(SG_ERR_INVALID_ARGUMENT, "sphere array missing");
+    if ((desc->n_textures && !desc->textures) || (desc->n_materials && !desc->materials) || (desc->n_lights && !desc->lights) ||
+        (desc->n_spectra && !desc->spectra) || (desc->n_meshes && !desc->meshes))
+        return fail(SG_ERR_INVALID_ARGUMENT, "texture / material / light / spectrum / mesh arrays missing");
     if (desc->camera.kind != SG_CAMERA_PERSPECTIVE && desc->camera.kind != SG_CAMERA_ORTHOGRAPHIC) return fail(SG_ERR_UNSUPPORTED, "camera kind is not on the GPU path");
     if (desc->n_primitives >= (1u << 31)) return fail(SG_ERR_UNSUPPORTED, "too many primitives");
     // validate references so device code never reads out of bounds
@@ -189,6 +350,14 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         if (p.mesh >= desc->n_meshes || p.tri >= desc->meshes[p.mesh].n_triangles || p.material >= desc->n_materials ||
             p.light >= (int32_t)desc->n_lights)
             return fail(SG_ERR_INVALID_ARGUMENT, "primitive " + std::to_string(i) + " references out-of-range mesh/triangle/material/light");
+        if (!(desc->meshes[p.mesh].flags & SG_MESH_BILINEAR) && p.light >= 0) {
+            // light sampling reads the emitter's render-space vertices (light_verts): an emitter inside an object definition would be
+            // sampled untransformed, and a light row of another kind / over another triangle would be sampled instead of this one
+            if (i >= n_top_prims) return fail(SG_ERR_UNSUPPORTED, "area lights inside object definitions are not supported (pbrt-v4 scene format)");
+            const SgLight& L = desc->lights[p.light];
+            if (L.kind != SG_LIGHT_DIFFUSE_AREA || L.mesh != p.mesh || L.tri != p.tri)
+                return fail(SG_ERR_INVALID_ARGUMENT, "an emissive triangle must point at an SG_LIGHT_DIFFUSE_AREA light over that triangle");
+        }
     }
     for (uint32_t i = 0; i < desc->n_objects; ++i) {
         const SgObject& o = desc->objects[i];
@@ -276,7 +445,6 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
     };
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
         const SgTexture& t = desc->textures[i];
-        if (!desc->textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture arrays missing");
         if (t.kind != SG_TEXTURE_IMAGE) {
             if (t.n_channels < 1 || tex_depth((int32_t)i, false, SG_MAX_TEXTURE_DEPTH) < 0)
                 return fail(SG_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": bad kind / node / operand ids or types, a cycle, or operands nested deeper than SG_MAX_TEXTURE_DEPTH");
@@ -325,6 +493,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
             return fail(SG_ERR_INVALID_ARGUMENT, "BVH of object " + std::to_string(i) + " is malformed");
     SgScene* s = new (std::nothrow) SgScene();
     if (!s) return fail(SG_ERR_OUT_OF_MEMORY, "host allocation failed");
+    s->dev = dev_index;
     int rc = SG_OK;
     auto bail = [&](int code) { sg_scene_destroy(s); return code; };
     DScene& d = s->d;
@@ -450,7 +619,7 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
         s->ts.scene_flags = desc->scene_flags;
         auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
         s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 8);
-        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 6);
+        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 12);
         s->ts.interior_burst = env_int("SG_INTERIOR_BURST", 4);
         s->ts.prefetch = env_int("SG_PREFETCH", 0);
         // shared-memory part of the per-thread stack: 20 levels x 8 B x 128 threads = 20.5 KB -> 9 CTAs (36 warps, the register limit at 56 regs) per SM;
@@ -572,6 +741,9 @@ int sg_scene_create(const SgSceneDesc* desc, SgScene** out) {
 
 int sg_scene_destroy(SgScene* s) {
     if (!s) return SG_OK;
+    for (SgScene* peer : s->peers) sg_scene_destroy(peer);
+    s->peers.clear();
+    DeviceGuard guard__(s->dev);
     cudaDeviceSynchronize();
     s->ws.release();
     for (void* p : s->owned) cudaFree(p);
@@ -581,14 +753,18 @@ int sg_scene_destroy(SgScene* s) {
     return SG_OK;
 }
 
-int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats* stats, void* stream_v) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+// The wavefront loop of one scene replica on its own device: samples [rp->sample_begin, rp->sample_end) of every pixel are
+// ADDED into d_film.  With `reduce` the film is then summed onto rank 0 of the process communicator in stream order.
+// Blocks until the stream has drained (the stats are read back).
+static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats* stats, cudaStream_t stream, bool reduce) {
     if (!s || !rp || !d_film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (rp->sample_end < rp->sample_begin || rp->sample_begin < 0) return fail(SG_ERR_INVALID_ARGUMENT, "bad sample range");
     if (rp->max_depth < 0 || rp->max_depth > 254) return fail(SG_ERR_INVALID_ARGUMENT, "max_depth out of range");
     const bool force_diffuse = (rp->option_flags & SG_OPT_FORCE_DIFFUSE) != 0;
     if (force_diffuse && rp->integrator != SG_INTEGRATOR_PATH) return fail(SG_ERR_UNSUPPORTED, "force_diffuse is on the GPU path for the path integrator only");
-    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
+    if (rp->integrator < SG_INTEGRATOR_PATH || rp->integrator > SG_INTEGRATOR_RANDOM_WALK) return fail(SG_ERR_INVALID_ARGUMENT, "unknown integrator kind");
+    DeviceGuard guard__(s->dev);
+    const int num_sms = g_dev[s->dev].num_sms;
     const bool count = (rp->flags & SG_RENDER_COUNT_VISITS) != 0;
     const uint64_t npix = s->n_pixels();
     const uint64_t total = npix * (uint64_t)(rp->sample_end - rp->sample_begin);
@@ -607,7 +783,6 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.full_res_x = s->d.film.full_resolution[0];
     k.n_samples = rp->sample_end - rp->sample_begin;
     { const char* v = std::getenv("SG_PATH_ORDER"); k.path_order = v ? std::atoi(v) : 1; }
-    if (rp->integrator < SG_INTEGRATOR_PATH || rp->integrator > SG_INTEGRATOR_RANDOM_WALK) return fail(SG_ERR_INVALID_ARGUMENT, "unknown integrator kind");
     k.integrator = rp->integrator; k.integrator_flags = rp->integrator_flags;
     const bool path_integrator = rp->integrator == SG_INTEGRATOR_PATH;
     if (k.n_samples == 0) k.n_samples = 1;
@@ -615,13 +790,15 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     const int n_depths = rp->max_depth + 1;
     const size_t smc = s->smem_closest, sms = s->smem_shadow;
     const TraceKernel kern_closest = trace_kernel(false, count, s->instanced), kern_shadow = trace_kernel(true, count, s->instanced);
-    const int grid_closest = persistent_grid((const void*)kern_closest, kTraceThreads, smc);
-    const int grid_shadow = persistent_grid((const void*)kern_shadow, kTraceThreads, sms);
-    const int shade_grid = g_num_sms * 8;
+    const int grid_closest = persistent_grid(num_sms, (const void*)kern_closest, kTraceThreads, smc);
+    const int grid_shadow = persistent_grid(num_sms, (const void*)kern_shadow, kTraceThreads, sms);
+    const int shade_grid = num_sms * 8;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
-    cudaEvent_t ev0, ev1;
-    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    EventBag bag;                           // events die on every return path
+    cudaEvent_t ev0 = bag.make(), ev1 = bag.make(), ev2 = bag.make();
+    if (!ev0 || !ev1 || !ev2) return fail(SG_ERR_CUDA, "cudaEventCreate failed");
     std::vector<cudaEvent_t> tev, sev;      // event pairs around closest-hit / any-hit launches
+    auto mark = [&](std::vector<cudaEvent_t>& v) -> int { cudaEvent_t a = bag.make(); if (!a) return fail(SG_ERR_CUDA, "cudaEventCreate failed"); CU(cudaEventRecord(a, stream)); v.push_back(a); return SG_OK; };
     uint64_t launches = 0, closest_launches = 0, shadow_launches = 0;
     CU(cudaEventRecord(ev0, stream));
     for (uint64_t first = 0; first < total; first += capacity) {
@@ -629,10 +806,10 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         CU(cudaMemsetAsync(w.q.counters, 0, (size_t)(rp->max_depth + 3) * C_STRIDE * sizeof(uint32_t), stream));
         k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
         for (int depth = 0; depth < n_depths; ++depth) {
-            if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+            if (time_trace && (rc = mark(tev)) != SG_OK) return rc;
             kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
-            if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); tev.push_back(a); }
+            if (time_trace && (rc = mark(tev)) != SG_OK) return rc;
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             for (int kind = 0; kind <= SG_MATERIAL_COATED_CONDUCTOR; ++kind) {
@@ -641,20 +818,24 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
                 ++launches;
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
-                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
+                if (time_trace && (rc = mark(sev)) != SG_OK) return rc;
                 kern_shadow<<<grid_shadow, kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
                 ++launches; ++shadow_launches;
-                if (time_trace) { cudaEvent_t a; CU(cudaEventCreate(&a)); CU(cudaEventRecord(a, stream)); sev.push_back(a); }
+                if (time_trace && (rc = mark(sev)) != SG_OK) return rc;
             }
         }
         k_film<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, cnt, (double*)d_film); ++launches;
         k_accum_stats<<<1, 1, 0, stream>>>(w.q.counters, n_depths, s->d_stats); ++launches;
     }
     CU(cudaEventRecord(ev1, stream));
-    CU(cudaEventSynchronize(ev1));
+    const bool do_reduce = reduce && g_proc_comm && g_proc_nranks > 1;
+    if (do_reduce) NC(g_nccl.Reduce(d_film, d_film, (size_t)npix * 4, ncclDouble, ncclSum, 0, g_proc_comm, stream));
+    CU(cudaEventRecord(ev2, stream));
+    CU(cudaEventSynchronize(ev2));
     CU(cudaGetLastError());
-    float ms = 0.0f;
+    float ms = 0.0f, rms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (do_reduce) CU(cudaEventElapsedTime(&rms, ev1, ev2));
     double closest_ms = 0.0, shadow_ms = 0.0;
     for (size_t i = 0; i + 1 < tev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, tev[i], tev[i + 1]); closest_ms += t; }
     for (size_t i = 0; i + 1 < sev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, sev[i], sev[i + 1]); shadow_ms += t; }
@@ -665,9 +846,6 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         for (size_t i = 0; i + 1 < sev.size(); i += 2) { float t = 0.0f; cudaEventElapsedTime(&t, sev[i], sev[i + 1]); std::fprintf(stderr, " %.3f", t); }
         std::fprintf(stderr, " | total %.3f\n", ms);
     }
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    for (cudaEvent_t e : sev) cudaEventDestroy(e);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         DevStats h;
         CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
@@ -678,63 +856,161 @@ int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         stats->closest_nodes = h.nodes_closest; stats->closest_tris = h.tris_closest;
         stats->closest_launches = closest_launches; stats->shadow_launches = shadow_launches;
         stats->closest_ms = closest_ms; stats->shadow_ms = shadow_ms;
+        stats->reduce_ms = rms; stats->n_devices = (uint32_t)g_proc_nranks; stats->rank = (uint32_t)g_proc_rank;
     }
     return SG_OK;
 }
 
-int sg_render(SgScene* s, const SgRenderParams* rp, SgFilmPixel* film, SgStats* stats) {
-    if (!s || !rp || !film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
-    const size_t npix = (size_t)s->n_pixels();
+// this rank's share of the call's sample range (SG_RENDER_SPLIT_SAMPLES with a process communicator)
+static SgRenderParams split_for_rank(const SgRenderParams& rp) {
+    SgRenderParams p = rp;
+    if ((rp.flags & SG_RENDER_SPLIT_SAMPLES) && g_proc_comm && g_proc_nranks > 1)
+        sg_sample_range_for_rank(rp.sample_begin, rp.sample_end, g_proc_rank, g_proc_nranks, &p.sample_begin, &p.sample_end);
+    return p;
+}
+
+int sg_render_device(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats* stats, void* stream_v) {
+    if (g_dev.empty()) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || !rp || !d_film) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    // NULL = the legacy default stream: the caller's zeroing of d_film (and whatever reads it next) is ordered there
+    const SgRenderParams p = split_for_rank(*rp);
+    return render_on(s, &p, d_film, stats, (cudaStream_t)stream_v, (rp->flags & SG_RENDER_REDUCE_FILM) != 0);
+}
+
+static int ensure_film(SgScene* s, size_t npix, bool host) {
+    DeviceGuard guard__(s->dev);
     if (s->film_pixels < npix) {
         if (s->d_film) cudaFree(s->d_film);
         s->d_film = nullptr; s->film_pixels = 0;
         CU(cudaMalloc((void**)&s->d_film, npix * sizeof(SgFilmPixel)));
         s->film_pixels = npix;
     }
-    CU(cudaMemsetAsync(s->d_film, 0, npix * sizeof(SgFilmPixel), g_stream));
-    int rc = sg_render_device(s, rp, s->d_film, stats, g_stream);
-    if (rc != SG_OK) return rc;
-    // D2H through a pinned staging buffer (allocated once per scene), then accumulate into the caller's film
-    if (s->h_film_pixels < npix) {
+    if (host && s->h_film_pixels < npix) {                  // pinned staging, allocated once per scene
         if (s->h_film) cudaFreeHost(s->h_film);
         s->h_film = nullptr; s->h_film_pixels = 0;
         CU(cudaHostAlloc((void**)&s->h_film, npix * sizeof(SgFilmPixel), cudaHostAllocDefault));
         s->h_film_pixels = npix;
     }
-    CU(cudaMemcpyAsync(s->h_film, s->d_film, npix * sizeof(SgFilmPixel), cudaMemcpyDeviceToHost, g_stream));
-    CU(cudaStreamSynchronize(g_stream));
-    const double* src = reinterpret_cast<const double*>(s->h_film);
-    double* dst = reinterpret_cast<double*>(film);
-    const bool overwrite = (rp->flags & SG_RENDER_OVERWRITE_FILM) != 0;
-    const size_t n = 4 * npix;
-    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-    auto work = [&](unsigned t) {
-        const size_t b = n * t / nt, e = n * (t + 1) / nt;
-        if (overwrite) std::memcpy(dst + b, src + b, (e - b) * sizeof(double));
-        else for (size_t i = b; i < e; ++i) dst[i] += src[i];
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& t : th) t.join();
+    return SG_OK;
+}
+
+int sg_render(SgScene* s, const SgRenderParams* rp, SgFilmPixel* film, SgStats* stats) {
+    if (g_dev.empty()) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (!s || !rp) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
+    const bool proc_reduce = (rp->flags & SG_RENDER_REDUCE_FILM) && g_proc_comm && g_proc_nranks > 1;
+    const bool root = !proc_reduce || g_proc_rank == 0;     // only the root's host film is written
+    if (root && !film) return fail(SG_ERR_INVALID_ARGUMENT, "null film");
+    const size_t npix = (size_t)s->n_pixels();
+    const int n_dev = 1 + (int)s->peers.size();
+    DeviceGuard guard__(s->dev);
+    cudaStream_t stream0 = g_dev[s->dev].stream;
+    int rc = ensure_film(s, npix, root);
+    if (rc != SG_OK) return rc;
+    SgStats st0; std::memset(&st0, 0, sizeof st0);
+    double reduce_ms = 0.0;
+    if (n_dev == 1) {
+        CU(cudaMemsetAsync(s->d_film, 0, npix * sizeof(SgFilmPixel), stream0));
+        const SgRenderParams p = split_for_rank(*rp);
+        rc = render_on(s, &p, s->d_film, &st0, stream0, proc_reduce);
+        if (rc != SG_OK) return rc;
+        reduce_ms = st0.reduce_ms;
+    } else {
+        // single process, n GPUs: one host thread per device renders that device's share of the sample range into its own
+        // film (integrator.rs:235-245: the reference fans tiles out over rayon's pool); then ONE ncclReduce onto devices[0]
+        std::vector<SgScene*> rep(n_dev); rep[0] = s;
+        for (int i = 1; i < n_dev; ++i) rep[i] = s->peers[i - 1];
+        std::vector<SgStats> st(n_dev); std::vector<int> rcs(n_dev, SG_OK); std::vector<std::string> errs(n_dev);
+        auto work = [&](int i) {
+            SgScene* r = rep[i];
+            DeviceGuard g(r->dev);
+            cudaStream_t stream = g_dev[r->dev].stream;
+            int c = ensure_film(r, npix, false);
+            if (c == SG_OK && cudaMemsetAsync(r->d_film, 0, npix * sizeof(SgFilmPixel), stream) != cudaSuccess) c = fail(SG_ERR_CUDA, "cudaMemsetAsync(film)");
+            if (c == SG_OK) {
+                SgRenderParams p = *rp;
+                sg_sample_range_for_rank(rp->sample_begin, rp->sample_end, i, n_dev, &p.sample_begin, &p.sample_end);
+                c = render_on(r, &p, r->d_film, &st[i], stream, false);
+            }
+            rcs[i] = c; if (c != SG_OK) errs[i] = g_err;
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_dev; ++i) th.emplace_back(work, i);
+        work(0);
+        for (auto& t : th) t.join();
+        for (int i = 0; i < n_dev; ++i) if (rcs[i] != SG_OK) return fail(rcs[i], "device " + std::to_string(g_dev[rep[i]->dev].id) + ": " + errs[i]);
+        st0 = st[0];
+        for (int i = 1; i < n_dev; ++i) {
+            st0.camera_paths += st[i].camera_paths; st0.closest_hit_rays += st[i].closest_hit_rays; st0.shadow_rays += st[i].shadow_rays;
+            st0.nodes_visited += st[i].nodes_visited; st0.tris_tested += st[i].tris_tested; st0.kernel_launches += st[i].kernel_launches;
+            st0.closest_nodes += st[i].closest_nodes; st0.closest_tris += st[i].closest_tris;
+            st0.closest_launches += st[i].closest_launches; st0.shadow_launches += st[i].shadow_launches;
+            st0.render_ms = std::max(st0.render_ms, st[i].render_ms); st0.trace_ms = std::max(st0.trace_ms, st[i].trace_ms);
+            st0.closest_ms = std::max(st0.closest_ms, st[i].closest_ms); st0.shadow_ms = std::max(st0.shadow_ms, st[i].shadow_ms);
+        }
+        EventBag bag; cudaEvent_t e0 = bag.make(), e1 = bag.make();
+        if (!e0 || !e1) return fail(SG_ERR_CUDA, "cudaEventCreate failed");
+        CU(cudaEventRecord(e0, stream0));
+        NC(g_nccl.GroupStart());
+        for (int i = 0; i < n_dev; ++i) {
+            const ncclResult_t r = g_nccl.Reduce(rep[i]->d_film, rep[i]->d_film, npix * 4, ncclDouble, ncclSum, 0, g_dev[rep[i]->dev].comm, g_dev[rep[i]->dev].stream);
+            if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(SG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r)); }
+        }
+        NC(g_nccl.GroupEnd());
+        CU(cudaEventRecord(e1, stream0));
+        for (int i = 1; i < n_dev; ++i) { DeviceGuard g(rep[i]->dev); CU(cudaStreamSynchronize(g_dev[rep[i]->dev].stream)); }
+        CU(cudaEventSynchronize(e1));
+        float t = 0.0f; CU(cudaEventElapsedTime(&t, e0, e1)); reduce_ms = t;
+    }
+    double d2h_ms = 0.0;
+    if (root) {
+        // D2H through the pinned staging buffer, then accumulate into the caller's film
+        EventBag bag; cudaEvent_t e0 = bag.make(), e1 = bag.make();
+        if (!e0 || !e1) return fail(SG_ERR_CUDA, "cudaEventCreate failed");
+        CU(cudaEventRecord(e0, stream0));
+        CU(cudaMemcpyAsync(s->h_film, s->d_film, npix * sizeof(SgFilmPixel), cudaMemcpyDeviceToHost, stream0));
+        CU(cudaEventRecord(e1, stream0));
+        CU(cudaStreamSynchronize(stream0));
+        float t = 0.0f; CU(cudaEventElapsedTime(&t, e0, e1)); d2h_ms = t;
+        const double* src = reinterpret_cast<const double*>(s->h_film);
+        double* dst = reinterpret_cast<double*>(film);
+        const bool overwrite = (rp->flags & SG_RENDER_OVERWRITE_FILM) != 0;
+        const size_t n = 4 * npix;
+        const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        auto work = [&](unsigned t) {
+            const size_t b = n * t / nt, e = n * (t + 1) / nt;
+            if (overwrite) std::memcpy(dst + b, src + b, (e - b) * sizeof(double));
+            else for (size_t i = b; i < e; ++i) dst[i] += src[i];
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    if (stats) {
+        *stats = st0;
+        stats->reduce_ms = reduce_ms; stats->d2h_ms = d2h_ms;
+        stats->n_devices = n_dev > 1 ? (uint32_t)n_dev : (uint32_t)g_proc_nranks;
+        stats->rank = (uint32_t)g_proc_rank;
+    }
     return SG_OK;
 }
 
 int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, const void* d_t_max, int any_hit, void* d_out,
                     SgStats* stats, void* stream_v) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    if (g_dev.empty()) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
     if (!s || n < 0 || (n > 0 && (!d_o || !d_d || !d_t_max || !d_out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
-    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : g_stream;
+    DeviceGuard guard__(s->dev);
+    cudaStream_t stream = (cudaStream_t)stream_v;            // NULL = the legacy default stream (see sg_render_device)
     const bool count = stats != nullptr;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), stream));
-    cudaEvent_t ev0, ev1;
-    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    EventBag bag; cudaEvent_t ev0 = bag.make(), ev1 = bag.make();
+    if (!ev0 || !ev1) return fail(SG_ERR_CUDA, "cudaEventCreate failed");
     CU(cudaEventRecord(ev0, stream));
     if (n > 0) {
         const size_t sm = any_hit ? s->smem_shadow : s->smem_closest;
         const TraceRaysKernel kern = trace_rays_kernel(any_hit != 0, count, s->instanced);
-        const int g = persistent_grid((const void*)kern, kTraceThreads, sm);
+        const int g = persistent_grid(g_dev[s->dev].num_sms, (const void*)kern, kTraceThreads, sm);
         kern<<<g, kTraceThreads, sm, stream>>>(s->d, s->ts, (long long)n, (const float*)d_o, (const float*)d_d, (const float*)d_t_max, (SgHit*)d_out, s->d_cursor, s->d_stats);
     }
     CU(cudaEventRecord(ev1, stream));
@@ -742,7 +1018,6 @@ int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, con
     CU(cudaGetLastError());
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         DevStats h;
         CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
@@ -757,7 +1032,7 @@ int sg_trace_device(SgScene* s, int64_t n, const void* d_o, const void* d_d, con
 }
 
 int sg_trace(SgScene* s, int64_t n, const float* o, const float* d, const float* t_max, int any_hit, SgHit* out, SgStats* stats) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!s || n < 0 || (n > 0 && (!o || !d || !t_max || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (n == 0) { if (stats) std::memset(stats, 0, sizeof *stats); return SG_OK; }
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; SgHit* d_out = nullptr;
@@ -777,7 +1052,7 @@ int sg_trace(SgScene* s, int64_t n, const float* o, const float* d, const float*
 }
 
 int sg_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sample_index, int64_t n, float* out) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (n < 0 || (n > 0 && !out)) return fail(SG_ERR_INVALID_ARGUMENT, "bad arguments");
     if (n == 0) return SG_OK;
     float* d = nullptr;
@@ -792,7 +1067,7 @@ int sg_sampler_fill(uint64_t seed, int raw, uint32_t pixel_index, uint32_t sampl
 
 int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_t* pixel_xy, const int32_t* sample_index,
                    float* out_rays, float* out_lambda) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!s || !rp || n < 0 || (n > 0 && (!pixel_xy || !sample_index || !out_rays || !out_lambda))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (n == 0) return SG_OK;
     int *d_xy = nullptr, *d_si = nullptr; float *d_r = nullptr, *d_l = nullptr;
@@ -813,7 +1088,7 @@ int sg_camera_rays(SgScene* s, const SgRenderParams* rp, int64_t n, const int32_
 }
 
 int sg_texture_eval_ctx(SgScene* s, int tex, int as_float, int64_t n, const float* q, const float* pdp, const float* nrm, const float* lambda, float* out) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!s || n < 0 || (n > 0 && (!q || !lambda || !out))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (tex < 0 || (uint32_t)tex >= s->d.n_textures) return fail(SG_ERR_INVALID_ARGUMENT, "texture id out of range");
     if (n == 0) return SG_OK;
@@ -840,7 +1115,7 @@ int sg_texture_eval(SgScene* s, int tex, int as_float, int64_t n, const float* q
 }
 
 int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_rgb) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!s || n < 0 || (n > 0 && (!film || !out_rgb))) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (n == 0) return SG_OK;
     double* d_f = nullptr; float* d_o = nullptr;
@@ -857,7 +1132,7 @@ int sg_film_develop(SgScene* s, const SgFilmPixel* film, int64_t n, float* out_r
 }
 
 int sg_film_get_image(SgScene* s, const SgFilmPixel* film, int32_t w, int32_t h, uint32_t flags, float* out_rgb) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!s || w < 0 || h < 0 || (flags & ~3u)) return fail(SG_ERR_INVALID_ARGUMENT, "sg_film_get_image: bad size or flags");
     const size_t n = (size_t)w * (size_t)h;
     if (n == 0) return SG_OK;
@@ -900,7 +1175,7 @@ int sg_image_pyramid_layout(int32_t width, int32_t height, int32_t nc, int32_t* 
 }
 
 int sg_image_generate_pyramid(const float* image, int32_t width, int32_t height, int32_t nc, int32_t wrap, float* out_texels) {
-    if (g_device < 0) return fail(SG_ERR_NOT_INITIALIZED, "sg_init has not been called");
+    ENTER(0);
     if (!image || !out_texels) return fail(SG_ERR_INVALID_ARGUMENT, "null argument");
     if (wrap != SG_WRAP_REPEAT && wrap != SG_WRAP_CLAMP) return fail(SG_ERR_UNSUPPORTED, "pyramid construction supports the repeat and clamp wrap modes (image.rs:826-828 asserts on black)");
     int32_t n_levels = 0; uint64_t n_texels = 0; SgImageLevel levels[32];

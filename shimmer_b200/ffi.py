@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHIMMER_GPU_LIB") or os.path.join(_HERE, "libshimmer_gpu.so")   # override: A/B builds only
 HOST_LIB_PATH = os.path.join(_HERE, "libshimmer_host.so")
 
-SG_ABI_VERSION = 8
+SG_ABI_VERSION = 9
 
 # enums (mirror include/shimmer_gpu.h)
 SG_MESH_HAS_N, SG_MESH_HAS_UV, SG_MESH_HAS_S = 1, 2, 4
@@ -31,6 +31,8 @@ SG_SIMPLEPATH_SAMPLE_LIGHTS, SG_SIMPLEPATH_SAMPLE_BSDF = 1, 2
 SG_OPT_DISABLE_PIXEL_JITTER, SG_OPT_DISABLE_WAVELENGTH_JITTER = 1, 2
 SG_OPT_DISABLE_TEXTURE_FILTERING, SG_OPT_FORCE_DIFFUSE = 4, 8
 SG_RENDER_COUNT_VISITS, SG_RENDER_TIME_KERNELS, SG_RENDER_OVERWRITE_FILM = 1, 2, 4
+SG_RENDER_SPLIT_SAMPLES, SG_RENDER_REDUCE_FILM = 8, 16
+SG_COMM_ID_BYTES = 128
 
 
 class SgBvhNode(C.Structure):
@@ -194,7 +196,8 @@ class SgStats(C.Structure):
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double),
                 ("closest_nodes", C.c_uint64), ("closest_tris", C.c_uint64), ("closest_launches", C.c_uint64),
-                ("shadow_launches", C.c_uint64), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
+                ("shadow_launches", C.c_uint64), ("closest_ms", C.c_double), ("shadow_ms", C.c_double),
+                ("reduce_ms", C.c_double), ("d2h_ms", C.c_double), ("n_devices", C.c_uint32), ("rank", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -209,7 +212,8 @@ class SgHit(C.Structure):
 ABI_SYMBOLS = ["sg_init", "sg_shutdown", "sg_last_error", "sg_abi_version", "sg_scene_create", "sg_scene_destroy",
                "sg_render", "sg_render_device", "sg_trace", "sg_trace_device", "sg_sampler_fill", "sg_camera_rays",
                "sg_film_develop", "sg_texture_eval", "sg_texture_eval_p", "sg_texture_eval_ctx", "sg_film_get_image", "sg_image_pyramid_layout",
-               "sg_image_generate_pyramid"]
+               "sg_image_generate_pyramid", "sg_init_multi", "sg_device_count", "sg_comm_get_unique_id", "sg_comm_init_rank",
+               "sg_comm_destroy", "sg_comm_rank", "sg_sample_range_for_rank", "sg_film_reduce_device"]
 
 
 class ShimmerGpuError(RuntimeError):
@@ -234,6 +238,14 @@ def load_library():
     fp = C.POINTER(C.c_float)
     lib.sg_init.argtypes = [C.c_int]; lib.sg_init.restype = C.c_int
     lib.sg_shutdown.argtypes = []; lib.sg_shutdown.restype = C.c_int
+    lib.sg_init_multi.argtypes = [C.POINTER(C.c_int), C.c_int]; lib.sg_init_multi.restype = C.c_int
+    lib.sg_device_count.argtypes = []; lib.sg_device_count.restype = C.c_int
+    lib.sg_comm_get_unique_id.argtypes = [vp]; lib.sg_comm_get_unique_id.restype = C.c_int
+    lib.sg_comm_init_rank.argtypes = [vp, C.c_int, C.c_int]; lib.sg_comm_init_rank.restype = C.c_int
+    lib.sg_comm_destroy.argtypes = []; lib.sg_comm_destroy.restype = C.c_int
+    lib.sg_comm_rank.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]; lib.sg_comm_rank.restype = C.c_int
+    lib.sg_sample_range_for_rank.argtypes = [i32, i32, C.c_int, C.c_int, C.POINTER(i32), C.POINTER(i32)]; lib.sg_sample_range_for_rank.restype = C.c_int
+    lib.sg_film_reduce_device.argtypes = [vp, i64, vp]; lib.sg_film_reduce_device.restype = C.c_int
     lib.sg_last_error.argtypes = []; lib.sg_last_error.restype = C.c_char_p
     lib.sg_abi_version.argtypes = []; lib.sg_abi_version.restype = C.c_int
     lib.sg_scene_create.argtypes = [C.POINTER(SgSceneDesc), C.POINTER(vp)]; lib.sg_scene_create.restype = C.c_int

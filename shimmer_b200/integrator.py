@@ -52,11 +52,20 @@ _initialised_device = None
 
 
 def _ensure_init(device):
+    """`device`: one CUDA device index (sg_init) or a list of them (sg_init_multi: this process drives all of them, scenes are
+    replicated and `render` splits the sample range across the devices with one in-library NCCL reduce)."""
     global _initialised_device
     lib = ffi.load_library()
-    if _initialised_device != device:
-        ffi.check(lib.sg_init(int(device)), "sg_init")
-        _initialised_device = device
+    key = tuple(int(d) for d in device) if isinstance(device, (list, tuple)) else int(device)
+    if _initialised_device != key:
+        if isinstance(key, tuple):
+            from .distributed import _preload_process_nccl
+            _preload_process_nccl()
+            arr = (C.c_int * len(key))(*key)
+            ffi.check(lib.sg_init_multi(arr, len(key)), "sg_init_multi")
+        else:
+            ffi.check(lib.sg_init(key), "sg_init")
+        _initialised_device = key
     return lib
 
 
@@ -119,7 +128,8 @@ class WavefrontPathIntegrator(Integrator):
         return self.film
 
     def render_device(self, options: Options, d_film_ptr, sample_range=None, stream=None, flags=0):
-        """Accumulates into a device film buffer (e.g. a torch.float64 CUDA tensor's data_ptr())."""
+        """Accumulates into a device film buffer (e.g. a torch.float64 CUDA tensor's data_ptr()).  `stream`: the cudaStream_t handle
+        the caller's work on that buffer is ordered on; None / 0 = the legacy default stream (torch's default stream)."""
         p = self._params(options, sample_range, flags)
         ffi.check(self._lib.sg_render_device(self._handle, C.byref(p), C.c_void_p(d_film_ptr), C.byref(self.stats),
                                              C.c_void_p(stream) if stream else None), "sg_render_device")

@@ -41,6 +41,7 @@ def test_struct_sizes_match_the_header_layout():
     assert C.sizeof(ffi.SgFilmPixel) == 32
     assert C.sizeof(ffi.SgHit) == 32
     assert C.sizeof(ffi.SgRenderParams) == 48
+    assert C.sizeof(ffi.SgStats) == 136          # ABI v9: + reduce_ms, d2h_ms, n_devices, rank
     assert C.sizeof(ffi.SgTextureMapping) == 112 and C.sizeof(ffi.SgTextureNode) == 32 and C.sizeof(ffi.SgMaterialTextures) == 48 and C.sizeof(ffi.SgDistribution2D) == 32 and C.sizeof(ffi.SgEnvMap) == 208
     assert np.dtype(ffi.SgBvhNode).itemsize == 32
 
@@ -82,3 +83,27 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liborc" not in txt and "import orc" not in txt and "oracle/" not in txt.replace("oracle/ is test", ""), f
+
+
+def test_host_only_entry_points_work_without_a_gpu():
+    """The multi-GPU bookkeeping that needs no device: the sample-range split the ranks use (must agree with the Python
+    mirror rank by rank), the communicator query, and the not-initialised errors."""
+    import ctypes as C
+    from shimmer_b200.distributed import sample_range_for_rank
+    lib = ffi.load_library()
+    for begin, end in ((0, 1), (0, 7), (3, 64), (0, 1024), (5, 5)):
+        for world in (1, 2, 3, 4, 8):
+            for rank in range(world):
+                b, e = C.c_int32(), C.c_int32()
+                assert lib.sg_sample_range_for_rank(begin, end, rank, world, C.byref(b), C.byref(e)) == 0
+                pb, pe = sample_range_for_rank(end - begin, rank, world)
+                assert (b.value, e.value) == (begin + pb, begin + pe)
+    b, e = C.c_int32(), C.c_int32()
+    assert lib.sg_sample_range_for_rank(0, 4, 2, 2, C.byref(b), C.byref(e)) == -1          # rank out of range
+    r, n = C.c_int(-1), C.c_int(-1)
+    assert lib.sg_comm_rank(C.byref(r), C.byref(n)) == 0 and (r.value, n.value) == (0, 1)
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.sg_device_count() == 0
+        assert lib.sg_comm_init_rank(C.create_string_buffer(ffi.SG_COMM_ID_BYTES), 0, 1) == -5   # SG_ERR_NOT_INITIALIZED
+        assert lib.sg_film_reduce_device(C.c_void_p(8), 1, None) == -5

@@ -6,6 +6,7 @@
 CONFIG is a comma-separated list of ENV=VALUE pairs ("base" = no overrides), e.g.
   base SG_PATH_ORDER=0 SG_LEAF_THRESHOLD=12,SG_REFILL_THRESHOLD=8
 Knobs are read by sg_scene_create / sg_render_device, so every config re-creates the scene.
+The pseudo-knob PIF=<n> sets max_paths_in_flight (the wavefront width).
 Prints per-config: render ms, closest/shadow ms per depth (CUDA events), Mpaths/s.
 """
 import argparse
@@ -35,12 +36,16 @@ def main():
     ref_film = None
     for conf in args.configs:
         saved = {}
+        pif = 0
         if conf != "base":
             for kv in conf.split(","):
                 k, v = kv.split("=")
+                if k == "PIF":                       # max_paths_in_flight (a constructor argument, not an environment knob)
+                    pif = int(v)
+                    continue
                 saved[k] = os.environ.get(k)
                 os.environ[k] = v
-        integ = create_integrator("wavefront", {"maxdepth": cfg["max_depth"]}, sc, {"pixelsamples": spp})
+        integ = create_integrator("wavefront", {"maxdepth": cfg["max_depth"]}, sc, {"pixelsamples": spp}, max_paths_in_flight=pif)
         opts = Options(seed=0, pixel_samples=spp)
         film = torch.zeros((integ.width * integ.height, 4), dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
