@@ -44,7 +44,7 @@ def build_gpu(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
     # NCCL is dlopen'ed at run time (csrc/shimmer_gpu.cu: nccl_load), so the library links against nothing but cudart and libdl
-    subprocess.run([nvcc, "--shared", "-o", out] + [obj for _, obj, _ in procs] + ["-ldl"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out] + [obj for _, obj, _ in procs] + ["-ldl"], check=True)
     return out
 
 

@@ -161,16 +161,16 @@ static __global__ void __launch_bounds__(256) k_generate(const __grid_constant__
         aux_store(st, i, aux);
         flags0 = kFlagAux;
     } else camera_stage(sc, rc.option_flags, px, py, rng, lam, o, d, w);
+    // L = 0, beta = 1, p_b = eta_scale = 1 and the (unused) previous light-sample context are NOT written: at wavefront depth d
+    // every queued path has depth d (one bounce per iteration), so the depth-0 kernels take those values as constants
+    // (kernel argument `depth` == 0) and the first shade kernel stores them.  A path that escapes at depth 0 gets its L = 0
+    // from the closest-hit kernel's retire step.  108 instead of 196 bytes per camera sample.
     st.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
     st.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    st.L[i] = spec1(0.0f);
-    st.beta[i] = spec1(1.0f);
     st.lambda[i] = lam.lambda; st.lpdf[i] = lam.pdf;
     st.rng_a[i] = make_ulonglong2(rng.s0, rng.s1); st.rng_b[i] = make_ulonglong2(rng.s2, rng.s3);
     st.pixel[i] = pix;
     st.flags[i] = flags0;
-    st.pb_eta[i] = make_float2(1.0f, 1.0f);
-    st.ctx0[i] = make_float4(0, 0, 0, 0); st.ctx1[i] = make_float4(0, 0, 0, 0); st.ctx2[i] = make_float4(0, 0, 0, 0);
     q.ray[0][i] = i;
 }
 
@@ -319,6 +319,7 @@ SGD void trace_persistent_post(const TraceScene& ts, IO& io, CursorT n, CursorT*
 
 struct ClosestIO {
     const DScene& sc; PathState st; Queues q; uint32_t* C; const uint32_t* queue; uint32_t queue_mask;
+    bool first_depth;           // depth 0: nobody has written L yet (k_generate leaves it out) -- escaping paths get L = 0 here
     uint32_t path;
     SGD void load(uint32_t i, float3& o, float3& d, float& tmax) {
         path = queue[i];
@@ -333,7 +334,10 @@ struct ClosestIO {
             if (hit.prim >= 0) {
                 st.hit_b[path] = make_float4(hit.b0, hit.b1, hit.b2, hit.t);
                 kind = 1 + (int)((__float_as_uint(__ldg(sc.tri_verts + 3 * (size_t)hit.prim).w) >> 28) & 7u);
-            } else kind = Q_MISS;
+            } else {
+                kind = Q_MISS;
+                if (first_depth) st.L[path] = spec1(0.0f);
+            }
         }
 #pragma unroll
         for (int k = 0; k < Q_NKINDS; ++k) {
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
         if constexpr (POST) trace_persistent_post<true>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem);
         else trace_persistent<true, COUNT, INST>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, cnt_nodes, cnt_tris);
     } else {
-        ClosestIO io{sc, st, q, C, q.ray[depth & 1], ts.queue_mask, 0};
+        ClosestIO io{sc, st, q, C, q.ray[depth & 1], ts.queue_mask, depth == 0, 0};
         if constexpr (POST) trace_persistent_post<false>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem);
         else trace_persistent<false, COUNT, INST>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
     }
@@ -397,8 +401,9 @@ static __global__ void __launch_bounds__(128) k_shade_miss(const __grid_constant
         const uint32_t fl = st.flags[path];
         const int pdepth = fl & 0xff; const bool specular_bounce = (fl >> 8) & 1u;
         Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
-        Spec L = st.L[path]; const Spec beta = st.beta[path];
-        const float p_b = st.pb_eta[path].x;
+        Spec L = st.L[path];                                                     // depth 0: zeroed by the closest-hit retire step
+        const Spec beta = depth == 0 ? spec1(1.0f) : st.beta[path];              // depth 0: not in memory yet (see k_generate)
+        const float p_b = depth == 0 ? 1.0f : st.pb_eta[path].x;
         const float4 rd4 = st.ray_d[path];
         const float3 rd = f3(rd4.x, rd4.y, rd4.z);
         for (int k = 0; k < sc.n_infinite; ++k) {
@@ -592,8 +597,9 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
             uint32_t fl = st.flags[path];
             int pdepth = fl & 0xff; bool specular_bounce = (fl >> 8) & 1u; bool any_non_specular = (fl >> 9) & 1u;
             Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
-            Spec L = st.L[path]; Spec beta = st.beta[path];
-            float2 pbe = st.pb_eta[path];
+            // depth 0 (warp-uniform kernel argument): L = 0, beta = 1, p_b = eta_scale = 1 are not in memory yet (see k_generate)
+            Spec L = depth == 0 ? spec1(0.0f) : st.L[path]; Spec beta = depth == 0 ? spec1(1.0f) : st.beta[path];
+            float2 pbe = depth == 0 ? make_float2(1.0f, 1.0f) : st.pb_eta[path];
             float p_b = pbe.x, eta_scale = pbe.y;
 
             SurfTex sx;
@@ -931,8 +937,13 @@ static __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DSc
     float rgb[3] = {0.0f, 0.0f, 0.0f};
     uint32_t pixel = 0xffffffffu;
     if (live) {
-        Wavelengths lam; lam.lambda = st.lambda[i]; lam.pdf = st.lpdf[i];
-        film_sample_rgb(sc, st.L[i], lam, rgb);
+        const Spec L = st.L[i];
+        // a black sample contributes rgb = +0 whatever its wavelengths (0 / pdf, times the sensor curves, summed from +0):
+        // skip its 32 bytes of wavelength state and 12 sensor lookups -- half of C5's samples are background
+        if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f || L.w != 0.0f) {
+            Wavelengths lam; lam.lambda = st.lambda[i]; lam.pdf = st.lpdf[i];
+            film_sample_rgb(sc, L, lam, rgb);
+        }
         pixel = st.pixel[i];
     }
     const float weight = 1.0f;                                                      // BoxFilter::sample weight, filter.rs:99-105

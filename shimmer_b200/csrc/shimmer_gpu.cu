@@ -618,8 +618,8 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
         for (int k = 0; k < 3 && N; ++k) { s->ts.root_bmin[k] = desc->nodes[0].bmin[k]; s->ts.root_bmax[k] = desc->nodes[0].bmax[k]; }
         s->ts.scene_flags = desc->scene_flags;
         auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
-        s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 8);
-        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 12);
+        s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 6);
+        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 14);
         s->ts.interior_burst = env_int("SG_INTERIOR_BURST", 4);
         s->ts.prefetch = env_int("SG_PREFETCH", 0);
         // shared-memory part of the per-thread stack: 20 levels x 8 B x 128 threads = 20.5 KB -> 9 CTAs (36 warps, the register limit at 56 regs) per SM;

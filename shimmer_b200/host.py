@@ -306,6 +306,7 @@ class SceneBuilder:
         self.textures = []       # dicts: levels (list of HxWxC f32 arrays) + SgTexture parameters
         self.n_objects = 0       # object definitions (ObjectBegin/End); meshes carry an `object` id or None
         self.instances = []      # (object id, render_from_instance Transform)
+        self.instance_ctms = []  # world_from_instance of each instance, as given
         self.spheres = []        # dicts: Sphere::new fields + material (top-level shapes, after the meshes)
         self.patch_meshes = []   # dicts: BilinearPatchMesh (4 vertex indices per patch); top-level shapes, after the triangle meshes
         self.env_maps = []       # dicts: ImageInfinitelight images + render_from_light (light.rs:805-981)
@@ -475,6 +476,8 @@ class SceneBuilder:
         """PerspectiveCamera::create/new (camera.rs:839-963) + CameraTransform::new (:506-523) +
         ProjectiveCameraBase::new (:595-642)."""
         W, H = resolution
+        self.camera_args = dict(pos=tuple(pos), look=tuple(look), up=tuple(up), fov=fov, resolution=(W, H), lens_radius=lens_radius,
+                                focal_distance=focal_distance, crop=crop, kind=kind, screen_window=screen_window)
         camera_from_world = Transform.look_at(pos, look, up)
         world_from_camera = camera_from_world.inverse()
         if self.rendering_space == "camera-world":
@@ -577,6 +580,7 @@ class SceneBuilder:
         """ObjectInstance: render_from_instance = render_from_object * world_from_render (scene.rs:2002)."""
         ctm = world_from_instance if world_from_instance is not None else Transform.identity()
         self.instances.append((obj, self.render_from_world * ctm * self.render_from_world.inverse()))
+        self.instance_ctms.append(ctm)                      # the CTM at the ObjectInstance directive (pbrt_export.py)
 
     def add_mesh(self, p, indices, material, n=None, uv=None, area_light=None, reverse_orientation=False,
                  object_from_world=None, object=None):
@@ -585,6 +589,8 @@ class SceneBuilder:
         (scene.rs:609-622)."""
         ctm = object_from_world if object_from_world is not None else Transform.identity()
         rfo = self.render_from_world * ctm
+        src = dict(p=np.asarray(p, dtype=np.float32).reshape(-1, 3).copy(), n=None if n is None else np.asarray(n, dtype=np.float32).reshape(-1, 3).copy(),
+                   ctm=object_from_world, reverse_orientation=reverse_orientation)       # what the scene file holds (pbrt_export.py)
         p = rfo.apply_points_f32(np.asarray(p, dtype=np.float32).reshape(-1, 3))
         if n is not None:
             n = rfo.apply_normals_f32(np.asarray(n, dtype=np.float32).reshape(-1, 3))
@@ -597,7 +603,7 @@ class SceneBuilder:
         if rfo.swaps_handedness(): flags |= ffi.SG_MESH_SWAPS_HANDEDNESS
         self.meshes.append(dict(p=p, idx=np.asarray(indices, dtype=np.uint32).reshape(-1, 3), n=n,
                                 uv=None if uv is None else np.asarray(uv, dtype=np.float32).reshape(-1, 2),
-                                flags=flags, material=material, area_light=area_light, object=object))
+                                flags=flags, material=material, area_light=area_light, object=object, src=src))
         if object is not None and area_light is not None:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.meshes) - 1
@@ -642,7 +648,8 @@ class SceneBuilder:
                                  theta_z_min=f32(np.arccos(clamp(zlo / r, f32(-1.0), f32(1.0)))),
                                  theta_z_max=f32(np.arccos(clamp(zhi / r, f32(-1.0), f32(1.0)))),
                                  phi_max=f32(f32(np.pi) / f32(180.0)) * clamp(f32(phi_max), f32(0.0), f32(360.0)),
-                                 flags=flags, material=material, area_light=area_light, object=object))
+                                 flags=flags, material=material, area_light=area_light, object=object,
+                                 src=dict(radius=radius, z_min=z_min, z_max=z_max, phi_max=phi_max, ctm=object_from_world, reverse_orientation=reverse_orientation)))
         if object is not None and area_light is not None:
             raise ValueError("area lights are not supported inside object definitions")
         return len(self.spheres) - 1
@@ -652,13 +659,13 @@ class SceneBuilder:
         sc = f32(scale) / spectrum_to_photometric(I)
         pr = self.render_from_world.apply_points_f32(np.asarray([pos], dtype=np.float32))[0]
         self.extra_lights.append(dict(kind=ffi.SG_LIGHT_POINT, spectrum=self.spectrum(("dense", spectrum_dense(I))),
-                                      scale=float(sc), pos=pr))
+                                      scale=float(sc), pos=pr, src=dict(pos=tuple(pos), I=I, scale=scale)))
 
     def add_uniform_infinite_light(self, L, scale=1.0):
         """Light::create "infinite" with a constant L (light.rs:697-728)."""
         sc = f32(scale) / spectrum_to_photometric(L)
         self.extra_lights.append(dict(kind=ffi.SG_LIGHT_UNIFORM_INFINITE, spectrum=self.spectrum(("dense", spectrum_dense(L))),
-                                      scale=float(sc), pos=np.zeros(3, np.float32)))
+                                      scale=float(sc), pos=np.zeros(3, np.float32), src=dict(L=L, scale=scale)))
 
     def add_image_infinite_light(self, image, scale=1.0, illuminance=None, light_from_world=None):
         """Light::create "infinite" with a `filename` (light.rs:164-232) + ImageInfinitelight::new (:916-964).  `image`: square

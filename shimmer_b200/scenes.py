@@ -173,8 +173,13 @@ def composite_scene(n_theta=708, n_phi=708, resolution=(3840, 2160), crop=None):
     return b
 
 
-def procedural_image(n=64, channels=3):
-    """Deterministic linear-valued test image (row 0 = top): checker x gradients, closed form."""
+def procedural_image(n=64, channels=3, quantize8=False):
+    """Deterministic linear-valued test image (row 0 = top): checker x gradients, closed form.  quantize8: texels rounded to
+    multiples of 1/255, i.e. exactly what an 8-bit PNG with a linear colour encoding decodes to (shimmer reads only PNG,
+    image.rs:1140-1149) -- the BASELINE C4 scene uses it so that its PBRT export (pbrt_export.py) is texel-exact."""
+    if quantize8:
+        a = procedural_image(n, channels)
+        return (np.rint(a.astype(np.float64) * 255.0).astype(np.float32) / np.float32(255.0)).astype(np.float32)
     y, x = np.mgrid[0:n, 0:n].astype(np.float64) / n
     checker = (np.floor(x * 8.0) + np.floor(y * 8.0)) % 2.0
     r = 0.12 + 0.76 * checker
@@ -231,8 +236,8 @@ def instanced_scene(n_theta=224, n_phi=224, grid=10, resolution=(1920, 1080), cr
     b.fix_instancing = fix_instancing
     half = 2.0 * grid
     b.set_camera(pos=(0.0, 0.55 * half, -1.25 * half), look=(0.0, 0.0, -0.1 * half), up=(0, 1, 0), fov=42.0, resolution=resolution, crop=crop)
-    rgb_img, mono_img = procedural_image(tex_size, 3), procedural_image(tex_size // 2, 1)
-    ground = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(2 * tex_size, 3), filter="bilinear", su=8.0, sv=8.0))
+    rgb_img, mono_img = procedural_image(tex_size, 3, quantize8=True), procedural_image(tex_size // 2, 1, quantize8=True)
+    ground = b.diffuse(_white(), reflectance_tex=b.image_texture(procedural_image(2 * tex_size, 3, quantize8=True), filter="bilinear", su=8.0, sv=8.0))
     skin = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="ewa", su=4.0, sv=2.0, max_anisotropy=8.0))
     bumpy = b.diffuse(_white(), reflectance_tex=b.image_texture(rgb_img, filter="trilinear", su=2.0, sv=2.0),
                       displacement_tex=b.image_texture(mono_img, filter="bilinear", su=12.0, sv=6.0, scale=0.02))

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("workload"); ap.add_argument("csv"); ap.add_argument("--log", default="")
     ap.add_argument("--desc", default="")
+    ap.add_argument("--rays-depth0", type=int, default=0, help="rays of the first closest-hit launch (= pixels x spp of the capture)")
     args = ap.parse_args()
     rows = [r for r in csv.reader(open(args.csv)) if len(r) > 10]
     h = rows[0]; ki, mi, vi, ii = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
@@ -61,7 +62,7 @@ def main():
            "lanes_per_inst_by_launch": [d["smsp__thread_inst_executed.sum"] / d["smsp__inst_executed.sum"] for d in closest],
            "shadow_rays": n_shadow, "warp_inst_per_shadow_ray": (swi / n_shadow) if n_shadow else None,
            "lanes_per_inst_shadow": (sti / swi) if swi else None,
-           "rays_depth0_launch": None,
+           "rays_depth0_launch": args.rays_depth0 or None,
            "dram_bytes_depth0_launch": closest[0].get("dram__bytes_read.sum", 0.0) + closest[0].get("dram__bytes_write.sum", 0.0)}
     out = os.path.join(ROOT, "profiles", "r02_issue.json")
     try:
