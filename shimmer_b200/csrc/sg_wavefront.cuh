@@ -816,7 +816,11 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                     }
                 } else {
                 // ---- sample_ld :897-963 ----
+#ifdef SG_EXP_SKIP_NEE      /* timing experiment only (tools/r02_exp_split.sh): wrong images */
+                if (false) {
+#else
                 if (bflags & (BX_DIFFUSE | BX_GLOSSY)) {
+#endif
                     LightCtx ctx; ctx.pi = s.pi; ctx.n = s.n; ctx.ns = s.sn;
                     const bool refl = bflags & BX_REFLECTION, trans = bflags & BX_TRANSMISSION;
                     if (refl && !trans) ctx.pi = p3fi_exact(offset_ray_origin(s.pi, s.n, wo_si));
@@ -860,7 +864,11 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
                 BSDFSample bs; bool prop = false;
                 bsdf.layer_seed = layer_seed(rng, 3);
+#ifdef SG_EXP_SKIP_SAMPLE   /* timing experiment only: every path ends after its first vertex */
+                alive = false;
+#else
                 alive = bsdf.sample_f(wo, u, u2, bs, prop);
+#endif
                 if (alive) {
                     beta = beta * (bs.f * absdot3(bs.wi, s.sn) / bs.pdf);
                     if (prop) { bsdf.layer_seed = layer_seed(rng, 4); p_b = bsdf.pdf(wo, bs.wi); }      // pdf_is_proportional :860-865
@@ -965,7 +973,7 @@ static __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DSc
 static __global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
     unsigned long long c = 0, s = 0;
     for (int d = 0; d < n_depths; ++d) { c += counters[d * C_STRIDE + C_NRAY]; s += counters[d * C_STRIDE + C_NSHADOW]; }
-    stats->closest += c; stats->shadow += s;
+    atomicAdd(&stats->closest, c); atomicAdd(&stats->shadow, s);              // two wavefronts (streams) may finish a batch at the same time
 }
 
 // ---- free-standing ray batches: the ray-cast parity / roofline entry (sg_trace) ----

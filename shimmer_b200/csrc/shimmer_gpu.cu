@@ -25,7 +25,9 @@ namespace {
 thread_local std::string g_err;
 // One entry per GPU this process drives.  g_dev[0] is the primary device: every entry point that is not a multi-GPU
 // render runs there.  A scene replica remembers the index of its device.
-struct Device { int id = -1; cudaStream_t stream = nullptr; int num_sms = 0; ncclComm_t comm = nullptr; };
+constexpr int kMaxWavefronts = 2;   // 3 and 4 in flight measured no better than 2 (gpurun_out/r02_overlap2.log)
+// aux[0]: the second wavefront of render_on; aux[1], aux[2]: the shadow-ray side streams of wavefront 0 and 1
+struct Device { int id = -1; cudaStream_t stream = nullptr; cudaStream_t aux[3] = {}; int num_sms = 0; ncclComm_t comm = nullptr; };
 std::vector<Device> g_dev;
 #define g_device (g_dev.empty() ? -1 : g_dev[0].id)
 #define g_stream (g_dev[0].stream)
@@ -115,7 +117,7 @@ struct SgScene {
     TraceScene ts{};
     size_t smem_closest = 0, smem_shadow = 0;
     std::vector<void*> owned;
-    Workspace ws;
+    Workspace ws[2];                 // wavefronts in flight (render_on deals batches round-robin to this many streams); kMaxWavefronts
     DevStats* d_stats = nullptr;
     unsigned long long* d_cursor = nullptr;
     bool kinds_present[8] = {false, false, false, false, false, false, false, false};
@@ -137,8 +139,8 @@ template <class T> int ws_alloc(Workspace& w, T** p, size_t n) {
     *p = (T*)q;
     return SG_OK;
 }
-int ensure_workspace(SgScene* s, uint32_t capacity, int max_depth) {
-    Workspace& w = s->ws;
+int ensure_workspace(SgScene* s, int which, uint32_t capacity, int max_depth) {
+    Workspace& w = s->ws[which];
     if (w.capacity >= capacity && w.max_depth >= max_depth) return SG_OK;
     w.release();
     w.st = PathState{};
@@ -196,6 +198,7 @@ static int device_open(int device, Device& D) {
     if (prop.major < 10) return fail(SG_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; found ") + prop.name);
     D.id = device; D.num_sms = prop.multiProcessorCount; D.comm = nullptr;
     CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+    for (cudaStream_t& a : D.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     return SG_OK;
 }
 static void devices_close() {
@@ -203,6 +206,7 @@ static void devices_close() {
         if (D.id >= 0) cudaSetDevice(D.id);
         if (D.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D.comm);
         if (D.stream) cudaStreamDestroy(D.stream);
+        for (cudaStream_t a : D.aux) if (a) cudaStreamDestroy(a);
     }
     g_dev.clear();
 }
@@ -745,7 +749,7 @@ int sg_scene_destroy(SgScene* s) {
     s->peers.clear();
     DeviceGuard guard__(s->dev);
     cudaDeviceSynchronize();
-    s->ws.release();
+    for (Workspace& w : s->ws) w.release();
     for (void* p : s->owned) cudaFree(p);
     if (s->d_film) cudaFree(s->d_film);
     if (s->h_film) cudaFreeHost(s->h_film);
@@ -771,10 +775,21 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     uint64_t cap64 = rp->max_paths_in_flight > 0 ? (uint64_t)rp->max_paths_in_flight : (1ull << 26);   // 64 Mi paths = 18.5 GB of 180 GB
     if (cap64 > total) cap64 = total;
     if (cap64 == 0) cap64 = 1;
+    // Several wavefronts in flight (default 2): batches are dealt round-robin to the caller's stream and auxiliary ones, each with
+    // its own path state and queues.  The persistent traversal kernels and the grid-stride shade kernels of one batch leave SMs
+    // idle in their tails and in the small late-depth launches; the other batches' kernels fill them (the hardware schedules CTAs
+    // of all streams).  Film and statistics updates are atomic, so the batches commute.  A one-batch job below 32 Mi paths is cut
+    // into equal parts (C1: +5 %); a bigger single batch stays whole (C2 at 64 Mi paths: halves lose 2 % -- large wavefronts
+    // amortise their own tails).  Per-kernel timing / visit counting keep one stream (their events bracket one kernel at a time).
+    static const int overlap_env = [] { const char* v = std::getenv("SG_OVERLAP"); return v ? std::atoi(v) : 2; }();
+    const bool time_or_count = (rp->flags & (SG_RENDER_TIME_KERNELS | SG_RENDER_COUNT_VISITS)) != 0;
+    int n_inflight = (overlap_env >= 2 && !time_or_count && total >= (1ull << 21)) ? std::min(overlap_env, kMaxWavefronts) : 1;
+    if (n_inflight > 1 && cap64 >= total) {
+        if (total < (1ull << 25)) cap64 = (total + n_inflight - 1) / n_inflight; else n_inflight = 1;
+    }
     const uint32_t capacity = (uint32_t)cap64;
-    int rc = ensure_workspace(s, capacity, rp->max_depth);
-    if (rc != SG_OK) return rc;
-    Workspace& w = s->ws;
+    int rc = SG_OK;
+    for (int i = 0; i < n_inflight; ++i) if ((rc = ensure_workspace(s, i, capacity, rp->max_depth)) != SG_OK) return rc;
     RenderConst k;
     k.seed = rp->seed; k.sample_begin = rp->sample_begin; k.spp = rp->samples_per_pixel; k.max_depth = rp->max_depth;
     k.regularize = rp->regularize; k.option_flags = rp->option_flags;
@@ -800,9 +815,27 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     std::vector<cudaEvent_t> tev, sev;      // event pairs around closest-hit / any-hit launches
     auto mark = [&](std::vector<cudaEvent_t>& v) -> int { cudaEvent_t a = bag.make(); if (!a) return fail(SG_ERR_CUDA, "cudaEventCreate failed"); CU(cudaEventRecord(a, stream)); v.push_back(a); return SG_OK; };
     uint64_t launches = 0, closest_launches = 0, shadow_launches = 0;
+    // Inside a batch the any-hit (shadow) traversal of depth d runs on a side stream, concurrently with the closest-hit
+    // traversal of depth d + 1: they touch disjoint state (shadow: sh_*, L; closest: ray_*, hit_*, the queues of d + 1) and
+    // each is a persistent kernel whose tail leaves SMs idle.  The shade kernels of d + 1 (which read L) wait for shadow(d).
+    static const int side_env = [] { const char* v = std::getenv("SG_SHADOW_SIDE_STREAM"); return v ? std::atoi(v) : 1; }();
+    // Only for one-wavefront jobs (C2: +1.4 %); with two wavefronts in flight the other batch already fills those tails and the
+    // side stream measured neutral to -1 % (gpurun_out/r02_side.log).
+    const bool side_stream = side_env != 0 && !time_or_count && n_inflight == 1;
+    cudaStream_t lanes[kMaxWavefronts] = {stream, g_dev[s->dev].aux[0]};
+    cudaStream_t sides[kMaxWavefronts] = {g_dev[s->dev].aux[1], g_dev[s->dev].aux[2]};
+    cudaEvent_t ev_shaded[kMaxWavefronts], ev_shadowed[kMaxWavefronts];
+    for (int i = 0; i < kMaxWavefronts; ++i) { ev_shaded[i] = bag.make(); ev_shadowed[i] = bag.make(); if (!ev_shaded[i] || !ev_shadowed[i]) return fail(SG_ERR_CUDA, "cudaEventCreate failed"); }
     CU(cudaEventRecord(ev0, stream));
-    for (uint64_t first = 0; first < total; first += capacity) {
+    for (int i = 1; i < n_inflight; ++i) CU(cudaStreamWaitEvent(lanes[i], ev0, 0));   // the auxiliary wavefront starts after the caller's prior work too
+    uint64_t batch = 0;
+    for (uint64_t first = 0; first < total; first += capacity, ++batch) {
         const uint32_t cnt = (uint32_t)((total - first) < capacity ? (total - first) : capacity);
+        const int lane = (int)(batch % (uint64_t)n_inflight);
+        cudaStream_t stream = lanes[lane];                                     // shadows the caller's stream inside the batch
+        cudaStream_t side = side_stream ? sides[lane] : stream;
+        Workspace& w = s->ws[lane];
+        bool shadow_pending = false;
         CU(cudaMemsetAsync(w.q.counters, 0, (size_t)(rp->max_depth + 3) * C_STRIDE * sizeof(uint32_t), stream));
         k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
         for (int depth = 0; depth < n_depths; ++depth) {
@@ -810,6 +843,7 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
             if (time_trace && (rc = mark(tev)) != SG_OK) return rc;
+            if (shadow_pending) { CU(cudaStreamWaitEvent(stream, ev_shadowed[lane], 0)); shadow_pending = false; }   // L of depth - 1 is final
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             for (int kind = 0; kind <= SG_MATERIAL_COATED_CONDUCTOR; ++kind) {
@@ -819,13 +853,22 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
                 if (time_trace && (rc = mark(sev)) != SG_OK) return rc;
-                kern_shadow<<<grid_shadow, kTraceThreads, sms, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
+                if (side != stream) { CU(cudaEventRecord(ev_shaded[lane], stream)); CU(cudaStreamWaitEvent(side, ev_shaded[lane], 0)); }
+                kern_shadow<<<grid_shadow, kTraceThreads, sms, side>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
                 ++launches; ++shadow_launches;
+                if (side != stream) { CU(cudaEventRecord(ev_shadowed[lane], side)); shadow_pending = true; }
                 if (time_trace && (rc = mark(sev)) != SG_OK) return rc;
             }
         }
+        if (shadow_pending) CU(cudaStreamWaitEvent(stream, ev_shadowed[lane], 0));
         k_film<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, cnt, (double*)d_film); ++launches;
         k_accum_stats<<<1, 1, 0, stream>>>(w.q.counters, n_depths, s->d_stats); ++launches;
+    }
+    for (int i = 1; i < n_inflight; ++i) {                                     // join: the caller's stream continues after every wavefront
+        cudaEvent_t e = bag.make();
+        if (!e) return fail(SG_ERR_CUDA, "cudaEventCreate failed");
+        CU(cudaEventRecord(e, lanes[i]));
+        CU(cudaStreamWaitEvent(stream, e, 0));
     }
     CU(cudaEventRecord(ev1, stream));
     const bool do_reduce = reduce && g_proc_comm && g_proc_nranks > 1;
