@@ -125,6 +125,8 @@ struct SgScene {
     bool general_lights = false;    // sphere / patch / point / image-infinite lights: k_shade<KIND, true, true, true>
     bool has_mix = false;           // Mix materials: k_resolve_mix + the mat_override path-state array
     bool tex_path = false;          // image textures, a non-zero constant displacement or non-triangle emitters: k_shade<KIND, true>
+    bool sort_by_material = false;  // tex_path and some kind has more than one material: shade queues are re-ordered by material id
+    int materials_of_kind[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
     uint64_t n_pixels() const { return (uint64_t)(d.film.pixel_bounds[2] - d.film.pixel_bounds[0]) * (uint64_t)(d.film.pixel_bounds[3] - d.film.pixel_bounds[1]); }
@@ -158,6 +160,11 @@ int ensure_workspace(SgScene* s, int which, uint32_t capacity, int max_depth) {
     for (int k = 0; k < Q_NKINDS; ++k) if ((rc = ws_alloc(w, &w.q.shade[k], n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.shadow, n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.counters, (size_t)(max_depth + 3) * C_STRIDE)) != SG_OK) return rc;
+    w.q.sorted = nullptr; w.q.sort_hist = nullptr;
+    if (s->sort_by_material) {                  // textured scenes with several materials of a kind: see k_sort_queue_* (sg_wavefront.cuh)
+        if ((rc = ws_alloc(w, &w.q.sorted, n)) != SG_OK) return rc;
+        if ((rc = ws_alloc(w, &w.q.sort_hist, (size_t)128)) != SG_OK) return rc;
+    }
     w.capacity = capacity; w.max_depth = max_depth;
     return SG_OK;
 }
@@ -695,6 +702,11 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
     s->tex_path = desc->n_textures > 0;
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if ((desc->materials[i].flags & SG_MAT_HAS_DISPLACEMENT) && desc->materials[i].displacement != 0.0f) s->tex_path = true;
+    for (uint32_t i = 0; i < desc->n_materials; ++i) if (desc->materials[i].kind >= 0 && desc->materials[i].kind < 8) s->materials_of_kind[desc->materials[i].kind]++;
+    {
+        static const int sort_env = [] { const char* v = std::getenv("SG_SORT_MATERIALS"); return v ? std::atoi(v) : 1; }();
+        for (int kd = 0; kd < 8; ++kd) if (s->tex_path && sort_env && s->materials_of_kind[kd] > 1) s->sort_by_material = true;
+    }
     for (uint32_t i = 0; i < desc->n_lights; ++i)               // lights only the general shade kernels handle (k_shade<.., LG = true>)
         if (desc->lights[i].kind != SG_LIGHT_DIFFUSE_AREA && desc->lights[i].kind != SG_LIGHT_UNIFORM_INFINITE) s->general_lights = true;
     d.n_nodes = desc->n_nodes; d.n_prims = desc->n_primitives; d.n_lights = desc->n_lights; d.n_materials = desc->n_materials;
@@ -848,7 +860,15 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             for (int kind = 0; kind <= SG_MATERIAL_COATED_CONDUCTOR; ++kind) {
                 if (!s->kinds_present[kind]) continue;
-                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth);
+                Queues qs = w.q;
+                if (w.q.sorted && (s->materials_of_kind[kind] > 1 || s->has_mix)) {     // re-order this kind's queue by material id
+                    CU(cudaMemsetAsync(w.q.sort_hist, 0, 128 * sizeof(uint32_t), stream));
+                    k_sort_queue_count<<<num_sms * 4, 256, 0, stream>>>(s->d, w.st, w.q, depth, 1 + kind);
+                    k_sort_queue_scatter<<<num_sms * 4, 256, 0, stream>>>(s->d, w.st, w.q, depth, 1 + kind);
+                    launches += 2;
+                    qs.shade[1 + kind] = w.q.sorted;
+                }
+                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
                 ++launches;
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
