@@ -77,6 +77,7 @@ static constexpr int kSpillLevels = 48;
 struct Stack {
     uint32_t* s_ref; float* s_t; int stride; int levels;
     uint2* spill;
+    float* s_save;          // INST kernels: 10 words per thread (stride apart) holding the render-space ray while the lane is inside an instance
     template <bool ANY> SGD void put(int sp, uint32_t ref, float t) const {
         if (sp < levels) { s_ref[sp * stride] = ref; if (!ANY) s_t[sp * stride] = t; }
         else spill[sp - levels] = make_uint2(ref, __float_as_uint(t));
@@ -153,9 +154,27 @@ SGD void instance_ray(const DInstance& I, bool inverse, float3& o, float3& d, fl
 // TransformedPrimitive::intersect / intersect_predicate (primitive.rs:155-175): move the lane into the instance's space
 // and start on the object's BvhAggregate.  The closest-hit path uses the inverse transform; the predicate uses the FORWARD
 // one in the reference (unless SG_SCENE_FIX_INSTANCING).
+// The render-space ray of a lane that enters an instance is parked in shared memory and restored on the way out: re-deriving it
+// (queue -> path -> ray_o / ray_d: three dependent global loads, then six IEEE divides for 1 / d and the shear constants) was a
+// large part of the instanced kernels' instance-transition cost, paid at leaf-phase lane counts.  Same values, so same results.
+SGD void lane_save_ray(const Lane& L, const Stack& S) {
+    float* p = S.s_save; const int st = S.stride;
+    p[0] = L.o.x; p[st] = L.o.y; p[2 * st] = L.o.z; p[3 * st] = L.inv_dir.x; p[4 * st] = L.inv_dir.y; p[5 * st] = L.inv_dir.z;
+    p[6 * st] = L.rp.sx; p[7 * st] = L.rp.sy; p[8 * st] = L.rp.sz; p[9 * st] = __int_as_float(L.rp.kz);
+}
+SGD void lane_restore_ray(Lane& L, const Stack& S) {
+    const float* p = S.s_save; const int st = S.stride;
+    L.o = f3(p[0], p[st], p[2 * st]); L.inv_dir = f3(p[3 * st], p[4 * st], p[5 * st]);
+    L.rp.sx = p[6 * st]; L.rp.sy = p[7 * st]; L.rp.sz = p[8 * st]; L.rp.kz = __float_as_int(p[9 * st]);
+    L.rp.kx = L.rp.kz + 1; if (L.rp.kx == 3) L.rp.kx = 0;
+    L.rp.ky = L.rp.kx + 1; if (L.rp.ky == 3) L.rp.ky = 0;
+    L.nx = L.inv_dir.x < 0.0f; L.ny = L.inv_dir.y < 0.0f; L.nz = L.inv_dir.z < 0.0f;
+}
+
 template <bool ANY, bool COUNT>
-SGD void lane_enter_instance(const TraceScene& ts, Lane& L, uint32_t inst_id, float3 o, float3 d, uint32_t& n_nodes) {
+SGD void lane_enter_instance(const TraceScene& ts, Lane& L, const Stack& S, uint32_t inst_id, float3 o, float3 d, uint32_t& n_nodes) {
     const DInstance& I = ts.instances[inst_id];
+    lane_save_ray(L, S);
     float tm = L.t_max;
     instance_ray(I, !ANY || (ts.scene_flags & SG_SCENE_FIX_INSTANCING) != 0, o, d, tm);
     L.t_saved = L.t_max; L.t_max = tm; L.inst = (int)inst_id; L.sp_base = L.sp; L.inst_hit = false;
@@ -197,9 +216,7 @@ SGD uint32_t lane_pop(Lane& L, const Stack& S, uint32_t& n_nodes, IO& io, IdxT i
                 if (t < L.t_max) return ref;
             }
             if (L.inst < 0) return kEmptyRef;
-            float3 o, d; float tm;
-            io.load(idx, o, d, tm);                                 // back to the render-space ray
-            lane_set_ray(L, o, d);
+            lane_restore_ray(L, S);                                 // back to the render-space ray
             if (!L.inst_hit) L.t_max = L.t_saved;                   // else t_max = si.t_hit of the instanced hit (primitive.rs:162)
             L.inst = -1; L.sp_base = 0;
         }
@@ -255,7 +272,7 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
             }
             float3 o, d; float tm;
             io.load(idx, o, d, tm);
-            lane_enter_instance<ANY, COUNT>(ts, L, __float_as_uint(v1.w), o, d, n_nodes);
+            lane_enter_instance<ANY, COUNT>(ts, L, S, __float_as_uint(v1.w), o, d, n_nodes);
             if (L.cur == kEmptyRef) L.cur = lane_pop<ANY, COUNT, INST>(L, S, n_nodes, io, idx);
             return;
         }

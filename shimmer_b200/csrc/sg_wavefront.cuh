@@ -192,6 +192,8 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
     S.s_ref = s_mem + threadIdx.x;
     S.s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x;
+    // INST kernels: the parked render-space ray (lane_save_ray) sits behind the stack levels (closest-hit: refs + entry distances, any-hit: refs)
+    S.s_save = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x * (ANY ? 1 : 2)) + threadIdx.x;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     bool has_ray = false, dead = false, finished = false;
     CursorT idx = 0;

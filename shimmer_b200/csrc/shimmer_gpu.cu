@@ -641,6 +641,10 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
         s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
     }
     s->instanced = desc->n_instances > 0 || desc->n_spheres > 0 || !pv.empty();      // anything that is not a triangle -> the general kernels
+    if (s->instanced) {                          // + the parked render-space ray of a lane inside an instance (sg_trace2.cuh lane_save_ray)
+        s->smem_closest += (size_t)kTraceThreads * 10 * sizeof(float);
+        s->smem_shadow += (size_t)kTraceThreads * 10 * sizeof(float);
+    }
     {
         float4* d_pv = nullptr;
         if ((rc = upload(pv.data(), pv.size(), &d_pv, s->owned)) != SG_OK) return bail(rc);
