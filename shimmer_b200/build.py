@@ -21,9 +21,9 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-# translation units of libshimmer_gpu.so: the C ABI + traversal kernels, and nine groups of shade-kernel instantiations
+# translation units of libshimmer_gpu.so: the C ABI + traversal kernels, and ten groups of shade-kernel instantiations
 # (csrc/sg_kernels.h).  They are compiled in parallel (one nvcc process each) and linked into one shared library.
-GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade_tu.cu", ["-DSG_TU=%d" % i]) for i in range(1, 10)]
+GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade_tu.cu", ["-DSG_TU=%d" % i]) for i in range(1, 11)]
 
 
 def build_gpu(force=False, verbose=False):

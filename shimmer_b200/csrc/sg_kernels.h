@@ -18,6 +18,8 @@ ShadeKernel shade_kernel_other_b(int kind);     //                              
 ShadeKernel shade_kernel_force_diffuse_a(int kind);   // k_shade<KIND, true, true, true, FD = true>: Options::force_diffuse (path integrator)  (SG_TU 8)
 ShadeKernel shade_kernel_force_diffuse_b(int kind);   //                                                                                  (SG_TU 9)
 ShadeKernel resolve_mix_kernel(bool tex);       // k_resolve_mix<TEX>                                                          (SG_TU 2)
+ShadeKernel shade_kernel_stage1(int kind);      // k_shade<Diffuse, TEX, .., STAGE 1>: get_bsdf only -> BSDF record; nullptr for other kinds (SG_TU 10)
+ShadeKernel shade_kernel_stage2(int kind, bool general_lights);   // k_shade<Diffuse, no TEX, .., STAGE 2>: the rest, from the record     (SG_TU 10)
 
 inline bool shade_kind_in_group_b(int kind) { return kind == SG_MATERIAL_COATED_DIFFUSE || kind == SG_MATERIAL_COATED_CONDUCTOR; }
 inline ShadeKernel shade_kernel(int kind, bool textured, bool general_lights, bool path_integrator, bool force_diffuse = false) {

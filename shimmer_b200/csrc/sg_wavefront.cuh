@@ -43,6 +43,8 @@ struct PathState {
     float4* aux0;       // rx_origin.xyz, rx_direction.x
     float4* aux1;       // rx_direction.yz, ry_origin.xy
     float4* aux2;       // ry_origin.z, ry_direction.xyz
+    // staged shading of textured scenes (k_shade STAGE 1 -> 2): the BSDF record of the current hit, allocated only then
+    float4* rec[6];     // pi.lo.xyz pi.hi.x | pi.hi.yz n.xy | n.z sn.xyz | fx.xyz wo_si.x | wo_si.yz - - | reflectance
 };
 static constexpr int kPathBytes = 16 * 16 + 4 + 4 + 4 + 8;   // per-path HBM footprint (276 B; +48 B with image textures)
 static constexpr uint32_t kFlagSpecular = 256u, kFlagNonSpecular = 512u, kFlagAux = 1024u;
@@ -596,7 +598,13 @@ static __global__ void __launch_bounds__(256) k_sort_queue_scatter(const __grid_
 // FD = Options::force_diffuse (interaction.rs:258-273): a separate set of instantiations (general superset only), so the regular
 // kernels carry none of it.
 template <bool FD, class A, class B> SGD auto& pick_bsdf(A& a, B& b) { if constexpr (FD) return b; else return a; }
-template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false>
+// STAGE (textured scenes, Diffuse materials, path integrator): 0 = the whole body in one kernel; 1 = get_bsdf only -- surface,
+// differentials, bump / normal map, texture lookups -- leaving a 96-byte BSDF record per hit (PathState::rec); 2 = everything
+// else -- emission + MIS, sample_ld, BSDF sampling, Russian roulette, the queue appends -- from that record, compiled WITHOUT any
+// texture code (TEX = false).  The fused textured kernel is 17 k instructions and instruction-fetch bound (ncu on C4:
+// `no_instruction` the top stall even after the material sort, issue-active 21 %); the two stages each fit the instruction
+// caches far better.  Same arithmetic in the same order per path, so the films are bit-identical to STAGE 0's.
+template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false, int STAGE = 0>
 __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
@@ -660,22 +668,32 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
             int pdepth = fl & 0xff; bool specular_bounce = (fl >> 8) & 1u; bool any_non_specular = (fl >> 9) & 1u;
             Wavelengths lam; lam.lambda = st.lambda[path]; lam.pdf = st.lpdf[path];
             // depth 0 (warp-uniform kernel argument): L = 0, beta = 1, p_b = eta_scale = 1 are not in memory yet (see k_generate)
-            Spec L = depth == 0 ? spec1(0.0f) : st.L[path]; Spec beta = depth == 0 ? spec1(1.0f) : st.beta[path];
-            float2 pbe = depth == 0 ? make_float2(1.0f, 1.0f) : st.pb_eta[path];
+            Spec L = (STAGE == 1 || depth == 0) ? spec1(0.0f) : st.L[path]; Spec beta = (STAGE == 1 || depth == 0) ? spec1(1.0f) : st.beta[path];
+            float2 pbe = (STAGE == 1 || depth == 0) ? make_float2(1.0f, 1.0f) : st.pb_eta[path];
             float p_b = pbe.x, eta_scale = pbe.y;
 
             SurfTex sx;
             Surf s;
             float3 wo_si = wo;                                   // SurfaceInteraction::wo (what sample_ld reads, integrator.rs:905-917)
+            BSDF<KIND> mb;
+            if constexpr (STAGE == 2) {                          // the record stage 1 left: interaction + shading frame + BSDF parameters
+                const float4 r0 = st.rec[0][path], r1 = st.rec[1][path], r2 = st.rec[2][path], r3 = st.rec[3][path], r4 = st.rec[4][path];
+                s.pi.lo = f3(r0.x, r0.y, r0.z); s.pi.hi = f3(r0.w, r1.x, r1.y);
+                s.n = f3(r1.z, r1.w, r2.x); s.sn = f3(r2.y, r2.z, r2.w);
+                s.sdpdu = s.sdpdv = f3(0.0f, 0.0f, 0.0f);
+                mb.fx = f3(r3.x, r3.y, r3.z); wo_si = f3(r3.w, r4.x, r4.y);
+                mb.r = st.rec[5][path];
+            } else {
             // scenes with instances / spheres / patches resolve the hit out of line, so that triangle-only scenes (hit_inst ==
             // nullptr) keep a small kernel: the shade kernels are sensitive to instruction-cache footprint
             if (st.hit_inst == nullptr) s = make_surface<TEX>(sc, geo, hb.x, hb.y, hb.z, &sx);
             else s = surface_general<TEX>(sc, geo, hb, rd, st.hit_inst[path], &sx, wo_si);
+            }
 
             const bool simple = !PATH && rc.integrator == SG_INTEGRATOR_SIMPLE_PATH, walk = !PATH && !simple;
             const bool sample_lights = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_LIGHTS) != 0, sample_bsdf_dir = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_BSDF) != 0;
             // emission + MIS against light sampling, :798-813
-            if (light_id >= 0) {
+            if (STAGE != 1 && light_id >= 0) {
                 const SgLight lt = sc.lights[light_id];
                 Spec le = light_l(sc, lt, s.n, wo, lam);
                 if (!spec_zero(le)) {
@@ -695,9 +713,14 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
             }
 
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
+            AuxRays aux; aux.has = false;
+            if constexpr (STAGE == 2) {                          // built by stage 1; a DiffuseBxDF has no other parameters
+                static_assert(STAGE != 2 || KIND == SG_MATERIAL_DIFFUSE, "staged shading carries the Diffuse BSDF record only");
+                mb.k = spec1(0.0f); mb.eta = 1.0f; mb.mf = TR::make(0.0f, 0.0f);
+                mb.fz = s.sn; mb.fy = cross3(mb.fz, mb.fx);
+            } else {
             if (geo.kind == SG_MATERIAL_MIX) material_id = st.mat_override[path];                   // resolved by k_resolve_mix (interaction.rs:206-221)
             const SgMaterial mat = sc.materials[material_id];
-            AuxRays aux; aux.has = false;
             if (TEX) {
                 if (sc.n_textures > 0) {
                     if (fl & kFlagAux) aux = aux_load(st, path);
@@ -725,7 +748,6 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 resolve_material_textures(sc, material_id, tc, lam, mv);
                 p_ur = mv.ur; p_vr = mv.vr; p_thickness = mv.thickness; p_g = mv.g; p_ur2 = mv.ur2; p_vr2 = mv.vr2; ov_mask = mv.mask;
             }
-            BSDF<KIND> mb;
             mb.r = spec1(0.0f); mb.k = spec1(0.0f); mb.eta = 1.0f; mb.mf = TR::make(0.0f, 0.0f);
             if (KIND == SG_MATERIAL_DIFFUSE) {
                 mb.r = spec_clamp(TEX && mat.tex_reflectance >= 0 ? eval_spectrum_texture(sc, mat.tex_reflectance, tc, lam)
@@ -783,6 +805,15 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 mb.mf = TR::make(ur, vr);
             }
             mb.fx = normalize3(s.sdpdu); mb.fz = s.sn; mb.fy = cross3(mb.fz, mb.fx);
+            }   // STAGE != 2
+            if constexpr (STAGE == 1) {                          // hand the hit over to stage 2
+                st.rec[0][path] = make_float4(s.pi.lo.x, s.pi.lo.y, s.pi.lo.z, s.pi.hi.x);
+                st.rec[1][path] = make_float4(s.pi.hi.y, s.pi.hi.z, s.n.x, s.n.y);
+                st.rec[2][path] = make_float4(s.n.z, s.sn.x, s.sn.y, s.sn.z);
+                st.rec[3][path] = make_float4(mb.fx.x, mb.fx.y, mb.fx.z, wo_si.x);
+                st.rec[4][path] = make_float4(wo_si.y, wo_si.z, 0.0f, 0.0f);
+                st.rec[5][path] = mb.r;
+            } else {
             // Options::force_diffuse: DiffuseBxDF(rho_hd(si.wo, [get_1d], [get_2d])) on the same frame (interaction.rs:258-273, bxdf.rs:49-71:
             // one BxDF-level sample, no BSDF-level rejection tests, kept when pdf > 0); sampled BEFORE any regularisation, as there.
             BSDF<SG_MATERIAL_DIFFUSE> db;
@@ -974,6 +1005,7 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
             if ((KIND == SG_MATERIAL_DIELECTRIC || KIND == SG_MATERIAL_COATED_DIFFUSE || KIND == SG_MATERIAL_THIN_DIELECTRIC || KIND == SG_MATERIAL_COATED_CONDUCTOR) &&
                 (PATH || (int)(fl & 0xffu) != rc.max_depth)) st.lpdf[path] = lam.pdf;
             want_next = alive;
+            }   // STAGE != 1
         }
         __syncwarp();
         {   // warp-aggregated queue appends

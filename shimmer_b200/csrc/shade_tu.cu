@@ -1,4 +1,4 @@
-// Shade-kernel instantiations, one group per translation unit (see sg_kernels.h): nvcc -DSG_TU=1..9 -c shade_tu.cu
+// Shade-kernel instantiations, one group per translation unit (see sg_kernels.h): nvcc -DSG_TU=1..10 -c shade_tu.cu
 #include "sg_kernels.h"
 
 namespace sg {
@@ -45,8 +45,16 @@ ShadeKernel shade_kernel_force_diffuse_b(int kind) {
     }
     return nullptr;
 }
+#elif SG_TU == 10
+// staged shading of textured scenes (k_shade STAGE 1 / 2; Diffuse materials, path integrator): stage 1 carries the texture code
+// (LG does not matter there: no light code), stage 2 is compiled without any (TEX = false) for both light-kind variants
+ShadeKernel shade_kernel_stage1(int kind) { return kind == SG_MATERIAL_DIFFUSE ? k_shade<SG_MATERIAL_DIFFUSE, true, true, false, false, 1> : nullptr; }
+ShadeKernel shade_kernel_stage2(int kind, bool general_lights) {
+    if (kind != SG_MATERIAL_DIFFUSE) return nullptr;
+    return general_lights ? k_shade<SG_MATERIAL_DIFFUSE, false, true, true, false, 2> : k_shade<SG_MATERIAL_DIFFUSE, false, true, false, false, 2>;
+}
 #else
-#error "compile with -DSG_TU=1..9"
+#error "compile with -DSG_TU=1..10"
 #endif
 
 }  // namespace sg

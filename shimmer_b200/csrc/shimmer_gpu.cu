@@ -126,6 +126,7 @@ struct SgScene {
     bool has_mix = false;           // Mix materials: k_resolve_mix + the mat_override path-state array
     bool tex_path = false;          // image textures, a non-zero constant displacement or non-triangle emitters: k_shade<KIND, true>
     bool sort_by_material = false;  // tex_path and some kind has more than one material: shade queues are re-ordered by material id
+    bool staged_shading = false;    // tex_path with Diffuse materials: k_shade STAGE 1 (get_bsdf -> record) + STAGE 2 (the rest) for the path integrator
     int materials_of_kind[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double* d_film = nullptr; size_t film_pixels = 0;
     SgFilmPixel* h_film = nullptr; size_t h_film_pixels = 0;      // pinned staging for sg_render
@@ -152,6 +153,7 @@ int ensure_workspace(SgScene* s, int which, uint32_t capacity, int max_depth) {
     WS(ray_o); WS(ray_d); WS(hit_b); WS(hit_prim); WS(L); WS(beta); WS(lambda); WS(lpdf); WS(rng_a); WS(rng_b);
     WS(pixel); WS(flags); WS(pb_eta); WS(ctx0); WS(ctx1); WS(ctx2); WS(sh_o); WS(sh_d); WS(sh_L);
     if (s->d.n_textures > 0) { WS(aux0); WS(aux1); WS(aux2); }
+    if (s->staged_shading) for (int r = 0; r < 6; ++r) if ((rc = ws_alloc(w, &w.st.rec[r], n)) != SG_OK) return rc;
     if (s->instanced) { WS(hit_inst); }
     if (s->has_mix) { WS(mat_override); }      // ray differentials only feed image-texture filtering
 #undef WS
@@ -710,6 +712,8 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
     {
         static const int sort_env = [] { const char* v = std::getenv("SG_SORT_MATERIALS"); return v ? std::atoi(v) : 1; }();
         for (int kd = 0; kd < 8; ++kd) if (s->tex_path && sort_env && s->materials_of_kind[kd] > 1) s->sort_by_material = true;
+        static const int stage_env = [] { const char* v = std::getenv("SG_STAGED_SHADING"); return v ? std::atoi(v) : 1; }();
+        s->staged_shading = stage_env != 0 && s->tex_path && s->kinds_present[SG_MATERIAL_DIFFUSE];
     }
     for (uint32_t i = 0; i < desc->n_lights; ++i)               // lights only the general shade kernels handle (k_shade<.., LG = true>)
         if (desc->lights[i].kind != SG_LIGHT_DIFFUSE_AREA && desc->lights[i].kind != SG_LIGHT_UNIFORM_INFINITE) s->general_lights = true;
@@ -871,6 +875,12 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
                     k_sort_queue_scatter<<<num_sms * 4, 256, 0, stream>>>(s->d, w.st, w.q, depth, 1 + kind);
                     launches += 2;
                     qs.shade[1 + kind] = w.q.sorted;
+                }
+                if (s->staged_shading && path_integrator && !force_diffuse && shade_kernel_stage1(kind)) {
+                    shade_kernel_stage1(kind)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                    shade_kernel_stage2(kind, s->general_lights)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                    launches += 2;
+                    continue;
                 }
                 shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
                 ++launches;
