@@ -178,7 +178,12 @@ SGD void lane_enter_instance(const TraceScene& ts, Lane& L, const Stack& S, uint
     float tm = L.t_max;
     instance_ray(I, !ANY || (ts.scene_flags & SG_SCENE_FIX_INSTANCING) != 0, o, d, tm);
     L.t_saved = L.t_max; L.t_max = tm; L.inst = (int)inst_id; L.sp_base = L.sp; L.inst_hit = false;
-    lane_set_ray(L, o, d);
+    // like lane_set_ray, but the watertight test's shear constants (three more IEEE divides) wait until a triangle of the object is
+    // actually tested -- most instance visits end in the object's upper BVH levels: the direction is parked in rp.s*, kz = -1
+    L.o = o;
+    L.inv_dir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    L.nx = L.inv_dir.x < 0.0f; L.ny = L.inv_dir.y < 0.0f; L.nz = L.inv_dir.z < 0.0f;
+    L.rp.kz = -1; L.rp.sx = d.x; L.rp.sy = d.y; L.rp.sz = d.z;
     L.cur = I.root_ref;
     if (I.root_has_bounds) {
         float te;
@@ -297,7 +302,10 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
             const float4 a0 = __ldg(pv), a1 = __ldg(pv + 1), a2 = __ldg(pv + 2), a3 = __ldg(pv + 3);
             hit_prim = intersect_blp(o, d, L.t_max, f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), f3(a3.x, a3.y, a3.z), b0, b1, t);
             b2 = 0.0f;
-        } else hit_prim = intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
+        } else {
+            if constexpr (INST) if (L.rp.kz < 0) L.rp = ray_precompute(f3(L.rp.sx, L.rp.sy, L.rp.sz));    // deferred by lane_enter_instance
+            hit_prim = intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
+        }
         if (hit_prim) {
             L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;
             if constexpr (INST) { L.hit.inst = L.inst; L.inst_hit = true; }

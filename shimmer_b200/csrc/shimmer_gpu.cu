@@ -631,9 +631,14 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
         for (int k = 0; k < 3 && N; ++k) { s->ts.root_bmin[k] = desc->nodes[0].bmin[k]; s->ts.root_bmax[k] = desc->nodes[0].bmax[k]; }
         s->ts.scene_flags = desc->scene_flags;
         auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+        // Scheduling knobs of the vote loop (sg_wavefront.cuh trace_persistent), tuned per kernel family on the B200
+        // (gpurun_out/r02_sweep*.log): triangle-only kernels refill at 14 waiting lanes and run interior steps in bursts of 4;
+        // the instanced kernels meet a leaf event (an instance to enter) every few steps, so bursts only make lanes wait --
+        // burst 1 and refill at 20: C4 276 -> 314 Mpaths/s (burst 2 / 3 / 8: 301 / 289 / 231).
+        const bool general_kernels = desc->n_instances > 0 || desc->n_spheres > 0 || !pv.empty();
         s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 6);
-        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", 14);
-        s->ts.interior_burst = env_int("SG_INTERIOR_BURST", 4);
+        s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", general_kernels ? 20 : 14);
+        s->ts.interior_burst = env_int("SG_INTERIOR_BURST", general_kernels ? 1 : 4);
         s->ts.prefetch = env_int("SG_PREFETCH", 0);
         // shared-memory part of the per-thread stack: 20 levels x 8 B x 128 threads = 20.5 KB -> 9 CTAs (36 warps, the register limit at 56 regs) per SM;
         // deeper levels (if the tree has them) spill to local memory (sg_trace2.cuh Stack)
