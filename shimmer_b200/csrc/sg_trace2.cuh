@@ -62,6 +62,8 @@ struct TraceScene {
     int leaf_threshold;         // warp-vote scheduling knobs (see trace_persistent)
     int refill_threshold;
     int interior_burst;
+    int refill_threshold_d0;    // the same knobs for the CLOSEST-HIT launch of depth 0 (camera rays: a warp's rays are near-identical, so
+    int interior_burst_d0;      //   waiting for most lanes before a refill keeps them in lockstep)
     int prefetch;
     const DInstance* instances; // object instancing (INST kernels only)
     const float4* patch_verts;  // bilinear patches (INST kernels only)

@@ -187,8 +187,10 @@ static __global__ void __launch_bounds__(256) k_generate(const __grid_constant__
 // are run back to back between votes.
 template <bool ANY, bool COUNT, bool INST, class IO, class CursorT>
 SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* cursor, uint32_t* s_mem,
-                          uint32_t& cnt_nodes, uint32_t& cnt_tris) {
+                          uint32_t& cnt_nodes, uint32_t& cnt_tris, bool first_depth = false) {
     const int lane = threadIdx.x & 31;
+    const int refill_threshold = first_depth ? ts.refill_threshold_d0 : ts.refill_threshold;
+    const int interior_burst = first_depth ? ts.interior_burst_d0 : ts.interior_burst;
     uint2 spill[kSpillLevels];
     Stack S;
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
@@ -205,7 +207,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         const uint32_t m_int = __ballot_sync(0xffffffffu, is_int);
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
         const uint32_t m_wait = __ballot_sync(0xffffffffu, finished || (!has_ray && !dead));
-        if ((m_int | m_leaf) == 0u || __popc(m_wait) >= ts.refill_threshold) {
+        if ((m_int | m_leaf) == 0u || __popc(m_wait) >= refill_threshold) {
             // ---- retire finished rays, claim new ones (warp-aggregated) ----
             if constexpr (!INST) L.hit.inst = -1;
             if (__ballot_sync(0xffffffffu, finished)) io.retire(finished, idx, L.hit, lane);
@@ -242,7 +244,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
         // ---- interior phase ----
         if (is_int) {
 #pragma unroll 1
-            for (int k = 0; k < ts.interior_burst; ++k) {
+            for (int k = 0; k < interior_burst; ++k) {
                 lane_step_interior<ANY, COUNT, INST>(ts, L, S, cnt_nodes, io, idx);
                 if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
                 if (L.cur & kLeafBit) break;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
     } else {
         ClosestIO io{sc, st, q, C, q.ray[depth & 1], ts.queue_mask, depth == 0, 0};
         if constexpr (POST) trace_persistent_post<false>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem);
-        else trace_persistent<false, COUNT, INST>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris);
+        else trace_persistent<false, COUNT, INST>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, cnt_nodes, cnt_tris, depth == 0);
     }
     if (COUNT) {
         atomicAdd(&stats->nodes, (unsigned long long)cnt_nodes);

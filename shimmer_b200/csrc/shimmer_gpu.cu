@@ -639,6 +639,12 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
         s->ts.leaf_threshold = env_int("SG_LEAF_THRESHOLD", 6);
         s->ts.refill_threshold = env_int("SG_REFILL_THRESHOLD", general_kernels ? 20 : 14);
         s->ts.interior_burst = env_int("SG_INTERIOR_BURST", general_kernels ? 1 : 4);
+        // Depth-0 closest-hit launch: refill only when ALL 32 lanes are done.  Camera rays of one warp are near-identical (pixel-major
+        // wavefront), so nobody waits long -- and the warp's hits are then appended to the shade queue as one group of 32 consecutive
+        // path slots, which keeps the depth-0 shade kernel's state accesses coalesced: C2 600 -> 629, C4 324 -> 350, C5 1709 -> 1741
+        // Mpaths/s (gpurun_out/r02_sweep5_*.log; both the traversal and the shading time drop).
+        s->ts.refill_threshold_d0 = env_int("SG_REFILL_THRESHOLD_D0", 32);
+        s->ts.interior_burst_d0 = env_int("SG_INTERIOR_BURST_D0", s->ts.interior_burst);
         s->ts.prefetch = env_int("SG_PREFETCH", 0);
         // shared-memory part of the per-thread stack: 20 levels x 8 B x 128 threads = 20.5 KB -> 9 CTAs (36 warps, the register limit at 56 regs) per SM;
         // deeper levels (if the tree has them) spill to local memory (sg_trace2.cuh Stack)
