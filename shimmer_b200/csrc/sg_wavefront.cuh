@@ -71,6 +71,10 @@ struct Queues {
     uint32_t* counters;     // (max_depth + 2) * C_STRIDE
     uint32_t* sorted;       // textured scenes: one shade queue re-ordered by material (k_sort_queue_*), else nullptr
     uint32_t* sort_hist;    // 2 x 64 words: bucket counts, bucket cursors
+    // order-preserving shade queues (k_queue_count / _scan / _scatter): the closest-hit kernel records the destination queue of
+    // ray-queue entry i in ray_kind[i] instead of appending; nullptr = append with atomics at retire time
+    uint8_t*  ray_kind;     // capacity bytes (0xff = none)
+    uint32_t* block_counts; // ceil(capacity / 2048) x Q_NKINDS words: per-block counts, turned into exclusive bases by k_queue_scan
 };
 
 struct RenderConst {
@@ -334,7 +338,7 @@ struct ClosestIO {
         const float4 o4 = st.ray_o[path], d4 = st.ray_d[path];
         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = INFINITY;
     }
-    SGD void retire(bool fin, uint32_t, const HitRec& hit, int lane) {
+    SGD void retire(bool fin, uint32_t idx, const HitRec& hit, int lane) {
         int kind = -1;
         if (fin) {
             st.hit_prim[path] = hit.prim;
@@ -346,6 +350,10 @@ struct ClosestIO {
                 kind = Q_MISS;
                 if (first_depth) st.L[path] = spec1(0.0f);
             }
+        }
+        if (q.ray_kind != nullptr) {                                        // order-preserving queues: just note where entry idx goes
+            if (fin) q.ray_kind[idx] = (uint8_t)kind;
+            return;
         }
 #pragma unroll
         for (int k = 0; k < Q_NKINDS; ++k) {
@@ -519,6 +527,132 @@ __global__ void __launch_bounds__(128) k_resolve_mix(const __grid_constant__ DSc
             }
         }
     }
+}
+
+// ---- order-preserving shade queues ----
+// Persistent warps finish their rays in any order, so appending hits to the shade queues at retire time (ballot + atomicAdd)
+// scatters neighbouring path slots all over the queues -- and the shade kernels then read their 200-350 bytes of path state per
+// hit uncoalesced (at depth >= 1 they wait on those loads: issue-active 27 % against 40 % at depth 0).  Instead the closest-hit
+// kernel writes the destination queue of ray-queue entry i to ray_kind[i], and a three-kernel stream compaction builds every
+// shade queue in RAY-QUEUE ORDER: per-block counts, an exclusive scan over the blocks, an ordered scatter.  Ray-queue order is
+// path-slot order at depth 0 and warp-sized runs of neighbouring slots afterwards (the shade kernels append a warp's survivors
+// together), so a shading warp touches a few contiguous stretches of every state array.  Cost: 5 bytes read per ray per pass.
+static constexpr int kQueueBlock = 2048;          // entries per block: 256 threads x 8 consecutive entries
+SGD void queue_load8(const Queues& q, uint32_t base, uint32_t n, int depth_parity, uint32_t kind8[8], uint32_t path8[8]) {
+    const uint32_t* ray = q.ray[depth_parity];
+    if (base + 8u <= n) {
+        const uint2 kk = *reinterpret_cast<const uint2*>(q.ray_kind + base);
+        const uint4 a = *reinterpret_cast<const uint4*>(ray + base), b = *reinterpret_cast<const uint4*>(ray + base + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { kind8[j] = (kk.x >> (8 * j)) & 0xffu; kind8[4 + j] = (kk.y >> (8 * j)) & 0xffu; }
+        path8[0] = a.x; path8[1] = a.y; path8[2] = a.z; path8[3] = a.w; path8[4] = b.x; path8[5] = b.y; path8[6] = b.z; path8[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = base + j < n;
+            kind8[j] = in ? q.ray_kind[base + j] : 0xffu; path8[j] = in ? ray[base + j] : 0u;
+        }
+    }
+}
+// per-thread counts of the 8 queues, 16 bits each, in two 64-bit words (a block holds at most 2048 entries of one kind)
+SGD void queue_pack_counts(const uint32_t kind8[8], unsigned long long& lo, unsigned long long& hi) {
+    lo = hi = 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t k = kind8[j];
+        if (k < 4u) lo += 1ull << (16 * k); else if (k < 8u) hi += 1ull << (16 * (k - 4u));
+    }
+}
+// count / scatter run on a fixed grid that strides over the 2048-entry blocks of the ray queue (its length n is only known on the
+// device; late depths hold a few per cent of the wavefront, and a capacity-sized grid of early-exit blocks cost 0.13 ms per launch)
+static __global__ void __launch_bounds__(256) k_queue_count(Queues q, int depth) {
+    const uint32_t n = q.counters[depth * C_STRIDE + C_NRAY];
+    __shared__ unsigned long long s_lo[8], s_hi[8];
+    for (uint32_t vb = blockIdx.x; vb * (uint32_t)kQueueBlock < n; vb += gridDim.x) {
+        const uint32_t base = vb * (uint32_t)kQueueBlock + threadIdx.x * 8u;
+        uint32_t kind8[8], path8[8];
+        queue_load8(q, base, n, depth & 1, kind8, path8);
+        unsigned long long lo, hi;
+        queue_pack_counts(kind8, lo, hi);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        if (threadIdx.x < Q_NKINDS) {
+            unsigned long long tl = 0ull, th = 0ull;
+            for (int w = 0; w < 8; ++w) { tl += s_lo[w]; th += s_hi[w]; }
+            const int k = threadIdx.x;
+            q.block_counts[(size_t)vb * Q_NKINDS + k] = (uint32_t)(((k < 4 ? tl : th) >> (16 * (k & 3))) & 0xffffull);
+        }
+        __syncthreads();
+    }
+}
+// exclusive scan of the per-block counts of every queue (one warp per queue kind would do; one 1024-thread block is simpler):
+// block_counts becomes block bases, the totals go to the depth's counters (what the shade kernels read as their work count).
+static __global__ void __launch_bounds__(1024) k_queue_scan(Queues q, int depth, uint32_t queue_mask) {
+    const uint32_t n = q.counters[depth * C_STRIDE + C_NRAY];
+    const uint32_t n_blocks = (n + kQueueBlock - 1) / kQueueBlock;
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (n_blocks + 1023u) / 1024u;                         // consecutive blocks per thread
+    for (int k = 0; k < Q_NKINDS; ++k) {
+        if (!((queue_mask >> k) & 1u)) {                                       // a queue this scene never feeds (TraceScene::queue_mask)
+            if (threadIdx.x == 0) q.counters[depth * C_STRIDE + C_NSHADE + k] = 0u;
+            continue;
+        }
+        const uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, n_blocks);
+        uint32_t sum = 0;
+        for (uint32_t b = b0; b < b1; ++b) sum += q.block_counts[(size_t)b * Q_NKINDS + k];
+        s_part[threadIdx.x] = sum;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {                                   // Hillis-Steele inclusive scan of the 1024 partial sums
+            const uint32_t v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0u;
+            __syncthreads();
+            s_part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        uint32_t run = s_part[threadIdx.x] - sum;                              // exclusive base of this thread's first block
+        for (uint32_t b = b0; b < b1; ++b) { const uint32_t c = q.block_counts[(size_t)b * Q_NKINDS + k]; q.block_counts[(size_t)b * Q_NKINDS + k] = run; run += c; }
+        if (threadIdx.x == 1023) q.counters[depth * C_STRIDE + C_NSHADE + k] = s_part[1023];
+        __syncthreads();
+    }
+}
+static __global__ void __launch_bounds__(256) k_queue_scatter(Queues q, int depth) {
+    const uint32_t n = q.counters[depth * C_STRIDE + C_NRAY];
+    __shared__ unsigned long long s_lo[8], s_hi[8];
+  for (uint32_t vb = blockIdx.x; vb * (uint32_t)kQueueBlock < n; vb += gridDim.x) {
+    const uint32_t base = vb * (uint32_t)kQueueBlock + threadIdx.x * 8u;
+    uint32_t kind8[8], path8[8];
+    queue_load8(q, base, n, depth & 1, kind8, path8);
+    unsigned long long lo, hi;
+    queue_pack_counts(kind8, lo, hi);
+    // exclusive prefix of the packed counts over the block's 256 threads (entry order = thread order)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long ilo = lo, ihi = hi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, ilo, o), b = __shfl_up_sync(0xffffffffu, ihi, o);
+        if (lane >= o) { ilo += a; ihi += b; }
+    }
+    if (lane == 31) { s_lo[warp] = ilo; s_hi[warp] = ihi; }
+    __syncthreads();
+    unsigned long long plo = ilo - lo, phi = ihi - hi;
+    for (int w = 0; w < warp; ++w) { plo += s_lo[w]; phi += s_hi[w]; }
+    uint32_t pos[Q_NKINDS];
+#pragma unroll
+    for (int k = 0; k < Q_NKINDS; ++k)
+        pos[k] = q.block_counts[(size_t)vb * Q_NKINDS + k] + (uint32_t)(((k < 4 ? plo : phi) >> (16 * (k & 3))) & 0xffffull);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t k = kind8[j];
+        if (k < (uint32_t)Q_NKINDS) {
+            uint32_t p = 0;
+#pragma unroll
+            for (int kk = 0; kk < Q_NKINDS; ++kk) if (k == (uint32_t)kk) p = pos[kk]++;
+            q.shade[k][p] = path8[j];
+        }
+    }
+    __syncthreads();                                                        // s_lo / s_hi are reused by the next block of entries
+  }
 }
 
 // ---- shade queue of one material KIND re-ordered by material ID (textured scenes) ----

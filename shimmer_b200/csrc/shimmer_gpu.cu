@@ -162,7 +162,14 @@ int ensure_workspace(SgScene* s, int which, uint32_t capacity, int max_depth) {
     for (int k = 0; k < Q_NKINDS; ++k) if ((rc = ws_alloc(w, &w.q.shade[k], n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.shadow, n)) != SG_OK) return rc;
     if ((rc = ws_alloc(w, &w.q.counters, (size_t)(max_depth + 3) * C_STRIDE)) != SG_OK) return rc;
-    w.q.sorted = nullptr; w.q.sort_hist = nullptr;
+    w.q.sorted = nullptr; w.q.sort_hist = nullptr; w.q.ray_kind = nullptr; w.q.block_counts = nullptr;
+    {   // order-preserving shade queues (sg_wavefront.cuh k_queue_*); the 8 extra bytes let the last thread of a block load whole words
+        static const int ordered_env = [] { const char* v = std::getenv("SG_ORDERED_QUEUES"); return v ? std::atoi(v) : 1; }();
+        if (ordered_env) {
+            if ((rc = ws_alloc(w, &w.q.ray_kind, n + 8)) != SG_OK) return rc;
+            if ((rc = ws_alloc(w, &w.q.block_counts, ((n + kQueueBlock - 1) / kQueueBlock) * (size_t)Q_NKINDS)) != SG_OK) return rc;
+        }
+    }
     if (s->sort_by_material) {                  // textured scenes with several materials of a kind: see k_sort_queue_* (sg_wavefront.cuh)
         if ((rc = ws_alloc(w, &w.q.sorted, n)) != SG_OK) return rc;
         if ((rc = ws_alloc(w, &w.q.sort_hist, (size_t)128)) != SG_OK) return rc;
@@ -874,6 +881,13 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
             kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
             ++launches; ++closest_launches;
             if (time_trace && (rc = mark(tev)) != SG_OK) return rc;
+            if (w.q.ray_kind) {                                    // build the shade queues of this depth in ray-queue order
+                const unsigned nblk = std::min((unsigned)((cnt + kQueueBlock - 1) / kQueueBlock), (unsigned)num_sms * 8u);
+                k_queue_count<<<nblk, 256, 0, stream>>>(w.q, depth);
+                k_queue_scan<<<1, 1024, 0, stream>>>(w.q, depth, s->ts.queue_mask);
+                k_queue_scatter<<<nblk, 256, 0, stream>>>(w.q, depth);
+                launches += 3;
+            }
             if (shadow_pending) { CU(cudaStreamWaitEvent(stream, ev_shadowed[lane], 0)); shadow_pending = false; }   // L of depth - 1 is final
             if (s->d.n_infinite > 0) { k_shade_miss<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
             if (s->has_mix) { resolve_mix_kernel(s->tex_path)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, w.q, k, depth); ++launches; }
