@@ -26,16 +26,20 @@ def _stale(target, sources):
 GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade_tu.cu", ["-DSG_TU=%d" % i]) for i in range(1, 11)]
 
 
-def build_gpu(force=False, verbose=False):
+def build_gpu(force=False, verbose=False, variant=None, defs=()):
+    """variant / defs: an A/B build with extra -D flags -> ab/libshimmer_gpu_<variant>.so (loaded through SHIMMER_GPU_LIB)"""
     out = os.path.join(HERE, "libshimmer_gpu.so")
+    if variant:
+        os.makedirs(os.path.join(HERE, "ab"), exist_ok=True)
+        out = os.path.join(HERE, "ab", "libshimmer_gpu_%s.so" % variant)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(HERE, "..", "include", "shimmer_gpu.h"))
     if not force and not _stale(out, srcs):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", variant) if variant else os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else [])
+    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + list(defs)
     procs = []
     for name, src, defs in GPU_UNITS:
         obj = os.path.join(objdir, name + ".o")
@@ -64,4 +68,8 @@ def build_all(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python -m shimmer_b200.build --variant t512 -DSG_SHADE_THREADS=512
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build_gpu(force=True, verbose="-v" in sys.argv, variant=name, defs=[a for a in sys.argv if a.startswith("-D")]))
+    else:
+        print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -90,6 +90,8 @@ struct RenderConst {
     int32_t  path_order;         // 0 = sample-major row-major (debug), 1 = pixel-major tiled
     int32_t  integrator;         // SgIntegratorKind
     int32_t  integrator_flags;   // SG_SIMPLEPATH_*
+    int32_t  shade_sync;         // shade kernels: bit mask of the stage barriers that keep a CTA's warps in the same code region
+    int32_t  shade_sync_tex;     //   (untextured / textured variants)
 };
 
 // Path order of a wavefront.  Wavefront slot g -> (pixel, sample): pixel-major, so the samples of one pixel
@@ -720,6 +722,10 @@ static __global__ void __launch_bounds__(256) k_sort_queue_scatter(const __grid_
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS 4
 #endif
+// threads per CTA of the lean (untextured) shade kernels; SG_SHADE_MIN_BLOCKS counts CTAs of 128 threads
+#ifndef SG_SHADE_THREADS
+#define SG_SHADE_THREADS 256
+#endif
 // textured variants (C4): resident blocks per SM measured on one box, same build otherwise -- 3 (168 regs): 176.1, 4 (128): 186.8,
 // 5 (96): 188.4, 6 (80): 186.5 Mpaths/s.  Occupancy buys more than the extra spills cost; the curve is flat from 4 to 6.
 #ifndef SG_SHADE_MIN_BLOCKS_TEX
@@ -741,7 +747,7 @@ template <bool FD, class A, class B> SGD auto& pick_bsdf(A& a, B& b) { if conste
 // `no_instruction` the top stall even after the material sort, issue-active 21 %); the two stages each fit the instruction
 // caches far better.  Same arithmetic in the same order per path, so the films are bit-identical to STAGE 0's.
 template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false, int STAGE = 0>
-__global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+__global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_MIN_BLOCKS_TEX : (SG_SHADE_MIN_BLOCKS * 128 / SG_SHADE_THREADS)) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
     const int qk = 1 + KIND;
@@ -754,7 +760,8 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
     // filter and bump-map code: shade queues are binned by material KIND only, and a warp of mixed EWA / bilinear / untextured
     // lanes runs at a few active lanes per instruction.  Nothing in the result depends on the processing order.
     constexpr int ITEMS = TEX ? 8 : 1;
-    constexpr uint32_t kChunk = 128u * ITEMS;
+    constexpr uint32_t kThreads = TEX ? 128u : (uint32_t)SG_SHADE_THREADS;
+    constexpr uint32_t kChunk = kThreads * ITEMS;
     __shared__ uint32_t s_sorted[TEX ? 1024 : 1];
     __shared__ uint32_t s_hist[64], s_off[64];
     for (uint32_t chunk = blockIdx.x * kChunk; chunk < n; chunk += gridDim.x * kChunk) {
@@ -788,7 +795,10 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
       }
 #pragma unroll 1
       for (int it = 0; it < ITEMS; ++it) {
-        const uint32_t i = chunk + it * 128u + threadIdx.x;
+        const uint32_t i = chunk + it * kThreads + threadIdx.x;
+        // stage barriers (full chunks only -- every thread of the CTA has an item and reaches them)
+        const int sync_mask = (chunk + kChunk <= n) ? (TEX ? rc.shade_sync_tex : rc.shade_sync) : 0;
+#define SG_STAGE_SYNC(bit) do { if (sync_mask & (bit)) __syncthreads(); } while (0)
         bool want_shadow = false, want_next = false;
         uint32_t path = 0;
         if (i < n) {
@@ -826,6 +836,7 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
             else s = surface_general<TEX>(sc, geo, hb, rd, st.hit_inst[path], &sx, wo_si);
             }
 
+            SG_STAGE_SYNC(1);
             const bool simple = !PATH && rc.integrator == SG_INTEGRATOR_SIMPLE_PATH, walk = !PATH && !simple;
             const bool sample_lights = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_LIGHTS) != 0, sample_bsdf_dir = (rc.integrator_flags & SG_SIMPLEPATH_SAMPLE_BSDF) != 0;
             // emission + MIS against light sampling, :798-813
@@ -848,6 +859,7 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 }
             }
 
+            SG_STAGE_SYNC(2);
             // get_bsdf, interaction.rs:187-278 + Material::get_bsdf
             AuxRays aux; aux.has = false;
             if constexpr (STAGE == 2) {                          // built by stage 1; a DiffuseBxDF has no other parameters
@@ -1044,6 +1056,7 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                         aux.has = false;
                     }
                 } else {
+                SG_STAGE_SYNC(4);
                 // ---- sample_ld :897-963 ----
 #ifdef SG_EXP_SKIP_NEE      /* timing experiment only (tools/r02_exp_split.sh): wrong images */
                 if (false) {
@@ -1088,6 +1101,7 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                         }
                     }
                 }
+                SG_STAGE_SYNC(8);
                 // ---- BSDF sampling :843-875 ----
                 const float u = rng.get_1d();
                 float2 u2; u2.x = rng.get_1d(); u2.y = rng.get_1d();
@@ -1160,6 +1174,8 @@ __global__ void __launch_bounds__(128, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_
                 if (want_next) q_next[qb + __popc(mask & ((1u << lane) - 1u))] = path;
             }
         }
+        SG_STAGE_SYNC(16);
+#undef SG_STAGE_SYNC
       }
       if constexpr (TEX) __syncthreads();                                            // s_sorted / s_hist are reused by the next chunk
     }

@@ -837,6 +837,8 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     k.n_samples = rp->sample_end - rp->sample_begin;
     { const char* v = std::getenv("SG_PATH_ORDER"); k.path_order = v ? std::atoi(v) : 1; }
     k.integrator = rp->integrator; k.integrator_flags = rp->integrator_flags;
+    { const char* v = std::getenv("SG_SHADE_SYNC"); k.shade_sync = v ? std::atoi(v) : 12; }           // barriers around sample_ld (see k_shade)
+    { const char* v = std::getenv("SG_SHADE_SYNC_TEX"); k.shade_sync_tex = v ? std::atoi(v) : 0; }
     const bool path_integrator = rp->integrator == SG_INTEGRATOR_PATH;
     if (k.n_samples == 0) k.n_samples = 1;
     const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
@@ -846,6 +848,7 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     const int grid_closest = persistent_grid(num_sms, (const void*)kern_closest, kTraceThreads, smc);
     const int grid_shadow = persistent_grid(num_sms, (const void*)kern_shadow, kTraceThreads, sms);
     const int shade_grid = num_sms * 8;
+    const int shade_grid_lean = shade_grid * 128 / SG_SHADE_THREADS;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     EventBag bag;                           // events die on every return path
     cudaEvent_t ev0 = bag.make(), ev1 = bag.make(), ev2 = bag.make();
@@ -903,11 +906,12 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
                 }
                 if (s->staged_shading && path_integrator && !force_diffuse && shade_kernel_stage1(kind)) {
                     shade_kernel_stage1(kind)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
-                    shade_kernel_stage2(kind, s->general_lights)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                    shade_kernel_stage2(kind, s->general_lights)<<<shade_grid_lean, SG_SHADE_THREADS, 0, stream>>>(s->d, w.st, qs, k, depth);
                     launches += 2;
                     continue;
                 }
-                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                const bool lean = !force_diffuse && path_integrator && !s->general_lights && !s->tex_path;     // shade_kernel_lean: TEX = false
+                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<lean ? shade_grid_lean : shade_grid, lean ? SG_SHADE_THREADS : 128, 0, stream>>>(s->d, w.st, qs, k, depth);
                 ++launches;
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
