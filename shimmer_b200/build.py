@@ -26,6 +26,11 @@ def _stale(target, sources):
 GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade_tu.cu", ["-DSG_TU=%d" % i]) for i in range(1, 11)]
 
 
+# units an A/B variant re-compiles (the C ABI + traversal unit, the lean shade kernels, the staged-shading unit); the rest is
+# linked from the default build's objects
+VARIANT_UNITS = ("shimmer_gpu", "shade_tu1", "shade_tu10")
+
+
 def build_gpu(force=False, verbose=False, variant=None, defs=()):
     """variant / defs: an A/B build with extra -D flags -> ab/libshimmer_gpu_<variant>.so (loaded through SHIMMER_GPU_LIB)"""
     out = os.path.join(HERE, "libshimmer_gpu.so")
@@ -41,14 +46,18 @@ def build_gpu(force=False, verbose=False, variant=None, defs=()):
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + list(defs)
     procs = []
-    for name, src, defs in GPU_UNITS:
+    reused = []
+    for name, src, udefs in GPU_UNITS:
         obj = os.path.join(objdir, name + ".o")
-        procs.append((name, obj, subprocess.Popen([nvcc] + flags + defs + ["-c", "-o", obj, os.path.join(CSRC, src)])))
+        if variant and name not in VARIANT_UNITS:       # A/B builds only re-compile the units their macros reach
+            reused.append(os.path.join(HERE, "build", name + ".o"))
+            continue
+        procs.append((name, obj, subprocess.Popen([nvcc] + flags + udefs + ["-c", "-o", obj, os.path.join(CSRC, src)])))
     failed = [name for name, _, p in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
     # NCCL is dlopen'ed at run time (csrc/shimmer_gpu.cu: nccl_load), so the library links against nothing but cudart and libdl
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out] + [obj for _, obj, _ in procs] + ["-ldl"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out] + [obj for _, obj, _ in procs] + reused + ["-ldl"], check=True)
     return out
 
 

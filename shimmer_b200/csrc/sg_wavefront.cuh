@@ -103,6 +103,11 @@ SGD void pixel_from_order(uint32_t ord, int w, int h, int& x, int& y) {
     const uint32_t W = (uint32_t)w, H = (uint32_t)h;
     const uint32_t by = ord / (W * 32u); uint32_t r = ord - by * W * 32u;
     const uint32_t bh = min(32u, H - by * 32u);
+    if (bh == 32u && (r >> 10) < (W >> 5)) {                // a full 32x32 block (all but the right / bottom edge): shifts only
+        const uint32_t bx = r >> 10; r &= 1023u;
+        x = (int)(bx * 32u + ((r >> 5) & 3u) * 8u + (r & 7u)); y = (int)(by * 32u + (r >> 7) * 4u + ((r >> 3) & 3u));
+        return;
+    }
     const uint32_t bx = r / (32u * bh); r -= bx * 32u * bh;
     const uint32_t bw = min(32u, W - bx * 32u);
     const uint32_t ty = r / (bw * 4u); r -= ty * bw * 4u;
@@ -140,7 +145,7 @@ static constexpr int kTraceThreads = SG_TRACE_THREADS;
 
 // ---- camera ray generation: evaluate_pixel_sample integrator.rs:326-362 ----
 static __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc,
-                                                  unsigned long long first_item, uint32_t count) {
+                                                  unsigned long long first_item, uint32_t first_ord, uint32_t first_rem, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) q.counters[C_NRAY] = count;
     if (i >= count) return;
@@ -152,8 +157,10 @@ static __global__ void __launch_bounds__(256) k_generate(const __grid_constant__
         const uint32_t lin = (uint32_t)(g % npix);
         wx = (int)(lin % (uint32_t)rc.win_w); wy = (int)(lin / (uint32_t)rc.win_w);
     } else {
-        s = rc.sample_begin + (int)(g % (unsigned long long)rc.n_samples);
-        pixel_from_order((uint32_t)(g / (unsigned long long)rc.n_samples), rc.win_w, rc.win_h, wx, wy);
+        // g / n_samples and g % n_samples without 64-bit division: the host split the batch's first item, the rest fits 32 bits
+        const uint32_t t = first_rem + i, dq = t / (uint32_t)rc.n_samples;
+        s = rc.sample_begin + (int)(t - dq * (uint32_t)rc.n_samples);
+        pixel_from_order(first_ord + dq, rc.win_w, rc.win_h, wx, wy);
     }
     const uint32_t pix = (uint32_t)wy * (uint32_t)rc.win_w + (uint32_t)wx;
     const int px = rc.win_x0 + wx, py = rc.win_y0 + wy;
@@ -589,34 +596,55 @@ static __global__ void __launch_bounds__(256) k_queue_count(Queues q, int depth)
         __syncthreads();
     }
 }
-// exclusive scan of the per-block counts of every queue (one warp per queue kind would do; one 1024-thread block is simpler):
-// block_counts becomes block bases, the totals go to the depth's counters (what the shade kernels read as their work count).
+// exclusive scan of the per-block counts of all eight queues at once: block_counts becomes block bases, the totals go to the depth's
+// counters (what the shade kernels read as their work count).  One 1024-thread block; a thread owns `per` consecutive blocks (two
+// 16-byte loads per block), the partial sums are scanned with warp shuffles + one pass over the 32 warp totals.
+static_assert(Q_NKINDS == 8, "k_queue_scan reads a block's eight counts as two uint4");
 static __global__ void __launch_bounds__(1024) k_queue_scan(Queues q, int depth, uint32_t queue_mask) {
     const uint32_t n = q.counters[depth * C_STRIDE + C_NRAY];
     const uint32_t n_blocks = (n + kQueueBlock - 1) / kQueueBlock;
-    __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_warp[32][Q_NKINDS];
     const uint32_t per = (n_blocks + 1023u) / 1024u;                         // consecutive blocks per thread
-    for (int k = 0; k < Q_NKINDS; ++k) {
-        if (!((queue_mask >> k) & 1u)) {                                       // a queue this scene never feeds (TraceScene::queue_mask)
-            if (threadIdx.x == 0) q.counters[depth * C_STRIDE + C_NSHADE + k] = 0u;
-            continue;
-        }
-        const uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, n_blocks);
-        uint32_t sum = 0;
-        for (uint32_t b = b0; b < b1; ++b) sum += q.block_counts[(size_t)b * Q_NKINDS + k];
-        s_part[threadIdx.x] = sum;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {                                   // Hillis-Steele inclusive scan of the 1024 partial sums
-            const uint32_t v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0u;
-            __syncthreads();
-            s_part[threadIdx.x] += v;
-            __syncthreads();
-        }
-        uint32_t run = s_part[threadIdx.x] - sum;                              // exclusive base of this thread's first block
-        for (uint32_t b = b0; b < b1; ++b) { const uint32_t c = q.block_counts[(size_t)b * Q_NKINDS + k]; q.block_counts[(size_t)b * Q_NKINDS + k] = run; run += c; }
-        if (threadIdx.x == 1023) q.counters[depth * C_STRIDE + C_NSHADE + k] = s_part[1023];
-        __syncthreads();
+    const uint32_t b0 = min(threadIdx.x * per, n_blocks), b1 = min(b0 + per, n_blocks);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* bc = reinterpret_cast<uint4*>(q.block_counts);
+    uint32_t sum[Q_NKINDS];
+#pragma unroll
+    for (int k = 0; k < Q_NKINDS; ++k) sum[k] = 0u;
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint4 lo = bc[2 * (size_t)b], hi = bc[2 * (size_t)b + 1];
+        sum[0] += lo.x; sum[1] += lo.y; sum[2] += lo.z; sum[3] += lo.w; sum[4] += hi.x; sum[5] += hi.y; sum[6] += hi.z; sum[7] += hi.w;
     }
+    uint32_t inc[Q_NKINDS];
+#pragma unroll
+    for (int k = 0; k < Q_NKINDS; ++k) {
+        uint32_t v = sum[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        inc[k] = v;
+        if (lane == 31) s_warp[warp][k] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < Q_NKINDS; ++k) {
+            uint32_t v = s_warp[lane][k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            s_warp[lane][k] = v;                                               // inclusive over the warps
+        }
+    }
+    __syncthreads();
+    uint32_t run[Q_NKINDS];
+#pragma unroll
+    for (int k = 0; k < Q_NKINDS; ++k) run[k] = inc[k] - sum[k] + (warp > 0 ? s_warp[warp - 1][k] : 0u);   // exclusive base of this thread's first block
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint4 lo = bc[2 * (size_t)b], hi = bc[2 * (size_t)b + 1];
+        bc[2 * (size_t)b] = make_uint4(run[0], run[1], run[2], run[3]); bc[2 * (size_t)b + 1] = make_uint4(run[4], run[5], run[6], run[7]);
+        run[0] += lo.x; run[1] += lo.y; run[2] += lo.z; run[3] += lo.w; run[4] += hi.x; run[5] += hi.y; run[6] += hi.z; run[7] += hi.w;
+    }
+    if (threadIdx.x < Q_NKINDS)                                               // a queue this scene never feeds (TraceScene::queue_mask) stays empty
+        q.counters[depth * C_STRIDE + C_NSHADE + threadIdx.x] = ((queue_mask >> threadIdx.x) & 1u) ? s_warp[31][threadIdx.x] : 0u;
 }
 static __global__ void __launch_bounds__(256) k_queue_scatter(Queues q, int depth) {
     const uint32_t n = q.counters[depth * C_STRIDE + C_NRAY];
@@ -717,14 +745,14 @@ static __global__ void __launch_bounds__(256) k_sort_queue_scatter(const __grid_
 
 // ---- surface shading, one kernel per material kind: PathIntegrator::li body integrator.rs:796-891
 //      + sample_ld :897-963 ----
-// lean variants: 4 blocks per SM (<= 128 registers, which the diffuse / conductor kernels do not even reach); 5 (96 registers) was
-// measured slower -- C2 557.5 -> 545.4, C3 543.6 -> 522.9 Mpaths/s.
-#ifndef SG_SHADE_MIN_BLOCKS
-#define SG_SHADE_MIN_BLOCKS 4
-#endif
-// threads per CTA of the lean (untextured) shade kernels; SG_SHADE_MIN_BLOCKS counts CTAs of 128 threads
+// lean variants: CTAs of SG_SHADE_THREADS threads, SG_SHADE_MIN_BLOCKS of them per SM.  16 warps per SM (<= 128 registers, which the
+// diffuse / conductor kernels do not even reach); 20 warps (96 registers) was measured slower in round 1 -- C2 557.5 -> 545.4,
+// C3 543.6 -> 522.9 Mpaths/s.
 #ifndef SG_SHADE_THREADS
 #define SG_SHADE_THREADS 256
+#endif
+#ifndef SG_SHADE_MIN_BLOCKS
+#define SG_SHADE_MIN_BLOCKS (512 / SG_SHADE_THREADS)
 #endif
 // textured variants (C4): resident blocks per SM measured on one box, same build otherwise -- 3 (168 regs): 176.1, 4 (128): 186.8,
 // 5 (96): 188.4, 6 (80): 186.5 Mpaths/s.  Occupancy buys more than the extra spills cost; the curve is flat from 4 to 6.
@@ -747,7 +775,7 @@ template <bool FD, class A, class B> SGD auto& pick_bsdf(A& a, B& b) { if conste
 // `no_instruction` the top stall even after the material sort, issue-active 21 %); the two stages each fit the instruction
 // caches far better.  Same arithmetic in the same order per path, so the films are bit-identical to STAGE 0's.
 template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false, int STAGE = 0>
-__global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_MIN_BLOCKS_TEX : (SG_SHADE_MIN_BLOCKS * 128 / SG_SHADE_THREADS)) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+__global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
     const int qk = 1 + KIND;

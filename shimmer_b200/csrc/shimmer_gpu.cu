@@ -878,7 +878,8 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
         Workspace& w = s->ws[lane];
         bool shadow_pending = false;
         CU(cudaMemsetAsync(w.q.counters, 0, (size_t)(rp->max_depth + 3) * C_STRIDE * sizeof(uint32_t), stream));
-        k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, cnt); ++launches;
+        // first = first_ord * n_samples + first_rem (pixel-order index and sample offset of the batch's first path)
+        k_generate<<<(cnt + 255) / 256, 256, 0, stream>>>(s->d, w.st, w.q, k, first, (uint32_t)(first / (uint64_t)k.n_samples), (uint32_t)(first % (uint64_t)k.n_samples), cnt); ++launches;
         for (int depth = 0; depth < n_depths; ++depth) {
             if (time_trace && (rc = mark(tev)) != SG_OK) return rc;
             kern_closest<<<grid_closest, kTraceThreads, smc, stream>>>(s->d, s->ts, w.st, w.q, depth, s->d_stats);
