@@ -343,7 +343,7 @@ struct ClosestIO {
     bool first_depth;           // depth 0: nobody has written L yet (k_generate leaves it out) -- escaping paths get L = 0 here
     uint32_t path;
     SGD void load(uint32_t i, float3& o, float3& d, float& tmax) {
-        path = queue[i];
+        path = first_depth ? i : queue[i];                      // the depth-0 ray queue is the identity (k_generate): one dependent load less
         const float4 o4 = st.ray_o[path], d4 = st.ray_d[path];
         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = INFINITY;
     }
