@@ -819,7 +819,7 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     // of all streams).  Film and statistics updates are atomic, so the batches commute.  A one-batch job below 32 Mi paths is cut
     // into equal parts (C1: +5 %); a bigger single batch stays whole (C2 at 64 Mi paths: halves lose 2 % -- large wavefronts
     // amortise their own tails).  Per-kernel timing / visit counting keep one stream (their events bracket one kernel at a time).
-    static const int overlap_env = [] { const char* v = std::getenv("SG_OVERLAP"); return v ? std::atoi(v) : 2; }();
+    const int overlap_env = [] { const char* v = std::getenv("SG_OVERLAP"); return v ? std::atoi(v) : 2; }();      // read per render (tests flip it)
     const bool time_or_count = (rp->flags & (SG_RENDER_TIME_KERNELS | SG_RENDER_COUNT_VISITS)) != 0;
     int n_inflight = (overlap_env >= 2 && !time_or_count && total >= (1ull << 21)) ? std::min(overlap_env, kMaxWavefronts) : 1;
     if (n_inflight > 1 && cap64 >= total) {
@@ -847,7 +847,7 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     const TraceKernel kern_closest = trace_kernel(false, count, s->instanced), kern_shadow = trace_kernel(true, count, s->instanced);
     const int grid_closest = persistent_grid(num_sms, (const void*)kern_closest, kTraceThreads, smc);
     const int grid_shadow = persistent_grid(num_sms, (const void*)kern_shadow, kTraceThreads, sms);
-    const int shade_grid = num_sms * 8;
+    const int shade_grid = num_sms * [] { const char* v = std::getenv("SG_SHADE_GRID"); return v && std::atoi(v) > 0 ? std::atoi(v) : 8; }();   // grid-stride shade kernels: CTAs of 128 threads per SM
     const int shade_grid_lean = shade_grid * 128 / SG_SHADE_THREADS;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     EventBag bag;                           // events die on every return path

@@ -57,7 +57,7 @@ def test_patch_scene_renders():
         sc = scenes.patch_tiny_scene(kind, resolution=(24, 24)).build()
         assert sc.meta["n_patches"] >= 38
         a, st, _ = orc.render(sc, orc.make_params(seed=1, spp=32), stream_mode=0)
-        b, _, _ = orc.render(sc, orc.make_params(seed=1, spp=32), stream_mode=1)
+        b, _, _ = orc.render(sc, orc.make_params(seed=1, spp=32), stream_mode=1, n_threads=1)     # deterministic tile order
         assert np.isfinite(a).all() and a[:, :3].sum() > 0
         assert abs(a[:, :3].sum() - b[:, :3].sum()) / b[:, :3].sum() < 0.08
 
