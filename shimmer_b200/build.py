@@ -28,7 +28,7 @@ GPU_UNITS = [("shimmer_gpu", "shimmer_gpu.cu", [])] + [("shade_tu%d" % i, "shade
 
 # units an A/B variant re-compiles (the C ABI + traversal unit, the lean shade kernels, the staged-shading unit); the rest is
 # linked from the default build's objects
-VARIANT_UNITS = ("shimmer_gpu", "shade_tu1", "shade_tu10")
+VARIANT_UNITS = ("shimmer_gpu", "shade_tu1", "shade_tu6", "shade_tu10")
 
 
 def build_gpu(force=False, verbose=False, variant=None, defs=()):

@@ -754,10 +754,14 @@ static __global__ void __launch_bounds__(256) k_sort_queue_scatter(const __grid_
 #ifndef SG_SHADE_MIN_BLOCKS
 #define SG_SHADE_MIN_BLOCKS (512 / SG_SHADE_THREADS)
 #endif
-// textured variants (C4): resident blocks per SM measured on one box, same build otherwise -- 3 (168 regs): 176.1, 4 (128): 186.8,
-// 5 (96): 188.4, 6 (80): 186.5 Mpaths/s.  Occupancy buys more than the extra spills cost; the curve is flat from 4 to 6.
+// textured variants (C4): 128-thread CTAs, resident blocks per SM measured on one box, same build otherwise -- 3 (168 regs): 176.1,
+// 4 (128): 186.8, 5 (96): 188.4, 6 (80): 186.5 Mpaths/s.  Round 2 (staged shading, material sort): 2 CTAs of 256 threads (128 regs, no
+// spills) 371.5 against 359.1 for 5 x 128 (96 regs) and 359.4 for 3 x 256 (80 regs); stage barriers change nothing here (r02_c33).
+#ifndef SG_SHADE_THREADS_TEX
+#define SG_SHADE_THREADS_TEX 256
+#endif
 #ifndef SG_SHADE_MIN_BLOCKS_TEX
-#define SG_SHADE_MIN_BLOCKS_TEX 5
+#define SG_SHADE_MIN_BLOCKS_TEX (512 / SG_SHADE_THREADS_TEX)
 #endif
 // TEX = the scene has image textures (or a non-zero constant displacement): screen-space differentials, texture lookups, bump /
 // normal mapping and specular ray-differential propagation (sg_texture.cuh) are compiled in.  TEX = false is the lean variant
@@ -775,7 +779,7 @@ template <bool FD, class A, class B> SGD auto& pick_bsdf(A& a, B& b) { if conste
 // `no_instruction` the top stall even after the material sort, issue-active 21 %); the two stages each fit the instruction
 // caches far better.  Same arithmetic in the same order per path, so the films are bit-identical to STAGE 0's.
 template <int KIND, bool TEX, bool PATH = true, bool LG = TEX, bool FD = false, int STAGE = 0>
-__global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
+__global__ void __launch_bounds__(TEX ? SG_SHADE_THREADS_TEX : SG_SHADE_THREADS, TEX ? SG_SHADE_MIN_BLOCKS_TEX : SG_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, PathState st, Queues q, RenderConst rc, int depth) {
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t* Cn = C + C_STRIDE;
     const int qk = 1 + KIND;
@@ -783,12 +787,12 @@ __global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_M
     const uint32_t* queue = q.shade[qk];
     uint32_t* q_next = q.ray[(depth + 1) & 1];
     const int lane = threadIdx.x & 31;
-    // Work distribution: a CTA takes chunks of 128 x ITEMS queue entries.  Textured scenes (ITEMS = 8) first sort the chunk by
+    // Work distribution: a CTA takes chunks of kThreads x ITEMS queue entries.  Textured scenes (1024-entry chunks) first sort the chunk by
     // material in shared memory (counting sort over 64 hash buckets), so that the 32 lanes of a warp run the same texture
     // filter and bump-map code: shade queues are binned by material KIND only, and a warp of mixed EWA / bilinear / untextured
     // lanes runs at a few active lanes per instruction.  Nothing in the result depends on the processing order.
-    constexpr int ITEMS = TEX ? 8 : 1;
-    constexpr uint32_t kThreads = TEX ? 128u : (uint32_t)SG_SHADE_THREADS;
+    constexpr uint32_t kThreads = TEX ? (uint32_t)SG_SHADE_THREADS_TEX : (uint32_t)SG_SHADE_THREADS;
+    constexpr int ITEMS = TEX ? 1024 / (int)kThreads : 1;
     constexpr uint32_t kChunk = kThreads * ITEMS;
     __shared__ uint32_t s_sorted[TEX ? 1024 : 1];
     __shared__ uint32_t s_hist[64], s_off[64];
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_M
         uint32_t e_path[ITEMS], e_slot[ITEMS];
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t i = chunk + k * 128u + threadIdx.x;
+            const uint32_t i = chunk + k * kThreads + threadIdx.x;
             e_slot[k] = 0xffffffffu; e_path[k] = 0u;
             if (i < n) {
                 e_path[k] = queue[i];
@@ -830,7 +834,7 @@ __global__ void __launch_bounds__(TEX ? 128 : SG_SHADE_THREADS, TEX ? SG_SHADE_M
         bool want_shadow = false, want_next = false;
         uint32_t path = 0;
         if (i < n) {
-            path = TEX ? s_sorted[it * 128u + threadIdx.x] : queue[i];
+            path = TEX ? s_sorted[it * kThreads + threadIdx.x] : queue[i];
             const float4 rd4 = st.ray_d[path];
             const float3 rd = f3(rd4.x, rd4.y, rd4.z);
             const float3 wo = -rd;

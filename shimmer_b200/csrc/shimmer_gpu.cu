@@ -848,7 +848,7 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     const int grid_closest = persistent_grid(num_sms, (const void*)kern_closest, kTraceThreads, smc);
     const int grid_shadow = persistent_grid(num_sms, (const void*)kern_shadow, kTraceThreads, sms);
     const int shade_grid = num_sms * [] { const char* v = std::getenv("SG_SHADE_GRID"); return v && std::atoi(v) > 0 ? std::atoi(v) : 8; }();   // grid-stride shade kernels: CTAs of 128 threads per SM
-    const int shade_grid_lean = shade_grid * 128 / SG_SHADE_THREADS;
+    const int shade_grid_lean = shade_grid * 128 / SG_SHADE_THREADS, shade_grid_tex = shade_grid * 128 / SG_SHADE_THREADS_TEX;
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(DevStats), stream));
     EventBag bag;                           // events die on every return path
     cudaEvent_t ev0 = bag.make(), ev1 = bag.make(), ev2 = bag.make();
@@ -906,13 +906,13 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
                     qs.shade[1 + kind] = w.q.sorted;
                 }
                 if (s->staged_shading && path_integrator && !force_diffuse && shade_kernel_stage1(kind)) {
-                    shade_kernel_stage1(kind)<<<shade_grid, 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                    shade_kernel_stage1(kind)<<<shade_grid_tex, SG_SHADE_THREADS_TEX, 0, stream>>>(s->d, w.st, qs, k, depth);
                     shade_kernel_stage2(kind, s->general_lights)<<<shade_grid_lean, SG_SHADE_THREADS, 0, stream>>>(s->d, w.st, qs, k, depth);
                     launches += 2;
                     continue;
                 }
                 const bool lean = !force_diffuse && path_integrator && !s->general_lights && !s->tex_path;     // shade_kernel_lean: TEX = false
-                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<lean ? shade_grid_lean : shade_grid, lean ? SG_SHADE_THREADS : 128, 0, stream>>>(s->d, w.st, qs, k, depth);
+                shade_kernel(kind, s->tex_path, s->general_lights, path_integrator, force_diffuse)<<<lean ? shade_grid_lean : shade_grid_tex, lean ? SG_SHADE_THREADS : SG_SHADE_THREADS_TEX, 0, stream>>>(s->d, w.st, qs, k, depth);
                 ++launches;
             }
             if (depth < rp->max_depth && s->d.n_lights > 0) {
