@@ -193,6 +193,7 @@ int persistent_grid(int num_sms, const void* kernel, int threads, size_t smem) {
     int per_sm = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (const char* v = std::getenv("SG_TRACE_BLOCKS_PER_SM")) { const int cap = std::atoi(v); if (cap >= 1 && cap < per_sm) per_sm = cap; }   // A/B knob: leave room for other streams' CTAs
     return num_sms * per_sm;        // grid = SM count x resident CTAs: one full wave, persistent
 }
 
