@@ -39,8 +39,9 @@ struct DScene {
     const float* n;
     const float* uv;
     const float* s;
-    const SgSpectrum* spectra;
+    const SgSpectrum* spectra;          // device copy: `pad` holds 1 + the spectrum's offset into spec_lut (0: none)
     const float* pool;
+    const uint16_t* spec_lut;           // piecewise-linear spectra: interval index at every integer wavelength 360..830 (sg_shading.cuh spectrum_get)
     const SgMaterial* materials;
     const SgLight* lights;
     const SgTexture* textures;          // image textures (sg_texture.cuh)

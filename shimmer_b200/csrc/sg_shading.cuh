@@ -55,6 +55,7 @@ SGD float blackbody(float lambda, float temperature) {           // spectrum.rs:
     float l2 = l * l; float l5 = l2 * l2 * l;
     return (2.0f * h * c * c) / (l5 * (expf((h * c) / (l * kb * temperature)) - 1.0f));
 }
+static constexpr int kSpecLutMin = 360, kSpecLutMax = 830;         // LAMBDA_MIN / LAMBDA_MAX, spectrum.rs
 SGD int find_interval_le(const float* L, int size, float lambda) {   // math.rs:322-333 with pred = L[i] <= lambda
     int first = 1, last = size - 2;
     while (last > 0) {
@@ -78,7 +79,15 @@ SGD float spectrum_get(const DScene& sc, int id, float lambda) {
     case SG_SPECTRUM_PIECEWISE_LINEAR: {
         const float* L = sc.pool + s.off_a; const float* V = sc.pool + s.off_b;
         if (s.n == 0 || lambda < __ldg(L) || lambda > __ldg(L + s.n - 1)) return 0.0f;
-        int o = find_interval_le(L, s.n, lambda);
+        // find_interval (math.rs:322-333) = the largest o in [0, n-2] with o == 0 or L[o] <= lambda.  Instead of the binary search
+        // (six dependent loads for a 48-knot spectrum, four wavelengths per lookup) start from that index for floor(lambda), tabulated
+        // at upload, and step forward over the knots inside the same 1 nm bin: the same index by construction, so the same value.
+        int o;
+        const int fl = __float2int_rz(lambda);
+        if (s.pad != 0u && fl >= kSpecLutMin && fl <= kSpecLutMax) {
+            o = (int)__ldg(sc.spec_lut + (s.pad - 1u) + (uint32_t)(fl - kSpecLutMin));
+            while (o < s.n - 2 && __ldg(L + o + 1) <= lambda) ++o;
+        } else o = find_interval_le(L, s.n, lambda);
         float l0 = __ldg(L + o), l1 = __ldg(L + o + 1);
         float t = (lambda - l0) / (l1 - l0);
         return lerpf(t, __ldg(V + o), __ldg(V + o + 1));

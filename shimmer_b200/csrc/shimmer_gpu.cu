@@ -702,7 +702,31 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
     UP(n, desc->n, desc->n ? (size_t)desc->n_vertices * 3 : 0, float);
     UP(uv, desc->uv, desc->uv ? (size_t)desc->n_vertices * 2 : 0, float);
     UP(s, desc->s, desc->s ? (size_t)desc->n_vertices * 3 : 0, float);
-    UP(spectra, desc->spectra, desc->n_spectra, SgSpectrum);
+    {   // piecewise-linear spectra: tabulate find_interval at every integer wavelength (spectrum_get steps forward from there)
+        std::vector<SgSpectrum> spectra_dev(desc->spectra, desc->spectra + desc->n_spectra);
+        std::vector<uint16_t> lut;
+        for (uint32_t i = 0; i < desc->n_spectra; ++i) {
+            SgSpectrum& sp = spectra_dev[i];
+            sp.pad = 0u;
+            if (sp.kind != SG_SPECTRUM_PIECEWISE_LINEAR || sp.n < 2 || sp.n > 65535) continue;
+            if ((uint64_t)sp.off_a + (uint64_t)sp.n > desc->n_pool || (uint64_t)sp.off_b + (uint64_t)sp.n > desc->n_pool)
+                return bail(fail(SG_ERR_INVALID_ARGUMENT, "spectrum " + std::to_string(i) + ": samples outside spectrum_pool"));
+            const float* L = desc->spectrum_pool + sp.off_a;
+            bool sorted = true;
+            for (int k = 1; k < sp.n; ++k) if (!(L[k - 1] <= L[k])) sorted = false;
+            if (!sorted) continue;                          // the binary search's answer is not "the last knot <= lambda" then: keep it
+            sp.pad = (uint32_t)lut.size() + 1u;
+            int o = 0;                                      // largest o in [0, n-2] with o == 0 or L[o] <= w; monotone in w
+            for (int w = kSpecLutMin; w <= kSpecLutMax; ++w) {
+                while (o + 1 <= sp.n - 2 && L[o + 1] <= (float)w) ++o;
+                lut.push_back((uint16_t)o);
+            }
+        }
+        SgSpectrum* p_sp = nullptr; uint16_t* p_lut = nullptr;
+        if ((rc = upload(spectra_dev.data(), spectra_dev.size(), &p_sp, s->owned)) != SG_OK) return bail(rc);
+        if ((rc = upload(lut.data(), lut.size(), &p_lut, s->owned)) != SG_OK) return bail(rc);
+        d.spectra = p_sp; d.spec_lut = p_lut;
+    }
     UP(pool, desc->spectrum_pool, desc->n_pool, float);
     UP(materials, desc->materials, desc->n_materials, SgMaterial);
     UP(lights, desc->lights, desc->n_lights, SgLight);

@@ -432,4 +432,16 @@ done
 cat gpurun_out/r02_ab_mb.log
 }
 
-if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
+# spectrum interval table (piecewise-linear spectra): GPU tests + five configs
+call36() {
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_c36_pytest.log 2>&1; tail -3 gpurun_out/r02_c36_pytest.log
+L=gpurun_out/r02_c36_perf.log; : > $L
+timeout 600 python tools/perf_ab.py --workload composite --spp 64 --reps 2 base 2>> gpurun_out/r02_c36.err | cut -c1-200 >> $L
+timeout 600 python tools/perf_ab.py --workload mesh1m --reps 2 base 2>> gpurun_out/r02_c36.err | cut -c1-200 >> $L
+timeout 600 python tools/perf_ab.py --workload glass --reps 1 base 2>> gpurun_out/r02_c36.err | cut -c1-200 >> $L
+timeout 600 python tools/perf_ab.py --workload instanced --reps 1 base 2>> gpurun_out/r02_c36.err | cut -c1-200 >> $L
+timeout 600 python tools/perf_ab.py --workload cornell --reps 3 base 2>> gpurun_out/r02_c36.err | cut -c1-200 >> $L
+cat $L
+}
+
+if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
