@@ -125,6 +125,12 @@ def test_invalid_variety_inputs_are_rejected():
     sc = scenes.tiny_scene("diffuse", resolution=(8, 8)).build()
     with pytest.raises(ShimmerGpuError, match="Unknown integrator"):
         create_integrator("wavefront", {"integrator": "bdpt"}, sc)
+    sc = scenes.tiny_scene("diffuse", resolution=(8, 8)).build()
+    spectra = sc.arrays["spectra"]
+    pl = [i for i in range(sc.desc.n_spectra) if spectra[i].kind == ffi.SG_SPECTRUM_PIECEWISE_LINEAR]
+    spectra[pl[0]].off_b = sc.desc.n_pool - 1                      # the values of a piecewise-linear spectrum would run past spectrum_pool
+    with pytest.raises(ShimmerGpuError, match="spectrum_pool"):
+        create_integrator("wavefront", {}, sc)
 
 
 @pytest.mark.parametrize("shape,wrap", [((64, 64, 3), "repeat"), ((32, 128, 1), "clamp"), ((37, 50, 3), "repeat"), ((100, 37, 1), "clamp"),
