@@ -444,4 +444,11 @@ timeout 600 python tools/perf_ab.py --workload cornell --reps 3 base 2>> gpurun_
 cat $L
 }
 
-if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
+# source-level capture of the depth-1 traversal kernels on C2 (profiles/r02_trace_ncu.md)
+call37() {
+SG_OVERLAP=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 2 -c 2 -f -o gpurun_out/r02_trace_src \
+   python tools/render_once.py --workload mesh1m --spp 16 --warm 0 > gpurun_out/r02_trace_src.log 2>&1
+ls -la gpurun_out/r02_trace_src.ncu-rep
+}
+
+if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 call37 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
