@@ -133,7 +133,8 @@ typedef struct SgMesh {
 typedef enum SgSpectrumKind {
     SG_SPECTRUM_CONSTANT = 0,        /* ConstantSpectrum, spectrum.rs:146-168: c        */
     SG_SPECTRUM_DENSE = 1,           /* DenselySampledSpectrum, :171-292: pool[off_a..+n], lambda_min */
-    SG_SPECTRUM_PIECEWISE_LINEAR = 2,/* PiecewiseLinearSpectrum, :295-440: lambdas at off_a, values at off_b, n */
+    SG_SPECTRUM_PIECEWISE_LINEAR = 2,/* PiecewiseLinearSpectrum, :295-440: lambdas at off_a, values at off_b, n; both runs must lie
+                                      * inside spectrum_pool (sg_scene_create rejects the scene otherwise); `pad` is ignored */
     SG_SPECTRUM_BLACKBODY = 3        /* BlackbodySpectrum, :443-495: c = T, scale = normalization_factor */
 } SgSpectrumKind;
 typedef struct SgSpectrum {
