@@ -65,6 +65,8 @@ struct TraceScene {
     int refill_threshold_d0;    // the same knobs for the CLOSEST-HIT launch of depth 0 (camera rays: a warp's rays are near-identical, so
     int interior_burst_d0;      //   waiting for most lanes before a refill keeps them in lockstep)
     int prefetch;
+    int refill_threshold_dual, leaf_threshold_dual;      // two-rays-per-lane kernels (k_trace_dual): thresholds count SLOTS (64 per warp)
+    int dual_levels_closest, dual_levels_shadow;         //   shared-memory stack levels per ray
     const DInstance* instances; // object instancing (INST kernels only)
     const float4* patch_verts;  // bilinear patches (INST kernels only)
     const DSphere* spheres;     // sphere shapes (INST kernels only: the "general" kernels handle everything that is not a triangle)

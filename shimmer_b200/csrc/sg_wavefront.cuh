@@ -347,6 +347,7 @@ struct ClosestIO {
         const float4 o4 = st.ray_o[path], d4 = st.ray_d[path];
         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = INFINITY;
     }
+    SGD void rebind(uint32_t i) { path = first_depth ? i : queue[i]; }           // two-rays-per-lane traversal: the slot being retired
     SGD void retire(bool fin, uint32_t idx, const HitRec& hit, int lane) {
         int kind = -1;
         if (fin) {
@@ -386,10 +387,125 @@ struct ShadowIO {
         const float4 o4 = st.sh_o[path], d4 = st.sh_d[path];
         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); tmax = SG_SHADOW_TMAX;
     }
+    SGD void rebind(uint32_t i) { path = queue[i]; }
     SGD void retire(bool fin, uint32_t, const HitRec& hit, int) {
         if (fin && hit.prim < 0) st.L[path] = st.L[path] + st.sh_L[path];      // unoccluded: L += beta * Ld
     }
 };
+
+// ---- two rays per lane (triangle-only scenes, A/B: SG_TRACE_DUAL=1) ----
+// The voted phase loop leaves lanes idle: a lane that reaches a leaf waits until enough lanes hold one, a finished lane waits for the
+// next refill (interior phases run at ~19 of 32 lanes, triangle phases at ~6).  Here every lane owns TWO rays -- one in registers,
+// one parked in shared memory with its own traversal stack -- and switches to the parked ray whenever the active one cannot take an
+// interior step (it holds a leaf, is finished, or the slot is empty).  Each ray is still traversed exactly as in trace_persistent
+// (same steps in the same order), so hits are bit-identical; only the interleaving changes.
+static constexpr int kSpillDual = 64;
+static constexpr int kParkWords = 19;
+template <bool ANY, class IO>
+SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_t* cursor, uint32_t* s_mem, int levels, bool first_depth) {
+    const int lane = threadIdx.x & 31;
+    const int stride = blockDim.x;
+    const int refill_threshold = first_depth ? 2 * ts.refill_threshold_d0 : ts.refill_threshold_dual;
+    const int interior_burst = first_depth ? ts.interior_burst_d0 : ts.interior_burst;
+    uint2 spill0[kSpillDual], spill1[kSpillDual];
+    const int stack_words = levels * stride * (ANY ? 1 : 2);
+    uint32_t* const base0 = s_mem + threadIdx.x;
+    uint32_t* const base1 = s_mem + stack_words + threadIdx.x;
+    float* const park = reinterpret_cast<float*>(s_mem + 2 * stack_words) + threadIdx.x;
+    Stack S; S.stride = stride; S.levels = levels; S.s_save = nullptr;
+    S.s_ref = base0; S.s_t = reinterpret_cast<float*>(base0 + levels * stride); S.spill = spill0;
+    int which = 0;
+    Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
+    L.o = f3(0.0f, 0.0f, 0.0f); L.inv_dir = f3(1.0f, 1.0f, 1.0f); L.rp.kx = 0; L.rp.ky = 1; L.rp.kz = 2; L.rp.sx = L.rp.sy = L.rp.sz = 0.0f;
+    L.t_max = 0.0f; L.nx = L.ny = L.nz = 0; L.hit.t = L.hit.b0 = L.hit.b1 = L.hit.b2 = 0.0f;
+    uint32_t idx = 0;
+    // slot states: 0 empty (wants a ray), 1 interior node next, 2 holds a leaf, 3 finished (to retire), 4 dead (queue exhausted)
+    int sa = 0, sb = 0;
+    uint32_t dummy_n = 0, dummy_t = 0;
+    auto swap_slots = [&]() {
+        float w[kParkWords];
+#pragma unroll
+        for (int k = 0; k < kParkWords; ++k) w[k] = park[k * stride];
+        park[0 * stride] = L.o.x; park[1 * stride] = L.o.y; park[2 * stride] = L.o.z;
+        park[3 * stride] = L.inv_dir.x; park[4 * stride] = L.inv_dir.y; park[5 * stride] = L.inv_dir.z;
+        park[6 * stride] = __int_as_float(L.rp.kx | (L.rp.ky << 2) | (L.rp.kz << 4));
+        park[7 * stride] = L.rp.sx; park[8 * stride] = L.rp.sy; park[9 * stride] = L.rp.sz;
+        park[10 * stride] = L.t_max; park[11 * stride] = __uint_as_float(L.cur); park[12 * stride] = __int_as_float(L.sp);
+        park[13 * stride] = __int_as_float(L.hit.prim); park[14 * stride] = L.hit.t;
+        park[15 * stride] = L.hit.b0; park[16 * stride] = L.hit.b1; park[17 * stride] = L.hit.b2;
+        park[18 * stride] = __uint_as_float(idx);
+        L.o = f3(w[0], w[1], w[2]); L.inv_dir = f3(w[3], w[4], w[5]);
+        const int kk = __float_as_int(w[6]); L.rp.kx = kk & 3; L.rp.ky = (kk >> 2) & 3; L.rp.kz = (kk >> 4) & 3;
+        L.rp.sx = w[7]; L.rp.sy = w[8]; L.rp.sz = w[9];
+        L.t_max = w[10]; L.cur = __float_as_uint(w[11]); L.sp = __float_as_int(w[12]);
+        L.hit.prim = __float_as_int(w[13]); L.hit.t = w[14]; L.hit.b0 = w[15]; L.hit.b1 = w[16]; L.hit.b2 = w[17];
+        idx = __float_as_uint(w[18]);
+        L.nx = L.inv_dir.x < 0.0f; L.ny = L.inv_dir.y < 0.0f; L.nz = L.inv_dir.z < 0.0f;
+        const int t = sa; sa = sb; sb = t;
+        which ^= 1;
+        uint32_t* const b = which ? base1 : base0;
+        S.s_ref = b; S.s_t = reinterpret_cast<float*>(b + levels * stride); S.spill = which ? spill1 : spill0;
+    };
+    auto state_of = [&]() { return L.cur == kEmptyRef ? 3 : ((L.cur & kLeafBit) ? 2 : 1); };
+    for (;;) {
+        if (sa != 1 && sb == 1) swap_slots();                                   // keep an interior ray active whenever the lane has one
+        const uint32_t m_int = __ballot_sync(0xffffffffu, sa == 1);
+        const uint32_t m_leaf_a = __ballot_sync(0xffffffffu, sa == 2), m_leaf_b = __ballot_sync(0xffffffffu, sb == 2);
+        const uint32_t m_need_a = __ballot_sync(0xffffffffu, sa == 0 || sa == 3), m_need_b = __ballot_sync(0xffffffffu, sb == 0 || sb == 3);
+        if ((m_int | m_leaf_a | m_leaf_b) == 0u || __popc(m_need_a) + __popc(m_need_b) >= refill_threshold) {
+            // ---- retire finished rays, claim new ones: one slot per lane and round (the slot to serve is made the active one) ----
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                if ((sb == 0 || sb == 3) && !(sa == 0 || sa == 3)) swap_slots();     // (also when the active slot is dead and a finished ray is parked)
+                const bool fin = sa == 3;
+                if (__ballot_sync(0xffffffffu, fin)) {
+                    if (fin) io.rebind(idx);
+                    L.hit.inst = -1;
+                    io.retire(fin, idx, L.hit, lane);
+                }
+                if (fin) sa = 0;
+                const bool need = sa == 0;
+                const uint32_t mask = __ballot_sync(0xffffffffu, need);
+                if (mask) {
+                    uint32_t base = 0;
+                    const int leader = __ffs(mask) - 1;
+                    if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(mask));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (need) {
+                        idx = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                        if (idx < n) {
+                            float3 o, d; float tmax;
+                            io.load(idx, o, d, tmax);
+                            lane_begin<ANY>(ts, L, o, d, tmax, dummy_n, false);
+                            sa = state_of();
+                        } else sa = 4;
+                    }
+                }
+                if (!__ballot_sync(0xffffffffu, sb == 0 || sb == 3)) break;
+            }
+            if (!__ballot_sync(0xffffffffu, (sa >= 1 && sa <= 3) || (sb >= 1 && sb <= 3))) break;
+            continue;
+        }
+        if (__popc(m_leaf_a) + __popc(m_leaf_b) >= ts.leaf_threshold_dual || m_int == 0u) {
+            // ---- triangle phase: every lane that holds a leaf in either slot tests one ----
+            if (sa != 2 && sb == 2) swap_slots();
+            if (sa == 2) {
+                lane_step_leaf<ANY, false, false>(ts, L, S, dummy_n, dummy_t, io, idx);
+                sa = state_of();
+            }
+            continue;
+        }
+        // ---- interior phase ----
+        if (sa == 1) {
+#pragma unroll 1
+            for (int k = 0; k < interior_burst; ++k) {
+                lane_step_interior<ANY, false, false>(ts, L, S, dummy_n, io, idx);
+                if (L.cur == kEmptyRef) { sa = 3; break; }
+                if (L.cur & kLeafBit) { sa = 2; break; }
+            }
+        }
+    }
+}
 
 template <bool ANY, bool COUNT, bool INST>
 __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST : SG_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
@@ -414,6 +530,23 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
             atomicAdd(&stats->nodes_closest, (unsigned long long)cnt_nodes);
             atomicAdd(&stats->tris_closest, (unsigned long long)cnt_tris);
         }
+    }
+}
+
+#ifndef SG_TRACE_MIN_BLOCKS_DUAL
+#define SG_TRACE_MIN_BLOCKS_DUAL 7
+#endif
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS_DUAL) k_trace_dual(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
+                                                         PathState st, Queues q, int depth, DevStats* stats) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t* C = q.counters + depth * C_STRIDE;
+    if (ANY) {
+        ShadowIO io{st, q.shadow, 0};
+        trace_persistent_dual<true>(ts, io, C[C_NSHADOW], C + C_CUR_SHADOW, s_mem, ts.dual_levels_shadow, false);
+    } else {
+        ClosestIO io{sc, st, q, C, q.ray[depth & 1], ts.queue_mask, depth == 0, 0};
+        trace_persistent_dual<false>(ts, io, C[C_NRAY], C + C_CUR_CLOSEST, s_mem, ts.dual_levels_closest, depth == 0);
     }
 }
 

@@ -115,7 +115,7 @@ struct SgScene {
     std::vector<SgScene*> peers;    // replicas on g_dev[1..] (sg_init_multi); owned by the primary
     DScene d{};
     TraceScene ts{};
-    size_t smem_closest = 0, smem_shadow = 0;
+    size_t smem_closest = 0, smem_shadow = 0, smem_closest_dual = 0, smem_shadow_dual = 0;
     std::vector<void*> owned;
     Workspace ws[2];                 // wavefronts in flight (render_on deals batches round-robin to this many streams); kMaxWavefronts
     DevStats* d_stats = nullptr;
@@ -183,6 +183,7 @@ TraceKernel trace_kernel(bool any, bool count, bool inst) {
     if (any) return count ? (inst ? k_trace<true, true, true> : k_trace<true, true, false>) : (inst ? k_trace<true, false, true> : k_trace<true, false, false>);
     return count ? (inst ? k_trace<false, true, true> : k_trace<false, true, false>) : (inst ? k_trace<false, false, true> : k_trace<false, false, false>);
 }
+TraceKernel trace_kernel_dual(bool any) { return any ? k_trace_dual<true> : k_trace_dual<false>; }
 typedef void (*TraceRaysKernel)(const DScene, const TraceScene, long long, const float*, const float*, const float*, SgHit*, unsigned long long*, DevStats*);
 TraceRaysKernel trace_rays_kernel(bool any, bool count, bool inst) {
     if (any) return count ? (inst ? k_trace_rays<true, true, true> : k_trace_rays<true, true, false>) : (inst ? k_trace_rays<true, false, true> : k_trace_rays<true, false, false>);
@@ -660,6 +661,13 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
         if (s->ts.stack_depth - s->ts.smem_levels > kSpillLevels) s->ts.smem_levels = s->ts.stack_depth - kSpillLevels;
         s->smem_closest = (size_t)s->ts.smem_levels * kTraceThreads * 8;
         s->smem_shadow = (size_t)s->ts.smem_levels * kTraceThreads * 4;
+        // two-rays-per-lane kernels (SG_TRACE_DUAL=1, triangle-only scenes): two stacks + one parked ray per thread
+        s->ts.dual_levels_closest = std::max(1, std::min(s->ts.stack_depth, env_int("SG_DUAL_LEVELS", 12)));
+        s->ts.dual_levels_shadow = std::max(1, std::min(s->ts.stack_depth, env_int("SG_DUAL_LEVELS_SHADOW", 20)));
+        s->ts.refill_threshold_dual = env_int("SG_DUAL_REFILL", 24);
+        s->ts.leaf_threshold_dual = env_int("SG_DUAL_LEAF", 12);
+        s->smem_closest_dual = (size_t)kTraceThreads * (2 * s->ts.dual_levels_closest * 8 + kParkWords * 4);
+        s->smem_shadow_dual = (size_t)kTraceThreads * (2 * s->ts.dual_levels_shadow * 4 + kParkWords * 4);
     }
     s->instanced = desc->n_instances > 0 || desc->n_spheres > 0 || !pv.empty();      // anything that is not a triangle -> the general kernels
     if (s->instanced) {                          // + the parked render-space ray of a lane inside an instance (sg_trace2.cuh lane_save_ray)
@@ -868,8 +876,13 @@ static int render_on(SgScene* s, const SgRenderParams* rp, void* d_film, SgStats
     if (k.n_samples == 0) k.n_samples = 1;
     const bool time_trace = (rp->flags & SG_RENDER_TIME_KERNELS) != 0;
     const int n_depths = rp->max_depth + 1;
-    const size_t smc = s->smem_closest, sms = s->smem_shadow;
-    const TraceKernel kern_closest = trace_kernel(false, count, s->instanced), kern_shadow = trace_kernel(true, count, s->instanced);
+    // A/B switch: two rays per lane (triangle-only scenes, no visit counting); bit 0 = closest-hit launches, bit 1 = any-hit launches
+    const int dual_env = [] { const char* v = std::getenv("SG_TRACE_DUAL"); return v ? std::atoi(v) : 0; }();
+    const bool dual_ok = !count && !s->instanced && s->ts.stack_depth - std::min(s->ts.dual_levels_closest, s->ts.dual_levels_shadow) <= kSpillDual;
+    const bool dual_c = dual_ok && (dual_env & 1), dual_s = dual_ok && (dual_env & 2);
+    const size_t smc = dual_c ? s->smem_closest_dual : s->smem_closest, sms = dual_s ? s->smem_shadow_dual : s->smem_shadow;
+    const TraceKernel kern_closest = dual_c ? trace_kernel_dual(false) : trace_kernel(false, count, s->instanced);
+    const TraceKernel kern_shadow = dual_s ? trace_kernel_dual(true) : trace_kernel(true, count, s->instanced);
     const int grid_closest = persistent_grid(num_sms, (const void*)kern_closest, kTraceThreads, smc);
     const int grid_shadow = persistent_grid(num_sms, (const void*)kern_shadow, kTraceThreads, sms);
     const int shade_grid = num_sms * [] { const char* v = std::getenv("SG_SHADE_GRID"); return v && std::atoi(v) > 0 ? std::atoi(v) : 8; }();   // grid-stride shade kernels: CTAs of 128 threads per SM

@@ -29,7 +29,8 @@ def _render(sc, cfg, spp, env, max_paths_in_flight=0):
     return film, st
 
 
-KNOBS = [{"SG_SHADE_SYNC": "0"}, {"SG_SHADE_SYNC": "31"}, {"SG_SHADE_SYNC_TEX": "14"}, {"SG_OVERLAP": "1"},
+KNOBS = [{"SG_SHADE_SYNC": "0"}, {"SG_SHADE_SYNC": "31"}, {"SG_SHADE_SYNC_TEX": "14"}, {"SG_OVERLAP": "1"}, {"SG_TRACE_DUAL": "3"},
+         {"SG_TRACE_DUAL": "3", "SG_DUAL_LEVELS": "3", "SG_DUAL_LEVELS_SHADOW": "2", "SG_DUAL_REFILL": "5", "SG_DUAL_LEAF": "3"},
          {"SG_REFILL_THRESHOLD": "4", "SG_LEAF_THRESHOLD": "12", "SG_INTERIOR_BURST": "2"}]
 
 

@@ -451,4 +451,25 @@ SG_OVERLAP=1 timeout 900 ncu --set full --clock-control none --import-source on 
 ls -la gpurun_out/r02_trace_src.ncu-rep
 }
 
-if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 call37 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
+# two rays per lane (k_trace_dual): scheduling-invariance test, C2 / C5 A/B
+call38() {
+timeout 300 python -m pytest tests/test_gpu_scheduling.py -m gpu -x -q > gpurun_out/r02_c38_pytest.log 2>&1; tail -5 gpurun_out/r02_c38_pytest.log
+L=gpurun_out/r02_c38_perf.log; : > $L
+timeout 300 python tools/perf_ab.py --workload mesh1m --reps 2 base SG_TRACE_DUAL=1 SG_TRACE_DUAL=2 SG_TRACE_DUAL=3 SG_TRACE_DUAL=3,SG_DUAL_LEAF=8,SG_DUAL_REFILL=16 SG_TRACE_DUAL=3,SG_DUAL_LEAF=16,SG_DUAL_REFILL=32 SG_TRACE_DUAL=3,SG_DUAL_LEVELS=16 2>> gpurun_out/r02_c38.err | cut -c1-200 >> $L
+timeout 300 python tools/perf_ab.py --workload composite --spp 64 --reps 2 base SG_TRACE_DUAL=3 2>> gpurun_out/r02_c38.err | cut -c1-200 >> $L
+cat $L
+}
+
+# two rays per lane: stack levels / thresholds, instruction counts of the depth-1 closest-hit launch with and without
+call39() {
+L=gpurun_out/r02_c39_perf.log; : > $L
+timeout 300 python tools/perf_ab.py --workload mesh1m --reps 2 base SG_TRACE_DUAL=1,SG_DUAL_LEVELS=6 SG_TRACE_DUAL=1,SG_DUAL_LEVELS=8 SG_TRACE_DUAL=1,SG_DUAL_LEVELS=10 SG_TRACE_DUAL=1,SG_DUAL_LEVELS=8,SG_DUAL_LEAF=20,SG_DUAL_REFILL=40 SG_TRACE_DUAL=1,SG_DUAL_LEVELS=8,SG_INTERIOR_BURST=8 2>> gpurun_out/r02_c39.err | cut -c1-200 >> $L
+cat $L
+M=smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__occupancy_limit_shared_mem,launch__occupancy_limit_registers
+for D in 0 1; do
+SG_TRACE_DUAL=$D SG_OVERLAP=1 timeout 300 ncu --metrics $M --clock-control none -k regex:k_trace -s 2 -c 1 --csv --log-file gpurun_out/r02_c39_dual$D.csv python tools/render_once.py --workload mesh1m --spp 16 --warm 0 > /dev/null 2>&1
+grep -E "k_trace" gpurun_out/r02_c39_dual$D.csv | awk -F'","' '{print $5, $(NF-2), $NF}' | cut -c1-200
+done
+}
+
+if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 call37 call38 call39 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
