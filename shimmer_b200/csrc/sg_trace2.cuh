@@ -64,7 +64,7 @@ struct TraceScene {
     int interior_burst;
     int refill_threshold_d0;    // the same knobs for the CLOSEST-HIT launch of depth 0 (camera rays: a warp's rays are near-identical, so
     int interior_burst_d0;      //   waiting for most lanes before a refill keeps them in lockstep)
-    int prefetch;
+    int prefetch;               // unused (SG_TRACE_PREFETCH is a build-time switch)
     int refill_threshold_dual, leaf_threshold_dual;      // two-rays-per-lane kernels (k_trace_dual): thresholds count SLOTS (64 per warp)
     int dual_levels_closest, dual_levels_shadow;         //   shared-memory stack levels per ray
     const DInstance* instances; // object instancing (INST kernels only)
@@ -241,7 +241,10 @@ SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint3
     const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
     const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);       // near child by dir_is_neg[axis], aggregate.rs:119-127
     const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
-    if (ts.prefetch) {
+#ifndef SG_TRACE_PREFETCH
+#define SG_TRACE_PREFETCH 0     /* measured on C2: -4 % (r02_sweep2); a build-time switch so that the hot loop carries no test for it */
+#endif
+    if (SG_TRACE_PREFETCH) {
         // start pulling the near child's node (or triangle) towards L1 while the two slab tests run
         const float4* nxt = (near_ref & kLeafBit) ? ts.tri_verts + 3 * (size_t)(near_ref & ~kLeafBit) : ts.node64 + 4 * (size_t)near_ref;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));

@@ -213,13 +213,19 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     S.s_save = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x * (ANY ? 1 : 2)) + threadIdx.x;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     bool has_ray = false, dead = false, finished = false;
+    uint32_t m_dead = 0u;                                                        // lanes that found the queue exhausted (changes in the refill phase only)
     CursorT idx = 0;
     for (;;) {
         const bool is_leaf = has_ray && (L.cur & kLeafBit) != 0;
         const bool is_int = has_ray && !is_leaf;
         const uint32_t m_int = __ballot_sync(0xffffffffu, is_int);
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, is_leaf);
-        const uint32_t m_wait = __ballot_sync(0xffffffffu, finished || (!has_ray && !dead));
+        // lanes waiting for a ray: finished, or never had one.  Every lane is in exactly one state, so the triangle-only kernels
+        // derive the mask from the other three (one vote less per iteration); the instanced kernels sit at their register cap and
+        // spill with one more live value, they keep the vote
+        uint32_t m_wait;
+        if constexpr (INST) m_wait = __ballot_sync(0xffffffffu, finished || (!has_ray && !dead));
+        else m_wait = ~(m_int | m_leaf | m_dead);
         if ((m_int | m_leaf) == 0u || __popc(m_wait) >= refill_threshold) {
             // ---- retire finished rays, claim new ones (warp-aggregated) ----
             if constexpr (!INST) L.hit.inst = -1;
@@ -243,6 +249,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
                     } else dead = true;
                 }
             }
+            if constexpr (!INST) m_dead = __ballot_sync(0xffffffffu, dead);
             if (!__ballot_sync(0xffffffffu, has_ray || finished)) break;
             continue;
         }
@@ -259,9 +266,12 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
 #pragma unroll 1
             for (int k = 0; k < interior_burst; ++k) {
                 lane_step_interior<ANY, COUNT, INST>(ts, L, S, cnt_nodes, io, idx);
-                if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
-                if (L.cur & kLeafBit) break;
+                if constexpr (INST) {                                            // (register allocation of the instanced kernels prefers this form)
+                    if (L.cur == kEmptyRef) { finished = true; has_ray = false; break; }
+                    if (L.cur & kLeafBit) break;
+                } else if (L.cur >= kEmptyRef) break;                            // one test for "finished" (== kEmptyRef) and "at a leaf" (bit 31)
             }
+            if constexpr (!INST) if (L.cur == kEmptyRef) { finished = true; has_ray = false; }
         }
     }
 }

@@ -472,4 +472,14 @@ grep -E "k_trace" gpurun_out/r02_c39_dual$D.csv | awk -F'","' '{print $5, $(NF-2
 done
 }
 
-if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 call37 call38 call39 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
+# vote-loop trims of the triangle-only traversal kernels: parity + scheduling tests, C2 / C5 / C4
+call40() {
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scheduling.py -m gpu -x -q > gpurun_out/r02_c40_pytest.log 2>&1; tail -2 gpurun_out/r02_c40_pytest.log
+L=gpurun_out/r02_c40_perf.log; : > $L
+timeout 300 python tools/perf_ab.py --workload mesh1m --reps 3 base 2>> gpurun_out/r02_c40.err | cut -c1-200 >> $L
+timeout 300 python tools/perf_ab.py --workload composite --spp 64 --reps 2 base 2>> gpurun_out/r02_c40.err | cut -c1-200 >> $L
+timeout 300 python tools/perf_ab.py --workload instanced --spp 32 --reps 2 base 2>> gpurun_out/r02_c40.err | cut -c1-200 >> $L
+cat $L
+}
+
+if [ "$1" = "list" ] || [ -z "$1" ]; then echo call2 call3 call4 call5 call6 call7 call8 call9 call10 call11 call12 call13 call14 call15 call16 call17 call18 call19 call20 call21 call22 call23 call24 call25 call26 call27 call28 call29 call30 call31 call32 call33 call34 call35 call36 call37 call38 call39 call40 sweep1 sweep2 sweep3 sweep4 sweep5 sweep6 ab_mb; else "$@"; fi
