@@ -79,15 +79,26 @@ struct TraceScene {
 // shared part is what lets 8 CTAs (32 warps) share an SM on deep trees; the spill path is rarely taken.
 static constexpr int kSpillLevels = 48;
 struct Stack {
-    uint32_t* s_ref; float* s_t; int stride; int levels;
+    uint32_t a_ref, a_t;    // shared-window byte addresses of this thread's level-0 slots (refs / entry distances): 32-bit st.shared / ld.shared,
+                            //   where a generic pointer costs a window-base lookup and a 64-bit address per access
+    int stride; int levels;
+    SGD void bind(uint32_t* ref0, float* t0) { a_ref = (uint32_t)__cvta_generic_to_shared(ref0); a_t = (uint32_t)__cvta_generic_to_shared(t0); }
     uint2* spill;
     float* s_save;          // INST kernels: 10 words per thread (stride apart) holding the render-space ray while the lane is inside an instance
     template <bool ANY> SGD void put(int sp, uint32_t ref, float t) const {
-        if (sp < levels) { s_ref[sp * stride] = ref; if (!ANY) s_t[sp * stride] = t; }
+        if (sp < levels) {
+            const uint32_t off = (uint32_t)(sp * stride) * 4u;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_ref + off), "r"(ref));
+            if (!ANY) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_t + off), "f"(t));
+        }
         else spill[sp - levels] = make_uint2(ref, __float_as_uint(t));
     }
     template <bool ANY> SGD void get(int sp, uint32_t& ref, float& t) const {
-        if (sp < levels) { ref = s_ref[sp * stride]; if (!ANY) t = s_t[sp * stride]; }
+        if (sp < levels) {
+            const uint32_t off = (uint32_t)(sp * stride) * 4u;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a_ref + off));
+            if (!ANY) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a_t + off));
+        }
         else { const uint2 e = spill[sp - levels]; ref = e.x; t = __uint_as_float(e.y); }
     }
 };
@@ -239,7 +250,8 @@ SGD void lane_step_interior(const TraceScene& ts, Lane& L, const Stack& S, uint3
     const float4* nd = ts.node64 + 4 * (size_t)L.cur;
     const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
     const uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z) & 3u;
-    const int neg = axis == 0 ? L.nx : (axis == 1 ? L.ny : L.nz);       // near child by dir_is_neg[axis], aggregate.rs:119-127
+    // near child by dir_is_neg[axis], aggregate.rs:119-127 (a shift instead of a two-level select: the select compiled to a divergent branch)
+    const int neg = (int)((((uint32_t)L.nx | ((uint32_t)L.ny << 1) | ((uint32_t)L.nz << 2)) >> axis) & 1u);
     const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
 #ifndef SG_TRACE_PREFETCH
 #define SG_TRACE_PREFETCH 0     /* measured on C2: -4 % (r02_sweep2); a build-time switch so that the hot loop carries no test for it */

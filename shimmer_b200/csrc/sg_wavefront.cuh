@@ -207,8 +207,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     uint2 spill[kSpillLevels];
     Stack S;
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
-    S.s_ref = s_mem + threadIdx.x;
-    S.s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x;
+    S.bind(s_mem + threadIdx.x, reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x);
     // INST kernels: the parked render-space ray (lane_save_ray) sits behind the stack levels (closest-hit: refs + entry distances, any-hit: refs)
     S.s_save = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x * (ANY ? 1 : 2)) + threadIdx.x;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
@@ -284,8 +283,7 @@ SGD void trace_persistent_post(const TraceScene& ts, IO& io, CursorT n, CursorT*
     uint2 spill[kSpillLevels];
     Stack S;
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
-    S.s_ref = s_mem + threadIdx.x;
-    S.s_t = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x;
+    S.bind(s_mem + threadIdx.x, reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x);
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     uint32_t pend = kEmptyRef; float pend_t = 0.0f;
     bool has_ray = false, dead = false, finished = false;
@@ -423,7 +421,7 @@ SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_
     uint32_t* const base1 = s_mem + stack_words + threadIdx.x;
     float* const park = reinterpret_cast<float*>(s_mem + 2 * stack_words) + threadIdx.x;
     Stack S; S.stride = stride; S.levels = levels; S.s_save = nullptr;
-    S.s_ref = base0; S.s_t = reinterpret_cast<float*>(base0 + levels * stride); S.spill = spill0;
+    S.bind(base0, reinterpret_cast<float*>(base0 + levels * stride)); S.spill = spill0;
     int which = 0;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     L.o = f3(0.0f, 0.0f, 0.0f); L.inv_dir = f3(1.0f, 1.0f, 1.0f); L.rp.kx = 0; L.rp.ky = 1; L.rp.kz = 2; L.rp.sx = L.rp.sy = L.rp.sz = 0.0f;
@@ -454,7 +452,7 @@ SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_
         const int t = sa; sa = sb; sb = t;
         which ^= 1;
         uint32_t* const b = which ? base1 : base0;
-        S.s_ref = b; S.s_t = reinterpret_cast<float*>(b + levels * stride); S.spill = which ? spill1 : spill0;
+        S.bind(b, reinterpret_cast<float*>(b + levels * stride)); S.spill = which ? spill1 : spill0;
     };
     auto state_of = [&]() { return L.cur == kEmptyRef ? 3 : ((L.cur & kLeafBit) ? 2 : 1); };
     for (;;) {
