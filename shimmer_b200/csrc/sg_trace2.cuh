@@ -79,25 +79,25 @@ struct TraceScene {
 // shared part is what lets 8 CTAs (32 warps) share an SM on deep trees; the spill path is rarely taken.
 static constexpr int kSpillLevels = 48;
 struct Stack {
-    uint32_t a_ref, a_t;    // shared-window byte addresses of this thread's level-0 slots (refs / entry distances): 32-bit st.shared / ld.shared,
-                            //   where a generic pointer costs a window-base lookup and a 64-bit address per access
+    uint32_t a_ref;         // shared-window byte address of this thread's level-0 slot: 32-bit st.shared / ld.shared, where a generic
+                            //   pointer costs a window-base lookup and a 64-bit address per access.  Closest-hit stacks hold (ref, entry
+                            //   distance) PAIRS, 8 bytes per entry and level-major (one 64-bit access per push / pop); any-hit stacks hold refs.
     int stride; int levels;
-    SGD void bind(uint32_t* ref0, float* t0) { a_ref = (uint32_t)__cvta_generic_to_shared(ref0); a_t = (uint32_t)__cvta_generic_to_shared(t0); }
+    // `stacks`: start of this stack's region (8-byte aligned); the thread's level-0 slot is `tid` entries in
+    template <bool ANY> SGD void bind(uint32_t* stacks, int tid) { a_ref = (uint32_t)__cvta_generic_to_shared(stacks + tid * (ANY ? 1 : 2)); }
     uint2* spill;
     float* s_save;          // INST kernels: 10 words per thread (stride apart) holding the render-space ray while the lane is inside an instance
     template <bool ANY> SGD void put(int sp, uint32_t ref, float t) const {
         if (sp < levels) {
-            const uint32_t off = (uint32_t)(sp * stride) * 4u;
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_ref + off), "r"(ref));
-            if (!ANY) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_t + off), "f"(t));
+            if (ANY) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_ref + (uint32_t)(sp * stride) * 4u), "r"(ref));
+            else asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_ref + (uint32_t)(sp * stride) * 8u), "r"(ref), "r"(__float_as_uint(t)));
         }
         else spill[sp - levels] = make_uint2(ref, __float_as_uint(t));
     }
     template <bool ANY> SGD void get(int sp, uint32_t& ref, float& t) const {
         if (sp < levels) {
-            const uint32_t off = (uint32_t)(sp * stride) * 4u;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a_ref + off));
-            if (!ANY) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a_t + off));
+            if (ANY) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a_ref + (uint32_t)(sp * stride) * 4u));
+            else { uint32_t tb; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(a_ref + (uint32_t)(sp * stride) * 8u)); t = __uint_as_float(tb); }
         }
         else { const uint2 e = spill[sp - levels]; ref = e.x; t = __uint_as_float(e.y); }
     }

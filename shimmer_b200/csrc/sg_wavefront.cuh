@@ -207,7 +207,7 @@ SGD void trace_persistent(const TraceScene& ts, IO& io, CursorT n, CursorT* curs
     uint2 spill[kSpillLevels];
     Stack S;
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
-    S.bind(s_mem + threadIdx.x, reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x);
+    S.template bind<ANY>(s_mem, (int)threadIdx.x);
     // INST kernels: the parked render-space ray (lane_save_ray) sits behind the stack levels (closest-hit: refs + entry distances, any-hit: refs)
     S.s_save = reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x * (ANY ? 1 : 2)) + threadIdx.x;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
@@ -283,7 +283,7 @@ SGD void trace_persistent_post(const TraceScene& ts, IO& io, CursorT n, CursorT*
     uint2 spill[kSpillLevels];
     Stack S;
     S.stride = blockDim.x; S.levels = ts.smem_levels; S.spill = spill;
-    S.bind(s_mem + threadIdx.x, reinterpret_cast<float*>(s_mem + (size_t)ts.smem_levels * blockDim.x) + threadIdx.x);
+    S.template bind<ANY>(s_mem, (int)threadIdx.x);
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     uint32_t pend = kEmptyRef; float pend_t = 0.0f;
     bool has_ray = false, dead = false, finished = false;
@@ -417,11 +417,11 @@ SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_
     const int interior_burst = first_depth ? ts.interior_burst_d0 : ts.interior_burst;
     uint2 spill0[kSpillDual], spill1[kSpillDual];
     const int stack_words = levels * stride * (ANY ? 1 : 2);
-    uint32_t* const base0 = s_mem + threadIdx.x;
-    uint32_t* const base1 = s_mem + stack_words + threadIdx.x;
+    uint32_t* const base0 = s_mem;
+    uint32_t* const base1 = s_mem + stack_words;
     float* const park = reinterpret_cast<float*>(s_mem + 2 * stack_words) + threadIdx.x;
     Stack S; S.stride = stride; S.levels = levels; S.s_save = nullptr;
-    S.bind(base0, reinterpret_cast<float*>(base0 + levels * stride)); S.spill = spill0;
+    S.template bind<ANY>(base0, (int)threadIdx.x); S.spill = spill0;
     int which = 0;
     Lane L; L.cur = kEmptyRef; L.sp = 0; L.hit.prim = -1; L.hit.inst = -1; L.inst = -1; L.sp_base = 0; L.t_saved = 0.0f; L.inst_hit = false;
     L.o = f3(0.0f, 0.0f, 0.0f); L.inv_dir = f3(1.0f, 1.0f, 1.0f); L.rp.kx = 0; L.rp.ky = 1; L.rp.kz = 2; L.rp.sx = L.rp.sy = L.rp.sz = 0.0f;
@@ -452,7 +452,7 @@ SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_
         const int t = sa; sa = sb; sb = t;
         which ^= 1;
         uint32_t* const b = which ? base1 : base0;
-        S.bind(b, reinterpret_cast<float*>(b + levels * stride)); S.spill = which ? spill1 : spill0;
+        S.template bind<ANY>(b, (int)threadIdx.x); S.spill = which ? spill1 : spill0;
     };
     auto state_of = [&]() { return L.cur == kEmptyRef ? 3 : ((L.cur & kLeafBit) ? 2 : 1); };
     for (;;) {
@@ -518,7 +518,7 @@ SGD void trace_persistent_dual(const TraceScene& ts, IO& io, uint32_t n, uint32_
 template <bool ANY, bool COUNT, bool INST>
 __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST : SG_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                          PathState st, Queues q, int depth, DevStats* stats) {
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t* C = q.counters + depth * C_STRIDE;
     uint32_t cnt_nodes = 0, cnt_tris = 0;
     constexpr bool POST = SG_TRACE_POSTPONE && !COUNT && !INST;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
 template <bool ANY>
 __global__ void __launch_bounds__(kTraceThreads, SG_TRACE_MIN_BLOCKS_DUAL) k_trace_dual(const __grid_constant__ DScene sc, const __grid_constant__ TraceScene ts,
                                                          PathState st, Queues q, int depth, DevStats* stats) {
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t* C = q.counters + depth * C_STRIDE;
     if (ANY) {
         ShadowIO io{st, q.shadow, 0};
@@ -1445,7 +1445,7 @@ __global__ void __launch_bounds__(kTraceThreads, INST ? SG_TRACE_MIN_BLOCKS_INST
                                                               long long n, const float* __restrict__ o, const float* __restrict__ d,
                                                               const float* __restrict__ tmax, SgHit* __restrict__ out,
                                                               unsigned long long* cursor, DevStats* stats) {
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t cnt_nodes = 0, cnt_tris = 0;
     RaysIO<ANY> io{sc, o, d, tmax, out};
     if constexpr (SG_TRACE_POSTPONE && !COUNT && !INST) trace_persistent_post<ANY>(ts, io, (unsigned long long)n, cursor, s_mem);
