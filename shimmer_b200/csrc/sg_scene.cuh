@@ -82,9 +82,15 @@ SGD RayPre ray_precompute(float3 d) {
 SGD float3 permute3(float3 v, int kx, int ky, int kz) { return f3(comp3(v, kx), comp3(v, ky), comp3(v, kz)); }
 
 // Triangle::intersect_triangle, triangle.rs:173-302.  Returns true on an accepted hit.
+// The degenerate-triangle test of triangle.rs:181 depends on the triangle only: the traversal kernels read it from a flag that
+// k_mark_degenerate (below) sets once per scene with this very expression (kDegenerateBit in tri_verts[3*i].w) and call
+// intersect_triangle<false>; every other caller evaluates it in place.
+static constexpr uint32_t kDegenerateBit = 0x80000000u;
+SGD bool triangle_is_degenerate(float3 p0, float3 p1, float3 p2) { return len2(cross3(p2 - p0, p1 - p0)) == 0.0f; }
+template <bool CHECK_DEGENERATE = true>
 SGD bool intersect_triangle(float3 o, const RayPre& rp, float t_max, float3 p0, float3 p1, float3 p2,
                             float& b0, float& b1, float& b2, float& t) {
-    if (len2(cross3(p2 - p0, p1 - p0)) == 0.0f) return false;                   // degenerate :181
+    if (CHECK_DEGENERATE && triangle_is_degenerate(p0, p1, p2)) return false;   // degenerate :181
     float3 p0t = permute3(p0 - o, rp.kx, rp.ky, rp.kz);
     float3 p1t = permute3(p1 - o, rp.kx, rp.ky, rp.kz);
     float3 p2t = permute3(p2 - o, rp.kx, rp.ky, rp.kz);

@@ -323,7 +323,7 @@ SGD void lane_step_leaf(const TraceScene& ts, Lane& L, const Stack& S, uint32_t&
             b2 = 0.0f;
         } else {
             if constexpr (INST) if (L.rp.kz < 0) L.rp = ray_precompute(f3(L.rp.sx, L.rp.sy, L.rp.sz));    // deferred by lane_enter_instance
-            hit_prim = intersect_triangle(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
+            hit_prim = !(__float_as_uint(v0.w) & kDegenerateBit) && intersect_triangle<false>(L.o, L.rp, L.t_max, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), b0, b1, b2, t);
         }
         if (hit_prim) {
             L.hit.prim = (int)pi; L.hit.t = t; L.hit.b0 = b0; L.hit.b1 = b1; L.hit.b2 = b2;

@@ -1393,6 +1393,19 @@ static __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DSc
     }
 }
 
+// Scene upload: evaluate the degenerate-triangle test of triangle.rs:181 once per triangle record (the same device expression the
+// traversal used to evaluate per test) and keep the answer in bit 31 of the record's first .w word.
+static __global__ void k_mark_degenerate(float4* tri_verts, uint32_t n_prims) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_prims) return;
+    float4* tv = tri_verts + 3 * (size_t)i;
+    const float4 v0 = tv[0], v1 = tv[1], v2 = tv[2];
+    if (((__float_as_uint(v0.w) >> 28) & 7u) == kKindInstance) return;                  // TransformedPrimitive record
+    if (__float_as_uint(v2.w) & (kSphereBit | kPatchBit)) return;                         // sphere / bilinear-patch record
+    if (triangle_is_degenerate(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z)))
+        tv[0].w = __uint_as_float(__float_as_uint(v0.w) | kDegenerateBit);
+}
+
 static __global__ void k_accum_stats(const uint32_t* counters, int n_depths, DevStats* stats) {
     unsigned long long c = 0, s = 0;
     for (int d = 0; d < n_depths; ++d) { c += counters[d * C_STRIDE + C_NRAY]; s += counters[d * C_STRIDE + C_NSHADOW]; }

@@ -702,6 +702,11 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
     if ((rc = upload((const float4*)desc->nodes, (size_t)desc->n_nodes * 2, &d_nodes, s->owned)) != SG_OK) return bail(rc);
     if ((rc = upload(tv.data(), tv.size(), &d_tv, s->owned)) != SG_OK) return bail(rc);
     d.nodes = d_nodes; d.tri_verts = d_tv; s->ts.tri_verts = d_tv;
+    if (!tv.empty()) {                                      // degenerate-triangle flags (sg_scene.cuh kDegenerateBit)
+        const uint32_t n_rec = (uint32_t)(tv.size() / 3);
+        k_mark_degenerate<<<(n_rec + 255) / 256, 256, 0, g_dev[s->dev].stream>>>(d_tv, n_rec);
+        CU(cudaStreamSynchronize(g_dev[s->dev].stream));
+    }
 #define UP(field, src, n, T) { T* p__ = nullptr; if ((rc = upload((const T*)(src), (size_t)(n), &p__, s->owned)) != SG_OK) return bail(rc); d.field = p__; }
     UP(prims, desc->primitives, desc->n_primitives, SgPrimitive);
     UP(meshes, desc->meshes, desc->n_meshes, SgMesh);

@@ -583,3 +583,42 @@ def test_force_diffuse_films(kind):
     integ.film[:] = 0
     assert not np.array_equal(plain, film)
     integ.close()
+
+
+def test_degenerate_triangles_are_skipped_like_the_reference():
+    """triangle.rs:181: a triangle whose cross product has zero length never reports a hit.  The traversal kernels read that
+    answer from a per-triangle flag set at scene upload (kDegenerateBit) instead of evaluating it per test: a mesh with repeated
+    and collinear vertices in front of a regular one must trace exactly like the oracle, visit counts included."""
+    from shimmer_b200.host import SceneBuilder
+    b = SceneBuilder()
+    b.set_camera(pos=(0.0, 1.0, -3.0), look=(0.0, 0.5, 0.0), up=(0, 1, 0), fov=45.0, resolution=(16, 16))
+    white = b.diffuse(("const", 0.6))
+    gp = np.array([[-2, 0, -2], [-2, 0, 2], [2, 0, 2], [2, 0, -2]], np.float32)
+    b.add_mesh(gp, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), white)
+    rng = np.random.default_rng(5)
+    n = 40
+    P = (rng.random((3 * n, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(1.5) + np.array([0, 0.9, 0], np.float32)
+    I = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    I[0::4, 2] = I[0::4, 1]                                               # repeated vertex
+    P[3 * 1 + 2::12] = (P[3 * 1::12] + P[3 * 1 + 1::12]) * np.float32(0.5)  # exactly representable midpoints: collinear
+    I[2::4] = I[2::4][:, [0, 0, 0]]                                       # a point
+    b.add_mesh(P, I, b.diffuse(("const", 0.3)))
+    lp = np.array([[-0.5, 2.5, -0.5], [0.5, 2.5, -0.5], [0.5, 2.5, 0.5], [-0.5, 2.5, 0.5]], np.float32)
+    b.add_mesh(lp, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), white, area_light=dict(L=("const", 1.0), scale=20.0, two_sided=False))
+    sc = b.build()
+    integ = create_integrator("wavefront", {}, sc, {"pixelsamples": 16})
+    m = 1 << 15
+    o, d = _ray_set(sc, m, seed=2)
+    tmax = np.full(m, np.inf, np.float32)
+    got, gst = integ.trace(o, d, tmax, want_stats=True)
+    ref, rst = orc.trace(sc, o, d, tmax)
+    assert _assert_hits_equal(got, ref) == 4
+    assert gst.nodes_visited == rst.nodes_visited and gst.tris_tested == rst.tris_tested
+    got2 = integ.trace(o, (d * np.float32(3.0)).astype(np.float32), np.full(m, np.float32(0.9999), np.float32), any_hit=True)
+    ref2, _ = orc.trace(sc, o, (d * np.float32(3.0)).astype(np.float32), np.full(m, np.float32(0.9999), np.float32), any_hit=True)
+    assert np.array_equal(got2["prim"], ref2["prim"])
+    film = integ.render(Options(seed=0, pixel_samples=16)).copy()          # the wavefront's own traversal kernels (k_trace)
+    rfilm, rs, _ = orc.render(sc, orc.make_params(seed=0, spp=16))
+    _film_close(film, rfilm)
+    assert integ.stats.closest_hit_rays == rs.closest_hit_rays and integ.stats.shadow_rays == rs.shadow_rays
+    integ.close()
