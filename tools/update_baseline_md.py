@@ -46,7 +46,7 @@ if 8 in b and 1 in b:
     m8 = b[8]["multi_gpu"]
     out.append("The film is 265 MB (3840 x 2160 x 4 f64); its reduce over NVLink takes %.1f ms (%.1f ms as seen by rank 0, which also waits for the slowest rank) and the D2H "
                "%.1f ms against %.0f ms of rendering at N = 8: the scaling loss (%.1f %% at N = 8) is the slowest rank's wavefront loop (%.0f ms against %.0f ms for an "
-               "ideal eighth of the one-GPU step: pipeline fill and drain of 16 batches per rank instead of 128), not the collective.  Builder-run, `--steps 5 --warmup 3`.\n" % (
+               "ideal eighth of the one-GPU step: pipeline fill and drain of 16 batches per rank instead of 128), not the collective.  Builder-run, `--steps 3..5 --warmup 3`.\n" % (
         m8["reduce_ms_fastest_rank"], m8["reduce_ms_root"], b[8]["e2e"].get("d2h_ms_root", float("nan")), b[8]["ms_per_step"],
         100 * (1 - b[8]["value"] / (8 * b[1]["value"])), m8["render_ms_slowest_rank"], b[1]["ms_per_step"] / 8))
 if 1 in b:
