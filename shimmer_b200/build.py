@@ -63,7 +63,7 @@ def build_gpu(force=False, verbose=False, variant=None, defs=()):
 
 def build_host(force=False):
     out = os.path.join(HERE, "libshimmer_host.so")
-    srcs = [os.path.join(CSRC, "host_bvh.cpp"), os.path.join(HERE, "..", "include", "shimmer_gpu.h")]
+    srcs = [os.path.join(CSRC, "host_bvh.cpp"), os.path.join(CSRC, "sg_host_tables.h"), os.path.join(HERE, "..", "include", "shimmer_gpu.h")]
     if not force and not _stale(out, srcs):
         return out
     cxx = shutil.which("g++") or "g++"

@@ -13,6 +13,7 @@
 //   * depth-first linear layout, first child at index+1 (:425-467)
 // The work list is explicit (no recursion) and nodes are emitted in pre-order directly.
 #include "../../include/shimmer_gpu.h"
+#include "sg_host_tables.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -109,6 +110,13 @@ void sh_triangle_bounds(int64_t n_tris, const uint32_t* indices, const float* p,
             out_bounds[6 * t + 3 + k] = std::fmax(std::fmax(a[k], b[k]), c[k]);
         }
     }
+}
+
+// Interval table of one piecewise-linear spectrum (sg_host_tables.h): out holds kSpecLutBins = 471 entries.  Returns 1 when the
+// table was built, 0 when the device keeps the binary search (n < 2, n > 65535, unsorted knots).
+int sh_spectrum_lut(const float* lambdas, int32_t n, uint16_t* out) {
+    if (!lambdas || !out) return 0;
+    return sg::build_spectrum_lut(lambdas, n, out) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 // (paths relative to /root/reference/src) whose arithmetic it reproduces.
 #pragma once
 #include "sg_sphere.cuh"
+#include "sg_host_tables.h"     // kSpecLutMin / kSpecLutMax (LAMBDA_MIN / LAMBDA_MAX, spectrum.rs)
 #include "sg_scene.cuh"
 
 namespace sg {
@@ -55,7 +56,6 @@ SGD float blackbody(float lambda, float temperature) {           // spectrum.rs:
     float l2 = l * l; float l5 = l2 * l2 * l;
     return (2.0f * h * c * c) / (l5 * (expf((h * c) / (l * kb * temperature)) - 1.0f));
 }
-static constexpr int kSpecLutMin = 360, kSpecLutMax = 830;         // LAMBDA_MIN / LAMBDA_MAX, spectrum.rs
 SGD int find_interval_le(const float* L, int size, float lambda) {   // math.rs:322-333 with pred = L[i] <= lambda
     int first = 1, last = size - 2;
     while (last > 0) {

@@ -724,16 +724,10 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
             if (sp.kind != SG_SPECTRUM_PIECEWISE_LINEAR || sp.n < 2 || sp.n > 65535) continue;
             if ((uint64_t)sp.off_a + (uint64_t)sp.n > desc->n_pool || (uint64_t)sp.off_b + (uint64_t)sp.n > desc->n_pool)
                 return bail(fail(SG_ERR_INVALID_ARGUMENT, "spectrum " + std::to_string(i) + ": samples outside spectrum_pool"));
-            const float* L = desc->spectrum_pool + sp.off_a;
-            bool sorted = true;
-            for (int k = 1; k < sp.n; ++k) if (!(L[k - 1] <= L[k])) sorted = false;
-            if (!sorted) continue;                          // the binary search's answer is not "the last knot <= lambda" then: keep it
-            sp.pad = (uint32_t)lut.size() + 1u;
-            int o = 0;                                      // largest o in [0, n-2] with o == 0 or L[o] <= w; monotone in w
-            for (int w = kSpecLutMin; w <= kSpecLutMax; ++w) {
-                while (o + 1 <= sp.n - 2 && L[o + 1] <= (float)w) ++o;
-                lut.push_back((uint16_t)o);
-            }
+            const size_t at = lut.size();
+            lut.resize(at + kSpecLutBins);
+            if (build_spectrum_lut(desc->spectrum_pool + sp.off_a, sp.n, lut.data() + at)) sp.pad = (uint32_t)at + 1u;
+            else lut.resize(at);                            // unsorted knots: keep the binary search
         }
         SgSpectrum* p_sp = nullptr; uint16_t* p_lut = nullptr;
         if ((rc = upload(spectra_dev.data(), spectra_dev.size(), &p_sp, s->owned)) != SG_OK) return bail(rc);

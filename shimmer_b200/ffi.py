@@ -280,6 +280,7 @@ def load_host_library():
     h = C.CDLL(HOST_LIB_PATH)
     h.sh_bvh_build.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]; h.sh_bvh_build.restype = C.c_int64
     h.sh_triangle_bounds.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]; h.sh_triangle_bounds.restype = None
+    h.sh_spectrum_lut.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]; h.sh_spectrum_lut.restype = C.c_int
     _host = h
     return h
 

@@ -128,3 +128,47 @@ def test_orthographic_camera_rays_closed_form():
     assert np.allclose(rays[:, 0], want_x, atol=1e-5) and np.allclose(rays[:, 1], want_y, atol=1e-5) and np.allclose(rays[:, 2], 0.0, atol=1e-6)
     film, st, _ = orc.render(sc, orc.make_params(seed=1, spp=16))
     assert np.isfinite(film).all() and film[:, :3].sum() > 0
+
+
+def _find_interval(L, lam):
+    """math.rs:322-333 with pred = L[i] <= lam (what PiecewiseLinearSpectrum::get runs, spectrum.rs:318-337)."""
+    size = len(L)
+    first, last = 1, size - 2
+    while last > 0:
+        half = last >> 1; middle = first + half
+        if L[middle] <= lam:
+            first = middle + 1; last -= half + 1
+        else:
+            last = half
+    return min(max(first - 1, 0), size - 2)
+
+
+def test_spectrum_interval_table_reproduces_find_interval():
+    """sg_scene_create tabulates find_interval at every integer wavelength 360..830 for piecewise-linear spectra and the device walks
+    forward from the entry of floor(lambda) (csrc/sg_host_tables.h, sg_shading.cuh spectrum_get): the walk must end on the interval
+    the reference's binary search returns -- for knots on and off the integers, several knots inside one bin, duplicates, knots
+    outside the visible range, and the named metal spectra the synthetic scenes use."""
+    import ctypes as C
+    from shimmer_b200 import ffi
+    h = ffi.load_host_library()
+    rng = np.random.default_rng(3)
+    cases = [np.arange(360, 831, 20, dtype=np.float32), np.arange(360, 831, 10, dtype=np.float32),
+             np.sort(rng.uniform(300, 900, 57)).astype(np.float32),
+             np.sort(np.concatenate([rng.uniform(500, 503, 40), [360, 830]])).astype(np.float32),      # many knots in a few bins
+             np.array([360, 400, 400, 400, 500.5, 500.5, 830], np.float32),                              # duplicates
+             np.array([400, 700], np.float32), np.array([100, 200, 300], np.float32), np.array([900, 1000, 1100], np.float32)]
+    lam = np.concatenate([np.arange(360, 831, dtype=np.float32), rng.uniform(360, 830, 4000).astype(np.float32),
+                          np.nextafter(np.arange(361, 831, dtype=np.float32), np.float32(0))])          # just below every integer
+    for L in cases:
+        out = np.zeros(471, np.uint16)
+        assert h.sh_spectrum_lut(L.ctypes.data, len(L), out.ctypes.data) == 1
+        n = len(L)
+        for x in lam:
+            o = int(out[int(x) - 360])
+            while o < n - 2 and L[o + 1] <= x:
+                o += 1
+            assert o == _find_interval(L, x), (L[:6], x)
+    unsorted = np.array([500, 400, 600], np.float32)
+    assert h.sh_spectrum_lut(unsorted.ctypes.data, 3, np.zeros(471, np.uint16).ctypes.data) == 0      # keeps the binary search
+    one = np.array([500], np.float32)
+    assert h.sh_spectrum_lut(one.ctypes.data, 1, np.zeros(471, np.uint16).ctypes.data) == 0
