@@ -705,7 +705,9 @@ static int scene_create_on(const SgSceneDesc* desc, int dev_index, SgScene** out
     if (!tv.empty()) {                                      // degenerate-triangle flags (sg_scene.cuh kDegenerateBit)
         const uint32_t n_rec = (uint32_t)(tv.size() / 3);
         k_mark_degenerate<<<(n_rec + 255) / 256, 256, 0, g_dev[s->dev].stream>>>(d_tv, n_rec);
-        CU(cudaStreamSynchronize(g_dev[s->dev].stream));
+        cudaError_t e = cudaStreamSynchronize(g_dev[s->dev].stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return bail(fail(SG_ERR_CUDA, std::string("k_mark_degenerate: ") + cudaGetErrorString(e)));
     }
 #define UP(field, src, n, T) { T* p__ = nullptr; if ((rc = upload((const T*)(src), (size_t)(n), &p__, s->owned)) != SG_OK) return bail(rc); d.field = p__; }
     UP(prims, desc->primitives, desc->n_primitives, SgPrimitive);
